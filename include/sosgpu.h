@@ -1,0 +1,194 @@
+/*
+ * sosgpu.h -- C ABI of libsosgpu.so: the B200-native (sm_100a) replacement for the inner loops of
+ * SOS-ABS V5.1's successive-orders hot path.
+ *
+ * Plain C types only (pointers + sizes); every entry point cites the reference interface it replaces.
+ * All array arguments are HOST buffers owned by the caller; the library owns device memory, streams
+ * and kernels.  There is NO CPU fallback: every compute entry returns SOSGPU_ERR_NO_DEVICE when no
+ * CUDA device is usable.
+ *
+ * Array conventions (useful extents, not the compile-time caps of inc/SOS.h):
+ *   angle vectors  V(-N:N)       -> double v[2N+1], element j at v[j+N]
+ *   fields         X(0:NT,-N:N)  -> double x[(2N+1)*(NT+1)], (i,k) at x[(k+N)*(NT+1)+i]   (level fastest)
+ *   kernels        P(-N:N,-N:N)  -> double p[(2N+1)^2], (j,k) at p[(k+N)*(2N+1)+(j+N)]
+ *   surface record               -> float  r[9*N*N], matrix m (R11,R12,R13,R21,..R33), (I,J) at r[m*N*N+(J-1)*N+(I-1)]
+ *   Fourier record               -> double rec[3*(2N+1)] in file order Q(-N:N), U(-N:N), I(-N:N)  (SOS_OS.F:1572-1574)
+ * The gfortran-ABI shims at the end use the reference's fixed strides instead.
+ */
+#ifndef SOSGPU_H
+#define SOSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOSGPU_OK              0
+#define SOSGPU_ERR_NO_DEVICE  -2   /* no usable CUDA device: the product path refuses to run */
+#define SOSGPU_ERR_CUDA       -3
+#define SOSGPU_ERR_ARG        -4
+#define SOSGPU_ERR_IER        -1   /* the reference's IER=-1 */
+
+/* compile-time caps mirrored from inc/SOS.h:471,480,202 */
+#define SOSGPU_NBMU_MAX 80
+#define SOSGPU_NB_MAX   200
+#define SOSGPU_NT_MAX   600
+
+/* stop reasons of the scattering loop (SOS_OS.F:1146-1417) */
+#define SOSGPU_STOP_IGMAX_PRE 0
+#define SOSGPU_STOP_GEOM      1
+#define SOSGPU_STOP_LOWVAL    2
+#define SOSGPU_STOP_RATIO     3
+#define SOSGPU_STOP_IGMAX     4
+
+typedef struct sosgpu_ctx sosgpu_ctx;
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int  sosgpu_create(sosgpu_ctx **ctx, int device);
+void sosgpu_destroy(sosgpu_ctx *ctx);
+const char *sosgpu_last_error(const sosgpu_ctx *ctx);
+int  sosgpu_device_count(void);
+/* number of kernels this library has launched since create (bench.py's gpu_launches) */
+long long sosgpu_launch_count(const sosgpu_ctx *ctx);
+/* wave sizing knobs: device memory budget for field buffers (bytes, 0 = default) and the
+ * maximum number of Fourier orders solved concurrently per term (0 = automatic) */
+int  sosgpu_set_options(sosgpu_ctx *ctx, size_t field_budget_bytes, int max_wave_orders);
+
+/* ---- what SOS_PREPA_OS hands to SOS for one wavelength (SOS_PREPA_OS.F:328-335, SOS.F:340-345) */
+typedef struct {
+  int nbmu;                 /* LUM_NBMU                                                      */
+  const double *rmu;        /* [2N+1] cosines, rmu[-j] = -rmu[j]; index 0 is ignored on input */
+  const double *ga;         /* [2N+1] weights                                                */
+  int n0;                   /* index of the solar angle (>0) or <=0 to use tetas             */
+  double tetas;             /* solar zenith angle, degrees                                   */
+  int os_nb;                /* OS_NB                                                         */
+  const double *alpha, *beta, *gamma, *zeta;   /* [os_nb+1]                                  */
+  double a_trunc, piz, piztr;                  /* truncation coefficient, albedos (SOS.F:523-543) */
+  double ron;               /* molecular depolarisation factor                               */
+  double rho;               /* Lambertian albedo RO                                          */
+  int imat_surf, ifresnel;  /* SOS_OS.F:599-612                                              */
+  double ind_surf;
+  const float *surf;        /* [n_surf_rec][9][N][N] REAL*4 records of the surface file, or NULL */
+  int n_surf_rec;
+  int igmax, ipolar;
+  double zout;              /* -1 = TOA up / BOA down, else altitude (km)                    */
+} sosgpu_optics;
+
+/* ---- one (wavelength, CKD term): the PROFIL_TMP content (SOS.F:511-516) + CKD weight ---------- */
+typedef struct {
+  int optics;               /* index into the optics array                                   */
+  int group;                /* aggregation group (wavelength); terms of a group are CKD-summed */
+  double aik;               /* CKD weight (SOS_PROC.F:3481-3487)                             */
+  int nt;
+  const double *zprof, *h, *pcaer, *pcmol;     /* [nt+1] as read from the profile file       */
+} sosgpu_term;
+
+/* per-term outputs; arrays sized by the caller with rec_stride = max(os_nb)+1 records */
+typedef struct {
+  double *rec;              /* [nterm][rec_stride][3][Wmax] zero padded, Wmax = 2*max(nbmu)+1 (may be NULL) */
+  int *n_fourier;           /* [nterm]                                                       */
+  int *n_scatter;           /* [nterm][rec_stride]                                           */
+  int *stop_reason;         /* [nterm][rec_stride]                                           */
+  double *emoins, *eplus;   /* [nterm]                                                       */
+  double *ttot_tronc, *ttot_vrai, *tauout;     /* [nterm] (SOS.F:518,567-586)                */
+  int *ier;                 /* [nterm]                                                       */
+} sosgpu_term_out;
+
+/* per-group outputs = what the SOS_AGGREGATE chain leaves behind (SOS_AGGREGATE.F:172-543) */
+typedef struct {
+  double *rec;              /* [ngroup][rec_stride][3][Wmax] CKD-weighted Fourier coefficients */
+  int *n_rec;               /* [ngroup] longest series of the group                          */
+  double *emoins, *eplus, *ttot_tronc, *ttot_vrai, *tauout;  /* [ngroup]                     */
+} sosgpu_group_out;
+
+/*
+ * The batched hot path.  Replaces, for every term, SOS (SOS.F:340) -> SOS_OS (SOS_OS.F:303) and the
+ * SOS_AGGREGATE accumulation of SOS_PROC.F:3459-3594, without the file hops.
+ * term_out / group_out members may individually be NULL.  rec_stride/wmax describe the caller's layout.
+ * When part_only != 0 the group sums are left as partial sums for a multi-GPU reduce
+ * (group scalars then hold sum(a*exp(-tau)) instead of -log(...); see sosgpu_group_finalize).
+ */
+int sosgpu_solve_batch(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics,
+                       const sosgpu_term *terms, int nterm, int ngroup,
+                       int rec_stride, int wmax, int part_only,
+                       sosgpu_term_out *term_out, sosgpu_group_out *group_out);
+
+/* turns reduced partial sums (sum a*exp(-tau)) into the reference's -log form (SOS_AGGREGATE.F:467-488) */
+int sosgpu_group_finalize(double *ttot_tronc, double *ttot_vrai, double *tauout, int ngroup);
+
+/*
+ * Same as sosgpu_solve_batch but keeps inputs resident on the device between calls:
+ * upload once, run many (bench.py's HBM-resident timing).  run returns outputs into host buffers
+ * only when the out pointers are non-NULL.
+ */
+typedef struct sosgpu_batch sosgpu_batch;
+int  sosgpu_batch_upload(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics,
+                         const sosgpu_term *terms, int nterm, int ngroup, sosgpu_batch **batch);
+/* SOS_OS-level upload: h/pcaer/pcmol are H, XDEL, YDEL exactly as SOS_OS receives them (no truncation
+ * adaptation), iborm[nterm] is SOS_OS's IBORM argument (SOS_OS.F:303-308) */
+int  sosgpu_batch_upload_os(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics,
+                            const sosgpu_term *terms, int nterm, int ngroup, const int *iborm,
+                            sosgpu_batch **batch);
+int  sosgpu_batch_run(sosgpu_ctx *ctx, sosgpu_batch *batch, int rec_stride, int wmax, int part_only,
+                      sosgpu_term_out *term_out, sosgpu_group_out *group_out);
+void sosgpu_batch_free(sosgpu_ctx *ctx, sosgpu_batch *batch);
+/* device pointer + element count of the resident group sums (for an in-place NCCL reduce) */
+int  sosgpu_batch_group_buffer(sosgpu_batch *batch, void **dev_ptr, size_t *n_doubles);
+/* statistics of the last run: total (term, s, n>=2) contraction steps, their algorithmic FLOPs
+ * (2*(6N)^2*(NT+1) each) and recurrence bytes (96*N*(NT+1) each), device ms of the
+ * fused step kernel (CUDA events on the launching stream) and its launch count */
+typedef struct {
+  long long steps; double flops; double bytes; double step_ms; long long step_launches;
+  double total_ms; long long launches;
+} sosgpu_stats;
+int  sosgpu_batch_stats(const sosgpu_batch *batch, sosgpu_stats *st);
+
+/* ---- single-routine operators (parity tests read like the reference's own subroutines) -------- */
+/* SOS_NOYAUX (SOS_OS.F:1857-2158): six kernels [W*W] + l=2 rows [W]; rmu[N] must hold mu_s */
+int sosgpu_noyaux(sosgpu_ctx *ctx, int is, int nbmu, const double *rmu, int os_nb,
+                  const double *alpha, const double *beta, const double *gamma, const double *zeta,
+                  double *xpl, double *xrl, double *xtl,
+                  double *bp, double *gr, double *gt, double *arr, double *art, double *att);
+/* SOS_FSOURCE_ORDREIG (SOS_OS.F:2663-3017) followed by SOS_INTEGR_EPOPT (SOS_OS.F:2222-2357):
+ * one fused order step X_{n-1} -> X_n for a single problem over a black surface (zero ground boundary
+ * values; bc_reserved must be NULL).  Also returns the source function J (i2,q2,u2) when non-NULL
+ * (computed by the same DMMA tiles, staged out for the test). */
+int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double *rmu, const double *ga, int os_nb,
+                      const double *alpha, const double *beta, const double *gamma, const double *zeta,
+                      double ron, int ipolar, int nt, const double *h, const double *xdel, const double *ydel,
+                      const double *i1, const double *q1, const double *u1, const double *bc_reserved,
+                      double *i1n, double *q1n, double *u1n, double *i2, double *q2, double *u2);
+
+/* SOS_TRPHI_OPTION / SOS_TRPHI (SOS_TRPHI.F:285-636, 749-1243): Fourier synthesis on the view
+ * azimuths + glitter / flat-sea direct terms.  rec: [nrec][3][2N+1].  Tables [7][nphi_cap][N] in the
+ * order SCA, I, Q, U, POL_ANG, POL_RATE, L_POL; returns the number of azimuth slots or <0. */
+int sosgpu_trphi_option(sosgpu_ctx *ctx, const double *rec, int nrec, int nbmu, const double *rmu,
+                        double tau, double tauout, int igli, int n0, double wind, double ind_surf,
+                        int ifresnel, int itrphi, double phios, int pas_phi, int ipolar,
+                        double *phi_fin, double *theta_fin, double *up, double *down, int nphi_cap);
+
+/* ---- gfortran-ABI drop-in symbols (F77 by-reference, fixed SOS.h strides, hidden string lengths) */
+/* SOS_OS.F:303-308 */
+void sos_os_(const int *nbmu, double *rmu, const double *ga, const int *os_nb, const int *nt,
+             const char *ficsurf, const char *ficos,
+             const int *n0, const double *tetas, const double *ro, const int *imat_surf,
+             const int *ifresnel, const double *ind_surf,
+             const double *h, const double *xdel, const double *ydel, const double *zprof, const double *ron,
+             double *alpha, double *beta, double *gamma, double *zeta, const double *zout,
+             const int *igmax, const int *iborm, const int *ipolar, const int *trace, const int *idlog,
+             double *emoins, double *eplus, int *ier, size_t len_ficsurf, size_t len_ficos);
+/* SOS_AGGREGATE.F:172-178 */
+void sos_aggregate_(const int *nbmu, const double *aik, const char *ficos_tmp,
+                    const double *ttot_tronc_tmp, const double *ttot_vrai_tmp, const double *tauout_tmp,
+                    const double *tdifmus_tmp, const double *tdifmug_tmp, const double *emoins_tmp,
+                    const double *eplus_tmp, const char *ficos_agg_tmp, const char *ficos,
+                    double *ttot_tronc, double *ttot_vrai, double *tauout, double *tdifmus, double *tdifmug,
+                    double *emoins, double *eplus, int *ier,
+                    size_t len_ficos_tmp, size_t len_ficos_agg_tmp, size_t len_ficos);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,316 @@
+"""Host-side mirror of the reference interface for the hot path, over the C ABI of libsosgpu.so.
+
+The names follow the reference's subroutines (SOS, SOS_OS, SOS_NOYAUX, SOS_AGGREGATE, SOS_TRPHI_OPTION);
+argument meaning and error behaviour (IER = 0 / -1) are the reference's.  There is no CPU fallback: if the
+CUDA library cannot be loaded or no CUDA device is present, `Solver()` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsosgpu.so")
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_fp = C.POINTER(C.c_float)
+
+SOSGPU_OK = 0
+SOSGPU_ERR_NO_DEVICE = -2
+
+
+class COptics(C.Structure):
+    _fields_ = [("nbmu", C.c_int), ("rmu", c_dp), ("ga", c_dp), ("n0", C.c_int), ("tetas", C.c_double),
+                ("os_nb", C.c_int), ("alpha", c_dp), ("beta", c_dp), ("gamma", c_dp), ("zeta", c_dp),
+                ("a_trunc", C.c_double), ("piz", C.c_double), ("piztr", C.c_double), ("ron", C.c_double),
+                ("rho", C.c_double), ("imat_surf", C.c_int), ("ifresnel", C.c_int), ("ind_surf", C.c_double),
+                ("surf", c_fp), ("n_surf_rec", C.c_int), ("igmax", C.c_int), ("ipolar", C.c_int),
+                ("zout", C.c_double)]
+
+
+class CTerm(C.Structure):
+    _fields_ = [("optics", C.c_int), ("group", C.c_int), ("aik", C.c_double), ("nt", C.c_int),
+                ("zprof", c_dp), ("h", c_dp), ("pcaer", c_dp), ("pcmol", c_dp)]
+
+
+class CTermOut(C.Structure):
+    _fields_ = [("rec", c_dp), ("n_fourier", c_ip), ("n_scatter", c_ip), ("stop_reason", c_ip),
+                ("emoins", c_dp), ("eplus", c_dp), ("ttot_tronc", c_dp), ("ttot_vrai", c_dp), ("tauout", c_dp),
+                ("ier", c_ip)]
+
+
+class CGroupOut(C.Structure):
+    _fields_ = [("rec", c_dp), ("n_rec", c_ip), ("emoins", c_dp), ("eplus", c_dp), ("ttot_tronc", c_dp),
+                ("ttot_vrai", c_dp), ("tauout", c_dp)]
+
+
+class CStats(C.Structure):
+    _fields_ = [("steps", C.c_longlong), ("flops", C.c_double), ("bytes", C.c_double), ("step_ms", C.c_double),
+                ("step_launches", C.c_longlong), ("total_ms", C.c_double), ("launches", C.c_longlong)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libsosgpu.so (built in-tree by __graft_entry__.build()).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libsosgpu.so is missing (%s): build it with __graft_entry__.build(); "
+                               "the SOS hot path has no CPU fallback" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        lib.sosgpu_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        lib.sosgpu_destroy.argtypes = [C.c_void_p]
+        lib.sosgpu_last_error.argtypes = [C.c_void_p]
+        lib.sosgpu_last_error.restype = C.c_char_p
+        lib.sosgpu_launch_count.argtypes = [C.c_void_p]
+        lib.sosgpu_launch_count.restype = C.c_longlong
+        lib.sosgpu_set_options.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+        lib.sosgpu_batch_upload.argtypes = [C.c_void_p, C.POINTER(COptics), C.c_int, C.POINTER(CTerm), C.c_int,
+                                            C.c_int, C.POINTER(C.c_void_p)]
+        lib.sosgpu_batch_upload_os.argtypes = [C.c_void_p, C.POINTER(COptics), C.c_int, C.POINTER(CTerm), C.c_int,
+                                               C.c_int, c_ip, C.POINTER(C.c_void_p)]
+        lib.sosgpu_batch_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(CTermOut),
+                                         C.POINTER(CGroupOut)]
+        lib.sosgpu_batch_free.argtypes = [C.c_void_p, C.c_void_p]
+        lib.sosgpu_batch_stats.argtypes = [C.c_void_p, C.POINTER(CStats)]
+        lib.sosgpu_batch_group_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        lib.sosgpu_group_finalize.argtypes = [c_dp, c_dp, c_dp, C.c_int]
+        _lib = lib
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+class TermResults:
+    """Per-term outputs of SOS / SOS_OS: Fourier records (file order Q,U,I), counts, fluxes, optical depths."""
+    pass
+
+
+class GroupResults:
+    """Per-wavelength outputs of the SOS_AGGREGATE chain."""
+    pass
+
+
+class Batch:
+    """Inputs resident in HBM (sosgpu_batch)."""
+
+    def __init__(self, solver, handle, nterm, ngroup, rec_stride, wmax, keep):
+        self.solver, self.handle = solver, handle
+        self.nterm, self.ngroup, self.rec_stride, self.wmax = nterm, ngroup, rec_stride, wmax
+        self._keep = keep
+
+    def free(self):
+        if self.handle:
+            self.solver.lib.sosgpu_batch_free(self.solver.ctx, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Solver:
+    """One CUDA device, one stream.  Mirrors SOS (SOS.F:340), SOS_OS (SOS_OS.F:303) and SOS_AGGREGATE."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.sosgpu_create(C.byref(h), device)
+        if rc != SOSGPU_OK:
+            raise RuntimeError("libsosgpu: cannot create a context on CUDA device %d (rc=%d): "
+                               "no usable GPU, and the SOS hot path has no CPU fallback" % (device, rc))
+        self.ctx = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.sosgpu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != SOSGPU_OK:
+            raise RuntimeError("libsosgpu %s failed (rc=%d): %s" % (what, rc, self.lib.sosgpu_last_error(self.ctx).decode()))
+
+    @property
+    def launches(self):
+        return int(self.lib.sosgpu_launch_count(self.ctx))
+
+    def set_options(self, field_budget_bytes=0, max_wave_orders=0):
+        self.lib.sosgpu_set_options(self.ctx, field_budget_bytes, max_wave_orders)
+
+    # ------------------------------------------------------------------ batch
+    def upload(self, workload, term_ids=None, os_level=False, iborm=None):
+        """H2D of a Workload (synth.Workload): optics entries are de-duplicated by identity."""
+        terms = workload.terms if term_ids is None else [workload.terms[i] for i in term_ids]
+        keep = []
+        omap, copt = {}, []
+        for t in terms:
+            o = workload.optics[t.optics]
+            if id(o) in omap:
+                continue
+            omap[id(o)] = len(copt)
+            arrs = [_f64(o.rmu), _f64(o.ga), _f64(o.alpha), _f64(o.beta), _f64(o.gamma), _f64(o.zeta)]
+            keep.extend(arrs)
+            co = COptics()
+            co.nbmu, co.rmu, co.ga, co.n0, co.tetas, co.os_nb = o.nbmu, _d(arrs[0]), _d(arrs[1]), o.n0, o.tetas, o.os_nb
+            co.alpha, co.beta, co.gamma, co.zeta = _d(arrs[2]), _d(arrs[3]), _d(arrs[4]), _d(arrs[5])
+            co.a_trunc, co.piz, co.piztr, co.ron, co.rho = o.a_trunc, o.piz, o.piztr, o.ron, o.rho
+            co.imat_surf, co.ifresnel, co.ind_surf = o.imat_surf, o.ifresnel, o.ind_surf
+            if o.imat_surf == 1:
+                s = np.ascontiguousarray(o.surf, dtype=np.float32)
+                keep.append(s)
+                co.surf, co.n_surf_rec = s.ctypes.data_as(c_fp), s.shape[0]
+            else:
+                co.surf, co.n_surf_rec = None, 0
+            co.igmax, co.ipolar, co.zout = o.igmax, o.ipolar, o.zout
+            copt.append(co)
+        gmap = {}
+        cterms = (CTerm * len(terms))()
+        for i, t in enumerate(terms):
+            o = workload.optics[t.optics]
+            g = gmap.setdefault(t.optics, len(gmap))
+            arrs = [_f64(t.zprof), _f64(t.h), _f64(t.pcaer), _f64(t.pcmol)]
+            keep.extend(arrs)
+            ct = cterms[i]
+            ct.optics, ct.group, ct.aik, ct.nt = omap[id(o)], g, t.aik, t.nt
+            ct.zprof, ct.h, ct.pcaer, ct.pcmol = (_d(a) for a in arrs)
+        coptics = (COptics * len(copt))(*copt)
+        h = C.c_void_p()
+        if os_level:
+            ib = np.ascontiguousarray(iborm, dtype=np.int32)
+            rc = self.lib.sosgpu_batch_upload_os(self.ctx, coptics, len(copt), cterms, len(terms), len(gmap),
+                                                 ib.ctypes.data_as(c_ip), C.byref(h))
+        else:
+            rc = self.lib.sosgpu_batch_upload(self.ctx, coptics, len(copt), cterms, len(terms), len(gmap), C.byref(h))
+        self._check(rc, "batch_upload")
+        rec_stride = max(workload.optics[t.optics].os_nb for t in terms) + 1
+        wmax = 2 * max(workload.optics[t.optics].nbmu for t in terms) + 1
+        b = Batch(self, h, len(terms), len(gmap), rec_stride, wmax, keep)
+        b.group_of_term = [gmap[t.optics] for t in terms]
+        b.nbmu_of_term = [workload.optics[t.optics].nbmu for t in terms]
+        return b
+
+    def run(self, batch, want_terms=True, want_groups=True, want_rec=True, part_only=False):
+        """Run the resident batch.  With want_* False nothing is copied back (device-resident timing)."""
+        nt, ng, rs, w = batch.nterm, batch.ngroup, batch.rec_stride, batch.wmax
+        tr = gr = None
+        to = go = None
+        if want_terms:
+            tr = TermResults()
+            tr.rec = np.zeros((nt, rs, 3, w)) if want_rec else None
+            tr.n_fourier = np.zeros(nt, dtype=np.int32)
+            tr.n_scatter = np.zeros((nt, rs), dtype=np.int32)
+            tr.stop_reason = np.zeros((nt, rs), dtype=np.int32)
+            for n in ("emoins", "eplus", "ttot_tronc", "ttot_vrai", "tauout"):
+                setattr(tr, n, np.zeros(nt))
+            tr.ier = np.zeros(nt, dtype=np.int32)
+            to = CTermOut(_d(tr.rec) if want_rec else None, tr.n_fourier.ctypes.data_as(c_ip),
+                          tr.n_scatter.ctypes.data_as(c_ip), tr.stop_reason.ctypes.data_as(c_ip),
+                          _d(tr.emoins), _d(tr.eplus), _d(tr.ttot_tronc), _d(tr.ttot_vrai), _d(tr.tauout),
+                          tr.ier.ctypes.data_as(c_ip))
+        if want_groups:
+            gr = GroupResults()
+            gr.rec = np.zeros((ng, rs, 3, w))
+            gr.n_rec = np.zeros(ng, dtype=np.int32)
+            for n in ("emoins", "eplus", "ttot_tronc", "ttot_vrai", "tauout"):
+                setattr(gr, n, np.zeros(ng))
+            go = CGroupOut(_d(gr.rec), gr.n_rec.ctypes.data_as(c_ip), _d(gr.emoins), _d(gr.eplus),
+                           _d(gr.ttot_tronc), _d(gr.ttot_vrai), _d(gr.tauout))
+        rc = self.lib.sosgpu_batch_run(self.ctx, batch.handle, rs, w, int(part_only),
+                                       C.byref(to) if to is not None else None,
+                                       C.byref(go) if go is not None else None)
+        self._check(rc, "batch_run")
+        return tr, gr
+
+    def stats(self, batch):
+        st = CStats()
+        self.lib.sosgpu_batch_stats(batch.handle, C.byref(st))
+        return {k: getattr(st, k) for k, _ in CStats._fields_}
+
+    def group_buffer(self, batch):
+        p, n = C.c_void_p(), C.c_size_t()
+        self.lib.sosgpu_batch_group_buffer(batch.handle, C.byref(p), C.byref(n))
+        return p.value, n.value
+
+    def solve(self, workload, term_ids=None, **kw):
+        """SOS + SOS_AGGREGATE for every term of the workload (host buffers in, host buffers out)."""
+        b = self.upload(workload, term_ids)
+        try:
+            return self.run(b, **kw)
+        finally:
+            b.free()
+
+    # ------------------------------------------------------------------ single routines
+    def sos_os(self, o, nt, h, xdel, ydel, zprof, iborm):
+        """SOS_OS (SOS_OS.F:303): profile arrays as SOS_OS receives them."""
+        from .synth import Term, Workload
+        wl = Workload("sos_os", [o], [Term(0, 1.0, _f64(zprof), _f64(h), _f64(xdel), _f64(ydel))])
+        b = self.upload(wl, os_level=True, iborm=[iborm])
+        try:
+            tr, _ = self.run(b, want_groups=False)
+        finally:
+            b.free()
+        return tr
+
+    def noyaux(self, is_, rmu, os_nb, alpha, beta, gamma, zeta):
+        """SOS_NOYAUX (SOS_OS.F:1857).  Same return convention as oracle.noyaux."""
+        rmu = _f64(rmu)
+        W = rmu.size
+        N = (W - 1) // 2
+        a, b, g, z = (_f64(x) for x in (alpha, beta, gamma, zeta))
+        out = {n: np.zeros(W) for n in ("xpl", "xrl", "xtl")}
+        ker = {n: np.zeros((W, W)) for n in ("bp", "gr", "gt", "arr", "art", "att")}
+        rc = self.lib.sosgpu_noyaux(self.ctx, C.c_int(is_), C.c_int(N), _d(rmu), C.c_int(os_nb), _d(a), _d(b), _d(g),
+                                    _d(z), _d(out["xpl"]), _d(out["xrl"]), _d(out["xtl"]), _d(ker["bp"]),
+                                    _d(ker["gr"]), _d(ker["gt"]), _d(ker["arr"]), _d(ker["art"]), _d(ker["att"]))
+        self._check(rc, "noyaux")
+        out.update(ker)
+        return out
+
+    def order_step(self, is_, rmu, ga, os_nb, alpha, beta, gamma, zeta, ron, ipolar, nt, h, xdel, ydel, i1, q1, u1):
+        """SOS_FSOURCE_ORDREIG + SOS_INTEGR_EPOPT fused (black surface).  Returns (i1n,q1n,u1n,i2,q2,u2)."""
+        rmu, ga = _f64(rmu), _f64(ga)
+        W = rmu.size
+        N = (W - 1) // 2
+        arrs = [_f64(x) for x in (alpha, beta, gamma, zeta, h, xdel, ydel, i1, q1, u1)]
+        outs = [np.zeros((W, nt + 1)) for _ in range(6)]
+        rc = self.lib.sosgpu_order_step(self.ctx, C.c_int(is_), C.c_int(N), _d(rmu), _d(ga), C.c_int(os_nb),
+                                        _d(arrs[0]), _d(arrs[1]), _d(arrs[2]), _d(arrs[3]), C.c_double(ron),
+                                        C.c_int(ipolar), C.c_int(nt), _d(arrs[4]), _d(arrs[5]), _d(arrs[6]),
+                                        _d(arrs[7]), _d(arrs[8]), _d(arrs[9]), None,
+                                        _d(outs[0]), _d(outs[1]), _d(outs[2]), _d(outs[3]), _d(outs[4]), _d(outs[5]))
+        self._check(rc, "order_step")
+        return outs
+
+    def trphi_option(self, rec, nbmu, rmu, tau, tauout, igli, n0, wind, ind_surf, ifresnel, itrphi, phios, pas_phi,
+                     ipolar):
+        """SOS_TRPHI_OPTION (SOS_TRPHI.F:285).  Same return convention as oracle.trphi_option."""
+        rec = np.ascontiguousarray(rec, dtype=np.float64)
+        cap = 2 if itrphi == 1 else 360 // max(pas_phi, 1) + 1
+        phi_fin, theta = np.zeros(cap), np.zeros(nbmu)
+        up, down = np.zeros((7, cap, nbmu)), np.zeros((7, cap, nbmu))
+        n = self.lib.sosgpu_trphi_option(self.ctx, _d(rec), C.c_int(rec.shape[0]), C.c_int(nbmu), _d(_f64(rmu)),
+                                         C.c_double(tau), C.c_double(tauout), C.c_int(igli), C.c_int(n0),
+                                         C.c_double(wind), C.c_double(ind_surf), C.c_int(ifresnel), C.c_int(itrphi),
+                                         C.c_double(phios), C.c_int(pas_phi), C.c_int(ipolar), _d(phi_fin), _d(theta),
+                                         _d(up), _d(down), C.c_int(cap))
+        if n < 0:
+            self._check(n, "trphi_option")
+        return n, phi_fin[:n], theta, up[:, :n], down[:, :n]

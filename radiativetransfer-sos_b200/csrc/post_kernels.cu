@@ -1,0 +1,165 @@
+// post_kernels.cu -- azimuth synthesis of the Fourier series onto the view directions
+// (SOS_TRPHI / SOS_TRPHI_OPTION, SOS_TRPHI.F:285-636, 749-1243, helpers :1278-1541, 1843-1907).
+// Compiled with -fmad=false: same operation order as the reference.
+// Bandwidth-type kernel: one thread per (group, azimuth, direction); each thread walks the Fourier
+// records of its group in ascending order (the reference's summation order).
+#include "sosgpu_internal.h"
+#include "post_kernels.h"
+#include <math.h>
+
+#define SEUIL_Z      ((double)0.0001f)    // CTE_SEUIL_Z  SOS.h:407 (REAL*4 literal)
+#define SEUIL_X      ((double)0.00001f)   // CTE_SEUIL_X  SOS.h:413
+#define THRESHOLD_QU (1.0e-15)            // CTE_THRESHOLD_Q_U_NULL SOS.h:418
+#define SOLAR_DISC   (6.8e-05)            // CTE_SOLAR_DISC_SOLID_ANGLE SOS.h:426
+#define VALEUR_INDEF (-999.0)             // INCTE_VALEUR_INDEF SOS_TRPHI.F:134
+
+// SOS_GLITTE, SOS_TRPHI.F:1278-1317
+__device__ static double glitte(double sig, double c0, double c1, double phi)
+{
+  const double x1 = sqrt(1 - c1 * c1) - cos(phi) * sqrt(1 - c0 * c0);
+  const double x2 = sqrt(1 - c0 * c0) * sin(phi);
+  const double x3 = c0 + c1;
+  const double c0n = (x3 / (sqrt(x1 * x1 + x2 * x2 + x3 * x3)));
+  const double xxx = (-(1 - c0n * c0n) / (sig * (c0n * c0n)));
+  if (xxx < -100) return 0.0;
+  const double pp = (1 / sig) * exp(xxx);
+  const double c2 = c0n * c0n;
+  return pp / (4 * c1 * (c2 * c2));
+}
+// SOS_ANGLE, SOS_TRPHI.F:1347-1375
+__device__ static void angle(double c0, double c1, double phi, double &coskip, double &cosdif)
+{
+  double s = 1.0;
+  if (sin(phi) > 0.0) s = -1.0;
+  cosdif = -c0 * c1 + sqrt(1 - c0 * c0) * sqrt(1 - c1 * c1) * cos(phi);
+  const double z = s * (sqrt(1 - cosdif * cosdif)) * (sqrt(1 - c1 * c1));
+  coskip = 0.0;
+  if (fabs(z) > SEUIL_Z) coskip = (c1 * cosdif + c0) / z;
+}
+// SOS_REFLEX, SOS_TRPHI.F:1433-1472
+__device__ static void reflex(double cosdif, double ind, double &r11, double &r12, double &r33)
+{
+  const double ind2 = ind * ind;
+  const double cosw = sqrt(.5 * (1 - cosdif));
+  const double v = .5 * (1 + cosdif);
+  const double x = sqrt(ind2 - v);
+  const double rl = (ind2 * cosw - x) / (ind2 * cosw + x);
+  const double rr = (cosw - x) / (cosw + x);
+  r11 = (rl * rl + rr * rr) / 2.0;
+  r12 = (rl * rl - rr * rr) / 2.0;
+  r33 = rr * rl;
+}
+// SOS_MATRIC, SOS_TRPHI.F:1505-1541
+__device__ static void matric(double coskip, double r11, double r12, double &m11, double &m21, double &m31)
+{
+  const double x = 1.0 - fabs(coskip);
+  double c2 = 1.0, s2 = 0.0;
+  if (x >= SEUIL_X) {
+    c2 = 2.0 * coskip * coskip - 1.0;
+    s2 = 2.0 * coskip * sqrt(1.0 - coskip * coskip);
+  }
+  if (coskip == 0.0) r12 = 0.0;
+  m11 = r11;
+  m21 = c2 * r12;
+  m31 = s2 * r12;
+}
+// SOS_POLAR, SOS_TRPHI.F:1843-1907
+__device__ static void polar(double xi, double xq, double xu, double pi, double &xan, double &tpol, double &lpol)
+{
+  if (xq != 0.0) {
+    const double xt = xu / xq;
+    if (xq > 0.0) xan = 90.0 * atan(xt) / pi;
+    else if (xu > 0.0) xan = 90.0 + 90.0 * atan(xt) / pi;
+    else xan = -90.0 + 90.0 * atan(xt) / pi;
+  } else {
+    if (xu > 0.0) xan = 45.0;
+    else if (xu < 0) xan = -45.0;
+    else xan = VALEUR_INDEF;
+  }
+  lpol = sqrt(xq * xq + xu * xu);
+  if (xi != 0.0) tpol = 100.0 * lpol / xi;
+  else tpol = VALEUR_INDEF;
+}
+
+// grid: (nphi, ngroup); block: threads over the 2N directions.
+// out: [ngroup][2 (up, down)][7][nphi][N]   tables SCA, I, Q, U, POL_ANG, POL_RATE, L_POL
+__global__ void k_trphi(const TrphiGroup *groups, const double *phis, int nphi, TrphiParams prm, double *out)
+{
+  const TrphiGroup g = groups[blockIdx.y];
+  const int ip = blockIdx.x;
+  const int N = g.nbmu, W = 2 * N + 1;
+  const double phi = phis[ip];
+  const double pi = prm.pi;
+  for (int t = threadIdx.x; t < 2 * N; t += blockDim.x) {
+    const int j = (t < N) ? (t + 1) : -(t - N + 1);
+    const double rmuj = g.rmu[j + N];
+    double c0 = g.rmu[g.n0 + N];                               // :882
+    const double cosang = -c0 * rmuj + sin(acos(c0)) * sin(acos(rmuj)) * cos(phi);
+    const double angdiff = acos(cosang) * 180.0 / pi;
+    double xq = 0.0, xu = 0.0, xi = 0.0;
+    if (g.nrec > 0) {                                          // :908-940
+      xq = g.rec[j + N]; xu = g.rec[W + j + N]; xi = g.rec[2 * W + j + N];
+      for (int is = 1; is < g.nrec; ++is) {
+        const double *r = g.rec + (size_t)is * 3 * W;
+        const double xphi = is * phi;
+        xq = xq + 2.0 * r[j + N] * cos(xphi);
+        xu = xu + 2.0 * r[W + j + N] * sin(xphi);
+        xi = xi + 2.0 * r[2 * W + j + N] * cos(xphi);
+      }
+    }
+    if (prm.igli == 1 && j > 0) {                              // :946-1001
+      const double at0 = exp(-g.tau / c0);
+      const double sigma2 = (double)0.003f + (double)0.00512f * prm.wind;
+      const double atj = at0 * exp(-(g.tau - g.tauout) / rmuj);
+      const double c1 = rmuj;
+      const double p = glitte(sigma2, c0, c1, phi);
+      double coskip, cosdif, r11, r12, r33, m11, m21, m31;
+      angle(c0, c1, phi, coskip, cosdif);
+      reflex(cosdif, prm.ind_surf, r11, r12, r33);
+      matric(coskip, r11, r12, m11, m21, m31);
+      xi = xi + m11 * atj * p;
+      if (prm.ipolar == 1) { xq = xq + m21 * atj * p; xu = xu + m31 * atj * p; }
+    }
+    if (prm.ifresnel == 1 && j == g.n0) {                      // :1008-1039
+      if ((cos(phi) == 1.0) && (g.n0 > 0)) {
+        const double at0 = exp(-g.tau / c0);
+        const double atj = at0 * exp(-(g.tau - g.tauout) / c0);
+        const double cosdif = 1.0 - 2.0 * c0 * c0;
+        double r11, r12, r33;
+        reflex(cosdif, prm.ind_surf, r11, r12, r33);
+        const double coef_sun = pi / SOLAR_DISC;
+        xi = xi + r11 * coef_sun * atj;
+        if (prm.ipolar == 1) xq = xq + r12 * coef_sun * atj;
+      }
+    }
+    if (xi <= 1.e-99) xi = 0.0;                                // :1212-1218
+    if (fabs(xq) < THRESHOLD_QU) xq = 0.0;
+    if (fabs(xu) < THRESHOLD_QU) xu = 0.0;
+    double xan, tpol, lpol;
+    polar(xi, xq, xu, pi, xan, tpol, lpol);
+    const int ud = (j > 0) ? 0 : 1, jj = (j > 0 ? j : -j) - 1;
+    double *o = out + (((size_t)blockIdx.y * 2 + ud) * 7) * nphi * N + (size_t)ip * N + jj;
+    const size_t ts = (size_t)nphi * N;
+    o[0] = angdiff; o[ts] = xi; o[2 * ts] = xq; o[3 * ts] = xu; o[4 * ts] = xan; o[5 * ts] = tpol; o[6 * ts] = lpol;
+  }
+}
+
+extern "C" void sos_launch_trphi(const TrphiGroup *groups, int ngroup, const double *phis, int nphi,
+                                 TrphiParams prm, double *out, cudaStream_t st)
+{
+  if (ngroup <= 0 || nphi <= 0) return;
+  dim3 grid(nphi, ngroup);
+  k_trphi<<<grid, 160, 0, st>>>(groups, phis, nphi, prm, out);
+}
+
+// RES = RES + AIK*TMP (SOS_AGGREGATE.F:401-403) for the file-level drop-in sos_aggregate_
+__global__ void k_axpy(double *res, const double *tmp, double aik, size_t n)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) res[i] = res[i] + aik * tmp[i];
+}
+extern "C" void sos_launch_axpy(double *res, const double *tmp, double aik, size_t n, cudaStream_t st)
+{
+  if (n == 0) return;
+  k_axpy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(res, tmp, aik, n);
+}

@@ -1,0 +1,95 @@
+// sosgpu_internal.h -- device data layout shared by the CUDA translation units of libsosgpu.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// ------------------------------------------------------------------------------------------------
+// Row / column numbering of the packed problem (DESIGN.md "Data layout in HBM")
+//   N  = nbmu, W = 2N+1, HB = roundup(3N,16) rows per direction block, KP = 2*HB.
+//   row r in [0,KP): d = r / HB (0: mu>0 "up", 1: mu<0 "down"), q = r % HB,
+//                    valid iff q < 3N, stokes = q / N (0 I, 1 Q, 2 U), k = q % N + 1.
+//   A field X(0:NT,-N:N) x {I,Q,U} of the reference is stored as X[r][level], level fastest,
+//   pitch LP = roundup(NT+1, 8); pad rows / pad levels stay zero.
+// ------------------------------------------------------------------------------------------------
+#define SOS_KB 16      // k-slab of the contraction (doubles)
+#define SOS_CH 64      // level chunk (columns of the DMMA tile)
+#define SOS_SA 20      // smem row stride of the A slab   (KB + 4: conflict-free 64-bit fragment loads)
+#define SOS_SB 68      // smem row stride of the B slab   (CH + 4)
+#define SOS_SJ 65      // smem row stride of the staging tile (odd: conflict-free row-per-thread scan)
+#define SOS_STAGES 3
+#define SOS_MAXW 8     // warps (16-row groups) per CTA tile
+
+struct OpticsDev {            // one per optics entry (device copy, arrays in a slab)
+  int nbmu, W, HB, KP, os_nb, n0, imat_surf, ifresnel, ipolar, igmax;
+  double tab;                 // TAB = -mu_s (SOS_OS.F:706-715)
+  double ro, ron, ind_surf, zout;
+  double beta2, gamma2, alpha2;      // Rayleigh coefficients (SOS_OS.F:678-699)
+  double f11sun, f12sun;             // F11(0), F12(0) of SOS_MAT_FRESNEL_PLAN_REFL
+  const double *rmu, *ga;            // [W] (rmu[N] = tab)
+  const double *alpha, *beta, *gamma, *zeta;   // [os_nb+1]
+  const double *f11, *f12, *f33;     // [N+1]
+  const float *surf;                 // [nrec][9][N][N] or null
+  int n_surf_rec;
+};
+
+struct TermDev {              // one per (wavelength, CKD term)
+  int optics, group, nt, LP, iborm;
+  int jout;                   // output level index J for zout != -1 (interp between J-1 and J), else -1
+  double zz;                  // interpolation weight ZZ (SOS_OS.F:1520)
+  double aik, eground;        // eground = exp(H(NT)/TAB)
+  const double *h, *xdel, *ydel;      // [nt+1] truncation-adapted profile (SOS.F:523-543)
+  const double *dt, *inv;             // [nt] layer optical thickness and reciprocal
+  const double *ch;                   // [nt+1] exp(-H/(-TAB))/4  (SOS_OS.F:837-839)
+  const double *cf;                   // [nt+1] flat-sea source attenuation (SOS_OS.F:3219,3278) or null
+  const double *att;                  // [nt][N] exp(-dt/mu_k)
+  double *i4;                         // [6][2N] running Fourier sums I4,Q4,U4,I5,Q5,U5 (component order below)
+};
+
+// component order of the 6N "TOA/BOA" vectors (histories, sums): c = d*3N + stokes*N + (k-1)
+struct ItemDev {              // one per (term, Fourier order) in the current wave
+  int term, is, kset;         // kset: index of the (optics, is) kernel set of this wave
+  int n;                      // current scattering order IG
+  int active, reason;
+  double *x[2];               // ping-pong fields [KP][LP]
+  double *hist_a, *hist_d, *sum3;     // [6N]
+  double *rii;                        // [3N] direct surface term at TOA (SOS_OS.F:1051-1084)
+  double *sumout;                     // [2][6N] sums at the two output levels (zout != -1) or null
+  double *riiout;                     // [2][3N]
+};
+
+struct KsetDev {              // kernel set of one (optics, Fourier order)
+  int optics, is, dual;       // dual: Rayleigh part present (is <= 2)
+  double beta0;
+  double *basis;              // [3][(os_nb+2)][W]  PSL,RSL,TSL(-1:NB,-N:N)
+  double *ker;                // [6][W*W] BP,GR,GT,ARR,ART,ATT   (j,k) at [(k+N)*W + (j+N)]
+  double *xpl;                // [3][W] XPL,XRL,XTL
+  double *apackA, *apackR;    // [KP][KP] row-major, 0.5*GA(j)*sign*element
+  double *c1, *c2;            // [KP] order-1 row coefficients (Rayleigh / aerosol)
+  double *fz1, *fz2;          // [KP] flat-sea order-1 row coefficients
+};
+
+// launch helpers implemented in the .cu files
+#ifdef __cplusplus
+extern "C" {
+#endif
+void sos_launch_basis(const KsetDev *ksets, const OpticsDev *optics, int nkset, cudaStream_t st);
+void sos_launch_kernels(const KsetDev *ksets, const OpticsDev *optics, int nkset, int maxW, cudaStream_t st);
+void sos_launch_pack(const KsetDev *ksets, const OpticsDev *optics, int nkset, int maxKP, cudaStream_t st);
+void sos_launch_att(const TermDev *terms, const OpticsDev *optics, int nterm, int max_elems, cudaStream_t st);
+void sos_launch_init(ItemDev *items, const TermDev *terms, const OpticsDev *optics, int nitem, cudaStream_t st);
+void sos_launch_test(ItemDev *items, const TermDev *terms, const OpticsDev *optics,
+                     const int *list_cur, int ncur, int *list_next, int *count_next, cudaStream_t st);
+void sos_launch_fourier(ItemDev *items, TermDev *terms, const OpticsDev *optics, int nterm,
+                        const int *item_of, int s0, int s1, int rec_stride_dev, int wdev,
+                        double *rec, int *n_fourier, int *n_scatter, int *stop_reason,
+                        double *emoins, double *eplus, int *done, cudaStream_t st);
+void sos_launch_aggregate(const TermDev *terms, const int *group_start, const int *group_terms, int ngroup,
+                          const double *rec, const int *n_fourier, int rec_stride_dev, int wdev,
+                          double *grec, int *gnrec, cudaStream_t st);
+// fused step: order1 != 0 -> analytic first-order source; list == null -> items 0..nitem-1;
+// mode bit 0: launch the aerosol-only instantiation (is > 2), bit 1: the Rayleigh+aerosol one (is <= 2)
+int  sos_launch_step(const ItemDev *items, const TermDev *terms, const OpticsDev *optics, const KsetDev *ksets,
+                     const int *list, int nitem, int order1, int mode, int maxHB, double *jdump, cudaStream_t st);
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,260 @@
+// sosgpu_shims.cu -- (1) azimuth synthesis entry points (SOS_TRPHI_OPTION), single wavelength and batched over the
+// resident group sums; (2) gfortran-ABI drop-in symbols sos_os_ / sos_aggregate_ that keep the reference's
+// argument lists, fixed SOS.h strides and file side effects (SOS_OS.F:303-308, SOS_AGGREGATE.F:172-178).
+#include "sosgpu_host.h"
+#include "post_kernels.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// ---------------------------------------------------------------------------------------------
+static int phis_of(int itrphi, double phios, int pas_phi, std::vector<double> &phis, std::vector<double> &phi_fin)
+{
+  const double pi = std::acos(-1.0);
+  phis.clear(); phi_fin.clear();
+  if (itrphi == 1) {                                           // SOS_TRPHI.F:435,494
+    phis.push_back(pi + phios * pi / 180.0);
+    phis.push_back(phios * pi / 180.0);
+    phi_fin.push_back(phios);                                  // PHI_FIN(0) ends up holding PHIOS (:445,504)
+    phi_fin.push_back(0.0);
+  } else if (itrphi == 2) {                                    // SOS_TRPHI.F:558-561
+    if (pas_phi < 1) return -1;
+    for (int iphi = 0; iphi <= 360; iphi += pas_phi) {
+      phis.push_back(pi * iphi / 180.0);
+      phi_fin.push_back((double)iphi);
+    }
+  } else return -1;
+  return (int)phis.size();
+}
+
+extern "C" int sosgpu_trphi_option(sosgpu_ctx *ctx, const double *rec, int nrec, int nbmu, const double *rmu,
+                                   double tau, double tauout, int igli, int n0, double wind, double ind_surf,
+                                   int ifresnel, int itrphi, double phios, int pas_phi, int ipolar,
+                                   double *phi_fin, double *theta_fin, double *up, double *down, int nphi_cap)
+{
+  if (!ctx) return SOSGPU_ERR_NO_DEVICE;
+  if (!rec || nrec < 1 || nbmu < 1 || nbmu > SOSGPU_NBMU_MAX || n0 < 1 || n0 > nbmu) return SOSGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const int N = nbmu, W = 2 * N + 1;
+  std::vector<double> phis, pf;
+  const int nphi = phis_of(itrphi, phios, pas_phi, phis, pf);
+  if (nphi < 1 || nphi > nphi_cap) return SOSGPU_ERR_ARG;
+  double *d_rec = nullptr, *d_rmu = nullptr, *d_phi = nullptr, *d_out = nullptr;
+  TrphiGroup *d_g = nullptr;
+  const size_t nout = (size_t)2 * 7 * nphi * N;
+  CK(cudaMalloc(&d_rec, (size_t)nrec * 3 * W * 8));
+  CK(cudaMalloc(&d_rmu, W * 8));
+  CK(cudaMalloc(&d_phi, nphi * 8));
+  CK(cudaMalloc(&d_out, nout * 8));
+  CK(cudaMalloc(&d_g, sizeof(TrphiGroup)));
+  CK(cudaMemcpyAsync(d_rec, rec, (size_t)nrec * 3 * W * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_rmu, rmu, W * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_phi, phis.data(), nphi * 8, cudaMemcpyHostToDevice, ctx->stream));
+  TrphiGroup g{d_rec, d_rmu, nrec, N, n0, tau, tauout};
+  CK(cudaMemcpyAsync(d_g, &g, sizeof(g), cudaMemcpyHostToDevice, ctx->stream));
+  TrphiParams prm{igli, ifresnel, ipolar, wind, ind_surf, std::acos(-1.0)};
+  sos_launch_trphi(d_g, 1, d_phi, nphi, prm, d_out, ctx->stream);
+  ctx->launches += 1;
+  std::vector<double> out(nout);
+  CK(cudaMemcpyAsync(out.data(), d_out, nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  // [2][7][nphi][N] -> caller tables [7][nphi_cap][N]
+  for (int ud = 0; ud < 2; ++ud) {
+    double *dst = ud == 0 ? up : down;
+    if (!dst) continue;
+    for (int t = 0; t < 7; ++t)
+      for (int ip = 0; ip < nphi; ++ip)
+        memcpy(dst + ((size_t)t * nphi_cap + ip) * N, &out[(((size_t)ud * 7 + t) * nphi + ip) * N], N * 8);
+  }
+  const double pi = std::acos(-1.0);
+  if (phi_fin) for (int ip = 0; ip < nphi; ++ip) phi_fin[ip] = pf[ip];
+  if (theta_fin) for (int j = 1; j <= N; ++j) theta_fin[j - 1] = std::acos(rmu[j + N]) * 180.0 / pi;   // :508,573
+  cudaFree(d_rec); cudaFree(d_rmu); cudaFree(d_phi); cudaFree(d_out); cudaFree(d_g);
+  return nphi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gfortran-ABI drop-ins.  One process-wide context, created on first use.
+static sosgpu_ctx *g_ctx = nullptr;
+static sosgpu_ctx *shim_ctx()
+{
+  if (!g_ctx) {
+    if (sosgpu_create(&g_ctx, 0) != SOSGPU_OK) {
+      fprintf(stderr, "  libsosgpu: no usable CUDA device -- the SOS hot path has no CPU fallback\n");
+      g_ctx = nullptr;
+    }
+  }
+  return g_ctx;
+}
+
+static std::string fstr(const char *s, size_t n)
+{
+  std::string r(s, n);
+  const size_t sp = r.find(' ');                               // the reference cuts file names at the first blank
+  if (sp != std::string::npos) r.resize(sp);
+  return r;
+}
+
+// gfortran unformatted sequential: 4-byte record markers
+static bool read_records(const std::string &path, std::vector<std::vector<char>> &recs)
+{
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  for (;;) {
+    int32_t n = 0;
+    if (fread(&n, 4, 1, f) != 1) break;
+    std::vector<char> r((size_t)n);
+    if (n > 0 && fread(r.data(), 1, (size_t)n, f) != (size_t)n) { fclose(f); return false; }
+    int32_t m = 0;
+    if (fread(&m, 4, 1, f) != 1 || m != n) { fclose(f); return false; }
+    recs.push_back(std::move(r));
+  }
+  fclose(f);
+  return true;
+}
+static bool write_records(const std::string &path, const double *rec, int nrec, size_t doubles_per_rec)
+{
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) return false;
+  const int32_t n = (int32_t)(doubles_per_rec * 8);
+  for (int r = 0; r < nrec; ++r) {
+    fwrite(&n, 4, 1, f);
+    fwrite(rec + (size_t)r * doubles_per_rec, 8, doubles_per_rec, f);
+    fwrite(&n, 4, 1, f);
+  }
+  fclose(f);
+  return true;
+}
+
+#define NBMU_MAX SOSGPU_NBMU_MAX
+#define NB_MAX SOSGPU_NB_MAX
+#define NT_MAX SOSGPU_NT_MAX
+
+extern "C" int sosgpu_batch_upload_os(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics,
+                                      const sosgpu_term *terms, int nterm, int ngroup, const int *iborm,
+                                      sosgpu_batch **batch);
+
+// SOS_OS.F:303-308.  Arrays use the reference's fixed extents: RMU/GA(-80:80), H/XDEL/YDEL/ZPROF(0:600),
+// ALPHA..ZETA(0:200).  TRACE/IDLOG are accepted and ignored (no log unit on this side).
+extern "C" void sos_os_(const int *nbmu, double *rmu, const double *ga, const int *os_nb, const int *nt,
+                        const char *ficsurf, const char *ficos,
+                        const int *n0, const double *tetas, const double *ro, const int *imat_surf,
+                        const int *ifresnel, const double *ind_surf,
+                        const double *h, const double *xdel, const double *ydel, const double *zprof, const double *ron,
+                        double *alpha, double *beta, double *gamma, double *zeta, const double *zout,
+                        const int *igmax, const int *iborm, const int *ipolar, const int *trace, const int *idlog,
+                        double *emoins, double *eplus, int *ier, size_t len_ficsurf, size_t len_ficos)
+{
+  (void)trace; (void)idlog; (void)beta;
+  *ier = 0;
+  const int N = *nbmu, W = 2 * N + 1, NB = *os_nb, NT = *nt;
+  sosgpu_ctx *ctx = shim_ctx();
+  if (!ctx || N < 1 || N > NBMU_MAX || NB > NB_MAX || NT > NT_MAX) { *ier = -1; return; }
+  const std::string fsurf = fstr(ficsurf, len_ficsurf), fos = fstr(ficos, len_ficos);
+  std::vector<double> rmu_c(W), ga_c(W);
+  for (int j = -N; j <= N; ++j) { rmu_c[j + N] = rmu[j + NBMU_MAX]; ga_c[j + N] = ga[j + NBMU_MAX]; }
+  std::vector<float> surf;
+  int nsurf = 0;
+  if (*imat_surf == 1) {                                       // :664-666, :916-925
+    std::vector<std::vector<char>> recs;
+    if (!read_records(fsurf, recs)) { fprintf(stdout, "  ERROR on SURFACE file opening for SOS_OS\n"); *ier = -1; return; }
+    const size_t need = (size_t)9 * N * N * 4;
+    for (auto &r : recs) {
+      if (r.size() < need) { fprintf(stdout, "  ERROR on SURFACE file reading for SOS_OS\n"); *ier = -1; return; }
+      const float *p = (const float *)r.data();
+      surf.insert(surf.end(), p, p + (size_t)9 * N * N);
+      ++nsurf;
+    }
+    if (nsurf < *iborm + 1) { fprintf(stdout, "  ERROR on SURFACE file reading for SOS_OS\n"); *ier = -1; return; }
+  }
+  sosgpu_optics o{};
+  o.nbmu = N; o.rmu = rmu_c.data(); o.ga = ga_c.data(); o.n0 = *n0; o.tetas = *tetas; o.os_nb = NB;
+  o.alpha = alpha; o.beta = beta; o.gamma = gamma; o.zeta = zeta; o.a_trunc = 0.0; o.piz = 1.0; o.piztr = 1.0;
+  o.ron = *ron; o.rho = *ro; o.imat_surf = *imat_surf; o.ifresnel = *ifresnel; o.ind_surf = *ind_surf;
+  o.surf = surf.empty() ? nullptr : surf.data(); o.n_surf_rec = nsurf; o.igmax = *igmax; o.ipolar = *ipolar; o.zout = *zout;
+  sosgpu_term t{};
+  t.optics = 0; t.group = 0; t.aik = 1.0; t.nt = NT; t.zprof = zprof; t.h = h; t.pcaer = xdel; t.pcmol = ydel;
+  // caller-visible side effects (:693-697, :715)
+  if (*ipolar == 0) for (int k = 0; k <= NB; ++k) { alpha[k] = 0.0; gamma[k] = 0.0; zeta[k] = 0.0; }
+  const double tab = (*n0 > 0) ? -rmu_c[*n0 + N] : -std::cos(std::acos(-1.0) * (*tetas) / 180.0);
+  rmu[NBMU_MAX] = tab;
+  if (tab == 0.0) { fprintf(stdout, "  SOS computation are stopped   because of a limb incidence\n"); return; }
+  if ((((*zout) < 0) && ((*zout) != -1.0)) || ((*zout) > 120.0)) {
+    fprintf(stdout, "  Inconsistency output altitude in the   atmospheric profile\n");
+    *ier = -1; return;
+  }
+  sosgpu_batch *b = nullptr;
+  const int ib = *iborm;
+  int rc = sosgpu_batch_upload_os(ctx, &o, 1, &t, 1, 1, &ib, &b);
+  if (rc != SOSGPU_OK) { *ier = -1; return; }
+  const int rs = NB + 1;
+  std::vector<double> rec((size_t)rs * 3 * W, 0.0);
+  int nf = 0; double em = 0, ep = 0;
+  sosgpu_term_out to{};
+  to.rec = rec.data(); to.n_fourier = &nf; to.emoins = &em; to.eplus = &ep;
+  rc = sosgpu_batch_run(ctx, b, rs, W, 0, &to, nullptr);
+  sosgpu_batch_free(ctx, b);
+  if (rc != SOSGPU_OK) { fprintf(stderr, "  libsosgpu: %s\n", sosgpu_last_error(ctx)); *ier = -1; return; }
+  *emoins = em; *eplus = ep;
+  if (fos != "NO_OUTPUT") {                                    // :671, :1571-1575
+    if (!write_records(fos, rec.data(), nf, (size_t)3 * W)) {
+      fprintf(stdout, "  ERROR on SOS binary result file opening for SOS_OS\n");
+      *ier = -1;
+    }
+  }
+}
+
+// SOS_AGGREGATE.F:172-178: RES = RES + AIK*TMP record by record with zero padding, file read-modify-write,
+// then the scalar accumulators (:452-488).  TDIFMUG uses the (-80:80) extent.
+extern "C" void sos_aggregate_(const int *nbmu, const double *aik, const char *ficos_tmp,
+                               const double *ttot_tronc_tmp, const double *ttot_vrai_tmp, const double *tauout_tmp,
+                               const double *tdifmus_tmp, const double *tdifmug_tmp, const double *emoins_tmp,
+                               const double *eplus_tmp, const char *ficos_agg_tmp, const char *ficos,
+                               double *ttot_tronc, double *ttot_vrai, double *tauout, double *tdifmus, double *tdifmug,
+                               double *emoins, double *eplus, int *ier,
+                               size_t len_ficos_tmp, size_t len_ficos_agg_tmp, size_t len_ficos)
+{
+  (void)ficos_agg_tmp; (void)len_ficos_agg_tmp;
+  const int N = *nbmu, W = 2 * N + 1;
+  sosgpu_ctx *ctx = shim_ctx();
+  if (!ctx) { *ier = -1; return; }
+  const std::string ftmp = fstr(ficos_tmp, len_ficos_tmp), fres = fstr(ficos, len_ficos);
+  std::vector<std::vector<char>> rt, rr;
+  if (!read_records(ftmp, rt)) { fprintf(stdout, "  SOS_AGGREGATE : ERROR_1101 : \n"); *ier = -1; return; }
+  const bool have = read_records(fres, rr);
+  const size_t per = (size_t)3 * W;
+  // record count incl. the reference's trailing all-zero record when the existing file is not shorter (:372-393)
+  size_t nout = std::max(rt.size(), rr.size());
+  if (have && rr.size() >= rt.size()) nout += 1;
+  std::vector<double> a(nout * per, 0.0), r(nout * per, 0.0);
+  for (size_t i = 0; i < rt.size(); ++i) memcpy(&a[i * per], rt[i].data(), std::min(rt[i].size(), per * 8));
+  for (size_t i = 0; i < rr.size(); ++i) memcpy(&r[i * per], rr[i].data(), std::min(rr[i].size(), per * 8));
+  double *d_a = nullptr, *d_r = nullptr;
+  bool ok = cudaSetDevice(ctx->device) == cudaSuccess && cudaMalloc(&d_a, a.size() * 8) == cudaSuccess &&
+            cudaMalloc(&d_r, r.size() * 8) == cudaSuccess;
+  if (ok) {
+    cudaMemcpyAsync(d_a, a.data(), a.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_r, r.data(), r.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+    sos_launch_axpy(d_r, d_a, *aik, r.size(), ctx->stream);
+    ctx->launches += 1;
+    cudaMemcpyAsync(r.data(), d_r, r.size() * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    ok = cudaStreamSynchronize(ctx->stream) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+  }
+  cudaFree(d_a); cudaFree(d_r);
+  if (!ok || !write_records(fres, r.data(), (int)nout, per)) { fprintf(stdout, "  SOS_AGGREGATE : ERROR_1302 : \n"); *ier = -1; return; }
+  *tdifmus = *tdifmus + (*aik) * (*tdifmus_tmp);               // :452-459
+  *emoins = *emoins + (*aik) * (*emoins_tmp);
+  *eplus = *eplus + (*aik) * (*eplus_tmp);
+  for (int j = -N; j <= N; ++j) tdifmug[j + NBMU_MAX] = tdifmug[j + NBMU_MAX] + (*aik) * tdifmug_tmp[j + NBMU_MAX];
+  double trans;                                                // :467-488
+  trans = (*ttot_tronc != 0) ? (*aik) * std::exp(-*ttot_tronc_tmp) + std::exp(-*ttot_tronc) : (*aik) * std::exp(-*ttot_tronc_tmp);
+  *ttot_tronc = -std::log(trans);
+  trans = (*ttot_vrai != 0) ? (*aik) * std::exp(-*ttot_vrai_tmp) + std::exp(-*ttot_vrai) : (*aik) * std::exp(-*ttot_vrai_tmp);
+  *ttot_vrai = -std::log(trans);
+  trans = (*tauout != 0) ? (*aik) * std::exp(-*tauout_tmp) + std::exp(-*tauout) : (*aik) * std::exp(-*tauout_tmp);
+  *tauout = -std::log(trans);
+}

@@ -1,0 +1,162 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle on identical (format-rounded) inputs.
+
+Bar (BASELINE.json north_star): numbers of Fourier orders and of scattering orders bit-identical;
+Stokes I/Q/U within 1e-9 relative (1e-12 absolute floor) at every output angle.
+"""
+import numpy as np
+import pytest
+
+from util import assert_stokes_close, oracle_term
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("is_", [0, 1, 2, 3, 5, 16])
+def test_noyaux(pkg, orc, solver, is_):
+    """SOS_NOYAUX (SOS_OS.F:1857-2158): six phase-matrix kernels + l=2 rows."""
+    o = pkg.synth.make_optics(nb_gauss=12, tetas=35.0, os_nb=24)
+    N = o.nbmu
+    rmu = o.rmu.copy()
+    rmu[N] = -o.rmu[N + o.n0]
+    ref = orc.noyaux(is_, rmu, o.os_nb, o.alpha, o.beta, o.gamma, o.zeta)
+    got = solver.noyaux(is_, rmu, o.os_nb, o.alpha, o.beta, o.gamma, o.zeta)
+    for k in ("xpl", "xrl", "xtl", "bp", "gr", "gt", "arr", "art", "att"):
+        scale = np.abs(ref[k]).max() + 1e-300
+        assert np.abs(got[k] - ref[k]).max() <= 1e-13 * scale, k
+
+
+@pytest.mark.parametrize("is_,nbg,nt", [(0, 8, 9), (2, 8, 70), (3, 12, 130), (6, 40, 100)])
+def test_order_step(pkg, orc, solver, is_, nbg, nt):
+    """SOS_FSOURCE_ORDREIG + SOS_INTEGR_EPOPT, one fused DMMA step vs the scalar loops."""
+    syn = pkg.synth
+    o = syn.make_optics(nb_gauss=nbg, tetas=35.0, os_nb=2 * nbg)
+    N, W = o.nbmu, 2 * o.nbmu + 1
+    rmu = o.rmu.copy()
+    rmu[N] = -o.rmu[N + o.n0]
+    rng = np.random.default_rng(7)
+    h = np.concatenate([[0.0], np.cumsum(rng.uniform(0.001, 0.006, nt))])
+    xdel, ydel = rng.uniform(0.1, 0.6, nt + 1), rng.uniform(0.1, 0.4, nt + 1)
+    i1, q1, u1 = (rng.standard_normal((W, nt + 1)) for _ in range(3))
+    ker = orc.noyaux(is_, rmu, o.os_nb, o.alpha, o.beta, o.gamma, o.zeta)
+    aaa = o.ron / (2 - o.ron)
+    aaa = (1 - aaa) / (1 + 2 * aaa)
+    i2, q2, u2 = orc.fsource_ordreig(is_, nt, xdel, ydel, 1.0 if is_ == 0 else 0.0, 0.5 * aaa, -aaa * np.sqrt(1.5),
+                                     3.0 * aaa, ker, i1, q1, u1, o.ga)
+    zi, zq, zu = (np.zeros((W, nt + 1)) for _ in range(3))
+    ri, rq, ru = orc.integr_epopt(rmu, nt, h, i2, q2, u2, zi, zq, zu)
+    gi, gq, gu, ji, jq, ju = solver.order_step(is_, rmu, o.ga, o.os_nb, o.alpha, o.beta, o.gamma, o.zeta, o.ron, 1,
+                                               nt, h, xdel, ydel, i1, q1, u1)
+    keep = np.arange(W) != N
+    for g, r, nm in ((ji, i2, "I2"), (jq, q2, "Q2"), (ju, u2, "U2"), (gi, ri, "I1"), (gq, rq, "Q1"), (gu, ru, "U1")):
+        scale = np.abs(r[keep]).max()
+        assert np.abs(g[keep] - r[keep]).max() <= 2e-13 * scale, nm
+
+
+def _check_terms(pkg, orc, solver, wl, ids=None):
+    tr, gr = solver.solve(wl, ids)
+    ids = range(len(wl.terms)) if ids is None else ids
+    for n, i in enumerate(ids):
+        t = wl.terms[i]
+        o = wl.optics[t.optics]
+        r = oracle_term(orc, o, t)
+        W = 2 * o.nbmu + 1
+        assert tr.ier[n] == r.ier
+        assert tr.n_fourier[n] == r.n_fourier, ("n_fourier", i, tr.n_fourier[n], r.n_fourier)
+        assert np.array_equal(tr.n_scatter[n, :r.n_fourier], r.n_scatter), ("n_scatter", i, tr.n_scatter[n, :r.n_fourier], r.n_scatter)
+        assert np.array_equal(tr.stop_reason[n, :r.n_fourier], r.stop_reason)
+        assert_stokes_close(tr.rec[n, :r.n_fourier, :, :W], r.rec, "term %d records" % i)
+        assert_stokes_close(tr.emoins[n], r.emoins, "emoins")
+        assert_stokes_close(tr.eplus[n], r.eplus, "eplus")
+        for k in ("ttot_tronc", "ttot_vrai", "tauout"):
+            assert getattr(tr, k)[n] == getattr(r, k), k
+    return tr, gr
+
+
+def test_solve_golden_cases(pkg, orc, solver):
+    """The four small cases of tests/golden (Lambert, BRDF/BPDF matrix, flat sea, output altitude)."""
+    import make_golden
+    syn = pkg.synth
+    for name, (o, t) in make_golden.cases(pkg).items():
+        wl = syn.Workload(name, [o], [t])
+        _check_terms(pkg, orc, solver, wl)
+
+
+def test_solve_rayleigh_only(pkg, orc, solver):
+    syn = pkg.synth
+    o = syn.make_optics(nb_gauss=12, tetas=35.0, os_nb=24, surface="lambert", rho=0.2, a_trunc=0.0, piztr=1.0)
+    wl = syn.Workload("ray", [o], [syn.Term(0, 1.0, *syn.profile(0.3, 8.0, 0.0, 2.0, 0.0))])
+    tr, _ = _check_terms(pkg, orc, solver, wl)
+    assert tr.n_fourier[0] == 3
+
+
+def test_solve_unpolarized(pkg, orc, solver):
+    syn = pkg.synth
+    o = syn.make_optics(nb_gauss=8, tetas=35.0, os_nb=16, surface="brdf", rho=0.05, ipolar=0)
+    wl = syn.Workload("unpol", [o], [syn.Term(0, 1.0, *syn.profile(0.05, 8.0, 0.2, 2.0, 0.0))])
+    tr, _ = _check_terms(pkg, orc, solver, wl)
+    assert np.all(tr.rec[0, :, 0] == 0.0) and np.all(tr.rec[0, :, 1] == 0.0)
+
+
+def test_solve_demo_config_and_aggregate(pkg, orc, solver):
+    """configs[0]-like (N=41, OS_NB=80, 5 CKD terms, ragged NT) + the SOS_AGGREGATE chain."""
+    syn = pkg.synth
+    wl = syn.config_demo(nterm=5, nb_gauss=40, os_nb=80, surface="brdf")
+    tr, gr = _check_terms(pkg, orc, solver, wl)
+    o = wl.optics[0]
+    agg = orc.Aggregate(o.nbmu, o.os_nb + 1)
+    for i, t in enumerate(wl.terms):
+        agg.add(t.aik, oracle_term(orc, o, t))
+    nmax = int(tr.n_fourier.max())
+    assert gr.n_rec[0] == nmax
+    assert_stokes_close(gr.rec[0, :nmax], agg.res[:nmax], "aggregated records")
+    assert np.all(agg.res[nmax:agg.nres] == 0.0)      # the reference's padding records carry no signal
+    for k in ("emoins", "eplus", "ttot_tronc", "ttot_vrai", "tauout"):
+        assert_stokes_close(getattr(gr, k)[0], agg.sc[k], k)
+
+
+def test_solve_mixed_batch_multiwave(pkg, orc, solver):
+    """Several wavelengths with different optics / N in one batch, forced through 3-order waves."""
+    syn = pkg.synth
+    wl = syn.Workload("mixed")
+    wl.optics.append(syn.make_optics(nb_gauss=8, tetas=35.0, os_nb=16, surface="lambert", rho=0.1))
+    wl.optics.append(syn.make_optics(nb_gauss=12, tetas=60.0, os_nb=24, surface="brdf", rho=0.0, seed=3))
+    wl.optics.append(syn.make_optics(nb_gauss=6, tetas=10.0, os_nb=12, surface="fresnel"))
+    rng = np.random.default_rng(11)
+    for p in range(3):
+        for k in range(3):
+            tg = float(np.exp(rng.uniform(np.log(1e-3), np.log(5.0))))
+            wl.terms.append(syn.Term(p, 1.0 / 3, *syn.profile(0.05, 8.0, 0.15 + 0.1 * p, 2.0, tg)))
+    solver.set_options(0, 3)
+    try:
+        _check_terms(pkg, orc, solver, wl)
+    finally:
+        solver.set_options(0, 0)
+
+
+def test_solve_long_profile(pkg, orc, solver):
+    """NT at the cap (600 layers) and a thick absorbing term."""
+    syn = pkg.synth
+    o = syn.make_optics(nb_gauss=8, tetas=35.0, os_nb=16, surface="lambert", rho=0.3)
+    wl = syn.Workload("thick", [o], [syn.Term(0, 1.0, *syn.profile(0.1, 8.0, 0.5, 2.0, 20.0)),
+                                     syn.Term(0, 1.0, *syn.profile(0.1, 8.0, 0.5, 2.0, 1.2))])
+    assert wl.terms[0].nt == 600
+    _check_terms(pkg, orc, solver, wl)
+
+
+def test_trphi_option(pkg, orc, solver):
+    """SOS_TRPHI_OPTION (SOS_TRPHI.F:285-636): azimuth synthesis + sun-glint direct term, both view modes."""
+    syn = pkg.synth
+    o = syn.make_optics(nb_gauss=12, tetas=35.0, os_nb=24, surface="glitter")
+    t = syn.Term(0, 1.0, *syn.profile(0.05, 8.0, 0.2, 2.0, 0.0))
+    r = oracle_term(orc, o, t)
+    for itrphi, phios, pas in ((1, 0.0, 0), (1, 37.5, 0), (2, 0.0, 30)):
+        n0, pf0, th0, up0, dn0 = orc.trphi_option(r.rec, o.nbmu, o.rmu, r.ttot_tronc, r.tauout, 1, o.n0, o.wind,
+                                                  o.ind_surf, 0, itrphi, phios, pas, 1)
+        n1, pf1, th1, up1, dn1 = solver.trphi_option(r.rec, o.nbmu, o.rmu, r.ttot_tronc, r.tauout, 1, o.n0, o.wind,
+                                                     o.ind_surf, 0, itrphi, phios, pas, 1)
+        assert n0 == n1
+        assert np.allclose(up1[0], up0[0], rtol=1e-12) and np.allclose(dn1[0], dn0[0], rtol=1e-12)
+        for tb in (1, 2, 3):
+            assert_stokes_close(up1[tb], up0[tb], "up table %d" % tb)
+            assert_stokes_close(dn1[tb], dn0[tb], "down table %d" % tb)
+        assert np.allclose(up1[4:], up0[4:], rtol=1e-7, atol=1e-9) and np.allclose(dn1[4:], dn0[4:], rtol=1e-7, atol=1e-9)
