@@ -156,8 +156,10 @@ class Solver:
         self.lib.sosgpu_set_options(self.ctx, field_budget_bytes, max_wave_orders)
 
     # ------------------------------------------------------------------ batch
-    def upload(self, workload, term_ids=None, os_level=False, iborm=None):
-        """H2D of a Workload (synth.Workload): optics entries are de-duplicated by identity."""
+    def upload(self, workload, term_ids=None, os_level=False, iborm=None, groups=None, ngroup=None):
+        """H2D of a Workload (synth.Workload): optics entries are de-duplicated by identity.
+        groups/ngroup: explicit aggregation group of each uploaded term (multi-GPU sharding keeps the global
+        group numbering on every rank); default = one group per wavelength present."""
         terms = workload.terms if term_ids is None else [workload.terms[i] for i in term_ids]
         keep = []
         omap, copt = {}, []
@@ -185,7 +187,7 @@ class Solver:
         cterms = (CTerm * len(terms))()
         for i, t in enumerate(terms):
             o = workload.optics[t.optics]
-            g = gmap.setdefault(t.optics, len(gmap))
+            g = groups[i] if groups is not None else gmap.setdefault(t.optics, len(gmap))
             arrs = [_f64(t.zprof), _f64(t.h), _f64(t.pcaer), _f64(t.pcmol)]
             keep.extend(arrs)
             ct = cterms[i]
@@ -193,17 +195,18 @@ class Solver:
             ct.zprof, ct.h, ct.pcaer, ct.pcmol = (_d(a) for a in arrs)
         coptics = (COptics * len(copt))(*copt)
         h = C.c_void_p()
+        ng = ngroup if groups is not None else len(gmap)
         if os_level:
             ib = np.ascontiguousarray(iborm, dtype=np.int32)
-            rc = self.lib.sosgpu_batch_upload_os(self.ctx, coptics, len(copt), cterms, len(terms), len(gmap),
+            rc = self.lib.sosgpu_batch_upload_os(self.ctx, coptics, len(copt), cterms, len(terms), ng,
                                                  ib.ctypes.data_as(c_ip), C.byref(h))
         else:
-            rc = self.lib.sosgpu_batch_upload(self.ctx, coptics, len(copt), cterms, len(terms), len(gmap), C.byref(h))
+            rc = self.lib.sosgpu_batch_upload(self.ctx, coptics, len(copt), cterms, len(terms), ng, C.byref(h))
         self._check(rc, "batch_upload")
         rec_stride = max(workload.optics[t.optics].os_nb for t in terms) + 1
         wmax = 2 * max(workload.optics[t.optics].nbmu for t in terms) + 1
-        b = Batch(self, h, len(terms), len(gmap), rec_stride, wmax, keep)
-        b.group_of_term = [gmap[t.optics] for t in terms]
+        b = Batch(self, h, len(terms), ng, rec_stride, wmax, keep)
+        b.h2d_bytes = int(sum(a.nbytes for a in keep))
         b.nbmu_of_term = [workload.optics[t.optics].nbmu for t in terms]
         return b
 

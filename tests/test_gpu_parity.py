@@ -49,7 +49,7 @@ def test_order_step(pkg, orc, solver, is_, nbg, nt):
     keep = np.arange(W) != N
     for g, r, nm in ((ji, i2, "I2"), (jq, q2, "Q2"), (ju, u2, "U2"), (gi, ri, "I1"), (gq, rq, "Q1"), (gu, ru, "U1")):
         scale = np.abs(r[keep]).max()
-        assert np.abs(g[keep] - r[keep]).max() <= 2e-13 * scale, nm
+        assert np.abs(g[keep] - r[keep]).max() <= 1e-11 * scale, nm      # random fields: heavy cancellation
 
 
 def _check_terms(pkg, orc, solver, wl, ids=None):
@@ -155,7 +155,7 @@ def test_trphi_option(pkg, orc, solver):
         n1, pf1, th1, up1, dn1 = solver.trphi_option(r.rec, o.nbmu, o.rmu, r.ttot_tronc, r.tauout, 1, o.n0, o.wind,
                                                      o.ind_surf, 0, itrphi, phios, pas, 1)
         assert n0 == n1
-        assert np.allclose(up1[0], up0[0], rtol=1e-12) and np.allclose(dn1[0], dn0[0], rtol=1e-12)
+        assert np.allclose(up1[0], up0[0], rtol=0, atol=1e-5) and np.allclose(dn1[0], dn0[0], rtol=0, atol=1e-5)   # degrees; acos is ill-conditioned at 0/180
         for tb in (1, 2, 3):
             assert_stokes_close(up1[tb], up0[tb], "up table %d" % tb)
             assert_stokes_close(dn1[tb], dn0[tb], "down table %d" % tb)
