@@ -204,16 +204,19 @@ __global__ void k_pack(const KsetDev *ksets, const OpticsDev *optics)
     va = z * kerA(ks, which, a, b, N, W);
     if (ks.dual) vr = z * kerR(ks, op, which, a, b, N, W);
   }
-  ks.apackA[idx] = va;
+  // slab-major, k swizzled by 4*(row&3): one contiguous R*128-byte block per (tile, k-slab) lands in shared
+  // memory as a bank-conflict-free DMMA A tile (step_kernel.cu)
+  ks.apackA[((size_t)(co >> 4) * KP + ro) * 16 + ((co & 15) ^ (4 * (ro & 3)))] = va;
   if (ks.dual) ks.apackR[idx] = vr;
 
   if (co == 0) {                                   // one thread per row: first-order coefficients
-    double c1 = 0.0, c2 = 0.0, f1 = 0.0, f2 = 0.0;
+    double c1 = 0.0, c2 = 0.0, f1 = 0.0, f2 = 0.0, ur = 0.0;
     if (qo < 3 * N) {
       const int so = qo / N, k = qo % N + 1;
       const int jj = (dout == 0) ? k : -k;
       const double *xpl = ks.xpl, *xrl = ks.xpl + W, *xtl = ks.xpl + 2 * W;
       const double spl = xpl[N];                               // XPL(JK), JK = 0 (:2526)
+      ur = (so == 0) ? xpl[k + N] : (so == 1 ? xrl[k + N] : xtl[k + N]);
       if (so == 0)      { c2 = kerA(ks, 0, 0, jj, N, W);  if (ks.dual) c1 = ks.beta0 + op.beta2 * xpl[jj + N] * spl; }
       else if (so == 1) { c2 = kerA(ks, 1, 0, jj, N, W);  if (ks.dual) c1 = op.gamma2 * xrl[jj + N] * spl; }
       else              { c2 = -kerA(ks, 2, 0, jj, N, W); if (ks.dual) c1 = -(op.gamma2 * xtl[jj + N] * spl); }
@@ -232,8 +235,49 @@ __global__ void k_pack(const KsetDev *ksets, const OpticsDev *optics)
         }
       }
     }
-    ks.c1[ro] = c1; ks.c2[ro] = c2; ks.fz1[ro] = f1; ks.fz2[ro] = f2;
+    ks.c1[ro] = c1; ks.c2[ro] = c2; ks.fz1[ro] = f1; ks.fz2[ro] = f2; ks.urow[ro] = ur;
   }
+}
+
+// Rank-4 factorisation of the molecular part per direction block (SOS_OS.F:2859-2876: every element of the
+// Rayleigh phase matrix is built from the l=2 rows only, so for a fixed output direction block
+//   I rows:  A_R[I(k)] = v0 + XPL(k) v1,   Q rows: A_R[Q(k)] = XRL(k) v2,   U rows: A_R[U(k)] = XTL(k) v3 ).
+// The functionals v_r are read off the dense rows with the best-conditioned k.  One thread per (dir, column).
+__global__ void k_pack_v(const KsetDev *ksets, const OpticsDev *optics)
+{
+  const KsetDev ks = ksets[blockIdx.y];
+  if (!ks.dual) return;
+  const OpticsDev &op = optics[ks.optics];
+  const int N = op.nbmu, W = op.W, HB = op.HB, KP = op.KP;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * KP) return;
+  const int d = idx / KP, co = idx % KP;
+  const double *xpl = ks.xpl, *xrl = ks.xpl + W, *xtl = ks.xpl + 2 * W;
+  int k1 = 1, k2 = 1, kr = 1, kt = 1;
+  for (int k = 2; k <= N; ++k) {
+    if (xpl[k + N] > xpl[k1 + N]) k1 = k;
+    if (xpl[k + N] < xpl[k2 + N]) k2 = k;
+    if (fabs(xrl[k + N]) > fabs(xrl[kr + N])) kr = k;
+    if (fabs(xtl[k + N]) > fabs(xtl[kt + N])) kt = k;
+  }
+  const double *R = ks.apackR;
+  const size_t rowI = (size_t)(d * HB), rowQ = (size_t)(d * HB + N), rowU = (size_t)(d * HB + 2 * N);
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  const double m1 = R[(rowI + k1 - 1) * KP + co], m2 = R[(rowI + k2 - 1) * KP + co];
+  const double p1 = xpl[k1 + N], p2 = xpl[k2 + N];
+  if (ks.beta0 == 0.0) {                           // the isotropic term exists for the Fourier order 0 only (:890)
+    const int kb = (fabs(p1) >= fabs(p2)) ? k1 : k2;
+    const double pb = xpl[kb + N];
+    if (pb != 0.0) v[1] = R[(rowI + kb - 1) * KP + co] / pb;
+  } else if (p1 != p2) {
+    v[1] = (m1 - m2) / (p1 - p2);
+    v[0] = m1 - p1 * v[1];
+  } else v[0] = m1;
+  if (xrl[kr + N] != 0.0) v[2] = R[(rowQ + kr - 1) * KP + co] / xrl[kr + N];
+  if (xtl[kt + N] != 0.0) v[3] = R[(rowU + kt - 1) * KP + co] / xtl[kt + N];
+  double *vp = ks.vpack + (size_t)d * 8 * KP;
+  for (int r = 0; r < 8; ++r)
+    vp[((size_t)(co >> 4) * 8 + r) * 16 + ((co & 15) ^ (4 * (r & 3)))] = (r < 4) ? v[r] : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -503,6 +547,8 @@ void sos_launch_pack(const KsetDev *ksets, const OpticsDev *optics, int nkset, i
   if (nkset <= 0) return;
   dim3 grid((unsigned)(((size_t)maxKP * maxKP + 255) / 256), nkset);
   k_pack<<<grid, 256, 0, st>>>(ksets, optics);
+  dim3 gridv((unsigned)((2 * maxKP + 127) / 128), nkset);
+  k_pack_v<<<gridv, 128, 0, st>>>(ksets, optics);
 }
 void sos_launch_att(const TermDev *terms, const OpticsDev *optics, int nterm, int max_elems, cudaStream_t st)
 {

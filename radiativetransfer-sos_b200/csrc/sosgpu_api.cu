@@ -468,7 +468,7 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
           ksets.push_back(k);
           koff.push_back(kbytes);
           const size_t W = ho.W, KP = ho.KP;
-          kbytes += al(3 * (ho.os_nb + 2) * W * 8) + al(6 * W * W * 8) + al(3 * W * 8) + al(KP * KP * 8) * (k.dual ? 2 : 1) + 4 * al(KP * 8);
+          kbytes += al(3 * (ho.os_nb + 2) * W * 8) + al(6 * W * W * 8) + al(3 * W * 8) + al(KP * KP * 8) * (k.dual ? 2 : 1) + 5 * al(KP * 8) + al(16 * KP * 8);
         } else kid = itk->second;
         (s <= 2 ? has_dual : has_single) = true;
         ItemDev it{};
@@ -512,6 +512,8 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
       k.c2 = (double *)p; p += al(KP * 8);
       k.fz1 = (double *)p; p += al(KP * 8);
       k.fz2 = (double *)p; p += al(KP * 8);
+      k.urow = (double *)p; p += al(KP * 8);
+      k.vpack = (double *)p; p += al(16 * KP * 8);
     }
     for (size_t i = 0; i < nitem; ++i) {
       ItemDev &it = items[i];
@@ -837,7 +839,7 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
   auto rup = [&](size_t x) { return (x + al - 1) / al * al; };
   KsetDev ks{};
   ks.optics = 0; ks.is = is; ks.dual = (is <= 2) ? 1 : 0; ks.beta0 = (is == 0) ? 1.0 : 0.0;
-  const size_t kbytes = rup(3 * (os_nb + 2) * W * 8) + rup(6 * W * W * 8) + rup(3 * W * 8) + 2 * rup((size_t)KP * KP * 8) + 4 * rup(KP * 8);
+  const size_t kbytes = rup(3 * (os_nb + 2) * W * 8) + rup(6 * W * W * 8) + rup(3 * W * 8) + 2 * rup((size_t)KP * KP * 8) + 5 * rup(KP * 8) + rup(16 * KP * 8);
   char *kp = nullptr;
   CK(cudaMalloc(&kp, kbytes));
   CK(cudaMemset(kp, 0, kbytes));
@@ -851,6 +853,8 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
   ks.c2 = (double *)p; p += rup(KP * 8);
   ks.fz1 = (double *)p; p += rup(KP * 8);
   ks.fz2 = (double *)p; p += rup(KP * 8);
+  ks.urow = (double *)p; p += rup(KP * 8);
+  ks.vpack = (double *)p; p += rup(16 * KP * 8);
   KsetDev *dks = nullptr;
   CK(cudaMalloc(&dks, sizeof(KsetDev)));
   CK(cudaMemcpy(dks, &ks, sizeof(ks), cudaMemcpyHostToDevice));

@@ -63,7 +63,10 @@ struct KsetDev {              // kernel set of one (optics, Fourier order)
   double *basis;              // [3][(os_nb+2)][W]  PSL,RSL,TSL(-1:NB,-N:N)
   double *ker;                // [6][W*W] BP,GR,GT,ARR,ART,ATT   (j,k) at [(k+N)*W + (j+N)]
   double *xpl;                // [3][W] XPL,XRL,XTL
-  double *apackA, *apackR;    // [KP][KP] row-major, 0.5*GA(j)*sign*element
+  double *apackA;             // [KP/16 slabs][KP rows][16] slab-major, k swizzled by 4*(row&3): 0.5*GA(j)*sign*element
+  double *apackR;             // [KP][KP] row-major molecular part (dense; source of the rank-4 factors)
+  double *vpack;              // [2 dirs][KP/16 slabs][8][16] swizzled: functionals V of the rank-4 molecular part
+  double *urow;               // [KP] XPL/XRL/XTL(k) of each packed row (I/Q/U rows): J_R = T0 + urow*T_type
   double *c1, *c2;            // [KP] order-1 row coefficients (Rayleigh / aerosol)
   double *fz1, *fz2;          // [KP] flat-sea order-1 row coefficients
 };
@@ -74,7 +77,7 @@ extern "C" {
 #endif
 void sos_launch_basis(const KsetDev *ksets, const OpticsDev *optics, int nkset, cudaStream_t st);
 void sos_launch_kernels(const KsetDev *ksets, const OpticsDev *optics, int nkset, int maxW, cudaStream_t st);
-void sos_launch_pack(const KsetDev *ksets, const OpticsDev *optics, int nkset, int maxKP, cudaStream_t st);
+void sos_launch_pack(const KsetDev *ksets, const OpticsDev *optics, int nkset, int maxKP, cudaStream_t st);   // 2 kernels
 void sos_launch_att(const TermDev *terms, const OpticsDev *optics, int nterm, int max_elems, cudaStream_t st);
 void sos_launch_init(ItemDev *items, const TermDev *terms, const OpticsDev *optics, int nitem, cudaStream_t st);
 void sos_launch_test(ItemDev *items, const TermDev *terms, const OpticsDev *optics,

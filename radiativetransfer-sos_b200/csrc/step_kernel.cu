@@ -3,7 +3,13 @@
 // One launch advances every active (term, Fourier order) item by one scattering order:
 //   J(level, mu) = XDEL(level) * (A_A X_{n-1})(level) + YDEL(level) * (A_R X_{n-1})(level)
 //        = SOS_FSOURCE_ORDREIG (SOS_OS.F:2663-3017) as a dense FP64 contraction on DMMA tiles
-//          (mma.sync.m8n8k4.f64), operands staged through shared memory by a 3-stage cp.async pipeline;
+//          (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).  Operands are staged into shared memory by the TMA
+//          engine (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) through a 3-stage pipeline:
+//          A_A is stored slab-major and pre-swizzled in HBM (k_pack), so one 16 KB bulk copy per k-slab
+//          lands a conflict-free tile; the field chunk is copied row by row into padded rows.
+//          The molecular part A_R has rank <= 4 per direction block (only the l=2 Legendre rows, SOS_OS.F:2859-2876):
+//          it is carried as 4 extra functional rows V (T = V X, one extra DMMA per k-step and warp) and
+//          expanded in the epilogue: J_R = u0 T0 + u(k) T_type.
 //   X_n = SOS_INTEGR_EPOPT(J, boundary values)  (SOS_OS.F:2222-2357), run on the tile while it is still
 //          on chip: the source function never goes to HBM;
 //   boundary values at the ground for mu>0 (Lambert / BRDF-BPDF quadrature / flat Fresnel,
@@ -12,19 +18,51 @@
 //          plus SOS_FSOURCE_DIFF_FRESNEL1 for a flat sea) and the boundary values are SOS_OS.F:970-992.
 //
 // CTA tile: up to 128 rows (8 warps x 16 rows) of one direction block x 64 levels; the level chunks are
-// swept in the direction of propagation so the recurrence state stays in registers.
+// swept in the direction of propagation so the recurrence state stays in registers.  Two CTAs are
+// resident per SM (<= 128 registers, ~83 KB shared memory each) so that one CTA's recurrence epilogue
+// overlaps the other's DMMA main loop.
 #include "sosgpu_internal.h"
 #include <math.h>
+#include <algorithm>
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool pred)
+#define STAGE_A_BYTES(rows) ((rows) * SOS_KB * 8)
+#define STAGE_V_BYTES (8 * SOS_KB * 8)
+#define STAGE_B_BYTES (SOS_KB * SOS_SB * 8)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
 {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int sz = pred ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int NKEEP>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  const unsigned addr = smem_u32(bar);
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// TMA engine, non-tensor bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, double b)
 {
@@ -33,32 +71,31 @@ __device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, doub
                : "d"(a), "d"(b));
 }
 
-struct StepSmem {
-  double *sA, *sA2, *sB, *sJ, *sG;
-};
-
-template <int DUAL, int ORDER1>
-__global__ void __launch_bounds__(256, 1)
+template <int LR, int ORDER1>
+__global__ void __launch_bounds__(256, 2)
 k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, const OpticsDev *__restrict__ optics,
-       const KsetDev *__restrict__ ksets, const int *__restrict__ list, int tiles_per_dir, int want_dual,
+       const KsetDev *__restrict__ ksets, const int *__restrict__ list, int tiles_per_dir, int want_lr,
        double *__restrict__ jdump)
 {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nw_launch = blockDim.x >> 5;
   const int rows_max = nw_launch * 16;
-  // carve shared memory
-  double *sA = smem;
-  double *sA2 = sA + (ORDER1 ? 0 : SOS_STAGES * rows_max * SOS_SA);
-  double *sB = sA2 + ((DUAL && !ORDER1) ? SOS_STAGES * rows_max * SOS_SA : 0);
-  double *sJ = sB + (ORDER1 ? 0 : SOS_STAGES * SOS_KB * SOS_SB);
-  double *sG = sJ + rows_max * SOS_SJ;
+  // ---- shared memory carve: [pipeline stages | aliased by the staging tile sJ] sT sG mbar ----
+  const int stage_bytes = STAGE_A_BYTES(rows_max) + (LR ? STAGE_V_BYTES : 0) + STAGE_B_BYTES;
+  const int pipe_bytes = ORDER1 ? 0 : SOS_STAGES * stage_bytes;
+  const int sj_bytes = rows_max * SOS_SJ * 8;
+  const int region = (pipe_bytes > sj_bytes ? pipe_bytes : sj_bytes);
+  double *sJ = reinterpret_cast<double *>(smem_raw);
+  double *sT = reinterpret_cast<double *>(smem_raw + region);           // [4][64] Rayleigh functionals of the chunk
+  double *sG = sT + 4 * SOS_CH;                                         // [3N] ground values of the downward field
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(sG + 3 * 80);
 
   const int per_item = 2 * tiles_per_dir;
   const int ii = blockIdx.x / per_item, t = blockIdx.x % per_item;
   const int item = list ? list[ii] : ii;
   const ItemDev it = items[item];
   const KsetDev ks = ksets[it.kset];
-  if (!ORDER1 && (ks.dual != want_dual)) return;               // handled by the other instantiation
+  if (!ORDER1 && (ks.dual != want_lr)) return;                 // handled by the other instantiation
   const TermDev tm = terms[it.term];
   const OpticsDev &op = optics[tm.optics];
   const int N = op.nbmu, HB = op.HB, KP = op.KP, NT = tm.nt, L = NT + 1, LP = tm.LP;
@@ -71,10 +108,16 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
   const int R = ng * 16;
   const int r0 = dir * HB + g0 * 16;                             // first packed row of the tile
   const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
   const bool up = (dir == 0);
 
   const double *__restrict__ xprev = it.x[it.n & 1];
   double *__restrict__ xnext = ORDER1 ? it.x[1] : it.x[(it.n + 1) & 1];
+
+  if (!ORDER1 && tid == 0) {
+    for (int s = 0; s < SOS_STAGES; ++s) mbar_init(full + s, 1);
+    fence_proxy_async();                                         // make the inits visible to the async proxy
+  }
 
   // ---------------- prologue: boundary value of this thread's row (mu > 0 rows only) ----------------
   const int myrow = r0 + tid;                                    // scan threads: tid < R
@@ -121,106 +164,106 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
           bc = (so == 0) ? acc * rrmu + xr : acc * rrmu;
         }
         if (op.ifresnel == 1) {                                  // flat sea (SOS_OS.F:1225-1239)
-          const double gi = sG[kk - 1], gq = sG[N + kk - 1], gu = sG[2 * N + kk - 1];
-          if (so == 0) bc = bc + op.f11[kk] * gi + op.f12[kk] * gq;
-          else if (so == 1) bc = bc + op.f12[kk] * gi + op.f11[kk] * gq;
+          const double gi = sG[kk - 1], gqv = sG[N + kk - 1], gu = sG[2 * N + kk - 1];
+          if (so == 0) bc = bc + op.f11[kk] * gi + op.f12[kk] * gqv;
+          else if (so == 1) bc = bc + op.f12[kk] * gi + op.f11[kk] * gqv;
           else bc = bc + op.f33[kk] * gu;
         }
       }
     }
   }
+  __syncthreads();                                               // mbarrier inits visible to all threads
 
   // ---------------- level chunks, swept in the direction of propagation ----------------
   const int n_chunk = (L + SOS_CH - 1) / SOS_CH;
   const int n_slab = KP / SOS_KB;
-  const int T = ORDER1 ? n_chunk : n_chunk * n_slab;
-  const double *__restrict__ Ag = ks.apackA + (size_t)r0 * KP;
-  const double *__restrict__ Ag2 = DUAL ? ks.apackR + (size_t)r0 * KP : nullptr;
+  // slab-major pre-swizzled operands (k_pack): A[(slab*KP + row)*16 + ...], V[dir][(slab*8 + r)*16 + ...]
+  const double *__restrict__ Ag = ks.apackA + (size_t)r0 * SOS_KB;
+  const double *__restrict__ Vg = LR ? ks.vpack + (size_t)dir * 8 * KP : nullptr;
 
   double acc[2][8][2];
-  double acc2[DUAL ? 2 : 1][DUAL ? 8 : 1][2];
+  double tacc[2][2];                                             // T = V X blocks of this warp (ni = wr + u*nw_launch, nw_launch >= 4)
   double z = 0.0, sprev = 0.0;                                    // recurrence state of this thread's row
+  unsigned it_count = 0;                                          // global slab counter (mbarrier phases)
 
-  auto issue = [&](int tt) {
-    const int stage = tt % SOS_STAGES;
-    const int chunk = tt / n_slab, slab = tt % n_slab;
-    const int ci = up ? (n_chunk - 1 - chunk) : chunk;
-    const int c0 = ci * SOS_CH, k0 = slab * SOS_KB;
-    double *a = sA + stage * rows_max * SOS_SA;
-    for (int idx = tid; idx < R * (SOS_KB / 2); idx += blockDim.x) {
-      const int row = idx >> 3, c = idx & 7;
-      cp_async16(a + row * SOS_SA + c * 2, Ag + (size_t)row * KP + k0 + c * 2, true);
-    }
-    if (DUAL) {
-      double *a2 = sA2 + stage * rows_max * SOS_SA;
-      for (int idx = tid; idx < R * (SOS_KB / 2); idx += blockDim.x) {
-        const int row = idx >> 3, c = idx & 7;
-        cp_async16(a2 + row * SOS_SA + c * 2, Ag2 + (size_t)row * KP + k0 + c * 2, true);
-      }
-    }
-    double *b = sB + stage * SOS_KB * SOS_SB;
-    for (int idx = tid; idx < SOS_KB * (SOS_CH / 2); idx += blockDim.x) {
-      const int krow = idx >> 5, c = idx & 31;
-      const int col = c0 + 2 * c;
-      const bool ok = col < LP;
-      cp_async16(b + krow * SOS_SB + 2 * c, ok ? (xprev + (size_t)(k0 + krow) * LP + col) : xprev, ok);
-    }
-  };
-
-  if (!ORDER1) {
-    for (int tt = 0; tt < SOS_STAGES - 1; ++tt) {
-      if (tt < T) issue(tt);
-      cp_async_commit();
-    }
-  }
-
-  for (int tt = 0; tt < T; ++tt) {
-    const int chunk = ORDER1 ? tt : tt / n_slab;
-    const int slab = ORDER1 ? 0 : tt % n_slab;
+  for (int chunk = 0; chunk < n_chunk; ++chunk) {
     const int ci = up ? (n_chunk - 1 - chunk) : chunk;
     const int c0 = ci * SOS_CH;
-    bool chunk_done = true;
 
     if (!ORDER1) {
-      cp_async_wait<SOS_STAGES - 2>();
-      __syncthreads();
-      if (tt + SOS_STAGES - 1 < T) issue(tt + SOS_STAGES - 1);
-      cp_async_commit();
-
-      if (slab == 0) {
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 8; ++ni) {
-            acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0;
-            if (DUAL) { acc2[mi][ni][0] = 0.0; acc2[mi][ni][1] = 0.0; }
-          }
+      const int ncol = min(SOS_CH, LP - c0);                       // valid (zero padded) columns of this chunk
+      const unsigned tx = (unsigned)(R * SOS_KB * 8 + (LR ? STAGE_V_BYTES : 0) + SOS_KB * ncol * 8);
+      auto issue = [&](int slab, unsigned cnt) {                   // executed by thread 0 only
+        const int stage = cnt % SOS_STAGES;
+        unsigned char *sp = smem_raw + stage * stage_bytes;
+        unsigned long long *bar = full + stage;
+        mbar_expect_tx(bar, tx);
+        bulk_g2s(sp, Ag + (size_t)slab * KP * SOS_KB, (unsigned)(R * SOS_KB * 8), bar);
+        sp += STAGE_A_BYTES(rows_max);
+        if (LR) { bulk_g2s(sp, Vg + (size_t)slab * 8 * SOS_KB, STAGE_V_BYTES, bar); sp += STAGE_V_BYTES; }
+        const double *xs = xprev + (size_t)slab * SOS_KB * LP + c0;
+        for (int kr = 0; kr < SOS_KB; ++kr)
+          bulk_g2s(sp + kr * SOS_SB * 8, xs + (size_t)kr * LP, (unsigned)(ncol * 8), bar);
+      };
+      if (tid == 0) {
+        fence_proxy_async();                                       // staging tile (generic writes) -> async writes
+        for (int s = 0; s < SOS_STAGES - 1 && s < n_slab; ++s) issue(s, it_count + s);
       }
-      if (wr < ng) {
-        const int stage = tt % SOS_STAGES;
-        const double *a = sA + stage * rows_max * SOS_SA + (wr * 16 + (lane >> 2)) * SOS_SA + (lane & 3);
-        const double *a2 = sA2 + stage * rows_max * SOS_SA + (wr * 16 + (lane >> 2)) * SOS_SA + (lane & 3);
-        const double *b = sB + stage * SOS_KB * SOS_SB + (lane & 3) * SOS_SB + (lane >> 2);
 #pragma unroll
-        for (int ks4 = 0; ks4 < SOS_KB / 4; ++ks4) {
-          const double a0 = a[ks4 * 4], a1 = a[8 * SOS_SA + ks4 * 4];
-          double ar0 = 0.0, ar1 = 0.0;
-          if (DUAL) { ar0 = a2[ks4 * 4]; ar1 = a2[8 * SOS_SA + ks4 * 4]; }
+      for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-          for (int ni = 0; ni < 8; ++ni) {
-            const double bv = b[ks4 * 4 * SOS_SB + ni * 8];
-            dmma8x8x4(acc[0][ni][0], acc[0][ni][1], a0, bv);
-            dmma8x8x4(acc[1][ni][0], acc[1][ni][1], a1, bv);
-            if (DUAL) {
-              dmma8x8x4(acc2[0][ni][0], acc2[0][ni][1], ar0, bv);
-              dmma8x8x4(acc2[1][ni][0], acc2[1][ni][1], ar1, bv);
+        for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+      tacc[0][0] = tacc[0][1] = tacc[1][0] = tacc[1][1] = 0.0;
+
+      for (int slab = 0; slab < n_slab; ++slab) {
+        const unsigned cnt = it_count + slab;
+        const int stage = cnt % SOS_STAGES;
+        mbar_wait(full + stage, (cnt / SOS_STAGES) & 1);
+        __syncthreads();                                           // everyone is done with stage (cnt-1)%S
+        if (tid == 0 && slab + SOS_STAGES - 1 < n_slab) issue(slab + SOS_STAGES - 1, cnt + SOS_STAGES - 1);
+        if (wr < ng || LR) {
+          const bool own = wr < ng;                                // warps beyond ng only help with T = V X
+          const unsigned char *sp = smem_raw + stage * stage_bytes;
+          const double *a = reinterpret_cast<const double *>(sp) + (wr * 16 + gq) * SOS_KB;
+          const double *v = reinterpret_cast<const double *>(sp + STAGE_A_BYTES(rows_max)) + gq * SOS_KB;
+          const double *b = reinterpret_cast<const double *>(sp + STAGE_A_BYTES(rows_max) + (LR ? STAGE_V_BYTES : 0)) + tq * SOS_SB + gq;
+          const int swz = 4 * (gq & 3);
+#pragma unroll
+          for (int ks4 = 0; ks4 < SOS_KB / 4; ++ks4) {
+            const int kc = (ks4 * 4 + tq) ^ swz;
+            if (own) {
+              const double a0 = a[kc], a1 = a[8 * SOS_KB + kc];
+              double bv[8];
+#pragma unroll
+              for (int ni = 0; ni < 8; ++ni) bv[ni] = b[ks4 * 4 * SOS_SB + ni * 8];
+#pragma unroll
+              for (int ni = 0; ni < 8; ++ni) {
+                dmma8x8x4(acc[0][ni][0], acc[0][ni][1], a0, bv[ni]);
+                dmma8x8x4(acc[1][ni][0], acc[1][ni][1], a1, bv[ni]);
+              }
+            }
+            if (LR) {                                              // T = V X: this warp's share of the 8 column blocks
+              const double av = v[kc];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int ni = wr + u * nw_launch;
+                if (ni < 8) dmma8x8x4(tacc[u][0], tacc[u][1], av, b[ks4 * 4 * SOS_SB + ni * 8]);
+              }
             }
           }
         }
       }
-      chunk_done = (slab == n_slab - 1);
+      it_count += n_slab;
+      __syncthreads();                                             // pipeline drained: stages may be reused as sJ
+      if (LR && gq < 4) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int ni = wr + u * nw_launch;
+          if (ni < 8) { sT[gq * SOS_CH + ni * 8 + 2 * tq] = tacc[u][0]; sT[gq * SOS_CH + ni * 8 + 2 * tq + 1] = tacc[u][1]; }
+        }
+      }
+      if (LR) __syncthreads();
     }
-    if (!chunk_done) continue;
 
     // ---------------- tile epilogue: source function -> staging tile ----------------
     if (ORDER1) {
@@ -241,19 +284,36 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       }
     } else {
       if (wr < ng) {
+        // Rayleigh expansion coefficients of this thread's two rows (SOS_OS.F:2859-2876 in factored form)
+        double u0[2] = {0.0, 0.0}, us[2] = {0.0, 0.0};
+        int ty[2] = {0, 0};
+        if (LR) {
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            const int qr = g0 * 16 + wr * 16 + mi * 8 + gq;        // row within the direction block
+            if (qr < 3 * N) {
+              ty[mi] = qr / N;
+              us[mi] = __ldg(ks.urow + dir * HB + qr);
+              u0[mi] = (ty[mi] == 0) ? 1.0 : 0.0;
+            }
+          }
+        }
 #pragma unroll
         for (int ni = 0; ni < 8; ++ni) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int col = ni * 8 + 2 * (lane & 3) + e;
+            const int col = ni * 8 + 2 * tq + e;
             const int level = c0 + col;
             double xd = 0.0, yd = 0.0;
-            if (level < L) { xd = __ldg(tm.xdel + level); if (DUAL) yd = __ldg(tm.ydel + level); }
+            if (level < L) { xd = __ldg(tm.xdel + level); if (LR) yd = __ldg(tm.ydel + level); }
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) {
-              double v = xd * acc[mi][ni][e];
-              if (DUAL) v = v + yd * acc2[mi][ni][e];
-              sJ[(wr * 16 + mi * 8 + (lane >> 2)) * SOS_SJ + col] = v;
+              double v = (level < L) ? xd * acc[mi][ni][e] : 0.0;
+              if (LR && level < L) {
+                const double tsel = sT[(ty[mi] + 1) * SOS_CH + col];
+                v = v + yd * (u0[mi] * sT[col] + us[mi] * tsel);
+              }
+              sJ[(wr * 16 + mi * 8 + gq) * SOS_SJ + col] = v;
             }
           }
         }
@@ -274,36 +334,35 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
     if (rowvalid) {
       double *js = sJ + tid * SOS_SJ;
       const double *att = tm.att + (kk - 1);
+      const int hi = min(c0 + SOS_CH - 1, NT);
       if (up) {                                                  // SOS_OS.F:2279-2310
-        const int hi = min(c0 + SOS_CH - 1, NT);
-        for (int level = hi; level >= c0; --level) {
+        int level = hi;
+        if (level == NT) { const double s = js[level - c0]; z = bc; js[level - c0] = z; sprev = s; --level; }
+        double a = 0.0, dl = 0.0, iv = 0.0;
+        if (level >= c0) { a = __ldg(att + (size_t)level * N); dl = __ldg(tm.dt + level); iv = __ldg(tm.inv + level); }
+        for (; level >= c0; --level) {
+          const double ac = a, dc = dl, ic = iv;
+          if (level > c0) { a = __ldg(att + (size_t)(level - 1) * N); dl = __ldg(tm.dt + level - 1); iv = __ldg(tm.inv + level - 1); }
           const int col = level - c0;
           const double s = js[col];
-          if (level == NT) {
-            z = bc;
-          } else {
-            const double a = __ldg(att + (size_t)level * N);
-            const double dl = __ldg(tm.dt + level), iv = __ldg(tm.inv + level);
-            const double A = (sprev - s) * iv;
-            z = z * a + (1.0 - a) * (A * mu + s) - A * (a * dl);
-          }
+          const double A = (sprev - s) * ic;
+          z = z * ac + (1.0 - ac) * (A * mu + s) - A * (ac * dc);
           js[col] = z;
           sprev = s;
         }
       } else {                                                   // SOS_OS.F:2320-2354
-        const int hi = min(c0 + SOS_CH - 1, NT);
         const double rmuk = -mu;
-        for (int level = c0; level <= hi; ++level) {
+        int level = c0;
+        if (level == 0) { const double s = js[0]; z = 0.0; js[0] = 0.0; sprev = s; ++level; }
+        double a = 0.0, dl = 0.0, iv = 0.0;
+        if (level <= hi) { a = __ldg(att + (size_t)(level - 1) * N); dl = __ldg(tm.dt + level - 1); iv = __ldg(tm.inv + level - 1); }
+        for (; level <= hi; ++level) {
+          const double ac = a, dc = dl, ic = iv;
+          if (level < hi) { a = __ldg(att + (size_t)level * N); dl = __ldg(tm.dt + level); iv = __ldg(tm.inv + level); }
           const int col = level - c0;
           const double s = js[col];
-          if (level == 0) {
-            z = 0.0;
-          } else {
-            const double a = __ldg(att + (size_t)(level - 1) * N);
-            const double dl = __ldg(tm.dt + level - 1), iv = __ldg(tm.inv + level - 1);
-            const double A = (s - sprev) * iv;
-            z = z * a + (1.0 - a) * (A * rmuk + s) + A * (a * dl);
-          }
+          const double A = (s - sprev) * ic;
+          z = z * ac + (1.0 - ac) * (A * rmuk + s) + A * (ac * dc);
           js[col] = z;
           sprev = s;
         }
@@ -317,20 +376,17 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       const int level = c0 + col, row = r0 + rowl;
       if (level < L && (row - dir * HB) < 3 * N) xnext[(size_t)row * LP + level] = sJ[rowl * SOS_SJ + col];
     }
+    __syncthreads();                                             // sJ is free again (next chunk's TMA may overwrite it)
   }
 }
 
-static size_t step_smem_bytes(int nw, int dual, int order1)
+static size_t step_smem_bytes(int nw, int lr, int order1)
 {
   const size_t rows = (size_t)nw * 16;
-  size_t d = 0;
-  if (!order1) {
-    d += (size_t)SOS_STAGES * rows * SOS_SA * (dual ? 2 : 1);
-    d += (size_t)SOS_STAGES * SOS_KB * SOS_SB;
-  }
-  d += rows * SOS_SJ;
-  d += 3 * 80;
-  return d * sizeof(double);
+  const size_t stage = STAGE_A_BYTES(rows) + (lr ? STAGE_V_BYTES : 0) + STAGE_B_BYTES;
+  const size_t pipe = order1 ? 0 : SOS_STAGES * stage;
+  const size_t sj = rows * SOS_SJ * 8;
+  return (pipe > sj ? pipe : sj) + (4 * SOS_CH + 3 * 80) * 8 + SOS_STAGES * 8 + 128;
 }
 
 extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const OpticsDev *optics,
@@ -340,7 +396,7 @@ extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const
   if (nitem <= 0) return 0;
   static bool attr_done = false;
   if (!attr_done) {
-    const int big = 227 * 1024;
+    const int big = 160 * 1024;
     cudaFuncSetAttribute(k_step<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_step<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_step<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -348,7 +404,7 @@ extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const
   }
   const int groups = maxHB / 16;
   const int tiles_per_dir = (groups + SOS_MAXW - 1) / SOS_MAXW;
-  const int nw = (groups + tiles_per_dir - 1) / tiles_per_dir;
+  const int nw = std::max((groups + tiles_per_dir - 1) / tiles_per_dir, 4);   // >= 4 warps: T = V X needs 8 column blocks / 2
   const dim3 grid((unsigned)nitem * 2 * tiles_per_dir);
   const dim3 block(nw * 32);
   int launches = 0;
@@ -356,12 +412,11 @@ extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const
     k_step<0, 1><<<grid, block, step_smem_bytes(nw, 0, 1), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, jdump);
     launches = 1;
   } else {
-    // items whose Fourier order carries a Rayleigh part (is <= 2) run the dual-accumulator instantiation
-    if (mode & 1) {
+    if (mode & 1) {                                              // aerosol-only Fourier orders (is > 2)
       k_step<0, 0><<<grid, block, step_smem_bytes(nw, 0, 0), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, jdump);
       ++launches;
     }
-    if (mode & 2) {
+    if (mode & 2) {                                              // is <= 2: molecular rank-4 part carried along
       k_step<1, 0><<<grid, block, step_smem_bytes(nw, 1, 0), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 1, jdump);
       ++launches;
     }
