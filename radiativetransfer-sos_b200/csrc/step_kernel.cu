@@ -39,6 +39,10 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
 {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
   const unsigned addr = smem_u32(bar);
@@ -89,6 +93,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
   double *sT = reinterpret_cast<double *>(smem_raw + region);           // [4][64] Rayleigh functionals of the chunk
   double *sG = sT + 4 * SOS_CH;                                         // [3N] ground values of the downward field
   unsigned long long *full = reinterpret_cast<unsigned long long *>(sG + 3 * 80);
+  unsigned long long *empty = full + SOS_STAGES;
 
   const int per_item = 2 * tiles_per_dir;
   const int ii = blockIdx.x / per_item, t = blockIdx.x % per_item;
@@ -115,7 +120,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
   double *__restrict__ xnext = ORDER1 ? it.x[1] : it.x[(it.n + 1) & 1];
 
   if (!ORDER1 && tid == 0) {
-    for (int s = 0; s < SOS_STAGES; ++s) mbar_init(full + s, 1);
+    for (int s = 0; s < SOS_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(full + SOS_STAGES + s, nw_launch); }
     fence_proxy_async();                                         // make the inits visible to the async proxy
   }
 
@@ -218,9 +223,12 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       for (int slab = 0; slab < n_slab; ++slab) {
         const unsigned cnt = it_count + slab;
         const int stage = cnt % SOS_STAGES;
+        // refill the stage used one iteration ago once every warp has released it (empty barrier), no CTA barrier
+        if (tid == 0 && slab + SOS_STAGES - 1 < n_slab) {
+          if (slab >= 1) mbar_wait(empty + (cnt - 1) % SOS_STAGES, ((cnt - 1) / SOS_STAGES) & 1);
+          issue(slab + SOS_STAGES - 1, cnt + SOS_STAGES - 1);
+        }
         mbar_wait(full + stage, (cnt / SOS_STAGES) & 1);
-        __syncthreads();                                           // everyone is done with stage (cnt-1)%S
-        if (tid == 0 && slab + SOS_STAGES - 1 < n_slab) issue(slab + SOS_STAGES - 1, cnt + SOS_STAGES - 1);
         if (wr < ng || LR) {
           const bool own = wr < ng;                                // warps beyond ng only help with T = V X
           const unsigned char *sp = smem_raw + stage * stage_bytes;
@@ -252,6 +260,8 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
             }
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);                 // this warp no longer reads the stage
       }
       it_count += n_slab;
       __syncthreads();                                             // pipeline drained: stages may be reused as sJ
@@ -338,33 +348,50 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       if (up) {                                                  // SOS_OS.F:2279-2310
         int level = hi;
         if (level == NT) { const double s = js[level - c0]; z = bc; js[level - c0] = z; sprev = s; --level; }
-        double a = 0.0, dl = 0.0, iv = 0.0;
-        if (level >= c0) { a = __ldg(att + (size_t)level * N); dl = __ldg(tm.dt + level); iv = __ldg(tm.inv + level); }
-        for (; level >= c0; --level) {
-          const double ac = a, dc = dl, ic = iv;
-          if (level > c0) { a = __ldg(att + (size_t)(level - 1) * N); dl = __ldg(tm.dt + level - 1); iv = __ldg(tm.inv + level - 1); }
-          const int col = level - c0;
-          const double s = js[col];
-          const double A = (sprev - s) * ic;
-          z = z * ac + (1.0 - ac) * (A * mu + s) - A * (ac * dc);
-          js[col] = z;
-          sprev = s;
+        // attenuation table 4 levels ahead (L2 latency), layer thickness tables are L1-resident broadcasts
+        double aq[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) aq[p] = (level - p >= c0) ? __ldg(att + (size_t)(level - p) * N) : 0.0;
+        for (; level >= c0; level -= 4) {
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int lv = level - p;
+            const double ac = aq[p];
+            if (lv - 4 >= c0) aq[p] = __ldg(att + (size_t)(lv - 4) * N);
+            if (lv >= c0) {
+              const double dc = __ldg(tm.dt + lv), ic = __ldg(tm.inv + lv);
+              const int col = lv - c0;
+              const double s = js[col];
+              const double A = (sprev - s) * ic;
+              z = z * ac + (1.0 - ac) * (A * mu + s) - A * (ac * dc);
+              js[col] = z;
+              sprev = s;
+            }
+          }
         }
       } else {                                                   // SOS_OS.F:2320-2354
         const double rmuk = -mu;
         int level = c0;
         if (level == 0) { const double s = js[0]; z = 0.0; js[0] = 0.0; sprev = s; ++level; }
-        double a = 0.0, dl = 0.0, iv = 0.0;
-        if (level <= hi) { a = __ldg(att + (size_t)(level - 1) * N); dl = __ldg(tm.dt + level - 1); iv = __ldg(tm.inv + level - 1); }
-        for (; level <= hi; ++level) {
-          const double ac = a, dc = dl, ic = iv;
-          if (level < hi) { a = __ldg(att + (size_t)level * N); dl = __ldg(tm.dt + level); iv = __ldg(tm.inv + level); }
-          const int col = level - c0;
-          const double s = js[col];
-          const double A = (s - sprev) * ic;
-          z = z * ac + (1.0 - ac) * (A * rmuk + s) + A * (ac * dc);
-          js[col] = z;
-          sprev = s;
+        double aq[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) aq[p] = (level + p <= hi) ? __ldg(att + (size_t)(level + p - 1) * N) : 0.0;
+        for (; level <= hi; level += 4) {
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int lv = level + p;
+            const double ac = aq[p];
+            if (lv + 4 <= hi) aq[p] = __ldg(att + (size_t)(lv + 3) * N);
+            if (lv <= hi) {
+              const double dc = __ldg(tm.dt + lv - 1), ic = __ldg(tm.inv + lv - 1);
+              const int col = lv - c0;
+              const double s = js[col];
+              const double A = (s - sprev) * ic;
+              z = z * ac + (1.0 - ac) * (A * rmuk + s) + A * (ac * dc);
+              js[col] = z;
+              sprev = s;
+            }
+          }
         }
       }
     }
@@ -386,7 +413,7 @@ static size_t step_smem_bytes(int nw, int lr, int order1)
   const size_t stage = STAGE_A_BYTES(rows) + (lr ? STAGE_V_BYTES : 0) + STAGE_B_BYTES;
   const size_t pipe = order1 ? 0 : SOS_STAGES * stage;
   const size_t sj = rows * SOS_SJ * 8;
-  return (pipe > sj ? pipe : sj) + (4 * SOS_CH + 3 * 80) * 8 + SOS_STAGES * 8 + 128;
+  return (pipe > sj ? pipe : sj) + (4 * SOS_CH + 3 * 80) * 8 + 2 * SOS_STAGES * 8 + 128;
 }
 
 extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const OpticsDev *optics,
