@@ -208,7 +208,8 @@ static int prep_term(const sosgpu_term &t, const HostOptics &o, HostTerm &h, boo
       h.tauout = (1 - h.zz) * h.h[j - 1] + h.zz * h.h[j];
     }
   }
-  h.dt.resize(nt); h.inv.resize(nt); h.ch.resize(nt + 1); h.cf.resize(nt + 1);
+  h.dt.assign(nt + 2, 0.0); h.inv.assign(nt + 2, 0.0);           // +2: TMA copies of the tables are 16-byte granular
+  h.ch.resize(nt + 1); h.cf.resize(nt + 1);
   for (int i = 0; i < nt; ++i) { h.dt[i] = h.h[i + 1] - h.h[i]; h.inv[i] = 1.0 / h.dt[i]; }
   for (int i = 0; i <= nt; ++i) h.ch[i] = std::exp(-h.h[i] / (-o.tab)) / 4.0;   // SOS_OS.F:837-839
   h.eground = std::exp(h.h[nt] / o.tab);
@@ -293,7 +294,7 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     size_t *o = &t_off[i * 7];
     o[0] = ar.putv(h.h); o[1] = ar.putv(h.xdel); o[2] = ar.putv(h.ydel); o[3] = ar.putv(h.dt);
     o[4] = ar.putv(h.inv); o[5] = ar.putv(h.ch); o[6] = ar.putv(h.cf);
-    att_off[i] = att_total; att_total += (size_t)h.nt * b->ho[h.optics].N;
+    att_off[i] = att_total; att_total += (((size_t)(h.nt + 2) * b->ho[h.optics].N + 1) & ~(size_t)1);   // 16-byte aligned, 2 pad rows
     i4_off[i] = i4_total; i4_total += (size_t)12 * b->ho[h.optics].N;
   }
   b->i4_total = i4_total;
@@ -581,6 +582,7 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
       float ms = 0.f;
       CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
       b->stats.step_ms += ms;
+      if (getenv("SOS_TRACE")) fprintf(stderr, "wave s0=%d ws=%d ig=%d active=%d step_ms=%.3f\n", s0, ws, ig, ncur, ms);
       ncur = b->h_count[0];
       cur ^= 1;
     }

@@ -24,6 +24,7 @@
 #include "sosgpu_internal.h"
 #include <math.h>
 #include <algorithm>
+#include <cstdlib>
 
 #define STAGE_A_BYTES(rows) ((rows) * SOS_KB * 8)
 #define STAGE_V_BYTES (8 * SOS_KB * 8)
@@ -38,6 +39,11 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
 {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// timing experiments: account bytes as transferred without moving them
+__device__ __forceinline__ void mbar_expect_tx_only_dummy(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 {
@@ -78,8 +84,8 @@ __device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, doub
 template <int LR, int ORDER1>
 __global__ void __launch_bounds__(256, 2)
 k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, const OpticsDev *__restrict__ optics,
-       const KsetDev *__restrict__ ksets, const int *__restrict__ list, int tiles_per_dir, int want_lr,
-       double *__restrict__ jdump)
+       const KsetDev *__restrict__ ksets, const int *__restrict__ list, int tiles_per_dir, int want_lr, int att_cap,
+       double *__restrict__ jdump, int dbg)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nw_launch = blockDim.x >> 5;
@@ -94,6 +100,13 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
   double *sG = sT + 4 * SOS_CH;                                         // [3N] ground values of the downward field
   unsigned long long *full = reinterpret_cast<unsigned long long *>(sG + 3 * 80);
   unsigned long long *empty = full + SOS_STAGES;
+  unsigned long long *tabbar = empty + SOS_STAGES;                      // per-chunk layer tables landed
+  double *sDt = reinterpret_cast<double *>(full + 2 * SOS_STAGES + 2);  // [<=66] layer optical thickness of the chunk
+  double *sInv = sDt + 72;                                              // [<=66] reciprocal
+  double *sXd = sInv + 72;                                              // [64] XDEL of the chunk's levels
+  double *sYd = sXd + 72;                                               // [64] YDEL
+  double *sU = sYd + 72;                                                // [128] urow of the tile's rows (LR)
+  double *sAtt = sU + 128;                                              // [<=66][N] exp(-dtau/mu_k) (when att_cap > 0)
 
   const int per_item = 2 * tiles_per_dir;
   const int ii = blockIdx.x / per_item, t = blockIdx.x % per_item;
@@ -119,11 +132,13 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
   const double *__restrict__ xprev = it.x[it.n & 1];
   double *__restrict__ xnext = ORDER1 ? it.x[1] : it.x[(it.n + 1) & 1];
 
-  if (!ORDER1 && tid == 0) {
+  if (tid == 0) {
     for (int s = 0; s < SOS_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(full + SOS_STAGES + s, nw_launch); }
+    mbar_init(tabbar, 1);
     fence_proxy_async();                                         // make the inits visible to the async proxy
   }
 
+  if (LR && tid < R) sU[tid] = (r0 + tid - dir * HB < 3 * N) ? ks.urow[r0 + tid] : 0.0;
   // ---------------- prologue: boundary value of this thread's row (mu > 0 rows only) ----------------
   const int myrow = r0 + tid;                                    // scan threads: tid < R
   const int q = (tid < R) ? (myrow - dir * HB) : 3 * N;
@@ -188,12 +203,28 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
 
   double acc[2][8][2];
   double tacc[2][2];                                             // T = V X blocks of this warp (ni = wr + u*nw_launch, nw_launch >= 4)
-  double z = 0.0, sprev = 0.0;                                    // recurrence state of this thread's row
+  double z = 0.0;                                                 // recurrence state of this thread's row (pass 2)
+  double scarry = 0.0;                                            // source function at the neighbouring level of the previous chunk (pass 1)
   unsigned it_count = 0;                                          // global slab counter (mbarrier phases)
 
   for (int chunk = 0; chunk < n_chunk; ++chunk) {
     const int ci = up ? (n_chunk - 1 - chunk) : chunk;
     const int c0 = ci * SOS_CH;
+    // layers touched by this chunk's recurrence: [c0-1, c0+63] clipped; even start so the bulk copies are 16-byte aligned
+    const int lb_al = max(c0 - 1, 0) & ~1;
+    const bool att_staged = (att_cap >= 66 * N);
+    if (tid == 0) {
+      const int le = min(c0 + SOS_CH - 1, NT - 1);
+      const int nrow = (le - lb_al + 2) & ~1;                      // even count (tables are padded by 2 rows)
+      fence_proxy_async();
+      const int nlev = (min(SOS_CH, L - c0) + 1) & ~1;             // levels of the chunk, even count
+      mbar_expect_tx(tabbar, (unsigned)(nrow * 16 + nlev * 16 + (att_staged ? nrow * N * 8 : 0)));
+      bulk_g2s(sXd, tm.xdel + c0, (unsigned)(nlev * 8), tabbar);
+      bulk_g2s(sYd, tm.ydel + c0, (unsigned)(nlev * 8), tabbar);
+      bulk_g2s(sDt, tm.dt + lb_al, (unsigned)(nrow * 8), tabbar);
+      bulk_g2s(sInv, tm.inv + lb_al, (unsigned)(nrow * 8), tabbar);
+      if (att_staged) bulk_g2s(sAtt, tm.att + (size_t)lb_al * N, (unsigned)(nrow * N * 8), tabbar);
+    }
 
     if (!ORDER1) {
       const int ncol = min(SOS_CH, LP - c0);                       // valid (zero padded) columns of this chunk
@@ -203,15 +234,17 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
         unsigned char *sp = smem_raw + stage * stage_bytes;
         unsigned long long *bar = full + stage;
         mbar_expect_tx(bar, tx);
-        bulk_g2s(sp, Ag + (size_t)slab * KP * SOS_KB, (unsigned)(R * SOS_KB * 8), bar);
+        if (dbg & 4) mbar_expect_tx_only_dummy(bar, (unsigned)(R * SOS_KB * 8));
+        else bulk_g2s(sp, Ag + (size_t)slab * KP * SOS_KB, (unsigned)(R * SOS_KB * 8), bar);
         sp += STAGE_A_BYTES(rows_max);
         if (LR) { bulk_g2s(sp, Vg + (size_t)slab * 8 * SOS_KB, STAGE_V_BYTES, bar); sp += STAGE_V_BYTES; }
         const double *xs = xprev + (size_t)slab * SOS_KB * LP + c0;
+        if (dbg & 8) bulk_g2s(sp, xprev, (unsigned)(SOS_KB * ncol * 8), bar);   // timing experiment: one copy of the same size
+        else
         for (int kr = 0; kr < SOS_KB; ++kr)
           bulk_g2s(sp + kr * SOS_SB * 8, xs + (size_t)kr * LP, (unsigned)(ncol * 8), bar);
       };
       if (tid == 0) {
-        fence_proxy_async();                                       // staging tile (generic writes) -> async writes
         for (int s = 0; s < SOS_STAGES - 1 && s < n_slab; ++s) issue(s, it_count + s);
       }
 #pragma unroll
@@ -229,7 +262,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
           issue(slab + SOS_STAGES - 1, cnt + SOS_STAGES - 1);
         }
         mbar_wait(full + stage, (cnt / SOS_STAGES) & 1);
-        if (wr < ng || LR) {
+        if ((wr < ng || LR) && !(dbg & 1)) {
           const bool own = wr < ng;                                // warps beyond ng only help with T = V X
           const unsigned char *sp = smem_raw + stage * stage_bytes;
           const double *a = reinterpret_cast<const double *>(sp) + (wr * 16 + gq) * SOS_KB;
@@ -265,6 +298,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       }
       it_count += n_slab;
       __syncthreads();                                             // pipeline drained: stages may be reused as sJ
+      mbar_wait(tabbar, chunk & 1);                                // XDEL/YDEL and layer tables of this chunk have landed
       if (LR && gq < 4) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -275,6 +309,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       if (LR) __syncthreads();
     }
 
+    if (dbg & 2) { __syncthreads(); continue; }                  // timing experiments only (SOS_DBG)
     // ---------------- tile epilogue: source function -> staging tile ----------------
     if (ORDER1) {
       __syncthreads();                                           // previous chunk's write-out has finished
@@ -303,7 +338,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
             const int qr = g0 * 16 + wr * 16 + mi * 8 + gq;        // row within the direction block
             if (qr < 3 * N) {
               ty[mi] = qr / N;
-              us[mi] = __ldg(ks.urow + dir * HB + qr);
+              us[mi] = sU[wr * 16 + mi * 8 + gq];
               u0[mi] = (ty[mi] == 0) ? 1.0 : 0.0;
             }
           }
@@ -315,7 +350,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
             const int col = ni * 8 + 2 * tq + e;
             const int level = c0 + col;
             double xd = 0.0, yd = 0.0;
-            if (level < L) { xd = __ldg(tm.xdel + level); if (LR) yd = __ldg(tm.ydel + level); }
+            if (level < L) { xd = sXd[col]; if (LR) yd = sYd[col]; }
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) {
               double v = (level < L) ? xd * acc[mi][ni][e] : 0.0;
@@ -340,57 +375,99 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       __syncthreads();
     }
 
-    // ---------------- SOS_INTEGR_EPOPT on the tile: one thread per row, sequential in level ----------------
+    // ---------------- SOS_INTEGR_EPOPT on the tile (SOS_OS.F:2279-2310 up, 2320-2354 down) ----------------
+    // The layer update is z <- z*a + c with c = (1-a)*(A*mu + S) -/+ A*(a*dtau), A = dS/dtau independent of z.
+    // Pass 1 (all threads, two per row, 32 levels each): c replaces S in the staging tile.
+    // Pass 2 (one thread per row): the bare recurrence, one dependent FMA per level.
+    {
+      const int row2 = tid >> 1, half = tid & 1;
+      const int q2 = (row2 < R) ? (r0 + row2 - dir * HB) : 3 * N;
+      const int hi = min(c0 + SOS_CH - 1, NT);
+      const int ncolv = hi - c0 + 1;                             // columns of this chunk that hold real levels
+      const bool valid2 = q2 < 3 * N;
+      double *js = sJ + (valid2 ? row2 : 0) * SOS_SJ;
+      const int k2 = valid2 ? q2 % N + 1 : 1;
+      const double mu2 = op.rmu[k2 + N];
+      const double *att = att_staged ? (sAtt + (k2 - 1) - (size_t)lb_al * N) : (tm.att + (k2 - 1));
+      const double *dtp = sDt - lb_al, *ivp = sInv - lb_al;
+      mbar_wait(tabbar, chunk & 1);                              // layer tables of this chunk have landed
+      const int lo_c = 32 * half, hi_c = min(32 * half + 31, ncolv - 1);
+      // boundary values are read before anybody overwrites them: column i needs S(i) and S(i+1) (up) / S(i-1) (down)
+      double bnd = scarry, s_edge = 0.0;
+      if (valid2) {
+        if (up) {
+          if (half == 0) bnd = (ncolv > 32) ? js[32] : 0.0;
+          s_edge = (hi_c >= lo_c) ? js[lo_c] : 0.0;
+        } else {
+          if (half == 1) bnd = js[31];
+          s_edge = (hi_c >= lo_c) ? js[hi_c] : 0.0;
+        }
+      }
+      __syncwarp();
+      if (valid2) {
+        double s = s_edge;
+        if (up) {
+          for (int i = lo_c; i <= hi_c; ++i) {                     // ascending: S(i+1) is still unmodified
+            const double sn = (i < hi_c) ? js[i + 1] : bnd;
+            const int lv = c0 + i;
+            if (lv < NT) {
+              const double a = att[(size_t)lv * N], dl = dtp[lv], iv = ivp[lv];
+              const double A = (sn - s) * iv;
+              js[i] = (1.0 - a) * (A * mu2 + s) - A * (a * dl);
+            }
+            s = sn;
+          }
+        } else {
+          const double rmuk = -mu2;
+          for (int i = hi_c; i >= lo_c; --i) {                     // descending: S(i-1) is still unmodified
+            const double sp = (i > lo_c) ? js[i - 1] : bnd;
+            const int lv = c0 + i;
+            if (lv > 0) {
+              const double a = att[(size_t)(lv - 1) * N], dl = dtp[lv - 1], iv = ivp[lv - 1];
+              const double A = (s - sp) * iv;
+              js[i] = (1.0 - a) * (A * rmuk + s) + A * (a * dl);
+            }
+            s = sp;
+          }
+        }
+      }
+      // the first (up) / last (down) column's S is the neighbour the next chunk needs: hand it to the partner thread
+      const double give = __shfl_sync(0xffffffffu, s_edge, up ? (lane & ~1) : (lane | 1));
+      if (half == (up ? 1 : 0)) scarry = give;
+    }
+    __syncthreads();
     if (rowvalid) {
       double *js = sJ + tid * SOS_SJ;
-      const double *att = tm.att + (kk - 1);
+      const double *att = att_staged ? (sAtt + (kk - 1) - (size_t)lb_al * N) : (tm.att + (kk - 1));
       const int hi = min(c0 + SOS_CH - 1, NT);
-      if (up) {                                                  // SOS_OS.F:2279-2310
+      if (up) {
         int level = hi;
-        if (level == NT) { const double s = js[level - c0]; z = bc; js[level - c0] = z; sprev = s; --level; }
-        // attenuation table 4 levels ahead (L2 latency), layer thickness tables are L1-resident broadcasts
+        if (level == NT) { z = bc; js[level - c0] = z; --level; }
         double aq[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) aq[p] = (level - p >= c0) ? __ldg(att + (size_t)(level - p) * N) : 0.0;
+        for (int p = 0; p < 4; ++p) aq[p] = (level - p >= c0) ? att[(size_t)(level - p) * N] : 0.0;
         for (; level >= c0; level -= 4) {
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const int lv = level - p;
             const double ac = aq[p];
-            if (lv - 4 >= c0) aq[p] = __ldg(att + (size_t)(lv - 4) * N);
-            if (lv >= c0) {
-              const double dc = __ldg(tm.dt + lv), ic = __ldg(tm.inv + lv);
-              const int col = lv - c0;
-              const double s = js[col];
-              const double A = (sprev - s) * ic;
-              z = z * ac + (1.0 - ac) * (A * mu + s) - A * (ac * dc);
-              js[col] = z;
-              sprev = s;
-            }
+            if (lv - 4 >= c0) aq[p] = att[(size_t)(lv - 4) * N];
+            if (lv >= c0) { z = z * ac + js[lv - c0]; js[lv - c0] = z; }
           }
         }
-      } else {                                                   // SOS_OS.F:2320-2354
-        const double rmuk = -mu;
+      } else {
         int level = c0;
-        if (level == 0) { const double s = js[0]; z = 0.0; js[0] = 0.0; sprev = s; ++level; }
+        if (level == 0) { z = 0.0; js[0] = 0.0; ++level; }
         double aq[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) aq[p] = (level + p <= hi) ? __ldg(att + (size_t)(level + p - 1) * N) : 0.0;
+        for (int p = 0; p < 4; ++p) aq[p] = (level + p <= hi) ? att[(size_t)(level + p - 1) * N] : 0.0;
         for (; level <= hi; level += 4) {
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const int lv = level + p;
             const double ac = aq[p];
-            if (lv + 4 <= hi) aq[p] = __ldg(att + (size_t)(lv + 3) * N);
-            if (lv <= hi) {
-              const double dc = __ldg(tm.dt + lv - 1), ic = __ldg(tm.inv + lv - 1);
-              const int col = lv - c0;
-              const double s = js[col];
-              const double A = (s - sprev) * ic;
-              z = z * ac + (1.0 - ac) * (A * rmuk + s) + A * (ac * dc);
-              js[col] = z;
-              sprev = s;
-            }
+            if (lv + 4 <= hi) aq[p] = att[(size_t)(lv + 3) * N];
+            if (lv <= hi) { z = z * ac + js[lv - c0]; js[lv - c0] = z; }
           }
         }
       }
@@ -407,13 +484,13 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
   }
 }
 
-static size_t step_smem_bytes(int nw, int lr, int order1)
+static size_t step_smem_bytes(int nw, int lr, int order1, int att_cap)
 {
   const size_t rows = (size_t)nw * 16;
   const size_t stage = STAGE_A_BYTES(rows) + (lr ? STAGE_V_BYTES : 0) + STAGE_B_BYTES;
   const size_t pipe = order1 ? 0 : SOS_STAGES * stage;
   const size_t sj = rows * SOS_SJ * 8;
-  return (pipe > sj ? pipe : sj) + (4 * SOS_CH + 3 * 80) * 8 + 2 * SOS_STAGES * 8 + 128;
+  return (pipe > sj ? pipe : sj) + (4 * SOS_CH + 3 * 80) * 8 + (2 * SOS_STAGES + 2) * 8 + (4 * 72 + 128 + att_cap) * 8 + 128;
 }
 
 extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const OpticsDev *optics,
@@ -432,19 +509,22 @@ extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const
   const int groups = maxHB / 16;
   const int tiles_per_dir = (groups + SOS_MAXW - 1) / SOS_MAXW;
   const int nw = std::max((groups + tiles_per_dir - 1) / tiles_per_dir, 4);   // >= 4 warps: T = V X needs 8 column blocks / 2
+  const int nmax = maxHB / 3;                                    // 3N <= HB
+  const int att_cap = (nmax <= 48) ? 66 * nmax : 0;            // stage the attenuation table of a chunk in smem when it fits
+  static const int dbg = getenv("SOS_DBG") ? atoi(getenv("SOS_DBG")) : 0;   // timing experiments only
   const dim3 grid((unsigned)nitem * 2 * tiles_per_dir);
   const dim3 block(nw * 32);
   int launches = 0;
   if (order1) {
-    k_step<0, 1><<<grid, block, step_smem_bytes(nw, 0, 1), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, jdump);
+    k_step<0, 1><<<grid, block, step_smem_bytes(nw, 0, 1, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, att_cap, jdump, dbg);
     launches = 1;
   } else {
     if (mode & 1) {                                              // aerosol-only Fourier orders (is > 2)
-      k_step<0, 0><<<grid, block, step_smem_bytes(nw, 0, 0), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, jdump);
+      k_step<0, 0><<<grid, block, step_smem_bytes(nw, 0, 0, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, att_cap, jdump, dbg);
       ++launches;
     }
     if (mode & 2) {                                              // is <= 2: molecular rank-4 part carried along
-      k_step<1, 0><<<grid, block, step_smem_bytes(nw, 1, 0), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 1, jdump);
+      k_step<1, 0><<<grid, block, step_smem_bytes(nw, 1, 0, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 1, att_cap, jdump, dbg);
       ++launches;
     }
   }
