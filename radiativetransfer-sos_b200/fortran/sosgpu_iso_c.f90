@@ -1,0 +1,78 @@
+!  sosgpu_iso_c.f90 -- ISO_C_BINDING interface of libsosgpu.so (include/sosgpu.h) for the Fortran host side.
+!
+!  COMPILE-UNTESTED: no Fortran compiler exists in the build image (SURVEY.md F2).  The C ABI it binds is
+!  exercised by the C++ shims (csrc/sosgpu_shims.cu) and the ctypes layer (api.py).
+!
+!  Two ways to drop the GPU path into SOS_PROC.F:
+!   (1) link libsosgpu.so *instead of* SOS_OS.o / SOS_AGGREGATE.o: it exports the F77 symbols sos_os_ and
+!       sos_aggregate_ with the reference's argument lists (SOS_OS.F:303-308, SOS_AGGREGATE.F:172-178);
+!       no source change in SOS.F / SOS_PROC.F.
+!   (2) replace the CKD loop SOS_PROC.F:3459-3594 by one call of sosgpu_solve_batch (all terms at once) using the
+!       interfaces below.
+module sosgpu_iso_c
+  use, intrinsic :: iso_c_binding
+  implicit none
+
+  type, bind(c) :: sosgpu_optics            ! SOS_PREPA_OS outputs + SOS scalars (include/sosgpu.h)
+    integer(c_int)    :: nbmu
+    type(c_ptr)       :: rmu, ga
+    integer(c_int)    :: n0
+    real(c_double)    :: tetas
+    integer(c_int)    :: os_nb
+    type(c_ptr)       :: alpha, beta, gamma, zeta
+    real(c_double)    :: a_trunc, piz, piztr, ron, rho
+    integer(c_int)    :: imat_surf, ifresnel
+    real(c_double)    :: ind_surf
+    type(c_ptr)       :: surf
+    integer(c_int)    :: n_surf_rec, igmax, ipolar
+    real(c_double)    :: zout
+  end type
+
+  type, bind(c) :: sosgpu_term              ! PROFIL_TMP content of one CKD term + its weight AIK
+    integer(c_int)    :: optics, group
+    real(c_double)    :: aik
+    integer(c_int)    :: nt
+    type(c_ptr)       :: zprof, h, pcaer, pcmol
+  end type
+
+  type, bind(c) :: sosgpu_term_out
+    type(c_ptr) :: rec, n_fourier, n_scatter, stop_reason, emoins, eplus, ttot_tronc, ttot_vrai, tauout, ier
+  end type
+
+  type, bind(c) :: sosgpu_group_out
+    type(c_ptr) :: rec, n_rec, emoins, eplus, ttot_tronc, ttot_vrai, tauout
+  end type
+
+  interface
+    integer(c_int) function sosgpu_create(ctx, device) bind(c, name="sosgpu_create")
+      import :: c_ptr, c_int
+      type(c_ptr), intent(out) :: ctx
+      integer(c_int), value :: device
+    end function
+    subroutine sosgpu_destroy(ctx) bind(c, name="sosgpu_destroy")
+      import :: c_ptr
+      type(c_ptr), value :: ctx
+    end subroutine
+    integer(c_int) function sosgpu_solve_batch(ctx, optics, noptics, terms, nterm, ngroup, rec_stride, wmax, &
+                                               part_only, term_out, group_out) bind(c, name="sosgpu_solve_batch")
+      import :: c_ptr, c_int, sosgpu_optics, sosgpu_term, sosgpu_term_out, sosgpu_group_out
+      type(c_ptr), value :: ctx
+      type(sosgpu_optics), intent(in) :: optics(*)
+      integer(c_int), value :: noptics
+      type(sosgpu_term), intent(in) :: terms(*)
+      integer(c_int), value :: nterm, ngroup, rec_stride, wmax, part_only
+      type(sosgpu_term_out), intent(in) :: term_out
+      type(sosgpu_group_out), intent(in) :: group_out
+    end function
+    integer(c_int) function sosgpu_trphi_option(ctx, rec, nrec, nbmu, rmu, tau, tauout, igli, n0, wind, ind_surf, &
+                                                ifresnel, itrphi, phios, pas_phi, ipolar, phi_fin, theta_fin, &
+                                                up, down, nphi_cap) bind(c, name="sosgpu_trphi_option")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx
+      real(c_double), intent(in) :: rec(*), rmu(*)
+      integer(c_int), value :: nrec, nbmu, igli, n0, ifresnel, itrphi, pas_phi, ipolar, nphi_cap
+      real(c_double), value :: tau, tauout, wind, ind_surf, phios
+      real(c_double), intent(out) :: phi_fin(*), theta_fin(*), up(*), down(*)
+    end function
+  end interface
+end module sosgpu_iso_c
