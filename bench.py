@@ -236,17 +236,28 @@ def main():
     t0 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(e2e_steps):
+        ta = time.perf_counter()
         b2 = solver.upload(wl, my_ids, groups=groups, ngroup=ngroup)
+        tb = time.perf_counter()
         tr, gr = solver.run(b2, want_terms=True, want_groups=True, want_rec=False, part_only=world > 1)
+        tc = time.perf_counter()
+        if os.environ.get("SOS_BENCH_VERBOSE"):
+            print("rank %d e2e: upload %.1f ms, run+download %.1f ms" % (rank, (tb - ta) * 1e3, (tc - tb) * 1e3), file=sys.stderr)
         if world > 1:
             p2, c2 = solver.group_buffer(b2)
 
             class _A2:
                 __cuda_array_interface__ = {"shape": (c2,), "typestr": "<f8", "data": (p2, False), "version": 2}
             dist.reduce(torch.as_tensor(_A2(), device=dev), dst=0, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize(dev)
+            if os.environ.get("SOS_BENCH_VERBOSE"):
+                print("rank %d e2e: reduce %.1f ms" % (rank, (time.perf_counter() - tc) * 1e3), file=sys.stderr)
         h2d += b2.h2d_bytes
         d2h += gr.rec.nbytes + tr.n_fourier.nbytes + tr.n_scatter.nbytes
+        td = time.perf_counter()
         b2.free()
+        if os.environ.get("SOS_BENCH_VERBOSE"):
+            print("rank %d e2e: free %.1f ms" % (rank, (time.perf_counter() - td) * 1e3), file=sys.stderr)
     sync_all()
     e2e_dt = (time.perf_counter() - t0) / e2e_steps
     e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)

@@ -169,6 +169,13 @@ int sosgpu_trphi_option(sosgpu_ctx *ctx, const double *rec, int nrec, int nbmu, 
                         int ifresnel, int itrphi, double phios, int pas_phi, int ipolar,
                         double *phi_fin, double *theta_fin, double *up, double *down, int nphi_cap);
 
+/* SOS_GLITTER (SOS_GLITTER.F:229) = SOS_GSF + SOS_MAT_FRESNEL + SOS_MAT_REFLEXION + SOS_NOYAUX_FRESNEL +
+ * SOS_MISE_FORMAT (SOS_SURFACE.F:1235,1708,2029,2307): Cox-Munk glitter reflection matrices, Fourier-decomposed,
+ * in the surface-file record layout.  rmu/chr: [2N+1] cosines / weights; surf: [os_nb+1][9][N][N] REAL*4;
+ * il_out (may be NULL): [N(N+1)/2] lengths IL of the G series per (theta1 >= theta2) pair. */
+int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
+                   int os_nm, double wind, double ind_surf, float *surf, int *il_out);
+
 /* ---- gfortran-ABI drop-in symbols (F77 by-reference, fixed SOS.h strides, hidden string lengths) */
 /* SOS_OS.F:303-308 */
 void sos_os_(const int *nbmu, double *rmu, const double *ga, const int *os_nb, const int *nt,

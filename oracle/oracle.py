@@ -218,3 +218,30 @@ def trphi_option(rec, nbmu, rmu, tau, tauout, igli, n0, wind, ind_surf, ifresnel
                                C.c_int(pas_phi), C.c_int(ipolar), _d(phi_fin), _d(theta), _d(up), _d(down),
                                C.c_int(cap))
     return n, phi_fin[:max(n, 0)], theta, up[:, :max(n, 0)], down[:, :max(n, 0)]
+
+
+def gsf_pair(c1, c2, sig, os_nm):
+    """SOS_GSF for one pair: (IL, E[0:os_nm+1])."""
+    e = np.zeros(os_nm + 1)
+    lib().orc_gsf_pair.restype = C.c_int
+    il = lib().orc_gsf_pair(C.c_double(c1), C.c_double(c2), C.c_double(sig), C.c_int(os_nm), _d(e))
+    return il, e
+
+
+def mat_fresnel(nbmu, rmu, chr_, ind, os_ns):
+    out = [np.zeros(os_ns + 1) for _ in range(4)]
+    lib().orc_mat_fresnel(C.c_int(nbmu), _d(_f64(rmu)), _d(_f64(chr_)), C.c_double(ind), C.c_int(os_ns),
+                          _d(out[0]), _d(out[1]), _d(out[2]), _d(out[3]))
+    return dict(alpha=out[0], beta=out[1], gamma=out[2], zeta=out[3])
+
+
+def glitter(nbmu, rmu, chr_, wind, ind, os_nb, os_ns, os_nm):
+    """SOS_GLITTER: surface-file records [os_nb+1, 9, N(J), N(I)] REAL*4 and the G-series lengths IL per pair."""
+    surf = np.zeros((os_nb + 1, 9, nbmu, nbmu), dtype=np.float32)
+    il = np.zeros(nbmu * (nbmu + 1) // 2, dtype=np.int32)
+    lib().orc_glitter.restype = C.c_int
+    ier = lib().orc_glitter(C.c_int(nbmu), _d(_f64(rmu)), _d(_f64(chr_)), C.c_double(wind), C.c_double(ind),
+                            C.c_int(os_nb), C.c_int(os_ns), C.c_int(os_nm), surf.ctypes.data_as(c_fp),
+                            il.ctypes.data_as(c_ip))
+    assert ier == 0
+    return surf, il

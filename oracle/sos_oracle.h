@@ -135,6 +135,16 @@ int orc_trphi_option(const double *rec, int nrec, int nbmu, const double *rmu, d
                      int itrphi, double phios, int pas_phi, int ipolar,
                      double *phi_fin, double *theta_fin, double *up, double *down, int nphi_cap);
 
+/* ---- rough-sea reflection matrices (sos_surface_oracle.c) ---- */
+/* SOS_GSF for one (theta1, theta2) pair (SOS_GLITTER.F:523-683); e has os_nm+1 entries; returns IL */
+int orc_gsf_pair(double c1, double c2, double sig, int os_nm, double *e);
+/* SOS_MAT_FRESNEL (SOS_SURFACE.F:1235-1603) incl. the 4(E15.8) round trip of RES_FRESNEL */
+void orc_mat_fresnel(int nbmu, const double *rmu, const double *chr, double ind, int os_ns,
+                     double *alpha, double *beta, double *gamma, double *zeta);
+/* SOS_GLITTER (SOS_GLITTER.F:229): surf [os_nb+1][9][N][N] REAL*4 in the surface-file record layout */
+int orc_glitter(int nbmu, const double *rmu, const double *chr, double wind, double ind,
+                int os_nb, int os_ns, int os_nm, float *surf, int *il_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -317,3 +317,13 @@ class Solver:
         if n < 0:
             self._check(n, "trphi_option")
         return n, phi_fin[:n], theta, up[:, :n], down[:, :n]
+
+    def glitter(self, nbmu, rmu, chr_, wind, ind_surf, os_nb, os_ns, os_nm):
+        """SOS_GLITTER (SOS_GLITTER.F:229): surface-file records [os_nb+1, 9, N, N] REAL*4 and the G-series lengths."""
+        surf = np.zeros((os_nb + 1, 9, nbmu, nbmu), dtype=np.float32)
+        il = np.zeros(nbmu * (nbmu + 1) // 2, dtype=np.int32)
+        rc = self.lib.sosgpu_glitter(self.ctx, C.c_int(nbmu), _d(_f64(rmu)), _d(_f64(chr_)), C.c_int(os_nb),
+                                     C.c_int(os_ns), C.c_int(os_nm), C.c_double(wind), C.c_double(ind_surf),
+                                     surf.ctypes.data_as(c_fp), il.ctypes.data_as(c_ip))
+        self._check(rc, "glitter")
+        return surf, il

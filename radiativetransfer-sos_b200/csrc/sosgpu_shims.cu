@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -75,6 +76,119 @@ extern "C" int sosgpu_trphi_option(sosgpu_ctx *ctx, const double *rec, int nrec,
   if (theta_fin) for (int j = 1; j <= N; ++j) theta_fin[j - 1] = std::acos(rmu[j + N]) * 180.0 / pi;   // :508,573
   cudaFree(d_rec); cudaFree(d_rmu); cudaFree(d_phi); cudaFree(d_out); cudaFree(d_g);
   return nphi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SOS_MAT_FRESNEL (SOS_SURFACE.F:1235-1603) on the host: O(N*NS + NS^2) scalar work whose output goes through the
+// reference's 4(E15.8) text file (RES_FRESNEL, :1552 / :1822) -- the decimal round trip is a host operation.
+static double round_e15_8(double x)
+{
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.7E", x);
+  return strtod(buf, nullptr);
+}
+static void mat_fresnel_host(int N, const double *rmu, const double *chr, double ind, int ns,
+                             std::vector<double> &alpha, std::vector<double> &beta, std::vector<double> &gamma,
+                             std::vector<double> &zeta)
+{
+  alpha.assign(ns + 1, 0.0); beta.assign(ns + 1, 0.0); gamma.assign(ns + 1, 0.0); zeta.assign(ns + 1, 0.0);
+  std::vector<double> delta(ns + 1, 0.0), r11(2 * N + 1), r12(2 * N + 1), r33(2 * N + 1), pl(ns + 3), pol(ns + 2);
+  for (int j = -N; j <= N; ++j) {                              // :1346-1381
+    if (j == 0) continue;
+    double c = rmu[j + N];
+    c = std::sqrt(.5 * (1 + c));
+    const double a = std::sqrt(ind * ind - 1.0 + c * c), b = ind * ind * c;
+    const double rl = -(b - a) / (b + a), rr = (c - a) / (c + a);
+    r11[j + N] = .5 * (rl * rl + rr * rr); r12[j + N] = .5 * (rl * rl - rr * rr); r33[j + N] = rl * rr;
+  }
+  for (int j = -N; j <= N; ++j) {                              // :1387-1400
+    if (j == 0) continue;
+    const double x = r11[j + N] * chr[j + N], xrmu = rmu[j + N];
+    pl[0] = 0.0; pl[1] = 1.0;
+    for (int k = 0; k <= ns; ++k) {
+      pl[k + 2] = ((2 * k + 1.) * xrmu * pl[k + 1] - k * pl[k]) / (k + 1.);
+      beta[k] = beta[k] + x * pl[k + 1];
+    }
+  }
+  for (int k = 0; k <= ns; ++k) beta[k] = (2 * k + 1) * beta[k] * .5;
+  for (int j = -N; j <= N; ++j) {                              // :1433-1456
+    if (j == 0) continue;
+    const double xxx = chr[j + N] * r12[j + N], xx = chr[j + N] * r33[j + N], xrmu = rmu[j + N];
+    pol[0] = 0.0; pol[1] = 0.0; pl[0] = 0.0; pl[1] = 1.0;
+    pol[2] = 3. * (1. - xrmu * xrmu) / 2. / std::sqrt(6.0);
+    for (int k = 2; k <= ns; ++k) {
+      const double d = (2. * k + 1.) / std::sqrt(1.0 * (k + 3.) * (k - 1.));
+      const double e = std::sqrt(1.0 * (k + 2.) * (k - 2.)) / (2. * k + 1.);
+      pol[k + 1] = d * (xrmu * pol[k] - e * pol[k - 1]);
+      gamma[k] = gamma[k] + xxx * pol[k];
+    }
+    for (int k = 0; k <= ns; ++k) {
+      pl[k + 2] = ((2. * k + 1.) * xrmu * pl[k + 1] - k * pl[k]) / (k + 1.);
+      delta[k] = delta[k] + xx * pl[k + 1];
+    }
+  }
+  for (int k = 0; k <= ns; ++k) { delta[k] = delta[k] * (2. * k + 1.) * .5; gamma[k] = gamma[k] * (2. * k + 1.) * .5; }
+  for (int i = 2; i <= ns; ++i) {                              // :1521-1546 (CO1, CO2 are REAL*4 expressions)
+    const float co1f = 4 * (2 * i + 1.f) / (float)i / (i - 1.f) / (i + 1.f) / (i + 2.f);
+    const float co2f = i * (i - 1.f) / ((i + 1.f) * (i + 2.f));
+    const double co1 = co1f;
+    double co2 = co2f;
+    const double co3 = co2 * delta[i];
+    co2 = co2 * beta[i];
+    const int nn = (int)(i * .5f), mm = (int)((i - 1) * .5f);
+    double som1 = 0, som2 = 0, som3 = 0, som4 = 0;
+    for (int j = 1; j <= nn; ++j) {
+      const double x2 = (double)((i - 1.f) * (i - 1.f) - 3.f * (2 * j - 1.f) * (i - j));
+      som1 = som1 + x2 * beta[i - 2 * j]; som2 = som2 + x2 * delta[i - 2 * j];
+    }
+    for (int j = 0; j <= mm; ++j) {
+      const double x2 = (double)((i - 1.f) * (i - 1.f) - 3.f * j * (2 * i - 2 * j - 1.f));
+      som3 = som3 + x2 * beta[i - 2 * j - 1]; som4 = som4 + x2 * delta[i - 2 * j - 1];
+    }
+    zeta[i] = co3 - co1 * (som2 - som3);
+    alpha[i] = co2 - co1 * (som1 - som4);
+  }
+  for (int k = 0; k <= ns; ++k) {
+    alpha[k] = round_e15_8(alpha[k]); beta[k] = round_e15_8(beta[k]);
+    gamma[k] = round_e15_8(gamma[k]); zeta[k] = round_e15_8(zeta[k]);
+  }
+}
+
+// SOS_GLITTER (SOS_GLITTER.F:229-371): surface-file records of a rough sea, one fused kernel (glitter_kernel.cu)
+extern "C" int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
+                              int os_nm, double wind, double ind_surf, float *surf, int *il_out)
+{
+  if (!ctx) return SOSGPU_ERR_NO_DEVICE;
+  if (!rmu || !chr || !surf || nbmu < 1 || nbmu > SOSGPU_NBMU_MAX || os_nb > SOSGPU_NB_MAX || os_ns < 2 || os_ns > 136 ||
+      os_nm < os_nb + os_ns || os_nm > 336) { ctx->err = "sosgpu_glitter: bad arguments"; return SOSGPU_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const int N = nbmu, W = 2 * N + 1, npair = N * (N + 1) / 2;
+  std::vector<double> al, be, ga, ze;
+  mat_fresnel_host(N, rmu, chr, ind_surf, os_ns, al, be, ga, ze);
+  const size_t nsurf = (size_t)(os_nb + 1) * 9 * N * N;
+  double *d_in = nullptr; float *d_surf = nullptr; int *d_il = nullptr;
+  CK(cudaMalloc(&d_in, (W + 4 * (os_ns + 1)) * 8));
+  CK(cudaMalloc(&d_surf, nsurf * 4));
+  CK(cudaMalloc(&d_il, npair * sizeof(int)));
+  CK(cudaMemcpyAsync(d_in, rmu, W * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const std::vector<double> *cf[4] = {&al, &be, &ga, &ze};
+  for (int c = 0; c < 4; ++c)
+    CK(cudaMemcpyAsync(d_in + W + c * (os_ns + 1), cf[c]->data(), (os_ns + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(d_surf, 0, nsurf * 4, ctx->stream));
+  GlitterParams p{};
+  p.nbmu = N; p.os_nb = os_nb; p.os_ns = os_ns; p.os_nm = os_nm;
+  p.sig = (double)0.003f + (double)0.00512f * wind;            // SIG = .003 + .00512*WIND (SOS_GLITTER.F:300)
+  p.coef = 1.0 / p.sig;                                        // (1./SIG) (:315)
+  p.pi = std::acos(-1.0);
+  p.rmu = d_in; p.alpha = d_in + W; p.beta = p.alpha + (os_ns + 1); p.gamma = p.beta + (os_ns + 1); p.zeta = p.gamma + (os_ns + 1);
+  sos_launch_glitter(p, d_surf, d_il, ctx->stream);
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(surf, d_surf, nsurf * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (il_out) CK(cudaMemcpyAsync(il_out, d_il, npair * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  cudaFree(d_in); cudaFree(d_surf); cudaFree(d_il);
+  return SOSGPU_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -160,3 +160,33 @@ def test_trphi_option(pkg, orc, solver):
             assert_stokes_close(up1[tb], up0[tb], "up table %d" % tb)
             assert_stokes_close(dn1[tb], dn0[tb], "down table %d" % tb)
         assert np.allclose(up1[4:], up0[4:], rtol=1e-7, atol=1e-9) and np.allclose(dn1[4:], dn0[4:], rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("nbg,wind", [(12, 2.0), (24, 7.5)])
+def test_glitter(pkg, orc, solver, nbg, wind):
+    """SOS_GLITTER pipeline (SOS_GSF, SOS_MAT_FRESNEL, SOS_MAT_REFLEXION, SOS_NOYAUX_FRESNEL, SOS_MISE_FORMAT):
+    REAL*4 surface-file records and the integer series lengths IL of every angle pair."""
+    rmu, ga, n0, _ = pkg.synth.sos_angles(nbg, 35.0)
+    N = (rmu.size - 1) // 2
+    os_ns, os_nb = 2 * nbg, 2 * nbg
+    os_nm = os_nb + os_ns
+    ref, il0 = orc.glitter(N, rmu, ga, wind, 1.34, os_nb, os_ns, os_nm)
+    got, il1 = solver.glitter(N, rmu, ga, wind, 1.34, os_nb, os_ns, os_nm)
+    assert np.array_equal(il0, il1)                     # data-dependent series cut: bit-identical counts
+    exact = np.mean(got.view(np.uint32) == ref.view(np.uint32))
+    assert exact > 0.999, exact                         # REAL*4 storage: bit-identical except rare rounding ties
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 2e-7 * scale
+
+
+def test_solve_with_glitter_surface(pkg, orc, solver):
+    """configs[1]-like: rough sea; the surface matrix comes from the glitter pipeline and feeds the solver."""
+    syn = pkg.synth
+    o = syn.make_optics(nb_gauss=12, tetas=35.0, os_nb=24, surface="glitter", rho=0.0)
+    surf, _ = solver.glitter(o.nbmu, o.rmu, o.ga, o.wind, o.ind_surf, o.os_nb, 24, 48)
+    ref, _ = orc.glitter(o.nbmu, o.rmu, o.ga, o.wind, o.ind_surf, o.os_nb, 24, 48)
+    o.surf = ref                                        # same REAL*4 file for both sides
+    assert np.mean(surf.view(np.uint32) == ref.view(np.uint32)) > 0.999
+    wl = syn.Workload("sea", [o], [syn.Term(0, 1.0, *syn.profile(0.05, 8.0, 0.2, 2.0, 0.0))])
+    tr, _ = _check_terms(pkg, orc, solver, wl)
+    assert tr.n_fourier[0] > 3
