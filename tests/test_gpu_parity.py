@@ -190,3 +190,66 @@ def test_solve_with_glitter_surface(pkg, orc, solver):
     wl = syn.Workload("sea", [o], [syn.Term(0, 1.0, *syn.profile(0.05, 8.0, 0.2, 2.0, 0.0))])
     tr, _ = _check_terms(pkg, orc, solver, wl)
     assert tr.n_fourier[0] > 3
+
+
+def test_gfortran_abi_sos_os_and_aggregate(pkg, orc, solver, tmp_path):
+    """Drop-in symbols sos_os_ / sos_aggregate_ (SOS_OS.F:303-308, SOS_AGGREGATE.F:172-178): F77 by-reference
+    arguments, SOS.h fixed strides, hidden CHARACTER*500 lengths, surface file in, SOS_Result.bin records out."""
+    import ctypes as C
+    import importlib
+    api = importlib.import_module("radiativetransfer-sos_b200.api")
+    fm, syn = pkg.formats, pkg.synth
+    lib = api.load_library()
+    o = syn.make_optics(nb_gauss=8, tetas=50.0, os_nb=16, surface="brdf", rho=0.05)
+    t = syn.Term(0, 1.0, *syn.profile(0.05, 8.0, 0.1, 2.0, 0.5))
+    r = oracle_term(orc, o, t)                       # SOS level; hand SOS_OS its truncation-adapted profile
+    N, NT = o.nbmu, t.nt
+    MX, NTM, NBM = 80, 600, 200
+
+    def strided(v, cap, off):
+        a = np.zeros(cap)
+        a[off:off + len(v)] = v
+        return a
+    rmu = np.zeros(2 * MX + 1); ga = np.zeros(2 * MX + 1)
+    rmu[MX - N:MX + N + 1] = o.rmu; ga[MX - N:MX + N + 1] = o.ga
+    h, xd, yd, zp = (strided(v, NTM + 1, 0) for v in (r.h, r.xdel, r.ydel, t.zprof))
+    al, be, gm, ze = (strided(v, NBM + 1, 0) for v in (o.alpha, o.beta, o.gamma, o.zeta))
+    fsurf, fos = str(tmp_path / "SURF.bin"), str(tmp_path / "FICOS_TMP")
+    fm.write_surface_bin(fsurf, o.surf)
+
+    def fstr(s):
+        return C.create_string_buffer(s.encode().ljust(500), 500)
+    ip = lambda v: C.byref(C.c_int(v))
+    dp = lambda v: C.byref(C.c_double(v))
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    em, ep, ier = C.c_double(0), C.c_double(0), C.c_int(99)
+    iborm = o.os_nb
+    lib.sos_os_(ip(N), P(rmu), P(ga), ip(o.os_nb), ip(NT), fstr(fsurf), fstr(fos), ip(o.n0), dp(o.tetas), dp(o.rho),
+                ip(1), ip(0), dp(o.ind_surf), P(h), P(xd), P(yd), P(zp), dp(o.ron), P(al), P(be), P(gm), P(ze),
+                dp(-1.0), ip(o.igmax), ip(iborm), ip(1), ip(0), ip(6), C.byref(em), C.byref(ep), C.byref(ier),
+                C.c_size_t(500), C.c_size_t(500))
+    assert ier.value == 0
+    assert rmu[MX] == -o.rmu[N + o.n0]               # caller-visible side effect RMU(0) = mu_s (SOS_OS.F:715)
+    rec = fm.read_result_bin(fos, N)
+    assert rec.shape[0] == r.n_fourier
+    assert_stokes_close(rec, r.rec, "sos_os_ records")
+    assert_stokes_close(em.value, r.emoins, "EMOINS")
+    # aggregate twice into a fresh result file (accumulators start at 0, SOS_PROC.F:1292-1302)
+    fres, fagg = str(tmp_path / "SOS_Result.bin"), str(tmp_path / "AGG_TMP")
+    tdg_tmp, tdg = np.zeros(2 * MX + 1), np.zeros(2 * MX + 1)
+    acc = [C.c_double(0) for _ in range(6)]          # ttot_tronc, ttot_vrai, tauout, tdifmus, emoins, eplus
+    agg = orc.Aggregate(N, o.os_nb + 1)
+    for aik in (0.25, 0.75):
+        ier2 = C.c_int(0)
+        lib.sos_aggregate_(ip(N), dp(aik), fstr(fos), dp(r.ttot_tronc), dp(r.ttot_vrai), dp(r.tauout), dp(0.0),
+                           P(tdg_tmp), dp(r.emoins), dp(r.eplus), fstr(fagg), fstr(fres),
+                           C.byref(acc[0]), C.byref(acc[1]), C.byref(acc[2]), C.byref(acc[3]), P(tdg),
+                           C.byref(acc[4]), C.byref(acc[5]), C.byref(ier2), C.c_size_t(500), C.c_size_t(500),
+                           C.c_size_t(500))
+        assert ier2.value == 0
+        agg.add(aik, r)
+    res = fm.read_result_bin(fres, N)
+    assert res.shape[0] == agg.nres                  # incl. the reference's trailing zero record
+    assert_stokes_close(res, agg.res[:agg.nres], "sos_aggregate_ records")
+    assert_stokes_close(acc[0].value, agg.sc["ttot_tronc"], "TTOT_TRONC")
+    assert_stokes_close(acc[5].value, agg.sc["eplus"], "EPLUS")
