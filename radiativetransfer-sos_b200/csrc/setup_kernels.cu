@@ -315,25 +315,25 @@ __global__ void k_init(ItemDev *items, const TermDev *terms, const OpticsDev *op
   ItemDev &it = items[blockIdx.x];
   const TermDev &tm = terms[it.term];
   const OpticsDev &op = optics[tm.optics];
-  const int N = op.nbmu, HB = op.HB, NT = tm.nt, LP = tm.LP;
+  const int N = op.nbmu, HB = op.HB, NT = tm.nt, KP = op.KP;
   const double *x1 = it.x[1];
   for (int c = threadIdx.x; c < 6 * N; c += blockDim.x) {
     const int d = c / (3 * N);
     const int r = comp_row(c, N, HB);
-    const double v = x1[(size_t)r * LP + (d == 0 ? 0 : NT)];
+    const double v = x1[SOS_XIDX(KP, r, d == 0 ? 0 : NT)];
     it.sum3[c] = v;
     it.hist_d[c] = v;
     it.hist_a[c] = 0.0;
     if (it.sumout) {
-      it.sumout[c] = x1[(size_t)r * LP + (tm.jout - 1)];
-      it.sumout[6 * N + c] = x1[(size_t)r * LP + tm.jout];
+      it.sumout[c] = x1[SOS_XIDX(KP, r, tm.jout - 1)];
+      it.sumout[6 * N + c] = x1[SOS_XIDX(KP, r, tm.jout)];
     }
     if (d == 0) {
       double rv = 0.0, ro0 = 0.0, ro1 = 0.0;
       if (op.imat_surf == 1) {
         const int so = c / N, k = c % N + 1;
         const double mu = op.rmu[k + N];
-        double g = x1[(size_t)r * LP + NT];                   // I1(NT,K) (boundary value is kept by the integration)
+        double g = x1[SOS_XIDX(KP, r, NT)];                   // I1(NT,K) (boundary value is kept by the integration)
         if (so == 0) {
           double xr = 0.0;
           if (!(op.ro == 0.0 || it.is != 0)) xr = -op.ro * op.tab * tm.eground;   // XR(K) (:979-980)
@@ -368,7 +368,7 @@ __global__ void k_test(ItemDev *items, const TermDev *terms, const OpticsDev *op
   ItemDev &it = items[item];
   const TermDev &tm = terms[it.term];
   const OpticsDev &op = optics[tm.optics];
-  const int N = op.nbmu, HB = op.HB, NT = tm.nt, LP = tm.LP;
+  const int N = op.nbmu, HB = op.HB, NT = tm.nt, KP = op.KP;
   const int ig = it.n + 1;                                    // label 503: IG=IG+1
   const double *xn = it.x[ig & 1];
   const double *xp = it.x[(ig - 1) & 1];
@@ -378,7 +378,7 @@ __global__ void k_test(ItemDev *items, const TermDev *terms, const OpticsDev *op
   if (ig != 2) {                                              // SOS_PARAM_CONV (:3430-3458)
     for (int c = threadIdx.x; c < NC; c += blockDim.x) {
       const int d = c / (3 * N);
-      const double g = xn[(size_t)comp_row(c, N, HB) * LP + (d == 0 ? 0 : NT)];
+      const double g = xn[SOS_XIDX(KP, comp_row(c, N, HB), d == 0 ? 0 : NT)];
       const double a1 = it.hist_a[c], d1 = it.hist_d[c], s3 = it.sum3[c];
       if (a1 != 0.0 && d1 != 0.0 && s3 != 0.0) {
         const double r = 1 - g / d1;
@@ -391,15 +391,15 @@ __global__ void k_test(ItemDev *items, const TermDev *terms, const OpticsDev *op
   if (ig != 2 && !(zconv > SEUIL_CV_SG)) {                    // geometric tail (:1293-1315, SOS_AJOUT_QUEUE)
     for (int c = threadIdx.x; c < NC; c += blockDim.x) {
       const int d = c / (3 * N);
-      const size_t rowoff = (size_t)comp_row(c, N, HB) * LP;
-      const double g = xn[rowoff + (d == 0 ? 0 : NT)];
+      const int crow = comp_row(c, N, HB);
+      const double g = xn[SOS_XIDX(KP, crow, d == 0 ? 0 : NT)];
       const double d1 = it.hist_d[c];
       const double q = (d1 == 0.0) ? 0.0 : g / (1 - g / d1);
       it.sum3[c] = it.sum3[c] + q;
       if (it.sumout) {
         for (int lv = 0; lv < 2; ++lv) {
           const int level = tm.jout - 1 + lv;
-          const double go = xn[rowoff + level], dprev = xp[rowoff + level];
+          const double go = xn[SOS_XIDX(KP, crow, level)], dprev = xp[SOS_XIDX(KP, crow, level)];
           const double qo = (dprev == 0.0) ? 0.0 : go / (1 - go / dprev);
           it.sumout[lv * NC + c] = it.sumout[lv * NC + c] + qo;
         }
@@ -412,15 +412,15 @@ __global__ void k_test(ItemDev *items, const TermDev *terms, const OpticsDev *op
   double z1 = 0.0, z2 = 0.0;
   for (int c = threadIdx.x; c < NC; c += blockDim.x) {
     const int d = c / (3 * N);
-    const size_t rowoff = (size_t)comp_row(c, N, HB) * LP;
-    const double g = xn[rowoff + (d == 0 ? 0 : NT)];
+    const int crow = comp_row(c, N, HB);
+    const double g = xn[SOS_XIDX(KP, crow, d == 0 ? 0 : NT)];
     it.hist_a[c] = it.hist_d[c];
     it.hist_d[c] = g;
     const double s3 = it.sum3[c] + g;
     it.sum3[c] = s3;
     if (it.sumout) {
-      it.sumout[c] = it.sumout[c] + xn[rowoff + tm.jout - 1];
-      it.sumout[NC + c] = it.sumout[NC + c] + xn[rowoff + tm.jout];
+      it.sumout[c] = it.sumout[c] + xn[SOS_XIDX(KP, crow, tm.jout - 1)];
+      it.sumout[NC + c] = it.sumout[NC + c] + xn[SOS_XIDX(KP, crow, tm.jout)];
     }
     z1 = fmax(z1, fabs(g));
     if (s3 != 0.0) z2 = fmax(z2, fabs(g / s3));

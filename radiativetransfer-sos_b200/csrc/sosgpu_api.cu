@@ -436,7 +436,7 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     for (int i = 0; i < nterm; ++i)
       if (!done[i] && s0 <= b->ht[i].iborm) {
         act.push_back(i);
-        bytes_per_order += (size_t)2 * b->ho[b->ht[i].optics].KP * b->ht[i].LP * sizeof(double);
+        bytes_per_order += (size_t)2 * SOS_XSIZE(b->ho[b->ht[i].optics].KP, b->ht[i].nt + 1) * sizeof(double);
       }
     if (act.empty()) break;
     int ws = b->smax - s0;
@@ -477,7 +477,7 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
         item_of[(size_t)ti * ws + (s - s0)] = (int)items.size();
         items.push_back(it);
         foff.push_back(fbytes);
-        fbytes += al((size_t)2 * ho.KP * ht.LP * 8);
+        fbytes += al((size_t)2 * SOS_XSIZE(ho.KP, ht.nt + 1) * 8);
         soff.push_back(sbytes);
         const size_t N = ho.N;
         sbytes += al((3 * 6 * N + 3 * N) * 8) + (ht.jout >= 0 ? al((2 * 6 * N + 2 * 3 * N) * 8) : 0);
@@ -523,7 +523,7 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
       const size_t N = ho.N;
       char *p = b->d_field + foff[i];
       it.x[0] = (double *)p;
-      it.x[1] = it.x[0] + (size_t)ho.KP * ht.LP;
+      it.x[1] = it.x[0] + SOS_XSIZE(ho.KP, ht.nt + 1);
       char *q = b->d_field + fbytes + soff[i];
       it.hist_a = (double *)q; it.hist_d = it.hist_a + 6 * N; it.sum3 = it.hist_d + 6 * N; it.rii = it.sum3 + 6 * N;
       if (ht.jout >= 0) {
@@ -861,7 +861,7 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
   CK(cudaMalloc(&dks, sizeof(KsetDev)));
   CK(cudaMemcpy(dks, &ks, sizeof(ks), cudaMemcpyHostToDevice));
   // fields: x[1] = input (order n=1 parity), x[0] = output, plus J dump
-  const size_t fsz = (size_t)KP * LP;
+  const size_t fsz = std::max(SOS_XSIZE(KP, L), (size_t)KP * LP);   // field (chunk-major) or J dump ([row][LP])
   std::vector<double> xin(fsz, 0.0);
   const double *src[3] = {i1, q1, u1};
   for (int d = 0; d < 2; ++d)
@@ -869,7 +869,7 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
       for (int k = 1; k <= N; ++k) {
         const int r = d * HB + s * N + (k - 1);
         const int kk = d == 0 ? k : -k;
-        for (int lv = 0; lv < L; ++lv) xin[(size_t)r * LP + lv] = src[s][(size_t)(kk + N) * L + lv];
+        for (int lv = 0; lv < L; ++lv) xin[SOS_XIDX(KP, r, lv)] = src[s][(size_t)(kk + N) * L + lv];
       }
   double *dx = nullptr;
   CK(cudaMalloc(&dx, 3 * fsz * 8));
@@ -898,7 +898,7 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
         const int r = d * HB + s * N + (k - 1);
         const int kk = d == 0 ? k : -k;
         for (int lv = 0; lv < L; ++lv) {
-          if (dstx[s]) dstx[s][(size_t)(kk + N) * L + lv] = xo[(size_t)r * LP + lv];
+          if (dstx[s]) dstx[s][(size_t)(kk + N) * L + lv] = xo[SOS_XIDX(KP, r, lv)];
           if (dstj[s]) dstj[s][(size_t)(kk + N) * L + lv] = jo[(size_t)r * LP + lv];
         }
       }

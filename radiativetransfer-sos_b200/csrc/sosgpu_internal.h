@@ -8,8 +8,8 @@
 //   N  = nbmu, W = 2N+1, HB = roundup(3N,16) rows per direction block, KP = 2*HB.
 //   row r in [0,KP): d = r / HB (0: mu>0 "up", 1: mu<0 "down"), q = r % HB,
 //                    valid iff q < 3N, stokes = q / N (0 I, 1 Q, 2 U), k = q % N + 1.
-//   A field X(0:NT,-N:N) x {I,Q,U} of the reference is stored as X[r][level], level fastest,
-//   pitch LP = roundup(NT+1, 8); pad rows / pad levels stay zero.
+//   A field X(0:NT,-N:N) x {I,Q,U} of the reference is stored chunk-major as X[level/64][r][68] (SOS_XIDX);
+//   pad rows / pad levels / pad columns stay zero.  LP = roundup(NT+1, 8) is only the pitch of test dumps.
 // ------------------------------------------------------------------------------------------------
 #define SOS_KB 16      // k-slab of the contraction (doubles)
 #define SOS_CH 64      // level chunk (columns of the DMMA tile)
@@ -17,6 +17,11 @@
 #define SOS_SB 68      // smem row stride of the B slab   (CH + 4)
 #define SOS_SJ 65      // smem row stride of the staging tile (odd: conflict-free row-per-thread scan)
 #define SOS_STAGES 3
+// Field layout in HBM: chunk-major, padded rows -- X[(level>>6)][row][SOS_SB], element (row, level):
+// the 16 k-rows x 64 levels a k-slab needs are one contiguous 16*SOS_SB*8-byte block = ONE TMA bulk copy that
+// lands in shared memory with the conflict-free padded pitch.
+#define SOS_XIDX(KP, row, level) ((((size_t)((level) >> 6)) * (size_t)(KP) + (size_t)(row)) * SOS_SB + ((level) & 63))
+#define SOS_XSIZE(KP, L) ((size_t)(((L) + SOS_CH - 1) / SOS_CH) * (size_t)(KP) * SOS_SB)
 #define SOS_MAXW 8     // warps (16-row groups) per CTA tile
 
 struct OpticsDev {            // one per optics entry (device copy, arrays in a slab)

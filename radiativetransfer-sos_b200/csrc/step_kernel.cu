@@ -160,7 +160,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       }
     } else {
       // ground values of the previous order's downward field: G[st*N + j-1] = X_{n-1}(NT, -j)
-      for (int c = tid; c < 3 * N; c += blockDim.x) sG[c] = xprev[(size_t)(HB + c) * LP + NT];
+      for (int c = tid; c < 3 * N; c += blockDim.x) sG[c] = xprev[SOS_XIDX(KP, HB + c, NT)];
       __syncthreads();
       if (rowvalid) {
         double xr = 0.0;
@@ -227,8 +227,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
     }
 
     if (!ORDER1) {
-      const int ncol = min(SOS_CH, LP - c0);                       // valid (zero padded) columns of this chunk
-      const unsigned tx = (unsigned)(R * SOS_KB * 8 + (LR ? STAGE_V_BYTES : 0) + SOS_KB * ncol * 8);
+      const unsigned tx = (unsigned)(R * SOS_KB * 8 + (LR ? STAGE_V_BYTES : 0) + STAGE_B_BYTES);
       auto issue = [&](int slab, unsigned cnt) {                   // executed by thread 0 only
         const int stage = cnt % SOS_STAGES;
         unsigned char *sp = smem_raw + stage * stage_bytes;
@@ -238,11 +237,8 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
         else bulk_g2s(sp, Ag + (size_t)slab * KP * SOS_KB, (unsigned)(R * SOS_KB * 8), bar);
         sp += STAGE_A_BYTES(rows_max);
         if (LR) { bulk_g2s(sp, Vg + (size_t)slab * 8 * SOS_KB, STAGE_V_BYTES, bar); sp += STAGE_V_BYTES; }
-        const double *xs = xprev + (size_t)slab * SOS_KB * LP + c0;
-        if (dbg & 8) bulk_g2s(sp, xprev, (unsigned)(SOS_KB * ncol * 8), bar);   // timing experiment: one copy of the same size
-        else
-        for (int kr = 0; kr < SOS_KB; ++kr)
-          bulk_g2s(sp + kr * SOS_SB * 8, xs + (size_t)kr * LP, (unsigned)(ncol * 8), bar);
+        // chunk-major padded field layout: the 16 x 64 slab (pitch SOS_SB) is one contiguous block
+        bulk_g2s(sp, xprev + SOS_XIDX(KP, slab * SOS_KB, c0), STAGE_B_BYTES, bar);
       };
       if (tid == 0) {
         for (int s = 0; s < SOS_STAGES - 1 && s < n_slab; ++s) issue(s, it_count + s);
@@ -478,7 +474,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
     for (int idx = tid; idx < R * SOS_CH; idx += blockDim.x) {
       const int rowl = idx >> 6, col = idx & 63;
       const int level = c0 + col, row = r0 + rowl;
-      if (level < L && (row - dir * HB) < 3 * N) xnext[(size_t)row * LP + level] = sJ[rowl * SOS_SJ + col];
+      if (level < L && (row - dir * HB) < 3 * N) xnext[SOS_XIDX(KP, row, level)] = sJ[rowl * SOS_SJ + col];
     }
     __syncthreads();                                             // sJ is free again (next chunk's TMA may overwrite it)
   }
