@@ -253,3 +253,45 @@ def test_gfortran_abi_sos_os_and_aggregate(pkg, orc, solver, tmp_path):
     assert_stokes_close(res, agg.res[:agg.nres], "sos_aggregate_ records")
     assert_stokes_close(acc[0].value, agg.sc["ttot_tronc"], "TTOT_TRONC")
     assert_stokes_close(acc[5].value, agg.sc["eplus"], "EPLUS")
+
+
+@pytest.mark.parametrize("nbg,os_nb", [(24, 48), (79, 24)])
+def test_solve_other_angle_counts(pkg, orc, solver, nbg, os_nb):
+    """N=25 (default -ANG.Rad.NbGauss 24: 5 row groups per direction) and N=80 (the CTE_OS_NBMU_MAX cap: KP=480,
+    two row tiles per direction, attenuation table not staged in shared memory)."""
+    syn = pkg.synth
+    o = syn.make_optics(nb_gauss=nbg, tetas=35.0, os_nb=os_nb, surface="lambert", rho=0.15)
+    assert o.nbmu == nbg + 1
+    wl = syn.Workload("n%d" % o.nbmu, [o], [syn.Term(0, 0.5, *syn.profile(0.08, 8.0, 0.25, 2.0, 0.02)),
+                                            syn.Term(0, 0.5, *syn.profile(0.08, 8.0, 0.25, 2.0, 0.9))])
+    _check_terms(pkg, orc, solver, wl)
+
+
+def test_band_properties_at_bench_size(pkg, orc, solver):
+    """BASELINE configs[2] at the bench size (96 spectral points, ~600 term-solves): size-independent properties
+    (the aggregated record is the AIK-weighted sum of the term records; counts within bounds; finite) plus a
+    random sample of terms against the oracle."""
+    syn = pkg.synth
+    wl = syn.config_ckd_band(npoints=96, seed=20261021, nb_gauss=40, os_nb=80, surface="lambert", rho=0.1)
+    tr, gr = solver.solve(wl)
+    assert np.all(tr.ier == 0) and np.isfinite(tr.rec).all() and np.isfinite(gr.rec).all()
+    assert np.all(tr.n_fourier >= 3) and np.all(tr.n_fourier <= 81)
+    for i in range(len(wl.terms)):
+        nf = tr.n_fourier[i]
+        assert np.all(tr.n_scatter[i, :nf] >= 2) and np.all(tr.n_scatter[i, :nf] <= 100)
+        assert np.all(tr.rec[i, nf:] == 0.0)
+    aik = np.array([t.aik for t in wl.terms])
+    grp = np.array([t.optics for t in wl.terms])
+    for g in range(0, 96, 7):
+        idx = np.where(grp == g)[0]
+        ref = np.zeros_like(gr.rec[g])
+        for i in idx:                                    # SOS_AGGREGATE order (SOS_AGGREGATE.F:397-413)
+            ref = ref + aik[i] * tr.rec[i]
+        assert np.array_equal(gr.rec[g], ref)
+        assert abs(aik[idx].sum() - 1.0) < 1e-12
+    rng = np.random.default_rng(3)
+    for i in rng.choice(len(wl.terms), 6, replace=False):
+        t = wl.terms[i]
+        r = oracle_term(orc, wl.optics[t.optics], t)
+        assert tr.n_fourier[i] == r.n_fourier and np.array_equal(tr.n_scatter[i, :r.n_fourier], r.n_scatter)
+        assert_stokes_close(tr.rec[i, :r.n_fourier], r.rec, "bench-size term %d" % i)
