@@ -3,7 +3,8 @@
 
 Workload (config.workload): BASELINE.json configs[2], an O2 A-band-like CKD absorption band on synthetic
 atmospheres: P spectral points per GPU, 1-25 CKD terms each (ragged NT 101..600), N=41 angles (40 Gauss +
-solar), OS_NB=80, Lambert surface; every term is one SOS/SOS_OS term-solve, terms are CKD-summed per point.
+solar), OS_NB=80, Lambert surface; every term is one SOS/SOS_OS term-solve, terms are CKD-summed per point and
+the band sums are synthesised on 13 azimuths (SOS_TRPHI_OPTION view mode 2) = one band-solve.
 configs[0]/[1] (single wavelength, 5 terms) are parity-test cases (tests/test_gpu_parity.py), too small to bench.
 
 One "step" = one pass of the hot path over the whole per-rank batch.  value = spectral points solved per second
@@ -202,6 +203,9 @@ def main():
         solver.run(batch, want_terms=False, want_groups=False, part_only=world > 1)
         if world > 1:
             dist.reduce(gview, dst=0, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize(dev)
+        if rank == 0:      # azimuth synthesis of the band sums (SOS_TRPHI_OPTION, view mode 2, 13 azimuths), device resident
+            solver.batch_trphi(batch, 0, 2.0, 1.34, 0, 2, 0.0, 30, 1, download=False)
 
     for _ in range(args.warmup):
         step_resident()
@@ -252,6 +256,9 @@ def main():
             torch.cuda.synchronize(dev)
             if os.environ.get("SOS_BENCH_VERBOSE"):
                 print("rank %d e2e: reduce %.1f ms" % (rank, (time.perf_counter() - tc) * 1e3), file=sys.stderr)
+        if rank == 0:
+            _, up_t, down_t = solver.batch_trphi(b2, 0, 2.0, 1.34, 0, 2, 0.0, 30, 1, download=True)
+            d2h += up_t.nbytes + down_t.nbytes
         h2d += b2.h2d_bytes
         d2h += gr.rec.nbytes + tr.n_fourier.nbytes + tr.n_scatter.nbytes
         td = time.perf_counter()

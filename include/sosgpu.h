@@ -169,6 +169,13 @@ int sosgpu_trphi_option(sosgpu_ctx *ctx, const double *rec, int nrec, int nbmu, 
                         int ifresnel, int itrphi, double phios, int pas_phi, int ipolar,
                         double *phi_fin, double *theta_fin, double *up, double *down, int nphi_cap);
 
+/* SOS_TRPHI_OPTION for every wavelength (group) of a resident batch, applied to the CKD-summed Fourier coefficients
+ * where the last sosgpu_batch_run left them on the device (after an in-place multi-GPU reduce on rank 0).
+ * up/down (may be NULL: device-resident timing): [ngroup][7][nphi_cap][Nmax], Nmax = max nbmu of the batch.
+ * Returns the number of azimuth slots. */
+int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *batch, int igli, double wind, double ind_surf, int ifresnel,
+                       int itrphi, double phios, int pas_phi, int ipolar, int nphi_cap, double *up, double *down);
+
 /* SOS_GLITTER (SOS_GLITTER.F:229) = SOS_GSF + SOS_MAT_FRESNEL + SOS_MAT_REFLEXION + SOS_NOYAUX_FRESNEL +
  * SOS_MISE_FORMAT (SOS_SURFACE.F:1235,1708,2029,2307): Cox-Munk glitter reflection matrices, Fourier-decomposed,
  * in the surface-file record layout.  rmu/chr: [2N+1] cosines / weights; surf: [os_nb+1][9][N][N] REAL*4;

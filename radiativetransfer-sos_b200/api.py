@@ -327,3 +327,17 @@ class Solver:
                                      surf.ctypes.data_as(c_fp), il.ctypes.data_as(c_ip))
         self._check(rc, "glitter")
         return surf, il
+
+    def batch_trphi(self, batch, igli, wind, ind_surf, ifresnel, itrphi, phios, pas_phi, ipolar, download=True):
+        """SOS_TRPHI_OPTION for every wavelength of a resident batch (after run); tables [ngroup, 7, nphi, Nmax]."""
+        cap = 2 if itrphi == 1 else 360 // max(pas_phi, 1) + 1
+        nmax = (batch.wmax - 1) // 2
+        up = np.zeros((batch.ngroup, 7, cap, nmax)) if download else None
+        down = np.zeros((batch.ngroup, 7, cap, nmax)) if download else None
+        n = self.lib.sosgpu_batch_trphi(self.ctx, batch.handle, C.c_int(igli), C.c_double(wind), C.c_double(ind_surf),
+                                        C.c_int(ifresnel), C.c_int(itrphi), C.c_double(phios), C.c_int(pas_phi),
+                                        C.c_int(ipolar), C.c_int(cap), _d(up) if download else None,
+                                        _d(down) if download else None)
+        if n < 0:
+            self._check(n, "batch_trphi")
+        return n, up, down

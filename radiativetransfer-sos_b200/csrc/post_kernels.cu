@@ -83,13 +83,15 @@ __device__ static void polar(double xi, double xq, double xu, double pi, double 
 
 // grid: (nphi, ngroup); block: threads over the 2N directions.
 // out: [ngroup][2 (up, down)][7][nphi][N]   tables SCA, I, Q, U, POL_ANG, POL_RATE, L_POL
-__global__ void k_trphi(const TrphiGroup *groups, const double *phis, int nphi, TrphiParams prm, double *out)
+__global__ void k_trphi(const TrphiGroup *groups, const double *phis, int nphi, int nout, TrphiParams prm, double *out)
 {
   const TrphiGroup g = groups[blockIdx.y];
   const int ip = blockIdx.x;
-  const int N = g.nbmu, W = 2 * N + 1;
+  const int N = g.nbmu, W = g.wstride;
   const double phi = phis[ip];
   const double pi = prm.pi;
+  if (nout < 0) nout = N;
+  if (g.nrec <= 0) return;
   for (int t = threadIdx.x; t < 2 * N; t += blockDim.x) {
     const int j = (t < N) ? (t + 1) : -(t - N + 1);
     const double rmuj = g.rmu[j + N];
@@ -138,8 +140,8 @@ __global__ void k_trphi(const TrphiGroup *groups, const double *phis, int nphi, 
     double xan, tpol, lpol;
     polar(xi, xq, xu, pi, xan, tpol, lpol);
     const int ud = (j > 0) ? 0 : 1, jj = (j > 0 ? j : -j) - 1;
-    double *o = out + (((size_t)blockIdx.y * 2 + ud) * 7) * nphi * N + (size_t)ip * N + jj;
-    const size_t ts = (size_t)nphi * N;
+    double *o = out + (((size_t)blockIdx.y * 2 + ud) * 7) * nphi * nout + (size_t)ip * nout + jj;   // nout = row pitch (max N)
+    const size_t ts = (size_t)nphi * nout;
     o[0] = angdiff; o[ts] = xi; o[2 * ts] = xq; o[3 * ts] = xu; o[4 * ts] = xan; o[5 * ts] = tpol; o[6 * ts] = lpol;
   }
 }
@@ -148,8 +150,16 @@ extern "C" void sos_launch_trphi(const TrphiGroup *groups, int ngroup, const dou
                                  TrphiParams prm, double *out, cudaStream_t st)
 {
   if (ngroup <= 0 || nphi <= 0) return;
+  // single wavelength: the output pitch is that group's N (read from the descriptor on the host side by the caller)
   dim3 grid(nphi, ngroup);
-  k_trphi<<<grid, 160, 0, st>>>(groups, phis, nphi, prm, out);
+  k_trphi<<<grid, 160, 0, st>>>(groups, phis, nphi, -1, prm, out);
+}
+extern "C" void sos_launch_trphi_stride(const TrphiGroup *groups, int ngroup, const double *phis, int nphi, int nout,
+                                        TrphiParams prm, double *out, cudaStream_t st)
+{
+  if (ngroup <= 0 || nphi <= 0) return;
+  dim3 grid(nphi, ngroup);
+  k_trphi<<<grid, 160, 0, st>>>(groups, phis, nphi, nout, prm, out);
 }
 
 // RES = RES + AIK*TMP (SOS_AGGREGATE.F:401-403) for the file-level drop-in sos_aggregate_

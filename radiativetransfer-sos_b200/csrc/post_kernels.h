@@ -6,6 +6,7 @@ struct TrphiGroup {          // one aggregated wavelength
   const double *rec;         // [nrec][3][2N+1] Fourier coefficients Q,U,I
   const double *rmu;         // [2N+1]
   int nrec, nbmu, n0;
+  int wstride;               // doubles between the Q, U, I rows of a record (>= 2N+1)
   double tau, tauout;        // TTOT_TRONC, TAUOUT after aggregation
 };
 struct TrphiParams {
@@ -24,6 +25,8 @@ extern "C" {
 void sos_launch_glitter(GlitterParams p, float *surf, int *il_out, cudaStream_t st);
 void sos_launch_trphi(const TrphiGroup *groups, int ngroup, const double *phis, int nphi,
                       TrphiParams prm, double *out, cudaStream_t st);
+void sos_launch_trphi_stride(const TrphiGroup *groups, int ngroup, const double *phis, int nphi, int nout,
+                             TrphiParams prm, double *out, cudaStream_t st);
 void sos_launch_axpy(double *res, const double *tmp, double aik, size_t n, cudaStream_t st);
 #ifdef __cplusplus
 }

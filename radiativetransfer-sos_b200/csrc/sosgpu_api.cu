@@ -760,6 +760,75 @@ extern "C" int sosgpu_batch_stats(const sosgpu_batch *b, sosgpu_stats *st)
 }
 
 // ---------------------------------------------------------------------------------------------
+// SOS_TRPHI_OPTION over every wavelength of the resident batch (band-solve = term-solves + CKD sum + synthesis).
+// Reads the CKD-summed Fourier coefficients where k_aggregate left them (no host round trip).
+#include "post_kernels.h"
+extern "C" int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *b, int igli, double wind, double ind_surf, int ifresnel,
+                                  int itrphi, double phios, int pas_phi, int ipolar, int nphi_cap, double *up, double *down)
+{
+  if (!ctx) return SOSGPU_ERR_NO_DEVICE;
+  if (!b) return SOSGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const double pi = std::acos(-1.0);
+  std::vector<double> phis;
+  if (itrphi == 1) { phis.push_back(pi + phios * pi / 180.0); phis.push_back(phios * pi / 180.0); }
+  else if (itrphi == 2 && pas_phi >= 1) { for (int iphi = 0; iphi <= 360; iphi += pas_phi) phis.push_back(pi * iphi / 180.0); }
+  else return SOSGPU_ERR_ARG;
+  const int nphi = (int)phis.size(), ng = b->ngroup;
+  if (nphi > nphi_cap) return SOSGPU_ERR_ARG;
+  std::vector<int> gn(ng);
+  CK(cudaMemcpy(gn.data(), b->d_gnrec, ng * sizeof(int), cudaMemcpyDeviceToHost));
+  const size_t per = (size_t)b->rs_dev * 3 * b->w_dev;
+  int nmax = 0;
+  std::vector<TrphiGroup> grp(ng);
+  for (int g = 0; g < ng; ++g) {
+    double tt = 0.0, to_ = 0.0;
+    int opt = -1;
+    for (int x = b->group_start[g]; x < b->group_start[g + 1]; ++x) {     // SOS_AGGREGATE.F:467-488, term order
+      const HostTerm &ht = b->ht[b->group_terms[x]];
+      if (opt < 0) opt = ht.optics;
+      double tr = (tt != 0) ? ht.aik * std::exp(-ht.ttot_tronc) + std::exp(-tt) : ht.aik * std::exp(-ht.ttot_tronc);
+      tt = -std::log(tr);
+      tr = (to_ != 0) ? ht.aik * std::exp(-ht.tauout) + std::exp(-to_) : ht.aik * std::exp(-ht.tauout);
+      to_ = -std::log(tr);
+    }
+    if (opt < 0) { grp[g] = TrphiGroup{b->d_grec, b->optics_dev[0].rmu, 0, b->ho[0].N, 1, b->w_dev, 0.0, 0.0}; continue; }
+    const HostOptics &ho = b->ho[opt];
+    if (ho.n0 < 1) { ctx->err = "sosgpu_batch_trphi needs the solar angle among the Gauss angles (n0 > 0)"; return SOSGPU_ERR_ARG; }
+    grp[g] = TrphiGroup{b->d_grec + (size_t)g * per, b->optics_dev[opt].rmu, gn[g], ho.N, ho.n0, b->w_dev, tt, to_};
+    nmax = std::max(nmax, ho.N);
+  }
+  // note: rmu[N] on the device holds mu_s (index 0), which SOS_TRPHI never reads
+  TrphiGroup *d_g = nullptr; double *d_phi = nullptr, *d_out = nullptr;
+  const size_t nout = (size_t)ng * 2 * 7 * nphi * nmax;
+  CK(cudaMalloc(&d_g, ng * sizeof(TrphiGroup)));
+  CK(cudaMalloc(&d_phi, nphi * 8));
+  CK(cudaMalloc(&d_out, nout * 8));
+  CK(cudaMemcpyAsync(d_g, grp.data(), ng * sizeof(TrphiGroup), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_phi, phis.data(), nphi * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(d_out, 0, nout * 8, ctx->stream));
+  TrphiParams prm{igli, ifresnel, ipolar, wind, ind_surf, pi};
+  sos_launch_trphi_stride(d_g, ng, d_phi, nphi, nmax, prm, d_out, ctx->stream);
+  ctx->launches += 1;
+  if (up || down) {
+    std::vector<double> out(nout);
+    CK(cudaMemcpyAsync(out.data(), d_out, nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int g = 0; g < ng; ++g)
+      for (int ud = 0; ud < 2; ++ud) {
+        double *dst = ud == 0 ? up : down;
+        if (!dst) continue;
+        for (int t = 0; t < 7; ++t)
+          for (int ip = 0; ip < nphi; ++ip)
+            memcpy(dst + (((size_t)g * 7 + t) * nphi_cap + ip) * nmax, &out[((((size_t)g * 2 + ud) * 7 + t) * nphi + ip) * nmax], nmax * 8);
+      }
+  } else CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  cudaFree(d_g); cudaFree(d_phi); cudaFree(d_out);
+  return nphi;
+}
+
+// ---------------------------------------------------------------------------------------------
 // single-routine operators
 extern "C" int sosgpu_noyaux(sosgpu_ctx *ctx, int is, int nbmu, const double *rmu, int os_nb,
                              const double *alpha, const double *beta, const double *gamma, const double *zeta,

@@ -54,7 +54,7 @@ extern "C" int sosgpu_trphi_option(sosgpu_ctx *ctx, const double *rec, int nrec,
   CK(cudaMemcpyAsync(d_rec, rec, (size_t)nrec * 3 * W * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_rmu, rmu, W * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_phi, phis.data(), nphi * 8, cudaMemcpyHostToDevice, ctx->stream));
-  TrphiGroup g{d_rec, d_rmu, nrec, N, n0, tau, tauout};
+  TrphiGroup g{d_rec, d_rmu, nrec, N, n0, W, tau, tauout};
   CK(cudaMemcpyAsync(d_g, &g, sizeof(g), cudaMemcpyHostToDevice, ctx->stream));
   TrphiParams prm{igli, ifresnel, ipolar, wind, ind_surf, std::acos(-1.0)};
   sos_launch_trphi(d_g, 1, d_phi, nphi, prm, d_out, ctx->stream);

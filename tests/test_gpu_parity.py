@@ -295,3 +295,23 @@ def test_band_properties_at_bench_size(pkg, orc, solver):
         r = oracle_term(orc, wl.optics[t.optics], t)
         assert tr.n_fourier[i] == r.n_fourier and np.array_equal(tr.n_scatter[i, :r.n_fourier], r.n_scatter)
         assert_stokes_close(tr.rec[i, :r.n_fourier], r.rec, "bench-size term %d" % i)
+
+
+def test_batch_trphi_band_solve(pkg, orc, solver):
+    """Band-solve = term-solves + CKD sum + azimuth synthesis, all on the device (sosgpu_batch_trphi)."""
+    syn = pkg.synth
+    wl = syn.config_ckd_band(npoints=3, seed=5, nb_gauss=8, os_nb=16, surface="lambert", rho=0.1, max_terms=5)
+    b = solver.upload(wl)
+    tr, gr = solver.run(b)
+    n, up, down = solver.batch_trphi(b, 0, 2.0, 1.34, 0, 2, 0.0, 30, 1)
+    b.free()
+    assert n == 13
+    o = wl.optics[0]
+    for g in range(3):
+        nr = int(gr.n_rec[g])
+        n0, pf, th, up0, dn0 = orc.trphi_option(gr.rec[g, :nr], o.nbmu, o.rmu, gr.ttot_tronc[g], gr.tauout[g], 0, o.n0,
+                                                2.0, 1.34, 0, 2, 0.0, 30, 1)
+        assert n0 == 13
+        for tb in (1, 2, 3):
+            assert_stokes_close(up[g, tb], up0[tb], "band up %d" % tb)
+            assert_stokes_close(down[g, tb], dn0[tb], "band down %d" % tb)
