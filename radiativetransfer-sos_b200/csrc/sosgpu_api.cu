@@ -68,6 +68,9 @@ struct sosgpu_batch {
   int *h_count = nullptr;           // pinned
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
   sosgpu_stats stats{};
+  // persistent buffers of sosgpu_batch_trphi
+  void *d_tg = nullptr; double *d_tphi = nullptr, *d_tout = nullptr; size_t tout_cap = 0, tphi_cap = 0;
+  std::vector<double> h_tout;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -97,6 +100,7 @@ extern "C" void sosgpu_destroy(sosgpu_ctx *ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  cudaFree(ctx->cache_field); cudaFree(ctx->cache_kpool);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -226,6 +230,7 @@ static void free_batch_device(sosgpu_batch *b)
   cudaFree(b->d_group_start); cudaFree(b->d_group_terms);
   cudaFree(b->d_field); cudaFree(b->d_kpool); cudaFree(b->d_items); cudaFree(b->d_ksets); cudaFree(b->d_item_of);
   cudaFree(b->d_list[0]); cudaFree(b->d_list[1]); cudaFree(b->d_count);
+  cudaFree(b->d_tg); cudaFree(b->d_tphi); cudaFree(b->d_tout);
   if (b->h_count) cudaFreeHost(b->h_count);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
@@ -236,7 +241,12 @@ static void free_batch_device(sosgpu_batch *b)
 extern "C" void sosgpu_batch_free(sosgpu_ctx *ctx, sosgpu_batch *b)
 {
   if (!b) return;
-  if (ctx) cudaSetDevice(ctx->device);
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    // keep the two big pools for the next batch of this context
+    if (b->field_bytes > ctx->cache_field_bytes) { cudaFree(ctx->cache_field); ctx->cache_field = b->d_field; ctx->cache_field_bytes = b->field_bytes; b->d_field = nullptr; }
+    if (b->kpool_bytes > ctx->cache_kpool_bytes) { cudaFree(ctx->cache_kpool); ctx->cache_kpool = b->d_kpool; ctx->cache_kpool_bytes = b->kpool_bytes; b->d_kpool = nullptr; }
+  }
   free_batch_device(b);
   delete b;
 }
@@ -485,6 +495,16 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     }
     const size_t nitem = items.size(), nk = ksets.size();
     // ---- pools ----
+    if (fbytes + sbytes > b->field_bytes && ctx->cache_field_bytes >= fbytes + sbytes) {
+      if (b->d_field) cudaFree(b->d_field);
+      b->d_field = ctx->cache_field; b->field_bytes = ctx->cache_field_bytes;
+      ctx->cache_field = nullptr; ctx->cache_field_bytes = 0;
+    }
+    if (kbytes > b->kpool_bytes && ctx->cache_kpool_bytes >= kbytes) {
+      if (b->d_kpool) cudaFree(b->d_kpool);
+      b->d_kpool = ctx->cache_kpool; b->kpool_bytes = ctx->cache_kpool_bytes;
+      ctx->cache_kpool = nullptr; ctx->cache_kpool_bytes = 0;
+    }
     if (fbytes + sbytes > b->field_bytes) {
       if (b->d_field) cudaFree(b->d_field);
       b->d_field = nullptr; b->field_bytes = 0;
@@ -799,11 +819,11 @@ extern "C" int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *b, int igli, do
     nmax = std::max(nmax, ho.N);
   }
   // note: rmu[N] on the device holds mu_s (index 0), which SOS_TRPHI never reads
-  TrphiGroup *d_g = nullptr; double *d_phi = nullptr, *d_out = nullptr;
   const size_t nout = (size_t)ng * 2 * 7 * nphi * nmax;
-  CK(cudaMalloc(&d_g, ng * sizeof(TrphiGroup)));
-  CK(cudaMalloc(&d_phi, nphi * 8));
-  CK(cudaMalloc(&d_out, nout * 8));
+  if (!b->d_tg) CK(cudaMalloc(&b->d_tg, ng * sizeof(TrphiGroup)));
+  if ((size_t)nphi > b->tphi_cap) { cudaFree(b->d_tphi); b->d_tphi = nullptr; CK(cudaMalloc(&b->d_tphi, nphi * 8)); b->tphi_cap = nphi; }
+  if (nout > b->tout_cap) { cudaFree(b->d_tout); b->d_tout = nullptr; CK(cudaMalloc(&b->d_tout, nout * 8)); b->tout_cap = nout; }
+  TrphiGroup *d_g = (TrphiGroup *)b->d_tg; double *d_phi = b->d_tphi, *d_out = b->d_tout;
   CK(cudaMemcpyAsync(d_g, grp.data(), ng * sizeof(TrphiGroup), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_phi, phis.data(), nphi * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(d_out, 0, nout * 8, ctx->stream));
@@ -811,7 +831,8 @@ extern "C" int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *b, int igli, do
   sos_launch_trphi_stride(d_g, ng, d_phi, nphi, nmax, prm, d_out, ctx->stream);
   ctx->launches += 1;
   if (up || down) {
-    std::vector<double> out(nout);
+    std::vector<double> &out = b->h_tout;
+    out.resize(nout);
     CK(cudaMemcpyAsync(out.data(), d_out, nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int g = 0; g < ng; ++g)
@@ -824,7 +845,6 @@ extern "C" int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *b, int igli, do
       }
   } else CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
-  cudaFree(d_g); cudaFree(d_phi); cudaFree(d_out);
   return nphi;
 }
 

@@ -20,4 +20,7 @@ struct sosgpu_ctx {
   long long launches = 0;
   size_t field_budget = (size_t)48 << 30;
   int max_wave_orders = 0;
+  // device pools handed back by freed batches (cudaMalloc/cudaFree of multi-GB pools cost tens of ms per call)
+  char *cache_field = nullptr; size_t cache_field_bytes = 0;
+  char *cache_kpool = nullptr; size_t cache_kpool_bytes = 0;
 };
