@@ -213,7 +213,7 @@ static int prep_term(const sosgpu_term &t, const HostOptics &o, HostTerm &h, boo
     }
   }
   h.dt.assign(nt + 2, 0.0); h.inv.assign(nt + 2, 0.0);           // +2: TMA copies of the tables are 16-byte granular
-  h.ch.resize(nt + 1); h.cf.resize(nt + 1);
+  h.ch.assign(nt + 2, 0.0); h.cf.assign(nt + 2, 0.0);            // +1: TMA table copies are 16-byte granular
   for (int i = 0; i < nt; ++i) { h.dt[i] = h.h[i + 1] - h.h[i]; h.inv[i] = 1.0 / h.dt[i]; }
   for (int i = 0; i <= nt; ++i) h.ch[i] = std::exp(-h.h[i] / (-o.tab)) / 4.0;   // SOS_OS.F:837-839
   h.eground = std::exp(h.h[nt] / o.tab);
@@ -510,6 +510,10 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
       b->d_field = nullptr; b->field_bytes = 0;
       CK(cudaMalloc(&b->d_field, fbytes + sbytes));
       b->field_bytes = fbytes + sbytes;
+      // Zeroed once per allocation: pad rows / levels / columns of the fields only ever meet zero coefficients of the
+      // packed operators, so they merely have to stay finite (no NaN bit patterns of fresh memory); every valid
+      // element and every per-item state array is rewritten by the order-1 kernel and k_init of each wave.
+      CK(cudaMemsetAsync(b->d_field, 0, fbytes + sbytes, st));
     }
     if (kbytes > b->kpool_bytes) {
       if (b->d_kpool) cudaFree(b->d_kpool);
@@ -517,7 +521,6 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
       CK(cudaMalloc(&b->d_kpool, kbytes));
       b->kpool_bytes = kbytes;
     }
-    CK(cudaMemsetAsync(b->d_field, 0, fbytes + sbytes, st));     // pad rows / levels of the fields must be zero
     CK(cudaMemsetAsync(b->d_kpool, 0, kbytes, st));              // PSL/RSL/TSL rely on zero-initialised storage
     for (size_t i = 0; i < nk; ++i) {
       KsetDev &k = ksets[i];

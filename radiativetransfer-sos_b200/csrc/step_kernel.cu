@@ -106,7 +106,9 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
   double *sXd = sInv + 72;                                              // [64] XDEL of the chunk's levels
   double *sYd = sXd + 72;                                               // [64] YDEL
   double *sU = sYd + 72;                                                // [128] urow of the tile's rows (LR)
-  double *sAtt = sU + 128;                                              // [<=66][N] exp(-dtau/mu_k) (when att_cap > 0)
+  double *sCh = sU + 128;                                               // [64] CH (and [64] CF) of the chunk (ORDER1)
+  double *sC = sCh + 2 * 72;                                            // [4][128] c1, c2, fz1, fz2 of the tile's rows (ORDER1)
+  double *sAtt = sC + 4 * 128;                                          // [<=66][N] exp(-dtau/mu_k) (when att_cap > 0)
 
   const int per_item = 2 * tiles_per_dir;
   const int ii = blockIdx.x / per_item, t = blockIdx.x % per_item;
@@ -139,6 +141,9 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
   }
 
   if (LR && tid < R) sU[tid] = (r0 + tid - dir * HB < 3 * N) ? ks.urow[r0 + tid] : 0.0;
+  if (ORDER1 && tid < R) {
+    sC[tid] = ks.c1[r0 + tid]; sC[128 + tid] = ks.c2[r0 + tid]; sC[256 + tid] = ks.fz1[r0 + tid]; sC[384 + tid] = ks.fz2[r0 + tid];
+  }
   // ---------------- prologue: boundary value of this thread's row (mu > 0 rows only) ----------------
   const int myrow = r0 + tid;                                    // scan threads: tid < R
   const int q = (tid < R) ? (myrow - dir * HB) : 3 * N;
@@ -218,7 +223,11 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       const int nrow = (le - lb_al + 2) & ~1;                      // even count (tables are padded by 2 rows)
       fence_proxy_async();
       const int nlev = (min(SOS_CH, L - c0) + 1) & ~1;             // levels of the chunk, even count
-      mbar_expect_tx(tabbar, (unsigned)(nrow * 16 + nlev * 16 + (att_staged ? nrow * N * 8 : 0)));
+      mbar_expect_tx(tabbar, (unsigned)(nrow * 16 + nlev * 16 + (ORDER1 ? nlev * 16 : 0) + (att_staged ? nrow * N * 8 : 0)));
+      if (ORDER1) {
+        bulk_g2s(sCh, tm.ch + c0, (unsigned)(nlev * 8), tabbar);
+        bulk_g2s(sCh + 72, tm.cf + c0, (unsigned)(nlev * 8), tabbar);
+      }
       bulk_g2s(sXd, tm.xdel + c0, (unsigned)(nlev * 8), tabbar);
       bulk_g2s(sYd, tm.ydel + c0, (unsigned)(nlev * 8), tabbar);
       bulk_g2s(sDt, tm.dt + lb_al, (unsigned)(nrow * 8), tabbar);
@@ -309,19 +318,21 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
     // ---------------- tile epilogue: source function -> staging tile ----------------
     if (ORDER1) {
       __syncthreads();                                           // previous chunk's write-out has finished
-      for (int idx = tid; idx < R * SOS_CH; idx += blockDim.x) {
-        const int rowl = idx >> 6, col = idx & 63;
-        const int level = c0 + col, row = r0 + rowl;
-        double v = 0.0;
-        if (level < L) {
+      mbar_wait(tabbar, chunk & 1);
+      {
+        // one column per thread, rows strided by blockDim/64: level-dependent factors are loaded once
+        const int col = tid & 63, level = c0 + col;
+        const bool lv_ok = level < L;
+        const double chv = lv_ok ? sCh[col] : 0.0, xdv = lv_ok ? sXd[col] : 0.0, ydv = lv_ok ? sYd[col] : 0.0;
+        const bool fr_on = (op.ifresnel == 1) && lv_ok && (up ? (level <= NT - 1) : (level >= 1));
+        const double cfv = fr_on ? sCh[72 + col] : 0.0;
+        for (int rowl = tid >> 6; rowl < R; rowl += (blockDim.x >> 6)) {
           // SOS_FSOURCE_ORDRE1 (SOS_OS.F:2553-2560): ATTDIR*(S2*PCAER + S1*PCRAY)
-          v = __dmul_rn(tm.ch[level], __dadd_rn(__dmul_rn(ks.c2[row], tm.xdel[level]), __dmul_rn(ks.c1[row], tm.ydel[level])));
-          if (op.ifresnel == 1) {                                // SOS_FSOURCE_DIFF_FRESNEL1 (SOS_OS.F:3224-3292)
-            const bool on = up ? (level <= NT - 1) : (level >= 1);
-            if (on) v = v + tm.cf[level] * (ks.fz2[row] * tm.xdel[level] + ks.fz1[row] * tm.ydel[level]);
-          }
+          double v = __dmul_rn(chv, __dadd_rn(__dmul_rn(sC[128 + rowl], xdv), __dmul_rn(sC[rowl], ydv)));
+          // SOS_FSOURCE_DIFF_FRESNEL1 (SOS_OS.F:3224-3292)
+          if (fr_on) v = v + cfv * (sC[384 + rowl] * xdv + sC[256 + rowl] * ydv);
+          sJ[rowl * SOS_SJ + col] = lv_ok ? v : 0.0;
         }
-        sJ[rowl * SOS_SJ + col] = v;
       }
     } else {
       if (wr < ng) {
@@ -486,7 +497,7 @@ static size_t step_smem_bytes(int nw, int lr, int order1, int att_cap)
   const size_t stage = STAGE_A_BYTES(rows) + (lr ? STAGE_V_BYTES : 0) + STAGE_B_BYTES;
   const size_t pipe = order1 ? 0 : SOS_STAGES * stage;
   const size_t sj = rows * SOS_SJ * 8;
-  return (pipe > sj ? pipe : sj) + (4 * SOS_CH + 3 * 80) * 8 + (2 * SOS_STAGES + 2) * 8 + (4 * 72 + 128 + att_cap) * 8 + 128;
+  return (pipe > sj ? pipe : sj) + (4 * SOS_CH + 3 * 80) * 8 + (2 * SOS_STAGES + 2) * 8 + (6 * 72 + 128 + 4 * 128 + att_cap) * 8 + 128;
 }
 
 extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const OpticsDev *optics,

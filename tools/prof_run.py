@@ -27,3 +27,10 @@ for r in range(runs):
              st["flops"] / max(st["step_ms"], 1e-9) / 1e9, st["steps"], len(wl.terms)))
 b.free()
 s.close()
+
+# useful vs executed contraction steps (Fourier orders computed beyond the Fourier stop are discarded work)
+s2 = api.Solver(0)
+tr, _ = s2.solve(wl, want_groups=False, want_rec=False)
+useful = sum(int(max(tr.n_scatter[i, k] - 1, 0)) for i in range(len(wl.terms)) for k in range(tr.n_fourier[i]))
+print("useful steps %d of %d executed (%.1f%%); n_fourier min/mean/max %d/%.1f/%d" %
+      (useful, st["steps"], 100.0 * useful / st["steps"], tr.n_fourier.min(), tr.n_fourier.mean(), tr.n_fourier.max()))
