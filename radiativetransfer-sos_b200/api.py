@@ -341,3 +341,57 @@ class Solver:
         if n < 0:
             self._check(n, "batch_trphi")
         return n, up, down
+
+    def transmissions(self, workload, term_ids=None):
+        """The -SOS.Trans branch of SOS (SOS.F:605-637): diffuse transmissions of the equivalent atmosphere for the
+        solar direction (TDIFMUS) and for every Gauss direction (TDIFMUG(1:N)): 1+N extra SOS_OS solves per term
+        with a black surface, IBORM=0, the truncation-adapted profile, and N0 = J.  All of them go to the GPU as one
+        SOS_OS-level batch.  Returns (tdifmus[nterm], tdifmug[nterm, N])."""
+        import copy
+        from .synth import Term, Workload
+        terms = workload.terms if term_ids is None else [workload.terms[i] for i in term_ids]
+        wl2 = Workload("trans")
+        variants = {}
+        index = []
+        for t in terms:
+            o = workload.optics[t.optics]
+            if id(o) not in variants:
+                vs = []
+                for n0 in [o.n0] + list(range(1, o.nbmu + 1)):
+                    v = copy.copy(o)
+                    v.n0, v.rho, v.imat_surf, v.ifresnel, v.zout, v.surf = n0, 0.0, 0, 0, -1.0, None
+                    wl2.optics.append(v)
+                    vs.append(len(wl2.optics) - 1)
+                variants[id(o)] = vs
+            # truncation adaptation of the profile (SOS.F:523-543), same statement order
+            h, xd, yd = _f64(t.h).copy(), _f64(t.pcaer).copy(), _f64(t.pcmol).copy()
+            if o.a_trunc != 0.0:
+                htr = np.zeros_like(h)
+                htr[0] = h[0]
+                for i in range(1, h.size):
+                    dh = h[i] - h[i - 1]
+                    va = xd[i] * dh
+                    vatr = va * (1 - o.piz * 0.5 * o.a_trunc)
+                    vr = yd[i] * dh
+                    vg = (1 - xd[i] - yd[i]) * dh
+                    htr[i] = (vatr + vr + vg) + htr[i - 1]
+                    xd[i] = vatr / (vatr + vr + vg)
+                    yd[i] = vr / (vatr + vr + vg)
+                h = htr
+            xd = xd * o.piztr
+            first = len(wl2.terms)
+            for vi in variants[id(o)]:
+                wl2.terms.append(Term(vi, 1.0, t.zprof, h, xd, yd))
+            index.append((first, o.nbmu))
+        b = self.upload(wl2, os_level=True, iborm=[0] * len(wl2.terms))
+        try:
+            tr, _ = self.run(b, want_groups=False, want_rec=False)
+        finally:
+            b.free()
+        nmax = max(n for _, n in index)
+        tdifmus = np.zeros(len(terms))
+        tdifmug = np.zeros((len(terms), nmax))
+        for i, (first, n) in enumerate(index):
+            tdifmus[i] = tr.emoins[first]                # EMOINS of the black-surface IS=0 solve (SOS.F:611-616)
+            tdifmug[i, :n] = tr.emoins[first + 1:first + 1 + n]
+        return tdifmus, tdifmug

@@ -315,3 +315,15 @@ def test_batch_trphi_band_solve(pkg, orc, solver):
         for tb in (1, 2, 3):
             assert_stokes_close(up[g, tb], up0[tb], "band up %d" % tb)
             assert_stokes_close(down[g, tb], dn0[tb], "band down %d" % tb)
+
+
+def test_transmissions(pkg, orc, solver):
+    """-SOS.Trans (SOS.F:605-637): TDIFMUS and TDIFMUG(1:N) from 1+N black-surface IS=0 solves per term."""
+    syn = pkg.synth
+    o = syn.make_optics(nb_gauss=8, tetas=35.0, os_nb=16, surface="brdf", rho=0.05)
+    wl = syn.Workload("trans", [o], [syn.Term(0, 1.0, *syn.profile(0.05, 8.0, 0.2, 2.0, 0.3))])
+    r = oracle_term(orc, o, wl.terms[0], want_trans=True)
+    tdifmus, tdifmug = solver.transmissions(wl)
+    N = o.nbmu
+    assert_stokes_close(tdifmus[0], r.tdifmus, "TDIFMUS")
+    assert_stokes_close(tdifmug[0], r.tdifmug[N + 1:], "TDIFMUG")
