@@ -81,6 +81,40 @@ __device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, doub
                : "d"(a), "d"(b));
 }
 
+// DMMAs of one k-slab for one warp: warp tile 16 rows x (8*NFR) levels (2 x NFR fragments of 8x8, K = 16 in 4 steps).
+// NFR = column blocks (8 levels) of the chunk that hold real levels; k-steps >= ks_lim only touch zero padding.
+template <int NFR, int LR>
+__device__ __forceinline__ void slab_mma(double (&acc)[2][8][2], double (&tacc)[2][2], const double *__restrict__ a,
+                                         const double *__restrict__ v, const double *__restrict__ b, bool own, int wr,
+                                         int nwl, int gq, int tq, int ks_lim)
+{
+  const int swz = 4 * (gq & 3);
+#pragma unroll
+  for (int ks4 = 0; ks4 < SOS_KB / 4; ++ks4) {
+    if (ks4 >= ks_lim) break;                                // uniform; false for 14 of 16 slabs
+    const int kc = (ks4 * 4 + tq) ^ swz;
+    if (own) {
+      const double a0 = a[kc], a1 = a[8 * SOS_KB + kc];
+      double bv[NFR];
+#pragma unroll
+      for (int ni = 0; ni < NFR; ++ni) bv[ni] = b[ks4 * 4 * SOS_SB + ni * 8];
+#pragma unroll
+      for (int ni = 0; ni < NFR; ++ni) {
+        dmma8x8x4(acc[0][ni][0], acc[0][ni][1], a0, bv[ni]);
+        dmma8x8x4(acc[1][ni][0], acc[1][ni][1], a1, bv[ni]);
+      }
+    }
+    if (LR) {                                                // T = V X: this warp's share of the 8 column blocks
+      const double av = v[kc];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int ni = wr + u * nwl;
+        if (ni < NFR) dmma8x8x4(tacc[u][0], tacc[u][1], av, b[ks4 * 4 * SOS_SB + ni * 8]);
+      }
+    }
+  }
+}
+
 template <int LR, int ORDER1>
 __global__ void __launch_bounds__(256, 2)
 k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, const OpticsDev *__restrict__ optics,
@@ -258,6 +292,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
         for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
       tacc[0][0] = tacc[0][1] = tacc[1][0] = tacc[1][1] = 0.0;
 
+      const int nfr = (min(SOS_CH, L - c0) + 7) >> 3;              // column blocks (8 levels) that hold real levels
       for (int slab = 0; slab < n_slab; ++slab) {
         const unsigned cnt = it_count + slab;
         const int stage = cnt % SOS_STAGES;
@@ -268,34 +303,24 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
         }
         mbar_wait(full + stage, (cnt / SOS_STAGES) & 1);
         if ((wr < ng || LR) && !(dbg & 1)) {
-          const bool own = wr < ng;                                // warps beyond ng only help with T = V X
           const unsigned char *sp = smem_raw + stage * stage_bytes;
           const double *a = reinterpret_cast<const double *>(sp) + (wr * 16 + gq) * SOS_KB;
           const double *v = reinterpret_cast<const double *>(sp + STAGE_A_BYTES(rows_max)) + gq * SOS_KB;
           const double *b = reinterpret_cast<const double *>(sp + STAGE_A_BYTES(rows_max) + (LR ? STAGE_V_BYTES : 0)) + tq * SOS_SB + gq;
-          const int swz = 4 * (gq & 3);
-#pragma unroll
-          for (int ks4 = 0; ks4 < SOS_KB / 4; ++ks4) {
-            const int kc = (ks4 * 4 + tq) ^ swz;
-            if (own) {
-              const double a0 = a[kc], a1 = a[8 * SOS_KB + kc];
-              double bv[8];
-#pragma unroll
-              for (int ni = 0; ni < 8; ++ni) bv[ni] = b[ks4 * 4 * SOS_SB + ni * 8];
-#pragma unroll
-              for (int ni = 0; ni < 8; ++ni) {
-                dmma8x8x4(acc[0][ni][0], acc[0][ni][1], a0, bv[ni]);
-                dmma8x8x4(acc[1][ni][0], acc[1][ni][1], a1, bv[ni]);
-              }
-            }
-            if (LR) {                                              // T = V X: this warp's share of the 8 column blocks
-              const double av = v[kc];
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int ni = wr + u * nw_launch;
-                if (ni < 8) dmma8x8x4(tacc[u][0], tacc[u][1], av, b[ks4 * 4 * SOS_SB + ni * 8]);
-              }
-            }
+          // k-steps that only touch the zero padding of a direction block contribute nothing: ks_lim of this slab
+          const int kq = (slab * SOS_KB) % HB;
+          const int ks_lim = (kq + SOS_KB <= 3 * N) ? 4 : max(0, (3 * N - kq + 3) >> 2);
+          const bool own = wr < ng;
+          // column blocks (8 levels) beyond the profile are skipped: one unrolled, predicate-free body per count
+          switch (nfr) {
+            case 8: slab_mma<8, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+            case 7: slab_mma<7, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+            case 6: slab_mma<6, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+            case 5: slab_mma<5, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+            case 4: slab_mma<4, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+            case 3: slab_mma<3, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+            case 2: slab_mma<2, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+            default: slab_mma<1, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
           }
         }
         __syncwarp();
