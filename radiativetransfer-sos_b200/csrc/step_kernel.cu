@@ -25,6 +25,7 @@
 #include <math.h>
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 
 #define STAGE_A_BYTES(rows) ((rows) * SOS_KB * 8)
 #define STAGE_V_BYTES (8 * SOS_KB * 8)
@@ -246,6 +247,13 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
   double scarry = 0.0;                                            // source function at the neighbouring level of the previous chunk (pass 1)
   unsigned it_count = 0;                                          // global slab counter (mbarrier phases)
 
+#ifdef SOS_PHASE_TIMING   // build with -DSOS_PHASE_TIMING and run with SOS_DBG=16: cycles per phase as seen by thread 0
+  long long tph[5] = {0, 0, 0, 0, 0}, tmark = clock64();
+  const long long tstart = tmark;
+#define TPH(i) do { if (dbg & 16) { const long long now_ = clock64(); tph[i] += now_ - tmark; tmark = now_; } } while (0)
+#else
+#define TPH(i) do { } while (0)
+#endif
   for (int chunk = 0; chunk < n_chunk; ++chunk) {
     const int ci = up ? (n_chunk - 1 - chunk) : chunk;
     const int c0 = ci * SOS_CH;
@@ -328,6 +336,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       }
       it_count += n_slab;
       __syncthreads();                                             // pipeline drained: stages may be reused as sJ
+      TPH(0);
       mbar_wait(tabbar, chunk & 1);                                // XDEL/YDEL and layer tables of this chunk have landed
       if (LR && gq < 4) {
 #pragma unroll
@@ -407,6 +416,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       __syncthreads();
     }
 
+    TPH(1);
     // ---------------- SOS_INTEGR_EPOPT on the tile (SOS_OS.F:2279-2310 up, 2320-2354 down) ----------------
     // The layer update is z <- z*a + c with c = (1-a)*(A*mu + S) -/+ A*(a*dtau), A = dS/dtau independent of z.
     // Pass 1 (all threads, two per row, 32 levels each): c replaces S in the staging tile.
@@ -437,29 +447,37 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       }
       __syncwarp();
       if (valid2) {
-        double s = s_edge;
+        // four independent columns per iteration (the loop is latency bound: few warps, long FP64 chains)
         if (up) {
-          for (int i = lo_c; i <= hi_c; ++i) {                     // ascending: S(i+1) is still unmodified
-            const double sn = (i < hi_c) ? js[i + 1] : bnd;
-            const int lv = c0 + i;
-            if (lv < NT) {
+          for (int i = lo_c; i <= hi_c; i += 4) {                  // ascending: S(i+1) is still unmodified
+            double sv[5], cv[4];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) { const int c = i + u; sv[u] = (c <= hi_c) ? js[c] : ((c == hi_c + 1) ? bnd : 0.0); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int lv = min(c0 + i + u, NT - 1);
               const double a = att[(size_t)lv * N], dl = dtp[lv], iv = ivp[lv];
-              const double A = (sn - s) * iv;
-              js[i] = (1.0 - a) * (A * mu2 + s) - A * (a * dl);
+              const double A = (sv[u + 1] - sv[u]) * iv;
+              cv[u] = (1.0 - a) * (A * mu2 + sv[u]) - A * (a * dl);
             }
-            s = sn;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (i + u <= hi_c && c0 + i + u < NT) js[i + u] = cv[u];
           }
         } else {
           const double rmuk = -mu2;
-          for (int i = hi_c; i >= lo_c; --i) {                     // descending: S(i-1) is still unmodified
-            const double sp = (i > lo_c) ? js[i - 1] : bnd;
-            const int lv = c0 + i;
-            if (lv > 0) {
+          for (int i = hi_c; i >= lo_c; i -= 4) {                  // descending: S(i-1) is still unmodified
+            double sv[5], cv[4];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) { const int c = i - u; sv[u] = (c >= lo_c) ? js[c] : ((c == lo_c - 1) ? bnd : 0.0); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int lv = max(c0 + i - u, 1);
               const double a = att[(size_t)(lv - 1) * N], dl = dtp[lv - 1], iv = ivp[lv - 1];
-              const double A = (s - sp) * iv;
-              js[i] = (1.0 - a) * (A * rmuk + s) + A * (a * dl);
+              const double A = (sv[u] - sv[u + 1]) * iv;
+              cv[u] = (1.0 - a) * (A * rmuk + sv[u]) + A * (a * dl);
             }
-            s = sp;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (i - u >= lo_c && c0 + i - u > 0) js[i - u] = cv[u];
           }
         }
       }
@@ -468,6 +486,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       if (half == (up ? 1 : 0)) scarry = give;
     }
     __syncthreads();
+    TPH(2);
     if (rowvalid) {
       double *js = sJ + tid * SOS_SJ;
       const double *att = att_staged ? (sAtt + (kk - 1) - (size_t)lb_al * N) : (tm.att + (kk - 1));
@@ -506,6 +525,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
     }
     __syncthreads();
 
+    TPH(3);
     // ---------------- write the new field tile (coalesced along levels) ----------------
     for (int idx = tid; idx < R * SOS_CH; idx += blockDim.x) {
       const int rowl = idx >> 6, col = idx & 63;
@@ -513,7 +533,14 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       if (level < L && (row - dir * HB) < 3 * N) xnext[SOS_XIDX(KP, row, level)] = sJ[rowl * SOS_SJ + col];
     }
     __syncthreads();                                             // sJ is free again (next chunk's TMA may overwrite it)
+    TPH(4);
   }
+#ifdef SOS_PHASE_TIMING
+  if ((dbg & 16) && tid == 0 && (blockIdx.x % 997) == 0)
+    printf("cta %d chunks %d: mainloop %lld store %lld pass1 %lld pass2 %lld writeout %lld total %lld\n", (int)blockIdx.x, n_chunk,
+           tph[0], tph[1], tph[2], tph[3], tph[4], clock64() - tstart);
+#endif
+#undef TPH
 }
 
 static size_t step_smem_bytes(int nw, int lr, int order1, int att_cap)
