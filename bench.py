@@ -31,6 +31,8 @@ PKG = "radiativetransfer-sos_b200"
 POINTS_PER_GPU = int(os.environ.get("SOS_BENCH_POINTS", "96"))
 NB_GAUSS, OS_NB = 40, 80
 METRIC = "polarized SOS spectral solves/sec"
+# DRAM traffic of one full-width k_step launch of this workload, from the ncu --set full capture under profiles/
+NCU_TRAFFIC_BYTES = 4.157373e9 + 2.000106e9
 UNIT = "spectral points/s"
 
 
@@ -301,7 +303,10 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "k_step (FP64 DMMA source-function contraction fused with the "
                          "layer recurrence)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None, "traffic": NCU_TRAFFIC_BYTES,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one full-width k_step<0,0> "
+                                           "launch (9920 CTAs, 4.9 ms under ncu) from the committed capture "
+                                           "profiles/r1_kstep_ncu_full_summary.txt; not measured live",
                          "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 "
                                         "entry)",
                          "algorithmic": "2*(6N)^2*(NT+1) FLOP per (term, Fourier order, scattering order>=2)",

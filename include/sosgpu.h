@@ -202,6 +202,46 @@ void sos_aggregate_(const int *nbmu, const double *aik, const char *ficos_tmp,
                     double *emoins, double *eplus, int *ier,
                     size_t len_ficos_tmp, size_t len_ficos_agg_tmp, size_t len_ficos);
 
+/* SOS.F:340-345 (hidden lengths in order of appearance: FICOS, FICTRANS, FICPROFIL, FICSURF).  Reads FICPROFIL,
+ * writes FICOS; FICTRANS is only compared with 'NO_OUTPUT' (the transmissions come back in TDIFMUS/TDIFMUG) */
+void sos_(const char *ficos, const char *fictrans, const char *ficprofil,
+          const int *nt, const double *zout, const int *igmax, const int *ipolar, const double *ron,
+          const double *ind_surf, const double *rho, const int *imat_surf, const int *ifresnel,
+          const char *ficsurf, const int *n0, const double *piz, const double *piztr, const double *a,
+          double *rmu, const double *ga, const double *tetas, const int *os_nb, const int *lum_nbmu,
+          double *alpha, double *beta, double *gamma, double *zeta,
+          double *ttot_tronc, double *ttot_vrai, double *tauout, double *tdifmus, double *tdifmug,
+          double *emoins, double *eplus, const int *trace, const int *idlog, int *ier,
+          size_t len_ficos, size_t len_fictrans, size_t len_ficprofil, size_t len_ficsurf);
+/* SOS_GLITTER.F:229-233: writes FICGLITTER (must not pre-exist); the three intermediate files are never created */
+void sos_glitter_(const int *lum_nbmu, const double *rmu, const double *chr, const double *wind,
+                  const double *ind, const int *os_nb, const int *os_ns, const int *os_nm,
+                  const char *fic_res_gsf, const char *fic_res_fresnel, const char *fic_res_mat_reflex,
+                  const char *ficglitter, const int *trace, int *ier,
+                  size_t len_gsf, size_t len_fresnel, size_t len_mat, size_t len_ficglitter);
+/* SOS_TRPHI.F:749-755: one azimuth (radians); IER=-1 when a Roujean/Rondeaux/Breon/Nadal/Maignan direct term is
+ * requested (not provided) */
+void sos_trphi_(const char *fichos, const int *nbmu, const double *rmu, const double *tau,
+                const double *tauout, const double *phi, const int *igli, const int *n0, const double *wind,
+                const double *ind_surf, const int *ifresnel, const int *iroujean, const double *k0,
+                const double *k1, const double *k2, const int *irondeaux, const int *ibreon,
+                const int *inadal, const double *alpha_nadal, const double *beta_nadal, const int *imaignan,
+                const double *coef_c_maignan, const int *ipolar, double *xit, double *xqt, double *xut,
+                double *angdiff, int *ier, size_t len_fichos);
+/* SOS_TRPHI.F:285-300: tables with the reference's extents PHI_FIN(0:360), THETA_FIN(0:80), X_FIN(0:360,0:80) */
+void sos_trphi_option_(const int *nbmu, const double *rmu, const double *ga, const char *fichos,
+                       const double *tau, const double *tauout, const double *zout, const int *igli,
+                       const int *n0, const double *wind, const double *ind_surf, const int *ifresnel,
+                       const int *iroujean, const double *k0, const double *k1, const double *k2,
+                       const int *irondeaux, const int *ibreon, const int *inadal, const double *alpha_nadal,
+                       const double *beta_nadal, const int *imaignan, const double *coef_c_maignan,
+                       const int *itrphi, const double *phios, const int *pas_phi, const int *ipolar,
+                       double *phi_fin, double *theta_fin,
+                       double *sca_up, double *i_up, double *q_up, double *u_up, double *pol_ang_up,
+                       double *pol_rate_up, double *l_pol_up,
+                       double *sca_down, double *i_down, double *q_down, double *u_down, double *pol_ang_down,
+                       double *pol_rate_down, double *l_pol_down, int *ier, size_t len_fichos);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,7 @@
 // sosgpu_shims.cu -- (1) azimuth synthesis entry points (SOS_TRPHI_OPTION), single wavelength and batched over the
-// resident group sums; (2) gfortran-ABI drop-in symbols sos_os_ / sos_aggregate_ that keep the reference's
-// argument lists, fixed SOS.h strides and file side effects (SOS_OS.F:303-308, SOS_AGGREGATE.F:172-178).
+// resident group sums; (2) gfortran-ABI drop-in symbols sos_ / sos_os_ / sos_aggregate_ / sos_glitter_ / sos_trphi_ /
+// sos_trphi_option_ that keep the reference's argument lists, fixed SOS.h strides and file side effects
+// (SOS.F:340-345, SOS_OS.F:303-308, SOS_AGGREGATE.F:172-178, SOS_GLITTER.F:229-233, SOS_TRPHI.F:285-300,749-755).
 #include "sosgpu_host.h"
 #include "post_kernels.h"
 
@@ -31,18 +32,13 @@ static int phis_of(int itrphi, double phios, int pas_phi, std::vector<double> &p
   return (int)phis.size();
 }
 
-extern "C" int sosgpu_trphi_option(sosgpu_ctx *ctx, const double *rec, int nrec, int nbmu, const double *rmu,
-                                   double tau, double tauout, int igli, int n0, double wind, double ind_surf,
-                                   int ifresnel, int itrphi, double phios, int pas_phi, int ipolar,
-                                   double *phi_fin, double *theta_fin, double *up, double *down, int nphi_cap)
+// Synthesis of one wavelength on a list of azimuths (radians): out = [2 (up, down)][7][nphi][N]
+static int trphi_core(sosgpu_ctx *ctx, const double *rec, int nrec, int N, const double *rmu, double tau, double tauout,
+                      int igli, int n0, double wind, double ind_surf, int ifresnel, int ipolar,
+                      const std::vector<double> &phis, std::vector<double> &out)
 {
-  if (!ctx) return SOSGPU_ERR_NO_DEVICE;
-  if (!rec || nrec < 1 || nbmu < 1 || nbmu > SOSGPU_NBMU_MAX || n0 < 1 || n0 > nbmu) return SOSGPU_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  const int N = nbmu, W = 2 * N + 1;
-  std::vector<double> phis, pf;
-  const int nphi = phis_of(itrphi, phios, pas_phi, phis, pf);
-  if (nphi < 1 || nphi > nphi_cap) return SOSGPU_ERR_ARG;
+  const int W = 2 * N + 1, nphi = (int)phis.size();
   double *d_rec = nullptr, *d_rmu = nullptr, *d_phi = nullptr, *d_out = nullptr;
   TrphiGroup *d_g = nullptr;
   const size_t nout = (size_t)2 * 7 * nphi * N;
@@ -59,10 +55,27 @@ extern "C" int sosgpu_trphi_option(sosgpu_ctx *ctx, const double *rec, int nrec,
   TrphiParams prm{igli, ifresnel, ipolar, wind, ind_surf, std::acos(-1.0)};
   sos_launch_trphi(d_g, 1, d_phi, nphi, prm, d_out, ctx->stream);
   ctx->launches += 1;
-  std::vector<double> out(nout);
+  out.resize(nout);
   CK(cudaMemcpyAsync(out.data(), d_out, nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
+  cudaFree(d_rec); cudaFree(d_rmu); cudaFree(d_phi); cudaFree(d_out); cudaFree(d_g);
+  return SOSGPU_OK;
+}
+
+extern "C" int sosgpu_trphi_option(sosgpu_ctx *ctx, const double *rec, int nrec, int nbmu, const double *rmu,
+                                   double tau, double tauout, int igli, int n0, double wind, double ind_surf,
+                                   int ifresnel, int itrphi, double phios, int pas_phi, int ipolar,
+                                   double *phi_fin, double *theta_fin, double *up, double *down, int nphi_cap)
+{
+  if (!ctx) return SOSGPU_ERR_NO_DEVICE;
+  if (!rec || nrec < 1 || nbmu < 1 || nbmu > SOSGPU_NBMU_MAX || n0 < 1 || n0 > nbmu) return SOSGPU_ERR_ARG;
+  const int N = nbmu;
+  std::vector<double> phis, pf, out;
+  const int nphi = phis_of(itrphi, phios, pas_phi, phis, pf);
+  if (nphi < 1 || nphi > nphi_cap) return SOSGPU_ERR_ARG;
+  const int rc = trphi_core(ctx, rec, nrec, N, rmu, tau, tauout, igli, n0, wind, ind_surf, ifresnel, ipolar, phis, out);
+  if (rc != SOSGPU_OK) return rc;
   // [2][7][nphi][N] -> caller tables [7][nphi_cap][N]
   for (int ud = 0; ud < 2; ++ud) {
     double *dst = ud == 0 ? up : down;
@@ -74,7 +87,6 @@ extern "C" int sosgpu_trphi_option(sosgpu_ctx *ctx, const double *rec, int nrec,
   const double pi = std::acos(-1.0);
   if (phi_fin) for (int ip = 0; ip < nphi; ++ip) phi_fin[ip] = pf[ip];
   if (theta_fin) for (int j = 1; j <= N; ++j) theta_fin[j - 1] = std::acos(rmu[j + N]) * 180.0 / pi;   // :508,573
-  cudaFree(d_rec); cudaFree(d_rmu); cudaFree(d_phi); cudaFree(d_out); cudaFree(d_g);
   return nphi;
 }
 
@@ -247,6 +259,7 @@ static bool write_records(const std::string &path, const double *rec, int nrec, 
 #define NBMU_MAX SOSGPU_NBMU_MAX
 #define NB_MAX SOSGPU_NB_MAX
 #define NT_MAX SOSGPU_NT_MAX
+#define SOSGPU_THRESHOLD_Q_U_NULL 1.0e-15   /* CTE_THRESHOLD_Q_U_NULL, SOS.h:418 */
 
 extern "C" int sosgpu_batch_upload_os(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics,
                                       const sosgpu_term *terms, int nterm, int ngroup, const int *iborm,
@@ -371,4 +384,273 @@ extern "C" void sos_aggregate_(const int *nbmu, const double *aik, const char *f
   *ttot_vrai = -std::log(trans);
   trans = (*tauout != 0) ? (*aik) * std::exp(-*tauout_tmp) + std::exp(-*tauout) : (*aik) * std::exp(-*tauout_tmp);
   *tauout = -std::log(trans);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SOS.F:340-345.  Reads PROFIL_TMP (format 70: 2X,I5,F10.5,3(E15.8), :511-516), applies the truncation
+// adaptation (:523-543), solves through sos_os_ (so FICOS / FICSURF and the caller-visible side effects behave
+// as there), derives TAUOUT / TTOT_* (:518,567-586) and, when FICTRANS is not 'NO_OUTPUT', the 1+N black-surface
+// IBORM=0 solves of the -SOS.Trans branch (:605-637) as ONE device batch.
+static bool parse_field(const std::string &line, size_t pos, size_t len, double &v)
+{
+  if (line.size() < pos + 1) return false;
+  std::string f = line.substr(pos, len);
+  for (auto &c : f) if (c == 'D' || c == 'd') c = 'E';
+  char *end = nullptr;
+  v = std::strtod(f.c_str(), &end);
+  return end != f.c_str();
+}
+
+extern "C" void sos_(const char *ficos, const char *fictrans, const char *ficprofil,
+                     const int *nt, const double *zout, const int *igmax, const int *ipolar, const double *ron,
+                     const double *ind_surf, const double *rho, const int *imat_surf, const int *ifresnel,
+                     const char *ficsurf, const int *n0, const double *piz, const double *piztr, const double *a,
+                     double *rmu, const double *ga, const double *tetas, const int *os_nb, const int *lum_nbmu,
+                     double *alpha, double *beta, double *gamma, double *zeta,
+                     double *ttot_tronc, double *ttot_vrai, double *tauout, double *tdifmus, double *tdifmug,
+                     double *emoins, double *eplus, const int *trace, const int *idlog, int *ier,
+                     size_t len_ficos, size_t len_fictrans, size_t len_ficprofil, size_t len_ficsurf)
+{
+  *ier = 0;
+  const int NT = *nt, N = *lum_nbmu, NB = *os_nb;
+  if (NT < 1 || NT > NT_MAX || N < 1 || N > NBMU_MAX || NB > NB_MAX) { *ier = -1; return; }
+  std::vector<double> zprof(NT_MAX + 1, 0.0), h(NT_MAX + 1, 0.0), xdel(NT_MAX + 1, 0.0), ydel(NT_MAX + 1, 0.0),
+      htr(NT_MAX + 1, 0.0);
+  {
+    FILE *f = fopen(fstr(ficprofil, len_ficprofil).c_str(), "r");
+    if (!f) { fprintf(stdout, "  ERROR on PROFILE file opening for SOS\n"); *ier = -1; return; }
+    char buf[512];
+    for (int i = 0; i <= NT; ++i) {
+      bool ok = fgets(buf, sizeof buf, f) != nullptr;
+      if (ok) {
+        const std::string line(buf);
+        ok = parse_field(line, 7, 10, zprof[i]) && parse_field(line, 17, 15, h[i]) &&
+             parse_field(line, 32, 15, xdel[i]) && parse_field(line, 47, 15, ydel[i]);
+      }
+      if (!ok) { fclose(f); fprintf(stdout, "  ERROR on PROFILE file reading for SOS\n"); *ier = -1; return; }
+    }
+    fclose(f);
+  }
+  *ttot_vrai = h[NT];                                          // :518
+  bool lta = true;
+  htr[0] = h[0];
+  if (*a != 0.0) {                                             // :525-537
+    for (int i = 1; i <= NT; ++i) {
+      const double dh = h[i] - h[i - 1];
+      const double va = xdel[i] * dh;
+      const double vatr = va * (1 - (*piz) * 0.5 * (*a));
+      const double vr = ydel[i] * dh;
+      const double vg = (1 - xdel[i] - ydel[i]) * dh;
+      htr[i] = (vatr + vr + vg) + htr[i - 1];
+      xdel[i] = vatr / (vatr + vr + vg);
+      ydel[i] = vr / (vatr + vr + vg);
+    }
+  }
+  for (int i = 0; i <= NT; ++i) {                              // :539-543
+    if (*a != 0.0) h[i] = htr[i];
+    xdel[i] = xdel[i] * (*piztr);
+    if (xdel[i] != 0.0) lta = false;
+  }
+  const int iborm = lta ? 2 : NB;                              // :549-550
+  sos_os_(lum_nbmu, rmu, ga, os_nb, nt, ficsurf, ficos, n0, tetas, rho, imat_surf, ifresnel, ind_surf,
+          h.data(), xdel.data(), ydel.data(), zprof.data(), ron, alpha, beta, gamma, zeta, zout, igmax, &iborm, ipolar,
+          trace, idlog, emoins, eplus, ier, len_ficsurf, len_ficos);
+  if (*ier != 0) { fprintf(stdout, "  ERROR on subroutine SOS_OS\n"); *ier = -1; return; }
+  if (*zout == -1) *tauout = h[0];                             // :567-583
+  else {
+    int j = 1;
+    while (j < NT && *zout < zprof[j]) ++j;
+    const double zz = (*zout - zprof[j - 1]) / (zprof[j] - zprof[j - 1]);
+    *tauout = (1 - zz) * h[j - 1] + zz * h[j];
+  }
+  *ttot_tronc = h[NT];                                         // :586
+  if (fstr(fictrans, len_fictrans) == "NO_OUTPUT") return;
+
+  // -SOS.Trans (:605-637): SOS_OS with RO=0, no surface matrix, no Fresnel, ZOUT=-1, IBORM=0 for the solar
+  // direction and then for N0 = 1..N; TDIFMUS / TDIFMUG(J) are the EMOINS of those solves.
+  sosgpu_ctx *ctx = shim_ctx();
+  if (!ctx) { *ier = -1; return; }
+  const int W = 2 * N + 1;
+  std::vector<double> rmu_c(W), ga_c(W);
+  for (int j = -N; j <= N; ++j) { rmu_c[j + N] = rmu[j + NBMU_MAX]; ga_c[j + N] = ga[j + NBMU_MAX]; }
+  std::vector<sosgpu_optics> ov(N + 1);
+  std::vector<sosgpu_term> tv(N + 1);
+  std::vector<int> ib(N + 1, 0);
+  for (int j = 0; j <= N; ++j) {
+    sosgpu_optics &o = ov[j];
+    o = sosgpu_optics{};
+    o.nbmu = N; o.rmu = rmu_c.data(); o.ga = ga_c.data(); o.n0 = (j == 0) ? *n0 : j; o.tetas = *tetas; o.os_nb = NB;
+    o.alpha = alpha; o.beta = beta; o.gamma = gamma; o.zeta = zeta; o.a_trunc = 0.0; o.piz = 1.0; o.piztr = 1.0;
+    o.ron = *ron; o.rho = 0.0; o.imat_surf = 0; o.ifresnel = 0; o.ind_surf = *ind_surf; o.surf = nullptr; o.n_surf_rec = 0;
+    o.igmax = *igmax; o.ipolar = *ipolar; o.zout = -1.0;
+    sosgpu_term &t = tv[j];
+    t = sosgpu_term{};
+    t.optics = j; t.group = 0; t.aik = 1.0; t.nt = NT; t.zprof = zprof.data(); t.h = h.data(); t.pcaer = xdel.data();
+    t.pcmol = ydel.data();
+  }
+  sosgpu_batch *b = nullptr;
+  int rc = sosgpu_batch_upload_os(ctx, ov.data(), N + 1, tv.data(), N + 1, 1, ib.data(), &b);
+  std::vector<double> em(N + 1, 0.0);
+  std::vector<int> ierv(N + 1, 0);
+  if (rc == SOSGPU_OK) {
+    sosgpu_term_out to{};
+    to.emoins = em.data(); to.ier = ierv.data();
+    rc = sosgpu_batch_run(ctx, b, NB + 1, W, 0, &to, nullptr);
+    sosgpu_batch_free(ctx, b);
+  }
+  for (int j = 0; j <= N && rc == SOSGPU_OK; ++j) if (ierv[j] != 0) rc = SOSGPU_ERR_IER;
+  if (rc != SOSGPU_OK) { fprintf(stdout, "  ERROR on subroutine SOS_OS\n"); *ier = -1; return; }
+  *tdifmus = em[0];
+  for (int j = 1; j <= N; ++j) tdifmug[j + NBMU_MAX] = em[j];
+  rmu[NBMU_MAX] = -rmu[N + NBMU_MAX];                          // RMU(0) after the last call (N0 = LUM_NBMU, SOS_OS.F:715)
+}
+
+// SOS_GLITTER.F:229-233.  The three intermediate files of the reference (RES_GSF, RES_FRESNEL, RES_MAT_REFLEX) are
+// deleted by the reference before it returns (:363-368) and are never created here; FICGLITTER must not pre-exist
+// (STATUS='NEW', SOS_SURFACE.F:2360) and receives OS_NB+1 unformatted records of 9*N*N REAL*4 (:2404-2412).
+extern "C" void sos_glitter_(const int *lum_nbmu, const double *rmu, const double *chr, const double *wind,
+                             const double *ind, const int *os_nb, const int *os_ns, const int *os_nm,
+                             const char *fic_res_gsf, const char *fic_res_fresnel, const char *fic_res_mat_reflex,
+                             const char *ficglitter, const int *trace, int *ier,
+                             size_t len_gsf, size_t len_fresnel, size_t len_mat, size_t len_ficglitter)
+{
+  (void)fic_res_gsf; (void)fic_res_fresnel; (void)fic_res_mat_reflex; (void)len_gsf; (void)len_fresnel; (void)len_mat;
+  (void)trace;
+  *ier = 0;
+  const int N = *lum_nbmu, W = 2 * N + 1, NB = *os_nb;
+  sosgpu_ctx *ctx = shim_ctx();
+  if (!ctx || N < 1 || N > NBMU_MAX || NB > NB_MAX) { *ier = -1; return; }
+  const std::string fout = fstr(ficglitter, len_ficglitter);
+  if (FILE *f = fopen(fout.c_str(), "rb")) {
+    fclose(f);
+    fprintf(stdout, "  ERROR on a file opening for SOS_MISE_FORMAT\n Erreur dans la routine SOS_MISE_FORMAT\n");
+    *ier = -1; return;
+  }
+  std::vector<double> rmu_c(W), chr_c(W);
+  for (int j = -N; j <= N; ++j) { rmu_c[j + N] = rmu[j + NBMU_MAX]; chr_c[j + N] = chr[j + NBMU_MAX]; }
+  const size_t per = (size_t)9 * N * N;
+  std::vector<float> surf(per * (NB + 1));
+  const int rc = sosgpu_glitter(ctx, N, rmu_c.data(), chr_c.data(), NB, *os_ns, *os_nm, *wind, *ind, surf.data(), nullptr);
+  if (rc != SOSGPU_OK) { fprintf(stdout, " Erreur dans la routine SOS_MAT_REFLEXION\n"); *ier = -1; return; }
+  FILE *f = fopen(fout.c_str(), "wb");
+  if (!f) { fprintf(stdout, "  ERROR on a file opening for SOS_MISE_FORMAT\n"); *ier = -1; return; }
+  const int32_t n = (int32_t)(per * 4);
+  for (int s = 0; s <= NB; ++s) {
+    fwrite(&n, 4, 1, f);
+    fwrite(&surf[(size_t)s * per], 4, per, f);
+    fwrite(&n, 4, 1, f);
+  }
+  fclose(f);
+}
+
+// Reads FICHOS (records Q,U,I(-N:N), SOS_TRPHI.F:895-897) into the compact layout
+static bool read_fichos(const std::string &path, int N, std::vector<double> &rec, int &nrec)
+{
+  std::vector<std::vector<char>> recs;
+  if (!read_records(path, recs)) { fprintf(stdout, "SOS_TRPHI : Error while opening a file\n"); return false; }
+  const size_t per = (size_t)3 * (2 * N + 1);
+  nrec = (int)recs.size();
+  rec.assign(per * std::max(nrec, 1), 0.0);
+  for (int i = 0; i < nrec; ++i) {
+    if (recs[i].size() < per * 8) { fprintf(stdout, "SOS_TRPHI : Error while reading or writing on a file\n"); return false; }
+    memcpy(&rec[i * per], recs[i].data(), per * 8);
+  }
+  if (nrec < 1) { fprintf(stdout, "SOS_TRPHI : Error while reading or writing on a file\n"); return false; }
+  return true;
+}
+
+static bool direct_model_requested(const int *iroujean, const int *irondeaux, const int *ibreon, const int *inadal,
+                                   const int *imaignan)
+{
+  if (*iroujean == 1 || *irondeaux == 1 || *ibreon == 1 || *inadal == 1 || *imaignan == 1) {
+    fprintf(stdout, "  libsosgpu: the Roujean / Rondeaux / Breon / Nadal / Maignan direct terms of SOS_TRPHI "
+                    "(SOS_TRPHI.F:1047-1200) are not provided by this library\n");
+    return true;
+  }
+  return false;
+}
+
+// SOS_TRPHI.F:749-755: one azimuth PHI (radians).  XIT/XQT/XUT/ANGDIFF(-80:80); index 0 of the Stokes arrays only
+// sees the final thresholding (:1212-1218), as in the reference.
+extern "C" void sos_trphi_(const char *fichos, const int *nbmu, const double *rmu, const double *tau,
+                           const double *tauout, const double *phi, const int *igli, const int *n0, const double *wind,
+                           const double *ind_surf, const int *ifresnel, const int *iroujean, const double *k0,
+                           const double *k1, const double *k2, const int *irondeaux, const int *ibreon,
+                           const int *inadal, const double *alpha_nadal, const double *beta_nadal, const int *imaignan,
+                           const double *coef_c_maignan, const int *ipolar, double *xit, double *xqt, double *xut,
+                           double *angdiff, int *ier, size_t len_fichos)
+{
+  (void)k0; (void)k1; (void)k2; (void)alpha_nadal; (void)beta_nadal; (void)coef_c_maignan;
+  *ier = 0;
+  const int N = *nbmu, W = 2 * N + 1;
+  sosgpu_ctx *ctx = shim_ctx();
+  if (!ctx || N < 1 || N > NBMU_MAX || *n0 < 1 || *n0 > N ||
+      direct_model_requested(iroujean, irondeaux, ibreon, inadal, imaignan)) {
+    *ier = -1; return;
+  }
+  std::vector<double> rec, rmu_c(W), out;
+  int nrec = 0;
+  if (!read_fichos(fstr(fichos, len_fichos), N, rec, nrec)) { *ier = -1; return; }
+  for (int j = -N; j <= N; ++j) rmu_c[j + N] = rmu[j + NBMU_MAX];
+  const std::vector<double> phis(1, *phi);
+  if (trphi_core(ctx, rec.data(), nrec, N, rmu_c.data(), *tau, *tauout, *igli, *n0, *wind, *ind_surf, *ifresnel, *ipolar,
+                 phis, out) != SOSGPU_OK) { *ier = -1; return; }
+  for (int j = 1; j <= N; ++j) {
+    angdiff[NBMU_MAX + j] = out[(size_t)(0 * 7 + 0) * N + j - 1]; angdiff[NBMU_MAX - j] = out[(size_t)(1 * 7 + 0) * N + j - 1];
+    xit[NBMU_MAX + j] = out[(size_t)(0 * 7 + 1) * N + j - 1];     xit[NBMU_MAX - j] = out[(size_t)(1 * 7 + 1) * N + j - 1];
+    xqt[NBMU_MAX + j] = out[(size_t)(0 * 7 + 2) * N + j - 1];     xqt[NBMU_MAX - j] = out[(size_t)(1 * 7 + 2) * N + j - 1];
+    xut[NBMU_MAX + j] = out[(size_t)(0 * 7 + 3) * N + j - 1];     xut[NBMU_MAX - j] = out[(size_t)(1 * 7 + 3) * N + j - 1];
+  }
+  const double pi = std::acos(-1.0), c0 = rmu[NBMU_MAX + *n0];   // :882-891 for J = 0
+  angdiff[NBMU_MAX] = std::acos(-c0 * rmu[NBMU_MAX] + std::sin(std::acos(c0)) * std::sin(std::acos(rmu[NBMU_MAX])) * std::cos(*phi))
+                      * 180.0 / pi;
+  if (xit[NBMU_MAX] <= 1e-99) xit[NBMU_MAX] = 0.0;
+  if (std::fabs(xqt[NBMU_MAX]) < SOSGPU_THRESHOLD_Q_U_NULL) xqt[NBMU_MAX] = 0.0;
+  if (std::fabs(xut[NBMU_MAX]) < SOSGPU_THRESHOLD_Q_U_NULL) xut[NBMU_MAX] = 0.0;
+}
+
+// SOS_TRPHI.F:285-300.  Output tables use the reference's extents: PHI_FIN(0:360), THETA_FIN(0:80), X_FIN(0:360,0:80)
+// (element (IP,JJ) at IP + 361*JJ).
+extern "C" void sos_trphi_option_(const int *nbmu, const double *rmu, const double *ga, const char *fichos,
+                                  const double *tau, const double *tauout, const double *zout, const int *igli,
+                                  const int *n0, const double *wind, const double *ind_surf, const int *ifresnel,
+                                  const int *iroujean, const double *k0, const double *k1, const double *k2,
+                                  const int *irondeaux, const int *ibreon, const int *inadal, const double *alpha_nadal,
+                                  const double *beta_nadal, const int *imaignan, const double *coef_c_maignan,
+                                  const int *itrphi, const double *phios, const int *pas_phi, const int *ipolar,
+                                  double *phi_fin, double *theta_fin,
+                                  double *sca_up, double *i_up, double *q_up, double *u_up, double *pol_ang_up,
+                                  double *pol_rate_up, double *l_pol_up,
+                                  double *sca_down, double *i_down, double *q_down, double *u_down, double *pol_ang_down,
+                                  double *pol_rate_down, double *l_pol_down, int *ier, size_t len_fichos)
+{
+  (void)ga; (void)zout; (void)k0; (void)k1; (void)k2; (void)alpha_nadal; (void)beta_nadal; (void)coef_c_maignan;
+  *ier = 0;
+  const int N = *nbmu, W = 2 * N + 1;
+  sosgpu_ctx *ctx = shim_ctx();
+  if (!ctx || N < 1 || N > NBMU_MAX || direct_model_requested(iroujean, irondeaux, ibreon, inadal, imaignan)) {
+    *ier = -1; return;
+  }
+  if (*itrphi != 1 && *itrphi != 2) return;                      // neither branch runs in the reference (:431,556)
+  std::vector<double> rec, rmu_c(W);
+  int nrec = 0;
+  if (!read_fichos(fstr(fichos, len_fichos), N, rec, nrec)) { *ier = -1; return; }
+  for (int j = -N; j <= N; ++j) rmu_c[j + N] = rmu[j + NBMU_MAX];
+  const int cap = 361;
+  std::vector<double> pf(cap), tf(N), up((size_t)7 * cap * N), down((size_t)7 * cap * N);
+  const int nphi = sosgpu_trphi_option(ctx, rec.data(), nrec, N, rmu_c.data(), *tau, *tauout, *igli, *n0, *wind, *ind_surf,
+                                       *ifresnel, *itrphi, *phios, *pas_phi, *ipolar, pf.data(), tf.data(), up.data(),
+                                       down.data(), cap);
+  if (nphi < 1) { *ier = -1; return; }
+  double *dst_up[7] = {sca_up, i_up, q_up, u_up, pol_ang_up, pol_rate_up, l_pol_up};
+  double *dst_dn[7] = {sca_down, i_down, q_down, u_down, pol_ang_down, pol_rate_down, l_pol_down};
+  for (int t = 0; t < 7; ++t)
+    for (int ip = 0; ip < nphi; ++ip)
+      for (int jj = 0; jj < N; ++jj) {
+        dst_up[t][ip + (size_t)361 * jj] = up[((size_t)t * cap + ip) * N + jj];
+        dst_dn[t][ip + (size_t)361 * jj] = down[((size_t)t * cap + ip) * N + jj];
+      }
+  if (*itrphi == 1) phi_fin[0] = pf[0];                          // only PHI_FIN(0) is assigned for ITRPHI=1 (:445,504)
+  else for (int ip = 0; ip < nphi; ++ip) phi_fin[ip] = pf[ip];
+  for (int jj = 0; jj < N; ++jj) theta_fin[jj] = tf[jj];
 }

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     src = open(os.path.join(ROOT, "include", "sosgpu.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"\b(sosgpu_[a-z_0-9]+|sos_os_|sos_aggregate_)\s*\(", src)
+    names = re.findall(r"\b(sosgpu_[a-z_0-9]+|sos_os_|sos_aggregate_|sos_|sos_glitter_|sos_trphi_|sos_trphi_option_)\s*\(", src)
     return sorted(set(names))
 
 

@@ -255,6 +255,118 @@ def test_gfortran_abi_sos_os_and_aggregate(pkg, orc, solver, tmp_path):
     assert_stokes_close(acc[5].value, agg.sc["eplus"], "EPLUS")
 
 
+def test_gfortran_abi_sos_glitter_trphi(pkg, orc, solver, tmp_path):
+    """Drop-in symbols sos_glitter_ -> sos_ (profile file in, truncation, -SOS.Trans) -> sos_trphi_option_ /
+    sos_trphi_ (SOS_GLITTER.F:229, SOS.F:340, SOS_TRPHI.F:285,749) chained through real files, as SOS_PROC does."""
+    import ctypes as C
+    import importlib
+    api = importlib.import_module("radiativetransfer-sos_b200.api")
+    fm, syn = pkg.formats, pkg.synth
+    lib = api.load_library()
+    o = syn.make_optics(nb_gauss=10, tetas=40.0, os_nb=20, surface="glitter", rho=0.0)
+    N, MX, NBM = o.nbmu, 80, 200
+    os_ns, os_nm = 20, 40
+
+    def fstr(s):
+        return C.create_string_buffer(s.encode().ljust(500), 500)
+    ip = lambda v: C.byref(C.c_int(v))
+    dp = lambda v: C.byref(C.c_double(v))
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    L500 = C.c_size_t(500)
+
+    def strided(v, cap):
+        a = np.zeros(cap)
+        a[:len(v)] = v
+        return a
+    rmu = np.zeros(2 * MX + 1); ga = np.zeros(2 * MX + 1)
+    rmu[MX - N:MX + N + 1] = o.rmu; ga[MX - N:MX + N + 1] = o.ga
+
+    # --- SOS_GLITTER: surface file
+    fgl = str(tmp_path / "GLITTER.bin")
+    ier = C.c_int(99)
+    lib.sos_glitter_(ip(N), P(rmu), P(ga), dp(o.wind), dp(o.ind_surf), ip(o.os_nb), ip(os_ns), ip(os_nm),
+                     fstr(str(tmp_path / "RES_GSF")), fstr(str(tmp_path / "RES_FRESNEL")),
+                     fstr(str(tmp_path / "RES_MAT_REFLEX")), fstr(fgl), ip(0), C.byref(ier), L500, L500, L500, L500)
+    assert ier.value == 0
+    ref_surf, _ = orc.glitter(N, o.rmu, o.ga, o.wind, o.ind_surf, o.os_nb, os_ns, os_nm)
+    got_surf = fm.read_surface_bin(fgl, N)
+    assert got_surf.shape == ref_surf.shape
+    assert np.mean(got_surf.view(np.uint32) == ref_surf.view(np.uint32)) > 0.999
+    lib.sos_glitter_(ip(N), P(rmu), P(ga), dp(o.wind), dp(o.ind_surf), ip(o.os_nb), ip(os_ns), ip(os_nm),
+                     fstr("a"), fstr("b"), fstr("c"), fstr(fgl), ip(0), C.byref(ier), L500, L500, L500, L500)
+    assert ier.value == -1                               # STATUS='NEW' (SOS_SURFACE.F:2360): refuses an existing file
+    fm.write_surface_bin(fgl + ".ref", ref_surf)         # both sides read the same REAL*4 file from here on
+
+    # --- SOS: profile file, truncation adaptation, transmissions
+    z, h, xa, ym = syn.profile(0.05, 8.0, 0.2, 2.0, 0.3)
+    fprof = str(tmp_path / "PROFIL_TMP")
+    fm.write_profile(fprof, z, h, xa, ym)
+    z, h, xa, ym = fm.read_profile(fprof)
+    NT = len(h) - 1
+    a_tr, piztr = 0.35, 0.97
+    piz = piztr / (1 + 0.5 * a_tr * (piztr - 1))         # SOS_PREPA_OS.F:700
+    o2 = syn.make_optics(nb_gauss=10, tetas=40.0, os_nb=20, surface="glitter", rho=0.0)
+    o2.surf, o2.imat_surf, o2.a_trunc, o2.piztr = ref_surf, 1, a_tr, piztr
+    assert o2.piz == piz
+    r = oracle_term(orc, o2, syn.Term(0, 1.0, z, h, xa, ym), want_trans=True)
+    al, be, gm, ze = (strided(v, NBM + 1) for v in (o.alpha, o.beta, o.gamma, o.zeta))
+    fos = str(tmp_path / "SOS_Result.bin")
+    sc = [C.c_double(0) for _ in range(6)]               # ttot_tronc, ttot_vrai, tauout, tdifmus, emoins, eplus
+    tdg = np.zeros(2 * MX + 1)
+    ier = C.c_int(99)
+    lib.sos_(fstr(fos), fstr(str(tmp_path / "Trans.txt")), fstr(fprof), ip(NT), dp(-1.0), ip(o.igmax), ip(1), dp(o.ron),
+             dp(o.ind_surf), dp(0.0), ip(1), ip(0), fstr(fgl + ".ref"), ip(o.n0), dp(piz), dp(piztr), dp(a_tr),
+             P(rmu), P(ga), dp(o.tetas), ip(o.os_nb), ip(N), P(al), P(be), P(gm), P(ze),
+             C.byref(sc[0]), C.byref(sc[1]), C.byref(sc[2]), C.byref(sc[3]), P(tdg), C.byref(sc[4]), C.byref(sc[5]),
+             ip(0), ip(6), C.byref(ier), L500, L500, L500, L500)
+    assert ier.value == 0
+    rec = fm.read_result_bin(fos, N)
+    assert rec.shape[0] == r.n_fourier
+    assert_stokes_close(rec, r.rec, "sos_ records")
+    for got, ref, what in zip(sc, (r.ttot_tronc, r.ttot_vrai, r.tauout, r.tdifmus, r.emoins, r.eplus),
+                              ("TTOT_TRONC", "TTOT_VRAI", "TAUOUT", "TDIFMUS", "EMOINS", "EPLUS")):
+        assert_stokes_close(got.value, ref, what)
+    assert_stokes_close(tdg[MX + 1:MX + N + 1], r.tdifmug[N + 1:], "TDIFMUG")
+    assert rmu[MX] == -o.rmu[2 * N]                       # RMU(0) after the last transmission solve (N0 = N)
+    rmu[MX] = 0.0
+
+    # --- SOS_TRPHI_OPTION / SOS_TRPHI on the result file
+    for itrphi, phios, pas in ((1, 20.0, 0), (2, 0.0, 45)):
+        n0, pf0, th0, up0, dn0 = orc.trphi_option(r.rec, N, o.rmu, r.ttot_tronc, r.tauout, 1, o.n0, o.wind,
+                                                  o.ind_surf, 0, itrphi, phios, pas, 1)
+        pf = np.zeros(361); th = np.zeros(MX + 1)
+        tabs = [np.zeros((MX + 1, 361)) for _ in range(14)]   # Fortran (0:360,0:80): element (IP,JJ) at [JJ, IP]
+        ier = C.c_int(99)
+        lib.sos_trphi_option_(ip(N), P(rmu), P(ga), fstr(fos), dp(r.ttot_tronc), dp(r.tauout), dp(-1.0), ip(1), ip(o.n0),
+                              dp(o.wind), dp(o.ind_surf), ip(0), ip(0), dp(0.0), dp(0.0), dp(0.0), ip(0), ip(0), ip(0),
+                              dp(0.0), dp(0.0), ip(0), dp(0.0), ip(itrphi), dp(phios), ip(pas), ip(1), P(pf), P(th),
+                              *[P(t) for t in tabs], C.byref(ier), L500)
+        assert ier.value == 0
+        assert np.array_equal(pf[:1], pf0[:1]) and (itrphi == 1 or np.array_equal(pf[:n0], pf0))
+        assert np.allclose(th[:N], th0, rtol=0, atol=1e-9)
+        for tb in (1, 2, 3):
+            assert_stokes_close(tabs[tb][:N, :n0].T, up0[tb], "FIN up table %d" % tb)
+            assert_stokes_close(tabs[7 + tb][:N, :n0].T, dn0[tb], "FIN down table %d" % tb)
+        assert np.allclose(tabs[0][:N, :n0].T, up0[0], rtol=0, atol=1e-5)
+    phi = 0.6
+    _, xi0, xq0, xu0, an0 = orc.trphi(r.rec, N, o.rmu, r.ttot_tronc, r.tauout, phi, 1, o.n0, o.wind, o.ind_surf, 0, 1)
+    xi, xq, xu, an = (np.zeros(2 * MX + 1) for _ in range(4))
+    ier = C.c_int(99)
+    lib.sos_trphi_(fstr(fos), ip(N), P(rmu), dp(r.ttot_tronc), dp(r.tauout), dp(phi), ip(1), ip(o.n0), dp(o.wind),
+                   dp(o.ind_surf), ip(0), ip(0), dp(0.0), dp(0.0), dp(0.0), ip(0), ip(0), ip(0), dp(0.0), dp(0.0), ip(0),
+                   dp(0.0), ip(1), P(xi), P(xq), P(xu), P(an), C.byref(ier), L500)
+    assert ier.value == 0
+    sel = np.r_[MX - N:MX, MX + 1:MX + N + 1]
+    sel0 = np.r_[0:N, N + 1:2 * N + 1]
+    assert_stokes_close(xi[sel], xi0[sel0], "XIT"); assert_stokes_close(xq[sel], xq0[sel0], "XQT")
+    assert_stokes_close(xu[sel], xu0[sel0], "XUT")
+    assert np.allclose(an[sel], an0[sel0], rtol=0, atol=1e-5)
+    lib.sos_trphi_(fstr(fos), ip(N), P(rmu), dp(r.ttot_tronc), dp(r.tauout), dp(phi), ip(1), ip(o.n0), dp(o.wind),
+                   dp(o.ind_surf), ip(0), ip(1), dp(0.1), dp(0.1), dp(0.1), ip(0), ip(0), ip(0), dp(0.0), dp(0.0), ip(0),
+                   dp(0.0), ip(1), P(xi), P(xq), P(xu), P(an), C.byref(ier), L500)
+    assert ier.value == -1                               # Roujean direct term: refused loudly, not silently skipped
+
+
 @pytest.mark.parametrize("nbg,os_nb", [(24, 48), (79, 24)])
 def test_solve_other_angle_counts(pkg, orc, solver, nbg, os_nb):
     """N=25 (default -ANG.Rad.NbGauss 24: 5 row groups per direction) and N=80 (the CTE_OS_NBMU_MAX cap: KP=480,
