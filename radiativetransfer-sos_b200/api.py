@@ -34,6 +34,11 @@ class CTerm(C.Structure):
                 ("zprof", c_dp), ("h", c_dp), ("pcaer", c_dp), ("pcmol", c_dp)]
 
 
+_TERM_DTYPE = np.dtype([("optics", "i4"), ("group", "i4"), ("aik", "f8"), ("nt", "i4"), ("_pad", "i4"),
+                        ("zprof", "u8"), ("h", "u8"), ("pcaer", "u8"), ("pcmol", "u8")])
+assert _TERM_DTYPE.itemsize == C.sizeof(CTerm)
+
+
 class CTermOut(C.Structure):
     _fields_ = [("rec", c_dp), ("n_fourier", c_ip), ("n_scatter", c_ip), ("stop_reason", c_ip),
                 ("emoins", c_dp), ("eplus", c_dp), ("ttot_tronc", c_dp), ("ttot_vrai", c_dp), ("tauout", c_dp),
@@ -184,15 +189,27 @@ class Solver:
             co.igmax, co.ipolar, co.zout = o.igmax, o.ipolar, o.zout
             copt.append(co)
         gmap = {}
-        cterms = (CTerm * len(terms))()
-        for i, t in enumerate(terms):
-            o = workload.optics[t.optics]
-            g = groups[i] if groups is not None else gmap.setdefault(t.optics, len(gmap))
-            arrs = [_f64(t.zprof), _f64(t.h), _f64(t.pcaer), _f64(t.pcmol)]
-            keep.extend(arrs)
-            ct = cterms[i]
-            ct.optics, ct.group, ct.aik, ct.nt = omap[id(o)], g, t.aik, t.nt
-            ct.zprof, ct.h, ct.pcaer, ct.pcmol = (_d(a) for a in arrs)
+        # sosgpu_term descriptors, filled through a numpy view of the same layout (a ctypes field store per term
+        # costs more than the H2D copy it describes)
+        nterm = len(terms)
+        tdesc = np.zeros(nterm, dtype=_TERM_DTYPE)
+        plist = []
+        h2d = 0
+        for t in terms:
+            arrs = (_f64(t.zprof), _f64(t.h), _f64(t.pcaer), _f64(t.pcmol))
+            keep.append(arrs)
+            plist.extend(a.__array_interface__["data"][0] for a in arrs)
+            h2d += 4 * arrs[0].nbytes
+        ptrs = np.array(plist, dtype=np.uint64).reshape(nterm, 4)
+        tdesc["optics"] = [omap[id(workload.optics[t.optics])] for t in terms]
+        tdesc["group"] = groups if groups is not None else [gmap.setdefault(t.optics, len(gmap)) for t in terms]
+        tdesc["aik"] = [t.aik for t in terms]
+        tdesc["nt"] = [t.nt for t in terms]
+        for k, name in enumerate(("zprof", "h", "pcaer", "pcmol")):
+            tdesc[name] = ptrs[:, k]
+        cterms = tdesc.ctypes.data_as(C.POINTER(CTerm))
+        h2d += int(sum(a.nbytes for a in keep if isinstance(a, np.ndarray)))
+        keep.append(tdesc)
         coptics = (COptics * len(copt))(*copt)
         h = C.c_void_p()
         ng = ngroup if groups is not None else len(gmap)
@@ -206,7 +223,7 @@ class Solver:
         rec_stride = max(workload.optics[t.optics].os_nb for t in terms) + 1
         wmax = 2 * max(workload.optics[t.optics].nbmu for t in terms) + 1
         b = Batch(self, h, len(terms), ng, rec_stride, wmax, keep)
-        b.h2d_bytes = int(sum(a.nbytes for a in keep))
+        b.h2d_bytes = h2d
         b.nbmu_of_term = [workload.optics[t.optics].nbmu for t in terms]
         return b
 

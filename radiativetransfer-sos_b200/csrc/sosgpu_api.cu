@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -53,6 +54,7 @@ struct sosgpu_batch {
   std::vector<TermDev> terms_dev;
   double *d_att = nullptr, *d_i4 = nullptr;
   size_t i4_total = 0;
+  size_t grec_bytes = 0;
   double *d_rec = nullptr, *d_emoins = nullptr, *d_eplus = nullptr, *d_grec = nullptr;
   int *d_nf = nullptr, *d_nsc = nullptr, *d_rsn = nullptr, *d_done = nullptr, *d_gnrec = nullptr;
   int *d_group_start = nullptr, *d_group_terms = nullptr;
@@ -92,6 +94,21 @@ extern "C" int sosgpu_create(sosgpu_ctx **out, int device)
     delete ctx;
     return SOSGPU_ERR_CUDA;
   }
+  // Device memory of the batches comes from a stream-ordered pool that never trims: uploading and freeing a batch
+  // per step (the host-buffer path) then costs no cudaMalloc/cudaFree (10-70 ms per step measured with plain calls).
+  cudaMemPoolProps props = {};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = device;
+  unsigned long long keep_all = ~0ull;
+  if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess ||
+      cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep_all) != cudaSuccess ||
+      cudaMallocHost(&ctx->h_count, 2 * sizeof(int)) != cudaSuccess) {
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SOSGPU_ERR_CUDA;
+  }
   *out = ctx;
   return SOSGPU_OK;
 }
@@ -100,7 +117,10 @@ extern "C" void sosgpu_destroy(sosgpu_ctx *ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaFree(ctx->cache_field); cudaFree(ctx->cache_kpool);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->grec_cache);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+  if (ctx->h_count) cudaFreeHost(ctx->h_count);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -222,32 +242,39 @@ static int prep_term(const sosgpu_term &t, const HostOptics &o, HostTerm &h, boo
   return SOSGPU_OK;
 }
 
-static void free_batch_device(sosgpu_batch *b)
+static void free_batch_device(sosgpu_ctx *ctx, sosgpu_batch *b)
 {
-  cudaFree(b->d_arena); cudaFree(b->d_optics); cudaFree(b->d_terms); cudaFree(b->d_att); cudaFree(b->d_i4);
-  cudaFree(b->d_rec); cudaFree(b->d_emoins); cudaFree(b->d_eplus); cudaFree(b->d_grec);
-  cudaFree(b->d_nf); cudaFree(b->d_nsc); cudaFree(b->d_rsn); cudaFree(b->d_done); cudaFree(b->d_gnrec);
-  cudaFree(b->d_group_start); cudaFree(b->d_group_terms);
-  cudaFree(b->d_field); cudaFree(b->d_kpool); cudaFree(b->d_items); cudaFree(b->d_ksets); cudaFree(b->d_item_of);
-  cudaFree(b->d_list[0]); cudaFree(b->d_list[1]); cudaFree(b->d_count);
-  cudaFree(b->d_tg); cudaFree(b->d_tphi); cudaFree(b->d_tout);
-  if (b->h_count) cudaFreeHost(b->h_count);
+  const bool tr = getenv("SOS_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
+  sos_dfree(ctx, b->d_field); sos_dfree(ctx, b->d_kpool);
+  const double t1 = now();
+  sos_dfree(ctx, b->d_arena); sos_dfree(ctx, b->d_optics); sos_dfree(ctx, b->d_terms); sos_dfree(ctx, b->d_att); sos_dfree(ctx, b->d_i4);
+  sos_dfree(ctx, b->d_rec); sos_dfree(ctx, b->d_emoins); sos_dfree(ctx, b->d_eplus);
+  sos_dfree(ctx, b->d_nf); sos_dfree(ctx, b->d_nsc); sos_dfree(ctx, b->d_rsn); sos_dfree(ctx, b->d_done); sos_dfree(ctx, b->d_gnrec);
+  sos_dfree(ctx, b->d_group_start); sos_dfree(ctx, b->d_group_terms);
+  sos_dfree(ctx, b->d_items); sos_dfree(ctx, b->d_ksets); sos_dfree(ctx, b->d_item_of);
+  sos_dfree(ctx, b->d_list[0]); sos_dfree(ctx, b->d_list[1]); sos_dfree(ctx, b->d_count);
+  sos_dfree(ctx, b->d_tg); sos_dfree(ctx, b->d_tphi); sos_dfree(ctx, b->d_tout);
+  const double t2 = now();
+  if (ctx && b->d_grec && b->grec_bytes > ctx->grec_cache_bytes) {
+    cudaFree(ctx->grec_cache);
+    ctx->grec_cache = b->d_grec; ctx->grec_cache_bytes = b->grec_bytes;
+  } else cudaFree(b->d_grec);
+  const double t3 = now();
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->evt0) cudaEventDestroy(b->evt0);
   if (b->evt1) cudaEventDestroy(b->evt1);
+  if (tr) fprintf(stderr, "batch_free: pools %.2f ms, small %.2f ms, group buffer %.2f ms, events %.2f ms\n", t1 - t0, t2 - t1,
+                  t3 - t2, now() - t3);
 }
 
 extern "C" void sosgpu_batch_free(sosgpu_ctx *ctx, sosgpu_batch *b)
 {
   if (!b) return;
-  if (ctx) {
-    cudaSetDevice(ctx->device);
-    // keep the two big pools for the next batch of this context
-    if (b->field_bytes > ctx->cache_field_bytes) { cudaFree(ctx->cache_field); ctx->cache_field = b->d_field; ctx->cache_field_bytes = b->field_bytes; b->d_field = nullptr; }
-    if (b->kpool_bytes > ctx->cache_kpool_bytes) { cudaFree(ctx->cache_kpool); ctx->cache_kpool = b->d_kpool; ctx->cache_kpool_bytes = b->kpool_bytes; b->d_kpool = nullptr; }
-  }
-  free_batch_device(b);
+  if (ctx) cudaSetDevice(ctx->device);
+  free_batch_device(ctx, b);
   delete b;
 }
 
@@ -257,22 +284,27 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
   if (!ctx) return SOSGPU_ERR_NO_DEVICE;
   if (!optics || !terms || noptics < 1 || nterm < 1 || ngroup < 1 || !out) { ctx->err = "bad arguments"; return SOSGPU_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
+  const auto t_up0 = std::chrono::steady_clock::now();
   sosgpu_batch *b = new sosgpu_batch();
+  struct Guard {                                                // frees a half-built batch on every error return
+    sosgpu_ctx *c; sosgpu_batch *b;
+    ~Guard() { if (b) { free_batch_device(c, b); delete b; } }
+  } guard{ctx, b};
   b->nterm = nterm; b->noptics = noptics; b->ngroup = ngroup;
   b->ho.resize(noptics); b->ht.resize(nterm);
   for (int i = 0; i < noptics; ++i) {
     int rc = prep_optics(optics[i], b->ho[i], os_level);
-    if (rc != SOSGPU_OK) { ctx->err = "invalid optics entry"; delete b; return rc; }
+    if (rc != SOSGPU_OK) { ctx->err = "invalid optics entry"; return rc; }
     b->maxHB = std::max(b->maxHB, b->ho[i].HB); b->maxW = std::max(b->maxW, b->ho[i].W);
     b->maxKP = std::max(b->maxKP, b->ho[i].KP); b->maxNB = std::max(b->maxNB, b->ho[i].os_nb);
   }
   int max_att = 0;
   for (int i = 0; i < nterm; ++i) {
     if (terms[i].optics < 0 || terms[i].optics >= noptics || terms[i].group < 0 || terms[i].group >= ngroup) {
-      ctx->err = "term refers to a missing optics / group"; delete b; return SOSGPU_ERR_ARG;
+      ctx->err = "term refers to a missing optics / group"; return SOSGPU_ERR_ARG;
     }
     int rc = prep_term(terms[i], b->ho[terms[i].optics], b->ht[i], os_level);
-    if (rc != SOSGPU_OK) { ctx->err = "invalid term entry"; delete b; return rc; }
+    if (rc != SOSGPU_OK) { ctx->err = "invalid term entry"; return rc; }
     if (os_level && iborm) b->ht[i].iborm = std::min(std::max(iborm[i], 0), b->ho[terms[i].optics].os_nb);
     b->smax = std::max(b->smax, b->ht[i].iborm + 1);
     max_att = std::max(max_att, b->ht[i].nt * b->ho[terms[i].optics].N);
@@ -280,6 +312,7 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
   b->rs_dev = b->maxNB + 1;
   b->w_dev = b->maxW;
 
+  const auto t_up1 = std::chrono::steady_clock::now();
   // ---- constant arena ----
   Arena ar;
   b->optics_dev.resize(noptics);
@@ -292,7 +325,7 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     o[9] = 0;
     if (h.imat_surf == 1) {
       const size_t need = (size_t)std::min(h.n_surf_rec, h.os_nb + 1);
-      if ((int)need < 1) { ctx->err = "surface matrix has no record"; delete b; return SOSGPU_ERR_ARG; }
+      if ((int)need < 1) { ctx->err = "surface matrix has no record"; return SOSGPU_ERR_ARG; }
       o[9] = ar.put(h.surf, need * 9 * h.N * h.N * sizeof(float));
     }
   }
@@ -308,10 +341,10 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     i4_off[i] = i4_total; i4_total += (size_t)12 * b->ho[h.optics].N;
   }
   b->i4_total = i4_total;
-  CK(cudaMalloc(&b->d_arena, ar.buf.size()));
+  CK(sos_dmalloc(ctx, &b->d_arena, ar.buf.size()));
   CK(cudaMemcpyAsync(b->d_arena, ar.buf.data(), ar.buf.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMalloc(&b->d_att, att_total * sizeof(double)));
-  CK(cudaMalloc(&b->d_i4, i4_total * sizeof(double)));
+  CK(sos_dmalloc(ctx, &b->d_att, att_total * sizeof(double)));
+  CK(sos_dmalloc(ctx, &b->d_i4, i4_total * sizeof(double)));
   for (int i = 0; i < noptics; ++i) {
     HostOptics &h = b->ho[i];
     OpticsDev &d = b->optics_dev[i];
@@ -342,8 +375,8 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     d.att = b->d_att + att_off[i];
     d.i4 = b->d_i4 + i4_off[i];
   }
-  CK(cudaMalloc(&b->d_optics, noptics * sizeof(OpticsDev)));
-  CK(cudaMalloc(&b->d_terms, nterm * sizeof(TermDev)));
+  CK(sos_dmalloc(ctx, &b->d_optics, noptics * sizeof(OpticsDev)));
+  CK(sos_dmalloc(ctx, &b->d_terms, nterm * sizeof(TermDev)));
   CK(cudaMemcpyAsync(b->d_optics, b->optics_dev.data(), noptics * sizeof(OpticsDev), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(b->d_terms, b->terms_dev.data(), nterm * sizeof(TermDev), cudaMemcpyHostToDevice, ctx->stream));
 
@@ -356,30 +389,44 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     std::vector<int> fill(b->group_start.begin(), b->group_start.end() - 1);
     for (int i = 0; i < nterm; ++i) b->group_terms[fill[b->ht[i].group]++] = i;
   }
-  CK(cudaMalloc(&b->d_group_start, (ngroup + 1) * sizeof(int)));
-  CK(cudaMalloc(&b->d_group_terms, nterm * sizeof(int)));
+  CK(sos_dmalloc(ctx, &b->d_group_start, (ngroup + 1) * sizeof(int)));
+  CK(sos_dmalloc(ctx, &b->d_group_terms, nterm * sizeof(int)));
   CK(cudaMemcpyAsync(b->d_group_start, b->group_start.data(), (ngroup + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(b->d_group_terms, b->group_terms.data(), nterm * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 
   const size_t per = (size_t)b->rs_dev * 3 * b->w_dev;
-  CK(cudaMalloc(&b->d_rec, (size_t)nterm * per * sizeof(double)));
-  CK(cudaMalloc(&b->d_grec, (size_t)ngroup * per * sizeof(double)));
-  CK(cudaMalloc(&b->d_emoins, nterm * sizeof(double)));
-  CK(cudaMalloc(&b->d_eplus, nterm * sizeof(double)));
-  CK(cudaMalloc(&b->d_nf, nterm * sizeof(int)));
-  CK(cudaMalloc(&b->d_nsc, (size_t)nterm * b->rs_dev * sizeof(int)));
-  CK(cudaMalloc(&b->d_rsn, (size_t)nterm * b->rs_dev * sizeof(int)));
-  CK(cudaMalloc(&b->d_done, nterm * sizeof(int)));
-  CK(cudaMalloc(&b->d_gnrec, ngroup * sizeof(int)));
-  CK(cudaMalloc(&b->d_count, 2 * sizeof(int)));
-  CK(cudaMallocHost(&b->h_count, 2 * sizeof(int)));
+  CK(sos_dmalloc(ctx, &b->d_rec, (size_t)nterm * per * sizeof(double)));
+  // The group sums are handed to NCCL (sosgpu_batch_group_buffer), so they stay a plain cudaMalloc block; a freed
+  // batch parks it in the context because cudaFree of it was measured at 1.5-670 ms (device-wide synchronisation).
+  b->grec_bytes = (size_t)ngroup * per * sizeof(double);
+  if (ctx->grec_cache && ctx->grec_cache_bytes >= b->grec_bytes) {
+    b->d_grec = ctx->grec_cache; b->grec_bytes = ctx->grec_cache_bytes;
+    ctx->grec_cache = nullptr; ctx->grec_cache_bytes = 0;
+  } else CK(cudaMalloc(&b->d_grec, b->grec_bytes));
+  CK(sos_dmalloc(ctx, &b->d_emoins, nterm * sizeof(double)));
+  CK(sos_dmalloc(ctx, &b->d_eplus, nterm * sizeof(double)));
+  CK(sos_dmalloc(ctx, &b->d_nf, nterm * sizeof(int)));
+  CK(sos_dmalloc(ctx, &b->d_nsc, (size_t)nterm * b->rs_dev * sizeof(int)));
+  CK(sos_dmalloc(ctx, &b->d_rsn, (size_t)nterm * b->rs_dev * sizeof(int)));
+  CK(sos_dmalloc(ctx, &b->d_done, nterm * sizeof(int)));
+  CK(sos_dmalloc(ctx, &b->d_gnrec, ngroup * sizeof(int)));
+  CK(sos_dmalloc(ctx, &b->d_count, 2 * sizeof(int)));
+  b->h_count = ctx->h_count;
   CK(cudaEventCreate(&b->ev0)); CK(cudaEventCreate(&b->ev1));
   CK(cudaEventCreate(&b->evt0)); CK(cudaEventCreate(&b->evt1));
 
   sos_launch_att(b->d_terms, b->d_optics, nterm, max_att, ctx->stream);
   ctx->launches += 1;
   CK(cudaGetLastError());
+  const auto t_up2 = std::chrono::steady_clock::now();
   CK(cudaStreamSynchronize(ctx->stream));
+  if (getenv("SOS_TRACE")) {
+    const auto t_up3 = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "batch_upload: host prep %.2f ms, arena + allocations + copies %.2f ms, wait %.2f ms\n", ms(t_up0, t_up1),
+            ms(t_up1, t_up2), ms(t_up2, t_up3));
+  }
+  guard.b = nullptr;
   *out = b;
   return SOSGPU_OK;
 }
@@ -400,9 +447,9 @@ extern "C" int sosgpu_batch_upload_os(sosgpu_ctx *ctx, const sosgpu_optics *opti
 template <class T> static int ensure(sosgpu_ctx *ctx, T **p, size_t *cap, size_t need)
 {
   if (need <= *cap) return SOSGPU_OK;
-  if (*p) cudaFree(*p);
+  if (*p) sos_dfree(ctx, *p);
   *p = nullptr; *cap = 0;
-  CK(cudaMalloc((void **)p, need * sizeof(T)));
+  CK(sos_dmalloc(ctx, p, need * sizeof(T)));
   *cap = need;
   return SOSGPU_OK;
 }
@@ -495,20 +542,10 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     }
     const size_t nitem = items.size(), nk = ksets.size();
     // ---- pools ----
-    if (fbytes + sbytes > b->field_bytes && ctx->cache_field_bytes >= fbytes + sbytes) {
-      if (b->d_field) cudaFree(b->d_field);
-      b->d_field = ctx->cache_field; b->field_bytes = ctx->cache_field_bytes;
-      ctx->cache_field = nullptr; ctx->cache_field_bytes = 0;
-    }
-    if (kbytes > b->kpool_bytes && ctx->cache_kpool_bytes >= kbytes) {
-      if (b->d_kpool) cudaFree(b->d_kpool);
-      b->d_kpool = ctx->cache_kpool; b->kpool_bytes = ctx->cache_kpool_bytes;
-      ctx->cache_kpool = nullptr; ctx->cache_kpool_bytes = 0;
-    }
     if (fbytes + sbytes > b->field_bytes) {
-      if (b->d_field) cudaFree(b->d_field);
+      if (b->d_field) sos_dfree(ctx, b->d_field);
       b->d_field = nullptr; b->field_bytes = 0;
-      CK(cudaMalloc(&b->d_field, fbytes + sbytes));
+      CK(sos_dmalloc(ctx, &b->d_field, fbytes + sbytes));
       b->field_bytes = fbytes + sbytes;
       // Zeroed once per allocation: pad rows / levels / columns of the fields only ever meet zero coefficients of the
       // packed operators, so they merely have to stay finite (no NaN bit patterns of fresh memory); every valid
@@ -516,9 +553,9 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
       CK(cudaMemsetAsync(b->d_field, 0, fbytes + sbytes, st));
     }
     if (kbytes > b->kpool_bytes) {
-      if (b->d_kpool) cudaFree(b->d_kpool);
+      if (b->d_kpool) sos_dfree(ctx, b->d_kpool);
       b->d_kpool = nullptr; b->kpool_bytes = 0;
-      CK(cudaMalloc(&b->d_kpool, kbytes));
+      CK(sos_dmalloc(ctx, &b->d_kpool, kbytes));
       b->kpool_bytes = kbytes;
     }
     CK(cudaMemsetAsync(b->d_kpool, 0, kbytes, st));              // PSL/RSL/TSL rely on zero-initialised storage
@@ -558,9 +595,9 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     if (ensure(ctx, &b->d_ksets, &b->ksets_cap, nk)) return SOSGPU_ERR_CUDA;
     if (ensure(ctx, &b->d_item_of, &b->item_of_cap, item_of.size())) return SOSGPU_ERR_CUDA;
     if (nitem > b->list_cap) {
-      cudaFree(b->d_list[0]); cudaFree(b->d_list[1]); b->d_list[0] = b->d_list[1] = nullptr; b->list_cap = 0;
-      CK(cudaMalloc(&b->d_list[0], nitem * sizeof(int)));
-      CK(cudaMalloc(&b->d_list[1], nitem * sizeof(int)));
+      sos_dfree(ctx, b->d_list[0]); sos_dfree(ctx, b->d_list[1]); b->d_list[0] = b->d_list[1] = nullptr; b->list_cap = 0;
+      CK(sos_dmalloc(ctx, &b->d_list[0], nitem * sizeof(int)));
+      CK(sos_dmalloc(ctx, &b->d_list[1], nitem * sizeof(int)));
       b->list_cap = nitem;
     }
     CK(cudaMemcpyAsync(b->d_items, items.data(), nitem * sizeof(ItemDev), cudaMemcpyHostToDevice, st));
@@ -823,9 +860,9 @@ extern "C" int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *b, int igli, do
   }
   // note: rmu[N] on the device holds mu_s (index 0), which SOS_TRPHI never reads
   const size_t nout = (size_t)ng * 2 * 7 * nphi * nmax;
-  if (!b->d_tg) CK(cudaMalloc(&b->d_tg, ng * sizeof(TrphiGroup)));
-  if ((size_t)nphi > b->tphi_cap) { cudaFree(b->d_tphi); b->d_tphi = nullptr; CK(cudaMalloc(&b->d_tphi, nphi * 8)); b->tphi_cap = nphi; }
-  if (nout > b->tout_cap) { cudaFree(b->d_tout); b->d_tout = nullptr; CK(cudaMalloc(&b->d_tout, nout * 8)); b->tout_cap = nout; }
+  if (!b->d_tg) CK(sos_dmalloc(ctx, &b->d_tg, ng * sizeof(TrphiGroup)));
+  if ((size_t)nphi > b->tphi_cap) { sos_dfree(ctx, b->d_tphi); b->d_tphi = nullptr; CK(sos_dmalloc(ctx, &b->d_tphi, nphi * 8)); b->tphi_cap = nphi; }
+  if (nout > b->tout_cap) { sos_dfree(ctx, b->d_tout); b->d_tout = nullptr; CK(sos_dmalloc(ctx, &b->d_tout, nout * 8)); b->tout_cap = nout; }
   TrphiGroup *d_g = (TrphiGroup *)b->d_tg; double *d_phi = b->d_tphi, *d_out = b->d_tout;
   CK(cudaMemcpyAsync(d_g, grp.data(), ng * sizeof(TrphiGroup), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_phi, phis.data(), nphi * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -867,10 +904,10 @@ extern "C" int sosgpu_noyaux(sosgpu_ctx *ctx, int is, int nbmu, const double *rm
   size_t o_g = ar.put(gamma, (os_nb + 1) * 8), o_z = ar.put(zeta, (os_nb + 1) * 8);
   const size_t nb_basis = (size_t)3 * (os_nb + 2) * W, nb_ker = (size_t)6 * W * W, nb_xpl = (size_t)3 * W;
   char *d = nullptr; double *dw = nullptr; OpticsDev *dop = nullptr; KsetDev *dks = nullptr;
-  CK(cudaMalloc(&d, ar.buf.size()));
-  CK(cudaMalloc(&dw, (nb_basis + nb_ker + nb_xpl) * 8));
-  CK(cudaMalloc(&dop, sizeof(OpticsDev)));
-  CK(cudaMalloc(&dks, sizeof(KsetDev)));
+  CK(sos_dmalloc(ctx, &d, ar.buf.size()));
+  CK(sos_dmalloc(ctx, &dw, (nb_basis + nb_ker + nb_xpl) * 8));
+  CK(sos_dmalloc(ctx, &dop, sizeof(OpticsDev)));
+  CK(sos_dmalloc(ctx, &dks, sizeof(KsetDev)));
   CK(cudaMemcpy(d, ar.buf.data(), ar.buf.size(), cudaMemcpyHostToDevice));
   CK(cudaMemset(dw, 0, (nb_basis + nb_ker + nb_xpl) * 8));
   OpticsDev op{};
@@ -893,7 +930,7 @@ extern "C" int sosgpu_noyaux(sosgpu_ctx *ctx, int is, int nbmu, const double *rm
   memcpy(bp, &ker[0], WW * 8); memcpy(gr, &ker[WW], WW * 8); memcpy(gt, &ker[2 * WW], WW * 8);
   memcpy(arr, &ker[3 * WW], WW * 8); memcpy(art, &ker[4 * WW], WW * 8); memcpy(att, &ker[5 * WW], WW * 8);
   memcpy(xpl, &x3[0], W * 8); memcpy(xrl, &x3[W], W * 8); memcpy(xtl, &x3[2 * W], W * 8);
-  cudaFree(d); cudaFree(dw); cudaFree(dop); cudaFree(dks);
+  sos_dfree(ctx, d); sos_dfree(ctx, dw); sos_dfree(ctx, dop); sos_dfree(ctx, dks);
   return SOSGPU_OK;
 }
 
@@ -935,7 +972,7 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
   ks.optics = 0; ks.is = is; ks.dual = (is <= 2) ? 1 : 0; ks.beta0 = (is == 0) ? 1.0 : 0.0;
   const size_t kbytes = rup(3 * (os_nb + 2) * W * 8) + rup(6 * W * W * 8) + rup(3 * W * 8) + 2 * rup((size_t)KP * KP * 8) + 5 * rup(KP * 8) + rup(16 * KP * 8);
   char *kp = nullptr;
-  CK(cudaMalloc(&kp, kbytes));
+  CK(sos_dmalloc(ctx, &kp, kbytes));
   CK(cudaMemset(kp, 0, kbytes));
   char *p = kp;
   ks.basis = (double *)p; p += rup(3 * (os_nb + 2) * W * 8);
@@ -950,7 +987,7 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
   ks.urow = (double *)p; p += rup(KP * 8);
   ks.vpack = (double *)p; p += rup(16 * KP * 8);
   KsetDev *dks = nullptr;
-  CK(cudaMalloc(&dks, sizeof(KsetDev)));
+  CK(sos_dmalloc(ctx, &dks, sizeof(KsetDev)));
   CK(cudaMemcpy(dks, &ks, sizeof(ks), cudaMemcpyHostToDevice));
   // fields: x[1] = input (order n=1 parity), x[0] = output, plus J dump
   const size_t fsz = std::max(SOS_XSIZE(KP, L), (size_t)KP * LP);   // field (chunk-major) or J dump ([row][LP])
@@ -964,14 +1001,14 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
         for (int lv = 0; lv < L; ++lv) xin[SOS_XIDX(KP, r, lv)] = src[s][(size_t)(kk + N) * L + lv];
       }
   double *dx = nullptr;
-  CK(cudaMalloc(&dx, 3 * fsz * 8));
+  CK(sos_dmalloc(ctx, &dx, 3 * fsz * 8));
   CK(cudaMemset(dx, 0, 3 * fsz * 8));
   CK(cudaMemcpy(dx + fsz, xin.data(), fsz * 8, cudaMemcpyHostToDevice));
   ItemDev it{};
   it.term = 0; it.is = is; it.kset = 0; it.n = 1; it.active = 1;
   it.x[0] = dx; it.x[1] = dx + fsz;
   ItemDev *dit = nullptr;
-  CK(cudaMalloc(&dit, sizeof(ItemDev)));
+  CK(sos_dmalloc(ctx, &dit, sizeof(ItemDev)));
   CK(cudaMemcpy(dit, &it, sizeof(it), cudaMemcpyHostToDevice));
   sos_launch_basis(dks, b->d_optics, 1, ctx->stream);
   sos_launch_kernels(dks, b->d_optics, 1, W, ctx->stream);
@@ -994,7 +1031,7 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
           if (dstj[s]) dstj[s][(size_t)(kk + N) * L + lv] = jo[(size_t)r * LP + lv];
         }
       }
-  cudaFree(kp); cudaFree(dks); cudaFree(dx); cudaFree(dit);
+  sos_dfree(ctx, kp); sos_dfree(ctx, dks); sos_dfree(ctx, dx); sos_dfree(ctx, dit);
   sosgpu_batch_free(ctx, b);
   return SOSGPU_OK;
 }

@@ -20,7 +20,18 @@ struct sosgpu_ctx {
   long long launches = 0;
   size_t field_budget = (size_t)48 << 30;
   int max_wave_orders = 0;
-  // device pools handed back by freed batches (cudaMalloc/cudaFree of multi-GB pools cost tens of ms per call)
-  char *cache_field = nullptr; size_t cache_field_bytes = 0;
-  char *cache_kpool = nullptr; size_t cache_kpool_bytes = 0;
+  int *h_count = nullptr;            // pinned word pair for the active-count readback of the wave loop
+  double *grec_cache = nullptr; size_t grec_cache_bytes = 0;   // group-sum buffer parked by the last freed batch
+  cudaMemPool_t pool = nullptr;      // stream-ordered pool (release threshold = never) behind sos_dmalloc / sos_dfree
 };
+
+template <class T> static inline cudaError_t sos_dmalloc(sosgpu_ctx *ctx, T **p, size_t bytes)
+{
+  return cudaMallocFromPoolAsync((void **)p, bytes ? bytes : 8, ctx->pool, ctx->stream);
+}
+static inline void sos_dfree(sosgpu_ctx *ctx, void *p)
+{
+  if (!p) return;
+  if (ctx) cudaFreeAsync(p, ctx->stream);
+  else cudaFree(p);
+}
