@@ -118,7 +118,7 @@ extern "C" void sosgpu_destroy(sosgpu_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  cudaFree(ctx->grec_cache);
+  cudaFree(ctx->grec_cache); cudaFree(ctx->cache_field); cudaFree(ctx->cache_kpool);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->h_count) cudaFreeHost(ctx->h_count);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -247,7 +247,12 @@ static void free_batch_device(sosgpu_ctx *ctx, sosgpu_batch *b)
   const bool tr = getenv("SOS_TRACE") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now();
-  sos_dfree(ctx, b->d_field); sos_dfree(ctx, b->d_kpool);
+  if (ctx && b->d_field && b->field_bytes > ctx->cache_field_bytes) {
+    cudaFree(ctx->cache_field); ctx->cache_field = b->d_field; ctx->cache_field_bytes = b->field_bytes;
+  } else cudaFree(b->d_field);
+  if (ctx && b->d_kpool && b->kpool_bytes > ctx->cache_kpool_bytes) {
+    cudaFree(ctx->cache_kpool); ctx->cache_kpool = b->d_kpool; ctx->cache_kpool_bytes = b->kpool_bytes;
+  } else cudaFree(b->d_kpool);
   const double t1 = now();
   sos_dfree(ctx, b->d_arena); sos_dfree(ctx, b->d_optics); sos_dfree(ctx, b->d_terms); sos_dfree(ctx, b->d_att); sos_dfree(ctx, b->d_i4);
   sos_dfree(ctx, b->d_rec); sos_dfree(ctx, b->d_emoins); sos_dfree(ctx, b->d_eplus);
@@ -542,10 +547,23 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     }
     const size_t nitem = items.size(), nk = ksets.size();
     // ---- pools ----
+    // The two multi-GB wave pools are plain cudaMalloc blocks parked in the context between batches (growing the
+    // stream-ordered pool by several GB costs ~0.5 s on first use; cudaFree synchronises the device).
+    if (fbytes + sbytes > b->field_bytes && ctx->cache_field_bytes >= fbytes + sbytes) {
+      if (b->d_field) cudaFree(b->d_field);
+      b->d_field = ctx->cache_field; b->field_bytes = ctx->cache_field_bytes;
+      ctx->cache_field = nullptr; ctx->cache_field_bytes = 0;
+      CK(cudaMemsetAsync(b->d_field, 0, b->field_bytes, st));     // see below: pads must be finite
+    }
+    if (kbytes > b->kpool_bytes && ctx->cache_kpool_bytes >= kbytes) {
+      if (b->d_kpool) cudaFree(b->d_kpool);
+      b->d_kpool = ctx->cache_kpool; b->kpool_bytes = ctx->cache_kpool_bytes;
+      ctx->cache_kpool = nullptr; ctx->cache_kpool_bytes = 0;
+    }
     if (fbytes + sbytes > b->field_bytes) {
-      if (b->d_field) sos_dfree(ctx, b->d_field);
+      if (b->d_field) cudaFree(b->d_field);
       b->d_field = nullptr; b->field_bytes = 0;
-      CK(sos_dmalloc(ctx, &b->d_field, fbytes + sbytes));
+      CK(cudaMalloc(&b->d_field, fbytes + sbytes));
       b->field_bytes = fbytes + sbytes;
       // Zeroed once per allocation: pad rows / levels / columns of the fields only ever meet zero coefficients of the
       // packed operators, so they merely have to stay finite (no NaN bit patterns of fresh memory); every valid
@@ -553,9 +571,9 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
       CK(cudaMemsetAsync(b->d_field, 0, fbytes + sbytes, st));
     }
     if (kbytes > b->kpool_bytes) {
-      if (b->d_kpool) sos_dfree(ctx, b->d_kpool);
+      if (b->d_kpool) cudaFree(b->d_kpool);
       b->d_kpool = nullptr; b->kpool_bytes = 0;
-      CK(sos_dmalloc(ctx, &b->d_kpool, kbytes));
+      CK(cudaMalloc(&b->d_kpool, kbytes));
       b->kpool_bytes = kbytes;
     }
     CK(cudaMemsetAsync(b->d_kpool, 0, kbytes, st));              // PSL/RSL/TSL rely on zero-initialised storage

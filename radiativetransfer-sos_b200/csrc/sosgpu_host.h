@@ -21,6 +21,8 @@ struct sosgpu_ctx {
   size_t field_budget = (size_t)48 << 30;
   int max_wave_orders = 0;
   int *h_count = nullptr;            // pinned word pair for the active-count readback of the wave loop
+  char *cache_field = nullptr; size_t cache_field_bytes = 0;   // wave pools parked by the last freed batch
+  char *cache_kpool = nullptr; size_t cache_kpool_bytes = 0;
   double *grec_cache = nullptr; size_t grec_cache_bytes = 0;   // group-sum buffer parked by the last freed batch
   cudaMemPool_t pool = nullptr;      // stream-ordered pool (release threshold = never) behind sos_dmalloc / sos_dfree
 };
