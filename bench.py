@@ -137,7 +137,7 @@ def run_reference(args, rank, world):
                        "nb_gauss": NB_GAUSS, "os_nb": OS_NB},
             "cpu_baseline": r,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 def dgemm_peak(torch, dev):
@@ -157,6 +157,16 @@ def dgemm_peak(torch, dev):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+_STDOUT_FD = None
+
+
+def _emit(text):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(text, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,6 +177,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # Library banners (e.g. "NCCL version ...") go to fd 1: keep stdout for the ONE JSON line by pointing fd 1 at
+    # stderr while working and restoring it for the final print.
+    sys.stdout.flush()
+    global _STDOUT_FD
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -316,7 +332,7 @@ def main():
                          "hbm_recurrence_GBs": st_acc["bytes"] / (st_acc["step_ms"] * 1e-3) / 1e9 if st_acc["step_ms"] else 0},
             "cpu_baseline": cb,
         }
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     batch.free()
     solver.close()
     if world > 1:
