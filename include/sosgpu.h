@@ -52,6 +52,9 @@ const char *sosgpu_last_error(const sosgpu_ctx *ctx);
 int  sosgpu_device_count(void);
 /* number of kernels this library has launched since create (bench.py's gpu_launches) */
 long long sosgpu_launch_count(const sosgpu_ctx *ctx);
+/* device time (CUDA events on the library's stream) of the kernel launched by the last sosgpu_glitter or
+ * sosgpu_batch_trphi call, ms */
+double sosgpu_last_kernel_ms(const sosgpu_ctx *ctx);
 /* wave sizing knobs: device memory budget for field buffers (bytes, 0 = default) and the
  * maximum number of Fourier orders solved concurrently per term (0 = automatic) */
 int  sosgpu_set_options(sosgpu_ctx *ctx, size_t field_budget_bytes, int max_wave_orders);

@@ -71,6 +71,8 @@ def load_library():
         lib.sosgpu_last_error.argtypes = [C.c_void_p]
         lib.sosgpu_last_error.restype = C.c_char_p
         lib.sosgpu_launch_count.argtypes = [C.c_void_p]
+        lib.sosgpu_last_kernel_ms.argtypes = [C.c_void_p]
+        lib.sosgpu_last_kernel_ms.restype = C.c_double
         lib.sosgpu_launch_count.restype = C.c_longlong
         lib.sosgpu_set_options.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
         lib.sosgpu_batch_upload.argtypes = [C.c_void_p, C.POINTER(COptics), C.c_int, C.POINTER(CTerm), C.c_int,
@@ -334,6 +336,10 @@ class Solver:
         if n < 0:
             self._check(n, "trphi_option")
         return n, phi_fin[:n], theta, up[:, :n], down[:, :n]
+
+    @property
+    def last_kernel_ms(self):
+        return float(self.lib.sosgpu_last_kernel_ms(self.ctx))
 
     def glitter(self, nbmu, rmu, chr_, wind, ind_surf, os_nb, os_ns, os_nm):
         """SOS_GLITTER (SOS_GLITTER.F:229): surface-file records [os_nb+1, 9, N, N] REAL*4 and the G-series lengths."""

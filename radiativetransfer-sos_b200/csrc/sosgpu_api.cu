@@ -104,7 +104,8 @@ extern "C" int sosgpu_create(sosgpu_ctx **out, int device)
   unsigned long long keep_all = ~0ull;
   if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess ||
       cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep_all) != cudaSuccess ||
-      cudaMallocHost(&ctx->h_count, 2 * sizeof(int)) != cudaSuccess) {
+      cudaMallocHost(&ctx->h_count, 2 * sizeof(int)) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess) {
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SOSGPU_ERR_CUDA;
@@ -121,12 +122,15 @@ extern "C" void sosgpu_destroy(sosgpu_ctx *ctx)
   cudaFree(ctx->grec_cache); cudaFree(ctx->cache_field); cudaFree(ctx->cache_kpool);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->h_count) cudaFreeHost(ctx->h_count);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
 extern "C" const char *sosgpu_last_error(const sosgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 extern "C" long long sosgpu_launch_count(const sosgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" double sosgpu_last_kernel_ms(const sosgpu_ctx *ctx) { return ctx ? (double)ctx->last_kernel_ms : 0.0; }
 extern "C" int sosgpu_set_options(sosgpu_ctx *ctx, size_t field_budget_bytes, int max_wave_orders)
 {
   if (!ctx) return SOSGPU_ERR_ARG;
@@ -886,7 +890,9 @@ extern "C" int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *b, int igli, do
   CK(cudaMemcpyAsync(d_phi, phis.data(), nphi * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(d_out, 0, nout * 8, ctx->stream));
   TrphiParams prm{igli, ifresnel, ipolar, wind, ind_surf, pi};
+  cudaEventRecord(ctx->ev_a, ctx->stream);
   sos_launch_trphi_stride(d_g, ng, d_phi, nphi, nmax, prm, d_out, ctx->stream);
+  cudaEventRecord(ctx->ev_b, ctx->stream);
   ctx->launches += 1;
   if (up || down) {
     std::vector<double> &out = b->h_tout;
@@ -903,6 +909,7 @@ extern "C" int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *b, int igli, do
       }
   } else CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
+  cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);
   return nphi;
 }
 

@@ -20,6 +20,7 @@ struct sosgpu_ctx {
   long long launches = 0;
   size_t field_budget = (size_t)48 << 30;
   int max_wave_orders = 0;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr; float last_kernel_ms = 0.f;   // device time of the last glitter / synthesis kernel
   int *h_count = nullptr;            // pinned word pair for the active-count readback of the wave loop
   char *cache_field = nullptr; size_t cache_field_bytes = 0;   // wave pools parked by the last freed batch
   char *cache_kpool = nullptr; size_t cache_kpool_bytes = 0;

@@ -193,12 +193,15 @@ extern "C" int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, cons
   p.coef = 1.0 / p.sig;                                        // (1./SIG) (:315)
   p.pi = std::acos(-1.0);
   p.rmu = d_in; p.alpha = d_in + W; p.beta = p.alpha + (os_ns + 1); p.gamma = p.beta + (os_ns + 1); p.zeta = p.gamma + (os_ns + 1);
+  cudaEventRecord(ctx->ev_a, ctx->stream);
   sos_launch_glitter(p, d_surf, d_il, ctx->stream);
+  cudaEventRecord(ctx->ev_b, ctx->stream);
   ctx->launches += 1;
   CK(cudaMemcpyAsync(surf, d_surf, nsurf * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (il_out) CK(cudaMemcpyAsync(il_out, d_il, npair * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
+  cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);
   cudaFree(d_in); cudaFree(d_surf); cudaFree(d_il);
   return SOSGPU_OK;
 }
