@@ -543,6 +543,387 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
 #undef TPH
 }
 
+// =================================================================================================
+// k_step2 -- EXPERIMENTAL (SOS_DBG & 128), parity-green but slower than k_step as of round 1 (16.4 vs 22.6 TFLOP/s):
+// same operator as k_step<LR, 0>, different schedule:
+//   * the TMA pipeline runs over the linear sequence (chunk, k-slab) and never drains between level chunks;
+//   * the recurrence epilogue works on the DMMA accumulators IN REGISTERS: source function, layer constants c and the
+//     serial recurrence z <- z*a + c (handed from lane to lane of a quad by shuffles, in the reference's level order)
+//     never go through a shared staging tile, and the new field is stored straight from the accumulator layout
+//     (16-byte stores, a quad writes 64 contiguous bytes of a row);
+//   * no CTA barrier per chunk (LR: one, for the 4 x 64 Rayleigh functionals): warps drift apart, so one warp's
+//     epilogue runs under the other warps' DMMAs of the next chunk.
+// Per-chunk layer tables are single-buffered behind a full/free mbarrier pair.
+template <int LR>
+__global__ void __launch_bounds__(256, 2)
+k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, const OpticsDev *__restrict__ optics,
+        const KsetDev *__restrict__ ksets, const int *__restrict__ list, int tiles_per_dir, int want_lr, int att_cap,
+        double *__restrict__ jdump)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int nthr = blockDim.x;
+  const int nw_launch = nthr >> 5;
+  const int rows_max = nw_launch * 16;
+  const int stage_bytes = STAGE_A_BYTES(rows_max) + (LR ? STAGE_V_BYTES : 0) + STAGE_B_BYTES;
+  double *sT = reinterpret_cast<double *>(smem_raw + SOS_STAGES * stage_bytes);   // [2][4][64] Rayleigh functionals (double-buffered)
+  double *sG = sT + 2 * 4 * SOS_CH;                                     // [3N] ground values of the downward field
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(sG + 3 * 80);
+  unsigned long long *empty = full + SOS_STAGES;
+  unsigned long long *tabfull = empty + SOS_STAGES;                     // layer tables of the chunk have landed
+  unsigned long long *tabfree = tabfull + 1;                            // every warp is done with the chunk's tables
+  double *sDt = reinterpret_cast<double *>(full + 2 * SOS_STAGES + 2);  // [<=66] layer optical thickness of the chunk
+  double *sInv = sDt + 72;
+  double *sXd = sInv + 72;
+  double *sYd = sXd + 72;
+  double *sU = sYd + 72;                                                // [128] urow of the tile's rows (LR)
+  double *sBc = sU + 128;                                               // [128] ground boundary value of the tile's rows
+  double *sAtt = sBc + 128;                                             // [<=66][N] exp(-dtau/mu_k) (when att_cap > 0)
+
+  const int per_item = 2 * tiles_per_dir;
+  const int ii = blockIdx.x / per_item, t = blockIdx.x % per_item;
+  const int item = list ? list[ii] : ii;
+  const ItemDev it = items[item];
+  const KsetDev ks = ksets[it.kset];
+  if (ks.dual != want_lr) return;                                // handled by the other instantiation
+  const TermDev tm = terms[it.term];
+  const OpticsDev &op = optics[tm.optics];
+  const int N = op.nbmu, HB = op.HB, KP = op.KP, NT = tm.nt, L = NT + 1, LP = tm.LP;
+  const int dir = t / tiles_per_dir, tile = t % tiles_per_dir;
+  const int groups = HB >> 4;
+  const int gpt = (groups + tiles_per_dir - 1) / tiles_per_dir;
+  const int g0 = tile * gpt;
+  if (g0 >= groups) return;
+  const int ng = min(gpt, groups - g0);
+  const int R = ng * 16;
+  const int r0 = dir * HB + g0 * 16;
+  const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const bool up = (dir == 0);
+  const double *__restrict__ xprev = it.x[it.n & 1];
+  double *__restrict__ xnext = it.x[(it.n + 1) & 1];
+
+  if (tid == 0) {
+    for (int s = 0; s < SOS_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, nw_launch); }
+    mbar_init(tabfull, 1);
+    mbar_init(tabfree, nw_launch);
+    fence_proxy_async();
+  }
+  if (LR && tid < R) sU[tid] = (r0 + tid - dir * HB < 3 * N) ? ks.urow[r0 + tid] : 0.0;
+
+  // ---------------- prologue: ground boundary value of row tid (mu > 0 rows only), as in k_step ----------------
+  {
+    const int q = (tid < R) ? (r0 + tid - dir * HB) : 3 * N;
+    const bool rowvalid = (tid < R) && (q < 3 * N);
+    const int so = rowvalid ? q / N : 0, kk = rowvalid ? q % N + 1 : 1;
+    const double mu = op.rmu[kk + N];
+    double bc = 0.0;
+    if (up) {
+      for (int c = tid; c < 3 * N; c += nthr) sG[c] = xprev[SOS_XIDX(KP, HB + c, NT)];
+      __syncthreads();
+      if (rowvalid) {
+        double xr = 0.0;
+        if (!(op.ro == 0.0 || it.is != 0)) {                     // Lambert (SOS_OS.F:1177-1190)
+          double lsol = 0.0;
+          for (int j = 1; j <= N; ++j) lsol = lsol + op.ga[j + N] * sG[j - 1] * op.rmu[j + N];
+          lsol = 2 * lsol * op.ro;
+          xr = lsol;
+          if (so == 0) bc = lsol;
+        }
+        if (op.imat_surf == 1) {                                 // BRDF / BPDF quadrature (SOS_OS.F:1194-1220)
+          const float *rs = op.surf + (size_t)it.is * 9 * N * N + (size_t)(so * 3) * N * N + (size_t)(kk - 1) * N;
+          const bool pol = (op.ipolar != 0);
+          double acc = 0.0;
+          for (int j = 1; j <= N; ++j) {
+            double r1 = (double)rs[j - 1], r2 = (double)rs[(size_t)N * N + j - 1], r3 = (double)rs[(size_t)2 * N * N + j - 1];
+            if (!pol) { if (so == 0) { r2 = 0.0; r3 = 0.0; } else { r1 = 0.0; r2 = 0.0; r3 = 0.0; } }
+            acc = acc + op.ga[j + N] * (sG[j - 1] * r1 + sG[N + j - 1] * r2 + sG[2 * N + j - 1] * r3);
+          }
+          const double rrmu = 2 / mu;
+          bc = (so == 0) ? acc * rrmu + xr : acc * rrmu;
+        }
+        if (op.ifresnel == 1) {                                  // flat sea (SOS_OS.F:1225-1239)
+          const double gi = sG[kk - 1], gqv = sG[N + kk - 1], gu = sG[2 * N + kk - 1];
+          if (so == 0) bc = bc + op.f11[kk] * gi + op.f12[kk] * gqv;
+          else if (so == 1) bc = bc + op.f12[kk] * gi + op.f11[kk] * gqv;
+          else bc = bc + op.f33[kk] * gu;
+        }
+      }
+    }
+    if (tid < 128) sBc[tid] = bc;
+  }
+  __syncthreads();                                               // mbarrier inits, sU, sBc visible
+
+  const int n_chunk = (L + SOS_CH - 1) / SOS_CH;
+  const int n_slab = KP / SOS_KB;
+  const int n_iter = n_chunk * n_slab;                           // linear (chunk, slab) sequence of the pipeline
+  const double *__restrict__ Ag = ks.apackA + (size_t)r0 * SOS_KB;
+  const double *__restrict__ Vg = LR ? ks.vpack + (size_t)dir * 8 * KP : nullptr;
+  const bool att_staged = (att_cap >= 66 * N);
+  const unsigned tx = (unsigned)(R * SOS_KB * 8 + (LR ? STAGE_V_BYTES : 0) + STAGE_B_BYTES);
+
+  auto issue = [&](int qi) {                                     // thread 0 only: loads of linear iteration qi
+    const int ch = qi / n_slab, slab = qi - ch * n_slab;
+    const int c0i = (up ? (n_chunk - 1 - ch) : ch) * SOS_CH;
+    unsigned char *sp = smem_raw + (qi % SOS_STAGES) * stage_bytes;
+    unsigned long long *bar = full + (qi % SOS_STAGES);
+    mbar_expect_tx(bar, tx);
+    bulk_g2s(sp, Ag + (size_t)slab * KP * SOS_KB, (unsigned)(R * SOS_KB * 8), bar);
+    sp += STAGE_A_BYTES(rows_max);
+    if (LR) { bulk_g2s(sp, Vg + (size_t)slab * 8 * SOS_KB, STAGE_V_BYTES, bar); sp += STAGE_V_BYTES; }
+    bulk_g2s(sp, xprev + SOS_XIDX(KP, slab * SOS_KB, c0i), STAGE_B_BYTES, bar);
+  };
+  auto issue_tables = [&](int ch) {                              // thread 0 only: layer tables of chunk ch
+    const int c0i = (up ? (n_chunk - 1 - ch) : ch) * SOS_CH;
+    const int lb = max(c0i - 1, 0) & ~1;
+    const int le = min(c0i + SOS_CH - 1, NT - 1);
+    const int nrow = (le - lb + 2) & ~1;
+    const int nlev = (min(SOS_CH, L - c0i) + 1) & ~1;
+    fence_proxy_async();
+    mbar_expect_tx(tabfull, (unsigned)(nrow * 16 + nlev * 16 + (att_staged ? nrow * N * 8 : 0)));
+    bulk_g2s(sXd, tm.xdel + c0i, (unsigned)(nlev * 8), tabfull);
+    bulk_g2s(sYd, tm.ydel + c0i, (unsigned)(nlev * 8), tabfull);
+    bulk_g2s(sDt, tm.dt + lb, (unsigned)(nrow * 8), tabfull);
+    bulk_g2s(sInv, tm.inv + lb, (unsigned)(nrow * 8), tabfull);
+    if (att_staged) bulk_g2s(sAtt, tm.att + (size_t)lb * N, (unsigned)(nrow * N * 8), tabfull);
+  };
+  if (tid == 0) {
+    issue_tables(0);
+    for (int s = 0; s < SOS_STAGES - 1 && s < n_iter; ++s) issue(s);
+  }
+
+  // rows of this thread in the accumulator layout: local row wr*16 + mi*8 + gq
+  const bool own = wr < ng;
+  bool rvalid[2];
+  double mu_r[2], bc_r[2], u0[2] = {0.0, 0.0}, us[2] = {0.0, 0.0};
+  int kidx[2], ty[2] = {0, 0};
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+    const int rl = wr * 16 + mi * 8 + gq;
+    const int qr = g0 * 16 + rl;                                 // row within the direction block
+    rvalid[mi] = own && (qr < 3 * N);
+    kidx[mi] = rvalid[mi] ? qr % N + 1 : 1;
+    mu_r[mi] = op.rmu[kidx[mi] + N];
+    bc_r[mi] = own ? sBc[rl & 127] : 0.0;
+    if (LR && rvalid[mi]) { ty[mi] = qr / N; us[mi] = sU[rl]; u0[mi] = (ty[mi] == 0) ? 1.0 : 0.0; }
+  }
+  double z[2] = {0.0, 0.0};                                       // recurrence state of the two rows
+  double scarry[2] = {0.0, 0.0};                                  // source function at the neighbouring level of the previous chunk
+  double acc[2][8][2];
+  double tacc[2][2];
+  const int qbase = lane & ~3;
+
+  for (int chunk = 0; chunk < n_chunk; ++chunk) {
+    const int ci = up ? (n_chunk - 1 - chunk) : chunk;
+    const int c0 = ci * SOS_CH;
+    const int lb_al = max(c0 - 1, 0) & ~1;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    tacc[0][0] = tacc[0][1] = tacc[1][0] = tacc[1][1] = 0.0;
+    const int nfr = (min(SOS_CH, L - c0) + 7) >> 3;
+
+    for (int slab = 0; slab < n_slab; ++slab) {
+      const int qi = chunk * n_slab + slab;
+      const int stage = qi % SOS_STAGES;
+      if (tid == 0) {
+        if (qi + SOS_STAGES - 1 < n_iter) {
+          if (qi >= 1) mbar_wait(empty + (qi - 1) % SOS_STAGES, ((qi - 1) / SOS_STAGES) & 1);
+          issue(qi + SOS_STAGES - 1);
+        }
+        if (chunk >= 1 && slab == (n_slab >> 1)) {                 // tables of this chunk, once everybody left the previous one
+          mbar_wait(tabfree, (chunk - 1) & 1);
+          issue_tables(chunk);
+        }
+      }
+      mbar_wait(full + stage, (qi / SOS_STAGES) & 1);
+      if (own || LR) {
+        const unsigned char *sp = smem_raw + stage * stage_bytes;
+        const double *a = reinterpret_cast<const double *>(sp) + (wr * 16 + gq) * SOS_KB;
+        const double *v = reinterpret_cast<const double *>(sp + STAGE_A_BYTES(rows_max)) + gq * SOS_KB;
+        const double *b = reinterpret_cast<const double *>(sp + STAGE_A_BYTES(rows_max) + (LR ? STAGE_V_BYTES : 0)) + tq * SOS_SB + gq;
+        const int kq = (slab * SOS_KB) % HB;
+        const int ks_lim = (kq + SOS_KB <= 3 * N) ? 4 : max(0, (3 * N - kq + 3) >> 2);
+        switch (nfr) {
+          case 8: slab_mma<8, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+          case 7: slab_mma<7, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+          case 6: slab_mma<6, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+          case 5: slab_mma<5, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+          case 4: slab_mma<4, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+          case 3: slab_mma<3, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+          case 2: slab_mma<2, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+          default: slab_mma<1, LR>(acc, tacc, a, v, b, own, wr, nw_launch, gq, tq, ks_lim); break;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + stage);
+    }
+
+    // ---------------- epilogue of this warp's 16 rows, in registers ----------------
+    const double *sTc = sT + (chunk & 1) * 4 * SOS_CH;
+    if (LR) {
+      double *sTw = sT + (chunk & 1) * 4 * SOS_CH;
+      if (gq < 4) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int ni = wr + u * nw_launch;
+          if (ni < 8) { sTw[gq * SOS_CH + ni * 8 + 2 * tq] = tacc[u][0]; sTw[gq * SOS_CH + ni * 8 + 2 * tq + 1] = tacc[u][1]; }
+        }
+      }
+      __syncthreads();                                           // the only CTA barrier per chunk (LR instantiation)
+    }
+    mbar_wait(tabfull, chunk & 1);
+    if (own) {
+      const int hi = min(c0 + SOS_CH - 1, NT);                    // last real level of the chunk
+      // --- source function S = XDEL * (A_A X) + YDEL * (A_R X) in place (SOS_FSOURCE_ORDREIG) ---
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = ni * 8 + 2 * tq + e;
+          const bool lv_ok = (c0 + col) < L;
+          const double xd = lv_ok ? sXd[col] : 0.0;
+          const double yd = (LR && lv_ok) ? sYd[col] : 0.0;
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            double v = lv_ok ? xd * acc[mi][ni][e] : 0.0;
+            if (LR && lv_ok) v = v + yd * (u0[mi] * sTc[col] + us[mi] * sTc[(ty[mi] + 1) * SOS_CH + col]);
+            acc[mi][ni][e] = v;
+          }
+        }
+      if (jdump) {                                               // test hook: expose the source function
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int level = c0 + ni * 8 + 2 * tq + e;
+              if (level < L) jdump[(size_t)(r0 + wr * 16 + mi * 8 + gq) * LP + level] = acc[mi][ni][e];
+            }
+      }
+      const double *dtp = sDt - lb_al, *ivp = sInv - lb_al;
+      const double *attp[2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+        attp[mi] = att_staged ? (sAtt + (kidx[mi] - 1) - (size_t)lb_al * N) : (tm.att + (kidx[mi] - 1));
+
+      if (up) {
+        // --- layer constants c(i) = (1-a)(A mu + S(i)) - A a dtau, A = (S(i+1) - S(i)) / dtau  (SOS_OS.F:2279-2310) ---
+        double edge[2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) edge[mi] = __shfl_sync(0xffffffffu, acc[mi][0][0], qbase);   // S at column 0 (before it is replaced)
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            // neighbour S(i+1) of this thread's second level: first level of the next lane, or of the next column block
+            const double nx_lane = __shfl_sync(0xffffffffu, acc[mi][ni][0], qbase | ((tq + 1) & 3));
+            const double nx_blk = (ni < 7) ? __shfl_sync(0xffffffffu, acc[mi][ni < 7 ? ni + 1 : 7][0], qbase) : scarry[mi];
+            const double s0 = acc[mi][ni][0], s1 = acc[mi][ni][1];
+            const double s2 = (tq == 3) ? nx_blk : nx_lane;   // levels beyond NT hold S = 0 by construction
+            const int col0 = ni * 8 + 2 * tq;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int level = c0 + col0 + e;
+              const int lv = min(level, NT - 1);
+              const double a = attp[mi][(size_t)lv * N], dl = dtp[lv], iv = ivp[lv];
+              const double sa = e ? s1 : s0, sb = e ? s2 : s1;
+              const double A = (sb - sa) * iv;
+              const double cv = (1.0 - a) * (A * mu_r[mi] + sa) - A * (a * dl);
+              if (level < NT) acc[mi][ni][e] = cv;
+            }
+          }
+        }
+        // --- recurrence z <- z a + c from the ground upwards (descending level), serial across the quad ---
+#pragma unroll
+        for (int ni = 7; ni >= 0; --ni) {
+#pragma unroll
+          for (int tt = 3; tt >= 0; --tt) {
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+              double zz = z[mi];
+#pragma unroll
+              for (int e = 1; e >= 0; --e) {
+                const int level = c0 + ni * 8 + 2 * tt + e;
+                if (level == NT) zz = bc_r[mi];
+                else if (level < NT) zz = zz * attp[mi][(size_t)level * N] + acc[mi][ni][e];
+                if (tq == tt && level <= NT) acc[mi][ni][e] = zz;
+              }
+              z[mi] = __shfl_sync(0xffffffffu, zz, qbase | tt);
+            }
+          }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) scarry[mi] = edge[mi];
+      } else {
+        // --- c(i) = (1-a)(A (-mu) + S(i)) + A a dtau, A = (S(i) - S(i-1)) / dtau  (SOS_OS.F:2320-2354) ---
+        double edge[2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) edge[mi] = __shfl_sync(0xffffffffu, acc[mi][7][1], qbase | 3);   // S at column 63
+#pragma unroll
+        for (int ni = 7; ni >= 0; --ni) {
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            const double pv_lane = __shfl_sync(0xffffffffu, acc[mi][ni][1], qbase | ((tq + 3) & 3));
+            const double pv_blk = (ni > 0) ? __shfl_sync(0xffffffffu, acc[mi][ni > 0 ? ni - 1 : 0][1], qbase | 3) : scarry[mi];
+            const double s1 = acc[mi][ni][0], s2 = acc[mi][ni][1];
+            const double s0 = (tq == 0) ? pv_blk : pv_lane;
+            const int col0 = ni * 8 + 2 * tq;
+            const double rmuk = -mu_r[mi];
+#pragma unroll
+            for (int e = 1; e >= 0; --e) {
+              const int level = c0 + col0 + e;
+              const int lv = min(max(level, 1), NT);
+              const double a = attp[mi][(size_t)(lv - 1) * N], dl = dtp[lv - 1], iv = ivp[lv - 1];
+              const double sa = e ? s2 : s1, sb = e ? s1 : s0;
+              const double A = (sa - sb) * iv;
+              const double cv = (1.0 - a) * (A * rmuk + sa) + A * (a * dl);
+              if (level > 0 && level <= hi) acc[mi][ni][e] = cv;
+            }
+          }
+        }
+        // --- recurrence from the top downwards (ascending level) ---
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+              double zz = z[mi];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int level = c0 + ni * 8 + 2 * tt + e;
+                if (level == 0) zz = 0.0;
+                else if (level <= hi) zz = zz * attp[mi][(size_t)(level - 1) * N] + acc[mi][ni][e];
+                if (tq == tt && level <= hi) acc[mi][ni][e] = zz;
+              }
+              z[mi] = __shfl_sync(0xffffffffu, zz, qbase | tt);
+            }
+          }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) scarry[mi] = edge[mi];
+      }
+      // --- new field, straight from the accumulator layout ---
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        if (!rvalid[mi]) continue;
+        const int row = r0 + wr * 16 + mi * 8 + gq;
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+          const int level = c0 + ni * 8 + 2 * tq;
+          double *dst = xnext + SOS_XIDX(KP, row, level);
+          if (level + 1 < L) *reinterpret_cast<double2 *>(dst) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+          else if (level < L) dst[0] = acc[mi][ni][0];
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tabfree);                         // this warp no longer reads the chunk's tables
+  }
+}
+
 static size_t step_smem_bytes(int nw, int lr, int order1, int att_cap)
 {
   const size_t rows = (size_t)nw * 16;
@@ -550,6 +931,13 @@ static size_t step_smem_bytes(int nw, int lr, int order1, int att_cap)
   const size_t pipe = order1 ? 0 : SOS_STAGES * stage;
   const size_t sj = rows * SOS_SJ * 8;
   return (pipe > sj ? pipe : sj) + (4 * SOS_CH + 3 * 80) * 8 + (2 * SOS_STAGES + 2) * 8 + (6 * 72 + 128 + 4 * 128 + att_cap) * 8 + 128;
+}
+
+static size_t step2_smem_bytes(int nw, int lr, int att_cap)
+{
+  const size_t rows = (size_t)nw * 16;
+  const size_t stage = STAGE_A_BYTES(rows) + (lr ? STAGE_V_BYTES : 0) + STAGE_B_BYTES;
+  return SOS_STAGES * stage + (2 * 4 * SOS_CH + 3 * 80) * 8 + (2 * SOS_STAGES + 2) * 8 + (4 * 72 + 128 + 128 + att_cap) * 8 + 128;
 }
 
 extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const OpticsDev *optics,
@@ -563,6 +951,8 @@ extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const
     cudaFuncSetAttribute(k_step<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_step<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_step<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_step2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_step2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     attr_done = true;
   }
   const int groups = maxHB / 16;
@@ -577,6 +967,15 @@ extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const
   if (order1) {
     k_step<0, 1><<<grid, block, step_smem_bytes(nw, 0, 1, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, att_cap, jdump, dbg);
     launches = 1;
+  } else if (dbg & 128) {                                        // experimental (round 2): register-resident epilogue, see DESIGN.md 7
+    if (mode & 1) {
+      k_step2<0><<<grid, block, step2_smem_bytes(nw, 0, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, att_cap, jdump);
+      ++launches;
+    }
+    if (mode & 2) {
+      k_step2<1><<<grid, block, step2_smem_bytes(nw, 1, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 1, att_cap, jdump);
+      ++launches;
+    }
   } else {
     if (mode & 1) {                                              // aerosol-only Fourier orders (is > 2)
       k_step<0, 0><<<grid, block, step_smem_bytes(nw, 0, 0, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, att_cap, jdump, dbg);
