@@ -41,11 +41,6 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
 {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// timing experiments: account bytes as transferred without moving them
-__device__ __forceinline__ void mbar_expect_tx_only_dummy(unsigned long long *bar, unsigned bytes)
-{
-  asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -284,8 +279,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
         unsigned char *sp = smem_raw + stage * stage_bytes;
         unsigned long long *bar = full + stage;
         mbar_expect_tx(bar, tx);
-        if (dbg & 4) mbar_expect_tx_only_dummy(bar, (unsigned)(R * SOS_KB * 8));
-        else bulk_g2s(sp, Ag + (size_t)slab * KP * SOS_KB, (unsigned)(R * SOS_KB * 8), bar);
+        bulk_g2s(sp, Ag + (size_t)slab * KP * SOS_KB, (unsigned)(R * SOS_KB * 8), bar);
         sp += STAGE_A_BYTES(rows_max);
         if (LR) { bulk_g2s(sp, Vg + (size_t)slab * 8 * SOS_KB, STAGE_V_BYTES, bar); sp += STAGE_V_BYTES; }
         // chunk-major padded field layout: the 16 x 64 slab (pitch SOS_SB) is one contiguous block
@@ -310,7 +304,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
           issue(slab + SOS_STAGES - 1, cnt + SOS_STAGES - 1);
         }
         mbar_wait(full + stage, (cnt / SOS_STAGES) & 1);
-        if ((wr < ng || LR) && !(dbg & 1)) {
+        if (wr < ng || LR) {
           const unsigned char *sp = smem_raw + stage * stage_bytes;
           const double *a = reinterpret_cast<const double *>(sp) + (wr * 16 + gq) * SOS_KB;
           const double *v = reinterpret_cast<const double *>(sp + STAGE_A_BYTES(rows_max)) + gq * SOS_KB;
@@ -348,7 +342,6 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       if (LR) __syncthreads();
     }
 
-    if (dbg & 2) { __syncthreads(); continue; }                  // timing experiments only (SOS_DBG)
     // ---------------- tile epilogue: source function -> staging tile ----------------
     if (ORDER1) {
       __syncthreads();                                           // previous chunk's write-out has finished
@@ -960,7 +953,7 @@ extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const
   const int nw = std::max((groups + tiles_per_dir - 1) / tiles_per_dir, 4);   // >= 4 warps: T = V X needs 8 column blocks / 2
   const int nmax = maxHB / 3;                                    // 3N <= HB
   const int att_cap = (nmax <= 48) ? 66 * nmax : 0;            // stage the attenuation table of a chunk in smem when it fits
-  static const int dbg = getenv("SOS_DBG") ? atoi(getenv("SOS_DBG")) : 0;   // timing experiments only
+  static const int dbg = getenv("SOS_DBG") ? atoi(getenv("SOS_DBG")) : 0;   // 16: phase timing (SOS_PHASE_TIMING builds), 128: k_step2
   const dim3 grid((unsigned)nitem * 2 * tiles_per_dir);
   const dim3 block(nw * 32);
   int launches = 0;
