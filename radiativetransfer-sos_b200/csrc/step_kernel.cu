@@ -550,8 +550,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
 template <int LR>
 __global__ void __launch_bounds__(256, 2)
 k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, const OpticsDev *__restrict__ optics,
-        const KsetDev *__restrict__ ksets, const int *__restrict__ list, int tiles_per_dir, int want_lr, int att_cap,
-        double *__restrict__ jdump)
+        const KsetDev *__restrict__ ksets, const int *__restrict__ list, int tiles_per_dir, int want_lr, int att_cap)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nthr = blockDim.x;
@@ -580,7 +579,7 @@ k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
   if (ks.dual != want_lr) return;                                // handled by the other instantiation
   const TermDev tm = terms[it.term];
   const OpticsDev &op = optics[tm.optics];
-  const int N = op.nbmu, HB = op.HB, KP = op.KP, NT = tm.nt, L = NT + 1, LP = tm.LP;
+  const int N = op.nbmu, HB = op.HB, KP = op.KP, NT = tm.nt, L = NT + 1;
   const int dir = t / tiles_per_dir, tile = t % tiles_per_dir;
   const int groups = HB >> 4;
   const int gpt = (groups + tiles_per_dir - 1) / tiles_per_dir;
@@ -705,6 +704,7 @@ k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
   double tacc[2][2];
   const int qbase = lane & ~3;
 
+#pragma unroll 1
   for (int chunk = 0; chunk < n_chunk; ++chunk) {
     const int ci = up ? (n_chunk - 1 - chunk) : chunk;
     const int c0 = ci * SOS_CH;
@@ -763,152 +763,177 @@ k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
           if (ni < 8) { sTw[gq * SOS_CH + ni * 8 + 2 * tq] = tacc[u][0]; sTw[gq * SOS_CH + ni * 8 + 2 * tq + 1] = tacc[u][1]; }
         }
       }
-      __syncthreads();                                           // the only CTA barrier per chunk (LR instantiation)
     }
     mbar_wait(tabfull, chunk & 1);
+    const int off = c0 - lb_al;                                  // table row of column 0 (0 or 2)
+    if (up && chunk == 0) {
+      // The chunk that holds level NT (swept first): blank the table entries of the levels / layers that do not exist,
+      // so that the element code below needs no level predicates: S = 0, a = 0, c = 0 there, and z stays 0 until
+      // level NT, where c is replaced by the ground boundary value.
+      const int cN = NT - c0;
+      for (int c = cN + 1 + tid; c < SOS_CH; c += nthr) { sXd[c] = 0.0; sYd[c] = 0.0; }
+      const int rs = NT - lb_al;
+      for (int r = rs + tid; r < 72; r += nthr) { sDt[r] = 0.0; sInv[r] = 0.0; }
+      for (int idx = rs * N + tid; idx < 66 * N; idx += nthr) sAtt[idx] = 0.0;
+    }
+    if (LR || (up && chunk == 0)) __syncthreads();               // sT of this chunk / blanked tables visible (CTA-uniform)
     if (own) {
-      const int hi = min(c0 + SOS_CH - 1, NT);                    // last real level of the chunk
+      const double *xdp = sXd + 2 * tq, *ydp = sYd + 2 * tq;
       // --- source function S = XDEL * (A_A X) + YDEL * (A_R X) in place (SOS_FSOURCE_ORDREIG) ---
 #pragma unroll
       for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int col = ni * 8 + 2 * tq + e;
-          const bool lv_ok = (c0 + col) < L;
-          const double xd = lv_ok ? sXd[col] : 0.0;
-          const double yd = (LR && lv_ok) ? sYd[col] : 0.0;
+          const double xd = xdp[ni * 8 + e];
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) {
-            double v = lv_ok ? xd * acc[mi][ni][e] : 0.0;
-            if (LR && lv_ok) v = v + yd * (u0[mi] * sTc[col] + us[mi] * sTc[(ty[mi] + 1) * SOS_CH + col]);
+            double v = xd * acc[mi][ni][e];
+            if (LR) {
+              const int col = ni * 8 + 2 * tq + e;
+              v = v + ydp[ni * 8 + e] * (u0[mi] * sTc[col] + us[mi] * sTc[(ty[mi] + 1) * SOS_CH + col]);
+            }
             acc[mi][ni][e] = v;
           }
         }
-      if (jdump) {                                               // test hook: expose the source function
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 8; ++ni)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int level = c0 + ni * 8 + 2 * tq + e;
-              if (level < L) jdump[(size_t)(r0 + wr * 16 + mi * 8 + gq) * LP + level] = acc[mi][ni][e];
-            }
-      }
-      const double *dtp = sDt - lb_al, *ivp = sInv - lb_al;
-      const double *attp[2];
-#pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
-        attp[mi] = att_staged ? (sAtt + (kidx[mi] - 1) - (size_t)lb_al * N) : (tm.att + (kidx[mi] - 1));
-
+      const int N8 = 8 * N;
       if (up) {
+        // table row of column col is col + off; this thread's columns are ni*8 + 2*tq + e
+        const double *dp = sDt + off + 2 * tq, *ip = sInv + off + 2 * tq;
+        const double *ap0 = sAtt + (kidx[0] - 1) + (off + 2 * tq) * N, *ap1 = sAtt + (kidx[1] - 1) + (off + 2 * tq) * N;
         // --- layer constants c(i) = (1-a)(A mu + S(i)) - A a dtau, A = (S(i+1) - S(i)) / dtau  (SOS_OS.F:2279-2310) ---
         double edge[2];
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi) edge[mi] = __shfl_sync(0xffffffffu, acc[mi][0][0], qbase);   // S at column 0 (before it is replaced)
+        for (int mi = 0; mi < 2; ++mi) edge[mi] = __shfl_sync(0xffffffffu, acc[mi][0][0], qbase);   // S at column 0
 #pragma unroll
         for (int ni = 0; ni < 8; ++ni) {
+          const double dl0 = dp[ni * 8], dl1 = dp[ni * 8 + 1], iv0 = ip[ni * 8], iv1 = ip[ni * 8 + 1];
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) {
-            // neighbour S(i+1) of this thread's second level: first level of the next lane, or of the next column block
+            const double *ap = (mi ? ap1 : ap0) + ni * N8;
             const double nx_lane = __shfl_sync(0xffffffffu, acc[mi][ni][0], qbase | ((tq + 1) & 3));
             const double nx_blk = (ni < 7) ? __shfl_sync(0xffffffffu, acc[mi][ni < 7 ? ni + 1 : 7][0], qbase) : scarry[mi];
             const double s0 = acc[mi][ni][0], s1 = acc[mi][ni][1];
-            const double s2 = (tq == 3) ? nx_blk : nx_lane;   // levels beyond NT hold S = 0 by construction
-            const int col0 = ni * 8 + 2 * tq;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int level = c0 + col0 + e;
-              const int lv = min(level, NT - 1);
-              const double a = attp[mi][(size_t)lv * N], dl = dtp[lv], iv = ivp[lv];
-              const double sa = e ? s1 : s0, sb = e ? s2 : s1;
-              const double A = (sb - sa) * iv;
-              const double cv = (1.0 - a) * (A * mu_r[mi] + sa) - A * (a * dl);
-              if (level < NT) acc[mi][ni][e] = cv;
-            }
+            const double s2 = (tq == 3) ? nx_blk : nx_lane;
+            const double a0 = ap[0], a1 = ap[N];
+            const double A0 = (s1 - s0) * iv0, A1 = (s2 - s1) * iv1;
+            acc[mi][ni][0] = (1.0 - a0) * (A0 * mu_r[mi] + s0) - A0 * (a0 * dl0);
+            acc[mi][ni][1] = (1.0 - a1) * (A1 * mu_r[mi] + s1) - A1 * (a1 * dl1);
           }
         }
-        // --- recurrence z <- z a + c from the ground upwards (descending level), serial across the quad ---
+        if (chunk == 0) {                                         // level NT: X = boundary value (z*0 + bc)
+          const int cN = NT - c0;
+#pragma unroll
+          for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              if (ni * 8 + 2 * tq + e == cN) { acc[0][ni][e] = bc_r[0]; acc[1][ni][e] = bc_r[1]; }
+        }
+        // --- recurrence z <- z a + c from the ground upwards (descending level); a quad hands z from lane to lane ---
 #pragma unroll
         for (int ni = 7; ni >= 0; --ni) {
+          double aa[2][2], zin[2];
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            const double *ap = (mi ? ap1 : ap0) + ni * N8;
+            aa[mi][0] = ap[0]; aa[mi][1] = ap[N];
+            zin[mi] = z[mi];
+          }
 #pragma unroll
           for (int tt = 3; tt >= 0; --tt) {
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) {
-              double zz = z[mi];
-#pragma unroll
-              for (int e = 1; e >= 0; --e) {
-                const int level = c0 + ni * 8 + 2 * tt + e;
-                if (level == NT) zz = bc_r[mi];
-                else if (level < NT) zz = zz * attp[mi][(size_t)level * N] + acc[mi][ni][e];
-                if (tq == tt && level <= NT) acc[mi][ni][e] = zz;
-              }
-              z[mi] = __shfl_sync(0xffffffffu, zz, qbase | tt);
+              if (tq == tt) zin[mi] = z[mi];
+              double tv = z[mi] * aa[mi][1] + acc[mi][ni][1];
+              tv = tv * aa[mi][0] + acc[mi][ni][0];
+              z[mi] = __shfl_sync(0xffffffffu, tv, qbase | tt);
             }
+          }
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            const double o1 = zin[mi] * aa[mi][1] + acc[mi][ni][1];
+            acc[mi][ni][1] = o1;
+            acc[mi][ni][0] = o1 * aa[mi][0] + acc[mi][ni][0];
           }
         }
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) scarry[mi] = edge[mi];
       } else {
-        // --- c(i) = (1-a)(A (-mu) + S(i)) + A a dtau, A = (S(i) - S(i-1)) / dtau  (SOS_OS.F:2320-2354) ---
+        // layer of level i is i - 1: table row of column col is col - 1 + off (column 0 of level 0 is clamped; its
+        // constant is replaced by 0 below)
+        const int rb = off + 2 * tq - 1;
+        const double *dp = sDt + rb, *ip = sInv + rb;
+        const double *ap0 = sAtt + (kidx[0] - 1) + rb * N, *ap1 = sAtt + (kidx[1] - 1) + rb * N;
+        const int fix0 = (rb < 0) ? 1 : 0;                        // only (c0 = 0, tq = 0): first element uses row 0
         double edge[2];
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) edge[mi] = __shfl_sync(0xffffffffu, acc[mi][7][1], qbase | 3);   // S at column 63
+        const double rmuk0 = -mu_r[0], rmuk1 = -mu_r[1];
 #pragma unroll
         for (int ni = 7; ni >= 0; --ni) {
+          const int f = (ni == 0) ? fix0 : 0;
+          const double dl0 = dp[ni * 8 + f], dl1 = dp[ni * 8 + 1], iv0 = ip[ni * 8 + f], iv1 = ip[ni * 8 + 1];
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) {
+            const double *ap = (mi ? ap1 : ap0) + ni * N8;
             const double pv_lane = __shfl_sync(0xffffffffu, acc[mi][ni][1], qbase | ((tq + 3) & 3));
             const double pv_blk = (ni > 0) ? __shfl_sync(0xffffffffu, acc[mi][ni > 0 ? ni - 1 : 0][1], qbase | 3) : scarry[mi];
             const double s1 = acc[mi][ni][0], s2 = acc[mi][ni][1];
             const double s0 = (tq == 0) ? pv_blk : pv_lane;
-            const int col0 = ni * 8 + 2 * tq;
-            const double rmuk = -mu_r[mi];
-#pragma unroll
-            for (int e = 1; e >= 0; --e) {
-              const int level = c0 + col0 + e;
-              const int lv = min(max(level, 1), NT);
-              const double a = attp[mi][(size_t)(lv - 1) * N], dl = dtp[lv - 1], iv = ivp[lv - 1];
-              const double sa = e ? s2 : s1, sb = e ? s1 : s0;
-              const double A = (sa - sb) * iv;
-              const double cv = (1.0 - a) * (A * rmuk + sa) + A * (a * dl);
-              if (level > 0 && level <= hi) acc[mi][ni][e] = cv;
-            }
+            const double a0 = ap[f * N], a1 = ap[N];
+            const double rmuk = mi ? rmuk1 : rmuk0;
+            const double A0 = (s1 - s0) * iv0, A1 = (s2 - s1) * iv1;
+            acc[mi][ni][0] = (1.0 - a0) * (A0 * rmuk + s1) + A0 * (a0 * dl0);
+            acc[mi][ni][1] = (1.0 - a1) * (A1 * rmuk + s2) + A1 * (a1 * dl1);
           }
         }
+        if (c0 == 0 && tq == 0) { acc[0][0][0] = 0.0; acc[1][0][0] = 0.0; }   // level 0: X = 0 (z = 0 on entry)
         // --- recurrence from the top downwards (ascending level) ---
 #pragma unroll
         for (int ni = 0; ni < 8; ++ni) {
+          const int f = (ni == 0) ? fix0 : 0;
+          double aa[2][2], zin[2];
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            const double *ap = (mi ? ap1 : ap0) + ni * N8;
+            aa[mi][0] = ap[f * N]; aa[mi][1] = ap[N];
+            zin[mi] = z[mi];
+          }
 #pragma unroll
           for (int tt = 0; tt < 4; ++tt) {
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) {
-              double zz = z[mi];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int level = c0 + ni * 8 + 2 * tt + e;
-                if (level == 0) zz = 0.0;
-                else if (level <= hi) zz = zz * attp[mi][(size_t)(level - 1) * N] + acc[mi][ni][e];
-                if (tq == tt && level <= hi) acc[mi][ni][e] = zz;
-              }
-              z[mi] = __shfl_sync(0xffffffffu, zz, qbase | tt);
+              if (tq == tt) zin[mi] = z[mi];
+              double tv = z[mi] * aa[mi][0] + acc[mi][ni][0];
+              tv = tv * aa[mi][1] + acc[mi][ni][1];
+              z[mi] = __shfl_sync(0xffffffffu, tv, qbase | tt);
             }
+          }
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            const double o0 = zin[mi] * aa[mi][0] + acc[mi][ni][0];
+            acc[mi][ni][0] = o0;
+            acc[mi][ni][1] = o0 * aa[mi][1] + acc[mi][ni][1];
           }
         }
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi) scarry[mi] = edge[mi];
       }
       // --- new field, straight from the accumulator layout ---
+      const int ncol = min(SOS_CH, L - c0);
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
         if (!rvalid[mi]) continue;
-        const int row = r0 + wr * 16 + mi * 8 + gq;
+        double *dst = xnext + SOS_XIDX(KP, r0 + wr * 16 + mi * 8 + gq, c0 + 2 * tq);
+        if (ncol == SOS_CH) {
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) {
-          const int level = c0 + ni * 8 + 2 * tq;
-          double *dst = xnext + SOS_XIDX(KP, row, level);
-          if (level + 1 < L) *reinterpret_cast<double2 *>(dst) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-          else if (level < L) dst[0] = acc[mi][ni][0];
+          for (int ni = 0; ni < 8; ++ni) *reinterpret_cast<double2 *>(dst + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        } else {
+#pragma unroll
+          for (int ni = 0; ni < 8; ++ni) {
+            const int col = ni * 8 + 2 * tq;
+            if (col + 1 < ncol) *reinterpret_cast<double2 *>(dst + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            else if (col < ncol) dst[ni * 8] = acc[mi][ni][0];
+          }
         }
       }
     }
@@ -960,13 +985,13 @@ extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const
   if (order1) {
     k_step<0, 1><<<grid, block, step_smem_bytes(nw, 0, 1, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, att_cap, jdump, dbg);
     launches = 1;
-  } else if (dbg & 128) {                                        // experimental (round 2): register-resident epilogue, see DESIGN.md 7
+  } else if ((dbg & 128) && !jdump && att_cap > 0) {                                        // experimental (round 2): register-resident epilogue, see DESIGN.md 7
     if (mode & 1) {
-      k_step2<0><<<grid, block, step2_smem_bytes(nw, 0, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, att_cap, jdump);
+      k_step2<0><<<grid, block, step2_smem_bytes(nw, 0, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, att_cap);
       ++launches;
     }
     if (mode & 2) {
-      k_step2<1><<<grid, block, step2_smem_bytes(nw, 1, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 1, att_cap, jdump);
+      k_step2<1><<<grid, block, step2_smem_bytes(nw, 1, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 1, att_cap);
       ++launches;
     }
   } else {
