@@ -346,13 +346,15 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     size_t *o = &t_off[i * 7];
     o[0] = ar.putv(h.h); o[1] = ar.putv(h.xdel); o[2] = ar.putv(h.ydel); o[3] = ar.putv(h.dt);
     o[4] = ar.putv(h.inv); o[5] = ar.putv(h.ch); o[6] = ar.putv(h.cf);
-    att_off[i] = att_total; att_total += (((size_t)(h.nt + 2) * b->ho[h.optics].N + 1) & ~(size_t)1);   // 16-byte aligned, 2 pad rows
+    // 16-byte aligned; rows >= nt up to the end of the last 64-level chunk (+2) stay zero: k_step2 reads them as a = 0
+    att_off[i] = att_total; att_total += (((size_t)(roundup(h.nt + 1, SOS_CH) + 2) * b->ho[h.optics].N + 1) & ~(size_t)1);
     i4_off[i] = i4_total; i4_total += (size_t)12 * b->ho[h.optics].N;
   }
   b->i4_total = i4_total;
   CK(sos_dmalloc(ctx, &b->d_arena, ar.buf.size()));
   CK(cudaMemcpyAsync(b->d_arena, ar.buf.data(), ar.buf.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(sos_dmalloc(ctx, &b->d_att, att_total * sizeof(double)));
+  CK(cudaMemsetAsync(b->d_att, 0, att_total * sizeof(double), ctx->stream));
   CK(sos_dmalloc(ctx, &b->d_i4, i4_total * sizeof(double)));
   for (int i = 0; i < noptics; ++i) {
     HostOptics &h = b->ho[i];

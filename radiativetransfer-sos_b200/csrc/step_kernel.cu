@@ -547,7 +547,9 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
 //   * no CTA barrier per chunk (LR: one, for the 4 x 64 Rayleigh functionals): warps drift apart, so one warp's
 //     epilogue runs under the other warps' DMMAs of the next chunk.
 // Per-chunk layer tables are single-buffered behind a full/free mbarrier pair.
-template <int LR>
+// STG: pipeline stages; ATTS: attenuation table of the chunk staged in shared memory (else read from global memory,
+// whose pad rows >= NT are zero)
+template <int LR, int STG, int ATTS>
 __global__ void __launch_bounds__(256, 2)
 k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, const OpticsDev *__restrict__ optics,
         const KsetDev *__restrict__ ksets, const int *__restrict__ list, int tiles_per_dir, int want_lr, int att_cap)
@@ -557,13 +559,13 @@ k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
   const int nw_launch = nthr >> 5;
   const int rows_max = nw_launch * 16;
   const int stage_bytes = STAGE_A_BYTES(rows_max) + (LR ? STAGE_V_BYTES : 0) + STAGE_B_BYTES;
-  double *sT = reinterpret_cast<double *>(smem_raw + SOS_STAGES * stage_bytes);   // [2][4][64] Rayleigh functionals (double-buffered)
+  double *sT = reinterpret_cast<double *>(smem_raw + STG * stage_bytes);   // [2][4][64] Rayleigh functionals (double-buffered)
   double *sG = sT + 2 * 4 * SOS_CH;                                     // [3N] ground values of the downward field
   unsigned long long *full = reinterpret_cast<unsigned long long *>(sG + 3 * 80);
-  unsigned long long *empty = full + SOS_STAGES;
-  unsigned long long *tabfull = empty + SOS_STAGES;                     // layer tables of the chunk have landed
+  unsigned long long *empty = full + STG;
+  unsigned long long *tabfull = empty + STG;                     // layer tables of the chunk have landed
   unsigned long long *tabfree = tabfull + 1;                            // every warp is done with the chunk's tables
-  double *sDt = reinterpret_cast<double *>(full + 2 * SOS_STAGES + 2);  // [<=66] layer optical thickness of the chunk
+  double *sDt = reinterpret_cast<double *>(full + 2 * STG + 2);  // [<=66] layer optical thickness of the chunk
   double *sInv = sDt + 72;
   double *sXd = sInv + 72;
   double *sYd = sXd + 72;
@@ -595,7 +597,7 @@ k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
   double *__restrict__ xnext = it.x[(it.n + 1) & 1];
 
   if (tid == 0) {
-    for (int s = 0; s < SOS_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, nw_launch); }
+    for (int s = 0; s < STG; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, nw_launch); }
     mbar_init(tabfull, 1);
     mbar_init(tabfree, nw_launch);
     fence_proxy_async();
@@ -650,14 +652,14 @@ k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
   const int n_iter = n_chunk * n_slab;                           // linear (chunk, slab) sequence of the pipeline
   const double *__restrict__ Ag = ks.apackA + (size_t)r0 * SOS_KB;
   const double *__restrict__ Vg = LR ? ks.vpack + (size_t)dir * 8 * KP : nullptr;
-  const bool att_staged = (att_cap >= 66 * N);
+  const bool att_staged = ATTS != 0;
   const unsigned tx = (unsigned)(R * SOS_KB * 8 + (LR ? STAGE_V_BYTES : 0) + STAGE_B_BYTES);
 
   auto issue = [&](int qi) {                                     // thread 0 only: loads of linear iteration qi
     const int ch = qi / n_slab, slab = qi - ch * n_slab;
     const int c0i = (up ? (n_chunk - 1 - ch) : ch) * SOS_CH;
-    unsigned char *sp = smem_raw + (qi % SOS_STAGES) * stage_bytes;
-    unsigned long long *bar = full + (qi % SOS_STAGES);
+    unsigned char *sp = smem_raw + (qi % STG) * stage_bytes;
+    unsigned long long *bar = full + (qi % STG);
     mbar_expect_tx(bar, tx);
     bulk_g2s(sp, Ag + (size_t)slab * KP * SOS_KB, (unsigned)(R * SOS_KB * 8), bar);
     sp += STAGE_A_BYTES(rows_max);
@@ -680,7 +682,7 @@ k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
   };
   if (tid == 0) {
     issue_tables(0);
-    for (int s = 0; s < SOS_STAGES - 1 && s < n_iter; ++s) issue(s);
+    for (int s = 0; s < STG - 1 && s < n_iter; ++s) issue(s);
   }
 
   // rows of this thread in the accumulator layout: local row wr*16 + mi*8 + gq
@@ -718,18 +720,18 @@ k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
 
     for (int slab = 0; slab < n_slab; ++slab) {
       const int qi = chunk * n_slab + slab;
-      const int stage = qi % SOS_STAGES;
+      const int stage = qi % STG;
       if (tid == 0) {
-        if (qi + SOS_STAGES - 1 < n_iter) {
-          if (qi >= 1) mbar_wait(empty + (qi - 1) % SOS_STAGES, ((qi - 1) / SOS_STAGES) & 1);
-          issue(qi + SOS_STAGES - 1);
+        if (qi + STG - 1 < n_iter) {
+          if (qi >= 1) mbar_wait(empty + (qi - 1) % STG, ((qi - 1) / STG) & 1);
+          issue(qi + STG - 1);
         }
         if (chunk >= 1 && slab == (n_slab >> 1)) {                 // tables of this chunk, once everybody left the previous one
           mbar_wait(tabfree, (chunk - 1) & 1);
           issue_tables(chunk);
         }
       }
-      mbar_wait(full + stage, (qi / SOS_STAGES) & 1);
+      mbar_wait(full + stage, (qi / STG) & 1);
       if (own || LR) {
         const unsigned char *sp = smem_raw + stage * stage_bytes;
         const double *a = reinterpret_cast<const double *>(sp) + (wr * 16 + gq) * SOS_KB;
@@ -774,7 +776,7 @@ k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
       for (int c = cN + 1 + tid; c < SOS_CH; c += nthr) { sXd[c] = 0.0; sYd[c] = 0.0; }
       const int rs = NT - lb_al;
       for (int r = rs + tid; r < 72; r += nthr) { sDt[r] = 0.0; sInv[r] = 0.0; }
-      for (int idx = rs * N + tid; idx < 66 * N; idx += nthr) sAtt[idx] = 0.0;
+      if (ATTS) for (int idx = rs * N + tid; idx < 66 * N; idx += nthr) sAtt[idx] = 0.0;
     }
     if (LR || (up && chunk == 0)) __syncthreads();               // sT of this chunk / blanked tables visible (CTA-uniform)
     if (own) {
@@ -799,7 +801,8 @@ k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
       if (up) {
         // table row of column col is col + off; this thread's columns are ni*8 + 2*tq + e
         const double *dp = sDt + off + 2 * tq, *ip = sInv + off + 2 * tq;
-        const double *ap0 = sAtt + (kidx[0] - 1) + (off + 2 * tq) * N, *ap1 = sAtt + (kidx[1] - 1) + (off + 2 * tq) * N;
+        const double *abase = ATTS ? (sAtt + (off + 2 * tq) * N) : (tm.att + (size_t)(c0 + 2 * tq) * N);
+        const double *ap0 = abase + (kidx[0] - 1), *ap1 = abase + (kidx[1] - 1);
         // --- layer constants c(i) = (1-a)(A mu + S(i)) - A a dtau, A = (S(i+1) - S(i)) / dtau  (SOS_OS.F:2279-2310) ---
         double edge[2];
 #pragma unroll
@@ -862,7 +865,8 @@ k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
         // constant is replaced by 0 below)
         const int rb = off + 2 * tq - 1;
         const double *dp = sDt + rb, *ip = sInv + rb;
-        const double *ap0 = sAtt + (kidx[0] - 1) + rb * N, *ap1 = sAtt + (kidx[1] - 1) + rb * N;
+        const double *abase = ATTS ? (sAtt + rb * N) : (tm.att + (ptrdiff_t)(c0 + 2 * tq - 1) * N);
+        const double *ap0 = abase + (kidx[0] - 1), *ap1 = abase + (kidx[1] - 1);
         const int fix0 = (rb < 0) ? 1 : 0;                        // only (c0 = 0, tq = 0): first element uses row 0
         double edge[2];
 #pragma unroll
@@ -951,11 +955,11 @@ static size_t step_smem_bytes(int nw, int lr, int order1, int att_cap)
   return (pipe > sj ? pipe : sj) + (4 * SOS_CH + 3 * 80) * 8 + (2 * SOS_STAGES + 2) * 8 + (6 * 72 + 128 + 4 * 128 + att_cap) * 8 + 128;
 }
 
-static size_t step2_smem_bytes(int nw, int lr, int att_cap)
+static size_t step2_smem_bytes(int nw, int lr, int att_cap, int stages)
 {
   const size_t rows = (size_t)nw * 16;
   const size_t stage = STAGE_A_BYTES(rows) + (lr ? STAGE_V_BYTES : 0) + STAGE_B_BYTES;
-  return SOS_STAGES * stage + (2 * 4 * SOS_CH + 3 * 80) * 8 + (2 * SOS_STAGES + 2) * 8 + (4 * 72 + 128 + 128 + att_cap) * 8 + 128;
+  return stages * stage + (2 * 4 * SOS_CH + 3 * 80) * 8 + (2 * SOS_STAGES + 2) * 8 + (4 * 72 + 128 + 128 + att_cap) * 8 + 128;
 }
 
 extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const OpticsDev *optics,
@@ -969,8 +973,10 @@ extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const
     cudaFuncSetAttribute(k_step<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_step<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_step<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_step2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_step2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_step2<0, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_step2<1, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_step2<0, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_step2<1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     attr_done = true;
   }
   const int groups = maxHB / 16;
@@ -985,13 +991,19 @@ extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const
   if (order1) {
     k_step<0, 1><<<grid, block, step_smem_bytes(nw, 0, 1, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, att_cap, jdump, dbg);
     launches = 1;
-  } else if ((dbg & 128) && !jdump && att_cap > 0) {                                        // experimental (round 2): register-resident epilogue, see DESIGN.md 7
-    if (mode & 1) {
-      k_step2<0><<<grid, block, step2_smem_bytes(nw, 0, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, att_cap);
-      ++launches;
-    }
-    if (mode & 2) {
-      k_step2<1><<<grid, block, step2_smem_bytes(nw, 1, att_cap), st>>>(items, terms, optics, ksets, list, tiles_per_dir, 1, att_cap);
+  } else if ((dbg & 128) && !jdump && att_cap > 0) {             // experimental: register-resident epilogue, see DESIGN.md 7
+    const bool deep = (dbg & 256) != 0;                          // 4 stages, attenuation table read from global memory
+    for (int lr = 0; lr < 2; ++lr) {
+      if (!(mode & (1 << lr))) continue;
+      if (deep) {
+        const size_t sm = step2_smem_bytes(nw, lr, 0, 4);
+        if (lr) k_step2<1, 4, 0><<<grid, block, sm, st>>>(items, terms, optics, ksets, list, tiles_per_dir, 1, 0);
+        else k_step2<0, 4, 0><<<grid, block, sm, st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, 0);
+      } else {
+        const size_t sm = step2_smem_bytes(nw, lr, att_cap, 3);
+        if (lr) k_step2<1, 3, 1><<<grid, block, sm, st>>>(items, terms, optics, ksets, list, tiles_per_dir, 1, att_cap);
+        else k_step2<0, 3, 1><<<grid, block, sm, st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, att_cap);
+      }
       ++launches;
     }
   } else {
