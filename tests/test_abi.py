@@ -49,3 +49,31 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "liboracle" not in txt and "sos_oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_ctypes_structs_match_header(tmp_path):
+    """The ctypes mirrors in api.py must have the layout a C compiler gives include/sosgpu.h (sizes and offsets)."""
+    import subprocess
+    api = importlib.import_module("radiativetransfer-sos_b200.api")
+    pairs = {"sosgpu_optics": api.COptics, "sosgpu_term": api.CTerm, "sosgpu_term_out": api.CTermOut,
+             "sosgpu_group_out": api.CGroupOut, "sosgpu_stats": api.CStats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sosgpu.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {}
+    for ln in out:
+        if ln.strip():
+            a, b, c = ln.split()
+            got[(a, b)] = int(c)
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
