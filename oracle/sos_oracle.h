@@ -9,8 +9,9 @@
  * PARITY UNPINNED: the reference is Fortran 77 and no Fortran compiler exists in
  * this image (nor on the GPU box), and the reference ships no golden vectors for
  * this path.  The oracle is therefore validated only by
- * (a) a second, independently written numpy formulation (tests/test_oracle_*.py),
- * (b) physics invariants (flux conservation, reciprocity, Rayleigh limits).
+ * (a) a second, independently written numpy formulation of the order-n source (tests/test_oracle.py),
+ * (b) physics: flux conservation, reflection reciprocity per Fourier order, closed-form first-order scattering
+ *     (scalar and polarized Rayleigh), and a scalar adding-doubling solver for the full multiple-scattering field.
  *
  * Array conventions mirror the reference's Fortran arrays with the *useful*
  * extents instead of the compile-time caps of inc/SOS.h:
