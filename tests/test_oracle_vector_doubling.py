@@ -1,0 +1,93 @@
+"""Independent pin of the POLARIZED multiple-scattering field: a vector (I, Q, U) adding-doubling solver built from
+first principles against the oracle's successive orders.
+
+Nothing here comes from the reference: the Rayleigh phase matrix is formed from the dipole amplitude matrix
+e_a(n) . e_b(n') in the meridian-plane bases (no rotation-angle formulas, no generalized spherical functions), Fourier
+transformed numerically in azimuth, and the layer is built by doubling with all four operators (R, T, R*, T*) carried
+explicitly, so no symmetry relation is assumed.  The oracle side runs SOS_OS in full (12 scattering orders, geometric tail,
+stop tests) with the l = 2 polarization kernels of SOS_NOYAUX and the sign table of SOS_FSOURCE_ORDREIG.
+Conventions that may legitimately differ are global signs of Q and U; U comes out with the opposite sign, I and Q equal."""
+import numpy as np
+import pytest
+
+
+def mueller_rayleigh(ct, phi, ctp, delta):
+    """3x3 (I,Q,U) phase matrix for scattering from (theta', phi'=0) into (theta, phi); Stokes referred to the meridian
+    planes with axes (theta_hat, phi_hat); delta = (1-rho_n)/(1+rho_n/2) weights the dipole part."""
+    st, stp = np.sqrt(1 - ct * ct), np.sqrt(1 - ctp * ctp)
+    th = np.array([ct * np.cos(phi), ct * np.sin(phi), -st])
+    ph = np.array([-np.sin(phi), np.cos(phi), 0.0])
+    thp = np.array([ctp, 0.0, -stp])
+    php = np.array([0.0, 1.0, 0.0])
+    a, b, c, d = th @ thp, th @ php, ph @ thp, ph @ php
+    m = np.array([[(a * a + b * b + c * c + d * d) / 2, (a * a - b * b + c * c - d * d) / 2, a * b + c * d],
+                  [(a * a + b * b - c * c - d * d) / 2, (a * a - b * b - c * c + d * d) / 2, a * b - c * d],
+                  [a * c + b * d, a * c - b * d, a * d + b * c]])
+    z = 1.5 * delta * m
+    z[0, 0] += 1 - delta
+    return z
+
+
+def mode_kernel(m, mu, sgn_out, sgn_in, delta, nphi=64):
+    """Kernel of Fourier mode m acting on (I_cos, Q_cos, U_sin), ordered [stokes][node]."""
+    n = len(mu)
+    k = np.zeros((3, n, 3, n))
+    phis = 2 * np.pi * np.arange(nphi) / nphi
+    for i in range(n):
+        for j in range(n):
+            zc, zs = np.zeros((3, 3)), np.zeros((3, 3))
+            for p in phis:
+                z = mueller_rayleigh(sgn_out * mu[i], p, sgn_in * mu[j], delta)
+                zc += z * np.cos(m * p)
+                zs += z * np.sin(m * p)
+            zc /= nphi
+            zs /= nphi
+            k[:, i, :, j] = [[zc[0, 0], zc[0, 1], -zs[0, 2]], [zc[1, 0], zc[1, 1], -zs[1, 2]], [zs[2, 0], zs[2, 1], zc[2, 2]]]
+    return k.reshape(3 * n, 3 * n)
+
+
+def vector_doubling(m, mu, w, tau, delta, nd=20):
+    n = len(mu)
+    d = tau / 2 ** nd
+    mu3, w3 = np.tile(mu, 3), np.tile(w, 3)
+    c = np.diag(2 * mu3 * w3)
+    scale = lambda k: (d / 4 * k / np.outer(mu3, mu3)) @ c
+    direct = np.diag(1 - d / mu3)
+    # polar axis pointing down: downward travel cos(theta) = +mu, upward = -mu
+    r, t = scale(mode_kernel(m, mu, -1, +1, delta)), scale(mode_kernel(m, mu, +1, +1, delta)) + direct
+    rs, ts = scale(mode_kernel(m, mu, +1, -1, delta)), scale(mode_kernel(m, mu, -1, -1, delta)) + direct
+    eye = np.eye(3 * n)
+    for _ in range(nd):
+        g1, g2 = np.linalg.inv(eye - r @ rs), np.linalg.inv(eye - rs @ r)
+        r, t, rs, ts = r + ts @ g1 @ r @ t, t @ g2 @ t, rs + t @ g2 @ rs @ ts, ts @ g1 @ ts
+    return r, t
+
+
+@pytest.mark.parametrize("ron", [0.0, 0.0279])
+def test_polarized_rayleigh_against_vector_doubling(pkg, orc, ron):
+    syn = pkg.synth
+    ng = 8
+    xg, wg = np.polynomial.legendre.leggauss(2 * ng)
+    mu, w = xg[ng:][::-1].copy(), wg[ng:][::-1].copy()
+    N = ng
+    rmu = np.concatenate([-mu[::-1], [0.0], mu])
+    ga = np.concatenate([w[::-1], [0.0], w])
+    o = syn.make_optics(nb_gauss=8, tetas=40.0, os_nb=16, a_trunc=0.0, piztr=1.0, ipolar=1)
+    NT, tau, j0 = 150, 0.5, 3
+    h, z = np.linspace(0, tau, NT + 1), np.linspace(100, 0, NT + 1)
+    r = orc.sos_os(N, rmu.copy(), ga, o.os_nb, NT, j0, 0.0, 0.0, 0, 0, 1.34, h, np.zeros(NT + 1), np.ones(NT + 1), z, ron,
+                   o.alpha.copy(), o.beta, o.gamma.copy(), o.zeta.copy(), -1.0, 100, 2, 1)
+    assert r.ier == 0 and r.n_fourier == 3 and r.n_scatter[0] >= 10
+    delta = (1 - ron) / (1 + ron / 2)
+    scale = np.abs(r.rec[0][2]).max()
+    e = np.zeros(3 * N)
+    e[j0 - 1] = 1 / (2 * w[j0 - 1])                        # unpolarized unit solar beam at node j0
+    for m in (0, 1, 2):
+        rr, tt = vector_doubling(m, mu, w, tau, delta)
+        up = (rr @ e).reshape(3, N)
+        dn = ((tt - np.diag(np.exp(-tau / np.tile(mu, 3)))) @ e).reshape(3, N)
+        rec_q, rec_u, rec_i = r.rec[m][0], r.rec[m][1], r.rec[m][2]
+        for got, ref in ((rec_i[N + 1:], up[0]), (rec_q[N + 1:], up[1]), (rec_u[N + 1:], -up[2]),
+                         (rec_i[:N][::-1], dn[0]), (rec_q[:N][::-1], dn[1]), (rec_u[:N][::-1], -dn[2])):
+            assert np.abs(got - ref).max() <= 3e-5 * scale, (m, np.abs(got - ref).max() / scale)
+        assert np.abs(up[1]).max() > 1e-3 * scale                  # the polarized components are not trivially small
