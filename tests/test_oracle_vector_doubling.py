@@ -91,3 +91,112 @@ def test_polarized_rayleigh_against_vector_doubling(pkg, orc, ron):
                          (rec_i[:N][::-1], dn[0]), (rec_q[:N][::-1], dn[1]), (rec_u[:N][::-1], -dn[2])):
             assert np.abs(got - ref).max() <= 3e-5 * scale, (m, np.abs(got - ref).max() / scale)
         assert np.abs(up[1]).max() > 1e-3 * scale                  # the polarized components are not trivially small
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# General scattering matrices (aerosols): F(Theta) from the expansion coefficients in the reference's convention,
+#   F11 = sum beta_l P_l,  F12 = sum gamma_l sqrt((l-2)!/(l+2)!) P_l^2,
+#   F22 +- F33 = sum (alpha_l +- zeta_l) d^l_{2,+-2}   (Wigner d through Jacobi polynomials),
+# rotated into the meridian frames with explicit basis vectors.  The construction is calibrated on Rayleigh, where it
+# must (and does, to 1e-15) reproduce the dipole phase matrix above.
+def _mueller_of_jones(a, b, c, d):
+    return np.array([[(a * a + b * b + c * c + d * d) / 2, (a * a - b * b + c * c - d * d) / 2, a * b + c * d],
+                     [(a * a + b * b - c * c - d * d) / 2, (a * a - b * b - c * c + d * d) / 2, a * b - c * d],
+                     [a * c + b * d, a * c - b * d, a * d + b * c]])
+
+
+def scattering_matrix(x, al, be, ga, ze):
+    from scipy.special import lpmv, gammaln, eval_jacobi, eval_legendre
+    f11 = f12 = fp = fm = 0.0
+    for l in range(len(be)):
+        f11 += be[l] * eval_legendre(l, x)
+        if l >= 2:
+            f12 += ga[l] * np.exp(0.5 * (gammaln(l - 1) - gammaln(l + 3))) * lpmv(2, l, x)
+            fp += (al[l] + ze[l]) / 2 * ((1 + x) / 2) ** 2 * eval_jacobi(l - 2, 0, 4, x)
+            fm += (al[l] - ze[l]) / 2 * ((1 - x) / 2) ** 2 * eval_jacobi(l - 2, 4, 0, x)
+    return np.array([[f11, f12, 0.0], [f12, fp + fm, 0.0], [0.0, 0.0, fp - fm]])
+
+
+def phase_matrix(ct, phi, ctp, fmat):
+    st, stp = np.sqrt(1 - ct * ct), np.sqrt(1 - ctp * ctp)
+    n = np.array([st * np.cos(phi), st * np.sin(phi), ct])
+    npr = np.array([stp, 0.0, ctp])
+    th = np.array([ct * np.cos(phi), ct * np.sin(phi), -st])
+    ph = np.array([-np.sin(phi), np.cos(phi), 0.0])
+    thp, php = np.array([ctp, 0.0, -stp]), np.array([0.0, 1.0, 0.0])
+    perp = np.cross(npr, n)
+    nrm = np.linalg.norm(perp)
+    perp = php.copy() if nrm < 1e-12 else perp / nrm          # forward / backward: the meridian plane of n' serves
+    parp, par = np.cross(perp, npr), np.cross(perp, n)
+    j1 = _mueller_of_jones(parp @ thp, parp @ php, perp @ thp, perp @ php)     # (theta', phi') -> scattering plane
+    j2 = _mueller_of_jones(th @ par, th @ perp, ph @ par, ph @ perp)           # scattering plane -> (theta, phi)
+    return j2 @ fmat(float(np.clip(n @ npr, -1.0, 1.0))) @ j1
+
+
+def test_general_phase_matrix_calibrated_on_rayleigh():
+    d = 0.9
+    al, be, ga, ze = np.array([0, 0, 3 * d]), np.array([1, 0, d / 2]), np.array([0, 0, -np.sqrt(1.5) * d]), np.zeros(3)
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        ct, ctp = rng.uniform(-1, 1, 2)
+        phi = rng.uniform(0, 2 * np.pi)
+        z = phase_matrix(ct, phi, ctp, lambda x: scattering_matrix(x, al, be, ga, ze))
+        assert np.abs(z - mueller_rayleigh(ct, phi, ctp, d)).max() < 1e-13
+
+
+def test_polarized_aerosol_layer_against_vector_doubling(pkg, orc):
+    """All six kernels of SOS_NOYAUX for l up to OS_NB, the alpha/zeta convention and the sign table of the source
+    function, in multiple scattering: aerosol layer (tau 0.4, w0 0.9, Q up to 11 % of I) against the vector doubling."""
+    from scipy.interpolate import CubicSpline
+    syn = pkg.synth
+    ng = 8
+    xg, wg = np.polynomial.legendre.leggauss(2 * ng)
+    mu, w = xg[ng:][::-1].copy(), wg[ng:][::-1].copy()
+    N = ng
+    rmu = np.concatenate([-mu[::-1], [0.0], mu])
+    gaw = np.concatenate([w[::-1], [0.0], w])
+    o = syn.make_optics(nb_gauss=8, tetas=40.0, os_nb=12, a_trunc=0.0, piztr=1.0, ipolar=1, g_modes=((0.6, 1.0),))
+    NT, tau, j0, w0 = 150, 0.4, 3, 0.9
+    h, z = np.linspace(0, tau, NT + 1), np.linspace(100, 0, NT + 1)
+    r = orc.sos_os(N, rmu.copy(), gaw, o.os_nb, NT, j0, 0.0, 0.0, 0, 0, 1.34, h, np.full(NT + 1, w0), np.zeros(NT + 1), z,
+                   0.0, o.alpha.copy(), o.beta, o.gamma.copy(), o.zeta.copy(), -1.0, 100, o.os_nb, 1)
+    assert r.ier == 0 and r.n_fourier > 4 and r.n_scatter[0] >= 8
+    xs = np.linspace(-1, 1, 2001)
+    spl = CubicSpline(xs, np.array([scattering_matrix(x, o.alpha, o.beta, o.gamma, o.zeta) for x in xs]).reshape(len(xs), 9))
+    fmat = lambda x: spl(x).reshape(3, 3)
+    modes, nphi = (0, 1, 2), 32
+    phis = 2 * np.pi * np.arange(nphi) / nphi
+    kern = {}
+    for so, si in ((-1, 1), (1, 1), (1, -1), (-1, -1)):
+        ks = {m: np.zeros((3, N, 3, N)) for m in modes}
+        for i in range(N):
+            for j in range(N):
+                zz = np.array([phase_matrix(so * mu[i], p, si * mu[j], fmat) for p in phis])
+                for m in modes:
+                    zc = (zz * np.cos(m * phis)[:, None, None]).mean(0)
+                    zs = (zz * np.sin(m * phis)[:, None, None]).mean(0)
+                    ks[m][:, i, :, j] = [[zc[0, 0], zc[0, 1], -zs[0, 2]], [zc[1, 0], zc[1, 1], -zs[1, 2]],
+                                         [zs[2, 0], zs[2, 1], zc[2, 2]]]
+        kern[(so, si)] = {m: ks[m].reshape(3 * N, 3 * N) for m in modes}
+    mu3, w3 = np.tile(mu, 3), np.tile(w, 3)
+    c = np.diag(2 * mu3 * w3)
+    nd = 20
+    d = tau / 2 ** nd
+    sc = lambda k: (w0 * d / 4 * k / np.outer(mu3, mu3)) @ c
+    scale = np.abs(r.rec[0][2]).max()
+    e = np.zeros(3 * N)
+    e[j0 - 1] = 1 / (2 * w[j0 - 1])
+    for m in modes:
+        rr, tt = sc(kern[(-1, 1)][m]), sc(kern[(1, 1)][m]) + np.diag(1 - d / mu3)
+        rs, ts = sc(kern[(1, -1)][m]), sc(kern[(-1, -1)][m]) + np.diag(1 - d / mu3)
+        eye = np.eye(3 * N)
+        for _ in range(nd):
+            g1, g2 = np.linalg.inv(eye - rr @ rs), np.linalg.inv(eye - rs @ rr)
+            rr, tt, rs, ts = rr + ts @ g1 @ rr @ tt, tt @ g2 @ tt, rs + tt @ g2 @ rs @ ts, ts @ g1 @ ts
+        up = (rr @ e).reshape(3, N)
+        dn = ((tt - np.diag(np.exp(-tau / mu3))) @ e).reshape(3, N)
+        rec_q, rec_u, rec_i = r.rec[m][0], r.rec[m][1], r.rec[m][2]
+        for got, ref in ((rec_i[N + 1:], up[0]), (rec_q[N + 1:], up[1]), (rec_u[N + 1:], -up[2]),
+                         (rec_i[:N][::-1], dn[0]), (rec_q[:N][::-1], dn[1]), (rec_u[:N][::-1], -dn[2])):
+            assert np.abs(got - ref).max() <= 3e-5 * scale, (m, np.abs(got - ref).max() / scale)
+    assert np.abs(r.rec[0][0]).max() > 0.05 * scale               # strongly polarized case
