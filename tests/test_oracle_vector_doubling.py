@@ -200,3 +200,44 @@ def test_polarized_aerosol_layer_against_vector_doubling(pkg, orc):
                          (rec_i[:N][::-1], dn[0]), (rec_q[:N][::-1], dn[1]), (rec_u[:N][::-1], -dn[2])):
             assert np.abs(got - ref).max() <= 3e-5 * scale, (m, np.abs(got - ref).max() / scale)
     assert np.abs(r.rec[0][0]).max() > 0.05 * scale               # strongly polarized case
+
+
+def test_polarized_rayleigh_over_lambert_ground(pkg, orc):
+    """Vector doubling with a depolarizing Lambertian ground (albedo 0.3, I -> I only, isotropic) coupled in closed form:
+    pins the Lambert boundary values (SOS_OS.F:978-980, 1177-1190) in the polarized scattering loop."""
+    syn = pkg.synth
+    ng = 8
+    xg, wg = np.polynomial.legendre.leggauss(2 * ng)
+    mu, w = xg[ng:][::-1].copy(), wg[ng:][::-1].copy()
+    N = ng
+    rmu = np.concatenate([-mu[::-1], [0.0], mu])
+    ga = np.concatenate([w[::-1], [0.0], w])
+    o = syn.make_optics(nb_gauss=8, tetas=40.0, os_nb=16, a_trunc=0.0, piztr=1.0, ipolar=1)
+    NT, tau, j0, rho = 150, 0.5, 3, 0.3
+    h, z = np.linspace(0, tau, NT + 1), np.linspace(100, 0, NT + 1)
+    r = orc.sos_os(N, rmu.copy(), ga, o.os_nb, NT, j0, 0.0, rho, 0, 0, 1.34, h, np.zeros(NT + 1), np.ones(NT + 1), z, 0.0,
+                   o.alpha.copy(), o.beta, o.gamma.copy(), o.zeta.copy(), -1.0, 100, 2, 1)
+    mu3 = np.tile(mu, 3)
+    n3 = 3 * N
+    # all four operators of the layer (illumination from above and from below)
+    d = tau / 2 ** 20
+    c = np.diag(2 * mu3 * np.tile(w, 3))
+    sc = lambda k: (d / 4 * k / np.outer(mu3, mu3)) @ c
+    direct = np.diag(1 - d / mu3)
+    rr, tt = sc(mode_kernel(0, mu, -1, +1, 1.0)), sc(mode_kernel(0, mu, +1, +1, 1.0)) + direct
+    rs, ts = sc(mode_kernel(0, mu, +1, -1, 1.0)), sc(mode_kernel(0, mu, -1, -1, 1.0)) + direct
+    eye = np.eye(n3)
+    for _ in range(20):
+        g1, g2 = np.linalg.inv(eye - rr @ rs), np.linalg.inv(eye - rs @ rr)
+        rr, tt, rs, ts = rr + ts @ g1 @ rr @ tt, tt @ g2 @ tt, rs + tt @ g2 @ rs @ ts, ts @ g1 @ ts
+    lop = np.zeros((n3, n3))
+    lop[:N, :N] = np.tile(2 * rho * mu * w, (N, 1))          # upward I (all nodes) from the downward flux; Q, U -> 0
+    e = np.zeros(n3)
+    e[j0 - 1] = 1 / (2 * w[j0 - 1])
+    dn = np.linalg.solve(eye - rs @ lop, tt @ e)
+    up = (rr @ e + ts @ (lop @ dn)).reshape(3, N)
+    dnd = (dn - np.exp(-tau / mu3) * e).reshape(3, N)
+    scale = np.abs(r.rec[0][2]).max()
+    for got, ref in ((r.rec[0][2][N + 1:], up[0]), (r.rec[0][0][N + 1:], up[1]),
+                     (r.rec[0][2][:N][::-1], dnd[0]), (r.rec[0][0][:N][::-1], dnd[1])):
+        assert np.abs(got - ref).max() <= 3e-5 * scale, np.abs(got - ref).max() / scale
