@@ -241,3 +241,55 @@ def test_polarized_rayleigh_over_lambert_ground(pkg, orc):
     for got, ref in ((r.rec[0][2][N + 1:], up[0]), (r.rec[0][0][N + 1:], up[1]),
                      (r.rec[0][2][:N][::-1], dnd[0]), (r.rec[0][0][:N][::-1], dnd[1])):
         assert np.abs(got - ref).max() <= 3e-5 * scale, np.abs(got - ref).max() / scale
+
+
+def test_polarized_rayleigh_over_flat_fresnel_sea(pkg, orc):
+    """Vector doubling with a flat dielectric interface (n = 1.34): specular reflection with the Fresnel amplitude
+    coefficients r_p, r_s in the meridian bases (Jones diag(r_p, r_s) -> Mueller), the specularly reflected direct beam
+    removed from the diffuse field as the reference does.  Pins SOS_MAT_FRESNEL_PLAN_REFL, the Fresnel boundary values
+    (SOS_OS.F:1225-1239) and SOS_FSOURCE_DIFF_FRESNEL1 for Fourier orders 0-2, I, Q and U."""
+    syn = pkg.synth
+    ng = 8
+    xg, wg = np.polynomial.legendre.leggauss(2 * ng)
+    mu, w = xg[ng:][::-1].copy(), wg[ng:][::-1].copy()
+    N = ng
+    rmu = np.concatenate([-mu[::-1], [0.0], mu])
+    ga = np.concatenate([w[::-1], [0.0], w])
+    o = syn.make_optics(nb_gauss=8, tetas=40.0, os_nb=16, a_trunc=0.0, piztr=1.0, ipolar=1)
+    NT, tau, j0, nref = 150, 0.5, 3, 1.34
+    h, z = np.linspace(0, tau, NT + 1), np.linspace(100, 0, NT + 1)
+    r = orc.sos_os(N, rmu.copy(), ga, o.os_nb, NT, j0, 0.0, 0.0, 0, 1, nref, h, np.zeros(NT + 1), np.ones(NT + 1), z, 0.0,
+                   o.alpha.copy(), o.beta, o.gamma.copy(), o.zeta.copy(), -1.0, 100, 2, 1)
+    assert r.ier == 0 and r.n_fourier == 3
+    mu3 = np.tile(mu, 3)
+    n3 = 3 * N
+    lop = np.zeros((n3, n3))
+    for i in range(N):
+        ci = mu[i]
+        ctr = np.sqrt(1 - (1 - ci * ci) / nref ** 2)
+        m3 = _mueller_of_jones((nref * ci - ctr) / (nref * ci + ctr), 0.0, 0.0, (ci - nref * ctr) / (ci + nref * ctr))
+        for a in range(3):
+            for b in range(3):
+                lop[a * N + i, b * N + i] = m3[a, b]
+    scale = np.abs(r.rec[0][2]).max()
+    e = np.zeros(n3)
+    e[j0 - 1] = 1 / (2 * w[j0 - 1])
+    att = np.diag(np.exp(-tau / mu3))
+    for m in (0, 1, 2):
+        d = tau / 2 ** 20
+        c = np.diag(2 * mu3 * np.tile(w, 3))
+        sc = lambda k: (d / 4 * k / np.outer(mu3, mu3)) @ c
+        direct = np.diag(1 - d / mu3)
+        rr, tt = sc(mode_kernel(m, mu, -1, +1, 1.0)), sc(mode_kernel(m, mu, +1, +1, 1.0)) + direct
+        rs, ts = sc(mode_kernel(m, mu, +1, -1, 1.0)), sc(mode_kernel(m, mu, -1, -1, 1.0)) + direct
+        eye = np.eye(n3)
+        for _ in range(20):
+            g1, g2 = np.linalg.inv(eye - rr @ rs), np.linalg.inv(eye - rs @ rr)
+            rr, tt, rs, ts = rr + ts @ g1 @ rr @ tt, tt @ g2 @ tt, rs + tt @ g2 @ rs @ ts, ts @ g1 @ ts
+        dn = np.linalg.solve(eye - rs @ lop, tt @ e)
+        up = ((rr @ e + ts @ (lop @ dn)) - att @ lop @ att @ e).reshape(3, N)   # minus the specular image of the sun
+        dnd = (dn - att @ e).reshape(3, N)
+        rec_q, rec_u, rec_i = r.rec[m][0], r.rec[m][1], r.rec[m][2]
+        for got, ref in ((rec_i[N + 1:], up[0]), (rec_q[N + 1:], up[1]), (rec_u[N + 1:], -up[2]),
+                         (rec_i[:N][::-1], dnd[0]), (rec_q[:N][::-1], dnd[1]), (rec_u[:N][::-1], -dnd[2])):
+            assert np.abs(got - ref).max() <= 8e-5 * scale, (m, np.abs(got - ref).max() / scale)
