@@ -77,3 +77,35 @@ def test_ctypes_structs_match_header(tmp_path):
         assert got[(cname, "size")] == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_gfortran_shims_refuse_without_gpu(tmp_path):
+    """The F77 drop-in symbols have no CPU path either: without a CUDA device they return IER = -1."""
+    import numpy as np
+    api = importlib.import_module("radiativetransfer-sos_b200.api")
+    lib = api.load_library()
+    lib.sosgpu_device_count.restype = C.c_int
+    if lib.sosgpu_device_count() > 0:
+        pytest.skip("a GPU is present")
+    ip = lambda v: C.byref(C.c_int(v))
+    dp = lambda v: C.byref(C.c_double(v))
+    fstr = lambda s: C.create_string_buffer(s.encode().ljust(500), 500)
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    L500 = C.c_size_t(500)
+    rmu, ga = np.zeros(161), np.zeros(161)
+    rmu[80 + 1:80 + 5] = [0.9, 0.7, 0.5, 0.3]
+    rmu[80 - 4:80] = -rmu[80 + 1:80 + 5][::-1]
+    ier = C.c_int(0)
+    out = str(tmp_path / "GLITTER.bin")
+    lib.sos_glitter_(ip(4), P(rmu), P(ga), dp(2.0), dp(1.34), ip(8), ip(8), ip(16), fstr("a"), fstr("b"), fstr("c"),
+                     fstr(out), ip(0), C.byref(ier), L500, L500, L500, L500)
+    assert ier.value == -1 and not os.path.exists(out)
+    h = np.linspace(0, 0.1, 601)
+    zero = np.zeros(601)
+    co = np.zeros(201)
+    em, ep = C.c_double(0), C.c_double(0)
+    ier = C.c_int(0)
+    lib.sos_os_(ip(4), P(rmu), P(ga), ip(8), ip(10), fstr("none"), fstr(str(tmp_path / "OS.bin")), ip(1), dp(30.0), dp(0.0),
+                ip(0), ip(0), dp(1.34), P(h), P(zero), P(zero + 1), P(zero), dp(0.0279), P(co), P(co), P(co), P(co),
+                dp(-1.0), ip(10), ip(2), ip(1), ip(0), ip(6), C.byref(em), C.byref(ep), C.byref(ier), L500, L500)
+    assert ier.value == -1 and not os.path.exists(str(tmp_path / "OS.bin"))
