@@ -550,7 +550,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
 // STG: pipeline stages; ATTS: attenuation table of the chunk staged in shared memory (else read from global memory,
 // whose pad rows >= NT are zero)
 template <int LR, int STG, int ATTS>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, STG > 4 ? 1 : 2)
 k_step2(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, const OpticsDev *__restrict__ optics,
         const KsetDev *__restrict__ ksets, const int *__restrict__ list, int tiles_per_dir, int want_lr, int att_cap)
 {
@@ -977,6 +977,8 @@ extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const
     cudaFuncSetAttribute(k_step2<1, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_step2<0, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_step2<1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_step2<0, 7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaFuncSetAttribute(k_step2<1, 7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     attr_done = true;
   }
   const int groups = maxHB / 16;
@@ -993,9 +995,20 @@ extern "C" int sos_launch_step(const ItemDev *items, const TermDev *terms, const
     launches = 1;
   } else if ((dbg & 128) && !jdump && att_cap > 0) {             // experimental: register-resident epilogue, see DESIGN.md 7
     const bool deep = (dbg & 256) != 0;                          // 4 stages, attenuation table read from global memory
+    const bool solo = (dbg & 512) != 0;                          // one CTA per SM, 7 stages (untested on hardware: round 2)
     for (int lr = 0; lr < 2; ++lr) {
       if (!(mode & (1 << lr))) continue;
-      if (deep) {
+      if (solo) {
+        // One CTA per SM with the whole shared memory as a deep pipeline (look-ahead 6 k-slabs) and up to 255
+        // registers: tools/dmma_smem_bench shows that 8 warps saturate the DMMA pipe once operands are resident.
+        if (lr) {
+          const size_t sm = step2_smem_bytes(nw, 1, att_cap, 7);
+          k_step2<1, 7, 1><<<grid, block, sm, st>>>(items, terms, optics, ksets, list, tiles_per_dir, 1, att_cap);
+        } else {
+          const size_t sm = step2_smem_bytes(nw, 0, att_cap, 7);
+          k_step2<0, 7, 1><<<grid, block, sm, st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, att_cap);
+        }
+      } else if (deep) {
         const size_t sm = step2_smem_bytes(nw, lr, 0, 4);
         if (lr) k_step2<1, 4, 0><<<grid, block, sm, st>>>(items, terms, optics, ksets, list, tiles_per_dir, 1, 0);
         else k_step2<0, 4, 0><<<grid, block, sm, st>>>(items, terms, optics, ksets, list, tiles_per_dir, 0, 0);
