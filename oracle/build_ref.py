@@ -1,0 +1,54 @@
+#!/usr/bin/env python3
+"""build_ref.py -- TEST INFRASTRUCTURE.  Builds oracle/_ref/libsosref.so from the reference's own Fortran sources
+where they lie under /root/reference (never copied into the repository): oracle/f77_to_c.py translates the hot-path
+source files to C, gcc compiles them with the oracle's flags (-O2 -ffp-contract=off -fno-fast-math: IEEE double/float
+arithmetic, no FMA contraction -- what `gfortran -O` emits on x86-64).  The GPU box has no /root/reference; it uses the
+prebuilt library that travels with the snapshot (oracle/_ref/ is git-ignored, not gpurun-ignored).
+
+usage: python oracle/build_ref.py [--force]      exit code 0 also when the reference tree is absent (nothing to do)
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("SOS_REFERENCE_ROOT", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+FILES = ["SOS_OS.F", "SOS_TRPHI.F", "SOS_GLITTER.F", "SOS_SURFACE.F"]
+
+
+def build(force=False, verbose=True):
+    lib = os.path.join(OUT, "libsosref.so")
+    src_dir, inc = os.path.join(REF, "src"), os.path.join(REF, "inc", "SOS.h")
+    if not os.path.isdir(src_dir):
+        return lib if os.path.exists(lib) else None
+    sys.path.insert(0, HERE)
+    import f77_to_c as t
+    srcs = [os.path.join(src_dir, f) for f in FILES]
+    newest = max(os.path.getmtime(p) for p in srcs + [inc, os.path.join(HERE, "f77_to_c.py"), os.path.abspath(__file__)])
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= newest:
+        return lib
+    os.makedirs(OUT, exist_ok=True)
+    defines = t.read_defines(inc)
+    protos, bodies, report = [], [], []
+    for p in srcs:
+        c, pr, rep = t.translate_file(p, defines)
+        protos += pr
+        bodies.append(c)
+        report += [(os.path.basename(p),) + r for r in rep]
+    csrc = os.path.join(OUT, "sosref.c")
+    with open(csrc, "w") as f:
+        f.write(t.PRELUDE + "\n".join(protos) + "\n\n" + "\n".join(bodies))
+    with open(os.path.join(OUT, "translation_report.txt"), "w") as f:
+        for fn, name, st in report:
+            f.write("%-16s %-32s %s\n" % (fn, name, st))
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-o", lib, csrc, "-lm"]
+    subprocess.run(cmd, check=True)
+    if verbose:
+        ok = sum(1 for r in report if r[2] == "ok")
+        print("oracle/_ref: %d of %d reference subroutines translated and compiled -> %s" % (ok, len(report), lib))
+    return lib
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

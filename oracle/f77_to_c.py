@@ -1,0 +1,813 @@
+#!/usr/bin/env python3
+"""f77_to_c.py -- TEST INFRASTRUCTURE.  Mechanical translator from the fixed-form Fortran 77 subset the SOS-ABS
+reference is written in to C, so that the reference's OWN source of the hot-path routines can be compiled and run in
+an image that has no Fortran compiler (oracle/build_ref.py drives it; outputs go to oracle/_ref/, never into the
+repository history).  It exists to pin oracle/sos_oracle.c: every restated routine is compared bit for bit with the
+translation of the routine it restates (tests/test_oracle_vs_reference.py).
+
+What is implemented is what those routines use, with Fortran's own semantics where they differ from C's:
+  * cpp-style #include / object-like #define (inc/SOS.h), fixed-form continuation, labels, '!' comments;
+  * INTEGER*4 / REAL / DOUBLE PRECISION / LOGICAL scalars and arrays with arbitrary bounds, column-major;
+    all dummy arguments by reference; local arrays static (gfortran places them in zeroed .bss);
+  * expression typing by Fortran's rules: REAL*4 literals and all-REAL*4 sub-expressions are evaluated in single
+    precision, mixed operands are promoted operand by operand, integer division truncates, x**n with an integer n is
+    libgcc's __powidf2 / __powisf2 multiplication chain, x**y otherwise pow / powf;
+  * DO loops with the iteration count fixed at entry (labelled or ENDDO), block and logical IF, GOTO, CONTINUE, CALL,
+    RETURN; WRITE / FORMAT are dropped (trace and error messages only in the routines translated).
+Anything else raises Unsupported and the routine is skipped (reported by build_ref.py).
+"""
+import re
+import sys
+
+
+class Unsupported(Exception):
+    pass
+
+
+# ----------------------------------------------------------------------------------------------- source lines
+def read_defines(path):
+    defs = {}
+    for ln in open(path, encoding="latin-1"):
+        m = re.match(r"#define\s+(\w+)\s+(.*?)\s*$", ln)
+        if m:
+            defs[m.group(1)] = m.group(2)
+    return defs
+
+
+def strip_comment(s):
+    out, q = [], False
+    for ch in s:
+        if ch == "'":
+            q = not q
+        if ch == "!" and not q:
+            break
+        out.append(ch)
+    return "".join(out).rstrip()
+
+
+def logical_lines(path, defines):
+    """Yields (label, statement_text_upper_outside_strings, first_physical_line_number)."""
+    stmts = []
+    for no, raw in enumerate(open(path, encoding="latin-1"), 1):
+        ln = raw.rstrip("\n").rstrip("\r")
+        if not ln.strip():
+            continue
+        if ln[0] in "Cc*!":
+            continue
+        if ln.startswith("#"):
+            m = re.match(r"#define\s+(\w+)\s+(.*?)\s*$", ln)
+            if m:
+                defines[m.group(1)] = m.group(2)
+            continue
+        ti = ln.find("\t")
+        if 0 <= ti < 6:                                           # gfortran: a tab in columns 1-6 jumps to the statement field
+            lab, rest = ln[:ti], ln[ti + 1:]
+            if rest[:1] in tuple("123456789"):
+                ln = "     " + rest[0] + rest[1:]
+            else:
+                ln = lab.ljust(5)[:5] + " " + rest
+        ln = ln.replace("\t", " ")
+        head = ln[:6].ljust(6)
+        body = strip_comment(ln[6:72] if False else ln[6:])      # the reference exceeds column 72 freely (gfortran -ffixed-line-length-none)
+        if head[:5].strip().startswith("!"):
+            continue
+        if head[5] not in " 0" and head[:5].strip() == "":
+            if not stmts:
+                raise Unsupported("continuation without a statement at line %d" % no)
+            stmts[-1][1] += " " + body.strip()
+            continue
+        if not body.strip():
+            continue
+        stmts.append([head[:5].strip(), body.strip(), no])
+    for lab, txt, no in stmts:
+        yield lab, txt, no
+
+
+TOKEN_RE = re.compile(r"""\s*(?:
+    (?P<str>'(?:[^']|'')*') |
+    (?P<dotop>\.(?:EQ|NE|LT|LE|GT|GE|AND|OR|NOT|TRUE|FALSE|EQV|NEQV)\.) |
+    (?P<num>(?:\d+\.?\d*|\.\d+)(?:[EDed][+-]?\d+)?) |
+    (?P<id>[A-Za-z_][A-Za-z_0-9]*) |
+    (?P<op>\*\*|//|[-+*/(),=:])
+)""", re.X)
+
+
+def tokenize(text, defines, depth=0):
+    toks, pos = [], 0
+    text = text.rstrip()
+    while pos < len(text):
+        m = TOKEN_RE.match(text, pos)
+        if not m:
+            raise Unsupported("cannot tokenize %r" % text[pos:pos + 20])
+        pos = m.end()
+        if m.group("str"):
+            toks.append(("str", m.group("str")))
+        elif m.group("dotop"):
+            toks.append(("op", m.group("dotop").upper()))
+        elif m.group("num"):
+            s = m.group("num").upper()
+            # "1.EQ." style: a trailing '.' followed by a dotted operator belongs to the operator
+            if s.endswith(".") and re.match(r"(EQ|NE|LT|LE|GT|GE|AND|OR)\.", text[pos:pos + 4].upper()):
+                s = s[:-1]
+                pos -= 1
+            toks.append(("num", s))
+        elif m.group("id"):
+            name = m.group("id")
+            up = name.upper()
+            key = name if name in defines else (up if up in defines else None)
+            if key is not None and depth < 8:
+                toks.extend(tokenize(defines[key], defines, depth + 1))
+            else:
+                toks.append(("id", up))
+        else:
+            toks.append(("op", m.group("op")))
+    return toks
+
+
+# ----------------------------------------------------------------------------------------------- expressions
+RANK = {"i": 0, "r": 1, "d": 2}
+CT = {"i": "int", "r": "float", "d": "double", "l": "int"}
+
+INTRINSICS = {
+    # name: (kind, ...)   kind 'd1': double function of one arg; 'g1': generic by argument type; 'conv': conversion
+    "DEXP": ("d1", "exp"), "DSQRT": ("d1", "sqrt"), "DCOS": ("d1", "cos"), "DSIN": ("d1", "sin"), "DTAN": ("d1", "tan"),
+    "DACOS": ("d1", "acos"), "DASIN": ("d1", "asin"), "DATAN": ("d1", "atan"), "DLOG": ("d1", "log"), "DLOG10": ("d1", "log10"),
+    "DABS": ("d1", "fabs"),
+    "EXP": ("g1", "exp"), "SQRT": ("g1", "sqrt"), "COS": ("g1", "cos"), "SIN": ("g1", "sin"), "TAN": ("g1", "tan"),
+    "ACOS": ("g1", "acos"), "ASIN": ("g1", "asin"), "ATAN": ("g1", "atan"), "LOG": ("g1", "log"), "ALOG": ("g1", "log"),
+    "ABS": ("abs",), "IABS": ("abs",),
+    "DBLE": ("conv", "d"), "DFLOAT": ("conv", "d"), "FLOAT": ("conv", "r"), "REAL": ("conv", "r"), "SNGL": ("conv", "r"),
+    "INT": ("conv", "i"), "IDINT": ("conv", "i"), "IFIX": ("conv", "i"),
+    "MAX": ("minmax", ">"), "MIN": ("minmax", "<"), "DMAX1": ("minmax", ">"), "DMIN1": ("minmax", "<"),
+    "AMAX1": ("minmax", ">"), "AMIN1": ("minmax", "<"), "MAX0": ("minmax", ">"), "MIN0": ("minmax", "<"),
+    "MOD": ("mod",),
+}
+
+
+def conv(code, frm, to):
+    if frm == to:
+        return code
+    if to == "l" or frm == "l":
+        return code
+    return "((%s)(%s))" % (CT[to], code)
+
+
+class Parser:
+    def __init__(self, toks, unit):
+        self.t, self.p, self.u = toks, 0, unit
+
+    def peek(self):
+        return self.t[self.p] if self.p < len(self.t) else ("end", "")
+
+    def take(self, val=None):
+        k, v = self.peek()
+        if val is not None and v != val:
+            raise Unsupported("expected %r, found %r" % (val, v))
+        self.p += 1
+        return k, v
+
+    def at(self, val):
+        return self.peek()[1] == val and self.peek()[0] == "op"
+
+    # precedence climbing
+    def expr(self):
+        return self.p_or()
+
+    def p_or(self):
+        a = self.p_and()
+        while self.at(".OR."):
+            self.take()
+            b = self.p_and()
+            a = ("(%s || %s)" % (a[0], b[0]), "l")
+        return a
+
+    def p_and(self):
+        a = self.p_not()
+        while self.at(".AND."):
+            self.take()
+            b = self.p_not()
+            a = ("(%s && %s)" % (a[0], b[0]), "l")
+        return a
+
+    def p_not(self):
+        if self.at(".NOT."):
+            self.take()
+            a = self.p_not()
+            return ("(!%s)" % a[0], "l")
+        return self.p_rel()
+
+    def p_rel(self):
+        a = self.p_add()
+        ops = {".EQ.": "==", ".NE.": "!=", ".LT.": "<", ".LE.": "<=", ".GT.": ">", ".GE.": ">="}
+        if self.peek()[0] == "op" and self.peek()[1] in ops:
+            op = ops[self.take()[1]]
+            b = self.p_add()
+            if a[1] == "c" or b[1] == "c":
+                if a[1] != "c" or b[1] != "c" or op not in ("==", "!="):
+                    raise Unsupported("character comparison")
+                return ("(f77_cmp(%s, %s) %s 0)" % (a[0], b[0], op), "l")
+            t = a[1] if RANK[a[1]] >= RANK[b[1]] else b[1]
+            return ("(%s %s %s)" % (conv(a[0], a[1], t), op, conv(b[0], b[1], t)), "l")
+        return a
+
+    def p_add(self):
+        if self.at("-") or self.at("+"):
+            op = self.take()[1]
+            a = self.p_mul()
+            a = ("(%s%s)" % (op, a[0]), a[1])
+        else:
+            a = self.p_mul()
+        while self.at("+") or self.at("-"):
+            op = self.take()[1]
+            b = self.p_mul()
+            a = self.arith(a, op, b)
+        return a
+
+    def p_mul(self):
+        a = self.p_pow()
+        while self.at("*") or self.at("/"):
+            op = self.take()[1]
+            b = self.p_pow()
+            a = self.arith(a, op, b)
+        return a
+
+    def p_pow(self):
+        a = self.p_primary()
+        if self.at("**"):
+            self.take()
+            if self.at("-") or self.at("+"):
+                raise Unsupported("signed exponent without parentheses")
+            b = self.p_pow()                                     # right associative
+            if b[1] == "i":
+                f = {"i": "f77_powi_i", "r": "f77_powi_f", "d": "f77_powi_d"}[a[1]]
+                return ("%s(%s, %s)" % (f, a[0], b[0]), a[1])
+            t = a[1] if RANK[a[1]] >= RANK[b[1]] else b[1]
+            if t == "i":
+                t = b[1]
+            f = "powf" if t == "r" else "pow"
+            return ("%s(%s, %s)" % (f, conv(a[0], a[1], t), conv(b[0], b[1], t)), t)
+        return a
+
+    def arith(self, a, op, b):
+        if a[1] not in RANK or b[1] not in RANK:
+            raise Unsupported("arithmetic on non-numeric operands")
+        t = a[1] if RANK[a[1]] >= RANK[b[1]] else b[1]
+        return ("(%s %s %s)" % (conv(a[0], a[1], t), op, conv(b[0], b[1], t)), t)
+
+    def p_primary(self):
+        k, v = self.take()
+        if k == "num":
+            if re.search(r"D", v):
+                return ("%s" % v.replace("D", "e"), "d")
+            if "." in v or "E" in v:
+                s = v
+                if s.endswith("."):
+                    s += "0"
+                if s.startswith("."):
+                    s = "0" + s
+                return ("%sf" % s, "r")
+            return (v, "i")
+        if k == "op" and v == "(":
+            a = self.expr()
+            self.take(")")
+            return ("(%s)" % a[0], a[1])
+        if k == "op" and v in (".TRUE.", ".FALSE."):
+            return ("1" if v == ".TRUE." else "0", "l")
+        if k == "str":
+            lit = v[1:-1].replace("''", "'")
+            return ('"%s", %d' % (lit.replace("\\", "\\\\").replace('"', '\\"'), len(lit)), "c")
+        if k == "id":
+            if self.at("("):
+                self.take("(")
+                args = []
+                if not self.at(")"):
+                    args.append(self.expr())
+                    while self.at(","):
+                        self.take()
+                        args.append(self.expr())
+                self.take(")")
+                if v in self.u.vars and self.u.vars[v]["dims"]:
+                    return (self.u.array_ref(v, args), self.u.vars[v]["type"])
+                return self.intrinsic(v, args)
+            if v in self.u.vars:
+                if self.u.vars[v]["type"] == "c":
+                    if v not in self.u.args:
+                        raise Unsupported("local CHARACTER variable %s" % v)
+                    return ("%s, len_%s" % (self.u.cname(v), self.u.cname(v)), "c")
+                return (self.u.scalar_ref(v), self.u.vars[v]["type"])
+            raise Unsupported("undeclared name %s" % v)
+        raise Unsupported("unexpected token %r" % (v,))
+
+    def intrinsic(self, name, args):
+        if name not in INTRINSICS:
+            raise Unsupported("function %s" % name)
+        spec = INTRINSICS[name]
+        kind = spec[0]
+        if kind == "d1":
+            return ("%s(%s)" % (spec[1], conv(args[0][0], args[0][1], "d")), "d")
+        if kind == "g1":
+            t = args[0][1]
+            if t == "i":
+                raise Unsupported("%s of an integer" % name)
+            return ("%s%s(%s)" % (spec[1], "f" if t == "r" else "", args[0][0]), t)
+        if kind == "abs":
+            t = args[0][1]
+            return ("%s(%s)" % ({"i": "abs", "r": "fabsf", "d": "fabs"}[t], args[0][0]), t)
+        if kind == "conv":
+            to = spec[1]
+            return (conv(args[0][0], args[0][1], to), to)
+        if kind == "minmax":
+            t = max((a[1] for a in args), key=lambda x: RANK[x])
+            code = conv(args[0][0], args[0][1], t)
+            for a in args[1:]:
+                b = conv(a[0], a[1], t)
+                code = "((%s) %s (%s) ? (%s) : (%s))" % (code, spec[1], b, code, b)
+            return (code, t)
+        if kind == "mod":
+            a, b = args
+            if a[1] == "i" and b[1] == "i":
+                return ("((%s) %% (%s))" % (a[0], b[0]), "i")
+            t = a[1] if RANK[a[1]] >= RANK[b[1]] else b[1]
+            return ("%s(%s, %s)" % ("fmodf" if t == "r" else "fmod", conv(a[0], a[1], t), conv(b[0], b[1], t)), t)
+        raise Unsupported(name)
+
+
+# ----------------------------------------------------------------------------------------------- program units
+TYPE_RE = re.compile(r"^(DOUBLE\s*PRECISION|REAL\s*\*\s*8|REAL\s*\*\s*4|REAL|INTEGER\s*\*\s*4|INTEGER\s*\*\s*2|INTEGER|LOGICAL\s*\*\s*4|LOGICAL|"
+                     r"CHARACTER\s*\*\s*\(?\s*[\w]+\s*\)?|CHARACTER)\s*(.*)$", re.I)
+
+
+def split_top(s, sep=","):
+    out, depth, cur, q = [], 0, [], False
+    for ch in s:
+        if ch == "'":
+            q = not q
+        if not q:
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            elif ch == sep and depth == 0:
+                out.append("".join(cur).strip())
+                cur = []
+                continue
+        cur.append(ch)
+    if "".join(cur).strip():
+        out.append("".join(cur).strip())
+    return out
+
+
+class Unit:
+    def __init__(self, name, args, defines):
+        self.name, self.args, self.defines = name, args, defines
+        self.vars = {}
+        self.body = []                 # C lines
+        self.labels_used = set()
+        self.stubs = set()
+        self.tmp = 0
+
+    def cname(self, v):
+        return "v_" + v.lower()
+
+    def scalar_ref(self, v):
+        return ("(*%s)" % self.cname(v)) if v in self.args else self.cname(v)
+
+    def dim_exprs(self, v):
+        out = []
+        for lo, hi in self.vars[v]["dims"]:
+            out.append((self.cstr(lo, "i"), None if hi == "*" else self.cstr(hi, "i")))
+        return out
+
+    def array_ref(self, v, args):
+        dims = self.dim_exprs(v)
+        if len(args) != len(dims):
+            raise Unsupported("rank mismatch on %s" % v)
+        idx, stride = None, None
+        for (a, t), (lo, hi) in zip(args, dims):
+            if t != "i":
+                raise Unsupported("non-integer subscript")
+            term = "((%s) - (%s))" % (a, lo)
+            if idx is None:
+                idx = term
+            else:
+                idx = "%s + (%s) * %s" % (idx, stride, term)
+            if hi is not None:
+                ext = "((%s) - (%s) + 1)" % (hi, lo)
+                stride = ext if stride is None else "(%s) * %s" % (stride, ext)
+        return "%s[%s]" % (self.cname(v), idx)
+
+    def cexpr(self, text_or_toks):
+        """(C code, Fortran type) of an expression"""
+        toks = tokenize(text_or_toks, self.defines) if isinstance(text_or_toks, str) else text_or_toks
+        p = Parser(toks, self)
+        e = p.expr()
+        if p.p != len(toks):
+            raise Unsupported("trailing tokens in expression: %r" % (toks[p.p:],))
+        return e
+
+    def cstr(self, text_or_toks, want):
+        """C code of an expression converted to the wanted type"""
+        e = self.cexpr(text_or_toks)
+        return conv(e[0], e[1], want)
+
+    def declare(self, ftype, rest):
+        ft = re.sub(r"\s+", "", ftype.upper())
+        if ft.startswith("DOUBLE") or ft == "REAL*8":
+            t = "d"
+        elif ft.startswith("REAL"):
+            t = "r"
+        elif ft.startswith("INTEGER"):
+            t = "i"
+        elif ft.startswith("LOGICAL"):
+            t = "l"
+        else:
+            t = "c"
+        for item in split_top(rest):
+            m = re.match(r"^(\w+)\s*(?:\((.*)\))?\s*(?:\*\s*\(?\s*\w+\s*\)?)?$", item.strip())
+            if not m:
+                raise Unsupported("declaration %r" % item)
+            name = m.group(1).upper()
+            dims = []
+            if m.group(2) is not None:
+                for d in split_top(m.group(2)):
+                    if ":" in d:
+                        lo, hi = [x.strip() for x in split_top(d, ":")]
+                    else:
+                        lo, hi = "1", d.strip()
+                    dims.append((lo, hi))
+            self.vars[name] = {"type": t, "dims": dims}
+
+
+def translate_unit(name, args, stmts, defines, known_subs):
+    u = Unit(name, args, defines)
+    out = []
+    # pass 1: declarations
+    exe = []
+    for lab, txt, no in stmts:
+        up = txt.upper()
+        m = TYPE_RE.match(txt)
+        if m and not re.match(r"^\w+\s*(\(.*\))?\s*=", txt):
+            u.declare(m.group(1), m.group(2))
+            continue
+        if up.startswith("IMPLICIT"):
+            continue
+        exe.append((lab, txt, no))
+    for a in args:
+        if a not in u.vars:
+            raise Unsupported("argument %s has no declaration" % a)
+    has_char = any(u.vars[a]["type"] == "c" for a in args)
+    # DO-loop bookkeeping
+    do_stack = []          # (terminal label or None)
+    ind = ["  "]
+
+    def emit(s):
+        out.append("".join(ind) + s)
+
+    def new_tmp():
+        u.tmp += 1
+        return "t%d_" % u.tmp
+
+    def simple_statement(txt):
+        """assignment / GOTO / CALL / RETURN / CONTINUE / WRITE as a single C statement string"""
+        up = txt.upper().strip()
+        if up == "CONTINUE":
+            return ";"
+        if up == "RETURN":
+            return "return;"
+        m = re.match(r"^GO\s*TO\s*(\d+)$", up)
+        if m:
+            u.labels_used.add(m.group(1))
+            return "goto L%s;" % m.group(1)
+        m = re.match(r"^(WRITE|READ|PRINT)\s*\((.*)$", txt, re.I | re.S)
+        if m or up.startswith("PRINT"):
+            if up.startswith("PRINT"):
+                return "; /* PRINT dropped */"
+            kind = m.group(1).upper()
+            rest = m.group(2)
+            depth, j = 1, 0
+            for j, ch in enumerate(rest):
+                if ch == "(":
+                    depth += 1
+                elif ch == ")":
+                    depth -= 1
+                    if depth == 0:
+                        break
+            ctl, items = split_top(rest[:j]), rest[j + 1:].strip()
+            pos = [c for c in ctl if "=" not in c]
+            kv = dict((c.split("=", 1)[0].strip().upper(), c.split("=", 1)[1].strip()) for c in ctl if "=" in c)
+            formatted = len(pos) > 1 or "FMT" in kv
+            if formatted:
+                if kind == "READ":
+                    raise Unsupported("formatted READ")
+                return "; /* formatted WRITE dropped */"
+            unit = u.cstr(kv.get("UNIT", pos[0] if pos else "0"), "i")
+            err = kv.get("ERR")
+            fail = "goto L%s;" % err if err else "abort();"
+            if err:
+                u.labels_used.add(err)
+            endl = kv.get("END")
+            if endl:
+                u.labels_used.add(endl)
+
+            def io_items(text):
+                code = []
+                for it in split_top(text):
+                    it = it.strip()
+                    if it.startswith("(") and it.endswith(")") and any(re.match(r"^\w+\s*=", q) for q in split_top(it[1:-1])):
+                        parts = split_top(it[1:-1])
+                        k = next(i for i, q in enumerate(parts) if re.match(r"^\w+\s*=", q))
+                        var, e1 = [x.strip() for x in parts[k].split("=", 1)]
+                        e2 = parts[k + 1]
+                        e3 = parts[k + 2] if len(parts) > k + 2 else "1"
+                        v = u.scalar_ref(var.upper())
+                        code.append("for (%s = %s; (%s) > 0 ? %s <= (%s) : %s >= (%s); %s += %s) {" %
+                                    (v, u.cstr(e1, "i"), u.cstr(e3, "i"), v, u.cstr(e2, "i"), v, u.cstr(e2, "i"), v, u.cstr(e3, "i")))
+                        code += io_items(", ".join(parts[:k]))
+                        code.append("}")
+                    else:
+                        e = u.cexpr(it)
+                        if e[1] == "c":
+                            raise Unsupported("character I/O item")
+                        if kind == "READ":
+                            code.append("if (!f77_ritem(%s, &%s, sizeof(%s))) { %s }" % (unit, e[0], CT[e[1]], fail))
+                        else:
+                            tmp = new_tmp()
+                            code.append("{ %s %s = %s; f77_witem(%s, &%s, sizeof(%s)); }" % (CT[e[1]], tmp, e[0], unit, tmp, CT[e[1]]))
+                return code
+            body = io_items(items)
+            if kind == "READ":
+                at_end = ("if (f77_eof(%s)) goto L%s; " % (unit, endl)) if endl else ""
+                return "{ %sif (!f77_rbegin(%s)) { %s } %s }" % (at_end, unit, fail, " ".join(body))
+            return "{ f77_wbegin(%s); %s if (!f77_wend(%s)) { %s } }" % (unit, " ".join(body), unit, fail)
+        m = re.match(r"^OPEN\s*\((.*)\)\s*$", txt, re.I | re.S)
+        if m:
+            kv = {}
+            for c in split_top(m.group(1)):
+                if "=" in c:
+                    kv[c.split("=", 1)[0].strip().upper()] = c.split("=", 1)[1].strip()
+                else:
+                    kv["UNIT"] = c.strip()
+            if "UNFORMATTED" not in kv.get("FORM", "").upper():
+                raise Unsupported("formatted OPEN")
+            f = u.cexpr(kv["FILE"])
+            if f[1] != "c":
+                raise Unsupported("OPEN FILE= expression")
+            err = kv.get("ERR")
+            if err:
+                u.labels_used.add(err)
+            st = kv.get("STATUS", "'UNKNOWN'").upper().strip("'")
+            return "if (!f77_open(%s, %s, %d)) { %s }" % (u.cstr(kv["UNIT"], "i"), f[0], {"OLD": 1, "NEW": 2}.get(st, 0),
+                                                        "goto L%s;" % err if err else "abort();")
+        m = re.match(r"^CLOSE\s*\((.*)\)\s*$", txt, re.I | re.S)
+        if m:
+            unit = [c for c in split_top(m.group(1)) if "=" not in c or c.upper().startswith("UNIT")][0].split("=")[-1]
+            return "f77_close(%s);" % u.cstr(unit, "i")
+        if re.match(r"^(REWIND|INQUIRE|BACKSPACE)\b", up):
+            raise Unsupported("file I/O: %s" % up[:20])
+        m = re.match(r"^CALL\s+(\w+)\s*\((.*)\)\s*$", txt, re.I | re.S)
+        if m:
+            callee = m.group(1).upper()
+            if callee not in known_subs:
+                # routine of another source file that is outside the hot path: calling it aborts
+                u.stubs.add(callee)
+                return "f77_untranslated(\"%s\");" % callee
+            pre, cargs, hidden = [], [], []
+            for a in split_top(m.group(2)):
+                aup = a.strip().upper()
+                if re.match(r"^\w+$", aup) and aup in u.vars and u.vars[aup]["type"] == "c":
+                    if aup not in u.args:
+                        raise Unsupported("local CHARACTER actual argument")
+                    cargs.append(u.cname(aup))
+                    hidden.append("len_" + u.cname(aup))
+                elif re.match(r"^\w+$", aup) and aup in u.vars:
+                    cargs.append(u.cname(aup) if (aup in u.args or u.vars[aup]["dims"]) else "&" + u.cname(aup))
+                elif re.match(r"^\w+\s*\(.*\)$", aup) and aup.split("(")[0].strip() in u.vars and u.vars[aup.split("(")[0].strip()]["dims"]:
+                    e = u.cexpr(a)
+                    cargs.append("&" + e[0])
+                else:
+                    e = u.cexpr(a)
+                    if e[1] == "c":
+                        raise Unsupported("character actual argument")
+                    tmp = new_tmp()
+                    pre.append("%s %s = %s;" % (CT[e[1]], tmp, e[0]))
+                    cargs.append("&" + tmp)
+            return "{ %s %s_(%s); }" % (" ".join(pre), callee.lower(), ", ".join(cargs + hidden))
+        # assignment
+        toks = tokenize(txt, defines)
+        depth, eq = 0, None
+        for i, (k, v) in enumerate(toks):
+            if k == "op" and v == "(":
+                depth += 1
+            elif k == "op" and v == ")":
+                depth -= 1
+            elif k == "op" and v == "=" and depth == 0:
+                eq = i
+                break
+        if eq is None:
+            raise Unsupported("statement %r" % txt[:40])
+        lhs = u.cexpr(toks[:eq])
+        rhs = u.cexpr(toks[eq + 1:])
+        if lhs[1] == "c" or rhs[1] == "c":
+            raise Unsupported("character assignment")
+        return "%s = %s;" % (lhs[0], conv(rhs[0], rhs[1], lhs[1]))
+
+    def close_do():
+        ind.pop()
+        emit("}")
+        ind.pop()
+        emit("}")
+
+    for lab, txt, no in exe:
+        up = txt.upper().strip()
+        try:
+            if up == "END":
+                break
+            if re.match(r"^FORMAT\s*\(", up):
+                continue
+            # terminal statement of labelled DO loops?
+            terminal_for = [d for d in do_stack if d is not None and d == lab]
+            m = re.match(r"^DO\s*WHILE\s*\((.*)\)\s*$", txt, re.I | re.S)
+            if m:
+                if lab:
+                    emit("L%s: ;" % lab)
+                emit("{")
+                ind.append("  ")
+                emit("while (%s) {" % u.cexpr(m.group(1))[0])
+                ind.append("  ")
+                do_stack.append(None)
+                continue
+            m = re.match(r"^DO\s+(?:(\d+)\s*,?\s*)?(\w+)\s*=\s*(.*)$", txt, re.I)
+            if m and "=" in txt and not re.match(r"^DO\w*\s*=", up.replace(" ", "")[:0] or "x"):
+                if lab:
+                    emit("L%s: ;" % lab)
+                parts = split_top(m.group(3))
+                if len(parts) not in (2, 3):
+                    raise Unsupported("DO bounds")
+                var = m.group(2).upper()
+                if var not in u.vars or u.vars[var]["type"] != "i":
+                    raise Unsupported("DO variable %s" % var)
+                e1, e2 = u.cstr(parts[0], "i"), u.cstr(parts[1], "i")
+                e3 = u.cstr(parts[2], "i") if len(parts) == 3 else "1"
+                v = u.scalar_ref(var)
+                t = new_tmp()
+                emit("{ int %s_s = %s; int %s_n; %s = %s; %s_n = ((%s) - %s + %s_s) / %s_s; if (%s_n < 0) %s_n = 0;" %
+                     (t, e3, t, v, e1, t, e2, v, t, t, t, t))
+                ind.append("  ")
+                emit("for (; %s_n > 0; --%s_n, %s += %s_s) {" % (t, t, v, t))
+                ind.append("  ")
+                do_stack.append(m.group(1))
+                continue
+            if up in ("ENDDO", "END DO"):
+                if not do_stack or do_stack[-1] is not None:
+                    raise Unsupported("ENDDO without DO")
+                if lab:
+                    emit("L%s: ;" % lab)
+                do_stack.pop()
+                close_do()
+                continue
+            m = re.match(r"^IF\s*\((.*)\)\s*THEN$", txt, re.I | re.S)
+            if m:
+                if lab:
+                    emit("L%s: ;" % lab)
+                emit("if (%s) {" % u.cexpr(m.group(1))[0])
+                ind.append("  ")
+                continue
+            m = re.match(r"^ELSE\s*IF\s*\((.*)\)\s*THEN$", txt, re.I | re.S)
+            if m:
+                ind.pop()
+                emit("} else if (%s) {" % u.cexpr(m.group(1))[0])
+                ind.append("  ")
+                continue
+            if up == "ELSE":
+                ind.pop()
+                emit("} else {")
+                ind.append("  ")
+                continue
+            if up in ("ENDIF", "END IF"):
+                ind.pop()
+                emit("}")
+                if lab:
+                    emit("L%s: ;" % lab)
+                continue
+            if lab:
+                emit("L%s: ;" % lab)
+            if up.startswith("IF"):
+                # logical IF: find the matching parenthesis
+                i = txt.index("(")
+                depth, j = 0, i
+                for j in range(i, len(txt)):
+                    if txt[j] == "(":
+                        depth += 1
+                    elif txt[j] == ")":
+                        depth -= 1
+                        if depth == 0:
+                            break
+                cond, rest = txt[i + 1:j], txt[j + 1:].strip()
+                if re.match(r"^\d+\s*,", rest):
+                    raise Unsupported("arithmetic IF")
+                emit("if (%s) { %s }" % (u.cexpr(cond)[0], simple_statement(rest)))
+            else:
+                emit(simple_statement(txt))
+            # close every labelled DO that ends on this statement (innermost first)
+            while do_stack and do_stack[-1] is not None and do_stack[-1] == lab:
+                do_stack.pop()
+                close_do()
+        except Unsupported as e:
+            raise Unsupported("%s line %d: %s" % (name, no, e))
+    if do_stack:
+        raise Unsupported("%s: unterminated DO" % name)
+    # signature and declarations
+    sig = []
+    for a in args:
+        v = u.vars[a]
+        sig.append("%s *%s" % ("char" if v["type"] == "c" else CT[v["type"]], u.cname(a)))
+    if has_char:
+        sig += ["size_t len_%s" % u.cname(a) for a in args if u.vars[a]["type"] == "c"]
+    decl = []
+    for n, v in u.vars.items():
+        if n in args:
+            continue
+        if v["type"] == "c":
+            continue
+        if v["dims"]:
+            size = " * ".join("((%s) - (%s) + 1)" % (u.cstr(hi, "i"), u.cstr(lo, "i")) for lo, hi in v["dims"])
+            decl.append("  static %s %s[%s];" % (CT[v["type"]], u.cname(n), size))
+        else:
+            decl.append("  %s %s = 0;" % (CT[v["type"]], u.cname(n)))
+    # drop labels that no GOTO targets (avoids unused-label noise)
+    body = [ln for ln in out if not (re.match(r"^\s*L(\d+): ;$", ln) and re.match(r"^\s*L(\d+): ;$", ln).group(1) not in u.labels_used)]
+    code = ["void %s_(%s)" % (name.lower(), ", ".join(sig)), "{"] + decl + body + ["}", ""]
+    return "\n".join(code), "void %s_(%s);" % (name.lower(), ", ".join(sig))
+
+
+PRELUDE = r'''/* GENERATED by oracle/f77_to_c.py from the reference's Fortran sources -- do not commit (oracle/_ref/ is git-ignored) */
+#include <math.h>
+#include <stdlib.h>
+#include <stddef.h>
+#include <unistd.h>
+/* libgcc's __powidf2 / __powisf2 (what gfortran emits for x**n with an integer n) */
+static double f77_powi_d(double x, int m) { unsigned n = m < 0 ? -(unsigned)m : (unsigned)m; double y = (n % 2) ? x : 1; while (n >>= 1) { x = x * x; if (n % 2) y *= x; } return m < 0 ? 1 / y : y; }
+static float f77_powi_f(float x, int m) { unsigned n = m < 0 ? -(unsigned)m : (unsigned)m; float y = (n % 2) ? x : 1; while (n >>= 1) { x = x * x; if (n % 2) y *= x; } return m < 0 ? 1 / y : y; }
+/* minimal gfortran-compatible unformatted sequential I/O (4-byte record markers) */
+#include <stdio.h>
+#include <string.h>
+static FILE *f77_fp[100]; static int f77_wr[100]; static unsigned char *f77_buf[100]; static size_t f77_len[100], f77_pos[100], f77_cap[100];
+static int f77_cmp(const char *a, size_t la, const char *b, size_t lb) { size_t n = la > lb ? la : lb; for (size_t i = 0; i < n; ++i) { char ca = i < la ? a[i] : ' ', cb = i < lb ? b[i] : ' '; if (ca != cb) return ca < cb ? -1 : 1; } return 0; }
+static int f77_open(int u, const char *name, size_t len, int status) { char path[1024]; while (len > 0 && name[len - 1] == ' ') --len; if (len >= sizeof path) return 0; memcpy(path, name, len); path[len] = 0;
+  if (f77_fp[u]) fclose(f77_fp[u]);
+  f77_wr[u] = 0;
+  if (status == 1) f77_fp[u] = fopen(path, "rb+"); else if (status == 2) { FILE *t = fopen(path, "rb"); if (t) { fclose(t); f77_fp[u] = 0; return 0; } f77_fp[u] = fopen(path, "wb+"); } else { f77_fp[u] = fopen(path, "rb+"); if (!f77_fp[u]) f77_fp[u] = fopen(path, "wb+"); }
+  return f77_fp[u] != 0; }
+static void f77_close(int u) { if (u >= 0 && u < 100 && f77_fp[u]) { long p = ftell(f77_fp[u]); fflush(f77_fp[u]); if (p >= 0 && f77_wr[u]) { if (ftruncate(fileno(f77_fp[u]), p)) {} } fclose(f77_fp[u]); f77_fp[u] = 0; } }
+static void f77_untranslated(const char *name) { fprintf(stderr, "f77_to_c: call of untranslated routine %s\n", name); abort(); }
+static int f77_eof(int u) { int c; if (!f77_fp[u]) return 1; c = fgetc(f77_fp[u]); if (c == EOF) return 1; ungetc(c, f77_fp[u]); return 0; }
+static int f77_rbegin(int u) { int n = 0; if (!f77_fp[u] || fread(&n, 4, 1, f77_fp[u]) != 1 || n < 0) return 0; if ((size_t)n > f77_cap[u]) { f77_buf[u] = (unsigned char *)realloc(f77_buf[u], n); f77_cap[u] = n; }
+  if (n && fread(f77_buf[u], 1, n, f77_fp[u]) != (size_t)n) return 0;
+  int m = 0;
+  if (fread(&m, 4, 1, f77_fp[u]) != 1 || m != n) return 0; f77_len[u] = n; f77_pos[u] = 0; return 1; }
+static int f77_ritem(int u, void *dst, size_t sz) { if (f77_pos[u] + sz > f77_len[u]) return 0; memcpy(dst, f77_buf[u] + f77_pos[u], sz); f77_pos[u] += sz; return 1; }
+static void f77_wbegin(int u) { f77_len[u] = 0; }
+static void f77_witem(int u, const void *src, size_t sz) { if (f77_len[u] + sz > f77_cap[u]) { f77_cap[u] = 2 * (f77_len[u] + sz); f77_buf[u] = (unsigned char *)realloc(f77_buf[u], f77_cap[u]); } memcpy(f77_buf[u] + f77_len[u], src, sz); f77_len[u] += sz; }
+static int f77_wend(int u) { int n = (int)f77_len[u]; if (!f77_fp[u]) return 0; f77_wr[u] = 1; return fwrite(&n, 4, 1, f77_fp[u]) == 1 && (n == 0 || fwrite(f77_buf[u], 1, n, f77_fp[u]) == (size_t)n) && fwrite(&n, 4, 1, f77_fp[u]) == 1; }
+static int f77_powi_i(int x, int m) { int y = 1; if (m < 0) return (x == 1) ? 1 : ((x == -1) ? ((m % 2) ? -1 : 1) : 0); while (m-- > 0) y *= x; return y; }
+'''
+
+
+def translate_file(path, defines, wanted=None):
+    """Returns (c_source, prototypes, report) for the SUBROUTINEs of one file."""
+    defines = dict(defines)
+    stmts = list(logical_lines(path, defines))
+    units, cur = [], None
+    for lab, txt, no in stmts:
+        m = re.match(r"^SUBROUTINE\s+(\w+)\s*(?:\((.*)\))?\s*$", txt, re.I | re.S)
+        if m:
+            cur = [m.group(1).upper(), [a.strip().upper() for a in split_top(m.group(2) or "")], []]
+            units.append(cur)
+            continue
+        if cur is not None:
+            cur[2].append((lab, txt, no))
+    names = {u[0] for u in units}
+    src, protos, report = [], [], []
+    ok = set()
+    # two passes so that a routine may CALL one defined later in the file
+    known = set(names)
+    for name, args, body in units:
+        if wanted and name not in wanted:
+            continue
+        try:
+            code, proto = translate_unit(name, args, body, defines, known)
+            src.append(code)
+            protos.append(proto)
+            ok.add(name)
+            report.append((name, "ok"))
+        except Unsupported as e:
+            report.append((name, "skipped: %s" % e))
+    return "\n".join(src), protos, report
+
+
+if __name__ == "__main__":
+    defs = read_defines(sys.argv[2]) if len(sys.argv) > 2 else {}
+    c, p, r = translate_file(sys.argv[1], defs)
+    for name, st in r:
+        print(name, st, file=sys.stderr)
+    print(PRELUDE + "\n".join(p) + "\n\n" + c)

@@ -1,0 +1,158 @@
+"""The oracle against the REFERENCE ITSELF: oracle/build_ref.py translates the reference's Fortran sources of the hot
+path mechanically to C (oracle/f77_to_c.py: Fortran typing rules, REAL*4 sub-expressions in single precision, libgcc's
+integer powers, column-major arrays with the compile-time extents of SOS.h, gfortran's unformatted record I/O) and
+compiles them into oracle/_ref/libsosref.so.  These tests run SOS_OS (driver + its 11 subroutines), SOS_TRPHI_OPTION /
+SOS_TRPHI and SOS_GSF from that library -- i.e. the reference's own statements -- and require the hand-written
+restatement in oracle/sos_oracle.c to reproduce them BIT FOR BIT: record counts, every Stokes value, fluxes, side
+effects.  Skipped only when neither /root/reference nor a prebuilt oracle/_ref/libsosref.so is available."""
+import ctypes as C
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MX, NTM, NBM = 80, 600, 200
+
+
+@pytest.fixture(scope="module")
+def ref():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    build_ref = importlib.import_module("build_ref")
+    lib = build_ref.build(verbose=False)
+    if lib is None:
+        pytest.skip("no /root/reference and no prebuilt oracle/_ref/libsosref.so")
+    return C.CDLL(lib)
+
+
+def _fs(s):
+    return C.create_string_buffer(s.encode().ljust(500), 500)
+
+
+_ip = lambda v: C.byref(C.c_int(v))
+_dp = lambda v: C.byref(C.c_double(v))
+_P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+_L = C.c_size_t(500)
+
+
+def _pad(v, n):
+    a = np.zeros(n)
+    a[:len(v)] = v
+    return a
+
+
+def run_reference_sos_os(ref, fm, o, h, xd, yd, z, iborm, tmp, surf=None, ifresnel=0, zout=-1.0, ipolar=None):
+    N, NT = o.nbmu, len(h) - 1
+    rmu, ga = np.zeros(2 * MX + 1), np.zeros(2 * MX + 1)
+    rmu[MX - N:MX + N + 1], ga[MX - N:MX + N + 1] = o.rmu, o.ga
+    H, XD, YD, Z = (_pad(v, NTM + 1) for v in (h, xd, yd, z))
+    al, be, gm, ze = (_pad(v, NBM + 1) for v in (o.alpha, o.beta, o.gamma, o.zeta))
+    fos, fsurf = os.path.join(tmp, "REF_OS.bin"), os.path.join(tmp, "SURF.bin")
+    if os.path.exists(fos):
+        os.remove(fos)
+    if surf is not None:
+        fm.write_surface_bin(fsurf, surf)
+    em, ep, ier = C.c_double(0), C.c_double(0), C.c_int(99)
+    ref.sos_os_(_ip(N), _P(rmu), _P(ga), _ip(o.os_nb), _ip(NT), _fs(fsurf), _fs(fos), _ip(o.n0), _dp(o.tetas), _dp(o.rho),
+                _ip(1 if surf is not None else 0), _ip(ifresnel), _dp(o.ind_surf), _P(H), _P(XD), _P(YD), _P(Z), _dp(o.ron),
+                _P(al), _P(be), _P(gm), _P(ze), _dp(zout), _ip(o.igmax), _ip(iborm), _ip(o.ipolar if ipolar is None else ipolar),
+                _ip(0), _ip(6), C.byref(em), C.byref(ep), C.byref(ier), _L, _L)
+    rec = fm.read_result_bin(fos, N) if os.path.exists(fos) else np.zeros((0, 3, 2 * N + 1))
+    return dict(ier=ier.value, rec=rec, emoins=em.value, eplus=ep.value, rmu0=rmu[MX], alpha=al, gamma=gm, zeta=ze)
+
+
+CASES = {
+    "lambert_black": dict(surface="lambert", rho=0.0),
+    "lambert_0.3": dict(surface="lambert", rho=0.3),
+    "brdf_matrix": dict(surface="brdf", rho=0.05),
+    "flat_fresnel": dict(surface="lambert", rho=0.0, ifresnel=1),
+    "unpolarized": dict(surface="lambert", rho=0.1, ipolar=0),
+    "output_altitude": dict(surface="lambert", rho=0.1, zout=3.0),
+    "rayleigh_only": dict(surface="lambert", rho=0.0, aerosol=0.0, iborm=2),
+    "thick_aerosol": dict(surface="lambert", rho=0.2, aerosol=1.2, nb_gauss=16, os_nb=40),
+    "n25": dict(surface="lambert", rho=0.1, nb_gauss=24, os_nb=32),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_sos_os_restatement_is_bit_identical_to_the_reference(pkg, orc, ref, case, tmp_path):
+    syn, fm = pkg.synth, pkg.formats
+    c = CASES[case]
+    o = syn.make_optics(nb_gauss=c.get("nb_gauss", 12), tetas=35.0, os_nb=c.get("os_nb", 24), surface=c["surface"],
+                        rho=c["rho"], zout=c.get("zout", -1.0), ipolar=c.get("ipolar", 1))
+    z, h, xa, ym = syn.profile(0.08, 8.0, c.get("aerosol", 0.25), 2.0, 0.05)
+    xd = np.array(xa) * o.piztr
+    iborm = c.get("iborm", o.os_nb)
+    ifr = c.get("ifresnel", 0)
+    surf = o.surf if o.imat_surf == 1 else None
+    al, gm, ze = o.alpha.copy(), o.gamma.copy(), o.zeta.copy()
+    rmu = o.rmu.copy()
+    r = orc.sos_os(o.nbmu, rmu, o.ga, o.os_nb, len(h) - 1, o.n0, o.tetas, o.rho, o.imat_surf, ifr, o.ind_surf, h, xd, ym, z,
+                   o.ron, al, o.beta, gm, ze, o.zout, o.igmax, iborm, o.ipolar, surf)
+    f = run_reference_sos_os(ref, fm, o, h, xd, ym, z, iborm, str(tmp_path), surf=surf, ifresnel=ifr, zout=o.zout)
+    assert f["ier"] == r.ier == 0
+    assert f["rec"].shape[0] == r.n_fourier                     # same number of Fourier orders written
+    assert np.array_equal(f["rec"], r.rec)                      # every Q, U, I value: identical bits
+    assert f["emoins"] == r.emoins and f["eplus"] == r.eplus
+    assert f["rmu0"] == -o.rmu[o.nbmu + o.n0]                    # caller-visible side effect RMU(0) = mu_s
+    if o.ipolar == 0:                                            # and the zeroing of alpha, gamma, zeta
+        assert not f["alpha"].any() and not f["gamma"].any() and not f["zeta"].any()
+
+
+def test_trphi_option_restatement_against_the_reference(pkg, orc, ref, tmp_path):
+    """SOS_TRPHI_OPTION / SOS_TRPHI / SOS_GLITTE / SOS_ANGLE / SOS_REFLEX / SOS_MATRIC / SOS_POLAR from the reference."""
+    syn, fm = pkg.synth, pkg.formats
+    o = syn.make_optics(nb_gauss=12, tetas=35.0, os_nb=24, surface="glitter")
+    z, h, xa, ym = syn.profile(0.05, 8.0, 0.2, 2.0, 0.0)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import oracle_term
+    r = oracle_term(orc, o, syn.Term(0, 1.0, z, h, xa, ym))
+    N = o.nbmu
+    fos = str(tmp_path / "SOS_Result.bin")
+    fm.write_result_bin(fos, r.rec)
+    rmu, ga = np.zeros(2 * MX + 1), np.zeros(2 * MX + 1)
+    rmu[MX - N:MX + N + 1], ga[MX - N:MX + N + 1] = o.rmu, o.ga
+    for itrphi, phios, pas, igli, ifr in ((1, 0.0, 0, 1, 0), (1, 37.5, 0, 1, 0), (2, 0.0, 30, 1, 0), (2, 0.0, 45, 0, 1)):
+        n0, pf0, th0, up0, dn0 = orc.trphi_option(r.rec, N, o.rmu, r.ttot_tronc, r.tauout, igli, o.n0, o.wind, o.ind_surf,
+                                                  ifr, itrphi, phios, pas, 1)
+        pf, th = np.zeros(361), np.zeros(MX + 1)
+        tabs = [np.zeros((MX + 1, 361)) for _ in range(14)]
+        ier = C.c_int(99)
+        ref.sos_trphi_option_(_ip(N), _P(rmu), _P(ga), _fs(fos), _dp(r.ttot_tronc), _dp(r.tauout), _dp(-1.0), _ip(igli),
+                              _ip(o.n0), _dp(o.wind), _dp(o.ind_surf), _ip(ifr), _ip(0), _dp(0.0), _dp(0.0), _dp(0.0), _ip(0),
+                              _ip(0), _ip(0), _dp(0.0), _dp(0.0), _ip(0), _dp(0.0), _ip(itrphi), _dp(phios), _ip(pas), _ip(1),
+                              _P(pf), _P(th), *[_P(t) for t in tabs], C.byref(ier), _L)
+        assert ier.value == 0
+        for tb in range(7):
+            assert np.array_equal(tabs[tb][:N, :n0].T, up0[tb]), (itrphi, "up", tb)
+            assert np.array_equal(tabs[7 + tb][:N, :n0].T, dn0[tb]), (itrphi, "down", tb)
+        assert np.array_equal(th[:N], th0)
+
+
+def test_gsf_restatement_against_the_reference(pkg, orc, ref, tmp_path):
+    """SOS_GSF / SOS_CALCG: Fourier series of the Cox-Munk G function for every (theta1 >= theta2) pair: the data-
+    dependent series lengths IL and every coefficient."""
+    rmu, ga, n0, _ = pkg.synth.sos_angles(10, 35.0)
+    N = (rmu.size - 1) // 2
+    wind, os_nm = 5.0, 48
+    sig = float(np.float32(0.003) + np.float32(0.00512) * np.float32(wind))
+    r = np.zeros(2 * MX + 1)
+    r[MX - N:MX + N + 1] = rmu
+    fgsf = str(tmp_path / "RES_GSF")
+    ier = C.c_int(99)
+    ref.sos_gsf_(_ip(N), _P(r), _dp(sig), _ip(os_nm), _fs(fgsf), C.byref(ier), _L)
+    assert ier.value == 0
+    raw = open(fgsf, "rb").read()
+    pos, npair = 0, 0
+    while pos < len(raw):
+        n = int(np.frombuffer(raw, dtype=np.int32, count=1, offset=pos)[0])
+        i1, i2, il = np.frombuffer(raw, dtype=np.int32, count=3, offset=pos + 4)
+        e = np.frombuffer(raw, dtype=np.float64, count=il + 1, offset=pos + 16)
+        il0, e0 = orc.gsf_pair(rmu[N + i1], rmu[N + i2], sig, os_nm)
+        assert il0 == il, (i1, i2)
+        assert np.array_equal(e0[:il + 1], e), (i1, i2)
+        pos += n + 8
+        npair += 1
+    assert npair == N * (N + 1) // 2
