@@ -31,8 +31,11 @@ def build(force=False, verbose=True):
     os.makedirs(OUT, exist_ok=True)
     defines = t.read_defines(inc)
     protos, bodies, report = [], [], []
+    known = set()
     for p in srcs:
-        c, pr, rep = t.translate_file(p, defines)
+        known |= t.subroutine_names(p)
+    for p in srcs:
+        c, pr, rep = t.translate_file(p, defines, known=known)
         protos += pr
         bodies.append(c)
         report += [(os.path.basename(p),) + r for r in rep]
@@ -44,6 +47,7 @@ def build(force=False, verbose=True):
             f.write("%-16s %-32s %s\n" % (fn, name, st))
     cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-o", lib, csrc, "-lm"]
     subprocess.run(cmd, check=True)
+    os.remove(csrc)                                             # the translated sources are not kept
     if verbose:
         ok = sum(1 for r in report if r[2] == "ok")
         print("oracle/_ref: %d of %d reference subroutines translated and compiled -> %s" % (ok, len(report), lib))

@@ -364,6 +364,8 @@ class Unit:
         self.body = []                 # C lines
         self.labels_used = set()
         self.stubs = set()
+        self.formats = {}
+        self.text_units = set()
         self.tmp = 0
 
     def cname(self, v):
@@ -452,6 +454,15 @@ def translate_unit(name, args, stmts, defines, known_subs):
         if up.startswith("IMPLICIT"):
             continue
         exe.append((lab, txt, no))
+    for lab, txt, no in exe:
+        m = re.match(r"^FORMAT\s*(\(.*\))\s*$", txt, re.I | re.S)
+        if m and lab:
+            u.formats[lab] = m.group(1)
+        m = re.match(r"^OPEN\s*\((.*)\)\s*$", txt, re.I | re.S)
+        if m and "UNFORMATTED" not in m.group(1).upper():
+            for c in split_top(m.group(1)):
+                if c.upper().replace(" ", "").startswith("UNIT="):
+                    u.text_units.add(c.split("=", 1)[1].strip())
     for a in args:
         if a not in u.vars:
             raise Unsupported("argument %s has no declaration" % a)
@@ -496,11 +507,14 @@ def translate_unit(name, args, stmts, defines, known_subs):
             pos = [c for c in ctl if "=" not in c]
             kv = dict((c.split("=", 1)[0].strip().upper(), c.split("=", 1)[1].strip()) for c in ctl if "=" in c)
             formatted = len(pos) > 1 or "FMT" in kv
-            if formatted:
+            unit_txt = kv.get("UNIT", pos[0] if pos else "0").strip()
+            fmt_lab = kv.get("FMT", pos[1] if len(pos) > 1 else None)
+            text_file = formatted and unit_txt in u.text_units and fmt_lab is not None and fmt_lab.strip() in u.formats
+            if formatted and not text_file:
                 if kind == "READ":
-                    raise Unsupported("formatted READ")
-                return "; /* formatted WRITE dropped */"
-            unit = u.cstr(kv.get("UNIT", pos[0] if pos else "0"), "i")
+                    raise Unsupported("formatted READ on a unit that is not opened here")
+                return "; /* trace / message WRITE dropped */"
+            unit = u.cstr(unit_txt, "i")
             err = kv.get("ERR")
             fail = "goto L%s;" % err if err else "abort();"
             if err:
@@ -524,17 +538,36 @@ def translate_unit(name, args, stmts, defines, known_subs):
                                     (v, u.cstr(e1, "i"), u.cstr(e3, "i"), v, u.cstr(e2, "i"), v, u.cstr(e2, "i"), v, u.cstr(e3, "i")))
                         code += io_items(", ".join(parts[:k]))
                         code.append("}")
+                    elif re.match(r"^\w+$", it) and it.upper() in u.vars and u.vars[it.upper()]["dims"]:
+                        v = u.vars[it.upper()]                         # whole array, storage order
+                        n = " * ".join("((%s) - (%s) + 1)" % (u.cstr(hi, "i"), u.cstr(lo, "i")) for lo, hi in v["dims"])
+                        if text_file:
+                            raise Unsupported("whole-array formatted I/O")
+                        if kind == "READ":
+                            code.append("if (!f77_ritem(%s, %s, (size_t)(%s) * sizeof(%s))) { %s }" % (unit, u.cname(it.upper()), n, CT[v["type"]], fail))
+                        else:
+                            code.append("f77_witem(%s, %s, (size_t)(%s) * sizeof(%s));" % (unit, u.cname(it.upper()), n, CT[v["type"]]))
                     else:
                         e = u.cexpr(it)
                         if e[1] == "c":
                             raise Unsupported("character I/O item")
-                        if kind == "READ":
+                        if text_file:
+                            if kind == "READ":
+                                code.append("{ double t_; if (!f77_fread(%s, &t_)) { %s } %s = (%s)t_; }" % (unit, fail, e[0], CT[e[1]]))
+                            else:
+                                code.append("f77_fwrite(%s, (double)(%s), %d);" % (unit, e[0], 1 if e[1] == "i" else 0))
+                        elif kind == "READ":
                             code.append("if (!f77_ritem(%s, &%s, sizeof(%s))) { %s }" % (unit, e[0], CT[e[1]], fail))
                         else:
                             tmp = new_tmp()
                             code.append("{ %s %s = %s; f77_witem(%s, &%s, sizeof(%s)); }" % (CT[e[1]], tmp, e[0], unit, tmp, CT[e[1]]))
                 return code
             body = io_items(items)
+            if text_file:
+                fmt = u.formats[fmt_lab.strip()].replace("\\", "\\\\").replace('"', '\\"')
+                if kind == "READ":
+                    return "{ if (!f77_fbegin(%s, \"%s\", 1)) { %s } %s }" % (unit, fmt, fail, " ".join(body))
+                return "{ if (!f77_fbegin(%s, \"%s\", 0)) { %s } %s if (!f77_fend(%s)) { %s } }" % (unit, fmt, fail, " ".join(body), unit, fail)
             if kind == "READ":
                 at_end = ("if (f77_eof(%s)) goto L%s; " % (unit, endl)) if endl else ""
                 return "{ %sif (!f77_rbegin(%s)) { %s } %s }" % (at_end, unit, fail, " ".join(body))
@@ -547,8 +580,7 @@ def translate_unit(name, args, stmts, defines, known_subs):
                     kv[c.split("=", 1)[0].strip().upper()] = c.split("=", 1)[1].strip()
                 else:
                     kv["UNIT"] = c.strip()
-            if "UNFORMATTED" not in kv.get("FORM", "").upper():
-                raise Unsupported("formatted OPEN")
+            text = "UNFORMATTED" not in kv.get("FORM", "").upper()
             f = u.cexpr(kv["FILE"])
             if f[1] != "c":
                 raise Unsupported("OPEN FILE= expression")
@@ -556,13 +588,18 @@ def translate_unit(name, args, stmts, defines, known_subs):
             if err:
                 u.labels_used.add(err)
             st = kv.get("STATUS", "'UNKNOWN'").upper().strip("'")
-            return "if (!f77_open(%s, %s, %d)) { %s }" % (u.cstr(kv["UNIT"], "i"), f[0], {"OLD": 1, "NEW": 2}.get(st, 0),
+            return "if (!f77_open(%s, %s, %d)) { %s }" % (u.cstr(kv["UNIT"], "i"), f[0], {"OLD": 1, "NEW": 2}.get(st, 0) + (4 if text else 0),
                                                         "goto L%s;" % err if err else "abort();")
         m = re.match(r"^CLOSE\s*\((.*)\)\s*$", txt, re.I | re.S)
         if m:
-            unit = [c for c in split_top(m.group(1)) if "=" not in c or c.upper().startswith("UNIT")][0].split("=")[-1]
-            return "f77_close(%s);" % u.cstr(unit, "i")
-        if re.match(r"^(REWIND|INQUIRE|BACKSPACE)\b", up):
+            parts = split_top(m.group(1))
+            unit = [c for c in parts if "=" not in c or c.upper().replace(" ", "").startswith("UNIT=")][0].split("=")[-1]
+            delete = any("DELETE" in c.upper() for c in parts)
+            return "f77_close(%s, %d);" % (u.cstr(unit, "i"), 1 if delete else 0)
+        m = re.match(r"^REWIND\s*\(?\s*(\w+)\s*\)?\s*$", txt, re.I)
+        if m:
+            return "f77_rewind(%s);" % u.cstr(m.group(1), "i")
+        if re.match(r"^(INQUIRE|BACKSPACE)\b", up):
             raise Unsupported("file I/O: %s" % up[:20])
         m = re.match(r"^CALL\s+(\w+)\s*\((.*)\)\s*$", txt, re.I | re.S)
         if m:
@@ -753,12 +790,39 @@ static float f77_powi_f(float x, int m) { unsigned n = m < 0 ? -(unsigned)m : (u
 #include <string.h>
 static FILE *f77_fp[100]; static int f77_wr[100]; static unsigned char *f77_buf[100]; static size_t f77_len[100], f77_pos[100], f77_cap[100];
 static int f77_cmp(const char *a, size_t la, const char *b, size_t lb) { size_t n = la > lb ? la : lb; for (size_t i = 0; i < n; ++i) { char ca = i < la ? a[i] : ' ', cb = i < lb ? b[i] : ' '; if (ca != cb) return ca < cb ? -1 : 1; } return 0; }
-static int f77_open(int u, const char *name, size_t len, int status) { char path[1024]; while (len > 0 && name[len - 1] == ' ') --len; if (len >= sizeof path) return 0; memcpy(path, name, len); path[len] = 0;
+static char f77_path[100][1024];
+static int f77_open(int u, const char *name, size_t len, int status) { char *path = f77_path[u]; while (len > 0 && name[len - 1] == ' ') --len; if (len >= 1024) return 0; memcpy(path, name, len); path[len] = 0;
   if (f77_fp[u]) fclose(f77_fp[u]);
-  f77_wr[u] = 0;
+  f77_wr[u] = 0; status &= 3;
   if (status == 1) f77_fp[u] = fopen(path, "rb+"); else if (status == 2) { FILE *t = fopen(path, "rb"); if (t) { fclose(t); f77_fp[u] = 0; return 0; } f77_fp[u] = fopen(path, "wb+"); } else { f77_fp[u] = fopen(path, "rb+"); if (!f77_fp[u]) f77_fp[u] = fopen(path, "wb+"); }
   return f77_fp[u] != 0; }
-static void f77_close(int u) { if (u >= 0 && u < 100 && f77_fp[u]) { long p = ftell(f77_fp[u]); fflush(f77_fp[u]); if (p >= 0 && f77_wr[u]) { if (ftruncate(fileno(f77_fp[u]), p)) {} } fclose(f77_fp[u]); f77_fp[u] = 0; } }
+static void f77_close(int u, int del) { if (u >= 0 && u < 100 && f77_fp[u]) { long p = ftell(f77_fp[u]); fflush(f77_fp[u]); if (p >= 0 && f77_wr[u]) { if (ftruncate(fileno(f77_fp[u]), p)) {} } fclose(f77_fp[u]); f77_fp[u] = 0; if (del) remove(f77_path[u]); } }
+static void f77_rewind(int u) { if (f77_fp[u]) { fflush(f77_fp[u]); fseek(f77_fp[u], 0, SEEK_SET); } }
+/* formatted records: the edit descriptors the reference uses on files (nX, Iw, Fw.d, Ew.d, Dw.d, groups with repeat counts) */
+static struct { char kind; int w, d; } f77_ed[100][256]; static int f77_ned[100], f77_ied[100]; static char f77_line[100][4096]; static size_t f77_col[100]; static int f77_rd[100];
+static const char *f77_fparse(int u, const char *p, int depth) { /* p points after '(' ; returns pointer after matching ')' */
+  while (*p && *p != ')') { int rep = 0, has = 0; while (*p == ' ' || *p == ',') ++p; if (*p == ')') break; while (*p >= '0' && *p <= '9') { rep = rep * 10 + (*p - '0'); ++p; has = 1; } if (!has) rep = 1;
+    if (*p == '(') { const char *q = p + 1, *e = q; for (int r = 0; r < rep; ++r) e = f77_fparse(u, q, depth + 1); p = e; continue; }
+    char k = *p; if (k >= 'a' && k <= 'z') k -= 32; ++p;
+    if (k == 'X') { if (f77_ned[u] < 256) { f77_ed[u][f77_ned[u]].kind = 'X'; f77_ed[u][f77_ned[u]].w = rep; f77_ned[u]++; } continue; }
+    int w = 0, d = 0; while (*p >= '0' && *p <= '9') { w = w * 10 + (*p - '0'); ++p; } if (*p == '.') { ++p; while (*p >= '0' && *p <= '9') { d = d * 10 + (*p - '0'); ++p; } }
+    for (int r = 0; r < rep && f77_ned[u] < 256; ++r) { f77_ed[u][f77_ned[u]].kind = k; f77_ed[u][f77_ned[u]].w = w; f77_ed[u][f77_ned[u]].d = d; f77_ned[u]++; } }
+  return *p == ')' ? p + 1 : p; }
+static int f77_fbegin(int u, const char *fmt, int rd) { if (!f77_fp[u]) return 0; f77_ned[u] = 0; f77_ied[u] = 0; f77_col[u] = 0; f77_rd[u] = rd; f77_fparse(u, fmt + 1, 0);
+  if (rd) { if (!fgets(f77_line[u], sizeof f77_line[u], f77_fp[u])) return 0; size_t n = strlen(f77_line[u]); while (n && (f77_line[u][n - 1] == '\n' || f77_line[u][n - 1] == '\r')) f77_line[u][--n] = 0; } else f77_line[u][0] = 0;
+  return 1; }
+static int f77_fnext(int u) { for (;;) { if (f77_ied[u] >= f77_ned[u]) { /* format reversion: new record */ if (f77_rd[u]) { if (!fgets(f77_line[u], sizeof f77_line[u], f77_fp[u])) return -1; } else { fprintf(f77_fp[u], "%s\n", f77_line[u]); f77_wr[u] = 1; f77_line[u][0] = 0; } f77_col[u] = 0; f77_ied[u] = 0; }
+    int i = f77_ied[u]++; if (f77_ed[u][i].kind == 'X') { if (f77_rd[u]) f77_col[u] += f77_ed[u][i].w; else { for (int k = 0; k < f77_ed[u][i].w; ++k) strcat(f77_line[u], " "); } continue; } return i; } }
+static void f77_fmt_e(char *out, double x, int w, int d, char ec) { char m[64], s[96]; if (x == 0.0) { snprintf(s, sizeof s, "0.%0*d%c+00", d, 0, ec); } else { snprintf(m, sizeof m, "%.*e", d - 1, fabs(x)); char *e = strchr(m, 'e'); int ex = atoi(e + 1) + 1; *e = 0; char dig[64]; int nd = 0; for (char *c = m; *c; ++c) if (*c != '.') dig[nd++] = *c; dig[nd] = 0;
+    snprintf(s, sizeof s, "%s0.%s%c%c%02d", x < 0 ? "-" : "", dig, ec, ex >= 0 ? '+' : '-', abs(ex)); }
+  size_t n = strlen(s); if ((int)n > w) { if (s[0] == '0') memmove(s, s + 1, n); else if (s[0] == '-' && s[1] == '0') memmove(s + 1, s + 2, n - 1); n = strlen(s); }
+  if ((int)n > w) { memset(out, '*', w); out[w] = 0; } else snprintf(out, 96, "%*s", w, s); }
+static void f77_fwrite(int u, double v, int is_int) { int i = f77_fnext(u); if (i < 0) return; char f[96]; char k = f77_ed[u][i].kind; int w = f77_ed[u][i].w, d = f77_ed[u][i].d;
+  if (k == 'I') snprintf(f, sizeof f, "%*d", w, (int)v); else if (k == 'F') snprintf(f, sizeof f, "%*.*f", w, d, v); else f77_fmt_e(f, v, w, d, k == 'D' ? 'D' : 'E'); (void)is_int; strcat(f77_line[u], f); }
+static int f77_fend(int u) { if (!f77_fp[u]) return 0; fprintf(f77_fp[u], "%s\n", f77_line[u]); f77_wr[u] = 1; return 1; }
+static int f77_fread(int u, double *v) { int i = f77_fnext(u); if (i < 0) return 0; int w = f77_ed[u][i].w, d = f77_ed[u][i].d; char f[128]; size_t n = strlen(f77_line[u]); int k = 0, dot = 0, expo = 0;
+  for (int c = 0; c < w && k < 120; ++c) { char ch = (f77_col[u] + c < n) ? f77_line[u][f77_col[u] + c] : ' '; if (ch == ' ') continue; if (ch == 'D' || ch == 'd') ch = 'E'; if (ch == '.') dot = 1; if (ch == 'E' || ch == 'e') expo = 1; f[k++] = ch; } f[k] = 0; f77_col[u] += w;
+  if (k == 0) { *v = 0.0; return 1; } char *end; *v = strtod(f, &end); if (end == f) return 0; if (!dot && !expo && f77_ed[u][i].kind != 'I') *v *= pow(10.0, -d); return 1; }
 static void f77_untranslated(const char *name) { fprintf(stderr, "f77_to_c: call of untranslated routine %s\n", name); abort(); }
 static int f77_eof(int u) { int c; if (!f77_fp[u]) return 1; c = fgetc(f77_fp[u]); if (c == EOF) return 1; ungetc(c, f77_fp[u]); return 0; }
 static int f77_rbegin(int u) { int n = 0; if (!f77_fp[u] || fread(&n, 4, 1, f77_fp[u]) != 1 || n < 0) return 0; if ((size_t)n > f77_cap[u]) { f77_buf[u] = (unsigned char *)realloc(f77_buf[u], n); f77_cap[u] = n; }
@@ -773,7 +837,16 @@ static int f77_powi_i(int x, int m) { int y = 1; if (m < 0) return (x == 1) ? 1 
 '''
 
 
-def translate_file(path, defines, wanted=None):
+def subroutine_names(path):
+    names = set()
+    for lab, txt, no in logical_lines(path, {}):
+        m = re.match(r"^SUBROUTINE\s+(\w+)", txt, re.I)
+        if m:
+            names.add(m.group(1).upper())
+    return names
+
+
+def translate_file(path, defines, wanted=None, known=None):
     """Returns (c_source, prototypes, report) for the SUBROUTINEs of one file."""
     defines = dict(defines)
     stmts = list(logical_lines(path, defines))
@@ -790,7 +863,7 @@ def translate_file(path, defines, wanted=None):
     src, protos, report = [], [], []
     ok = set()
     # two passes so that a routine may CALL one defined later in the file
-    known = set(names)
+    known = set(names) | set(known or ())
     for name, args, body in units:
         if wanted and name not in wanted:
             continue

@@ -156,3 +156,28 @@ def test_gsf_restatement_against_the_reference(pkg, orc, ref, tmp_path):
         pos += n + 8
         npair += 1
     assert npair == N * (N + 1) // 2
+
+
+@pytest.mark.parametrize("nbg,wind", [(10, 2.0), (12, 7.5)])
+def test_glitter_chain_restatement_is_bit_identical_to_the_reference(pkg, orc, ref, nbg, wind, tmp_path):
+    """SOS_GLITTER from the reference: SOS_GSF -> SOS_MAT_FRESNEL (through its 4(E15.8) text file) -> SOS_MAT_REFLEXION +
+    SOS_NOYAUX_FRESNEL -> SOS_MISE_FORMAT, intermediate files deleted at the end as the reference does.  The REAL*4
+    records of the surface file must equal the oracle's, bit for bit."""
+    syn, fm = pkg.synth, pkg.formats
+    rmu, ga, n0, _ = syn.sos_angles(nbg, 35.0)
+    N = (rmu.size - 1) // 2
+    os_nb = os_ns = 2 * nbg
+    os_nm = os_nb + os_ns
+    r, g = np.zeros(2 * MX + 1), np.zeros(2 * MX + 1)
+    r[MX - N:MX + N + 1], g[MX - N:MX + N + 1] = rmu, ga
+    fgl = str(tmp_path / "GLITTER.bin")
+    ier = C.c_int(99)
+    ref.sos_glitter_(_ip(N), _P(r), _P(g), _dp(wind), _dp(1.34), _ip(os_nb), _ip(os_ns), _ip(os_nm), _fs(str(tmp_path / "GSF")),
+                     _fs(str(tmp_path / "FRESNEL")), _fs(str(tmp_path / "MAT_REFLEX")), _fs(fgl), _ip(0), C.byref(ier),
+                     _L, _L, _L, _L)
+    assert ier.value == 0
+    assert sorted(os.listdir(tmp_path)) == ["GLITTER.bin"]            # the three intermediate files are gone
+    got = fm.read_surface_bin(fgl, N)
+    want, _ = orc.glitter(N, rmu, ga, wind, 1.34, os_nb, os_ns, os_nm)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
