@@ -35,11 +35,13 @@ def read_defines(path):
 
 
 def strip_comment(s):
-    out, q = [], False
+    out, q = [], None
     for ch in s:
-        if ch == "'":
-            q = not q
-        if ch == "!" and not q:
+        if q is None and ch in "'\"":
+            q = ch
+        elif q is not None and ch == q:
+            q = None
+        if ch == "!" and q is None:
             break
         out.append(ch)
     return "".join(out).rstrip()
@@ -84,7 +86,7 @@ def logical_lines(path, defines):
 
 
 TOKEN_RE = re.compile(r"""\s*(?:
-    (?P<str>'(?:[^']|'')*') |
+    (?P<str>'(?:[^']|'')*'|"[^"]*") |
     (?P<dotop>\.(?:EQ|NE|LT|LE|GT|GE|AND|OR|NOT|TRUE|FALSE|EQV|NEQV)\.) |
     (?P<num>(?:\d+\.?\d*|\.\d+)(?:[EDed][+-]?\d+)?) |
     (?P<id>[A-Za-z_][A-Za-z_0-9]*) |
@@ -101,7 +103,10 @@ def tokenize(text, defines, depth=0):
             raise Unsupported("cannot tokenize %r" % text[pos:pos + 20])
         pos = m.end()
         if m.group("str"):
-            toks.append(("str", m.group("str")))
+            v = m.group("str")
+            if v.startswith('"'):
+                v = "'" + v[1:-1].replace("'", "''") + "'"
+            toks.append(("str", v))
         elif m.group("dotop"):
             toks.append(("op", m.group("dotop").upper()))
         elif m.group("num"):
@@ -292,7 +297,7 @@ class Parser:
             if v in self.u.vars:
                 if self.u.vars[v]["type"] == "c":
                     if v not in self.u.args:
-                        raise Unsupported("local CHARACTER variable %s" % v)
+                        return ("%s, (size_t)(%s)" % (self.u.cname(v), self.u.cstr(self.u.vars[v]["clen"], "i")), "c")
                     return ("%s, len_%s" % (self.u.cname(v), self.u.cname(v)), "c")
                 return (self.u.scalar_ref(v), self.u.vars[v]["type"])
             raise Unsupported("undeclared name %s" % v)
@@ -424,6 +429,8 @@ class Unit:
             t = "l"
         else:
             t = "c"
+        m0 = re.match(r"^CHARACTER\*\(?(\w+)\)?$", ft)
+        clen = m0.group(1) if m0 else "1"
         for item in split_top(rest):
             m = re.match(r"^(\w+)\s*(?:\((.*)\))?\s*(?:\*\s*\(?\s*\w+\s*\)?)?$", item.strip())
             if not m:
@@ -437,7 +444,7 @@ class Unit:
                     else:
                         lo, hi = "1", d.strip()
                     dims.append((lo, hi))
-            self.vars[name] = {"type": t, "dims": dims}
+            self.vars[name] = {"type": t, "dims": dims, "clen": clen}
 
 
 def translate_unit(name, args, stmts, defines, known_subs):
@@ -463,6 +470,8 @@ def translate_unit(name, args, stmts, defines, known_subs):
             for c in split_top(m.group(1)):
                 if c.upper().replace(" ", "").startswith("UNIT="):
                     u.text_units.add(c.split("=", 1)[1].strip())
+                elif "=" not in c:
+                    u.text_units.add(c.strip())
     for a in args:
         if a not in u.vars:
             raise Unsupported("argument %s has no declaration" % a)
@@ -612,10 +621,8 @@ def translate_unit(name, args, stmts, defines, known_subs):
             for a in split_top(m.group(2)):
                 aup = a.strip().upper()
                 if re.match(r"^\w+$", aup) and aup in u.vars and u.vars[aup]["type"] == "c":
-                    if aup not in u.args:
-                        raise Unsupported("local CHARACTER actual argument")
                     cargs.append(u.cname(aup))
-                    hidden.append("len_" + u.cname(aup))
+                    hidden.append(("len_" + u.cname(aup)) if aup in u.args else "(size_t)(%s)" % u.cstr(u.vars[aup]["clen"], "i"))
                 elif re.match(r"^\w+$", aup) and aup in u.vars:
                     cargs.append(u.cname(aup) if (aup in u.args or u.vars[aup]["dims"]) else "&" + u.cname(aup))
                 elif re.match(r"^\w+\s*\(.*\)$", aup) and aup.split("(")[0].strip() in u.vars and u.vars[aup.split("(")[0].strip()]["dims"]:
@@ -644,6 +651,8 @@ def translate_unit(name, args, stmts, defines, known_subs):
             raise Unsupported("statement %r" % txt[:40])
         lhs = u.cexpr(toks[:eq])
         rhs = u.cexpr(toks[eq + 1:])
+        if lhs[1] == "c" and rhs[1] == "c":
+            return "f77_assign(%s, %s);" % (lhs[0], rhs[0])
         if lhs[1] == "c" or rhs[1] == "c":
             raise Unsupported("character assignment")
         return "%s = %s;" % (lhs[0], conv(rhs[0], rhs[1], lhs[1]))
@@ -765,6 +774,9 @@ def translate_unit(name, args, stmts, defines, known_subs):
         if n in args:
             continue
         if v["type"] == "c":
+            if v["dims"]:
+                raise Unsupported("CHARACTER array %s" % n)
+            decl.append("  static char %s[%s];" % (u.cname(n), u.cstr(v["clen"], "i")))
             continue
         if v["dims"]:
             size = " * ".join("((%s) - (%s) + 1)" % (u.cstr(hi, "i"), u.cstr(lo, "i")) for lo, hi in v["dims"])
@@ -789,6 +801,7 @@ static float f77_powi_f(float x, int m) { unsigned n = m < 0 ? -(unsigned)m : (u
 #include <stdio.h>
 #include <string.h>
 static FILE *f77_fp[100]; static int f77_wr[100]; static unsigned char *f77_buf[100]; static size_t f77_len[100], f77_pos[100], f77_cap[100];
+static void f77_assign(char *d, size_t ld, const char *s, size_t ls) { for (size_t i = 0; i < ld; ++i) d[i] = i < ls ? s[i] : ' '; }
 static int f77_cmp(const char *a, size_t la, const char *b, size_t lb) { size_t n = la > lb ? la : lb; for (size_t i = 0; i < n; ++i) { char ca = i < la ? a[i] : ' ', cb = i < lb ? b[i] : ' '; if (ca != cb) return ca < cb ? -1 : 1; } return 0; }
 static char f77_path[100][1024];
 static int f77_open(int u, const char *name, size_t len, int status) { char *path = f77_path[u]; while (len > 0 && name[len - 1] == ' ') --len; if (len >= 1024) return 0; memcpy(path, name, len); path[len] = 0;

@@ -181,3 +181,39 @@ def test_glitter_chain_restatement_is_bit_identical_to_the_reference(pkg, orc, r
     want, _ = orc.glitter(N, rmu, ga, wind, 1.34, os_nb, os_ns, os_nm)
     assert got.shape == want.shape
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("a_trunc,trans", [(0.0, False), (0.35, True)])
+def test_sos_restatement_is_bit_identical_to_the_reference(pkg, orc, ref, a_trunc, trans, tmp_path):
+    """SOS (SOS.F:340-697) from the reference: formatted read of the profile file, truncation adaptation, SOS_OS, tau at
+    the output level, and the 1+N black-surface IBORM=0 solves of -SOS.Trans."""
+    syn, fm = pkg.synth, pkg.formats
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import oracle_term
+    o = syn.make_optics(nb_gauss=10, tetas=40.0, os_nb=20, surface="lambert", rho=0.1, a_trunc=a_trunc, piztr=0.97)
+    z, h, xa, ym = syn.profile(0.05, 8.0, 0.2, 2.0, 0.3)
+    fprof = str(tmp_path / "PROFIL_TMP")
+    fm.write_profile(fprof, z, h, xa, ym)
+    z, h, xa, ym = fm.read_profile(fprof)
+    NT, N = len(h) - 1, o.nbmu
+    r = oracle_term(orc, o, syn.Term(0, 1.0, z, h, xa, ym), want_trans=trans)
+    rmu, ga = np.zeros(2 * MX + 1), np.zeros(2 * MX + 1)
+    rmu[MX - N:MX + N + 1], ga[MX - N:MX + N + 1] = o.rmu, o.ga
+    al, be, gm, ze = (_pad(v, NBM + 1) for v in (o.alpha, o.beta, o.gamma, o.zeta))
+    fos = str(tmp_path / "SOS_Result.bin")
+    sc = [C.c_double(0) for _ in range(6)]               # ttot_tronc, ttot_vrai, tauout, tdifmus, emoins, eplus
+    tdg = np.zeros(2 * MX + 1)
+    ier = C.c_int(99)
+    ref.sos_(_fs(fos), _fs(str(tmp_path / "Trans.txt") if trans else "NO_OUTPUT"), _fs(fprof), _ip(NT), _dp(-1.0), _ip(o.igmax),
+             _ip(1), _dp(o.ron), _dp(o.ind_surf), _dp(o.rho), _ip(0), _ip(0), _fs("none"), _ip(o.n0), _dp(o.piz), _dp(o.piztr),
+             _dp(o.a_trunc), _P(rmu), _P(ga), _dp(o.tetas), _ip(o.os_nb), _ip(N), _P(al), _P(be), _P(gm), _P(ze),
+             C.byref(sc[0]), C.byref(sc[1]), C.byref(sc[2]), C.byref(sc[3]), _P(tdg), C.byref(sc[4]), C.byref(sc[5]),
+             _ip(0), _ip(6), C.byref(ier), _L, _L, _L, _L)
+    assert ier.value == r.ier == 0
+    rec = fm.read_result_bin(fos, N)
+    assert rec.shape[0] == r.n_fourier and np.array_equal(rec, r.rec)
+    assert sc[0].value == r.ttot_tronc and sc[1].value == r.ttot_vrai and sc[2].value == r.tauout
+    assert sc[4].value == r.emoins and sc[5].value == r.eplus
+    if trans:
+        assert sc[3].value == r.tdifmus
+        assert np.array_equal(tdg[MX + 1:MX + N + 1], r.tdifmug[N + 1:])
