@@ -179,6 +179,14 @@ class Parser:
         return self.p_or()
 
     def p_or(self):
+        a = self.p_or1()
+        while self.at(".EQV.") or self.at(".NEQV."):
+            op = self.take()[1]
+            b = self.p_or1()
+            a = ("((!!(%s)) %s (!!(%s)))" % (a[0], "==" if op == ".EQV." else "!=", b[0]), "l")
+        return a
+
+    def p_or1(self):
         a = self.p_and()
         while self.at(".OR."):
             self.take()
@@ -282,6 +290,14 @@ class Parser:
             lit = v[1:-1].replace("''", "'")
             return ('"%s", %d' % (lit.replace("\\", "\\\\").replace('"', '\\"'), len(lit)), "c")
         if k == "id":
+            if self.at("(") and v in self.u.vars and self.u.vars[v]["type"] == "c" and not self.u.vars[v]["dims"]:
+                self.take("(")
+                lo = self.expr()
+                self.take(":")
+                hi = self.expr()
+                self.take(")")
+                base = self.u.cname(v)
+                return ("%s + ((%s) - 1), (size_t)((%s) - (%s) + 1)" % (base, lo[0], hi[0], lo[0]), "c")
             if self.at("("):
                 self.take("(")
                 args = []
@@ -293,12 +309,18 @@ class Parser:
                 self.take(")")
                 if v in self.u.vars and self.u.vars[v]["dims"]:
                     return (self.u.array_ref(v, args), self.u.vars[v]["type"])
+                if v == "INDEX" and len(args) == 2 and args[0][1] == "c" and args[1][1] == "c":
+                    return ("f77_index(%s, %s)" % (args[0][0], args[1][0]), "i")
                 return self.intrinsic(v, args)
             if v in self.u.vars:
                 if self.u.vars[v]["type"] == "c":
                     if v not in self.u.args:
                         return ("%s, (size_t)(%s)" % (self.u.cname(v), self.u.cstr(self.u.vars[v]["clen"], "i")), "c")
                     return ("%s, len_%s" % (self.u.cname(v), self.u.cname(v)), "c")
+                return (self.u.scalar_ref(v), self.u.vars[v]["type"])
+            if not self.u.implicit_none and not self.at("("):
+                # Fortran implicit typing: I-N integer, otherwise REAL
+                self.u.vars[v] = {"type": "i" if v[0] in "IJKLMN" else "r", "dims": [], "clen": "1"}
                 return (self.u.scalar_ref(v), self.u.vars[v]["type"])
             raise Unsupported("undeclared name %s" % v)
         raise Unsupported("unexpected token %r" % (v,))
@@ -370,6 +392,7 @@ class Unit:
         self.labels_used = set()
         self.stubs = set()
         self.formats = {}
+        self.implicit_none = False
         self.text_units = set()
         self.tmp = 0
 
@@ -459,6 +482,7 @@ def translate_unit(name, args, stmts, defines, known_subs):
             u.declare(m.group(1), m.group(2))
             continue
         if up.startswith("IMPLICIT"):
+            u.implicit_none = True
             continue
         exe.append((lab, txt, no))
     for lab, txt, no in exe:
@@ -579,6 +603,9 @@ def translate_unit(name, args, stmts, defines, known_subs):
                 return "{ if (!f77_fbegin(%s, \"%s\", 0)) { %s } %s if (!f77_fend(%s)) { %s } }" % (unit, fmt, fail, " ".join(body), unit, fail)
             if kind == "READ":
                 at_end = ("if (f77_eof(%s)) goto L%s; " % (unit, endl)) if endl else ""
+                if "IOSTAT" in kv:
+                    ios = u.cexpr(kv["IOSTAT"])[0]
+                    return "{ %s = 0; if (f77_eof(%s)) { %s = -1; } else { if (!f77_rbegin(%s)) { %s } %s } }" % (ios, unit, ios, unit, fail, " ".join(body))
                 return "{ %sif (!f77_rbegin(%s)) { %s } %s }" % (at_end, unit, fail, " ".join(body))
             return "{ f77_wbegin(%s); %s if (!f77_wend(%s)) { %s } }" % (unit, " ".join(body), unit, fail)
         m = re.match(r"^OPEN\s*\((.*)\)\s*$", txt, re.I | re.S)
@@ -608,8 +635,18 @@ def translate_unit(name, args, stmts, defines, known_subs):
         m = re.match(r"^REWIND\s*\(?\s*(\w+)\s*\)?\s*$", txt, re.I)
         if m:
             return "f77_rewind(%s);" % u.cstr(m.group(1), "i")
-        if re.match(r"^(INQUIRE|BACKSPACE)\b", up):
+        if re.match(r"^BACKSPACE\b", up):
             raise Unsupported("file I/O: %s" % up[:20])
+        m = re.match(r"^INQUIRE\s*\((.*)\)\s*$", txt, re.I | re.S)
+        if m:
+            kv = dict((c.split("=", 1)[0].strip().upper(), c.split("=", 1)[1].strip()) for c in split_top(m.group(1)) if "=" in c)
+            if "FILE" not in kv or "EXIST" not in kv:
+                raise Unsupported("INQUIRE form")
+            f = u.cexpr(kv["FILE"])
+            return "%s = f77_exists(%s);" % (u.cexpr(kv["EXIST"])[0], f[0])
+        m = re.match(r"^CALL\s+SYSTEM\s*\((.*)\)\s*$", txt, re.I | re.S)
+        if m:
+            return "f77_system(%s);" % u.cexpr(m.group(1))[0]
         m = re.match(r"^CALL\s+(\w+)\s*\((.*)\)\s*$", txt, re.I | re.S)
         if m:
             callee = m.group(1).upper()
@@ -650,6 +687,26 @@ def translate_unit(name, args, stmts, defines, known_subs):
         if eq is None:
             raise Unsupported("statement %r" % txt[:40])
         lhs = u.cexpr(toks[:eq])
+        if any(k == "op" and v == "//" for k, v in toks[eq + 1:]):
+            parts, cur, depth = [], [], 0
+            for k, v in toks[eq + 1:]:
+                if k == "op" and v == "(":
+                    depth += 1
+                if k == "op" and v == ")":
+                    depth -= 1
+                if k == "op" and v == "//" and depth == 0:
+                    parts.append(cur)
+                    cur = []
+                else:
+                    cur.append((k, v))
+            parts.append(cur)
+            code = "{ static char cat_[4096]; size_t n_ = 0; "
+            for pt in parts:
+                e = u.cexpr(pt)
+                if e[1] != "c":
+                    raise Unsupported("concatenation of a non-character operand")
+                code += "n_ = f77_cat(cat_, n_, %s); " % e[0]
+            return code + "f77_assign(%s, cat_, n_); }" % lhs[0]
         rhs = u.cexpr(toks[eq + 1:])
         if lhs[1] == "c" and rhs[1] == "c":
             return "f77_assign(%s, %s);" % (lhs[0], rhs[0])
@@ -801,6 +858,10 @@ static float f77_powi_f(float x, int m) { unsigned n = m < 0 ? -(unsigned)m : (u
 #include <stdio.h>
 #include <string.h>
 static FILE *f77_fp[100]; static int f77_wr[100]; static unsigned char *f77_buf[100]; static size_t f77_len[100], f77_pos[100], f77_cap[100];
+static int f77_index(const char *s, size_t ls, const char *t, size_t lt) { if (lt == 0 || lt > ls) return 0; for (size_t i = 0; i + lt <= ls; ++i) if (memcmp(s + i, t, lt) == 0) return (int)i + 1; return 0; }
+static size_t f77_cat(char *buf, size_t n, const char *s, size_t ls) { if (n + ls > 4096) ls = 4096 - n; memcpy(buf + n, s, ls); return n + ls; }
+static int f77_exists(const char *s, size_t ls) { char p[1024]; while (ls > 0 && s[ls - 1] == ' ') --ls; if (ls >= sizeof p) return 0; memcpy(p, s, ls); p[ls] = 0; FILE *f = fopen(p, "rb"); if (f) { fclose(f); return 1; } return 0; }
+static void f77_system(const char *s, size_t ls) { char p[4200]; while (ls > 0 && s[ls - 1] == ' ') --ls; if (ls >= sizeof p) return; memcpy(p, s, ls); p[ls] = 0; if (system(p)) {} }
 static void f77_assign(char *d, size_t ld, const char *s, size_t ls) { for (size_t i = 0; i < ld; ++i) d[i] = i < ls ? s[i] : ' '; }
 static int f77_cmp(const char *a, size_t la, const char *b, size_t lb) { size_t n = la > lb ? la : lb; for (size_t i = 0; i < n; ++i) { char ca = i < la ? a[i] : ' ', cb = i < lb ? b[i] : ' '; if (ca != cb) return ca < cb ? -1 : 1; } return 0; }
 static char f77_path[100][1024];

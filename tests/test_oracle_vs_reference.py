@@ -217,3 +217,34 @@ def test_sos_restatement_is_bit_identical_to_the_reference(pkg, orc, ref, a_trun
     if trans:
         assert sc[3].value == r.tdifmus
         assert np.array_equal(tdg[MX + 1:MX + N + 1], r.tdifmug[N + 1:])
+
+
+def test_aggregate_restatement_is_bit_identical_to_the_reference(pkg, orc, ref, tmp_path):
+    """SOS_AGGREGATE from the reference (file read-modify-write through a temporary file and `mv`), three CKD terms whose
+    Fourier series have different lengths, in an order that triggers the trailing all-zero record; records and the
+    scalar accumulators (incl. the -log(sum a exp(-tau)) aggregation of the optical depths) must equal the oracle's."""
+    syn, fm = pkg.synth, pkg.formats
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import oracle_term
+    o = syn.make_optics(nb_gauss=8, tetas=35.0, os_nb=16, surface="lambert", rho=0.1)
+    N = o.nbmu
+    terms = [syn.Term(0, a, *syn.profile(0.05, 8.0, aer, 2.0, gas)) for a, aer, gas in ((0.2, 0.25, 0.02), (0.5, 0.0, 0.5), (0.3, 0.25, 3.0))]
+    rs = [oracle_term(orc, o, t) for t in terms]
+    assert len({r.n_fourier for r in rs}) > 1                      # ragged series lengths
+    agg = orc.Aggregate(N, o.os_nb + 4)
+    fres, ftmp, fagg = str(tmp_path / "SOS_Result.bin"), str(tmp_path / "OS_TMP.bin"), str(tmp_path / "AGG_TMP.bin")
+    acc = [C.c_double(0) for _ in range(6)]                        # ttot_tronc, ttot_vrai, tauout, tdifmus, emoins, eplus
+    tdg_tmp, tdg = np.zeros(2 * MX + 1), np.zeros(2 * MX + 1)
+    for t, r in zip(terms, rs):
+        fm.write_result_bin(ftmp, r.rec)
+        ier = C.c_int(0)
+        ref.sos_aggregate_(_ip(N), _dp(t.aik), _fs(ftmp), _dp(r.ttot_tronc), _dp(r.ttot_vrai), _dp(r.tauout), _dp(0.0), _P(tdg_tmp),
+                           _dp(r.emoins), _dp(r.eplus), _fs(fagg), _fs(fres), C.byref(acc[0]), C.byref(acc[1]), C.byref(acc[2]),
+                           C.byref(acc[3]), _P(tdg), C.byref(acc[4]), C.byref(acc[5]), C.byref(ier), _L, _L, _L)
+        assert ier.value == 0
+        agg.add(t.aik, r)
+        res = fm.read_result_bin(fres, N)
+        assert res.shape[0] == agg.nres                            # incl. the reference's trailing zero record
+        assert np.array_equal(res, agg.res[:agg.nres])
+    assert acc[0].value == agg.sc["ttot_tronc"] and acc[1].value == agg.sc["ttot_vrai"] and acc[2].value == agg.sc["tauout"]
+    assert acc[4].value == agg.sc["emoins"] and acc[5].value == agg.sc["eplus"]
