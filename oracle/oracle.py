@@ -3,8 +3,9 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 legs may import this module.  The product path (radiativetransfer-sos_b200) never does.
 
-PARITY UNPINNED: the reference is Fortran 77, no Fortran compiler exists in this image and
-the reference ships no golden vectors for this path (see oracle/sos_oracle.h).
+PIN: bit-identical to oracle/_ref/libsosref.so, the reference's own Fortran sources translated mechanically to C
+(oracle/build_ref.py, tests/test_oracle_vs_reference.py); no Fortran compiler exists in this image and the reference
+ships no golden vectors, so a gfortran build is not part of the pin (see oracle/sos_oracle.h).
 """
 import ctypes as C
 import os

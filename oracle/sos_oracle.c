@@ -9,7 +9,8 @@
  * sub-expressions in single precision before promotion).
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math (no FMA contraction, no re-association).
  *
- * PARITY UNPINNED: no Fortran compiler / no golden vectors (see header).
+ * PIN: bit-identical to oracle/_ref (the reference's own source, mechanically translated; see sos_oracle.h);
+ * not checked against a gfortran build (no Fortran compiler, no golden vectors).
  */
 #include "sos_oracle.h"
 #include <math.h>

@@ -6,12 +6,18 @@
  * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
  * legs may load it.  The product library (libsosgpu.so) never links or calls it.
  *
- * PARITY UNPINNED: the reference is Fortran 77 and no Fortran compiler exists in
- * this image (nor on the GPU box), and the reference ships no golden vectors for
- * this path.  The oracle is therefore validated only by
+ * PARITY PIN: the reference is Fortran 77 and no Fortran compiler exists in this image (nor on the GPU box), and the
+ * reference ships no golden vectors for this path.  The pin is therefore the reference's own
+ * SOURCE run through a mechanical translation: oracle/build_ref.py + oracle/f77_to_c.py turn SOS.F, SOS_OS.F,
+ * SOS_AGGREGATE.F, SOS_TRPHI.F, SOS_GLITTER.F and SOS_SURFACE.F (31 of their 32 subroutines) into C with Fortran's typing
+ * rules and gfortran's record I/O, compiled into oracle/_ref/libsosref.so.  tests/test_oracle_vs_reference.py requires
+ * this restatement to equal that library BIT FOR BIT (records, loop counts, fluxes, optical depths, surface files, view
+ * tables, side effects).  What the pin does not cover is a gfortran BUILD of the same statements (libm is the same glibc;
+ * expression evaluation follows the same rules; tests/test_oracle.py bounds the effect of last-bit differences).
+ * Independent of any reading of the Fortran, the restatement is also checked against
  * (a) a second, independently written numpy formulation of the order-n source (tests/test_oracle.py),
  * (b) physics: flux conservation, reflection reciprocity per Fourier order, closed-form first-order scattering
- *     (scalar and polarized Rayleigh), and a scalar adding-doubling solver for the full multiple-scattering field.
+ *     (scalar and polarized Rayleigh), scalar and vector adding-doubling solvers for the full multiple-scattering field.
  *
  * Array conventions mirror the reference's Fortran arrays with the *useful*
  * extents instead of the compile-time caps of inc/SOS.h:

@@ -7,7 +7,7 @@
  *   SOS_NOYAUX_FRESNEL (:2029-2227), SOS_MISE_FORMAT (:2307-2443).
  * The temporary files of the reference are replaced by memory, but their lossy channels are kept:
  * RES_FRESNEL is written with 4(E15.8) (8 significant digits) and the M_ij are REAL*4.
- * PARITY UNPINNED (no Fortran compiler, no golden vectors).
+ * PIN: bit-identical to the translated reference chain in oracle/_ref (see sos_oracle.h); no gfortran build available.
  */
 #include "sos_oracle.h"
 #include <math.h>
