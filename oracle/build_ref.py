@@ -22,8 +22,10 @@ def build(force=False, verbose=True):
     src_dir, inc = os.path.join(REF, "src"), os.path.join(REF, "inc", "SOS.h")
     if not os.path.isdir(src_dir):
         return lib if os.path.exists(lib) else None
-    sys.path.insert(0, HERE)
-    import f77_to_c as t
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sos_f77_to_c", os.path.join(HERE, "f77_to_c.py"))
+    t = importlib.util.module_from_spec(spec)                   # by path: sys.path stays untouched
+    spec.loader.exec_module(t)
     srcs = [os.path.join(src_dir, f) for f in FILES]
     newest = max(os.path.getmtime(p) for p in srcs + [inc, os.path.join(HERE, "f77_to_c.py"), os.path.abspath(__file__)])
     if not force and os.path.exists(lib) and os.path.getmtime(lib) >= newest:

@@ -19,8 +19,10 @@ MX, NTM, NBM = 80, 600, 200
 
 @pytest.fixture(scope="module")
 def ref():
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    build_ref = importlib.import_module("build_ref")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sos_build_ref", os.path.join(ROOT, "oracle", "build_ref.py"))
+    build_ref = importlib.util.module_from_spec(spec)             # by path: oracle/ must not shadow the oracle package
+    spec.loader.exec_module(build_ref)
     lib = build_ref.build(verbose=False)
     if lib is None:
         pytest.skip("no /root/reference and no prebuilt oracle/_ref/libsosref.so")
