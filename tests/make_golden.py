@@ -1,4 +1,7 @@
-"""Generates tests/golden/oracle_small.npz from the C oracle (NOT from the reference: no Fortran compiler here).
+"""Generates tests/golden/oracle_small.npz from the C oracle.  tests/test_oracle_vs_reference.py
+(test_committed_golden_vectors_are_what_the_reference_produces) checks that the committed file equals, bit for bit, what
+the reference's own SOS produces when run from oracle/_ref (the Fortran sources translated to C), so the fixtures are
+reference-generated vectors in content even though no Fortran compiler exists here.
 Run: python tests/make_golden.py"""
 import importlib
 import os

@@ -250,3 +250,38 @@ def test_aggregate_restatement_is_bit_identical_to_the_reference(pkg, orc, ref, 
         assert np.array_equal(res, agg.res[:agg.nres])
     assert acc[0].value == agg.sc["ttot_tronc"] and acc[1].value == agg.sc["ttot_vrai"] and acc[2].value == agg.sc["tauout"]
     assert acc[4].value == agg.sc["emoins"] and acc[5].value == agg.sc["eplus"]
+
+
+def test_committed_golden_vectors_are_what_the_reference_produces(pkg, ref, tmp_path):
+    """tests/golden/oracle_small.npz (the fixtures the GPU parity tests use on a box that has no /root/reference) against
+    the reference's own SOS run here from oracle/_ref: identical record counts and identical bits."""
+    import importlib.util
+    syn, fm = pkg.synth, pkg.formats
+    spec = importlib.util.spec_from_file_location("sos_make_golden", os.path.join(ROOT, "tests", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "oracle_small.npz"))
+    for name, (o, t) in mg.cases(pkg).items():
+        N = o.nbmu
+        fprof, fos, fsurf = (str(tmp_path / (name + s)) for s in ("_PROFIL_TMP", "_OS.bin", "_SURF.bin"))
+        fm.write_profile(fprof, t.zprof, t.h, t.pcaer, t.pcmol)
+        back = fm.read_profile(fprof)
+        for a, b in zip(back, (t.zprof, t.h, t.pcaer, t.pcmol)):
+            assert np.array_equal(a, np.asarray(b))               # the synthetic profiles are exact in the file format
+        if o.imat_surf == 1:
+            fm.write_surface_bin(fsurf, o.surf)
+        rmu, ga = np.zeros(2 * MX + 1), np.zeros(2 * MX + 1)
+        rmu[MX - N:MX + N + 1], ga[MX - N:MX + N + 1] = o.rmu, o.ga
+        al, be, gm, ze = (_pad(v, NBM + 1) for v in (o.alpha, o.beta, o.gamma, o.zeta))
+        sc = [C.c_double(0) for _ in range(6)]
+        tdg = np.zeros(2 * MX + 1)
+        ier = C.c_int(99)
+        ref.sos_(_fs(fos), _fs("NO_OUTPUT"), _fs(fprof), _ip(t.nt), _dp(o.zout), _ip(o.igmax), _ip(o.ipolar), _dp(o.ron),
+                 _dp(o.ind_surf), _dp(o.rho), _ip(o.imat_surf), _ip(o.ifresnel), _fs(fsurf), _ip(o.n0), _dp(o.piz), _dp(o.piztr),
+                 _dp(o.a_trunc), _P(rmu), _P(ga), _dp(o.tetas), _ip(o.os_nb), _ip(N), _P(al), _P(be), _P(gm), _P(ze),
+                 C.byref(sc[0]), C.byref(sc[1]), C.byref(sc[2]), C.byref(sc[3]), _P(tdg), C.byref(sc[4]), C.byref(sc[5]),
+                 _ip(0), _ip(6), C.byref(ier), _L, _L, _L, _L)
+        assert ier.value == 0, name
+        rec = fm.read_result_bin(fos, N)
+        assert rec.shape[0] == int(gold[name + "_nf"]), name
+        assert np.array_equal(rec, gold[name + "_rec"]), name
