@@ -1,0 +1,176 @@
+"""Self-tests of oracle/f77_to_c.py: the Fortran semantics the pin of the oracle relies on (expression typing, integer
+division, integer powers, DO trip counts, array bounds and storage order, unformatted and formatted records), each on a
+tiny fixed-form routine translated, compiled and called here."""
+import ctypes as C
+import importlib.util
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def f77():
+    spec = importlib.util.spec_from_file_location("sos_f77_to_c", os.path.join(ROOT, "oracle", "f77_to_c.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def compile_fortran(f77, tmp_path, name, source):
+    src = tmp_path / (name + ".F")
+    src.write_text(source)
+    c, protos, report = f77.translate_file(str(src), {})
+    assert all(st == "ok" for _, st in report), report
+    csrc = tmp_path / (name + ".c")
+    csrc.write_text(f77.PRELUDE + "\n".join(protos) + "\n\n" + c)
+    lib = tmp_path / ("lib" + name + ".so")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", "-o", str(lib), str(csrc), "-lm"], check=True)
+    return C.CDLL(str(lib))
+
+
+def test_expression_typing_and_powers(f77, tmp_path):
+    lib = compile_fortran(f77, tmp_path, "typing", """
+      SUBROUTINE TYPING(IS,L,A,OUT,KOUT)
+      IMPLICIT NONE
+      INTEGER*4 IS,L,KOUT(4)
+      DOUBLE PRECISION A,OUT(10)
+      REAL R
+      OUT(1)=2.*IS/(L*(L+1.))
+      OUT(2)=0.1
+      OUT(3)=0.1D0
+      OUT(4)=A**2
+      OUT(5)=A**3
+      OUT(6)=A**(-2)
+      OUT(7)=A**(IS*0.5)
+      R=1./3.
+      OUT(8)=R
+      OUT(9)=R*A
+      OUT(10)=-A**2
+      KOUT(1)=7/2
+      KOUT(2)=(-7)/2
+      KOUT(3)=IS**3
+      KOUT(4)=2.9D0
+      RETURN
+      END
+""")
+    out, kout = np.zeros(10), np.zeros(4, dtype=np.int32)
+    a = 1.2345678901234567
+    lib.typing_(C.byref(C.c_int(3)), C.byref(C.c_int(7)), C.byref(C.c_double(a)), out.ctypes.data_as(C.POINTER(C.c_double)),
+                kout.ctypes.data_as(C.POINTER(C.c_int)))
+    f = np.float32
+    assert out[0] == float(f(2.0) * f(3) / (f(7) * (f(7) + f(1.0))))             # all-REAL*4 expression, single-precision divide
+    assert out[1] == float(f(0.1)) and out[2] == 0.1
+    assert out[3] == a * a and out[4] == a * (a * a)                           # libgcc __powidf2 chains
+    assert out[5] == 1.0 / (a * a)
+    assert out[6] == a ** float(f(3) * f(0.5))                                 # REAL exponent, promoted operand by operand
+    r = f(1.0) / f(3.0)
+    assert out[7] == float(r) and out[8] == float(r) * a
+    assert out[9] == -(a * a)                                                  # unary minus binds looser than **
+    assert list(kout) == [3, -3, 27, 2]
+
+
+def test_do_loops_arrays_and_records(f77, tmp_path):
+    lib = compile_fortran(f77, tmp_path, "loops", """
+      SUBROUTINE LOOPS(N,A,KOUT,FIC,IER)
+      IMPLICIT NONE
+      INTEGER*4 N,KOUT(6),IER,I,J,M,CNT
+      DOUBLE PRECISION A(-2:2,0:3),B(-2:2,0:3),X(4)
+      CHARACTER*200 FIC
+      IER=0
+      CNT=0
+      M=N
+      DO 10 I=1,M
+         M=M+5
+         CNT=CNT+1
+ 10   CONTINUE
+      KOUT(1)=CNT
+      KOUT(2)=I
+      CNT=0
+      DO I=10,1,-3
+         CNT=CNT+1
+      ENDDO
+      KOUT(3)=CNT
+      KOUT(4)=I
+      CNT=0
+      DO I=5,1
+         CNT=CNT+1
+      ENDDO
+      KOUT(5)=CNT
+      DO 20 J=0,3
+      DO 20 I=-2,2
+         IF (I.EQ.0) GOTO 20
+         A(I,J)=10.D0*J+I
+ 20   CONTINUE
+      OPEN(UNIT=11,FILE=FIC,FORM='UNFORMATTED',ERR=900)
+      WRITE(11,err=900) ((A(I,J),I=-2,2),J=0,3),N
+      WRITE(11,err=900) (A(I,1),I=2,-2,-1)
+      CLOSE(11)
+      OPEN(UNIT=11,FILE=FIC,FORM='UNFORMATTED',STATUS='OLD',ERR=900)
+      READ(11,err=900) ((B(I,J),I=-2,2),J=0,3),M
+      READ(11,err=900) (X(I),I=1,4)
+      CLOSE(11)
+      KOUT(6)=M
+      DO J=0,3
+         DO I=-2,2
+            IF (B(I,J).NE.A(I,J)) IER=-1
+         ENDDO
+      ENDDO
+      IF (X(1).NE.A(2,1)) IER=-2
+      IF (X(4).NE.A(-1,1)) IER=-3
+      RETURN
+ 900  IER=-9
+      RETURN
+      END
+""")
+    a = np.full(20, -1.0)
+    kout = np.zeros(6, dtype=np.int32)
+    ier = C.c_int(5)
+    fic = str(tmp_path / "rec.bin")
+    lib.loops_(C.byref(C.c_int(4)), a.ctypes.data_as(C.POINTER(C.c_double)), kout.ctypes.data_as(C.POINTER(C.c_int)),
+               C.create_string_buffer(fic.encode().ljust(200), 200), C.byref(ier), C.c_size_t(200))
+    assert ier.value == 0
+    assert list(kout) == [4, 5, 4, -2, 0, 4]          # trip counts fixed at entry; DO variable after the loop; zero-trip loop
+    ref = np.full((4, 5), -1.0)                       # [J][I+2]: column-major, first index fastest
+    for j in range(4):
+        for i in range(-2, 3):
+            if i != 0:
+                ref[j, i + 2] = 10.0 * j + i
+    assert np.array_equal(a.reshape(4, 5), ref)
+    raw = open(fic, "rb").read()
+    assert np.frombuffer(raw, dtype=np.int32, count=1)[0] == 20 * 8 + 4        # gfortran record marker of the first record
+
+
+def test_formatted_e15_8_round_trip(f77, pkg, tmp_path):
+    lib = compile_fortran(f77, tmp_path, "fmt", """
+      SUBROUTINE FMT(V,W,FIC,IER)
+      IMPLICIT NONE
+      DOUBLE PRECISION V(4),W(4)
+      INTEGER*4 IER,K
+      CHARACTER*200 FIC
+      IER=0
+      OPEN(UNIT=3,FILE=FIC,ERR=900)
+      WRITE(3,207,err=900) V(1),V(2),V(3),V(4)
+      CLOSE(3)
+      OPEN(UNIT=3,FILE=FIC,STATUS='OLD',ERR=900)
+      READ(3,207,err=900) W(1),W(2),W(3),W(4)
+      CLOSE(3)
+      RETURN
+ 900  IER=-1
+      RETURN
+ 207  FORMAT(4(E15.8))
+      END
+""")
+    v = np.array([0.123456789012, -3.14159265358979e-7, 0.0, 9.99999999e12])
+    w = np.zeros(4)
+    ier = C.c_int(9)
+    fic = str(tmp_path / "fresnel.txt")
+    lib.fmt_(v.ctypes.data_as(C.POINTER(C.c_double)), w.ctypes.data_as(C.POINTER(C.c_double)),
+             C.create_string_buffer(fic.encode().ljust(200), 200), C.byref(ier), C.c_size_t(200))
+    assert ier.value == 0
+    fm = pkg.formats
+    assert open(fic).read() == "".join(fm.fortran_e(x, 15, 8) for x in v) + "\n"
+    assert np.array_equal(w, fm.round_e(v, 8))
