@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("SOS_REFERENCE_ROOT", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
-FILES = ["SOS_OS.F", "SOS.F", "SOS_AGGREGATE.F", "SOS_TRPHI.F", "SOS_GLITTER.F", "SOS_SURFACE.F"]
+FILES = ["SOS_OS.F", "SOS.F", "SOS_AGGREGATE.F", "SOS_TRPHI.F", "SOS_GLITTER.F", "SOS_SURFACE.F", "SOS_ANGLES.F"]
 
 
 def build(force=False, verbose=True):

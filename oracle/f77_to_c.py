@@ -320,7 +320,7 @@ class Parser:
                 return (self.u.scalar_ref(v), self.u.vars[v]["type"])
             if not self.u.implicit_none and not self.at("("):
                 # Fortran implicit typing: I-N integer, otherwise REAL
-                self.u.vars[v] = {"type": "i" if v[0] in "IJKLMN" else "r", "dims": [], "clen": "1"}
+                self.u.vars[v] = {"type": self.u.implicit[v[0]], "dims": [], "clen": "1"}
                 return (self.u.scalar_ref(v), self.u.vars[v]["type"])
             raise Unsupported("undeclared name %s" % v)
         raise Unsupported("unexpected token %r" % (v,))
@@ -393,6 +393,7 @@ class Unit:
         self.stubs = set()
         self.formats = {}
         self.implicit_none = False
+        self.implicit = {ch: ("i" if ch in "IJKLMN" else "r") for ch in "ABCDEFGHIJKLMNOPQRSTUVWXYZ"}
         self.text_units = set()
         self.tmp = 0
 
@@ -475,6 +476,7 @@ def translate_unit(name, args, stmts, defines, known_subs):
     out = []
     # pass 1: declarations
     exe = []
+    pending_dims = []
     for lab, txt, no in stmts:
         up = txt.upper()
         m = TYPE_RE.match(txt)
@@ -482,7 +484,28 @@ def translate_unit(name, args, stmts, defines, known_subs):
             u.declare(m.group(1), m.group(2))
             continue
         if up.startswith("IMPLICIT"):
-            u.implicit_none = True
+            if re.match(r"^IMPLICIT\s+NONE", up):
+                u.implicit_none = True
+                continue
+            m2 = re.match(r"^IMPLICIT\s+(DOUBLE\s*PRECISION|REAL\s*\*\s*8|REAL|INTEGER(?:\s*\*\s*4)?|LOGICAL)\s*\((.*)\)\s*$", up)
+            if not m2:
+                raise Unsupported("IMPLICIT form: %s" % up)
+            tt = "d" if (m2.group(1).startswith("DOUBLE") or m2.group(1).replace(" ", "") == "REAL*8") else ("r" if m2.group(1).startswith("REAL") else ("i" if m2.group(1).startswith("INTEGER") else "l"))
+            for rng in m2.group(2).split(","):
+                a, _, b = rng.strip().partition("-")
+                for o_ in range(ord(a.strip()), ord((b or a).strip()) + 1):
+                    u.implicit[chr(o_)] = tt
+            continue
+        m2 = re.match(r"^PARAMETER\s*\((.*)\)\s*$", txt, re.I | re.S)
+        if m2:
+            for item in split_top(m2.group(1)):
+                k, v = item.split("=", 1)
+                u.defines = dict(u.defines)
+                u.defines[k.strip().upper()] = "(" + v.strip() + ")"
+            continue
+        m2 = re.match(r"^DIMENSION\s+(.*)$", txt, re.I | re.S)
+        if m2:
+            pending_dims.append(m2.group(1))
             continue
         exe.append((lab, txt, no))
     for lab, txt, no in exe:
@@ -496,9 +519,19 @@ def translate_unit(name, args, stmts, defines, known_subs):
                     u.text_units.add(c.split("=", 1)[1].strip())
                 elif "=" not in c:
                     u.text_units.add(c.strip())
+    for text in pending_dims:                                     # DIMENSION with implicit typing
+        for item in split_top(text):
+            nm = item.split("(")[0].strip().upper()
+            if nm in u.vars:
+                t0 = {"d": "DOUBLE PRECISION", "r": "REAL", "i": "INTEGER", "l": "LOGICAL"}[u.vars[nm]["type"]]
+            else:
+                t0 = {"d": "DOUBLE PRECISION", "r": "REAL", "i": "INTEGER", "l": "LOGICAL"}[u.implicit[nm[0]]]
+            u.declare(t0, item)
     for a in args:
         if a not in u.vars:
-            raise Unsupported("argument %s has no declaration" % a)
+            if u.implicit_none:
+                raise Unsupported("argument %s has no declaration" % a)
+            u.vars[a] = {"type": u.implicit[a[0]], "dims": [], "clen": "1"}
     has_char = any(u.vars[a]["type"] == "c" for a in args)
     # DO-loop bookkeeping
     do_stack = []          # (terminal label or None)
@@ -674,7 +707,7 @@ def translate_unit(name, args, stmts, defines, known_subs):
                     cargs.append("&" + tmp)
             return "{ %s %s_(%s); }" % (" ".join(pre), callee.lower(), ", ".join(cargs + hidden))
         # assignment
-        toks = tokenize(txt, defines)
+        toks = tokenize(txt, u.defines)
         depth, eq = 0, None
         for i, (k, v) in enumerate(toks):
             if k == "op" and v == "(":
@@ -747,6 +780,8 @@ def translate_unit(name, args, stmts, defines, known_subs):
                 if len(parts) not in (2, 3):
                     raise Unsupported("DO bounds")
                 var = m.group(2).upper()
+                if var not in u.vars and not u.implicit_none:
+                    u.vars[var] = {"type": u.implicit[var[0]], "dims": [], "clen": "1"}
                 if var not in u.vars or u.vars[var]["type"] != "i":
                     raise Unsupported("DO variable %s" % var)
                 e1, e2 = u.cstr(parts[0], "i"), u.cstr(parts[1], "i")

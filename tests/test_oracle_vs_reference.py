@@ -285,3 +285,15 @@ def test_committed_golden_vectors_are_what_the_reference_produces(pkg, ref, tmp_
         rec = fm.read_result_bin(fos, N)
         assert rec.shape[0] == int(gold[name + "_nf"]), name
         assert np.array_equal(rec, gold[name + "_rec"]), name
+
+
+def test_gauss_angles_of_the_input_generator_equal_the_reference(pkg, ref):
+    """SOS_GAUSS (SOS_ANGLES.F:1022-1103) from the reference against synth.sos_gauss, which produces the Gauss angles and
+    weights of every synthetic workload (tests and bench)."""
+    for mm in (5, 13, 25, 41):
+        mxa = 100                                                    # CTE_NBANGLES_MAX (SOS.h:555)
+        amu, pmu = np.zeros(2 * mxa + 1), np.zeros(2 * mxa + 1)
+        ref.sos_gauss_(_ip(mm), _P(amu), _P(pmu))
+        mu, w = pkg.synth.sos_gauss(mm)
+        got_mu, got_w = amu[mxa + 1:mxa + mm], pmu[mxa + 1:mxa + mm]
+        assert np.array_equal(np.asarray(mu), got_mu) and np.array_equal(np.asarray(w), got_w), mm
