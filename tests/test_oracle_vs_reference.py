@@ -297,3 +297,33 @@ def test_gauss_angles_of_the_input_generator_equal_the_reference(pkg, ref):
         mu, w = pkg.synth.sos_gauss(mm)
         got_mu, got_w = amu[mxa + 1:mxa + mm], pmu[mxa + 1:mxa + mm]
         assert np.array_equal(np.asarray(mu), got_mu) and np.array_equal(np.asarray(w), got_w), mm
+
+
+def test_random_configurations_bit_identical(pkg, orc, ref, tmp_path):
+    """Seeded random sweep (angles, expansion order, surface type, albedo, flat-sea flag, polarization switch, output
+    altitude, solar angle, IGMAX, aerosol and gas loads): the restatement and the reference agree on every bit."""
+    syn, fm = pkg.synth, pkg.formats
+    rng = np.random.default_rng(12345)
+    for it in range(12):
+        nbg = int(rng.choice([4, 6, 8, 12, 16, 24]))
+        os_nb = int(rng.choice([8, 12, 16, 24, 40]))
+        surface = str(rng.choice(["lambert", "brdf", "lambert"]))
+        rho = float(rng.choice([0.0, 0.05, 0.3, 0.8]))
+        ifr = int(rng.random() < 0.25) if surface == "lambert" else 0
+        ipolar = int(rng.random() < 0.8)
+        zout = float(rng.choice([-1.0, -1.0, 0.0, 1.7, 10.0, 55.5]))
+        tetas = float(rng.uniform(5, 80))
+        igmax = int(rng.choice([100, 100, 3, 7]))
+        o = syn.make_optics(nb_gauss=nbg, tetas=tetas, os_nb=os_nb, surface=surface, rho=rho, zout=zout, ipolar=ipolar,
+                            igmax=igmax, seed=it)
+        aer, gas = float(rng.choice([0.0, 0.05, 0.3, 1.0])), float(rng.choice([0.0, 0.1, 2.0, 10.0]))
+        z, h, xa, ym = syn.profile(float(rng.uniform(0.01, 0.3)), 8.0, aer, 2.0, gas)
+        xd = np.array(xa) * o.piztr
+        iborm = 2 if aer == 0.0 else o.os_nb
+        surf = o.surf if o.imat_surf == 1 else None
+        r = orc.sos_os(o.nbmu, o.rmu.copy(), o.ga, o.os_nb, len(h) - 1, o.n0, o.tetas, o.rho, o.imat_surf, ifr, o.ind_surf, h, xd,
+                       ym, z, o.ron, o.alpha.copy(), o.beta, o.gamma.copy(), o.zeta.copy(), o.zout, o.igmax, iborm, o.ipolar, surf)
+        f = run_reference_sos_os(ref, fm, o, h, xd, ym, z, iborm, str(tmp_path), surf=surf, ifresnel=ifr, zout=o.zout)
+        assert f["ier"] == r.ier, it
+        assert f["rec"].shape[0] == r.n_fourier and np.array_equal(f["rec"], r.rec), it
+        assert f["emoins"] == r.emoins and f["eplus"] == r.eplus, it
