@@ -3,18 +3,28 @@
 reference is written in to C, so that the reference's OWN source of the hot-path routines can be compiled and run in
 an image that has no Fortran compiler (oracle/build_ref.py drives it; outputs go to oracle/_ref/, never into the
 repository history).  It exists to pin oracle/sos_oracle.c: every restated routine is compared bit for bit with the
-translation of the routine it restates (tests/test_oracle_vs_reference.py).
+translation of the routine it restates (tests/test_oracle_vs_reference.py); tests/test_f77_translator.py checks the
+translator's own semantics on tiny routines.
 
 What is implemented is what those routines use, with Fortran's own semantics where they differ from C's:
-  * cpp-style #include / object-like #define (inc/SOS.h), fixed-form continuation, labels, '!' comments;
-  * INTEGER*4 / REAL / DOUBLE PRECISION / LOGICAL scalars and arrays with arbitrary bounds, column-major;
-    all dummy arguments by reference; local arrays static (gfortran places them in zeroed .bss);
+  * cpp-style #include / object-like #define (inc/SOS.h), PARAMETER, fixed-form continuation and tab form, labels,
+    '!' comments, statements beyond column 72;
+  * INTEGER*4 / REAL / DOUBLE PRECISION / LOGICAL / CHARACTER*n scalars, arrays with arbitrary bounds (column-major),
+    IMPLICIT NONE or implicit typing (default and IMPLICIT <type> (ranges)), DIMENSION; all dummy arguments by reference
+    with hidden CHARACTER lengths after the argument list (gfortran ABI); local arrays static (gfortran places them in
+    zeroed .bss);
   * expression typing by Fortran's rules: REAL*4 literals and all-REAL*4 sub-expressions are evaluated in single
     precision, mixed operands are promoted operand by operand, integer division truncates, x**n with an integer n is
-    libgcc's __powidf2 / __powisf2 multiplication chain, x**y otherwise pow / powf;
-  * DO loops with the iteration count fixed at entry (labelled or ENDDO), block and logical IF, GOTO, CONTINUE, CALL,
-    RETURN; WRITE / FORMAT are dropped (trace and error messages only in the routines translated).
-Anything else raises Unsupported and the routine is skipped (reported by build_ref.py).
+    libgcc's __powidf2 / __powisf2 multiplication chain, x**y otherwise pow / powf; generic and specific intrinsics;
+  * DO loops with the iteration count fixed at entry (labelled, shared terminal labels, ENDDO), DO WHILE, block and
+    logical IF, GOTO, CONTINUE, CALL (temporaries for expression arguments), RETURN;
+  * I/O as gfortran does it: unformatted sequential records with 4-byte markers (implied DO lists, whole arrays, ERR=,
+    END=, IOSTAT=), formatted records on files opened in the routine (nX, Iw, Fw.d, Ew.d, Dw.d, repeat groups, format
+    reversion), OPEN (STATUS OLD / NEW / UNKNOWN), CLOSE (STATUS='DELETE'), REWIND, INQUIRE(FILE=, EXIST=);
+    trace / message WRITEs (list-directed or to units not opened in the routine) are dropped;
+  * CHARACTER: comparison with blank padding, assignment, substrings, //, INDEX, CALL SYSTEM.
+Calls of routines that are not among the translated files abort at run time (they are outside the hot path).
+Anything else raises Unsupported and the routine is skipped (reported in oracle/_ref/translation_report.txt).
 """
 import re
 import sys
