@@ -14,7 +14,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("SOS_REFERENCE_ROOT", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
-FILES = ["SOS_OS.F", "SOS.F", "SOS_AGGREGATE.F", "SOS_TRPHI.F", "SOS_GLITTER.F", "SOS_SURFACE.F", "SOS_ANGLES.F"]
+# hot path + the input generator's Gauss angles + the "next" rows N1 / N2 of section 8(f), whose
+# reference routines are then available to future parity tests (and make SOS_TRPHI's Roujean / BPDF branches callable)
+FILES = ["SOS_OS.F", "SOS.F", "SOS_AGGREGATE.F", "SOS_TRPHI.F", "SOS_GLITTER.F", "SOS_SURFACE.F", "SOS_ANGLES.F",
+         "SOS_ROUJEAN.F", "SOS_SURFACE_BPDF.F", "SOS_PROFIL.F", "SOS_ABSPROFILE.F"]
 
 
 def build(force=False, verbose=True):
@@ -36,6 +39,9 @@ def build(force=False, verbose=True):
     known = set()
     for p in srcs:
         known |= t.subroutine_names(p)
+    for p in srcs:                                              # first pass: which routines translate at all
+        _, _, rep = t.translate_file(p, defines, known=known)
+        known -= {name for name, st in rep if st != "ok"}        # calls of skipped routines become run-time aborts
     for p in srcs:
         c, pr, rep = t.translate_file(p, defines, known=known)
         protos += pr
