@@ -118,23 +118,29 @@ def cpu_baseline(wl, budget_s=20.0, max_threads=None):
             "term_solves_per_s": len(ids) / dt}
 
 
-def cpu_baseline_reference(wl, points_per_core=1):
+def cpu_baseline_reference(wl, points_per_core=3):
     """Times the reference's own flow (SOS -> SOS_OS -> SOS_AGGREGATE, with its files) from oracle/_ref/libsosref.so =
     the reference's Fortran sources translated to C by oracle/f77_to_c.py (no Fortran compiler exists here), on a
-    bounded sample of whole spectral points, one process per host core."""
+    bounded sample of whole spectral points.  One process per host core; TERM-solves are distributed over the processes
+    (longest first, BASELINE.md section 3), the workers are warm before the clock starts.  value = wall-clock rate;
+    the occupancy rate (cores x points / sum of busy seconds) is reported beside it."""
     from oracle import ref_runner
     if not ref_runner.available():
         raise RuntimeError("oracle/_ref/libsosref.so is missing")
     cores = os.cpu_count() or 1
     npts = len({t.optics for t in wl.terms})
     ids = set(range(min(npts, max(1, cores * points_per_core))))
-    pts, nterm, dt = ref_runner.run_points(wl, ids, cores)
-    return {"value": pts / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": "%d spectral points (%d term-solves) of the same band in %.1f s through the reference's per-term flow "
-                      "(PROFIL_TMP -> SOS -> SOS_OS -> SOS_AGGREGATE, files included); reference Fortran translated to C by "
-                      "oracle/f77_to_c.py and compiled with gcc -O2 (no Fortran compiler available), one process per core"
-                      % (pts, nterm, dt),
-            "term_solves_per_s": nterm / dt}
+    r = ref_runner.run_points(wl, ids, cores)
+    wall_rate = r["points"] / r["wall"]
+    occ_rate = r["workers"] * r["points"] / r["busy_sum"]
+    return {"value": wall_rate, "unit": UNIT, "cores": r["workers"], "kind": "reference",
+            "sample": "%d spectral points (%d term-solves) of the same band in %.1f s wall through the reference's per-term flow "
+                      "(PROFIL_TMP -> SOS -> SOS_OS, then SOS_AGGREGATE, files included); term-solves spread over %d "
+                      "single-thread processes (longest first), workers warm before the clock; wall-based %.3f points/s, "
+                      "occupancy-based (cores x points / sum of busy seconds) %.3f points/s; reference Fortran translated "
+                      "to C by oracle/f77_to_c.py, gcc -O2 (no Fortran compiler available)"
+                      % (r["points"], r["terms"], r["wall"], r["workers"], wall_rate, occ_rate),
+            "term_solves_per_s": r["terms"] / r["wall"], "occupancy_value": occ_rate}
 
 
 def run_reference(args, rank, world):
@@ -321,9 +327,11 @@ def main():
     if rank == 0:
         peak = dgemm_peak(torch, dev)
         achieved = st_acc["flops"] / (st_acc["step_ms"] * 1e-3) / 1e12 if st_acc["step_ms"] > 0 else 0.0
-        if world == 1:                                 # the CPU leg is timed at N=1 only
+        if os.environ.get("SOS_BENCH_NOCPU"):              # kernel-tuning runs: skip the CPU leg
+            cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "skipped (SOS_BENCH_NOCPU)"}
+        elif world == 1:                               # the CPU leg is timed at N=1 only
             try:
-                cb = cpu_baseline_reference(make_workload(POINTS_PER_GPU), points_per_core=1)
+                cb = cpu_baseline_reference(make_workload(POINTS_PER_GPU))
             except Exception as e1:
                 try:
                     cb = cpu_baseline(make_workload(POINTS_PER_GPU), budget_s=15.0)

@@ -111,6 +111,10 @@ __device__ __forceinline__ void slab_mma(double (&acc)[2][8][2], double (&tacc)[
   }
 }
 
+// EXPERIMENT (SOS_DBG & 1024): one "main loop" token per SM in global memory -- the two co-resident CTAs take turns in
+// the DMMA main loop, so that one CTA's recurrence epilogue always runs under the other's main loop (anti-phase).
+__device__ unsigned g_sm_token[256];
+
 template <int LR, int ORDER1>
 __global__ void __launch_bounds__(256, 2)
 k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, const OpticsDev *__restrict__ optics,
@@ -243,7 +247,7 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
   unsigned it_count = 0;                                          // global slab counter (mbarrier phases)
 
 #ifdef SOS_PHASE_TIMING   // build with -DSOS_PHASE_TIMING and run with SOS_DBG=16: cycles per phase as seen by thread 0
-  long long tph[5] = {0, 0, 0, 0, 0}, tmark = clock64();
+  long long tph[6] = {0, 0, 0, 0, 0, 0}, tmark = clock64();
   const long long tstart = tmark;
 #define TPH(i) do { if (dbg & 16) { const long long now_ = clock64(); tph[i] += now_ - tmark; tmark = now_; } } while (0)
 #else
@@ -288,6 +292,15 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       if (tid == 0) {
         for (int s = 0; s < SOS_STAGES - 1 && s < n_slab; ++s) issue(s, it_count + s);
       }
+      if (dbg & 1024) {
+        if (tid == 0) {
+          unsigned smid;
+          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+          while (atomicCAS(&g_sm_token[smid], 0u, 1u) != 0u) __nanosleep(64);
+        }
+        __syncthreads();
+      }
+      TPH(5);
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -330,6 +343,11 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
       }
       it_count += n_slab;
       __syncthreads();                                             // pipeline drained: stages may be reused as sJ
+      if ((dbg & 1024) && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        atomicExch(&g_sm_token[smid], 0u);
+      }
       TPH(0);
       mbar_wait(tabbar, chunk & 1);                                // XDEL/YDEL and layer tables of this chunk have landed
       if (LR && gq < 4) {
@@ -530,8 +548,8 @@ k_step(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, con
   }
 #ifdef SOS_PHASE_TIMING
   if ((dbg & 16) && tid == 0 && (blockIdx.x % 997) == 0)
-    printf("cta %d chunks %d: mainloop %lld store %lld pass1 %lld pass2 %lld writeout %lld total %lld\n", (int)blockIdx.x, n_chunk,
-           tph[0], tph[1], tph[2], tph[3], tph[4], clock64() - tstart);
+    printf("cta %d chunks %d slabs %d R %d: mainloop %lld store %lld pass1 %lld pass2 %lld writeout %lld token+restart %lld total %lld\n", (int)blockIdx.x, n_chunk,
+           n_slab, R, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], clock64() - tstart);
 #endif
 #undef TPH
 }

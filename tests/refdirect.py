@@ -1,0 +1,109 @@
+"""In-process calls into oracle/_ref/libsosref.so (the reference's own Fortran statements, translated to C by
+oracle/f77_to_c.py) for the GPU parity tests: SOS_GLITTER, SOS_TRPHI_OPTION, SOS_AGGREGATE, plus the multi-process
+term-solve runner.  TEST INFRASTRUCTURE: only tests/ and bench.py's CPU legs come here.
+
+On the GPU box /root/reference does not exist: the library is the prebuilt one that travels with the repository
+snapshot (oracle/_ref/ is git-ignored, not gpurun-ignored)."""
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MX, NTM, NBM = 80, 600, 200
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def runner():
+    return _load("sos_ref_runner", os.path.join(ROOT, "oracle", "ref_runner.py"))
+
+
+def lib():
+    """The reference library: built from /root/reference when that exists (this container), else the prebuilt file."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libsosref.so")
+    if os.path.isdir("/root/reference"):
+        build_ref = _load("sos_build_ref", os.path.join(ROOT, "oracle", "build_ref.py"))
+        path = build_ref.build(verbose=False) or path
+    if not os.path.exists(path):
+        return None
+    return C.CDLL(path)
+
+
+def _fs(s):
+    return C.create_string_buffer(s.encode().ljust(500), 500)
+
+
+_ip = lambda v: C.byref(C.c_int(int(v)))
+_dp = lambda v: C.byref(C.c_double(float(v)))
+_P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+_L = C.c_size_t(500)
+
+
+def _angles(o_rmu, o_ga, N):
+    rmu, ga = np.zeros(2 * MX + 1), np.zeros(2 * MX + 1)
+    rmu[MX - N:MX + N + 1], ga[MX - N:MX + N + 1] = o_rmu, o_ga
+    return rmu, ga
+
+
+def glitter(ref, fm, tmp, N, rmu, ga, wind, ind, os_nb, os_ns, os_nm):
+    """SOS_GLITTER (SOS_GLITTER.F:229) through its files -> REAL*4 records [os_nb+1][9][N][N]."""
+    r, g = _angles(rmu, ga, N)
+    fgl = os.path.join(tmp, "GLITTER.bin")
+    if os.path.exists(fgl):
+        os.remove(fgl)
+    ier = C.c_int(99)
+    ref.sos_glitter_(_ip(N), _P(r), _P(g), _dp(wind), _dp(ind), _ip(os_nb), _ip(os_ns), _ip(os_nm), _fs(os.path.join(tmp, "GSF")),
+                     _fs(os.path.join(tmp, "FRESNEL")), _fs(os.path.join(tmp, "MAT_REFLEX")), _fs(fgl), _ip(0), C.byref(ier),
+                     _L, _L, _L, _L)
+    assert ier.value == 0, "reference SOS_GLITTER IER=%d" % ier.value
+    return fm.read_surface_bin(fgl, N)
+
+
+def trphi_option(ref, fm, tmp, rec, N, rmu, ga, tau, tauout, igli, n0, wind, ind, ifresnel, itrphi, phios, pas, ipolar=1,
+                 roujean=None, bpdf=None):
+    """SOS_TRPHI_OPTION (SOS_TRPHI.F:285) on a result file -> (nphi, phi, theta, up[7][nphi][N], down[7][nphi][N]).
+    roujean = (k0, k1, k2); bpdf = dict(irondeaux=, ibreon=, inadal=, alpha=, beta=, imaignan=, coef=)."""
+    fos = os.path.join(tmp, "TRPHI_Result.bin")
+    fm.write_result_bin(fos, rec)
+    r, g = _angles(rmu, ga, N)
+    pf, th = np.zeros(361), np.zeros(MX + 1)
+    tabs = [np.zeros((MX + 1, 361)) for _ in range(14)]
+    ier = C.c_int(99)
+    k0, k1, k2 = roujean if roujean else (0.0, 0.0, 0.0)
+    b = dict(irondeaux=0, ibreon=0, inadal=0, alpha=0.0, beta=0.0, imaignan=0, coef=0.0)
+    b.update(bpdf or {})
+    ref.sos_trphi_option_(_ip(N), _P(r), _P(g), _fs(fos), _dp(tau), _dp(tauout), _dp(-1.0), _ip(igli), _ip(n0), _dp(wind), _dp(ind),
+                          _ip(ifresnel), _ip(1 if roujean else 0), _dp(k0), _dp(k1), _dp(k2), _ip(b["irondeaux"]), _ip(b["ibreon"]),
+                          _ip(b["inadal"]), _dp(b["alpha"]), _dp(b["beta"]), _ip(b["imaignan"]), _dp(b["coef"]), _ip(itrphi),
+                          _dp(phios), _ip(pas), _ip(ipolar), _P(pf), _P(th), *[_P(t) for t in tabs], C.byref(ier), _L)
+    assert ier.value == 0, "reference SOS_TRPHI_OPTION IER=%d" % ier.value
+    nphi = 2 if itrphi == 1 else 360 // pas + 1
+    up = np.array([tabs[t][:N, :nphi].T for t in range(7)])
+    down = np.array([tabs[7 + t][:N, :nphi].T for t in range(7)])
+    return nphi, pf[:nphi].copy(), th[:N].copy(), up, down
+
+
+def compare_terms(tr, res, ids, wl, assert_close, what):
+    """CUDA term results vs the reference's: returns (count mismatches, terms) after asserting nothing -- the caller
+    decides; Stokes are compared only where the counts agree."""
+    bad = []
+    for n, i in enumerate(ids):
+        r = res[i]
+        W = 2 * wl.optics[wl.terms[i].optics].nbmu + 1
+        nf = r["rec"].shape[0]
+        if tr.n_fourier[n] != nf:
+            bad.append((i, int(tr.n_fourier[n]), nf))
+            continue
+        assert_close(tr.rec[n, :nf, :, :W], r["rec"], "%s term %d records" % (what, i))
+        assert_close(tr.emoins[n], r["emoins"], "%s term %d EMOINS" % (what, i))
+        assert_close(tr.eplus[n], r["eplus"], "%s term %d EPLUS" % (what, i))
+        for k in ("ttot_tronc", "ttot_vrai", "tauout"):
+            assert getattr(tr, k)[n] == r[k], (what, i, k)
+    return bad

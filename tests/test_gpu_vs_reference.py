@@ -1,0 +1,122 @@
+"""GPU parity tests against the REFERENCE ITSELF (oracle/_ref/libsosref.so = the reference's Fortran statements translated
+to C), one per BASELINE.json config, without the hand restatement in between:
+
+  cfg1  demo:      N=41, OS_NB=80, 5 CKD terms, Lambert rho=0 + Cox-Munk glitter surface, View 1 (phi = 0 / 180)
+  cfg2  demoPolar: the same solve synthesised on View 2 (dphi = 30, 13 azimuths)
+  cfg3  CKD band:  the bench band, ALL 620 term-solves of the 96 spectral points
+  cfg4  hyperspectral sweep: 64 wavelengths at N=25 with a BRDF/BPDF surface matrix per wavelength
+  cfg5  angular stress: N=80 (CTE_OS_NBMU_MAX), OS_NB=200 (CTE_OS_NB_MAX), output at an altitude
+
+The whole chain runs on each side: for cfg1/2 the GPU-generated glitter file feeds the GPU solve and the
+reference-generated file feeds the reference solve.  Bar: number of Fourier orders identical, Stokes within 1e-9 relative
+(1e-12 floor); every test prints its count-mismatch tally (mismatches / terms)."""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+import refdirect
+from util import assert_stokes_close
+
+pytestmark = pytest.mark.gpu
+CORES = os.cpu_count() or 1
+
+
+@pytest.fixture(scope="module")
+def ref():
+    lib = refdirect.lib()
+    if lib is None:
+        pytest.fail("oracle/_ref/libsosref.so is missing: run __graft_entry__.build() where /root/reference exists")
+    return lib
+
+
+def _solve_both(pkg, solver, wl, ids=None):
+    ids = list(range(len(wl.terms))) if ids is None else list(ids)
+    rr = refdirect.runner()
+    res, wall, busy = rr.solve_terms(wl, ids, CORES)
+    b = solver.upload(wl, ids)
+    tr, gr = solver.run(b)
+    return ids, res, b, tr, gr
+
+
+def _tally(name, bad, n):
+    print("\n[count parity] %s: %d mismatches / %d term-solves %s" % (name, len(bad), n, bad[:5] if bad else ""))
+
+
+def test_cfg1_cfg2_demo_glitter_chain(pkg, solver, ref, tmp_path):
+    syn, fm = pkg.synth, pkg.formats
+    wl = syn.config_demo(nterm=5, nb_gauss=40, os_nb=80, surface="glitter")
+    o = wl.optics[0]
+    N, os_ns, os_nm = o.nbmu, 80, 160
+    assert N == 41 and o.rho == 0.0
+    # surface file: each side makes its own
+    surf_gpu, il = solver.glitter(N, o.rmu, o.ga, o.wind, o.ind_surf, o.os_nb, os_ns, os_nm)
+    surf_ref = refdirect.glitter(ref, fm, str(tmp_path), N, o.rmu, o.ga, o.wind, o.ind_surf, o.os_nb, os_ns, os_nm)
+    same = np.mean(surf_gpu.view(np.uint32) == surf_ref.view(np.uint32))
+    print("\n[glitter N=41] REAL*4 records bit-identical: %.4f %%, max |diff| / max %.2e"
+          % (100 * same, np.abs(surf_gpu - surf_ref).max() / np.abs(surf_ref).max()))
+    assert same > 0.999
+    wl_ref, wl_gpu = copy.deepcopy(wl), copy.deepcopy(wl)
+    wl_ref.optics[0].surf, wl_gpu.optics[0].surf = surf_ref, surf_gpu
+    rr = refdirect.runner()
+    ids = list(range(len(wl.terms)))
+    res, _, _ = rr.solve_terms(wl_ref, ids, CORES)
+    b = solver.upload(wl_gpu)
+    try:
+        tr, gr = solver.run(b)
+        bad = refdirect.compare_terms(tr, res, ids, wl, assert_stokes_close, "cfg1")
+        _tally("cfg1/cfg2 demo + glitter chain (N=41, OS_NB=80)", bad, len(ids))
+        assert not bad
+        # SOS_AGGREGATE of the reference over its own term files
+        agg_rec, agg_sc = rr.aggregate_point(ref, fm, str(tmp_path), N, [(wl.terms[i].aik, res[i]) for i in ids])
+        nr = int(gr.n_rec[0])
+        assert_stokes_close(gr.rec[0, :nr, :, :2 * N + 1], agg_rec[:nr], "aggregated records")
+        assert not agg_rec[nr:].any()
+        for k in ("emoins", "eplus", "ttot_tronc", "ttot_vrai", "tauout"):
+            assert_stokes_close(getattr(gr, k)[0], agg_sc[k], k)
+        # View 1 (cfg1) and View 2 (cfg2) with the sun-glint direct term
+        for itrphi, phios, pas in ((1, 0.0, 0), (2, 0.0, 30)):
+            n1, up, dn = solver.batch_trphi(b, 1, o.wind, o.ind_surf, 0, itrphi, phios, pas, 1)
+            n0, pf, th, up0, dn0 = refdirect.trphi_option(ref, fm, str(tmp_path), agg_rec[:nr], N, o.rmu, o.ga, agg_sc["ttot_tronc"],
+                                                          agg_sc["tauout"], 1, o.n0, o.wind, o.ind_surf, 0, itrphi, phios, pas)
+            assert n0 == n1
+            for tb in (1, 2, 3):
+                assert_stokes_close(up[0, tb, :n0, :N], up0[tb], "view %d up table %d" % (itrphi, tb))
+                assert_stokes_close(dn[0, tb, :n0, :N], dn0[tb], "view %d down table %d" % (itrphi, tb))
+    finally:
+        b.free()
+
+
+def test_cfg3_bench_band_all_terms(pkg, solver, ref):
+    """Every term-solve of the bench workload (BASELINE configs[2]: 96 points, 620 terms) against the reference."""
+    wl = pkg.synth.config_ckd_band(npoints=96, seed=20261021, nb_gauss=40, os_nb=80, surface="lambert", rho=0.1)
+    ids, res, b, tr, gr = _solve_both(pkg, solver, wl)
+    b.free()
+    bad = refdirect.compare_terms(tr, res, ids, wl, assert_stokes_close, "cfg3")
+    _tally("cfg3 O2-A-like CKD band, all terms (N=41, OS_NB=80)", bad, len(ids))
+    assert not bad
+
+
+def test_cfg4_hyperspectral_64_wavelengths(pkg, solver, ref):
+    wl = pkg.synth.config_hyperspectral(nwave=64, nb_gauss=24, os_nb=80)
+    assert wl.optics[0].nbmu == 25
+    ids, res, b, tr, gr = _solve_both(pkg, solver, wl)
+    b.free()
+    bad = refdirect.compare_terms(tr, res, ids, wl, assert_stokes_close, "cfg4")
+    _tally("cfg4 hyperspectral sweep, 64 wavelengths (N=25, OS_NB=80, surface matrix)", bad, len(ids))
+    assert not bad
+
+
+def test_cfg5_angular_stress_caps(pkg, solver, ref):
+    """N = CTE_OS_NBMU_MAX = 80 and OS_NB = CTE_OS_NB_MAX = 200 (SOS.h:471,480): 201 Fourier orders x 480-row contractions,
+    output level inside the atmosphere."""
+    wl = pkg.synth.config_angular_stress(nterm=8)
+    o = wl.optics[0]
+    assert o.nbmu == 80 and o.os_nb == 200 and o.zout != -1.0
+    ids, res, b, tr, gr = _solve_both(pkg, solver, wl)
+    b.free()
+    bad = refdirect.compare_terms(tr, res, ids, wl, assert_stokes_close, "cfg5")
+    _tally("cfg5 angular stress (N=80, OS_NB=200, zout=3 km)", bad, len(ids))
+    assert not bad
+    assert int(tr.n_fourier.max()) > 81                      # beyond what any OS_NB=80 case reaches

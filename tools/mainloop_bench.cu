@@ -1,0 +1,245 @@
+// mainloop_bench.cu -- the k_step main loop in isolation: FP64 DMMA (m8n8k4) tiles whose operands are STREAMED by the TMA
+// engine (cp.async.bulk + mbarrier) through a multi-stage shared-memory pipeline, with the operand layouts of k_step
+// (A slab [rows][KB] k-swizzled, field slab [KB][NCOL+4]) and only a token epilogue (accumulators stored once per level
+// chunk).  It answers what tools/dmma_smem_bench.cu (resident operands: 36.8 TFLOP/s) cannot: how much of the DMMA pipe a
+// given delivery scheme sustains.  Variants (template parameters):
+//   KB    k-slab depth (16 as in round 1, or 8)
+//   STG   pipeline stages
+//   NF    8-level column blocks per warp (8 -> 64-level chunk, 16 -> 128-level chunk)
+//   PROD  0: thread 0 of consumer warp 0 also issues the copies (round-1 scheme); 1: a dedicated producer warp
+//   CL    cluster size 1 or 2; with 2 the two CTAs share the A slab: each loads one half and multicasts it to both
+//   occupancy (1 or 2 CTAs per SM) follows from the shared-memory request.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mainloop_bench mainloop_bench.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(unsigned long long *bar, unsigned cta)
+{
+  unsigned remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  const unsigned addr = smem_u32(bar);
+  unsigned ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long *bar, unsigned parity)
+{
+  const unsigned addr = smem_u32(bar);
+  unsigned ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned short mask)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::"r"(
+                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+#define ROWS 128
+#define KP 256
+
+template <int KB, int STG, int NF, int PROD, int CL, int OCC>
+__global__ void __launch_bounds__(256 + 32 * PROD, OCC)
+k(const double *__restrict__ Apool, int nsets, const double *__restrict__ Xpool, size_t xspan, double *__restrict__ out, int nchunk,
+  int epi_cycles)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int NCOL = NF * 8, SB = NCOL + 4;
+  constexpr int A_BYTES = ROWS * KB * 8, B_BYTES = KB * SB * 8, STAGE = A_BYTES + B_BYTES;
+  constexpr int NSLAB = KP / KB;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + STG * STAGE);
+  unsigned long long *empty = full + STG;
+  const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5, gq = lane >> 2, tq = lane & 3;
+  unsigned crank = 0;
+  if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
+  if (tid == 0) {
+    for (int s = 0; s < STG; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 8 * CL); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  if (CL > 1) { asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;\n" ::: "memory"); }
+  else __syncthreads();
+
+  const int pair = blockIdx.x / CL;                               // CTAs of a cluster share the kernel set (A)
+  const double *Ag = Apool + (size_t)(pair % nsets) * KP * KP;
+  const double *Xg = Xpool + (size_t)blockIdx.x * xspan;
+  const int n_iter = nchunk * NSLAB;
+  const unsigned tx = A_BYTES + B_BYTES;
+
+  auto issue = [&](int q) {
+    const int st = q % STG, ch = q / NSLAB, slab = q - ch * NSLAB;
+    unsigned char *sp = smem + st * STAGE;
+    mbar_expect_tx(full + st, tx);
+    if (CL == 1) bulk_g2s(sp, Ag + (size_t)slab * KP * KB, A_BYTES, full + st);
+    else bulk_g2s_mc(sp + crank * (A_BYTES / CL), Ag + (size_t)slab * KP * KB + (size_t)crank * (ROWS / CL) * KB, A_BYTES / CL, full + st,
+                     (unsigned short)((1u << CL) - 1));
+    bulk_g2s(sp + A_BYTES, Xg + ((size_t)ch * NSLAB + slab) * (KB * SB), B_BYTES, full + st);
+  };
+
+  if (PROD && wr == 8) {                                          // dedicated producer warp
+    if (lane == 0) {
+      for (int q = 0; q < n_iter; ++q) {
+        if (q >= STG) { if (CL > 1) mbar_wait_cluster(empty + q % STG, ((q / STG) - 1) & 1); else mbar_wait(empty + q % STG, ((q / STG) - 1) & 1); }
+        issue(q);
+      }
+    }
+  } else {
+    if (!PROD && tid == 0) for (int q = 0; q < STG - 1 && q < n_iter; ++q) issue(q);
+    double acc[2][NF][2];
+    const int swz = (KB == 16) ? 4 * (gq & 3) : 4 * ((gq >> 1) & 1);
+    double *dst = out + ((size_t)blockIdx.x * ROWS + wr * 16 + gq) * NCOL + 2 * tq;
+    for (int ch = 0; ch < nchunk; ++ch) {
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NF; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      for (int slab = 0; slab < NSLAB; ++slab) {
+        const int q = ch * NSLAB + slab, st = q % STG;
+        if (!PROD && tid == 0 && q + STG - 1 < n_iter) {
+          if (q >= 1) { if (CL > 1) mbar_wait_cluster(empty + (q - 1) % STG, ((q - 1) / STG) & 1); else mbar_wait(empty + (q - 1) % STG, ((q - 1) / STG) & 1); }
+          issue(q + STG - 1);
+        }
+        mbar_wait(full + st, (q / STG) & 1);
+        const unsigned char *sp = smem + st * STAGE;
+        const double *a = reinterpret_cast<const double *>(sp) + (wr * 16 + gq) * KB;
+        const double *b = reinterpret_cast<const double *>(sp + A_BYTES) + tq * SB + gq;
+#pragma unroll
+        for (int ks4 = 0; ks4 < KB / 4; ++ks4) {
+          const int kc = (ks4 * 4 + tq) ^ swz;
+          const double a0 = a[kc], a1 = a[8 * KB + kc];
+          double bv[NF];
+#pragma unroll
+          for (int ni = 0; ni < NF; ++ni) bv[ni] = b[ks4 * 4 * SB + ni * 8];
+#pragma unroll
+          for (int ni = 0; ni < NF; ++ni) { dmma(acc[0][ni][0], acc[0][ni][1], a0, bv[ni]); dmma(acc[1][ni][0], acc[1][ni][1], a1, bv[ni]); }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(empty + st);
+          if (CL > 1) mbar_arrive_remote(empty + st, crank ^ 1);
+        }
+      }
+      // token epilogue: one store of the accumulators per chunk (+ an optional busy wait standing in for the recurrence)
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NF; ++ni) *reinterpret_cast<double2 *>(dst + (size_t)mi * 8 * NCOL + ni * 8) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+      if (epi_cycles > 0) { const long long t0 = clock64(); while (clock64() - t0 < epi_cycles) { } }
+    }
+  }
+  if (CL > 1) { asm volatile("barrier.cluster.arrive.aligned;\nbarrier.cluster.wait.aligned;\n" ::: "memory"); }
+}
+
+static double *g_A, *g_X, *g_out;
+static const int NSETS = 24;
+static const size_t XSPAN = (size_t)6 * 256 * 140;               // doubles per CTA (covers NF=16: 6 chunks * 256 k * 132)
+
+template <int KB, int STG, int NF, int PROD, int CL, int OCC>
+void run_(int ctas_per_sm, int epi_cycles)
+{
+  constexpr int NCOL = NF * 8, SB = NCOL + 4;
+  constexpr int STAGE = ROWS * KB * 8 + KB * SB * 8;
+  const int smem_need = STG * STAGE + 2 * STG * 8;
+  const int smem = ctas_per_sm == 2 ? (smem_need > 100 * 1024 ? smem_need : 100 * 1024) : (smem_need > 120 * 1024 ? smem_need : 120 * 1024);
+  if (smem > 227 * 1024 || (ctas_per_sm == 2 && smem > 113 * 1024)) return;
+  auto kern = k<KB, STG, NF, PROD, CL, OCC>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int nchunk = 6, waves = 4;
+  const int grid = 148 * ctas_per_sm * waves;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256 + 32 * PROD); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    cudaLaunchKernelEx(&cfg, kern, (const double *)g_A, NSETS, (const double *)g_X, XSPAN, g_out, nchunk, epi_cycles);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const double fl = 2.0 * ROWS * NCOL * KP * nchunk * (double)grid;
+  printf("KB=%2d STG=%d NCOL=%3d PROD=%d CL=%d CTAs/SM=%d smem=%3dKB epi=%5d : %6.2f TFLOP/s  %7.3f ms (%s)\n", KB, STG, NCOL, PROD, CL,
+         ctas_per_sm, smem / 1024, epi_cycles, fl / best / 1e9, best, cudaGetErrorString(cudaGetLastError()));
+  fflush(stdout);
+}
+
+template <int KB, int STG, int NF, int PROD, int CL>
+void run(int ctas_per_sm, int epi_cycles = 0)
+{
+  if (ctas_per_sm == 2) { if constexpr (NF == 8) run_<KB, STG, NF, PROD, CL, 2>(2, epi_cycles); }
+  else run_<KB, STG, NF, PROD, CL, 1>(1, epi_cycles);
+}
+
+int main()
+{
+  cudaMalloc(&g_A, (size_t)NSETS * KP * KP * 8);
+  const size_t xbytes = (size_t)148 * 2 * 4 * XSPAN * 8;
+  cudaMalloc(&g_X, xbytes);
+  cudaMalloc(&g_out, (size_t)148 * 2 * 4 * ROWS * 128 * 8);
+  cudaMemset(g_A, 0, (size_t)NSETS * KP * KP * 8);
+  cudaMemset(g_X, 0, xbytes);
+  printf("X pool %.2f GB\n", xbytes / 1e9);
+  // round-1 scheme
+  run<16, 3, 8, 0, 1>(2);
+  run<16, 3, 8, 0, 1>(1);
+  run<16, 7, 8, 0, 1>(1);
+  // dedicated producer warp
+  run<16, 3, 8, 1, 1>(2);
+  run<16, 4, 8, 1, 1>(2);
+  run<16, 7, 8, 1, 1>(1);
+  // thinner slabs, more stages
+  run<8, 6, 8, 1, 1>(2);
+  run<8, 8, 8, 1, 1>(2);
+  run<8, 12, 8, 1, 1>(1);
+  // 128-level chunks (one CTA per SM: 128 accumulator registers)
+  run<16, 4, 16, 1, 1>(1);
+  run<16, 6, 16, 1, 1>(1);
+  run<8, 8, 16, 1, 1>(1);
+  // clusters of 2 sharing the A slab by multicast
+  run<16, 3, 8, 1, 2>(2);
+  run<16, 4, 8, 1, 2>(2);
+  run<16, 7, 8, 1, 2>(1);
+  run<16, 6, 16, 1, 2>(1);
+  // with a stand-in epilogue (busy wait per chunk and warp)
+  run<16, 3, 8, 0, 1>(2, 20000);
+  run<16, 4, 8, 1, 1>(2, 20000);
+  run<16, 7, 8, 1, 1>(1, 20000);
+  run<16, 6, 16, 1, 1>(1, 20000);
+  return 0;
+}

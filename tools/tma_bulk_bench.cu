@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(128, 1) k(const char *src, size_t src_bytes, i
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
-  const size_t span = src_bytes / gridDim.x;                     // each CTA walks its own L2-resident window
+  const size_t span = (src_bytes / gridDim.x) & ~(size_t)1023;                   // each CTA walks its own L2-resident window
   const char *base = src + (size_t)blockIdx.x * span;
   const size_t nwin = span / copy_bytes;
   auto issue = [&](int i) {
