@@ -28,53 +28,6 @@ struct Arena {
   template <class T> size_t putv(const std::vector<T> &v) { return put(v.data(), v.size() * sizeof(T)); }
 };
 
-struct HostOptics {
-  int N, W, HB, KP, os_nb, n0, imat_surf, ifresnel, ipolar, igmax, n_surf_rec;
-  double tab, ro, ron, ind_surf, zout, beta2, gamma2, alpha2, f11sun, f12sun, a_trunc, piz, piztr;
-  std::vector<double> rmu, ga, alpha, beta, gamma, zeta, f11, f12, f33;
-  const float *surf;
-  bool limb;
-};
-
-struct HostTerm {
-  int optics, group, nt, LP, iborm, jout, ier;
-  double zz, aik, eground, ttot_vrai, ttot_tronc, tauout;
-  std::vector<double> h, xdel, ydel, dt, inv, ch, cf;
-};
-
-struct sosgpu_batch {
-  std::vector<HostOptics> ho;
-  std::vector<HostTerm> ht;
-  int nterm = 0, noptics = 0, ngroup = 0;
-  int rs_dev = 0, w_dev = 0, maxHB = 0, maxW = 0, maxKP = 0, maxNB = 0, smax = 0;
-  char *d_arena = nullptr;
-  OpticsDev *d_optics = nullptr;
-  TermDev *d_terms = nullptr;
-  std::vector<OpticsDev> optics_dev;
-  std::vector<TermDev> terms_dev;
-  double *d_att = nullptr, *d_i4 = nullptr;
-  size_t i4_total = 0;
-  size_t grec_bytes = 0;
-  double *d_rec = nullptr, *d_emoins = nullptr, *d_eplus = nullptr, *d_grec = nullptr;
-  int *d_nf = nullptr, *d_nsc = nullptr, *d_rsn = nullptr, *d_done = nullptr, *d_gnrec = nullptr;
-  int *d_group_start = nullptr, *d_group_terms = nullptr;
-  std::vector<int> group_start, group_terms;
-  // wave pools (grown on demand)
-  char *d_field = nullptr; size_t field_bytes = 0;
-  char *d_kpool = nullptr; size_t kpool_bytes = 0;
-  ItemDev *d_items = nullptr; size_t items_cap = 0;
-  KsetDev *d_ksets = nullptr; size_t ksets_cap = 0;
-  int *d_item_of = nullptr; size_t item_of_cap = 0;
-  int *d_list[2] = {nullptr, nullptr}; size_t list_cap = 0;
-  int *d_count = nullptr;           // [2]
-  int *h_count = nullptr;           // pinned
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
-  sosgpu_stats stats{};
-  // persistent buffers of sosgpu_batch_trphi
-  void *d_tg = nullptr; double *d_tphi = nullptr, *d_tout = nullptr; size_t tout_cap = 0, tphi_cap = 0;
-  std::vector<double> h_tout;
-};
-
 // ---------------------------------------------------------------------------------------------
 extern "C" int sosgpu_device_count(void)
 {
@@ -105,7 +58,9 @@ extern "C" int sosgpu_create(sosgpu_ctx **out, int device)
   if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess ||
       cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep_all) != cudaSuccess ||
       cudaMallocHost(&ctx->h_count, 2 * sizeof(int)) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
+      cudaMalloc(&ctx->d_work_counter, 64) != cudaSuccess ||
+      cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SOSGPU_ERR_CUDA;
@@ -119,7 +74,7 @@ extern "C" void sosgpu_destroy(sosgpu_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  cudaFree(ctx->grec_cache); cudaFree(ctx->cache_field); cudaFree(ctx->cache_kpool);
+  cudaFree(ctx->grec_cache); cudaFree(ctx->cache_field); cudaFree(ctx->cache_kpool); cudaFree(ctx->d_work_counter);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->h_count) cudaFreeHost(ctx->h_count);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -654,8 +609,11 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     for (int ig = 2; ig <= igmax && ncur > 0; ++ig) {
       CK(cudaMemsetAsync(b->d_count + (cur ^ 1), 0, sizeof(int), st));
       CK(cudaEventRecord(b->ev0, st));
-      const int nl = sos_launch_step(b->d_items, b->d_terms, b->d_optics, b->d_ksets, b->d_list[cur], ncur, 0, mode,
-                                     b->maxHB, jdump_dev, st);
+      const int nl = getenv("SOS_OLD_STEP")
+                         ? sos_launch_step(b->d_items, b->d_terms, b->d_optics, b->d_ksets, b->d_list[cur], ncur, 0, mode, b->maxHB,
+                                           jdump_dev, st)
+                         : sos_launch_sweep(b->d_items, b->d_terms, b->d_optics, b->d_ksets, b->d_list[cur], nullptr, ncur, b->maxHB,
+                                            ctx->d_work_counter, ctx->num_sms, jdump_dev, st);
       CK(cudaEventRecord(b->ev1, st));
       sos_launch_test(b->d_items, b->d_terms, b->d_optics, b->d_list[cur], ncur, b->d_list[cur ^ 1], b->d_count + (cur ^ 1), st);
       ctx->launches += nl + 1;
@@ -1041,7 +999,8 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
   sos_launch_kernels(dks, b->d_optics, 1, W, ctx->stream);
   sos_launch_pack(dks, b->d_optics, 1, KP, ctx->stream);
   ctx->launches += 3;
-  ctx->launches += sos_launch_step(dit, b->d_terms, b->d_optics, dks, nullptr, 1, 0, ks.dual ? 2 : 1, HB, dx + 2 * fsz, ctx->stream);
+  ctx->launches += sos_launch_sweep(dit, b->d_terms, b->d_optics, dks, nullptr, nullptr, 1, HB, ctx->d_work_counter, ctx->num_sms,
+                                    dx + 2 * fsz, ctx->stream);
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   std::vector<double> xo(fsz), jo(fsz);

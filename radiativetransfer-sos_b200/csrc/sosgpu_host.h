@@ -3,6 +3,7 @@
 #include "../../include/sosgpu.h"
 #include "sosgpu_internal.h"
 #include <string>
+#include <vector>
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -25,6 +26,8 @@ struct sosgpu_ctx {
   char *cache_field = nullptr; size_t cache_field_bytes = 0;   // wave pools parked by the last freed batch
   char *cache_kpool = nullptr; size_t cache_kpool_bytes = 0;
   double *grec_cache = nullptr; size_t grec_cache_bytes = 0;   // group-sum buffer parked by the last freed batch
+  unsigned *d_work_counter = nullptr; int num_sms = 0;   // work queue of the persistent sweep kernel
+  void *nccl_comm = nullptr; int nranks = 1, rank = 0;   // sosgpu_comm_init
   cudaMemPool_t pool = nullptr;      // stream-ordered pool (release threshold = never) behind sos_dmalloc / sos_dfree
 };
 
@@ -38,3 +41,57 @@ static inline void sos_dfree(sosgpu_ctx *ctx, void *p)
   if (ctx) cudaFreeAsync(p, ctx->stream);
   else cudaFree(p);
 }
+
+struct HostOptics {
+  int N, W, HB, KP, os_nb, n0, imat_surf, ifresnel, ipolar, igmax, n_surf_rec;
+  double tab, ro, ron, ind_surf, zout, beta2, gamma2, alpha2, f11sun, f12sun, a_trunc, piz, piztr;
+  std::vector<double> rmu, ga, alpha, beta, gamma, zeta, f11, f12, f33;
+  const float *surf;
+  bool limb;
+};
+
+struct HostTerm {
+  int optics, group, nt, LP, iborm, jout, ier;
+  double zz, aik, eground, ttot_vrai, ttot_tronc, tauout;
+  std::vector<double> h, xdel, ydel, dt, inv, ch, cf;
+};
+
+struct sosgpu_batch {
+  std::vector<HostOptics> ho;
+  std::vector<HostTerm> ht;
+  int nterm = 0, noptics = 0, ngroup = 0;
+  int rs_dev = 0, w_dev = 0, maxHB = 0, maxW = 0, maxKP = 0, maxNB = 0, smax = 0;
+  char *d_arena = nullptr;
+  OpticsDev *d_optics = nullptr;
+  TermDev *d_terms = nullptr;
+  std::vector<OpticsDev> optics_dev;
+  std::vector<TermDev> terms_dev;
+  double *d_att = nullptr, *d_i4 = nullptr;
+  size_t i4_total = 0;
+  size_t grec_bytes = 0;
+  double *d_rec = nullptr, *d_emoins = nullptr, *d_eplus = nullptr, *d_grec = nullptr;
+  int *d_nf = nullptr, *d_nsc = nullptr, *d_rsn = nullptr, *d_done = nullptr, *d_gnrec = nullptr;
+  int *d_group_start = nullptr, *d_group_terms = nullptr;
+  std::vector<int> group_start, group_terms;
+  // wave pools (grown on demand)
+  char *d_field = nullptr; size_t field_bytes = 0;
+  char *d_kpool = nullptr; size_t kpool_bytes = 0;
+  ItemDev *d_items = nullptr; size_t items_cap = 0;
+  KsetDev *d_ksets = nullptr; size_t ksets_cap = 0;
+  int *d_item_of = nullptr; size_t item_of_cap = 0;
+  int *d_list[2] = {nullptr, nullptr}; size_t list_cap = 0;
+  int *d_count = nullptr;           // [2]
+  int *h_count = nullptr;           // pinned
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+  sosgpu_stats stats{};
+  // persistent buffers of sosgpu_batch_trphi
+  void *d_tg = nullptr; double *d_tphi = nullptr, *d_tout = nullptr; size_t tout_cap = 0, tphi_cap = 0;
+  std::vector<double> h_tout;
+  // multi-GPU (sosgpu_comm.cu): optics entry of every group (default: first local term's), and the band-wide group
+  // metadata after sosgpu_batch_reduce_groups (sums of a*exp(-tau), fluxes, longest series)
+  std::vector<int> group_optics;
+  bool reduced = false;
+  std::vector<double> g_em, g_ep, g_tt, g_tv, g_to;
+  std::vector<int> g_nrec;
+};
+

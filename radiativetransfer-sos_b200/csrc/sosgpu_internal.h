@@ -98,6 +98,11 @@ void sos_launch_aggregate(const TermDev *terms, const int *group_start, const in
 // mode bit 0: launch the aerosol-only instantiation (is > 2), bit 1: the Rayleigh+aerosol one (is <= 2)
 int  sos_launch_step(const ItemDev *items, const TermDev *terms, const OpticsDev *optics, const KsetDev *ksets,
                      const int *list, int nitem, int order1, int mode, int maxHB, double *jdump, cudaStream_t st);
+// one scattering order n >= 2 (sweep_kernel.cu): persistent warp-specialised kernel; the item count is read from
+// count_ptr on the device when non-null (nitem is then an upper bound)
+int  sos_launch_sweep(const ItemDev *items, const TermDev *terms, const OpticsDev *optics, const KsetDev *ksets,
+                      const int *list, const int *count_ptr, int nitem, int maxHB, unsigned *work_counter, int num_sms,
+                      double *jdump, cudaStream_t st);
 #ifdef __cplusplus
 }
 #endif
