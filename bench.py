@@ -31,8 +31,10 @@ PKG = "radiativetransfer-sos_b200"
 POINTS_PER_GPU = int(os.environ.get("SOS_BENCH_POINTS", "96"))
 NB_GAUSS, OS_NB = 40, 80
 METRIC = "polarized SOS spectral solves/sec"
-# DRAM traffic of one full-width k_step launch of this workload, from the ncu --set full capture under profiles/
+# DRAM traffic of one full-width launch of the hot kernel on this workload, from the ncu --set full capture under profiles/
 NCU_TRAFFIC_BYTES = 4.157373e9 + 2.000106e9
+NCU_TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one full-width launch from the committed ncu capture "
+                      "under profiles/ (not measured live)")
 UNIT = "spectral points/s"
 
 
@@ -196,12 +198,40 @@ def _emit(text):
     print(text, flush=True)
 
 
+def lpt_partition(costs, nparts):
+    """Longest-processing-time-first partition of whole spectral points: returns part index per point."""
+    order = np.argsort(-np.asarray(costs, dtype=np.float64), kind="stable")
+    load = np.zeros(nparts)
+    part = np.zeros(len(costs), dtype=np.int64)
+    for p in order:
+        k = int(np.argmin(load))
+        part[p] = k
+        load[k] += costs[p]
+    return part
+
+
+def point_costs(wl):
+    """Cost proxy of a spectral point: sum over its CKD terms of levels x (1 + scattering optical depth)."""
+    c = np.zeros(len(wl.optics))
+    for t in wl.terms:
+        dh = np.diff(np.asarray(t.h))
+        tau_scat = float(np.sum(dh * (np.asarray(t.pcaer)[1:] + np.asarray(t.pcmol)[1:])))
+        c[t.optics] += (t.nt + 1) * (1.0 + tau_scat)
+    return c
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--band-points", type=int, default=0,
+                    help="strong scaling: a FIXED band of this many spectral points shared by all GPUs (default: weak "
+                         "scaling, %d points per GPU)" % POINTS_PER_GPU)
+    ap.add_argument("--shard", default=os.environ.get("SOS_BENCH_SHARD", "wavelengths"), choices=["wavelengths", "terms"],
+                    help="wavelengths: whole spectral points per GPU (LPT), no reduce, one NCCL gather of the result tables; "
+                         "terms: CKD terms round-robin, one NCCL reduce of the partial band sums")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -223,22 +253,37 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the SOS hot path has no CPU fallback")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    solver = api.Solver(local)
     if world > 1:
+        # torch.distributed is launch plumbing only (barrier, max over ranks, broadcast of the 128-byte NCCL id);
+        # the data path uses the communicator owned by libsosgpu.so
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        uid = torch.zeros(api.Solver.UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(solver.comm_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(uid, src=0)
+        solver.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
 
-    # global band: POINTS_PER_GPU * world points; terms sharded round-robin along the CKD-term axis
-    wl = make_workload(POINTS_PER_GPU * world)
-    my_ids = list(range(rank, len(wl.terms), world))
-    ngroup = len(wl.optics)
-    solver = api.Solver(local)
-    groups = [wl.terms[i].optics for i in my_ids]
+    npoints_total = args.band_points if args.band_points > 0 else POINTS_PER_GPU * world
+    scaling = "strong" if args.band_points > 0 else "weak"
+    wl = make_workload(npoints_total)
+    nterms_total = len(wl.terms)
+    if args.shard == "wavelengths":
+        part = lpt_partition(point_costs(wl), world)
+        my_points = [p for p in range(npoints_total) if part[p] == rank]
+        local_group = {p: g for g, p in enumerate(my_points)}
+        my_ids = [i for i, t in enumerate(wl.terms) if part[t.optics] == rank]
+        groups = [local_group[wl.terms[i].optics] for i in my_ids]
+        ngroup = len(my_points)
+        groups_of_rank = [int(np.sum(part == r)) for r in range(world)]
+    else:
+        my_ids = list(range(rank, nterms_total, world))
+        groups = [wl.terms[i].optics for i in my_ids]
+        ngroup = npoints_total
+        groups_of_rank = None
     batch = solver.upload(wl, my_ids, groups=groups, ngroup=ngroup)
-    gptr, gcount = solver.group_buffer(batch)
-
-    class _Arr:                                   # zero-copy torch view of the resident group sums
-        __cuda_array_interface__ = {"shape": (gcount,), "typestr": "<f8", "data": (gptr, False), "version": 2}
-    gview = torch.as_tensor(_Arr(), device=dev) if world > 1 else None
+    NPHI = 13                                          # SOS_TRPHI_OPTION view mode 2, dphi = 30
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -246,13 +291,20 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    def finish(b, download):
+        """CKD band sums -> azimuth synthesis -> complete band result on rank 0."""
+        if args.shard == "wavelengths":
+            solver.batch_trphi(b, 0, 2.0, 1.34, 0, 2, 0.0, 30, 1, download=False)
+            return solver.gather_tables(b, groups_of_rank, NPHI, root=0, download=download)
+        solver.reduce_groups(b, root=0)                # ONE ncclReduce of the partial band sums (+ group metadata)
+        if rank == 0:
+            _, up_t, down_t = solver.batch_trphi(b, 0, 2.0, 1.34, 0, 2, 0.0, 30, 1, download=download)
+            return up_t, down_t
+        return None, None
+
     def step_resident():
-        solver.run(batch, want_terms=False, want_groups=False, part_only=world > 1)
-        if world > 1:
-            dist.reduce(gview, dst=0, op=dist.ReduceOp.SUM)
-            torch.cuda.synchronize(dev)
-        if rank == 0:      # azimuth synthesis of the band sums (SOS_TRPHI_OPTION, view mode 2, 13 azimuths), device resident
-            solver.batch_trphi(batch, 0, 2.0, 1.34, 0, 2, 0.0, 30, 1, download=False)
+        solver.run(batch, want_terms=False, want_groups=False, part_only=args.shard == "terms" and world > 1)
+        finish(batch, False)
 
     for _ in range(args.warmup):
         step_resident()
@@ -285,6 +337,7 @@ def main():
     e2e_steps = max(1, min(args.steps, 3))
     h2d = d2h = 0
     t0 = 0.0
+    verbose = bool(os.environ.get("SOS_BENCH_VERBOSE"))
     for e2e_it in range(-1, e2e_steps):            # iteration -1 is an untimed warm-up of the host-buffer path
         if e2e_it == 0:
             sync_all()
@@ -293,37 +346,35 @@ def main():
         ta = time.perf_counter()
         b2 = solver.upload(wl, my_ids, groups=groups, ngroup=ngroup)
         tb = time.perf_counter()
-        tr, gr = solver.run(b2, want_terms=True, want_groups=True, want_rec=False, part_only=world > 1)
+        if args.shard == "wavelengths":            # every rank brings back the CKD-summed Fourier coefficients of its wavelengths
+            tr, gr = solver.run(b2, want_terms=True, want_groups=True, want_rec=False)
+            d2h += gr.rec.nbytes
+        else:
+            tr, _ = solver.run(b2, want_terms=True, want_groups=False, want_rec=False, part_only=world > 1)
         tc = time.perf_counter()
-        if os.environ.get("SOS_BENCH_VERBOSE"):
-            print("rank %d e2e: upload %.1f ms, run+download %.1f ms" % (rank, (tb - ta) * 1e3, (tc - tb) * 1e3), file=sys.stderr)
-        if world > 1:
-            p2, c2 = solver.group_buffer(b2)
-
-            class _A2:
-                __cuda_array_interface__ = {"shape": (c2,), "typestr": "<f8", "data": (p2, False), "version": 2}
-            dist.reduce(torch.as_tensor(_A2(), device=dev), dst=0, op=dist.ReduceOp.SUM)
-            torch.cuda.synchronize(dev)
-            if os.environ.get("SOS_BENCH_VERBOSE"):
-                print("rank %d e2e: reduce %.1f ms" % (rank, (time.perf_counter() - tc) * 1e3), file=sys.stderr)
-        if rank == 0:
-            _, up_t, down_t = solver.batch_trphi(b2, 0, 2.0, 1.34, 0, 2, 0.0, 30, 1, download=True)
+        up_t, down_t = finish(b2, True)
+        if args.shard == "terms" and rank == 0:
+            gr = solver.groups(b2)                 # the REDUCED band sums
+            d2h += gr.rec.nbytes
+        if up_t is not None:
             d2h += up_t.nbytes + down_t.nbytes
         h2d += b2.h2d_bytes
-        d2h += gr.rec.nbytes + tr.n_fourier.nbytes + tr.n_scatter.nbytes
+        d2h += tr.n_fourier.nbytes + tr.n_scatter.nbytes
         td = time.perf_counter()
         b2.free()
-        if os.environ.get("SOS_BENCH_VERBOSE"):
-            print("rank %d e2e: free %.1f ms" % (rank, (time.perf_counter() - td) * 1e3), file=sys.stderr)
+        if verbose:
+            print("rank %d e2e: upload %.1f ms, run+download %.1f ms, finish %.1f ms, free %.1f ms"
+                  % (rank, (tb - ta) * 1e3, (tc - tb) * 1e3, (td - tc) * 1e3, (time.perf_counter() - td) * 1e3), file=sys.stderr)
     sync_all()
     e2e_dt = (time.perf_counter() - t0) / e2e_steps
-    e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    e2e_t = torch.tensor([e2e_dt, float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_dt = float(e2e_t[0])
+        tmax = e2e_t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.SUM)
+        e2e_dt, h2d, d2h = float(tmax[0]), float(e2e_t[1]), float(e2e_t[2])
+    flops_t = torch.tensor([st_acc["flops"], st_acc["step_ms"]], dtype=torch.float64, device=dev)
 
-    npoints_total = POINTS_PER_GPU * world
-    nterms_total = len(wl.terms)
     if rank == 0:
         peak = dgemm_peak(torch, dev)
         achieved = st_acc["flops"] / (st_acc["step_ms"] * 1e-3) / 1e12 if st_acc["step_ms"] > 0 else 0.0
@@ -340,30 +391,34 @@ def main():
                     cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
         else:
             cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "timed at N=1 only"}
+        shard_txt = {"wavelengths": "whole spectral points per GPU (LPT on levels x (1 + scattering depth)), no reduce; one NCCL "
+                                    "send/recv gather of the synthesised tables to rank 0 (communicator owned by libsosgpu.so)",
+                     "terms": "CKD-term axis round-robin, ONE ncclReduce of the partial band sums + group metadata to rank 0 "
+                              "(communicator owned by libsosgpu.so)"}[args.shard]
         line = {
             "metric": METRIC, "value": npoints_total / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "O2 A-band-like CKD band (BASELINE configs[2]): %d spectral points/GPU, %d CKD "
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "O2 A-band-like CKD band (BASELINE configs[2]): %d spectral points (%s), %d CKD "
                                    "term-solves total, N=41 angles, OS_NB=80, NT 101..600, Lambert rho=0.1"
-                                   % (POINTS_PER_GPU, nterms_total),
-                       "points_per_gpu": POINTS_PER_GPU, "term_solves": nterms_total,
+                                   % (npoints_total, "%d per GPU" % POINTS_PER_GPU if scaling == "weak" else "fixed band",
+                                      nterms_total),
+                       "points_per_gpu": npoints_total / world, "term_solves": nterms_total,
                        "term_solves_per_s": nterms_total / (step_ms * 1e-3),
-                       "sharding": "CKD-term axis round-robin, 1 NCCL reduce of the band sums" if world > 1 else "none",
+                       "sharding": shard_txt if world > 1 else "none",
                        "cache": "field working set (GBs) >> 126 MB L2; no reuse between steps"},
             "e2e": {"value": npoints_total / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d / e2e_steps),
                     "d2h_bytes_per_step": int(d2h / e2e_steps)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "k_step (FP64 DMMA source-function contraction fused with the "
-                         "layer recurrence)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "kernel": "k_sweep (FP64 DMMA source-function contraction fused with the "
+                         "layer recurrence; persistent, warp-specialised)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None, "traffic": NCU_TRAFFIC_BYTES,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one full-width k_step<0,0> "
-                                           "launch (9920 CTAs, 4.9 ms under ncu) from the committed capture "
-                                           "profiles/r1_kstep_ncu_full_summary.txt; not measured live",
+                         "traffic_source": NCU_TRAFFIC_SOURCE,
                          "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 "
                                         "entry)",
-                         "algorithmic": "2*(6N)^2*(NT+1) FLOP per (term, Fourier order, scattering order>=2)",
+                         "algorithmic": "2*(6N)^2*(NT+1) FLOP per (term, Fourier order, scattering order>=2), only orders "
+                                        "the reference computes too (orders past a Fourier stop are not counted)",
                          "kernel_ms_per_step": st_acc["step_ms"] / args.steps,
                          "kernel_launches_per_step": st_acc["step_launches"] / args.steps,
                          "kernel_share_of_step": st_acc["step_ms"] / max(st_acc["total_ms"], 1e-9),
@@ -371,6 +426,7 @@ def main():
             "cpu_baseline": cb,
         }
         _emit(json.dumps(line))
+    del flops_t
     batch.free()
     solver.close()
     if world > 1:

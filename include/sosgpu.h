@@ -148,6 +148,29 @@ typedef struct {
 } sosgpu_stats;
 int  sosgpu_batch_stats(const sosgpu_batch *batch, sosgpu_stats *st);
 
+/* ---- multi-GPU: one process per GPU, the library owns the NCCL communicator --------------------------
+ * NCCL is bound at run time (dlopen of libnccl.so.2).  Rank 0 creates the unique id, the host program broadcasts its
+ * SOSGPU_UNIQUE_ID_BYTES bytes by whatever it has (MPI_Bcast, a file, ...), every rank calls sosgpu_comm_init. */
+#define SOSGPU_UNIQUE_ID_BYTES 128
+int sosgpu_comm_unique_id(char *id);
+int sosgpu_comm_init(sosgpu_ctx *ctx, int nranks, int rank, const char *id);
+int sosgpu_comm_destroy(sosgpu_ctx *ctx);
+int sosgpu_comm_barrier(sosgpu_ctx *ctx);
+/* Term-sharded layout (the CKD terms of every wavelength are spread over the ranks; every rank keeps the global group
+ * numbering): after sosgpu_batch_run, ONE in-place ncclReduce (sum, f64) of the partial CKD-weighted sums
+ * [ngroup][S+1][3][W] together with the per-group scalars and series lengths forms the band sums on `root`
+ * (SOS_AGGREGATE.F:351-488 across GPUs).  Afterwards, on root, sosgpu_batch_trphi synthesises the band sums and
+ * sosgpu_batch_groups returns them.  With one rank (or no communicator) it only finalises the local sums. */
+int sosgpu_batch_reduce_groups(sosgpu_ctx *ctx, sosgpu_batch *batch, int root);
+int sosgpu_batch_groups(sosgpu_ctx *ctx, sosgpu_batch *batch, int rec_stride, int wmax, sosgpu_group_out *group_out);
+/* optics entry (index into the uploaded optics array) of every group: needed on a rank that owns no term of a group */
+int sosgpu_batch_set_group_optics(sosgpu_batch *batch, const int *optics_of_group);
+/* Wavelength-sharded layout (every rank owns whole wavelengths; no reduce): collects the tables of the last
+ * sosgpu_batch_trphi call of every rank on `root`, in rank order, with one grouped ncclSend/ncclRecv.
+ * groups_of_rank[nranks]; up/down (root; may be NULL): [sum of groups][7][nphi][nmax]. */
+int sosgpu_batch_gather_tables(sosgpu_ctx *ctx, sosgpu_batch *batch, int root, const int *groups_of_rank, int nphi, int nmax,
+                               double *up, double *down);
+
 /* ---- single-routine operators (parity tests read like the reference's own subroutines) -------- */
 /* SOS_NOYAUX (SOS_OS.F:1857-2158): six kernels [W*W] + l=2 rows [W]; rmu[N] must hold mu_s */
 int sosgpu_noyaux(sosgpu_ctx *ctx, int is, int nbmu, const double *rmu, int os_nb,

@@ -85,6 +85,14 @@ def load_library():
         lib.sosgpu_batch_stats.argtypes = [C.c_void_p, C.POINTER(CStats)]
         lib.sosgpu_batch_group_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         lib.sosgpu_group_finalize.argtypes = [c_dp, c_dp, c_dp, C.c_int]
+        lib.sosgpu_comm_unique_id.argtypes = [C.c_char_p]
+        lib.sosgpu_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        lib.sosgpu_comm_destroy.argtypes = [C.c_void_p]
+        lib.sosgpu_comm_barrier.argtypes = [C.c_void_p]
+        lib.sosgpu_batch_reduce_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.sosgpu_batch_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(CGroupOut)]
+        lib.sosgpu_batch_set_group_optics.argtypes = [C.c_void_p, c_ip]
+        lib.sosgpu_batch_gather_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_ip, C.c_int, C.c_int, c_dp, c_dp]
         _lib = lib
     return _lib
 
@@ -278,6 +286,57 @@ class Solver:
             return self.run(b, **kw)
         finally:
             b.free()
+
+    # ------------------------------------------------------------------ multi-GPU (the library owns the NCCL communicator)
+    UNIQUE_ID_BYTES = 128
+
+    def comm_unique_id(self):
+        """Rank 0: ncclGetUniqueId; the caller broadcasts the bytes to the other ranks."""
+        buf = C.create_string_buffer(self.UNIQUE_ID_BYTES)
+        self._check(self.lib.sosgpu_comm_unique_id(buf), "comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, nranks, rank, unique_id):
+        self._check(self.lib.sosgpu_comm_init(self.ctx, nranks, rank, C.create_string_buffer(bytes(unique_id), self.UNIQUE_ID_BYTES)),
+                    "comm_init")
+        self.nranks, self.rank = nranks, rank
+
+    def comm_barrier(self):
+        self._check(self.lib.sosgpu_comm_barrier(self.ctx), "comm_barrier")
+
+    def set_group_optics(self, batch, optics_of_group):
+        a = np.ascontiguousarray(optics_of_group, dtype=np.int32)
+        self._check(self.lib.sosgpu_batch_set_group_optics(batch.handle, a.ctypes.data_as(c_ip)), "set_group_optics")
+
+    def reduce_groups(self, batch, root=0):
+        """Term-sharded layout: ONE in-place ncclReduce of the partial CKD sums + group metadata to `root`."""
+        self._check(self.lib.sosgpu_batch_reduce_groups(self.ctx, batch.handle, root), "reduce_groups")
+
+    def groups(self, batch):
+        """Band sums on the root after reduce_groups (what the SOS_AGGREGATE chain leaves behind)."""
+        ng, rs, w = batch.ngroup, batch.rec_stride, batch.wmax
+        gr = GroupResults()
+        gr.rec = np.zeros((ng, rs, 3, w))
+        gr.n_rec = np.zeros(ng, dtype=np.int32)
+        for n in ("emoins", "eplus", "ttot_tronc", "ttot_vrai", "tauout"):
+            setattr(gr, n, np.zeros(ng))
+        go = CGroupOut(_d(gr.rec), gr.n_rec.ctypes.data_as(c_ip), _d(gr.emoins), _d(gr.eplus), _d(gr.ttot_tronc),
+                       _d(gr.ttot_vrai), _d(gr.tauout))
+        self._check(self.lib.sosgpu_batch_groups(self.ctx, batch.handle, rs, w, C.byref(go)), "batch_groups")
+        return gr
+
+    def gather_tables(self, batch, groups_of_rank, nphi, root=0, download=True):
+        """Wavelength-sharded layout: tables of the last batch_trphi call of every rank, collected on `root`
+        ([sum groups, 7, nphi, Nmax] up and down; None on the other ranks or when download is False)."""
+        g = np.ascontiguousarray(groups_of_rank, dtype=np.int32)
+        nmax = (batch.wmax - 1) // 2
+        is_root = getattr(self, "rank", 0) == root
+        up = np.zeros((int(g.sum()), 7, nphi, nmax)) if (download and is_root) else None
+        down = np.zeros_like(up) if up is not None else None
+        self._check(self.lib.sosgpu_batch_gather_tables(self.ctx, batch.handle, root, g.ctypes.data_as(c_ip), nphi, nmax,
+                                                        _d(up) if up is not None else None,
+                                                        _d(down) if down is not None else None), "gather_tables")
+        return up, down
 
     # ------------------------------------------------------------------ single routines
     def sos_os(self, o, nt, h, xdel, ydel, zprof, iborm):

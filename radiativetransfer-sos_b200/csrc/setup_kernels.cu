@@ -361,11 +361,13 @@ __global__ void k_init(ItemDev *items, const TermDev *terms, const OpticsDev *op
 // One scattering order has been integrated (field of order n+1 sits in x[(n+1)&1]):
 // SOS_OS.F:1248-1417 with SOS_PARAM_CONV, SOS_AJOUT_QUEUE, SOS_ARRET_DIFFUS_1/2.
 __global__ void k_test(ItemDev *items, const TermDev *terms, const OpticsDev *optics,
-                       const int *list_cur, int *list_next, int *count_next)
+                       const int *list_cur, const int *count_cur, int *list_next, int *count_next)
 {
   __shared__ double red[32];
-  const int item = list_cur[blockIdx.x];
+  if (count_cur && (int)blockIdx.x >= *count_cur) return;      // the grid is an upper bound: the wave loop never waits for the count
+  const int item = list_cur ? list_cur[blockIdx.x] : (int)blockIdx.x;
   ItemDev &it = items[item];
+  if (!it.active) return;                                     // IG=2 > IGMAX at label 503: no scattering order at all
   const TermDev &tm = terms[it.term];
   const OpticsDev &op = optics[tm.optics];
   const int N = op.nbmu, HB = op.HB, NT = tm.nt, KP = op.KP;
@@ -561,9 +563,9 @@ void sos_launch_init(ItemDev *items, const TermDev *terms, const OpticsDev *opti
   if (nitem > 0) k_init<<<nitem, 256, 0, st>>>(items, terms, optics);
 }
 void sos_launch_test(ItemDev *items, const TermDev *terms, const OpticsDev *optics,
-                     const int *list_cur, int ncur, int *list_next, int *count_next, cudaStream_t st)
+                     const int *list_cur, const int *count_cur, int ncur, int *list_next, int *count_next, cudaStream_t st)
 {
-  if (ncur > 0) k_test<<<ncur, 256, 0, st>>>(items, terms, optics, list_cur, list_next, count_next);
+  if (ncur > 0) k_test<<<ncur, 256, 0, st>>>(items, terms, optics, list_cur, count_cur, list_next, count_next);
 }
 void sos_launch_fourier(ItemDev *items, TermDev *terms, const OpticsDev *optics, int nterm,
                         const int *item_of, int s0, int s1, int rec_stride_dev, int wdev,

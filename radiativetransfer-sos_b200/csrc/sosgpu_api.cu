@@ -36,6 +36,7 @@ extern "C" int sosgpu_device_count(void)
   return n;
 }
 
+extern "C" void sosgpu_destroy(sosgpu_ctx *ctx);
 extern "C" int sosgpu_create(sosgpu_ctx **out, int device)
 {
   if (!out) return SOSGPU_ERR_ARG;
@@ -57,14 +58,16 @@ extern "C" int sosgpu_create(sosgpu_ctx **out, int device)
   unsigned long long keep_all = ~0ull;
   if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess ||
       cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep_all) != cudaSuccess ||
-      cudaMallocHost(&ctx->h_count, 2 * sizeof(int)) != cudaSuccess ||
+      cudaMallocHost(&ctx->h_count, 16 * sizeof(int)) != cudaSuccess ||
       cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
       cudaMalloc(&ctx->d_work_counter, 64) != cudaSuccess ||
       cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
-    cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    sosgpu_destroy(ctx);                                         // releases whatever was created so far
     return SOSGPU_ERR_CUDA;
   }
+  for (int k = 0; k < 8; ++k)
+    if (cudaEventCreateWithFlags(&ctx->ev_cnt[k], cudaEventDisableTiming) != cudaSuccess) { sosgpu_destroy(ctx); return SOSGPU_ERR_CUDA; }
+  ctx->trace = getenv("SOS_TRACE") != nullptr;
   *out = ctx;
   return SOSGPU_OK;
 }
@@ -74,11 +77,13 @@ extern "C" void sosgpu_destroy(sosgpu_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  cudaFree(ctx->grec_cache); cudaFree(ctx->cache_field); cudaFree(ctx->cache_kpool); cudaFree(ctx->d_work_counter);
+  cudaFree(ctx->grec_cache); cudaFree(ctx->cache_field); cudaFree(ctx->cache_kpool); cudaFree(ctx->d_work_counter); cudaFree(ctx->d_gather);
+  sosgpu_comm_destroy(ctx);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->h_count) cudaFreeHost(ctx->h_count);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  for (int k = 0; k < 8; ++k) if (ctx->ev_cnt[k]) cudaEventDestroy(ctx->ev_cnt[k]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -230,6 +235,8 @@ static void free_batch_device(sosgpu_ctx *ctx, sosgpu_batch *b)
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->evt0) cudaEventDestroy(b->evt0);
   if (b->evt1) cudaEventDestroy(b->evt1);
+  for (cudaEvent_t e : b->ev_order) cudaEventDestroy(e);
+  b->ev_order.clear();
   if (tr) fprintf(stderr, "batch_free: pools %.2f ms, small %.2f ms, group buffer %.2f ms, events %.2f ms\n", t1 - t0, t2 - t1,
                   t3 - t2, now() - t3);
 }
@@ -355,6 +362,9 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     std::vector<int> fill(b->group_start.begin(), b->group_start.end() - 1);
     for (int i = 0; i < nterm; ++i) b->group_terms[fill[b->ht[i].group]++] = i;
   }
+  b->group_optics.assign(ngroup, -1);
+  for (int g = 0; g < ngroup; ++g)
+    if (b->group_start[g + 1] > b->group_start[g]) b->group_optics[g] = b->ht[b->group_terms[b->group_start[g]]].optics;
   CK(sos_dmalloc(ctx, &b->d_group_start, (ngroup + 1) * sizeof(int)));
   CK(sos_dmalloc(ctx, &b->d_group_terms, nterm * sizeof(int)));
   CK(cudaMemcpyAsync(b->d_group_start, b->group_start.data(), (ngroup + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -364,7 +374,8 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
   CK(sos_dmalloc(ctx, &b->d_rec, (size_t)nterm * per * sizeof(double)));
   // The group sums are handed to NCCL (sosgpu_batch_group_buffer), so they stay a plain cudaMalloc block; a freed
   // batch parks it in the context because cudaFree of it was measured at 1.5-670 ms (device-wide synchronisation).
-  b->grec_bytes = (size_t)ngroup * per * sizeof(double);
+  // + per-group tail (8 scalars, rs_dev series-length indicators) so that ONE ncclReduce carries everything (sosgpu_comm.cu)
+  b->grec_bytes = (size_t)ngroup * (per + 8 + b->rs_dev) * sizeof(double);
   if (ctx->grec_cache && ctx->grec_cache_bytes >= b->grec_bytes) {
     b->d_grec = ctx->grec_cache; b->grec_bytes = ctx->grec_cache_bytes;
     ctx->grec_cache = nullptr; ctx->grec_cache_bytes = 0;
@@ -430,6 +441,7 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
   const int nterm = b->nterm;
   const size_t per = (size_t)b->rs_dev * 3 * b->w_dev;
   b->stats = sosgpu_stats{};
+  b->reduced = false;
   CK(cudaEventRecord(b->evt0, st));
   CK(cudaMemsetAsync(b->d_rec, 0, (size_t)nterm * per * sizeof(double), st));
   CK(cudaMemsetAsync(b->d_i4, 0, b->i4_total * sizeof(double), st));
@@ -602,31 +614,51 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     CK(cudaGetLastError());
 
     // ---- scattering orders ----
+    // The loop never waits for the GPU: the sweep kernel and k_test read the number of still-active items from device
+    // memory; the host only follows it with a lag of SOS_LAG orders (pinned counters + events) to shrink k_test's grid
+    // and to stop launching once everything has converged.
     int igmax = 0;
     for (int ti : act) igmax = std::max(igmax, b->ho[b->ht[ti].optics].igmax);
-    int ncur = (int)nitem, cur = 0;
-    const int mode = (has_single ? 1 : 0) | (has_dual ? 2 : 0);
-    for (int ig = 2; ig <= igmax && ncur > 0; ++ig) {
+    enum { SOS_LAG = 3, SOS_RING = 8 };
+    int cur = 0, ub = (int)nitem;
+    std::vector<int> order_ev;                                   // event pair index of every launched order
+    (void)has_single; (void)has_dual;
+    for (int ig = 2; ig <= igmax; ++ig) {
+      if (ig - 2 >= SOS_LAG) {                                   // count after order ig-SOS_LAG
+        const int k = (ig - SOS_LAG) % SOS_RING;
+        CK(cudaEventSynchronize(ctx->ev_cnt[k]));
+        ub = std::min(ub, ctx->h_count[k]);
+        if (ub <= 0) break;
+      }
+      const bool first = (ig == 2);
+      const int *list_cur = first ? nullptr : b->d_list[cur];
+      const int *count_cur = first ? nullptr : b->d_count + cur;
       CK(cudaMemsetAsync(b->d_count + (cur ^ 1), 0, sizeof(int), st));
-      CK(cudaEventRecord(b->ev0, st));
-      const int nl = getenv("SOS_OLD_STEP")
-                         ? sos_launch_step(b->d_items, b->d_terms, b->d_optics, b->d_ksets, b->d_list[cur], ncur, 0, mode, b->maxHB,
-                                           jdump_dev, st)
-                         : sos_launch_sweep(b->d_items, b->d_terms, b->d_optics, b->d_ksets, b->d_list[cur], nullptr, ncur, b->maxHB,
-                                            ctx->d_work_counter, ctx->num_sms, jdump_dev, st);
-      CK(cudaEventRecord(b->ev1, st));
-      sos_launch_test(b->d_items, b->d_terms, b->d_optics, b->d_list[cur], ncur, b->d_list[cur ^ 1], b->d_count + (cur ^ 1), st);
+      if (b->ev_order.size() < 2 * (order_ev.size() + 1)) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        b->ev_order.push_back(e0); b->ev_order.push_back(e1);
+      }
+      cudaEvent_t e0 = b->ev_order[2 * order_ev.size()], e1 = b->ev_order[2 * order_ev.size() + 1];
+      order_ev.push_back(ig);
+      CK(cudaEventRecord(e0, st));
+      const int nl = sos_launch_sweep(b->d_items, b->d_terms, b->d_optics, b->d_ksets, list_cur, count_cur, ub, b->maxHB,
+                                      ctx->d_work_counter, ctx->num_sms, jdump_dev, st);
+      CK(cudaEventRecord(e1, st));
+      sos_launch_test(b->d_items, b->d_terms, b->d_optics, list_cur, count_cur, ub, b->d_list[cur ^ 1], b->d_count + (cur ^ 1), st);
       ctx->launches += nl + 1;
       b->stats.step_launches += nl;
-      CK(cudaMemcpyAsync(b->h_count, b->d_count + (cur ^ 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      CK(cudaGetLastError());
-      float ms = 0.f;
-      CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
-      b->stats.step_ms += ms;
-      if (getenv("SOS_TRACE")) fprintf(stderr, "wave s0=%d ws=%d ig=%d active=%d step_ms=%.3f\n", s0, ws, ig, ncur, ms);
-      ncur = b->h_count[0];
+      CK(cudaMemcpyAsync(ctx->h_count + (ig % SOS_RING), b->d_count + (cur ^ 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(ctx->ev_cnt[ig % SOS_RING], st));
       cur ^= 1;
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (size_t k = 0; k < order_ev.size(); ++k) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, b->ev_order[2 * k], b->ev_order[2 * k + 1]));
+      b->stats.step_ms += ms;
+      if (ctx->trace) fprintf(stderr, "wave s0=%d ws=%d ig=%d step_ms=%.3f\n", s0, ws, order_ev[k], ms);
     }
 
     // ---- per-order bookkeeping and Fourier stop, in order ----
@@ -825,21 +857,23 @@ extern "C" int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *b, int igli, do
   std::vector<TrphiGroup> grp(ng);
   for (int g = 0; g < ng; ++g) {
     double tt = 0.0, to_ = 0.0;
-    int opt = -1;
-    for (int x = b->group_start[g]; x < b->group_start[g + 1]; ++x) {     // SOS_AGGREGATE.F:467-488, term order
-      const HostTerm &ht = b->ht[b->group_terms[x]];
-      if (opt < 0) opt = ht.optics;
-      double tr = (tt != 0) ? ht.aik * std::exp(-ht.ttot_tronc) + std::exp(-tt) : ht.aik * std::exp(-ht.ttot_tronc);
-      tt = -std::log(tr);
-      tr = (to_ != 0) ? ht.aik * std::exp(-ht.tauout) + std::exp(-to_) : ht.aik * std::exp(-ht.tauout);
-      to_ = -std::log(tr);
-    }
-    if (opt < 0) { grp[g] = TrphiGroup{b->d_grec, b->optics_dev[0].rmu, 0, b->ho[0].N, 1, b->w_dev, 0.0, 0.0}; continue; }
+    const int opt = b->group_optics[g];
+    if (b->reduced) { tt = b->g_tt[g]; to_ = b->g_to[g]; }       // band-wide values after sosgpu_batch_reduce_groups
+    else
+      for (int x = b->group_start[g]; x < b->group_start[g + 1]; ++x) {   // SOS_AGGREGATE.F:467-488, term order
+        const HostTerm &ht = b->ht[b->group_terms[x]];
+        double tr = (tt != 0) ? ht.aik * std::exp(-ht.ttot_tronc) + std::exp(-tt) : ht.aik * std::exp(-ht.ttot_tronc);
+        tt = -std::log(tr);
+        tr = (to_ != 0) ? ht.aik * std::exp(-ht.tauout) + std::exp(-to_) : ht.aik * std::exp(-ht.tauout);
+        to_ = -std::log(tr);
+      }
+    if (opt < 0) { grp[g] = TrphiGroup{b->d_grec, b->optics_dev[0].rmu, 0, b->ho[0].N, 1, b->w_dev, 0.0, 0.0}; nmax = std::max(nmax, b->ho[0].N); continue; }
     const HostOptics &ho = b->ho[opt];
     if (ho.n0 < 1) { ctx->err = "sosgpu_batch_trphi needs the solar angle among the Gauss angles (n0 > 0)"; return SOSGPU_ERR_ARG; }
     grp[g] = TrphiGroup{b->d_grec + (size_t)g * per, b->optics_dev[opt].rmu, gn[g], ho.N, ho.n0, b->w_dev, tt, to_};
     nmax = std::max(nmax, ho.N);
   }
+  for (int i = 0; i < b->noptics; ++i) nmax = std::max(nmax, b->ho[i].N);   // same table pitch on every rank
   // note: rmu[N] on the device holds mu_s (index 0), which SOS_TRPHI never reads
   const size_t nout = (size_t)ng * 2 * 7 * nphi * nmax;
   if (!b->d_tg) CK(sos_dmalloc(ctx, &b->d_tg, ng * sizeof(TrphiGroup)));

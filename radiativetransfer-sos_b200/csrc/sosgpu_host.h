@@ -22,12 +22,15 @@ struct sosgpu_ctx {
   size_t field_budget = (size_t)48 << 30;
   int max_wave_orders = 0;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr; float last_kernel_ms = 0.f;   // device time of the last glitter / synthesis kernel
-  int *h_count = nullptr;            // pinned word pair for the active-count readback of the wave loop
+  int *h_count = nullptr;            // pinned ring of active counts, read back with a lag (the wave loop never waits)
+  cudaEvent_t ev_cnt[8] = {};        // one event per ring slot
+  bool trace = false;                // SOS_TRACE, read once at create
   char *cache_field = nullptr; size_t cache_field_bytes = 0;   // wave pools parked by the last freed batch
   char *cache_kpool = nullptr; size_t cache_kpool_bytes = 0;
   double *grec_cache = nullptr; size_t grec_cache_bytes = 0;   // group-sum buffer parked by the last freed batch
   unsigned *d_work_counter = nullptr; int num_sms = 0;   // work queue of the persistent sweep kernel
   void *nccl_comm = nullptr; int nranks = 1, rank = 0;   // sosgpu_comm_init
+  double *d_gather = nullptr; size_t gather_cap = 0; std::vector<double> h_gather;   // root side of sosgpu_batch_gather_tables
   cudaMemPool_t pool = nullptr;      // stream-ordered pool (release threshold = never) behind sos_dmalloc / sos_dfree
 };
 
@@ -83,6 +86,7 @@ struct sosgpu_batch {
   int *d_count = nullptr;           // [2]
   int *h_count = nullptr;           // pinned
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+  std::vector<cudaEvent_t> ev_order;  // timing event pairs of the sweep launches of a wave
   sosgpu_stats stats{};
   // persistent buffers of sosgpu_batch_trphi
   void *d_tg = nullptr; double *d_tphi = nullptr, *d_tout = nullptr; size_t tout_cap = 0, tphi_cap = 0;

@@ -85,8 +85,9 @@ void sos_launch_kernels(const KsetDev *ksets, const OpticsDev *optics, int nkset
 void sos_launch_pack(const KsetDev *ksets, const OpticsDev *optics, int nkset, int maxKP, cudaStream_t st);   // 2 kernels
 void sos_launch_att(const TermDev *terms, const OpticsDev *optics, int nterm, int max_elems, cudaStream_t st);
 void sos_launch_init(ItemDev *items, const TermDev *terms, const OpticsDev *optics, int nitem, cudaStream_t st);
+// list_cur == null: items 0..ncur-1; count_cur != null: number of valid list entries on the device (ncur = upper bound)
 void sos_launch_test(ItemDev *items, const TermDev *terms, const OpticsDev *optics,
-                     const int *list_cur, int ncur, int *list_next, int *count_next, cudaStream_t st);
+                     const int *list_cur, const int *count_cur, int ncur, int *list_next, int *count_next, cudaStream_t st);
 void sos_launch_fourier(ItemDev *items, TermDev *terms, const OpticsDev *optics, int nterm,
                         const int *item_of, int s0, int s1, int rec_stride_dev, int wdev,
                         double *rec, int *n_fourier, int *n_scatter, int *stop_reason,

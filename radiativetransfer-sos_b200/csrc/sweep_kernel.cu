@@ -82,18 +82,17 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;\n" ::"
 __device__ __forceinline__ int acc_slot(int row, int cpair) { return row * (SW_ACC_PITCH / 2) + (cpair ^ ((row >> 1) & 3)); }
 
 // DMMAs of one k-slab for one warp: warp tile 16 rows x (8*NFR) levels (2 x NFR fragments of 8x8, K = 16 in 4 steps).
-// NFR = column blocks (8 levels) of the chunk that hold real levels; k-steps >= ks_lim only touch zero padding.
-template <int NFR, int LR>
+// NFR = column blocks (8 levels) of the chunk that hold real levels; KS = k-steps of the slab that hold real rows
+// (the zero padding at the end of a direction block is skipped).
+template <int NFR, int LR, int OWN, int KS>
 __device__ __forceinline__ void slab_mma(double (&acc)[2][8][2], double (&tacc)[2], const double *__restrict__ a,
-                                         const double *__restrict__ v, const double *__restrict__ b, bool own, int wr, int gq,
-                                         int tq, int ks_lim)
+                                         const double *__restrict__ v, const double *__restrict__ b, int wr, int gq, int tq)
 {
   const int swz = 4 * (gq & 3);
 #pragma unroll
-  for (int ks4 = 0; ks4 < SOS_KB / 4; ++ks4) {
-    if (ks4 >= ks_lim) break;                                // uniform; false for 14 of 16 slabs
+  for (int ks4 = 0; ks4 < KS; ++ks4) {
     const int kc = (ks4 * 4 + tq) ^ swz;
-    if (own) {
+    if (OWN) {
       const double a0 = a[kc], a1 = a[8 * SOS_KB + kc];
       double bv[NFR];
 #pragma unroll
@@ -108,30 +107,70 @@ __device__ __forceinline__ void slab_mma(double (&acc)[2][8][2], double (&tacc)[
   }
 }
 
-template <int LR>
-__device__ __forceinline__ void slab_dispatch(int nfr, double (&acc)[2][8][2], double (&tacc)[2], const double *a, const double *v,
-                                              const double *b, bool own, int wr, int gq, int tq, int ks_lim)
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity)
 {
-  switch (nfr) {
-    case 8: slab_mma<8, LR>(acc, tacc, a, v, b, own, wr, gq, tq, ks_lim); break;
-    case 7: slab_mma<7, LR>(acc, tacc, a, v, b, own, wr, gq, tq, ks_lim); break;
-    case 6: slab_mma<6, LR>(acc, tacc, a, v, b, own, wr, gq, tq, ks_lim); break;
-    case 5: slab_mma<5, LR>(acc, tacc, a, v, b, own, wr, gq, tq, ks_lim); break;
-    case 4: slab_mma<4, LR>(acc, tacc, a, v, b, own, wr, gq, tq, ks_lim); break;
-    case 3: slab_mma<3, LR>(acc, tacc, a, v, b, own, wr, gq, tq, ks_lim); break;
-    case 2: slab_mma<2, LR>(acc, tacc, a, v, b, own, wr, gq, tq, ks_lim); break;
-    default: slab_mma<1, LR>(acc, tacc, a, v, b, own, wr, gq, tq, ks_lim); break;
+  unsigned ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+// The k-slabs of one level chunk for one warp.  The readiness of the NEXT stage is probed while the DMMAs of the current
+// slab are in flight, so the blocking wait at the top of a slab is normally skipped.
+template <int NFR, int LR, int OWN>
+__device__ __forceinline__ void chunk_mma(double (&acc)[2][8][2], double (&tacc)[2], const unsigned char *sStage,
+                                          unsigned long long *full, unsigned long long *empty, unsigned &q, int n_slab, int HB,
+                                          int N3, int wr, int lane, int gq, int tq)
+{
+  bool ready = mbar_test(full + q % SW_STG, (q / SW_STG) & 1);
+  for (int slab = 0; slab < n_slab; ++slab, ++q) {
+    const int st = q % SW_STG;
+    if (!ready) mbar_wait(full + st, (q / SW_STG) & 1);
+    const unsigned char *sp = sStage + st * SW_STAGE;
+    const double *a = reinterpret_cast<const double *>(sp) + (wr * 16 + gq) * SOS_KB;
+    const double *v = reinterpret_cast<const double *>(sp + SW_A_BYTES) + gq * SOS_KB;
+    const double *b = reinterpret_cast<const double *>(sp + SW_A_BYTES + SW_V_BYTES) + tq * SOS_SB + gq;
+    const int kq = (slab * SOS_KB) % HB;
+    ready = mbar_test(full + (q + 1) % SW_STG, ((q + 1) / SW_STG) & 1);   // result is consumed after this slab's DMMAs
+    if (kq + SOS_KB <= N3) slab_mma<NFR, LR, OWN, 4>(acc, tacc, a, v, b, wr, gq, tq);
+    else {                                                     // tail of a direction block: k-steps of pure padding skipped
+      const int ks_lim = max(0, (N3 - kq + 3) >> 2);
+      if (ks_lim == 3) slab_mma<NFR, LR, OWN, 3>(acc, tacc, a, v, b, wr, gq, tq);
+      else if (ks_lim == 2) slab_mma<NFR, LR, OWN, 2>(acc, tacc, a, v, b, wr, gq, tq);
+      else if (ks_lim == 1) slab_mma<NFR, LR, OWN, 1>(acc, tacc, a, v, b, wr, gq, tq);
+      else if (ks_lim >= 4) slab_mma<NFR, LR, OWN, 4>(acc, tacc, a, v, b, wr, gq, tq);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + st);
   }
 }
 
-struct Unit {                                                  // decoded work unit (uniform per CTA)
-  int item, dir, g0, ng, R, r0, N, HB, KP, NT, L, n_chunk, n_slab, lr, valid;
+template <int LR, int OWN>
+__device__ __forceinline__ void chunk_dispatch(int nfr, double (&acc)[2][8][2], double (&tacc)[2], const unsigned char *sStage,
+                                               unsigned long long *full, unsigned long long *empty, unsigned &q, int n_slab, int HB,
+                                               int N3, int wr, int lane, int gq, int tq)
+{
+  switch (nfr) {
+    case 8: chunk_mma<8, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
+    case 7: chunk_mma<7, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
+    case 6: chunk_mma<6, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
+    case 5: chunk_mma<5, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
+    case 4: chunk_mma<4, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
+    case 3: chunk_mma<3, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
+    case 2: chunk_mma<2, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
+    default: chunk_mma<1, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
+  }
+}
+
+struct Unit {                                                  // decoded work unit (uniform per CTA), 64 bytes
+  int item, dir, g0, ng, R, r0, N, HB, KP, NT, L, n_chunk, n_slab, lr, valid, w;
 };
 
 __device__ __forceinline__ Unit decode_unit(int w, const ItemDev *items, const TermDev *terms, const OpticsDev *optics,
                                             const KsetDev *ksets, const int *list, int tiles_per_dir)
 {
   Unit u;
+  u.w = w;
   const int per_item = 2 * tiles_per_dir;
   const int ii = w / per_item, t = w - ii * per_item;
   u.item = list ? list[ii] : ii;
@@ -144,7 +183,7 @@ __device__ __forceinline__ Unit decode_unit(int w, const ItemDev *items, const T
   const int groups = u.HB >> 4;
   const int gpt = (groups + tiles_per_dir - 1) / tiles_per_dir;
   u.g0 = tile * gpt;
-  u.valid = u.g0 < groups;
+  u.valid = (u.g0 < groups) && it.active;                      // inactive: IGMAX < 2 (SOS_OS.F:1152)
   u.ng = u.valid ? min(gpt, groups - u.g0) : 0;
   u.R = u.ng * 16;
   u.r0 = u.dir * u.HB + u.g0 * 16;
@@ -175,8 +214,8 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
   unsigned long long *full = bars, *empty = bars + SW_STG;
   unsigned long long *acc_full = bars + 2 * SW_STG, *acc_empty = acc_full + 1, *tab_full = acc_full + 2, *tab_empty = acc_full + 3;
   unsigned long long *work_full = acc_full + 4, *work_empty = acc_full + 6;       // [2] each
-  int *sWork = reinterpret_cast<int *>(acc_full + 8);                               // [2]
-  double *sAtt = reinterpret_cast<double *>(acc_full + 10);                         // [<=66][N] exp(-dtau/mu_k)
+  Unit *sUnit = reinterpret_cast<Unit *>(acc_full + 8);                             // [2] decoded work units (64 bytes each)
+  double *sAtt = reinterpret_cast<double *>(acc_full + 24);                         // [<=66][N] exp(-dtau/mu_k)
 
   const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5;
   if (tid == 0) {
@@ -197,12 +236,14 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
       int w = (int)atomicAdd(work_counter, 1u);
       if (w >= nwork) w = -1;
       const int slot = wn & 1;
+      Unit u;
+      if (w >= 0) u = decode_unit(w, items, terms, optics, ksets, list, tiles_per_dir);
+      else { u = Unit{}; u.w = -1; }
       if (wn >= 2) mbar_wait(work_empty + slot, ((wn >> 1) - 1) & 1);
-      sWork[slot] = w;
+      sUnit[slot] = u;                                           // the other roles take the decoded unit from shared memory
       mbar_arrive(work_full + slot);
       ++wn;
       if (w < 0) break;
-      const Unit u = decode_unit(w, items, terms, optics, ksets, list, tiles_per_dir);
       if (!u.valid) continue;
       const ItemDev &it = items[u.item];
       const TermDev &tm = terms[it.term];
@@ -252,12 +293,11 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
     while (true) {
       const int slot = wn & 1;
       mbar_wait(work_full + slot, (wn >> 1) & 1);
-      const int w = sWork[slot];
+      const Unit u = sUnit[slot];
       __syncwarp();
       if (lane == 0) mbar_arrive(work_empty + slot);
       ++wn;
-      if (w < 0) break;
-      const Unit u = decode_unit(w, items, terms, optics, ksets, list, tiles_per_dir);
+      if (u.w < 0) break;
       if (!u.valid) continue;
       const bool own = wr < u.ng;
       const bool up = (u.dir == 0);
@@ -270,19 +310,12 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
 #pragma unroll
           for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
         tacc[0] = tacc[1] = 0.0;
-        for (int slab = 0; slab < u.n_slab; ++slab, ++q) {
-          const int st = q % SW_STG;
-          mbar_wait(full + st, (q / SW_STG) & 1);
-          const unsigned char *sp = sStage + st * SW_STAGE;
-          const double *a = reinterpret_cast<const double *>(sp) + (wr * 16 + gq) * SOS_KB;
-          const double *v = reinterpret_cast<const double *>(sp + SW_A_BYTES) + gq * SOS_KB;
-          const double *b = reinterpret_cast<const double *>(sp + SW_A_BYTES + SW_V_BYTES) + tq * SOS_SB + gq;
-          const int kq = (slab * SOS_KB) % u.HB;
-          const int ks_lim = (kq + SOS_KB <= 3 * u.N) ? 4 : max(0, (3 * u.N - kq + 3) >> 2);
-          if (u.lr) slab_dispatch<1>(nfr, acc, tacc, a, v, b, own, wr, gq, tq, ks_lim);
-          else if (own) slab_dispatch<0>(nfr, acc, tacc, a, v, b, true, wr, gq, tq, ks_lim);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(empty + st);
+        if (u.lr) {
+          if (own) chunk_dispatch<1, 1>(nfr, acc, tacc, sStage, full, empty, q, u.n_slab, u.HB, 3 * u.N, wr, lane, gq, tq);
+          else chunk_dispatch<1, 0>(nfr, acc, tacc, sStage, full, empty, q, u.n_slab, u.HB, 3 * u.N, wr, lane, gq, tq);
+        } else {
+          if (own) chunk_dispatch<0, 1>(nfr, acc, tacc, sStage, full, empty, q, u.n_slab, u.HB, 3 * u.N, wr, lane, gq, tq);
+          else chunk_dispatch<0, 0>(nfr, acc, tacc, sStage, full, empty, q, u.n_slab, u.HB, 3 * u.N, wr, lane, gq, tq);
         }
         // ---- hand the raw accumulators to the recurrence warps ----
         if (accn >= 1) mbar_wait(acc_empty, (accn - 1) & 1);
@@ -311,12 +344,11 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
     while (true) {
       const int slot = wn & 1;
       mbar_wait(work_full + slot, (wn >> 1) & 1);
-      const int w = sWork[slot];
+      const Unit u = sUnit[slot];
       __syncwarp();
       if (lane == 0) mbar_arrive(work_empty + slot);
       ++wn;
-      if (w < 0) break;
-      const Unit u = decode_unit(w, items, terms, optics, ksets, list, tiles_per_dir);
+      if (u.w < 0) break;
       if (!u.valid) continue;
       const ItemDev &it = items[u.item];
       const TermDev &tm = terms[it.term];
@@ -496,7 +528,7 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
 
 static size_t sweep_smem_bytes(int att_rows_cap, int nmax)
 {
-  return (size_t)SW_STG * SW_STAGE + (size_t)128 * SW_ACC_PITCH * 8 + (4 * SOS_CH + 4 * 72 + 3 * 80) * 8 + (2 * SW_STG + 10) * 8 +
+  return (size_t)SW_STG * SW_STAGE + (size_t)128 * SW_ACC_PITCH * 8 + (4 * SOS_CH + 4 * 72 + 3 * 80) * 8 + (2 * SW_STG + 24) * 8 +
          (size_t)att_rows_cap * nmax * 8 + 128;
 }
 
