@@ -187,6 +187,16 @@ int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double *rmu, cons
                       const double *i1, const double *q1, const double *u1, const double *bc_reserved,
                       double *i1n, double *q1n, double *u1n, double *i2, double *q2, double *u2);
 
+/* Direct-beam terms of the land-surface models in SOS_TRPHI (SOS_TRPHI.F:1047-1200: Roujean BRDF, Rondeaux / Breon /
+ * Maignan / Nadal BPDF; helpers SOS_ROUJEAN.F:891-1022, SOS_SURFACE_BPDF.F:1606-1641).  The selection applies to the
+ * following sosgpu_trphi_option / sosgpu_batch_trphi calls of the context; NULL switches all of them off. */
+typedef struct {
+  int iroujean; double k0, k1, k2;
+  int irondeaux, ibreon, inadal; double alpha_nadal, beta_nadal;
+  int imaignan; double coef_c_maignan;
+} sosgpu_direct_models;
+int sosgpu_set_direct_models(sosgpu_ctx *ctx, const sosgpu_direct_models *dm);
+
 /* SOS_TRPHI_OPTION / SOS_TRPHI (SOS_TRPHI.F:285-636, 749-1243): Fourier synthesis on the view
  * azimuths + glitter / flat-sea direct terms.  rec: [nrec][3][2N+1].  Tables [7][nphi_cap][N] in the
  * order SCA, I, Q, U, POL_ANG, POL_RATE, L_POL; returns the number of azimuth slots or <0. */
@@ -208,6 +218,12 @@ int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *batch, int igli, double wi
  * il_out (may be NULL): [N(N+1)/2] lengths IL of the G series per (theta1 >= theta2) pair. */
 int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
                    int os_nm, double wind, double ind_surf, float *surf, int *il_out);
+
+/* SOS_MAT_FRESNEL (SOS_SURFACE.F:1235-1603): Legendre expansion of the Fresnel reflection matrix for the refractive index
+ * ind_surf on the quadrature (rmu, chr: [2N+1]); returns what the reference's RES_FRESNEL file holds, i.e. the coefficients
+ * [os_ns+1] after the 4(E15.8) decimal round trip. */
+int sosgpu_mat_fresnel(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *chr, double ind_surf, int os_ns,
+                       double *alpha, double *beta, double *gamma, double *zeta);
 
 /* ---- gfortran-ABI drop-in symbols (F77 by-reference, fixed SOS.h strides, hidden string lengths) */
 /* SOS_OS.F:303-308 */
@@ -245,8 +261,7 @@ void sos_glitter_(const int *lum_nbmu, const double *rmu, const double *chr, con
                   const char *fic_res_gsf, const char *fic_res_fresnel, const char *fic_res_mat_reflex,
                   const char *ficglitter, const int *trace, int *ier,
                   size_t len_gsf, size_t len_fresnel, size_t len_mat, size_t len_ficglitter);
-/* SOS_TRPHI.F:749-755: one azimuth (radians); IER=-1 when a Roujean/Rondeaux/Breon/Nadal/Maignan direct term is
- * requested (not provided) */
+/* SOS_TRPHI.F:749-755: one azimuth (radians), incl. the Roujean / Rondeaux / Breon / Nadal / Maignan direct terms */
 void sos_trphi_(const char *fichos, const int *nbmu, const double *rmu, const double *tau,
                 const double *tauout, const double *phi, const int *igli, const int *n0, const double *wind,
                 const double *ind_surf, const int *ifresnel, const int *iroujean, const double *k0,

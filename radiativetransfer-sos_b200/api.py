@@ -50,6 +50,12 @@ class CGroupOut(C.Structure):
                 ("ttot_vrai", c_dp), ("tauout", c_dp)]
 
 
+class CDirectModels(C.Structure):
+    _fields_ = [("iroujean", C.c_int), ("k0", C.c_double), ("k1", C.c_double), ("k2", C.c_double),
+                ("irondeaux", C.c_int), ("ibreon", C.c_int), ("inadal", C.c_int), ("alpha_nadal", C.c_double),
+                ("beta_nadal", C.c_double), ("imaignan", C.c_int), ("coef_c_maignan", C.c_double)]
+
+
 class CStats(C.Structure):
     _fields_ = [("steps", C.c_longlong), ("flops", C.c_double), ("bytes", C.c_double), ("step_ms", C.c_double),
                 ("step_launches", C.c_longlong), ("total_ms", C.c_double), ("launches", C.c_longlong)]
@@ -85,6 +91,7 @@ def load_library():
         lib.sosgpu_batch_stats.argtypes = [C.c_void_p, C.POINTER(CStats)]
         lib.sosgpu_batch_group_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         lib.sosgpu_group_finalize.argtypes = [c_dp, c_dp, c_dp, C.c_int]
+        lib.sosgpu_set_direct_models.argtypes = [C.c_void_p, C.POINTER(CDirectModels)]
         lib.sosgpu_comm_unique_id.argtypes = [C.c_char_p]
         lib.sosgpu_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
         lib.sosgpu_comm_destroy.argtypes = [C.c_void_p]
@@ -166,6 +173,19 @@ class Solver:
     @property
     def launches(self):
         return int(self.lib.sosgpu_launch_count(self.ctx))
+
+    def set_direct_models(self, roujean=None, irondeaux=0, ibreon=0, nadal=None, maignan=None):
+        """Direct-beam terms of the land-surface models in SOS_TRPHI (SOS_TRPHI.F:1047-1200) for the following synthesis
+        calls: roujean=(k0,k1,k2), nadal=(alpha,beta), maignan=coef_c; no argument switches them all off."""
+        dm = CDirectModels()
+        if roujean is not None:
+            dm.iroujean, dm.k0, dm.k1, dm.k2 = 1, roujean[0], roujean[1], roujean[2]
+        dm.irondeaux, dm.ibreon = int(irondeaux), int(ibreon)
+        if nadal is not None:
+            dm.inadal, dm.alpha_nadal, dm.beta_nadal = 1, nadal[0], nadal[1]
+        if maignan is not None:
+            dm.imaignan, dm.coef_c_maignan = 1, maignan
+        self._check(self.lib.sosgpu_set_direct_models(self.ctx, C.byref(dm)), "set_direct_models")
 
     def set_options(self, field_budget_bytes=0, max_wave_orders=0):
         self.lib.sosgpu_set_options(self.ctx, field_budget_bytes, max_wave_orders)
@@ -409,6 +429,14 @@ class Solver:
                                      surf.ctypes.data_as(c_fp), il.ctypes.data_as(c_ip))
         self._check(rc, "glitter")
         return surf, il
+
+    def mat_fresnel(self, nbmu, rmu, chr_, ind_surf, os_ns):
+        """SOS_MAT_FRESNEL (SOS_SURFACE.F:1235): alpha, beta, gamma, zeta [os_ns+1] as the RES_FRESNEL file holds them."""
+        out = [np.zeros(os_ns + 1) for _ in range(4)]
+        rc = self.lib.sosgpu_mat_fresnel(self.ctx, C.c_int(nbmu), _d(_f64(rmu)), _d(_f64(chr_)), C.c_double(ind_surf),
+                                         C.c_int(os_ns), _d(out[0]), _d(out[1]), _d(out[2]), _d(out[3]))
+        self._check(rc, "mat_fresnel")
+        return out
 
     def batch_trphi(self, batch, igli, wind, ind_surf, ifresnel, itrphi, phios, pas_phi, ipolar, download=True):
         """SOS_TRPHI_OPTION for every wavelength of a resident batch (after run); tables [ngroup, 7, nphi, Nmax]."""

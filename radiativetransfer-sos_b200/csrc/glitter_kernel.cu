@@ -248,3 +248,89 @@ extern "C" void sos_launch_glitter(GlitterParams p, float *surf, int *il_out, cu
   const size_t smem = (size_t)(PH_NU + 1 + p.os_nm + p.os_ns + p.os_nb + 2 + 12 * (p.os_ns + 1)) * sizeof(double);
   k_glitter<<<npair, 256, smem, st>>>(p, surf, il_out);
 }
+
+
+// =================================================================================================
+// SOS_MAT_FRESNEL (SOS_SURFACE.F:1235-1603): Legendre / generalised-Legendre expansion of the Fresnel reflection matrix
+// by Gauss quadrature.  One block; thread k owns expansion order k: it runs the polynomial recurrences up to its own order
+// for every quadrature angle and accumulates in the reference's angle order (j = -N..N), so every coefficient is the
+// reference's own sequence of operations (the recurrences are recomputed per thread instead of shared: O(NS^2 N) flops,
+// microseconds).  out: [4][ns+1] = ALPHA, BETA, GAMMA, ZETA before the 4(E15.8) text channel (rounded on the host).
+__global__ void k_mat_fresnel(int N, const double *__restrict__ rmu, const double *__restrict__ chr, double ind, int ns,
+                              double *__restrict__ out)
+{
+  extern __shared__ double sh[];
+  double *r11 = sh, *r12 = sh + (2 * N + 1), *r33 = sh + 2 * (2 * N + 1);
+  double *beta = sh + 3 * (2 * N + 1), *delta = beta + (ns + 1), *gamma = delta + (ns + 1);
+  const int W = 2 * N + 1;
+  for (int t = threadIdx.x; t < W; t += blockDim.x) {           // :1346-1381
+    const int j = t - N;
+    if (j == 0) continue;
+    double c = rmu[t];
+    c = sqrt(.5 * (1 + c));
+    const double a = sqrt(ind * ind - 1.0 + c * c), b = ind * ind * c;
+    const double rl = -(b - a) / (b + a), rr = (c - a) / (c + a);
+    r11[t] = .5 * (rl * rl + rr * rr); r12[t] = .5 * (rl * rl - rr * rr); r33[t] = rl * rr;
+  }
+  __syncthreads();
+  const double sq6 = sqrt(6.0);
+  for (int k = threadIdx.x; k <= ns; k += blockDim.x) {
+    double bk = 0.0, dk = 0.0, gk = 0.0;
+    for (int j = -N; j <= N; ++j) {
+      if (j == 0) continue;
+      const double xrmu = rmu[j + N];
+      // Legendre recurrence (:1387-1400, :1448-1454): PL(K+1) after K steps starting from PL(-1)=0, PL(0)=1
+      double p0 = 0.0, p1 = 1.0;
+      for (int kk = 0; kk < k; ++kk) {
+        const double p2 = ((2 * kk + 1.) * xrmu * p1 - kk * p0) / (kk + 1.);
+        p0 = p1; p1 = p2;
+      }
+      bk = bk + (r11[j + N] * chr[j + N]) * p1;
+      dk = dk + (chr[j + N] * r33[j + N]) * p1;
+      if (k >= 2) {                                             // generalised function POL(K) (:1433-1447)
+        double q0 = 0.0, q1 = 3. * (1. - xrmu * xrmu) / 2. / sq6;   // POL(1), POL(2)
+        for (int kk = 2; kk < k; ++kk) {
+          const double d = (2. * kk + 1.) / sqrt(1.0 * (kk + 3.) * (kk - 1.));
+          const double e = sqrt(1.0 * (kk + 2.) * (kk - 2.)) / (2. * kk + 1.);
+          const double q2 = d * (xrmu * q1 - e * q0);
+          q0 = q1; q1 = q2;
+        }
+        gk = gk + (chr[j + N] * r12[j + N]) * q1;
+      }
+    }
+    beta[k] = (2 * k + 1) * bk * .5;                            // :1404
+    delta[k] = dk * (2. * k + 1.) * .5;                         // :1460-1463
+    gamma[k] = gk * (2. * k + 1.) * .5;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= ns; i += blockDim.x) {         // :1521-1546 (CO1, CO2 are REAL*4 expressions)
+    double al = 0.0, ze = 0.0;
+    if (i >= 2) {
+      const float co1f = 4 * (2 * i + 1.f) / (float)i / (i - 1.f) / (i + 1.f) / (i + 2.f);
+      const float co2f = i * (i - 1.f) / ((i + 1.f) * (i + 2.f));
+      const double co1 = co1f;
+      double co2 = co2f;
+      const double co3 = co2 * delta[i];
+      co2 = co2 * beta[i];
+      const int nn = (int)(i * .5f), mm = (int)((i - 1) * .5f);
+      double som1 = 0, som2 = 0, som3 = 0, som4 = 0;
+      for (int j = 1; j <= nn; ++j) {
+        const double x2 = (double)((i - 1.f) * (i - 1.f) - 3.f * (2 * j - 1.f) * (i - j));
+        som1 = som1 + x2 * beta[i - 2 * j]; som2 = som2 + x2 * delta[i - 2 * j];
+      }
+      for (int j = 0; j <= mm; ++j) {
+        const double x2 = (double)((i - 1.f) * (i - 1.f) - 3.f * j * (2 * i - 2 * j - 1.f));
+        som3 = som3 + x2 * beta[i - 2 * j - 1]; som4 = som4 + x2 * delta[i - 2 * j - 1];
+      }
+      ze = co3 - co1 * (som2 - som3);
+      al = co2 - co1 * (som1 - som4);
+    }
+    out[i] = al; out[(ns + 1) + i] = beta[i]; out[2 * (ns + 1) + i] = gamma[i]; out[3 * (ns + 1) + i] = ze;
+  }
+}
+
+extern "C" void sos_launch_mat_fresnel(int N, const double *rmu, const double *chr, double ind, int ns, double *out, cudaStream_t st)
+{
+  const size_t smem = (size_t)(3 * (2 * N + 1) + 3 * (ns + 1)) * sizeof(double);
+  k_mat_fresnel<<<1, 160, smem, st>>>(N, rmu, chr, ind, ns, out);
+}

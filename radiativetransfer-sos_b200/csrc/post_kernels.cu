@@ -63,6 +63,42 @@ __device__ static void matric(double coskip, double r11, double r12, double &m11
   m21 = c2 * r12;
   m31 = s2 * r12;
 }
+// SOS_CALC_F_ROUJEAN, SOS_ROUJEAN.F:891-1022 (CTE_TETAS/TETAV_LIM_ROUJEAN = 60 degrees, CTE_SEUIL_NUM = 1.D-10: SOS.h:347,355,361)
+__device__ static double calc_f_roujean(double k0, double k1, double k2, double c1, double s1, double c2, double s2, double phi)
+{
+  const double pi = 4.0 * atan(1.0);
+  double xphi = phi;
+  if (xphi < 0.0) xphi = -xphi;
+  if (xphi > pi) xphi = 2. * pi - xphi;
+  double xc1 = c1, xs1 = s1, xc2 = c2, xs2 = s2;
+  if (acos(c1) * 180. / pi > 60) { xc1 = cos(60 * pi / 180.0); xs1 = sin(60 * pi / 180.0); }
+  if (acos(c2) * 180. / pi > 60) { xc2 = cos(60 * pi / 180.0); xs2 = sin(60 * pi / 180.0); }
+  const double cosphi = cos(xphi);
+  const double tants = xs1 / xc1, tantv = xs2 / xc2;
+  double f1 = 0.5 * ((pi - xphi) * cosphi + sin(xphi)) * tants * tantv;
+  f1 = f1 - tants - tantv;
+  f1 = f1 - sqrt(tants * tants + tantv * tantv - 2. * tantv * tants * cosphi);
+  f1 = f1 / pi;
+  double coszeta = xc1 * xc2 + xs1 * xs2 * cosphi;
+  if (fabs(fabs(coszeta) - 1.0) <= 1.e-10) {
+    if ((coszeta >= (1. - 1.e-10)) && (coszeta <= (1. + 1.e-10))) coszeta = 1.0;
+    else coszeta = -1.0;
+  }
+  const double zeta = acos(coszeta);
+  double f2 = 4. * ((pi / 2. - zeta) * coszeta + sin(zeta)) / (3. * pi * (xc1 + xc2));
+  f2 = f2 - (1.0 / 3.0);
+  double f = k0 + k1 * f1 + k2 * f2;
+  f = f * c2 * c1;
+  return f;
+}
+// SOS_CALCG_MAIGNAN, SOS_SURFACE_BPDF.F:1606-1641
+__device__ static double calcg_maignan(double c1, double c2, double s12, double phi, double coef_c)
+{
+  const double cos_2i = c1 * c2 - s12 * cos(phi);
+  double tan2_i = (1 - cos_2i) / (1 + cos_2i);
+  if (tan2_i < 0.0) tan2_i = 0.0;
+  return coef_c * exp(-sqrt(tan2_i)) / (1. / c1 + 1. / c2);
+}
 // SOS_POLAR, SOS_TRPHI.F:1843-1907
 __device__ static void polar(double xi, double xq, double xu, double pi, double &xan, double &tpol, double &lpol)
 {
@@ -133,6 +169,54 @@ __global__ void k_trphi(const TrphiGroup *groups, const double *phis, int nphi, 
         xi = xi + r11 * coef_sun * atj;
         if (prm.ipolar == 1) xq = xq + r12 * coef_sun * atj;
       }
+    }
+    if (prm.iroujean == 1 && j > 0) {                          // Roujean BRDF direct term (:1047-1072)
+      const double at0 = exp(-g.tau / c0);
+      const double s0 = sqrt(1.0 - c0 * c0);
+      const double c1 = rmuj;
+      const double atj = at0 * exp(-(g.tau - g.tauout) / c1);
+      const double s1 = sqrt(1.0 - c1 * c1);
+      const double phirj = pi - phi;
+      const double f = calc_f_roujean(prm.k0, prm.k1, prm.k2, c0, s0, c1, s1, phirj);
+      xi = xi + atj * f / c1;
+    }
+    if ((prm.irondeaux == 1 || prm.ibreon == 1 || prm.imaignan == 1) && j > 0) {   // vegetation / soil BPDF (:1080-1122)
+      const double at0 = exp(-g.tau / c0);
+      const double s0 = sqrt(1.0 - c0 * c0);
+      const double c1 = rmuj;
+      const double atj = at0 * exp(-(g.tau - g.tauout) / c1);
+      double coskip, cosdif, r11, r12, r33, m11, m21, m31;
+      angle(c0, c1, phi, coskip, cosdif);
+      reflex(cosdif, prm.ind_surf, r11, r12, r33);
+      matric(coskip, r11, r12, m11, m21, m31);
+      double p = 0.0;
+      if (prm.irondeaux == 1) p = 1. / (4. * (1 + c1 / c0));
+      if (prm.ibreon == 1) p = 1. / (4. * c1);
+      if (prm.imaignan == 1) {
+        const double s1 = sqrt(1.0 - c1 * c1);
+        const double s12 = s0 * s1;
+        p = calcg_maignan(c0, c1, s12, phi, prm.coef_c_maignan);
+        p = p / (4. * c1);
+      }
+      xi = xi + m11 * atj * p;
+      if (prm.ipolar == 1) { xq = xq + m21 * atj * p; xu = xu + m31 * atj * p; }
+    }
+    if (prm.inadal == 1 && j > 0) {                            // Nadal BPDF (:1130-1178)
+      const double at0 = exp(-g.tau / c0);
+      const double c1 = rmuj;
+      const double atj = at0 * exp(-(g.tau - g.tauout) / c1);
+      double coskip, cosdif, r11, r12, r33, m11, m21, m31;
+      angle(c0, c1, phi, coskip, cosdif);
+      reflex(cosdif, prm.ind_surf, r11, r12, r33);
+      matric(coskip, r11, r12, m11, m21, m31);
+      const double f21fresnel = -r12;
+      double f21nadal = -prm.beta_nadal * f21fresnel / (c0 + c1);
+      f21nadal = prm.alpha_nadal * (1.0 - exp(f21nadal));
+      double p;
+      if (f21fresnel < 1.0e-10) p = prm.alpha_nadal * prm.beta_nadal / (c0 + c1);
+      else p = f21nadal / f21fresnel;
+      xi = xi + m11 * atj * p;
+      if (prm.ipolar == 1) { xq = xq + m21 * atj * p; xu = xu + m31 * atj * p; }
     }
     if (xi <= 1.e-99) xi = 0.0;                                // :1212-1218
     if (fabs(xq) < THRESHOLD_QU) xq = 0.0;

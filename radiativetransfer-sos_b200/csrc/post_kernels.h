@@ -12,6 +12,11 @@ struct TrphiGroup {          // one aggregated wavelength
 struct TrphiParams {
   int igli, ifresnel, ipolar;
   double wind, ind_surf, pi;
+  // direct-beam terms of the land-surface models (SOS_TRPHI.F:1047-1200); all zero = none
+  int iroujean, irondeaux, ibreon, inadal, imaignan;
+  double k0, k1, k2;                 // Roujean BRDF
+  double alpha_nadal, beta_nadal;    // Nadal BPDF
+  double coef_c_maignan;             // Maignan BPDF
 };
 struct GlitterParams {       // SOS_GLITTER (SOS_GLITTER.F:229): one surface file
   int nbmu, os_nb, os_ns, os_nm;
@@ -23,6 +28,8 @@ struct GlitterParams {       // SOS_GLITTER (SOS_GLITTER.F:229): one surface fil
 extern "C" {
 #endif
 void sos_launch_glitter(GlitterParams p, float *surf, int *il_out, cudaStream_t st);
+// SOS_MAT_FRESNEL: out [4][ns+1] = ALPHA, BETA, GAMMA, ZETA (unrounded); rmu, chr: [2N+1] device
+void sos_launch_mat_fresnel(int N, const double *rmu, const double *chr, double ind, int ns, double *out, cudaStream_t st);
 void sos_launch_trphi(const TrphiGroup *groups, int ngroup, const double *phis, int nphi,
                       TrphiParams prm, double *out, cudaStream_t st);
 void sos_launch_trphi_stride(const TrphiGroup *groups, int ngroup, const double *phis, int nphi, int nout,

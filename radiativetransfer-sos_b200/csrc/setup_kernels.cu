@@ -281,7 +281,12 @@ __global__ void k_pack_v(const KsetDev *ksets, const OpticsDev *optics)
 }
 
 // ------------------------------------------------------------------------------------------------
-// att[layer][k-1] = exp(-dt[layer]/mu_k)  (SOS_OS.F:2291 DEXP(-DTAU/RMUK); :2335 is the same value)
+// att[layer][k-1] = a = exp(-dt[layer]/mu_k)  (SOS_OS.F:2291 DEXP(-DTAU/RMUK); :2335 is the same value), and the two weights
+// of the layer integration in the form the sweep kernel uses:  with S the source function at the two levels of the layer,
+//   SOS_OS.F:2288-2309:  (1-a)*(A*mu + S_i) - A*a*dt,  A = (S_j - S_i)/dt   ==   (1 - a - g)*S_i + g*S_j,
+//   g = (1-a)*mu/dt - a   (same g for the downward sweep, :2332-2353).
+// g = x/2 - x^2/3 + ... for x = dt/mu -> 0: the closed form cancels there, so small x uses the series
+// g = sum_{n>=1} (-1)^(n+1) n x^n / (n+1)!  (error below 1e-17 for x < 0.25 with 14 terms).
 __global__ void k_att(const TermDev *terms, const OpticsDev *optics)
 {
   const TermDev tm = terms[blockIdx.y];
@@ -290,7 +295,31 @@ __global__ void k_att(const TermDev *terms, const OpticsDev *optics)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= tm.nt * N) return;
   const int layer = idx / N, k = idx % N + 1;
-  const_cast<double *>(tm.att)[idx] = exp(-tm.dt[layer] / op.rmu[k + N]);
+  const double x = tm.dt[layer] / op.rmu[k + N];
+  const double a = exp(-tm.dt[layer] / op.rmu[k + N]);
+  const_cast<double *>(tm.att)[idx] = a;
+  const double t = -expm1(-x);                                // 1 - a without cancellation
+  double g;
+  if (x < 0.25) {
+    double term = x * 0.5, sum = term;                         // n = 1
+    for (int n = 2; n <= 14; ++n) {
+      term = -term * x * (double)n / ((double)(n - 1) * (double)(n + 1));   // ratio of consecutive terms: -x n / ((n-1)(n+1))
+      sum = sum + term;
+    }
+    g = sum;
+  } else g = t / x - a;
+  const double b = t - g;
+  const_cast<double *>(tm.gco)[idx] = g;
+  const_cast<double *>(tm.bco)[idx] = b;
+  // Aerosol-only Fourier orders (S = XDEL * accumulator): weights with XDEL folded in, indexed by the level they update.
+  //   upward   level i = layer,     neighbour i+1:  c = pup[i]*acc(i) + qup[i]*acc(i+1)
+  //   downward level i = layer + 1, neighbour i-1:  c = pdn[i]*acc(i) + qdn[i]*acc(i-1)
+  const double xd_lo = tm.xdel[layer], xd_hi = tm.xdel[layer + 1];
+  const size_t up_i = (size_t)layer * N + (k - 1), dn_i = (size_t)(layer + 1) * N + (k - 1);
+  const_cast<double *>(tm.pup)[up_i] = b * xd_lo;
+  const_cast<double *>(tm.qup)[up_i] = g * xd_hi;
+  const_cast<double *>(tm.pdn)[dn_i] = b * xd_hi;
+  const_cast<double *>(tm.qdn)[dn_i] = g * xd_lo;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -68,6 +68,7 @@ extern "C" int sosgpu_create(sosgpu_ctx **out, int device)
   for (int k = 0; k < 8; ++k)
     if (cudaEventCreateWithFlags(&ctx->ev_cnt[k], cudaEventDisableTiming) != cudaSuccess) { sosgpu_destroy(ctx); return SOSGPU_ERR_CUDA; }
   ctx->trace = getenv("SOS_TRACE") != nullptr;
+  ctx->old_order1 = getenv("SOS_OLD_ORDER1") != nullptr;
   *out = ctx;
   return SOSGPU_OK;
 }
@@ -91,6 +92,12 @@ extern "C" void sosgpu_destroy(sosgpu_ctx *ctx)
 extern "C" const char *sosgpu_last_error(const sosgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 extern "C" long long sosgpu_launch_count(const sosgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" double sosgpu_last_kernel_ms(const sosgpu_ctx *ctx) { return ctx ? (double)ctx->last_kernel_ms : 0.0; }
+extern "C" int sosgpu_set_direct_models(sosgpu_ctx *ctx, const sosgpu_direct_models *dm)
+{
+  if (!ctx) return SOSGPU_ERR_NO_DEVICE;
+  ctx->dm = dm ? *dm : sosgpu_direct_models{};
+  return SOSGPU_OK;
+}
 extern "C" int sosgpu_set_options(sosgpu_ctx *ctx, size_t field_budget_bytes, int max_wave_orders)
 {
   if (!ctx) return SOSGPU_ERR_ARG;
@@ -315,8 +322,8 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
   b->i4_total = i4_total;
   CK(sos_dmalloc(ctx, &b->d_arena, ar.buf.size()));
   CK(cudaMemcpyAsync(b->d_arena, ar.buf.data(), ar.buf.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CK(sos_dmalloc(ctx, &b->d_att, att_total * sizeof(double)));
-  CK(cudaMemsetAsync(b->d_att, 0, att_total * sizeof(double), ctx->stream));
+  CK(sos_dmalloc(ctx, &b->d_att, 7 * att_total * sizeof(double)));      // a, g, 1-a-g, pup, qup, pdn, qdn tables (k_att)
+  CK(cudaMemsetAsync(b->d_att, 0, 7 * att_total * sizeof(double), ctx->stream));
   CK(sos_dmalloc(ctx, &b->d_i4, i4_total * sizeof(double)));
   for (int i = 0; i < noptics; ++i) {
     HostOptics &h = b->ho[i];
@@ -346,6 +353,10 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     d.inv = (const double *)(b->d_arena + o[4]); d.ch = (const double *)(b->d_arena + o[5]);
     d.cf = (const double *)(b->d_arena + o[6]);
     d.att = b->d_att + att_off[i];
+    d.gco = b->d_att + att_total + att_off[i];
+    d.bco = b->d_att + 2 * att_total + att_off[i];
+    d.pup = b->d_att + 3 * att_total + att_off[i]; d.qup = b->d_att + 4 * att_total + att_off[i];
+    d.pdn = b->d_att + 5 * att_total + att_off[i]; d.qdn = b->d_att + 6 * att_total + att_off[i];
     d.i4 = b->d_i4 + i4_off[i];
   }
   CK(sos_dmalloc(ctx, &b->d_optics, noptics * sizeof(OpticsDev)));
@@ -489,7 +500,15 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     std::vector<size_t> koff, foff, soff;
     bool has_single = false, has_dual = false;
-    for (int ti : act) {
+    // Work units are handed out dynamically in list order: longest profiles first bounds the tail of every launch to the
+    // shortest units; terms of one wavelength stay adjacent within a length class (they share the A operand in L2).
+    std::vector<int> act_sorted(act);
+    std::stable_sort(act_sorted.begin(), act_sorted.end(), [&](int x, int y) {
+      const int cx = (b->ht[x].nt + SOS_CH) / SOS_CH, cy = (b->ht[y].nt + SOS_CH) / SOS_CH;
+      if (cx != cy) return cx > cy;
+      return b->ht[x].optics < b->ht[y].optics;
+    });
+    for (int ti : act_sorted) {
       const HostTerm &ht = b->ht[ti];
       const HostOptics &ho = b->ho[ht.optics];
       for (int s = s0; s < s1 && s <= ht.iborm; ++s) {
@@ -607,8 +626,9 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     sos_launch_pack(b->d_ksets, b->d_optics, (int)nk, b->maxKP, st);
     ctx->launches += 3;
     // ---- order 1 ----
-    ctx->launches += sos_launch_step(b->d_items, b->d_terms, b->d_optics, b->d_ksets, nullptr, (int)nitem, 1, 0, b->maxHB,
-                                     nullptr, st);
+    ctx->launches += ctx->old_order1
+                         ? sos_launch_step(b->d_items, b->d_terms, b->d_optics, b->d_ksets, nullptr, (int)nitem, 1, 0, b->maxHB, nullptr, st)
+                         : sos_launch_order1(b->d_items, b->d_terms, b->d_optics, b->d_ksets, (int)nitem, b->maxKP, st);
     sos_launch_init(b->d_items, b->d_terms, b->d_optics, (int)nitem, st);
     ctx->launches += 1;
     CK(cudaGetLastError());
@@ -883,7 +903,7 @@ extern "C" int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *b, int igli, do
   CK(cudaMemcpyAsync(d_g, grp.data(), ng * sizeof(TrphiGroup), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_phi, phis.data(), nphi * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(d_out, 0, nout * 8, ctx->stream));
-  TrphiParams prm{igli, ifresnel, ipolar, wind, ind_surf, pi};
+  const TrphiParams prm = sos_trphi_params(ctx, igli, ifresnel, ipolar, wind, ind_surf, pi);
   cudaEventRecord(ctx->ev_a, ctx->stream);
   sos_launch_trphi_stride(d_g, ng, d_phi, nphi, nmax, prm, d_out, ctx->stream);
   cudaEventRecord(ctx->ev_b, ctx->stream);

@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/sosgpu.h"
 #include "sosgpu_internal.h"
+#include "post_kernels.h"
 #include <string>
 #include <vector>
 
@@ -24,7 +25,9 @@ struct sosgpu_ctx {
   cudaEvent_t ev_a = nullptr, ev_b = nullptr; float last_kernel_ms = 0.f;   // device time of the last glitter / synthesis kernel
   int *h_count = nullptr;            // pinned ring of active counts, read back with a lag (the wave loop never waits)
   cudaEvent_t ev_cnt[8] = {};        // one event per ring slot
+  sosgpu_direct_models dm = {};      // land-surface direct terms of SOS_TRPHI (sosgpu_set_direct_models)
   bool trace = false;                // SOS_TRACE, read once at create
+  bool old_order1 = false;           // SOS_OLD_ORDER1: round-1 order-1 kernel (A/B timing only)
   char *cache_field = nullptr; size_t cache_field_bytes = 0;   // wave pools parked by the last freed batch
   char *cache_kpool = nullptr; size_t cache_kpool_bytes = 0;
   double *grec_cache = nullptr; size_t grec_cache_bytes = 0;   // group-sum buffer parked by the last freed batch
@@ -99,3 +102,14 @@ struct sosgpu_batch {
   std::vector<int> g_nrec;
 };
 
+
+static inline TrphiParams sos_trphi_params(const sosgpu_ctx *ctx, int igli, int ifresnel, int ipolar, double wind, double ind_surf, double pi)
+{
+  TrphiParams p{};
+  p.igli = igli; p.ifresnel = ifresnel; p.ipolar = ipolar; p.wind = wind; p.ind_surf = ind_surf; p.pi = pi;
+  const sosgpu_direct_models &d = ctx->dm;
+  p.iroujean = d.iroujean; p.k0 = d.k0; p.k1 = d.k1; p.k2 = d.k2;
+  p.irondeaux = d.irondeaux; p.ibreon = d.ibreon; p.inadal = d.inadal; p.alpha_nadal = d.alpha_nadal; p.beta_nadal = d.beta_nadal;
+  p.imaignan = d.imaignan; p.coef_c_maignan = d.coef_c_maignan;
+  return p;
+}

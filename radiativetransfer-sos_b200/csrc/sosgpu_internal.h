@@ -46,7 +46,9 @@ struct TermDev {              // one per (wavelength, CKD term)
   const double *dt, *inv;             // [nt] layer optical thickness and reciprocal
   const double *ch;                   // [nt+1] exp(-H/(-TAB))/4  (SOS_OS.F:837-839)
   const double *cf;                   // [nt+1] flat-sea source attenuation (SOS_OS.F:3219,3278) or null
-  const double *att;                  // [nt][N] exp(-dt/mu_k)
+  const double *att;                  // [nt][N] a = exp(-dt/mu_k)
+  const double *gco, *bco;            // [nt][N] layer-integration weights g = (1-a)*mu/dt - a and 1 - a - g (k_att)
+  const double *pup, *qup, *pdn, *qdn;   // [nt+1][N] the same weights times XDEL of the two levels, per sweep direction (k_att)
   double *i4;                         // [6][2N] running Fourier sums I4,Q4,U4,I5,Q5,U5 (component order below)
 };
 
@@ -99,6 +101,9 @@ void sos_launch_aggregate(const TermDev *terms, const int *group_start, const in
 // mode bit 0: launch the aerosol-only instantiation (is > 2), bit 1: the Rayleigh+aerosol one (is <= 2)
 int  sos_launch_step(const ItemDev *items, const TermDev *terms, const OpticsDev *optics, const KsetDev *ksets,
                      const int *list, int nitem, int order1, int mode, int maxHB, double *jdump, cudaStream_t st);
+// first scattering order of every item of a wave (analytic source, boundary values, layer integration)
+int  sos_launch_order1(const ItemDev *items, const TermDev *terms, const OpticsDev *optics, const KsetDev *ksets,
+                       int nitem, int maxKP, cudaStream_t st);
 // one scattering order n >= 2 (sweep_kernel.cu): persistent warp-specialised kernel; the item count is read from
 // count_ptr on the device when non-null (nitem is then an upper bound)
 int  sos_launch_sweep(const ItemDev *items, const TermDev *terms, const OpticsDev *optics, const KsetDev *ksets,

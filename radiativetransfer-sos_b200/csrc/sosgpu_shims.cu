@@ -52,7 +52,7 @@ static int trphi_core(sosgpu_ctx *ctx, const double *rec, int nrec, int N, const
   CK(cudaMemcpyAsync(d_phi, phis.data(), nphi * 8, cudaMemcpyHostToDevice, ctx->stream));
   TrphiGroup g{d_rec, d_rmu, nrec, N, n0, W, tau, tauout};
   CK(cudaMemcpyAsync(d_g, &g, sizeof(g), cudaMemcpyHostToDevice, ctx->stream));
-  TrphiParams prm{igli, ifresnel, ipolar, wind, ind_surf, std::acos(-1.0)};
+  const TrphiParams prm = sos_trphi_params(ctx, igli, ifresnel, ipolar, wind, ind_surf, std::acos(-1.0));
   sos_launch_trphi(d_g, 1, d_phi, nphi, prm, d_out, ctx->stream);
   ctx->launches += 1;
   out.resize(nout);
@@ -99,71 +99,46 @@ static double round_e15_8(double x)
   snprintf(buf, sizeof buf, "%.7E", x);
   return strtod(buf, nullptr);
 }
-static void mat_fresnel_host(int N, const double *rmu, const double *chr, double ind, int ns,
-                             std::vector<double> &alpha, std::vector<double> &beta, std::vector<double> &gamma,
-                             std::vector<double> &zeta)
+// SOS_MAT_FRESNEL (SOS_SURFACE.F:1235-1603): the expansion runs on the device (k_mat_fresnel, glitter_kernel.cu); its result
+// reaches SOS_MAT_REFLEXION through the reference's 4(E15.8) text file (RES_FRESNEL, :1552 / :1822), i.e. rounded to 8
+// significant decimal digits -- that decimal round trip is the host's part.  d_in: [W rmu | W chr | 4*(ns+1) coefficients].
+static int mat_fresnel_device(sosgpu_ctx *ctx, int N, double ind, int ns, double *d_in, std::vector<double> &coef)
 {
-  alpha.assign(ns + 1, 0.0); beta.assign(ns + 1, 0.0); gamma.assign(ns + 1, 0.0); zeta.assign(ns + 1, 0.0);
-  std::vector<double> delta(ns + 1, 0.0), r11(2 * N + 1), r12(2 * N + 1), r33(2 * N + 1), pl(ns + 3), pol(ns + 2);
-  for (int j = -N; j <= N; ++j) {                              // :1346-1381
-    if (j == 0) continue;
-    double c = rmu[j + N];
-    c = std::sqrt(.5 * (1 + c));
-    const double a = std::sqrt(ind * ind - 1.0 + c * c), b = ind * ind * c;
-    const double rl = -(b - a) / (b + a), rr = (c - a) / (c + a);
-    r11[j + N] = .5 * (rl * rl + rr * rr); r12[j + N] = .5 * (rl * rl - rr * rr); r33[j + N] = rl * rr;
-  }
-  for (int j = -N; j <= N; ++j) {                              // :1387-1400
-    if (j == 0) continue;
-    const double x = r11[j + N] * chr[j + N], xrmu = rmu[j + N];
-    pl[0] = 0.0; pl[1] = 1.0;
-    for (int k = 0; k <= ns; ++k) {
-      pl[k + 2] = ((2 * k + 1.) * xrmu * pl[k + 1] - k * pl[k]) / (k + 1.);
-      beta[k] = beta[k] + x * pl[k + 1];
-    }
-  }
-  for (int k = 0; k <= ns; ++k) beta[k] = (2 * k + 1) * beta[k] * .5;
-  for (int j = -N; j <= N; ++j) {                              // :1433-1456
-    if (j == 0) continue;
-    const double xxx = chr[j + N] * r12[j + N], xx = chr[j + N] * r33[j + N], xrmu = rmu[j + N];
-    pol[0] = 0.0; pol[1] = 0.0; pl[0] = 0.0; pl[1] = 1.0;
-    pol[2] = 3. * (1. - xrmu * xrmu) / 2. / std::sqrt(6.0);
-    for (int k = 2; k <= ns; ++k) {
-      const double d = (2. * k + 1.) / std::sqrt(1.0 * (k + 3.) * (k - 1.));
-      const double e = std::sqrt(1.0 * (k + 2.) * (k - 2.)) / (2. * k + 1.);
-      pol[k + 1] = d * (xrmu * pol[k] - e * pol[k - 1]);
-      gamma[k] = gamma[k] + xxx * pol[k];
-    }
-    for (int k = 0; k <= ns; ++k) {
-      pl[k + 2] = ((2. * k + 1.) * xrmu * pl[k + 1] - k * pl[k]) / (k + 1.);
-      delta[k] = delta[k] + xx * pl[k + 1];
-    }
-  }
-  for (int k = 0; k <= ns; ++k) { delta[k] = delta[k] * (2. * k + 1.) * .5; gamma[k] = gamma[k] * (2. * k + 1.) * .5; }
-  for (int i = 2; i <= ns; ++i) {                              // :1521-1546 (CO1, CO2 are REAL*4 expressions)
-    const float co1f = 4 * (2 * i + 1.f) / (float)i / (i - 1.f) / (i + 1.f) / (i + 2.f);
-    const float co2f = i * (i - 1.f) / ((i + 1.f) * (i + 2.f));
-    const double co1 = co1f;
-    double co2 = co2f;
-    const double co3 = co2 * delta[i];
-    co2 = co2 * beta[i];
-    const int nn = (int)(i * .5f), mm = (int)((i - 1) * .5f);
-    double som1 = 0, som2 = 0, som3 = 0, som4 = 0;
-    for (int j = 1; j <= nn; ++j) {
-      const double x2 = (double)((i - 1.f) * (i - 1.f) - 3.f * (2 * j - 1.f) * (i - j));
-      som1 = som1 + x2 * beta[i - 2 * j]; som2 = som2 + x2 * delta[i - 2 * j];
-    }
-    for (int j = 0; j <= mm; ++j) {
-      const double x2 = (double)((i - 1.f) * (i - 1.f) - 3.f * j * (2 * i - 2 * j - 1.f));
-      som3 = som3 + x2 * beta[i - 2 * j - 1]; som4 = som4 + x2 * delta[i - 2 * j - 1];
-    }
-    zeta[i] = co3 - co1 * (som2 - som3);
-    alpha[i] = co2 - co1 * (som1 - som4);
-  }
-  for (int k = 0; k <= ns; ++k) {
-    alpha[k] = round_e15_8(alpha[k]); beta[k] = round_e15_8(beta[k]);
-    gamma[k] = round_e15_8(gamma[k]); zeta[k] = round_e15_8(zeta[k]);
-  }
+  const int W = 2 * N + 1;
+  double *d_coef = d_in + 2 * W;
+  sos_launch_mat_fresnel(N, d_in, d_in + W, ind, ns, d_coef, ctx->stream);
+  ctx->launches += 1;
+  coef.resize((size_t)4 * (ns + 1));
+  CK(cudaMemcpyAsync(coef.data(), d_coef, coef.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  for (double &v : coef) v = round_e15_8(v);
+  CK(cudaMemcpyAsync(d_coef, coef.data(), coef.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  return SOSGPU_OK;
+}
+
+extern "C" int sosgpu_mat_fresnel(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *chr, double ind_surf, int os_ns,
+                                  double *alpha, double *beta, double *gamma, double *zeta)
+{
+  if (!ctx) return SOSGPU_ERR_NO_DEVICE;
+  if (!rmu || !chr || nbmu < 1 || nbmu > SOSGPU_NBMU_MAX || os_ns < 2 || os_ns > 136) { ctx->err = "sosgpu_mat_fresnel: bad arguments"; return SOSGPU_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const int W = 2 * nbmu + 1;
+  double *d_in = nullptr;
+  CK(sos_dmalloc(ctx, &d_in, (size_t)(2 * W + 4 * (os_ns + 1)) * 8));
+  struct Guard { sosgpu_ctx *c; void *p; ~Guard() { sos_dfree(c, p); } } guard{ctx, d_in};
+  CK(cudaMemcpyAsync(d_in, rmu, W * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_in + W, chr, W * 8, cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<double> coef;
+  const int rc = mat_fresnel_device(ctx, nbmu, ind_surf, os_ns, d_in, coef);
+  if (rc != SOSGPU_OK) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t n = os_ns + 1;
+  if (alpha) memcpy(alpha, &coef[0], n * 8);
+  if (beta) memcpy(beta, &coef[n], n * 8);
+  if (gamma) memcpy(gamma, &coef[2 * n], n * 8);
+  if (zeta) memcpy(zeta, &coef[3 * n], n * 8);
+  return SOSGPU_OK;
 }
 
 // SOS_GLITTER (SOS_GLITTER.F:229-371): surface-file records of a rough sea, one fused kernel (glitter_kernel.cu)
@@ -175,24 +150,25 @@ extern "C" int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, cons
       os_nm < os_nb + os_ns || os_nm > 336) { ctx->err = "sosgpu_glitter: bad arguments"; return SOSGPU_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   const int N = nbmu, W = 2 * N + 1, npair = N * (N + 1) / 2;
-  std::vector<double> al, be, ga, ze;
-  mat_fresnel_host(N, rmu, chr, ind_surf, os_ns, al, be, ga, ze);
   const size_t nsurf = (size_t)(os_nb + 1) * 9 * N * N;
-  double *d_in = nullptr; float *d_surf = nullptr; int *d_il = nullptr;
-  CK(cudaMalloc(&d_in, (W + 4 * (os_ns + 1)) * 8));
-  CK(cudaMalloc(&d_surf, nsurf * 4));
-  CK(cudaMalloc(&d_il, npair * sizeof(int)));
+  // one block from the stream-ordered pool (no cudaMalloc / cudaFree per call): [inputs + coefficients | IL | records]
+  const size_t in_bytes = ((size_t)(2 * W + 4 * (os_ns + 1)) * 8 + 255) / 256 * 256, il_bytes = ((size_t)npair * 4 + 255) / 256 * 256;
+  char *d_blk = nullptr;
+  CK(sos_dmalloc(ctx, &d_blk, in_bytes + il_bytes + nsurf * 4));
+  struct Guard { sosgpu_ctx *c; void *p; ~Guard() { sos_dfree(c, p); } } guard{ctx, d_blk};
+  double *d_in = (double *)d_blk; int *d_il = (int *)(d_blk + in_bytes); float *d_surf = (float *)(d_blk + in_bytes + il_bytes);
   CK(cudaMemcpyAsync(d_in, rmu, W * 8, cudaMemcpyHostToDevice, ctx->stream));
-  const std::vector<double> *cf[4] = {&al, &be, &ga, &ze};
-  for (int c = 0; c < 4; ++c)
-    CK(cudaMemcpyAsync(d_in + W + c * (os_ns + 1), cf[c]->data(), (os_ns + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_in + W, chr, W * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(d_surf, 0, nsurf * 4, ctx->stream));
+  std::vector<double> coef;
+  const int rcf = mat_fresnel_device(ctx, N, ind_surf, os_ns, d_in, coef);
+  if (rcf != SOSGPU_OK) return rcf;
   GlitterParams p{};
   p.nbmu = N; p.os_nb = os_nb; p.os_ns = os_ns; p.os_nm = os_nm;
   p.sig = (double)0.003f + (double)0.00512f * wind;            // SIG = .003 + .00512*WIND (SOS_GLITTER.F:300)
   p.coef = 1.0 / p.sig;                                        // (1./SIG) (:315)
   p.pi = std::acos(-1.0);
-  p.rmu = d_in; p.alpha = d_in + W; p.beta = p.alpha + (os_ns + 1); p.gamma = p.beta + (os_ns + 1); p.zeta = p.gamma + (os_ns + 1);
+  p.rmu = d_in; p.alpha = d_in + 2 * W; p.beta = p.alpha + (os_ns + 1); p.gamma = p.beta + (os_ns + 1); p.zeta = p.gamma + (os_ns + 1);
   cudaEventRecord(ctx->ev_a, ctx->stream);
   sos_launch_glitter(p, d_surf, d_il, ctx->stream);
   cudaEventRecord(ctx->ev_b, ctx->stream);
@@ -202,7 +178,6 @@ extern "C" int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, cons
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);
-  cudaFree(d_in); cudaFree(d_surf); cudaFree(d_il);
   return SOSGPU_OK;
 }
 
@@ -562,16 +537,18 @@ static bool read_fichos(const std::string &path, int N, std::vector<double> &rec
   return true;
 }
 
-static bool direct_model_requested(const int *iroujean, const int *irondeaux, const int *ibreon, const int *inadal,
-                                   const int *imaignan)
-{
-  if (*iroujean == 1 || *irondeaux == 1 || *ibreon == 1 || *inadal == 1 || *imaignan == 1) {
-    fprintf(stdout, "  libsosgpu: the Roujean / Rondeaux / Breon / Nadal / Maignan direct terms of SOS_TRPHI "
-                    "(SOS_TRPHI.F:1047-1200) are not provided by this library\n");
-    return true;
+// the land-surface direct terms requested through the Fortran argument list, for the duration of one shim call
+struct DirectModelScope {
+  sosgpu_ctx *ctx; sosgpu_direct_models saved;
+  DirectModelScope(sosgpu_ctx *c, const int *iroujean, const double *k0, const double *k1, const double *k2, const int *irondeaux,
+                   const int *ibreon, const int *inadal, const double *alpha_nadal, const double *beta_nadal, const int *imaignan,
+                   const double *coef_c_maignan) : ctx(c), saved(c->dm)
+  {
+    ctx->dm = sosgpu_direct_models{*iroujean, *k0, *k1, *k2, *irondeaux, *ibreon, *inadal, *alpha_nadal, *beta_nadal, *imaignan,
+                                   *coef_c_maignan};
   }
-  return false;
-}
+  ~DirectModelScope() { ctx->dm = saved; }
+};
 
 // SOS_TRPHI.F:749-755: one azimuth PHI (radians).  XIT/XQT/XUT/ANGDIFF(-80:80); index 0 of the Stokes arrays only
 // sees the final thresholding (:1212-1218), as in the reference.
@@ -583,14 +560,11 @@ extern "C" void sos_trphi_(const char *fichos, const int *nbmu, const double *rm
                            const double *coef_c_maignan, const int *ipolar, double *xit, double *xqt, double *xut,
                            double *angdiff, int *ier, size_t len_fichos)
 {
-  (void)k0; (void)k1; (void)k2; (void)alpha_nadal; (void)beta_nadal; (void)coef_c_maignan;
   *ier = 0;
   const int N = *nbmu, W = 2 * N + 1;
   sosgpu_ctx *ctx = shim_ctx();
-  if (!ctx || N < 1 || N > NBMU_MAX || *n0 < 1 || *n0 > N ||
-      direct_model_requested(iroujean, irondeaux, ibreon, inadal, imaignan)) {
-    *ier = -1; return;
-  }
+  if (!ctx || N < 1 || N > NBMU_MAX || *n0 < 1 || *n0 > N) { *ier = -1; return; }
+  DirectModelScope dms(ctx, iroujean, k0, k1, k2, irondeaux, ibreon, inadal, alpha_nadal, beta_nadal, imaignan, coef_c_maignan);
   std::vector<double> rec, rmu_c(W), out;
   int nrec = 0;
   if (!read_fichos(fstr(fichos, len_fichos), N, rec, nrec)) { *ier = -1; return; }
@@ -627,13 +601,12 @@ extern "C" void sos_trphi_option_(const int *nbmu, const double *rmu, const doub
                                   double *sca_down, double *i_down, double *q_down, double *u_down, double *pol_ang_down,
                                   double *pol_rate_down, double *l_pol_down, int *ier, size_t len_fichos)
 {
-  (void)ga; (void)zout; (void)k0; (void)k1; (void)k2; (void)alpha_nadal; (void)beta_nadal; (void)coef_c_maignan;
+  (void)ga; (void)zout;
   *ier = 0;
   const int N = *nbmu, W = 2 * N + 1;
   sosgpu_ctx *ctx = shim_ctx();
-  if (!ctx || N < 1 || N > NBMU_MAX || direct_model_requested(iroujean, irondeaux, ibreon, inadal, imaignan)) {
-    *ier = -1; return;
-  }
+  if (!ctx || N < 1 || N > NBMU_MAX) { *ier = -1; return; }
+  DirectModelScope dms(ctx, iroujean, k0, k1, k2, irondeaux, ibreon, inadal, alpha_nadal, beta_nadal, imaignan, coef_c_maignan);
   if (*itrphi != 1 && *itrphi != 2) return;                      // neither branch runs in the reference (:431,556)
   std::vector<double> rec, rmu_c(W);
   int nrec = 0;

@@ -30,6 +30,7 @@
 #include <math.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #define SW_STG 4                       // operand pipeline stages
 #define SW_MMA_WARPS 8
@@ -123,6 +124,7 @@ __device__ __forceinline__ void chunk_mma(double (&acc)[2][8][2], double (&tacc)
                                           int N3, int wr, int lane, int gq, int tq)
 {
   bool ready = mbar_test(full + q % SW_STG, (q / SW_STG) & 1);
+  int kq = 0;                                                  // first k-row of the slab within its direction block
   for (int slab = 0; slab < n_slab; ++slab, ++q) {
     const int st = q % SW_STG;
     if (!ready) mbar_wait(full + st, (q / SW_STG) & 1);
@@ -130,7 +132,6 @@ __device__ __forceinline__ void chunk_mma(double (&acc)[2][8][2], double (&tacc)
     const double *a = reinterpret_cast<const double *>(sp) + (wr * 16 + gq) * SOS_KB;
     const double *v = reinterpret_cast<const double *>(sp + SW_A_BYTES) + gq * SOS_KB;
     const double *b = reinterpret_cast<const double *>(sp + SW_A_BYTES + SW_V_BYTES) + tq * SOS_SB + gq;
-    const int kq = (slab * SOS_KB) % HB;
     ready = mbar_test(full + (q + 1) % SW_STG, ((q + 1) / SW_STG) & 1);   // result is consumed after this slab's DMMAs
     if (kq + SOS_KB <= N3) slab_mma<NFR, LR, OWN, 4>(acc, tacc, a, v, b, wr, gq, tq);
     else {                                                     // tail of a direction block: k-steps of pure padding skipped
@@ -142,6 +143,8 @@ __device__ __forceinline__ void chunk_mma(double (&acc)[2][8][2], double (&tacc)
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + st);
+    kq += SOS_KB;
+    if (kq >= HB) kq -= HB;
   }
 }
 
@@ -195,10 +198,10 @@ __device__ __forceinline__ Unit decode_unit(int w, const ItemDev *items, const T
 
 }  // namespace
 
-__global__ void __launch_bounds__(SW_THREADS, 1)
+__global__ void __launch_bounds__(SW_THREADS, 1)   // 13 warps are allocated as 16: 128 registers per thread
 k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, const OpticsDev *__restrict__ optics,
         const KsetDev *__restrict__ ksets, const int *__restrict__ list, const int *__restrict__ count_ptr, int count_fixed,
-        int tiles_per_dir, int att_rows_cap, unsigned *__restrict__ work_counter, double *__restrict__ jdump)
+        int tiles_per_dir, unsigned *__restrict__ work_counter, double *__restrict__ jdump, int dbg)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // ---- shared memory carve ----
@@ -207,15 +210,12 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
   double *sT = sAcc + 128 * SW_ACC_PITCH;                                           // [4][64] raw molecular functionals
   double *sXd = sT + 4 * SOS_CH;                                                    // [<=66] XDEL of the chunk's levels
   double *sYd = sXd + 72;
-  double *sDt = sYd + 72;                                                           // [<=66] layers lb_al..
-  double *sInv = sDt + 72;
-  double *sG = sInv + 72;                                                           // [3*80] ground values of the downward field
+  double *sG = sYd + 72;                                                           // [3*80] ground values of the downward field
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(sG + 3 * 80);
   unsigned long long *full = bars, *empty = bars + SW_STG;
   unsigned long long *acc_full = bars + 2 * SW_STG, *acc_empty = acc_full + 1, *tab_full = acc_full + 2, *tab_empty = acc_full + 3;
   unsigned long long *work_full = acc_full + 4, *work_empty = acc_full + 6;       // [2] each
   Unit *sUnit = reinterpret_cast<Unit *>(acc_full + 8);                             // [2] decoded work units (64 bytes each)
-  double *sAtt = reinterpret_cast<double *>(acc_full + 24);                         // [<=66][N] exp(-dtau/mu_k)
 
   const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5;
   if (tid == 0) {
@@ -265,19 +265,12 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
           if (u.lr) bulk_g2s(sp + SW_A_BYTES, Vg + (size_t)slab * 8 * SOS_KB, SW_V_BYTES, full + st);
           bulk_g2s(sp + SW_A_BYTES + SW_V_BYTES, xprev + SOS_XIDX(u.KP, slab * SOS_KB, c0), SW_B_BYTES, full + st);
         }
-        // layer tables of this chunk (needed once its main loop is over): rows [lb_al, le], even start and count
-        const int lb_al = max(c0 - 1, 0) & ~1;
-        const int le = min(c0 + SOS_CH - 1, u.NT - 1);
-        const int nrow = (le - lb_al + 2) & ~1;
+        // XDEL / YDEL of this chunk's levels (needed once its main loop is over)
         const int nlev = (min(SOS_CH, u.L - c0) + 1) & ~1;
-        const bool att_staged = nrow <= att_rows_cap;
         if (tabn >= 1) mbar_wait(tab_empty, (tabn - 1) & 1);
-        mbar_expect_tx(tab_full, (unsigned)(nrow * 16 + nlev * 16 + (att_staged ? nrow * u.N * 8 : 0)));
+        mbar_expect_tx(tab_full, (unsigned)(nlev * 16));
         bulk_g2s(sXd, tm.xdel + c0, (unsigned)(nlev * 8), tab_full);
         bulk_g2s(sYd, tm.ydel + c0, (unsigned)(nlev * 8), tab_full);
-        bulk_g2s(sDt, tm.dt + lb_al, (unsigned)(nrow * 8), tab_full);
-        bulk_g2s(sInv, tm.inv + lb_al, (unsigned)(nrow * 8), tab_full);
-        if (att_staged) bulk_g2s(sAtt, tm.att + (size_t)lb_al * u.N, (unsigned)(nrow * u.N * 8), tab_full);
         ++tabn;
       }
     }
@@ -319,7 +312,7 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
         }
         // ---- hand the raw accumulators to the recurrence warps ----
         if (accn >= 1) mbar_wait(acc_empty, (accn - 1) & 1);
-        if (own) {
+        if (own && !(dbg & 2)) {
           double2 *sA2 = reinterpret_cast<double2 *>(sAcc);
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) {
@@ -401,25 +394,27 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
       }
 
       const double2 *sA2 = reinterpret_cast<const double2 *>(sAcc);
+      double2 *sAw2 = reinterpret_cast<double2 *>(sAcc);          // the new field replaces the accumulators in place
+      double *sAw = sAcc;
       const int tsel = (so + 1) * SOS_CH;                        // sT row of this row's Stokes type
       double z = 0.0;                                            // recurrence state
       double sedge = 0.0;                                        // source function at the neighbouring level of the previous chunk
-      const double rmuk = -mu;
+      double redge = 0.0;                                        // ... and its raw accumulator (aerosol-only orders)
       for (int chunk = 0; chunk < u.n_chunk; ++chunk) {
         const int ci = up ? (u.n_chunk - 1 - chunk) : chunk;
         const int c0 = ci * SOS_CH;
-        const int lb_al = max(c0 - 1, 0) & ~1;
-        const int le = min(c0 + SOS_CH - 1, NT - 1);
-        const int nrow = (le - lb_al + 2) & ~1;
-        const bool att_staged = nrow <= att_rows_cap;
         mbar_wait(tab_full, accn & 1);
         mbar_wait(acc_full, accn & 1);
-        if (rowvalid) {
-          // layer l of this row: attenuation a(l), dtau(l), 1/dtau(l)
-          const double *attp = att_staged ? (sAtt + (kk - 1) - (size_t)lb_al * N) : (tm.att + (kk - 1));
-          const double *dtp = sDt - lb_al, *ivp = sInv - lb_al;
+        if (rowvalid && !(dbg & 1)) {
+          // Layer l of this row: a = exp(-dtau/mu), g = (1-a)*mu/dtau - a, b = 1 - a - g (tables of k_att, coalesced over the
+          // rows of a warp).  With S the source function at the two levels of a layer, SOS_INTEGR_EPOPT's update
+          //   z <- z*a + (1-a)*(A*mu + S_i) -/+ A*a*dtau,  A = dS/dtau   (SOS_OS.F:2288-2309, 2332-2353)
+          // is z <- z*a + b*S_i + g*S_j: 4 FP64 instructions per level.  (FP64 vector instructions share the pipe with DMMA
+          // and each costs about a DMMA slot -- tools/mainloop_bench.cu -- so the recurrence warps must be frugal.)
+          const double *__restrict__ attp = tm.att + (kk - 1);
+          const double *__restrict__ gp = tm.gco + (kk - 1);
+          const double *__restrict__ bp = tm.bco + (kk - 1);
           const int top = min(c0 + SOS_CH - 1, NT);              // highest real level of the chunk
-          double *xrow = xnext + SOS_XIDX(KP, u.r0 + e, c0);     // element (row, level c0)
           double *jrow = jdump ? jdump + (size_t)(u.r0 + e) * tm.LP + c0 : nullptr;
           // source function of column col from the raw accumulator (SOS_FSOURCE_ORDREIG, molecular part in factored form)
           auto source = [&](double araw, int col) -> double {
@@ -432,25 +427,53 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
             return (col & 1) ? t.y : t.x;
           };
           if (up) {
-            // ---- from the ground upwards: levels top .. c0 (SOS_OS.F:2279-2310) ----
+            // ---- from the ground upwards: levels top .. c0; level i uses layer i and S(i+1) ----
             int lv = top;
             const int full_hi = jdump ? c0 - 1 : ((top == NT) ? (NT & ~7) - 1 : top);   // levels c0 .. full_hi: whole blocks of 8 below NT
             for (; lv > full_hi; --lv) {                         // ragged head (at most 8 levels; holds level NT)
               const int col = lv - c0;
-              const double s = source(raw(col), col);
+              const double rw = raw(col);
+              const double s = source(rw, col);
               if (lv == NT) z = bc;
-              else {
-                const double a = attp[(size_t)lv * N], dl = dtp[lv], iv = ivp[lv];
-                const double A = (sedge - s) * iv;
-                z = z * a + ((1.0 - a) * (A * mu + s) - A * (a * dl));
-              }
-              sedge = s;
-              xrow[col] = z;
+              else z = z * attp[(size_t)lv * N] + (bp[(size_t)lv * N] * s + gp[(size_t)lv * N] * sedge);
+              sedge = s; redge = rw;
+              sAw[2 * acc_slot(e, col >> 1) + (col & 1)] = z;
               if (jrow) jrow[col] = s;
             }
+            if (!u.lr) {
+              // aerosol-only orders: c = pup*acc(i) + qup*acc(i+1), 3 FP64 instructions per level
+              const double *__restrict__ pp = tm.pup + (kk - 1), *__restrict__ qp = tm.qup + (kk - 1);
+              for (; lv >= c0; lv -= 8) {
+                const int cb = lv - 7 - c0;
+                double R[9], aa[8], pw[8], qw[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const size_t l = (size_t)(c0 + cb + j) * N;
+                  aa[j] = attp[l]; pw[j] = pp[l]; qw[j] = qp[l];
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                  const double2 t = sA2[acc_slot(e, (cb >> 1) + p)];
+                  R[2 * p] = t.x; R[2 * p + 1] = t.y;
+                }
+                R[8] = redge;
+#pragma unroll
+                for (int p = 3; p >= 0; --p) {
+                  const double zo = z * aa[2 * p + 1] + (pw[2 * p + 1] * R[2 * p + 1] + qw[2 * p + 1] * R[2 * p + 2]);
+                  z = zo * aa[2 * p] + (pw[2 * p] * R[2 * p] + qw[2 * p] * R[2 * p + 1]);
+                  sAw2[acc_slot(e, (cb >> 1) + p)] = make_double2(z, zo);
+                }
+                redge = R[0];
+              }
+            } else
             for (; lv >= c0; lv -= 8) {                          // whole blocks of 8 levels, lv = highest level of the block
               const int cb = lv - 7 - c0;                        // first column of the block (multiple of 8)
-              double S[9], cst[8], aa[8];
+              double S[9], aa[8], gg[8], bb[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const size_t l = (size_t)(c0 + cb + j) * N;
+                aa[j] = attp[l]; gg[j] = gp[l]; bb[j] = bp[l];
+              }
 #pragma unroll
               for (int p = 0; p < 4; ++p) {
                 const double2 t = sA2[acc_slot(e, (cb >> 1) + p)];
@@ -459,27 +482,53 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
               }
               S[8] = sedge;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int l = c0 + cb + j;
-                const double a = attp[(size_t)l * N], dl = dtp[l], iv = ivp[l];
-                const double A = (S[j + 1] - S[j]) * iv;
-                cst[j] = (1.0 - a) * (A * mu + S[j]) - A * (a * dl);
-                aa[j] = a;
+              for (int p = 3; p >= 0; --p) {                     // the new field replaces the accumulators pair by pair
+                const double zo = z * aa[2 * p + 1] + (bb[2 * p + 1] * S[2 * p + 1] + gg[2 * p + 1] * S[2 * p + 2]);
+                z = zo * aa[2 * p] + (bb[2 * p] * S[2 * p] + gg[2 * p] * S[2 * p + 1]);
+                sAw2[acc_slot(e, (cb >> 1) + p)] = make_double2(z, zo);
               }
-              double o[8];
-#pragma unroll
-              for (int j = 7; j >= 0; --j) { z = z * aa[j] + cst[j]; o[j] = z; }
               sedge = S[0];
-#pragma unroll
-              for (int p = 0; p < 4; ++p) *reinterpret_cast<double2 *>(xrow + cb + 2 * p) = make_double2(o[2 * p], o[2 * p + 1]);
             }
           } else {
-            // ---- from the top downwards: levels c0 .. top (SOS_OS.F:2320-2354) ----
+            // ---- from the top downwards: levels c0 .. top; level i uses layer i-1 and S(i-1) ----
             int lv = c0;
             const int n_full = jdump ? 0 : ((top + 1 - c0) >> 3);  // whole blocks of 8 in this chunk
+            if (!u.lr) {
+              const double *__restrict__ pp = tm.pdn + (kk - 1), *__restrict__ qp = tm.qdn + (kk - 1);
+              for (int blk = 0; blk < n_full; ++blk, lv += 8) {
+                const int cb = lv - c0;
+                double R[9], aa[8], pw[8], qw[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  aa[j] = attp[(size_t)max(lv + j - 1, 0) * N];   // layer above level lv+j
+                  const size_t l = (size_t)(lv + j) * N;
+                  pw[j] = pp[l]; qw[j] = qp[l];                   // level-indexed (row 0 is zero: X(0) = 0)
+                }
+                R[0] = redge;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                  const double2 t = sA2[acc_slot(e, (cb >> 1) + p)];
+                  R[2 * p + 1] = t.x; R[2 * p + 2] = t.y;
+                }
+                if (lv == 0) aa[0] = 0.0;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                  const double ze = z * aa[2 * p] + (pw[2 * p] * R[2 * p + 1] + qw[2 * p] * R[2 * p]);
+                  z = ze * aa[2 * p + 1] + (pw[2 * p + 1] * R[2 * p + 2] + qw[2 * p + 1] * R[2 * p + 1]);
+                  sAw2[acc_slot(e, (cb >> 1) + p)] = make_double2(ze, z);
+                }
+                redge = R[8];
+                sedge = sXd[cb + 7] * R[8];                       // the ragged tail of the profile continues with the generic form
+              }
+            } else
             for (int blk = 0; blk < n_full; ++blk, lv += 8) {
               const int cb = lv - c0;
-              double S[9], cst[8], aa[8];
+              double S[9], aa[8], gg[8], bb[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const size_t l = (size_t)max(lv + j - 1, 0) * N;   // layer above level lv+j (level 0 has none: fixed below)
+                aa[j] = attp[l]; gg[j] = gp[l]; bb[j] = bp[l];
+              }
               S[0] = sedge;
 #pragma unroll
               for (int p = 0; p < 4; ++p) {
@@ -487,49 +536,63 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
                 S[2 * p + 1] = source(t.x, cb + 2 * p);
                 S[2 * p + 2] = source(t.y, cb + 2 * p + 1);
               }
+              if (lv == 0) { aa[0] = 0.0; gg[0] = 0.0; bb[0] = 0.0; }   // level 0: X = 0
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int l = max(lv + j - 1, 0);                // layer above level lv+j (level 0 has none: fixed below)
-                const double a = attp[(size_t)l * N], dl = dtp[l], iv = ivp[l];
-                const double A = (S[j + 1] - S[j]) * iv;
-                cst[j] = (1.0 - a) * (A * rmuk + S[j + 1]) + A * (a * dl);
-                aa[j] = a;
+              for (int p = 0; p < 4; ++p) {
+                const double ze = z * aa[2 * p] + (bb[2 * p] * S[2 * p + 1] + gg[2 * p] * S[2 * p]);
+                z = ze * aa[2 * p + 1] + (bb[2 * p + 1] * S[2 * p + 2] + gg[2 * p + 1] * S[2 * p + 1]);
+                sAw2[acc_slot(e, (cb >> 1) + p)] = make_double2(ze, z);
               }
-              if (lv == 0) { cst[0] = 0.0; aa[0] = 0.0; }         // level 0: X = 0
-              double o[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { z = z * aa[j] + cst[j]; o[j] = z; }
               sedge = S[8];
-#pragma unroll
-              for (int p = 0; p < 4; ++p) *reinterpret_cast<double2 *>(xrow + cb + 2 * p) = make_double2(o[2 * p], o[2 * p + 1]);
             }
             for (; lv <= top; ++lv) {                            // ragged tail
               const int col = lv - c0;
-              const double s = source(raw(col), col);
+              const double rw = raw(col);
+              const double s = source(rw, col);
               if (lv == 0) z = 0.0;
               else {
-                const double a = attp[(size_t)(lv - 1) * N], dl = dtp[lv - 1], iv = ivp[lv - 1];
-                const double A = (s - sedge) * iv;
-                z = z * a + ((1.0 - a) * (A * rmuk + s) + A * (a * dl));
+                const size_t l = (size_t)(lv - 1) * N;
+                z = z * attp[l] + (bp[l] * s + gp[l] * sedge);
               }
-              sedge = s;
-              xrow[col] = z;
+              sedge = s; redge = rw;
+              sAw[2 * acc_slot(e, col >> 1) + (col & 1)] = z;
               if (jrow) jrow[col] = s;
             }
           }
         }
+        // ---- copy-out: the tile now holds X_n; whole rows go to HBM with one 512-byte store instruction per row
+        //      (a row-per-thread store would touch 32 lines per instruction and stall the MMA warps' shared-memory loads) ----
+        epi_bar();
+        if (lane == 0) mbar_arrive(tab_empty);                   // the layer tables are free for the next chunk
+        {
+          const int ncol = min(SOS_CH, L - c0);                  // real levels of this chunk
+          const int ew = e >> 5;
+          for (int rl = ew; rl < u.R; rl += SW_EPI_WARPS) {
+            if (u.g0 * 16 + rl >= 3 * N) break;                  // pad rows stay zero (rows ascend)
+            const double2 t = sA2[acc_slot(rl, lane)];
+            double *dst = xnext + SOS_XIDX(KP, u.r0 + rl, c0) + 2 * lane;
+            if (2 * lane + 1 < ncol) *reinterpret_cast<double2 *>(dst) = t;
+            else if (2 * lane < ncol) *dst = t.x;
+          }
+        }
         __syncwarp();
-        if (lane == 0) { mbar_arrive(acc_empty); mbar_arrive(tab_empty); }
+        if (lane == 0) mbar_arrive(acc_empty);
         ++accn;
       }
     }
   }
 }
 
-static size_t sweep_smem_bytes(int att_rows_cap, int nmax)
+static int sweep_dbg()
 {
-  return (size_t)SW_STG * SW_STAGE + (size_t)128 * SW_ACC_PITCH * 8 + (4 * SOS_CH + 4 * 72 + 3 * 80) * 8 + (2 * SW_STG + 24) * 8 +
-         (size_t)att_rows_cap * nmax * 8 + 128;
+  static const int v = getenv("SOS_SWEEP_DBG") ? atoi(getenv("SOS_SWEEP_DBG")) : 0;   // timing experiments only (results invalid)
+  return v;
+}
+
+static size_t sweep_smem_bytes()
+{
+  return (size_t)SW_STG * SW_STAGE + (size_t)128 * SW_ACC_PITCH * 8 + (4 * SOS_CH + 2 * 72 + 3 * 80) * 8 + (2 * SW_STG + 24) * 8 +
+         128;
 }
 
 // One scattering order for the items of `list` (or 0..nitem-1).  The number of items comes from device memory when
@@ -541,14 +604,12 @@ extern "C" int sos_launch_sweep(const ItemDev *items, const TermDev *terms, cons
   if (nitem <= 0) return 0;
   const int groups = maxHB / 16;
   const int tiles_per_dir = (groups + SW_MMA_WARPS - 1) / SW_MMA_WARPS;
-  const int nmax = maxHB / 3;                                    // 3N <= HB
-  int att_rows = 66;
-  while (att_rows > 0 && sweep_smem_bytes(att_rows, nmax) > 227 * 1024) att_rows = 0;   // all or nothing
-  const size_t smem = sweep_smem_bytes(att_rows, nmax);
+  const size_t smem = sweep_smem_bytes();
   cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaMemsetAsync(work_counter, 0, sizeof(unsigned), st);
   const long long units = (long long)nitem * 2 * tiles_per_dir;
   const int grid = (int)std::min<long long>(num_sms, units);
-  k_sweep<<<grid, SW_THREADS, smem, st>>>(items, terms, optics, ksets, list, count_ptr, nitem, tiles_per_dir, att_rows, work_counter, jdump);
+  k_sweep<<<grid, SW_THREADS, smem, st>>>(items, terms, optics, ksets, list, count_ptr, nitem, tiles_per_dir, work_counter, jdump,
+                                             sweep_dbg());
   return 1;
 }

@@ -66,6 +66,23 @@ def glitter(ref, fm, tmp, N, rmu, ga, wind, ind, os_nb, os_ns, os_nm):
     return fm.read_surface_bin(fgl, N)
 
 
+def mat_fresnel(ref, tmp, N, rmu, ga, ind, os_ns):
+    """SOS_MAT_FRESNEL (SOS_SURFACE.F:1235) -> alpha, beta, gamma, zeta [os_ns+1] read back from its 4(E15.8) text file."""
+    r, g = _angles(rmu, ga, N)
+    f = os.path.join(tmp, "RES_FRESNEL")
+    ier = C.c_int(99)
+    ref.sos_mat_fresnel_(_ip(N), _P(r), _P(g), _dp(ind), _ip(os_ns), _fs(f), _ip(0), C.byref(ier), _L)
+    assert ier.value == 0, "reference SOS_MAT_FRESNEL IER=%d" % ier.value
+    rows = []
+    with open(f) as fh:
+        for line in fh:
+            if line.strip():
+                rows.append([float(line[i * 15:(i + 1) * 15]) for i in range(4)])
+    a = np.array(rows)
+    assert a.shape == (os_ns + 1, 4)
+    return a[:, 0], a[:, 1], a[:, 2], a[:, 3]
+
+
 def trphi_option(ref, fm, tmp, rec, N, rmu, ga, tau, tauout, igli, n0, wind, ind, ifresnel, itrphi, phios, pas, ipolar=1,
                  roujean=None, bpdf=None):
     """SOS_TRPHI_OPTION (SOS_TRPHI.F:285) on a result file -> (nphi, phi, theta, up[7][nphi][N], down[7][nphi][N]).

@@ -364,7 +364,8 @@ def test_gfortran_abi_sos_glitter_trphi(pkg, orc, solver, tmp_path):
     lib.sos_trphi_(fstr(fos), ip(N), P(rmu), dp(r.ttot_tronc), dp(r.tauout), dp(phi), ip(1), ip(o.n0), dp(o.wind),
                    dp(o.ind_surf), ip(0), ip(1), dp(0.1), dp(0.1), dp(0.1), ip(0), ip(0), ip(0), dp(0.0), dp(0.0), ip(0),
                    dp(0.0), ip(1), P(xi), P(xq), P(xu), P(an), C.byref(ier), L500)
-    assert ier.value == -1                               # Roujean direct term: refused loudly, not silently skipped
+    assert ier.value == 0                                # Roujean direct term (SOS_TRPHI.F:1047-1072; values: test_gpu_vs_reference)
+    assert np.abs(xi[MX + 1:MX + N + 1] - xi0[N + 1:]).max() > 1e-6   # the direct term is there
 
 
 @pytest.mark.parametrize("nbg,os_nb", [(24, 48), (79, 24)])
@@ -439,3 +440,36 @@ def test_transmissions(pkg, orc, solver):
     N = o.nbmu
     assert_stokes_close(tdifmus[0], r.tdifmus, "TDIFMUS")
     assert_stokes_close(tdifmug[0], r.tdifmug[N + 1:], "TDIFMUG")
+
+
+def test_comm_api_single_rank(pkg, orc, solver):
+    """The library-owned NCCL communicator with ONE rank: sosgpu_comm_init, the in-place reduce of the band sums + group
+    metadata (identity here), sosgpu_batch_groups, and the table gather must reproduce the plain single-GPU results."""
+    syn = pkg.synth
+    wl = syn.config_ckd_band(npoints=3, seed=5, nb_gauss=8, os_nb=16, surface="lambert", rho=0.1, max_terms=5)
+    solver.comm_init(1, 0, solver.comm_unique_id())
+    b = solver.upload(wl)
+    try:
+        tr, gr = solver.run(b)
+        n, up, down = solver.batch_trphi(b, 0, 2.0, 1.34, 0, 2, 0.0, 30, 1)
+        b2 = solver.upload(wl)
+        solver.run(b2, want_terms=False, want_groups=False, part_only=True)
+        solver.reduce_groups(b2, root=0)
+        g2 = solver.groups(b2)
+        assert np.array_equal(g2.n_rec, gr.n_rec)
+        assert np.array_equal(g2.rec, gr.rec)
+        for k in ("emoins", "eplus"):
+            assert_stokes_close(getattr(g2, k), getattr(gr, k), k)
+        for k in ("ttot_tronc", "ttot_vrai", "tauout"):       # closed form -log(sum a e^-tau) vs the reference's running form
+            assert np.allclose(getattr(g2, k), getattr(gr, k), rtol=1e-12, atol=1e-15), k
+        n2, up2, down2 = solver.batch_trphi(b2, 0, 2.0, 1.34, 0, 2, 0.0, 30, 1)
+        for tb in (1, 2, 3):
+            assert_stokes_close(up2[:, tb], up[:, tb], "reduced-band up table %d" % tb)
+        # wavelength-sharded layout: gather of the synthesised tables (one rank: a device-to-host copy in rank order)
+        solver.batch_trphi(b, 0, 2.0, 1.34, 0, 2, 0.0, 30, 1, download=False)
+        gu, gd = solver.gather_tables(b, [b.ngroup], n, root=0)
+        assert np.array_equal(gu, up) and np.array_equal(gd, down)
+        b2.free()
+    finally:
+        b.free()
+        solver.lib.sosgpu_comm_destroy(solver.ctx)

@@ -120,3 +120,69 @@ def test_cfg5_angular_stress_caps(pkg, solver, ref):
     _tally("cfg5 angular stress (N=80, OS_NB=200, zout=3 km)", bad, len(ids))
     assert not bad
     assert int(tr.n_fourier.max()) > 81                      # beyond what any OS_NB=80 case reaches
+
+
+@pytest.mark.parametrize("model", ["roujean", "rondeaux", "breon", "nadal", "maignan"])
+def test_trphi_land_surface_direct_terms(pkg, solver, ref, model, tmp_path):
+    """SOS_TRPHI's direct-beam terms of the land-surface models (SOS_TRPHI.F:1047-1200 with SOS_CALC_F_ROUJEAN,
+    SOS_ROUJEAN.F:891, and SOS_CALCG_MAIGNAN, SOS_SURFACE_BPDF.F:1606) against the reference's SOS_TRPHI_OPTION."""
+    syn, fm = pkg.synth, pkg.formats
+    o = syn.make_optics(nb_gauss=24, tetas=35.0, os_nb=32, surface="brdf", rho=0.0)
+    wl = syn.Workload("land", [o], [syn.Term(0, 1.0, *syn.profile(0.05, 8.0, 0.2, 2.0, 0.1))])
+    tr, gr = solver.solve(wl)
+    nr = int(gr.n_rec[0])
+    N = o.nbmu
+    rec = gr.rec[0, :nr, :, :2 * N + 1]
+    kw = dict(roujean=dict(roujean=(0.25, 0.04, 0.30)), rondeaux=dict(irondeaux=1), breon=dict(ibreon=1),
+              nadal=dict(nadal=(0.017, 75.0)), maignan=dict(maignan=6.0))[model]
+    solver.set_direct_models(**kw)
+    try:
+        for itrphi, phios, pas in ((1, 15.0, 0), (2, 0.0, 45)):
+            n1, pf1, th1, up1, dn1 = solver.trphi_option(rec, N, o.rmu, gr.ttot_tronc[0], gr.tauout[0], 0, o.n0, 2.0, 1.5, 0,
+                                                         itrphi, phios, pas, 1)
+            bp = {k: v for k, v in (("irondeaux", kw.get("irondeaux", 0)), ("ibreon", kw.get("ibreon", 0)))}
+            if "nadal" in kw:
+                bp.update(inadal=1, alpha=kw["nadal"][0], beta=kw["nadal"][1])
+            if "maignan" in kw:
+                bp.update(imaignan=1, coef=kw["maignan"])
+            n0, pf0, th0, up0, dn0 = refdirect.trphi_option(ref, fm, str(tmp_path), rec, N, o.rmu, o.ga, gr.ttot_tronc[0], gr.tauout[0],
+                                                            0, o.n0, 2.0, 1.5, 0, itrphi, phios, pas, roujean=kw.get("roujean"), bpdf=bp)
+            assert n0 == n1
+            for tb in (1, 2, 3):
+                assert_stokes_close(up1[tb], up0[tb], "%s up table %d" % (model, tb))
+                assert_stokes_close(dn1[tb], dn0[tb], "%s down table %d" % (model, tb))
+            # the direct term is really there: the table differs from the one without it
+            solver.set_direct_models()
+            _, _, _, upn, _ = solver.trphi_option(rec, N, o.rmu, gr.ttot_tronc[0], gr.tauout[0], 0, o.n0, 2.0, 1.5, 0, itrphi, phios, pas, 1)
+            assert np.abs(up1[1] - upn[1]).max() > 1e-6
+            solver.set_direct_models(**kw)
+    finally:
+        solver.set_direct_models()
+
+
+@pytest.mark.parametrize("nbg,ind", [(12, 1.34), (40, 1.34), (24, 1.5)])
+def test_mat_fresnel_isolated(pkg, solver, ref, nbg, ind, tmp_path):
+    """SOS_MAT_FRESNEL (SOS_SURFACE.F:1235-1603) on its own: the device expansion + the E15.8 channel must give the very
+    numbers the reference writes to RES_FRESNEL (8 significant digits: identical decimals, i.e. identical doubles)."""
+    rmu, ga, n0, _ = pkg.synth.sos_angles(nbg, 35.0)
+    N = (rmu.size - 1) // 2
+    os_ns = 2 * nbg
+    got = solver.mat_fresnel(N, rmu, ga, ind, os_ns)
+    want = refdirect.mat_fresnel(ref, str(tmp_path), N, rmu, ga, ind, os_ns)
+    for name, g, w in zip(("alpha", "beta", "gamma", "zeta"), got, want):
+        assert np.array_equal(g, w), (name, np.abs(g - w).max())
+
+
+def test_order1_isolated(pkg, solver, ref):
+    """SOS_FSOURCE_ORDRE1 + boundary values + SOS_INTEGR_EPOPT alone (k_order1): IGMAX = 1 stops the reference after the first
+    scattering order, for a Lambertian ground, a BRDF matrix and a flat Fresnel sea (SOS_FSOURCE_DIFF_FRESNEL1)."""
+    syn = pkg.synth
+    wl = syn.Workload("order1")
+    for surface, rho in (("lambert", 0.3), ("brdf", 0.05), ("fresnel", 0.0)):
+        wl.optics.append(syn.make_optics(nb_gauss=16, tetas=40.0, os_nb=32, surface=surface, rho=rho, igmax=1, seed=len(wl.optics)))
+        wl.terms.append(syn.Term(len(wl.optics) - 1, 1.0, *syn.profile(0.08, 8.0, 0.25, 2.0, 0.4)))
+    ids, res, b, tr, gr = _solve_both(pkg, solver, wl)
+    b.free()
+    bad = refdirect.compare_terms(tr, res, ids, wl, assert_stokes_close, "order1")
+    assert not bad
+    assert np.all(tr.n_scatter[:, :3] <= 2)
