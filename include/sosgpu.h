@@ -225,6 +225,14 @@ int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *c
 int sosgpu_mat_fresnel(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *chr, double ind_surf, int os_ns,
                        double *alpha, double *beta, double *gamma, double *zeta);
 
+/* SOS_Up.txt / SOS_Down.txt (SOS_ABS_MAIN.F:2250-2519, record formats :3095-3096, headers SOS_TRPHI.F:1570-1796) from the
+ * tables of sosgpu_trphi_option ([7][nphi_cap][N]: SCA, I, Q, U, POL_ANG, POL_RATE, L_POL), byte-compatible with the
+ * reference.  fix_sca_index = 0 keeps the reference's indexing of the upward scattering angle by degrees in view mode 2
+ * (SOS_ABS_MAIN.F:2467); host-only (no device needed). */
+int sosgpu_write_updown(const char *fic_up, const char *fic_down, int nbmu, int itrphi, double phios, int pas_phi, double zout,
+                        const double *phi_fin, const double *theta_fin, const double *up, const double *down, int nphi_cap,
+                        int fix_sca_index);
+
 /* ---- gfortran-ABI drop-in symbols (F77 by-reference, fixed SOS.h strides, hidden string lengths) */
 /* SOS_OS.F:303-308 */
 void sos_os_(const int *nbmu, double *rmu, const double *ga, const int *os_nb, const int *nt,

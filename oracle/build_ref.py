@@ -50,6 +50,9 @@ def build(force=False, verbose=True):
     csrc = os.path.join(OUT, "sosref.c")
     with open(csrc, "w") as f:
         f.write(t.PRELUDE + "\n".join(protos) + "\n\n" + "\n".join(bodies))
+        # test-only access to the Fortran unit table, so that a test can hand an open unit to SOS_OUTPUT_HEADER(_POLAR_DIAG)
+        f.write("\nint sosref_open_unit(int u, const char *path) { return f77_open(u, path, strlen(path), 4); }\n"
+                "void sosref_close_unit(int u) { f77_close(u, 0); }\n")
     with open(os.path.join(OUT, "translation_report.txt"), "w") as f:
         for fn, name, st in report:
             f.write("%-16s %-32s %s\n" % (fn, name, st))

@@ -112,6 +112,21 @@ def _f64(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
 
 
+def write_updown(fic_up, fic_down, nbmu, itrphi, phios, pas_phi, zout, phi_fin, theta_fin, up, down, fix_sca_index=False):
+    """SOS_Up.txt / SOS_Down.txt (SOS_ABS_MAIN.F:2250-2519) from the tables of Solver.trphi_option ([7, nphi, N] each).
+    Host-only formatting inside libsosgpu.so; no device needed."""
+    lib = load_library()
+    up, down = _f64(up), _f64(down)
+    assert up.ndim == 3 and up.shape == down.shape and up.shape[0] == 7 and up.shape[2] == nbmu
+    lib.sosgpu_write_updown.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, c_dp, c_dp,
+                                        c_dp, c_dp, C.c_int, C.c_int]
+    pf = _f64(phi_fin) if phi_fin is not None else np.zeros(up.shape[1])
+    rc = lib.sosgpu_write_updown(str(fic_up).encode(), str(fic_down).encode(), nbmu, itrphi, float(phios), int(pas_phi), float(zout),
+                                 _d(pf), _d(_f64(theta_fin)), _d(up), _d(down), up.shape[1], int(bool(fix_sca_index)))
+    if rc != SOSGPU_OK:
+        raise RuntimeError("sosgpu_write_updown failed (rc=%d)" % rc)
+
+
 class TermResults:
     """Per-term outputs of SOS / SOS_OS: Fourier records (file order Q,U,I), counts, fluxes, optical depths."""
     pass

@@ -1,0 +1,162 @@
+// order1_kernel.cu -- first scattering order of libsosgpu.so (sm_100a).  Orders n >= 2 are in sweep_kernel.cu.
+#include "sosgpu_internal.h"
+#include <math.h>
+
+// k_order1 -- first scattering order of every (term, Fourier order) item of a wave: the analytic source
+// (SOS_FSOURCE_ORDRE1, SOS_OS.F:2431-2565, plus SOS_FSOURCE_DIFF_FRESNEL1 :3106-3295 for a flat sea; the layer
+// integration is linear in the source, so both sources are integrated at once), the boundary values SOS_OS.F:970-992 and
+// SOS_INTEGR_EPOPT (:2222-2357).  No contraction here: the kernel is bound by the 96*N*(NT+1)/2 bytes it writes per item.
+// One thread per packed row sweeps all levels in the direction of propagation in blocks of 16 levels (two groups of 8:
+// the layer constants of a group are independent, only the 8 recurrence FMAs are serial); a block goes through a small
+// shared tile so that the CTA stores whole 128-byte runs per row.  Few registers, many CTAs per SM.
+#define O1_PITCH 18
+__global__ void __launch_bounds__(128)
+k_order1(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, const OpticsDev *__restrict__ optics,
+         const KsetDev *__restrict__ ksets)
+{
+  __shared__ __align__(16) double tile[128 * O1_PITCH];
+  const ItemDev &it = items[blockIdx.x];
+  const KsetDev &ks = ksets[it.kset];
+  const TermDev &tm = terms[it.term];
+  const OpticsDev &op = optics[tm.optics];
+  const int N = op.nbmu, HB = op.HB, KP = op.KP, NT = tm.nt;
+  const int tid = threadIdx.x;
+  const int row = blockIdx.y * 128 + tid;
+  const int dir = (row < KP) ? row / HB : 1, q = row - dir * HB;
+  const bool valid = row < KP && q < 3 * N;                      // pad rows stay zero
+  const bool up = (dir == 0);
+  const int so = valid ? q / N : 0, kk = valid ? q % N + 1 : 1;
+  const double mu = op.rmu[kk + N];
+  const int rowc = valid ? row : 0;
+  const double c1 = ks.c1[rowc], c2 = ks.c2[rowc], fz1 = ks.fz1[rowc], fz2 = ks.fz2[rowc];
+  const bool fres = (op.ifresnel == 1);
+  double *__restrict__ xo = it.x[1];
+  const double *__restrict__ attp = tm.att + (kk - 1);
+  const double *__restrict__ chp = tm.ch, *__restrict__ cfp = tm.cf, *__restrict__ xdp = tm.xdel, *__restrict__ ydp = tm.ydel;
+  const double *__restrict__ dtp = tm.dt, *__restrict__ ivp = tm.inv;
+  // source function of level lv (SOS_OS.F:2553-2560 and :3224-3292)
+  auto source = [&](int lv) -> double {
+    const double xdv = xdp[lv], ydv = ydp[lv];
+    double v = __dmul_rn(chp[lv], __dadd_rn(__dmul_rn(c2, xdv), __dmul_rn(c1, ydv)));
+    if (fres && (up ? (lv <= NT - 1) : (lv >= 1))) v = v + cfp[lv] * (fz2 * xdv + fz1 * ydv);
+    return v;
+  };
+  double bc = 0.0;                                               // SOS_OS.F:970-992
+  if (valid && up) {
+    if (so == 0 && !(op.ro == 0.0 || it.is != 0)) bc = -op.ro * op.tab * tm.eground;
+    if (op.imat_surf == 1) {
+      const float *rs = op.surf + (size_t)it.is * 9 * N * N;
+      const double rr = tm.eground / mu;
+      double rv = (double)rs[(size_t)(so * 3) * N * N + (size_t)(kk - 1) * N + (op.n0 - 1)];
+      if (op.ipolar == 0 && so != 0) rv = 0.0;
+      bc = (so == 0) ? bc + rv * rr : rv * rr;
+    }
+  }
+  const double rmuk = -mu;
+  double z = 0.0, sedge = 0.0;
+  double *trow = tile + tid * O1_PITCH;
+  const int nblk = (NT + 16) >> 4;                               // blocks of 16 levels covering 0..NT
+  for (int step = 0; step < nblk; ++step) {
+    const int b16 = (up ? (nblk - 1 - step) : step) << 4;        // first level of this thread's block
+    if (valid) {
+#pragma unroll
+      for (int g8 = 0; g8 < 2; ++g8) {
+        const int b0 = b16 + (up ? 8 - 8 * g8 : 8 * g8);         // group of 8 levels, in the direction of propagation
+        double *tg = trow + (b0 - b16);
+        if (up) {
+          if (b0 + 7 < NT) {                                     // whole group below the ground level
+            double S[9], cst[8], aa[8], o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) S[j] = source(b0 + j);
+            S[8] = sedge;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int l = b0 + j;
+              const double a = attp[(size_t)l * N], dl = dtp[l], iv = ivp[l];
+              const double A = (S[j + 1] - S[j]) * iv;
+              cst[j] = (1.0 - a) * (A * mu + S[j]) - A * (a * dl);
+              aa[j] = a;
+            }
+#pragma unroll
+            for (int j = 7; j >= 0; --j) { z = z * aa[j] + cst[j]; o[j] = z; }
+            sedge = S[0];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) *reinterpret_cast<double2 *>(tg + 2 * p) = make_double2(o[2 * p], o[2 * p + 1]);
+          } else {
+            for (int lv = min(b0 + 7, NT); lv >= b0; --lv) {      // the group that holds level NT
+              const double s = source(lv);
+              if (lv == NT) z = bc;
+              else {
+                const double a = attp[(size_t)lv * N], dl = dtp[lv], iv = ivp[lv];
+                const double A = (sedge - s) * iv;
+                z = z * a + ((1.0 - a) * (A * mu + s) - A * (a * dl));
+              }
+              sedge = s;
+              tg[lv - b0] = z;
+            }
+          }
+        } else {
+          if (b0 + 7 <= NT) {
+            double S[9], cst[8], aa[8], o[8];
+            S[0] = sedge;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) S[j + 1] = source(b0 + j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int l = max(b0 + j - 1, 0);
+              const double a = attp[(size_t)l * N], dl = dtp[l], iv = ivp[l];
+              const double A = (S[j + 1] - S[j]) * iv;
+              cst[j] = (1.0 - a) * (A * rmuk + S[j + 1]) + A * (a * dl);
+              aa[j] = a;
+            }
+            if (b0 == 0) { cst[0] = 0.0; aa[0] = 0.0; }           // level 0: X = 0
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { z = z * aa[j] + cst[j]; o[j] = z; }
+            sedge = S[8];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) *reinterpret_cast<double2 *>(tg + 2 * p) = make_double2(o[2 * p], o[2 * p + 1]);
+          } else {
+            for (int lv = b0; lv <= min(b0 + 7, NT); ++lv) {
+              const double s = source(lv);
+              if (lv == 0) z = 0.0;
+              else {
+                const double a = attp[(size_t)(lv - 1) * N], dl = dtp[lv - 1], iv = ivp[lv - 1];
+                const double A = (s - sedge) * iv;
+                z = z * a + ((1.0 - a) * (A * rmuk + s) + A * (a * dl));
+              }
+              sedge = s;
+              tg[lv - b0] = z;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- copy-out: 8 lanes store one row's 16 levels (128 bytes), a warp 4 rows per instruction ----
+    {
+      const int part = tid & 7;
+      for (int rl = tid >> 3; rl < 128; rl += 16) {
+        const int r = blockIdx.y * 128 + rl;
+        if (r >= KP) break;
+        const int d = r / HB;
+        if (r - d * HB >= 3 * N) continue;
+        const int rb16 = ((d == 0) ? (nblk - 1 - step) : step) << 4;
+        const int lv = rb16 + 2 * part;
+        const double2 t = *reinterpret_cast<const double2 *>(tile + rl * O1_PITCH + 2 * part);
+        double *dst = xo + SOS_XIDX(KP, r, lv);
+        if (lv + 1 <= NT) *reinterpret_cast<double2 *>(dst) = t;
+        else if (lv <= NT) *dst = t.x;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" int sos_launch_order1(const ItemDev *items, const TermDev *terms, const OpticsDev *optics, const KsetDev *ksets,
+                                 int nitem, int maxKP, cudaStream_t st)
+{
+  if (nitem <= 0) return 0;
+  const dim3 grid((unsigned)nitem, (unsigned)((maxKP + 127) / 128));
+  k_order1<<<grid, 128, 0, st>>>(items, terms, optics, ksets);
+  return 1;
+}

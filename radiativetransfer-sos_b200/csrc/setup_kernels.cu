@@ -322,6 +322,19 @@ __global__ void k_att(const TermDev *terms, const OpticsDev *optics)
   const_cast<double *>(tm.qdn)[dn_i] = g * xd_lo;
 }
 
+// Per-level attenuation of the direct solar beam: CH(i) = exp(-H(i)/mu_s)/4 (SOS_OS.F:837-839) and, for a flat sea, the beam
+// reflected by the surface CF(i) = exp(2 H(NT)/TAB)/4 * exp(-H(i)/TAB) (SOS_OS.F:3219, 3278, 3285); TAB = -mu_s.
+__global__ void k_beam(const TermDev *terms, const OpticsDev *optics)
+{
+  const TermDev tm = terms[blockIdx.x];
+  const OpticsDev &op = optics[tm.optics];
+  const double coefnt = exp(2.0 * tm.h[tm.nt] / op.tab) / 4.0;
+  for (int i = threadIdx.x; i <= tm.nt; i += blockDim.x) {
+    const_cast<double *>(tm.ch)[i] = exp(-tm.h[i] / (-op.tab)) / 4.0;
+    const_cast<double *>(tm.cf)[i] = coefnt * exp(-tm.h[i] / op.tab);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double block_max(double v, double *red)
 {
@@ -586,6 +599,7 @@ void sos_launch_att(const TermDev *terms, const OpticsDev *optics, int nterm, in
   if (nterm <= 0) return;
   dim3 grid((max_elems + 127) / 128, nterm);
   k_att<<<grid, 128, 0, st>>>(terms, optics);
+  k_beam<<<nterm, 128, 0, st>>>(terms, optics);
 }
 void sos_launch_init(ItemDev *items, const TermDev *terms, const OpticsDev *optics, int nitem, cudaStream_t st)
 {

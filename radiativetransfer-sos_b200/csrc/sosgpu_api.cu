@@ -68,7 +68,6 @@ extern "C" int sosgpu_create(sosgpu_ctx **out, int device)
   for (int k = 0; k < 8; ++k)
     if (cudaEventCreateWithFlags(&ctx->ev_cnt[k], cudaEventDisableTiming) != cudaSuccess) { sosgpu_destroy(ctx); return SOSGPU_ERR_CUDA; }
   ctx->trace = getenv("SOS_TRACE") != nullptr;
-  ctx->old_order1 = getenv("SOS_OLD_ORDER1") != nullptr;
   *out = ctx;
   return SOSGPU_OK;
 }
@@ -206,10 +205,7 @@ static int prep_term(const sosgpu_term &t, const HostOptics &o, HostTerm &h, boo
   h.dt.assign(nt + 2, 0.0); h.inv.assign(nt + 2, 0.0);           // +2: TMA copies of the tables are 16-byte granular
   h.ch.assign(nt + 2, 0.0); h.cf.assign(nt + 2, 0.0);            // +1: TMA table copies are 16-byte granular
   for (int i = 0; i < nt; ++i) { h.dt[i] = h.h[i + 1] - h.h[i]; h.inv[i] = 1.0 / h.dt[i]; }
-  for (int i = 0; i <= nt; ++i) h.ch[i] = std::exp(-h.h[i] / (-o.tab)) / 4.0;   // SOS_OS.F:837-839
-  h.eground = std::exp(h.h[nt] / o.tab);
-  const double coefnt = std::exp(2.0 * h.h[nt] / o.tab) / 4.0;  // SOS_OS.F:3219
-  for (int i = 0; i <= nt; ++i) h.cf[i] = coefnt * std::exp(-h.h[i] / o.tab);   // :3278,3285
+  h.eground = std::exp(h.h[nt] / o.tab);                       // CH / CF per level are filled on the device (k_beam)
   return SOSGPU_OK;
 }
 
@@ -403,8 +399,8 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
   CK(cudaEventCreate(&b->ev0)); CK(cudaEventCreate(&b->ev1));
   CK(cudaEventCreate(&b->evt0)); CK(cudaEventCreate(&b->evt1));
 
-  sos_launch_att(b->d_terms, b->d_optics, nterm, max_att, ctx->stream);
-  ctx->launches += 1;
+  sos_launch_att(b->d_terms, b->d_optics, nterm, max_att, ctx->stream);   // k_att + k_beam
+  ctx->launches += 2;
   CK(cudaGetLastError());
   const auto t_up2 = std::chrono::steady_clock::now();
   CK(cudaStreamSynchronize(ctx->stream));
@@ -471,6 +467,13 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     if (any) CK(cudaMemcpyAsync(b->d_done, done.data(), nterm * sizeof(int), cudaMemcpyHostToDevice, st));
   }
 
+  // field budget: the configured cap, but never more than 70 % of what the device can still give plus what this batch /
+  // context already holds: a large batch on a smaller or shared GPU gets narrower waves, not an out-of-memory error
+  size_t budget = ctx->field_budget;
+  if (b->field_bytes == 0 && ctx->cache_field_bytes == 0) {      // only when a pool has to be allocated (the query is not free)
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::min(budget, (size_t)(0.7 * (double)free_b));
+  }
   int s0 = 0;
   std::vector<ItemDev> items;
   std::vector<KsetDev> ksets;
@@ -489,7 +492,7 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     const int by_par = std::max(8, (int)((1024 + act.size() - 1) / act.size()));
     ws = std::min(ws, by_par);
     if (ctx->max_wave_orders > 0) ws = std::min(ws, ctx->max_wave_orders);
-    ws = std::min<size_t>(ws, std::max<size_t>(1, ctx->field_budget / std::max<size_t>(bytes_per_order, 1)));
+    ws = std::min<size_t>(ws, std::max<size_t>(1, budget / std::max<size_t>(bytes_per_order, 1)));
     const int s1 = s0 + ws;
 
     // ---- kernel sets: unique (optics, s) ----
@@ -499,7 +502,6 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     size_t kbytes = 0, fbytes = 0, sbytes = 0;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     std::vector<size_t> koff, foff, soff;
-    bool has_single = false, has_dual = false;
     // Work units are handed out dynamically in list order: longest profiles first bounds the tail of every launch to the
     // shortest units; terms of one wavelength stay adjacent within a length class (they share the A operand in L2).
     std::vector<int> act_sorted(act);
@@ -525,7 +527,6 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
           const size_t W = ho.W, KP = ho.KP;
           kbytes += al(3 * (ho.os_nb + 2) * W * 8) + al(6 * W * W * 8) + al(3 * W * 8) + al(KP * KP * 8) * (k.dual ? 2 : 1) + 5 * al(KP * 8) + al(16 * KP * 8);
         } else kid = itk->second;
-        (s <= 2 ? has_dual : has_single) = true;
         ItemDev it{};
         it.term = ti; it.is = s; it.kset = kid; it.n = 1; it.active = 1; it.reason = -1;
         item_of[(size_t)ti * ws + (s - s0)] = (int)items.size();
@@ -626,9 +627,7 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     sos_launch_pack(b->d_ksets, b->d_optics, (int)nk, b->maxKP, st);
     ctx->launches += 3;
     // ---- order 1 ----
-    ctx->launches += ctx->old_order1
-                         ? sos_launch_step(b->d_items, b->d_terms, b->d_optics, b->d_ksets, nullptr, (int)nitem, 1, 0, b->maxHB, nullptr, st)
-                         : sos_launch_order1(b->d_items, b->d_terms, b->d_optics, b->d_ksets, (int)nitem, b->maxKP, st);
+    ctx->launches += sos_launch_order1(b->d_items, b->d_terms, b->d_optics, b->d_ksets, (int)nitem, b->maxKP, st);
     sos_launch_init(b->d_items, b->d_terms, b->d_optics, (int)nitem, st);
     ctx->launches += 1;
     CK(cudaGetLastError());
@@ -642,7 +641,6 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     enum { SOS_LAG = 3, SOS_RING = 8 };
     int cur = 0, ub = (int)nitem;
     std::vector<int> order_ev;                                   // event pair index of every launched order
-    (void)has_single; (void)has_dual;
     for (int ig = 2; ig <= igmax; ++ig) {
       if (ig - 2 >= SOS_LAG) {                                   // count after order ig-SOS_LAG
         const int k = (ig - SOS_LAG) % SOS_RING;
@@ -740,9 +738,13 @@ static int download(sosgpu_ctx *ctx, sosgpu_batch *b, int rec_stride, int wmax, 
   CK(cudaMemcpy(ep.data(), b->d_eplus, nterm * sizeof(double), cudaMemcpyDeviceToHost));
   if (to) {
     if (to->rec) {
-      tmp.resize((size_t)nterm * per);
-      CK(cudaMemcpy(tmp.data(), b->d_rec, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-      convert(tmp.data(), to->rec, nterm);
+      if (rec_stride == b->rs_dev && wmax == b->w_dev)           // caller's layout = device layout: one straight copy
+        CK(cudaMemcpy(to->rec, b->d_rec, (size_t)nterm * per * sizeof(double), cudaMemcpyDeviceToHost));
+      else {
+        tmp.resize((size_t)nterm * per);
+        CK(cudaMemcpy(tmp.data(), b->d_rec, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        convert(tmp.data(), to->rec, nterm);
+      }
     }
     if (to->n_fourier) memcpy(to->n_fourier, nf.data(), nterm * sizeof(int));
     if (to->n_scatter || to->stop_reason) {
@@ -767,9 +769,13 @@ static int download(sosgpu_ctx *ctx, sosgpu_batch *b, int rec_stride, int wmax, 
   }
   if (go) {
     if (go->rec) {
-      tmp.resize((size_t)ngroup * per);
-      CK(cudaMemcpy(tmp.data(), b->d_grec, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-      convert(tmp.data(), go->rec, ngroup);
+      if (rec_stride == b->rs_dev && wmax == b->w_dev)
+        CK(cudaMemcpy(go->rec, b->d_grec, (size_t)ngroup * per * sizeof(double), cudaMemcpyDeviceToHost));
+      else {
+        tmp.resize((size_t)ngroup * per);
+        CK(cudaMemcpy(tmp.data(), b->d_grec, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        convert(tmp.data(), go->rec, ngroup);
+      }
     }
     if (go->n_rec) CK(cudaMemcpy(go->n_rec, b->d_gnrec, ngroup * sizeof(int), cudaMemcpyDeviceToHost));
     // scalars: the caller-owned accumulators of SOS_AGGREGATE.F:452-488, in term order

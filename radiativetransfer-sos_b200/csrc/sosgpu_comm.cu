@@ -271,15 +271,11 @@ extern "C" int sosgpu_batch_gather_tables(sosgpu_ctx *ctx, sosgpu_batch *b, int 
     NK(api->GroupEnd());
   }
   if (is_root && (up || down)) {
-    std::vector<double> &out = ctx->h_gather;
-    out.resize(total * per_group);
-    CK(cudaMemcpyAsync(out.data(), d_all, out.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    // device [g][2 (up, down)][7][nphi][nmax] -> the two caller tables, one strided copy each (no staging buffer)
     const size_t half = (size_t)7 * nphi * nmax;
-    for (size_t g = 0; g < total; ++g) {
-      if (up) memcpy(up + g * half, &out[g * per_group], half * sizeof(double));
-      if (down) memcpy(down + g * half, &out[g * per_group + half], half * sizeof(double));
-    }
+    if (up) CK(cudaMemcpy2DAsync(up, half * 8, d_all, per_group * 8, half * 8, total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (down) CK(cudaMemcpy2DAsync(down, half * 8, d_all + half, per_group * 8, half * 8, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
   } else CK(cudaStreamSynchronize(ctx->stream));
   return SOSGPU_OK;
 }

@@ -27,7 +27,6 @@ struct sosgpu_ctx {
   cudaEvent_t ev_cnt[8] = {};        // one event per ring slot
   sosgpu_direct_models dm = {};      // land-surface direct terms of SOS_TRPHI (sosgpu_set_direct_models)
   bool trace = false;                // SOS_TRACE, read once at create
-  bool old_order1 = false;           // SOS_OLD_ORDER1: round-1 order-1 kernel (A/B timing only)
   char *cache_field = nullptr; size_t cache_field_bytes = 0;   // wave pools parked by the last freed batch
   char *cache_kpool = nullptr; size_t cache_kpool_bytes = 0;
   double *grec_cache = nullptr; size_t grec_cache_bytes = 0;   // group-sum buffer parked by the last freed batch

@@ -13,16 +13,12 @@
 // ------------------------------------------------------------------------------------------------
 #define SOS_KB 16      // k-slab of the contraction (doubles)
 #define SOS_CH 64      // level chunk (columns of the DMMA tile)
-#define SOS_SA 20      // smem row stride of the A slab   (KB + 4: conflict-free 64-bit fragment loads)
 #define SOS_SB 68      // smem row stride of the B slab   (CH + 4)
-#define SOS_SJ 65      // smem row stride of the staging tile (odd: conflict-free row-per-thread scan)
-#define SOS_STAGES 3
 // Field layout in HBM: chunk-major, padded rows -- X[(level>>6)][row][SOS_SB], element (row, level):
 // the 16 k-rows x 64 levels a k-slab needs are one contiguous 16*SOS_SB*8-byte block = ONE TMA bulk copy that
 // lands in shared memory with the conflict-free padded pitch.
 #define SOS_XIDX(KP, row, level) ((((size_t)((level) >> 6)) * (size_t)(KP) + (size_t)(row)) * SOS_SB + ((level) & 63))
 #define SOS_XSIZE(KP, L) ((size_t)(((L) + SOS_CH - 1) / SOS_CH) * (size_t)(KP) * SOS_SB)
-#define SOS_MAXW 8     // warps (16-row groups) per CTA tile
 
 struct OpticsDev {            // one per optics entry (device copy, arrays in a slab)
   int nbmu, W, HB, KP, os_nb, n0, imat_surf, ifresnel, ipolar, igmax;
@@ -97,10 +93,6 @@ void sos_launch_fourier(ItemDev *items, TermDev *terms, const OpticsDev *optics,
 void sos_launch_aggregate(const TermDev *terms, const int *group_start, const int *group_terms, int ngroup,
                           const double *rec, const int *n_fourier, int rec_stride_dev, int wdev,
                           double *grec, int *gnrec, cudaStream_t st);
-// fused step: order1 != 0 -> analytic first-order source; list == null -> items 0..nitem-1;
-// mode bit 0: launch the aerosol-only instantiation (is > 2), bit 1: the Rayleigh+aerosol one (is <= 2)
-int  sos_launch_step(const ItemDev *items, const TermDev *terms, const OpticsDev *optics, const KsetDev *ksets,
-                     const int *list, int nitem, int order1, int mode, int maxHB, double *jdump, cudaStream_t st);
 // first scattering order of every item of a wave (analytic source, boundary values, layer integration)
 int  sos_launch_order1(const ItemDev *items, const TermDev *terms, const OpticsDev *optics, const KsetDev *ksets,
                        int nitem, int maxKP, cudaStream_t st);
