@@ -219,6 +219,19 @@ int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *batch, int igli, double wi
 int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
                    int os_nm, double wind, double ind_surf, float *surf, int *il_out);
 
+/* SOS_SURFACE_BPDF (SOS_SURFACE_BPDF.F:219-392) for the Rondeaux (isurf = 4) and Breon (isurf = 5) vegetation / soil BPDF
+ * models: SOS_GSF_RONDEAUX_BREON + SOS_MAT_FRESNEL + SOS_MAT_REFLEXION + SOS_MISE_FORMAT; same record layout as sosgpu_glitter.
+ * (The Nadal and Maignan models, isurf 6 / 7, are not provided: SOSGPU_ERR_ARG.) */
+int sosgpu_surface_bpdf(sosgpu_ctx *ctx, int isurf, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
+                        int os_nm, double ind_surf, float *surf);
+
+/* SOS_ROUJEAN (SOS_ROUJEAN.F:212-416: SOS_FSF_ROUJEAN + SOS_MISE_FORMAT_RJ): Fourier series of Roujean's BRDF (k0, k1, k2) for
+ * every (incidence, reflection) pair, surf [os_nb+1][9][N][N] REAL*4 (only R11 non-zero).  SOSGPU_ERR_IER when the model
+ * gives a negative BRDF (the reference's label 993). */
+int sosgpu_roujean(sosgpu_ctx *ctx, int nbmu, const double *rmu, int os_nb, double k0, double k1, double k2, float *surf);
+/* SOS_BPDF_AJOUT_BRDF (SOS_SURFACE.F:2503-2669): out = surf1 + surf2, record by record (BPDF + BRDF land surface) */
+int sosgpu_bpdf_ajout_brdf(sosgpu_ctx *ctx, const float *surf1, const float *surf2, int nbmu, int os_nb, float *out);
+
 /* SOS_MAT_FRESNEL (SOS_SURFACE.F:1235-1603): Legendre expansion of the Fresnel reflection matrix for the refractive index
  * ind_surf on the quadrature (rmu, chr: [2N+1]); returns what the reference's RES_FRESNEL file holds, i.e. the coefficients
  * [os_ns+1] after the 4(E15.8) decimal round trip. */

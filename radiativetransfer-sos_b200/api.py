@@ -445,6 +445,33 @@ class Solver:
         self._check(rc, "glitter")
         return surf, il
 
+    def surface_bpdf(self, isurf, nbmu, rmu, chr_, ind_surf, os_nb, os_ns, os_nm):
+        """SOS_SURFACE_BPDF (SOS_SURFACE_BPDF.F:219) for isurf = 4 (Rondeaux) or 5 (Breon): records [os_nb+1, 9, N, N] REAL*4."""
+        surf = np.zeros((os_nb + 1, 9, nbmu, nbmu), dtype=np.float32)
+        rc = self.lib.sosgpu_surface_bpdf(self.ctx, C.c_int(isurf), C.c_int(nbmu), _d(_f64(rmu)), _d(_f64(chr_)), C.c_int(os_nb),
+                                          C.c_int(os_ns), C.c_int(os_nm), C.c_double(ind_surf), surf.ctypes.data_as(c_fp))
+        self._check(rc, "surface_bpdf")
+        return surf
+
+    def roujean(self, nbmu, rmu, os_nb, k0, k1, k2):
+        """SOS_ROUJEAN (SOS_ROUJEAN.F:212): Fourier series of Roujean's BRDF, records [os_nb+1, 9, N, N] REAL*4."""
+        surf = np.zeros((os_nb + 1, 9, nbmu, nbmu), dtype=np.float32)
+        rc = self.lib.sosgpu_roujean(self.ctx, C.c_int(nbmu), _d(_f64(rmu)), C.c_int(os_nb), C.c_double(k0), C.c_double(k1),
+                                     C.c_double(k2), surf.ctypes.data_as(c_fp))
+        self._check(rc, "roujean")
+        return surf
+
+    def bpdf_ajout_brdf(self, surf1, surf2):
+        """SOS_BPDF_AJOUT_BRDF (SOS_SURFACE.F:2503): sum of two surface files (BPDF + BRDF)."""
+        a = np.ascontiguousarray(surf1, dtype=np.float32)
+        b = np.ascontiguousarray(surf2, dtype=np.float32)
+        assert a.shape == b.shape
+        out = np.zeros_like(a)
+        rc = self.lib.sosgpu_bpdf_ajout_brdf(self.ctx, a.ctypes.data_as(c_fp), b.ctypes.data_as(c_fp), C.c_int(a.shape[2]),
+                                             C.c_int(a.shape[0] - 1), out.ctypes.data_as(c_fp))
+        self._check(rc, "bpdf_ajout_brdf")
+        return out
+
     def mat_fresnel(self, nbmu, rmu, chr_, ind_surf, os_ns):
         """SOS_MAT_FRESNEL (SOS_SURFACE.F:1235): alpha, beta, gamma, zeta [os_ns+1] as the RES_FRESNEL file holds them."""
         out = [np.zeros(os_ns + 1) for _ in range(4)]

@@ -48,6 +48,17 @@ __global__ void k_glitter(GlitterParams p, float *__restrict__ surf, int *__rest
   cs12 = .5 * cs12 * cs12;
   const int tid = threadIdx.x, nthr = blockDim.x;
 
+  if (p.gmodel != 0) {
+    // ---------------- SOS_GSF_RONDEAUX_BREON (SOS_SURFACE_BPDF.F:463-591): G does not depend on the azimuth ----------------
+    for (int i = tid; i < ng; i += nthr) G[i] = 0.0;
+    __syncthreads();
+    if (tid == 0) {
+      G[0] = (p.gmodel == 1) ? 1. / (1. / c1 + 1. / c2) : 1.;    // Rondeaux : Breon
+      s_il = 0;
+      if (il_out) il_out[pair] = 0;
+    }
+    __syncthreads();
+  } else {
   // ---------------- SOS_GSF: support [0, PHIB] of G(phi) ----------------
   if (tid == 0) {
     double g = calcg(cs12, c12, s12, sig, 0.0);
@@ -112,6 +123,7 @@ __global__ void k_glitter(GlitterParams p, float *__restrict__ surf, int *__rest
     if (il_out) il_out[pair] = il;
   }
   __syncthreads();
+  }
   const int lim = s_il;
   for (int i = lim + 1 + tid; i <= NM; i += nthr) G[i] = 0.0;        // SOS_SURFACE.F:1846-1848
 

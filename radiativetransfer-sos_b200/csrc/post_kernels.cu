@@ -12,6 +12,7 @@
 #define THRESHOLD_QU (1.0e-15)            // CTE_THRESHOLD_Q_U_NULL SOS.h:418
 #define SOLAR_DISC   (6.8e-05)            // CTE_SOLAR_DISC_SOLID_ANGLE SOS.h:426
 #define VALEUR_INDEF (-999.0)             // INCTE_VALEUR_INDEF SOS_TRPHI.F:134
+#define SOSGPU_NB_MAX_DEV 200             // CTE_OS_NB_MAX SOS.h:480
 
 // SOS_GLITTE, SOS_TRPHI.F:1278-1317
 __device__ static double glitte(double sig, double c0, double c1, double phi)
@@ -256,4 +257,102 @@ extern "C" void sos_launch_axpy(double *res, const double *tmp, double aik, size
 {
   if (n == 0) return;
   k_axpy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(res, tmp, aik, n);
+}
+
+
+// =================================================================================================
+// SOS_ROUJEAN (SOS_ROUJEAN.F:212-416) = SOS_FSF_ROUJEAN (:417-832) + SOS_MISE_FORMAT_RJ (:1102-1224): Fourier series of
+// Roujean's BRDF F(theta1, theta2, phi) for every (incidence, reflection) pair, written straight into the surface-file
+// record layout (only P11 is non-zero).  One CTA per pair (I1, I2):
+//   U(i) = F(phi_i), i = 0..1024                                   one thread per sample (:513-521)
+//   E(s) = (sum_i U(i) cos(s phi_i)) * Q / pi, i ascending         one thread per order s: the reference's own sequence (:556-563)
+//   B1(s) = max_i |(T1_s(i) - F_i)/F_i|, T1_s(i) = E(0) + 2 sum_{s'<=s} E(s') cos(s' phi_i)   one thread per sample walks s
+//           upwards with a running sum (the reference's order of additions, :571-586); the maximum is order independent
+//   the series stops at the first s where B1 no longer decreases (:588-593): later coefficients stay zero.
+// status[pair] = 1 when a negative BRDF value was met (the reference aborts with IER = -1, label 993).
+#define RJ_NU 1024
+__device__ __forceinline__ void atomic_max_pos(double *addr, double v)
+{
+  // non-negative doubles order like their bit patterns; NaN (0/0) has a larger pattern than any finite value, which makes the
+  // comparison B1 > threshold / B1 < B1_PREC false, as in the reference
+  atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+__global__ void k_roujean(int N, const double *__restrict__ rmu, int os_nb, double k0, double k1, double k2,
+                          float *__restrict__ surf, int *__restrict__ status)
+{
+  __shared__ double U[RJ_NU + 1];
+  __shared__ double E[SOSGPU_NB_MAX_DEV + 1], B1[SOSGPU_NB_MAX_DEV + 1];
+  __shared__ int s_last, s_neg;
+  const int pair = blockIdx.x;
+  const int I1 = pair / N + 1, I2 = pair % N + 1;
+  const double pi = acos(-1.0);
+  const double c1 = rmu[I1 + N], c2 = rmu[I2 + N];
+  const double s1 = sqrt(1 - c1 * c1), s2 = sqrt(1 - c2 * c2);
+  const double q = pi / RJ_NU;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  if (tid == 0) s_neg = 0;
+  for (int s = tid; s <= os_nb; s += nthr) B1[s] = 0.0;
+  __syncthreads();
+  for (int i = tid; i <= RJ_NU; i += nthr) {
+    const double phios = q * i;
+    const double f = calc_f_roujean(k0, k1, k2, c1, s1, c2, s2, pi - phios);
+    U[i] = f;
+    if (f < 0.0) s_neg = 1;
+  }
+  __syncthreads();
+  for (int s = tid; s <= os_nb; s += nthr) {
+    double y = 0.0;
+    for (int i = 0; i <= RJ_NU; ++i) {
+      const double phios = i * q;
+      y = y + U[i] * cos(s * phios);
+    }
+    E[s] = y * q / pi;
+  }
+  __syncthreads();
+  for (int i = tid; i <= RJ_NU; i += nthr) {
+    const double phios = q * i;
+    const double f = U[i];
+    double t1 = E[0];
+    atomic_max_pos(&B1[0], fabs((t1 - f) / f));
+    for (int s = 1; s <= os_nb; ++s) {
+      t1 = t1 + 2. * E[s] * cos(s * phios);
+      atomic_max_pos(&B1[s], fabs((t1 - f) / f));
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {                                             // :588-596: stop when the recombination error stops decreasing
+    double b1_prec = 1.e300;
+    int last = os_nb;                                         // last order whose coefficient was computed by the reference
+    for (int s = 0; s <= os_nb; ++s) {
+      if (B1[s] < b1_prec) { b1_prec = B1[s]; continue; }
+      last = s;
+      break;
+    }
+    s_last = last;
+    if (status) status[pair] = s_neg;
+  }
+  __syncthreads();
+  const int last = s_last;
+  const size_t nn = (size_t)N * N;
+  for (int s = tid; s <= os_nb; s += nthr) {
+    float *rec = surf + (size_t)s * 9 * nn;                   // record s, matrix P11, element (I, J) column-major
+    rec[(size_t)(I2 - 1) * N + (I1 - 1)] = (s <= last) ? (float)E[s] : 0.f;
+  }
+}
+
+extern "C" void sos_launch_roujean(int N, const double *rmu, int os_nb, double k0, double k1, double k2, float *surf, int *status,
+                                   cudaStream_t st)
+{
+  k_roujean<<<N * N, 256, 0, st>>>(N, rmu, os_nb, k0, k1, k2, surf, status);
+}
+
+// SOS_BPDF_AJOUT_BRDF (SOS_SURFACE.F:2503-2669): the nine REAL*4 matrices of two surface files are added record by record
+__global__ void k_ajout_brdf(float *out, const float *a, const float *b, size_t n)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+extern "C" void sos_launch_ajout_brdf(float *out, const float *a, const float *b, size_t n, cudaStream_t st)
+{
+  if (n) k_ajout_brdf<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, a, b, n);
 }

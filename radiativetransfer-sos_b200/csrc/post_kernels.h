@@ -20,6 +20,7 @@ struct TrphiParams {
 };
 struct GlitterParams {       // SOS_GLITTER (SOS_GLITTER.F:229): one surface file
   int nbmu, os_nb, os_ns, os_nm;
+  int gmodel;                // G function: 0 Cox-Munk (SOS_GSF), 1 Rondeaux, 2 Breon (SOS_GSF_RONDEAUX_BREON, azimuth independent)
   double sig, coef, pi;      // sigma^2 = .003 + .00512*W (REAL*4 literals), COEF = 1/sigma^2
   const double *rmu;         // [2N+1] device
   const double *alpha, *beta, *gamma, *zeta;   // [os_ns+1] Fresnel expansion (after the E15.8 channel), device
@@ -34,6 +35,10 @@ void sos_launch_trphi(const TrphiGroup *groups, int ngroup, const double *phis, 
                       TrphiParams prm, double *out, cudaStream_t st);
 void sos_launch_trphi_stride(const TrphiGroup *groups, int ngroup, const double *phis, int nphi, int nout,
                              TrphiParams prm, double *out, cudaStream_t st);
+// SOS_ROUJEAN: surf [os_nb+1][9][N][N] REAL*4 (zeroed by the caller), status [N*N] (1: negative BRDF met)
+void sos_launch_roujean(int N, const double *rmu, int os_nb, double k0, double k1, double k2, float *surf, int *status,
+                        cudaStream_t st);
+void sos_launch_ajout_brdf(float *out, const float *a, const float *b, size_t n, cudaStream_t st);
 void sos_launch_axpy(double *res, const double *tmp, double aik, size_t n, cudaStream_t st);
 #ifdef __cplusplus
 }

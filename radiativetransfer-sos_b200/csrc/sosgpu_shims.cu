@@ -142,8 +142,9 @@ extern "C" int sosgpu_mat_fresnel(sosgpu_ctx *ctx, int nbmu, const double *rmu, 
 }
 
 // SOS_GLITTER (SOS_GLITTER.F:229-371): surface-file records of a rough sea, one fused kernel (glitter_kernel.cu)
-extern "C" int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
-                              int os_nm, double wind, double ind_surf, float *surf, int *il_out)
+// gmodel 0: Cox-Munk glitter (wind); 1 / 2: Rondeaux / Breon BPDF (SOS_SURFACE_BPDF.F:219-392 with ISURF = 4 / 5)
+static int reflection_matrices(sosgpu_ctx *ctx, int gmodel, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
+                               int os_nm, double wind, double ind_surf, float *surf, int *il_out)
 {
   if (!ctx) return SOSGPU_ERR_NO_DEVICE;
   if (!rmu || !chr || !surf || nbmu < 1 || nbmu > SOSGPU_NBMU_MAX || os_nb > SOSGPU_NB_MAX || os_ns < 2 || os_ns > 136 ||
@@ -164,9 +165,9 @@ extern "C" int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, cons
   const int rcf = mat_fresnel_device(ctx, N, ind_surf, os_ns, d_in, coef);
   if (rcf != SOSGPU_OK) return rcf;
   GlitterParams p{};
-  p.nbmu = N; p.os_nb = os_nb; p.os_ns = os_ns; p.os_nm = os_nm;
+  p.nbmu = N; p.os_nb = os_nb; p.os_ns = os_ns; p.os_nm = os_nm; p.gmodel = gmodel;
   p.sig = (double)0.003f + (double)0.00512f * wind;            // SIG = .003 + .00512*WIND (SOS_GLITTER.F:300)
-  p.coef = 1.0 / p.sig;                                        // (1./SIG) (:315)
+  p.coef = gmodel == 0 ? 1.0 / p.sig : 1.0;                    // (1./SIG) (:315); SOS_MAT_REFLEXION(1.D+00, ...) for the BPDF models
   p.pi = std::acos(-1.0);
   p.rmu = d_in; p.alpha = d_in + 2 * W; p.beta = p.alpha + (os_ns + 1); p.gamma = p.beta + (os_ns + 1); p.zeta = p.gamma + (os_ns + 1);
   cudaEventRecord(ctx->ev_a, ctx->stream);
@@ -178,6 +179,69 @@ extern "C" int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, cons
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
   cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);
+  return SOSGPU_OK;
+}
+
+extern "C" int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
+                              int os_nm, double wind, double ind_surf, float *surf, int *il_out)
+{
+  return reflection_matrices(ctx, 0, nbmu, rmu, chr, os_nb, os_ns, os_nm, wind, ind_surf, surf, il_out);
+}
+
+extern "C" int sosgpu_surface_bpdf(sosgpu_ctx *ctx, int isurf, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
+                                   int os_nm, double ind_surf, float *surf)
+{
+  if (ctx && isurf != 4 && isurf != 5) { ctx->err = "sosgpu_surface_bpdf: only the Rondeaux (4) and Breon (5) models are provided"; return SOSGPU_ERR_ARG; }
+  return reflection_matrices(ctx, isurf == 4 ? 1 : 2, nbmu, rmu, chr, os_nb, os_ns, os_nm, 0.0, ind_surf, surf, nullptr);
+}
+
+// SOS_ROUJEAN (SOS_ROUJEAN.F:212): Fourier series of Roujean's BRDF in the surface-file record layout
+extern "C" int sosgpu_roujean(sosgpu_ctx *ctx, int nbmu, const double *rmu, int os_nb, double k0, double k1, double k2, float *surf)
+{
+  if (!ctx) return SOSGPU_ERR_NO_DEVICE;
+  if (!rmu || !surf || nbmu < 1 || nbmu > SOSGPU_NBMU_MAX || os_nb < 0 || os_nb > SOSGPU_NB_MAX) { ctx->err = "sosgpu_roujean: bad arguments"; return SOSGPU_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const int N = nbmu, W = 2 * N + 1;
+  const size_t nsurf = (size_t)(os_nb + 1) * 9 * N * N;
+  const size_t in_bytes = ((size_t)W * 8 + 255) / 256 * 256, st_bytes = ((size_t)N * N * 4 + 255) / 256 * 256;
+  char *d_blk = nullptr;
+  CK(sos_dmalloc(ctx, &d_blk, in_bytes + st_bytes + nsurf * 4));
+  struct Guard { sosgpu_ctx *c; void *p; ~Guard() { sos_dfree(c, p); } } guard{ctx, d_blk};
+  double *d_rmu = (double *)d_blk; int *d_status = (int *)(d_blk + in_bytes); float *d_surf = (float *)(d_blk + in_bytes + st_bytes);
+  CK(cudaMemcpyAsync(d_rmu, rmu, W * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(d_surf, 0, nsurf * 4, ctx->stream));
+  cudaEventRecord(ctx->ev_a, ctx->stream);
+  sos_launch_roujean(N, d_rmu, os_nb, k0, k1, k2, d_surf, d_status, ctx->stream);
+  cudaEventRecord(ctx->ev_b, ctx->stream);
+  ctx->launches += 1;
+  std::vector<int> status((size_t)N * N);
+  CK(cudaMemcpyAsync(status.data(), d_status, status.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(surf, d_surf, nsurf * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);
+  for (int v : status)
+    if (v) { ctx->err = "SOS_FSF_ROUJEAN : BRDF < 0 (unsuitable model parameters)"; return SOSGPU_ERR_IER; }   // label 993
+  return SOSGPU_OK;
+}
+
+// SOS_BPDF_AJOUT_BRDF (SOS_SURFACE.F:2503): out = surf1 + surf2 over [os_nb+1][9][N][N] REAL*4 records
+extern "C" int sosgpu_bpdf_ajout_brdf(sosgpu_ctx *ctx, const float *surf1, const float *surf2, int nbmu, int os_nb, float *out)
+{
+  if (!ctx) return SOSGPU_ERR_NO_DEVICE;
+  if (!surf1 || !surf2 || !out || nbmu < 1 || nbmu > SOSGPU_NBMU_MAX || os_nb < 0 || os_nb > SOSGPU_NB_MAX) return SOSGPU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)(os_nb + 1) * 9 * nbmu * nbmu;
+  float *d = nullptr;
+  CK(sos_dmalloc(ctx, &d, 3 * n * 4));
+  struct Guard { sosgpu_ctx *c; void *p; ~Guard() { sos_dfree(c, p); } } guard{ctx, d};
+  CK(cudaMemcpyAsync(d, surf1, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d + n, surf2, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  sos_launch_ajout_brdf(d + 2 * n, d, d + n, n, ctx->stream);
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(out, d + 2 * n, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
   return SOSGPU_OK;
 }
 

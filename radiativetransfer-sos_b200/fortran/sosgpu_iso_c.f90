@@ -74,5 +74,70 @@ module sosgpu_iso_c
       real(c_double), value :: tau, tauout, wind, ind_surf, phios
       real(c_double), intent(out) :: phi_fin(*), theta_fin(*), up(*), down(*)
     end function
+    ! ---- multi-GPU: one process (MPI rank) per GPU, the library owns the NCCL communicator --------------------------
+    integer(c_int) function sosgpu_comm_unique_id(id) bind(c, name="sosgpu_comm_unique_id")
+      import :: c_int, c_char
+      character(kind=c_char), intent(out) :: id(128)           ! rank 0 creates it; MPI_Bcast the 128 bytes
+    end function
+    integer(c_int) function sosgpu_comm_init(ctx, nranks, rank, id) bind(c, name="sosgpu_comm_init")
+      import :: c_ptr, c_int, c_char
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nranks, rank
+      character(kind=c_char), intent(in) :: id(128)
+    end function
+    integer(c_int) function sosgpu_batch_upload(ctx, optics, noptics, terms, nterm, ngroup, batch) &
+                                                bind(c, name="sosgpu_batch_upload")
+      import :: c_ptr, c_int, sosgpu_optics, sosgpu_term
+      type(c_ptr), value :: ctx
+      type(sosgpu_optics), intent(in) :: optics(*)
+      integer(c_int), value :: noptics
+      type(sosgpu_term), intent(in) :: terms(*)
+      integer(c_int), value :: nterm, ngroup
+      type(c_ptr), intent(out) :: batch
+    end function
+    integer(c_int) function sosgpu_batch_run(ctx, batch, rec_stride, wmax, part_only, term_out, group_out) &
+                                             bind(c, name="sosgpu_batch_run")
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx, batch, term_out, group_out     ! c_loc of the out structures, or c_null_ptr
+      integer(c_int), value :: rec_stride, wmax, part_only
+    end function
+    integer(c_int) function sosgpu_batch_reduce_groups(ctx, batch, root) bind(c, name="sosgpu_batch_reduce_groups")
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx, batch
+      integer(c_int), value :: root                             ! ONE ncclReduce of the partial CKD sums + metadata
+    end function
+    integer(c_int) function sosgpu_batch_groups(ctx, batch, rec_stride, wmax, group_out) bind(c, name="sosgpu_batch_groups")
+      import :: c_ptr, c_int, sosgpu_group_out
+      type(c_ptr), value :: ctx, batch
+      integer(c_int), value :: rec_stride, wmax
+      type(sosgpu_group_out), intent(in) :: group_out
+    end function
+    integer(c_int) function sosgpu_batch_trphi(ctx, batch, igli, wind, ind_surf, ifresnel, itrphi, phios, pas_phi, ipolar, &
+                                               nphi_cap, up, down) bind(c, name="sosgpu_batch_trphi")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: ctx, batch, up, down
+      integer(c_int), value :: igli, ifresnel, itrphi, pas_phi, ipolar, nphi_cap
+      real(c_double), value :: wind, ind_surf, phios
+    end function
+    integer(c_int) function sosgpu_batch_gather_tables(ctx, batch, root, groups_of_rank, nphi, nmax, up, down) &
+                                                       bind(c, name="sosgpu_batch_gather_tables")
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx, batch, up, down
+      integer(c_int), value :: root, nphi, nmax
+      integer(c_int), intent(in) :: groups_of_rank(*)
+    end function
+    subroutine sosgpu_batch_free(ctx, batch) bind(c, name="sosgpu_batch_free")
+      import :: c_ptr
+      type(c_ptr), value :: ctx, batch
+    end subroutine
+    ! ---- SOS_Up.txt / SOS_Down.txt (SOS_ABS_MAIN.F:2250-2519), byte-compatible ---------------------------------------
+    integer(c_int) function sosgpu_write_updown(fic_up, fic_down, nbmu, itrphi, phios, pas_phi, zout, phi_fin, theta_fin, &
+                                                up, down, nphi_cap, fix_sca_index) bind(c, name="sosgpu_write_updown")
+      import :: c_int, c_double, c_char
+      character(kind=c_char), intent(in) :: fic_up(*), fic_down(*)   ! NUL-terminated
+      integer(c_int), value :: nbmu, itrphi, pas_phi, nphi_cap, fix_sca_index
+      real(c_double), value :: phios, zout
+      real(c_double), intent(in) :: phi_fin(*), theta_fin(*), up(*), down(*)
+    end function
   end interface
 end module sosgpu_iso_c

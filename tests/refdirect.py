@@ -66,6 +66,46 @@ def glitter(ref, fm, tmp, N, rmu, ga, wind, ind, os_nb, os_ns, os_nm):
     return fm.read_surface_bin(fgl, N)
 
 
+def roujean(ref, fm, tmp, N, rmu, ga, os_nb, k0, k1, k2):
+    """SOS_ROUJEAN (SOS_ROUJEAN.F:212) through its files -> (IER, REAL*4 records [os_nb+1][9][N][N])."""
+    r, g = _angles(rmu, ga, N)
+    f = os.path.join(tmp, "ROUJEAN.bin")
+    if os.path.exists(f):
+        os.remove(f)
+    ier = C.c_int(99)
+    ref.sos_roujean_(_ip(N), _P(r), _P(g), _ip(os_nb), _dp(k0), _dp(k1), _dp(k2), _fs(os.path.join(tmp, "RJ_MAT_REFLEX")), _fs(f),
+                     _ip(0), C.byref(ier), _L, _L)
+    return ier.value, (fm.read_surface_bin(f, N) if ier.value == 0 else None)
+
+
+def surface_bpdf(ref, fm, tmp, isurf, N, rmu, ga, ind, os_nb, os_ns, os_nm):
+    """SOS_SURFACE_BPDF (SOS_SURFACE_BPDF.F:219) through its files -> REAL*4 records."""
+    r, g = _angles(rmu, ga, N)
+    f = os.path.join(tmp, "BPDF.bin")
+    if os.path.exists(f):
+        os.remove(f)
+    ier = C.c_int(99)
+    ref.sos_surface_bpdf_(_ip(N), _P(r), _P(g), _dp(ind), _ip(isurf), _dp(0.0), _dp(0.0), _dp(0.0), _ip(os_nb), _ip(os_ns), _ip(os_nm),
+                          _fs(os.path.join(tmp, "B_GSF")), _fs(os.path.join(tmp, "B_FRESNEL")), _fs(os.path.join(tmp, "B_MAT_REFLEX")),
+                          _fs(f), _ip(0), C.byref(ier), _L, _L, _L, _L)
+    assert ier.value == 0, "reference SOS_SURFACE_BPDF IER=%d" % ier.value
+    return fm.read_surface_bin(f, N)
+
+
+def bpdf_ajout_brdf(ref, fm, tmp, surf1, surf2):
+    """SOS_BPDF_AJOUT_BRDF (SOS_SURFACE.F:2503) through its files."""
+    N, os_nb = surf1.shape[2], surf1.shape[0] - 1
+    f1, f2, f3 = (os.path.join(tmp, n) for n in ("AJ1.bin", "AJ2.bin", "AJ3.bin"))
+    fm.write_surface_bin(f1, surf1)
+    fm.write_surface_bin(f2, surf2)
+    if os.path.exists(f3):
+        os.remove(f3)
+    ier = C.c_int(99)
+    ref.sos_bpdf_ajout_brdf_(_fs(f1), _fs(f2), _ip(N), _ip(os_nb), _fs(f3), C.byref(ier), _L, _L, _L)
+    assert ier.value == 0, "reference SOS_BPDF_AJOUT_BRDF IER=%d" % ier.value
+    return fm.read_surface_bin(f3, N)
+
+
 def mat_fresnel(ref, tmp, N, rmu, ga, ind, os_ns):
     """SOS_MAT_FRESNEL (SOS_SURFACE.F:1235) -> alpha, beta, gamma, zeta [os_ns+1] read back from its 4(E15.8) text file."""
     r, g = _angles(rmu, ga, N)

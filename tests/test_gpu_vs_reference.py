@@ -186,3 +186,46 @@ def test_order1_isolated(pkg, solver, ref):
     bad = refdirect.compare_terms(tr, res, ids, wl, assert_stokes_close, "order1")
     assert not bad
     assert np.all(tr.n_scatter[:, :3] <= 2)
+
+
+def test_land_surface_files_roujean_breon(pkg, solver, ref, tmp_path):
+    """SOS_ROUJEAN (BRDF Fourier series), SOS_SURFACE_BPDF for the Rondeaux and Breon models and
+    SOS_BPDF_AJOUT_BRDF, each against the reference through its files; then cfg4's surface for real: the Roujean + Breon
+    file made on each side feeds each side's solve (N=25, OS_NB=80)."""
+    syn, fm = pkg.synth, pkg.formats
+    rmu, ga, n0, _ = syn.sos_angles(24, 35.0)
+    N, os_nb, os_ns = (rmu.size - 1) // 2, 80, 48
+    k = (0.25, 0.04, 0.30)
+    ier, rj_ref = refdirect.roujean(ref, fm, str(tmp_path), N, rmu, ga, os_nb, *k)
+    assert ier == 0
+    rj = solver.roujean(N, rmu, os_nb, *k)
+    same = np.mean(rj.view(np.uint32) == rj_ref.view(np.uint32))
+    nz_ref = (np.abs(rj_ref[:, 0]).reshape(os_nb + 1, -1).max(axis=1) > 0).sum()
+    nz = (np.abs(rj[:, 0]).reshape(os_nb + 1, -1).max(axis=1) > 0).sum()
+    print("\n[roujean N=%d] REAL*4 records bit-identical: %.4f %%; orders with a non-zero coefficient: %d (reference %d)"
+          % (N, 100 * same, nz, nz_ref))
+    assert same > 0.995 and np.abs(rj - rj_ref).max() <= 2e-7 * np.abs(rj_ref).max()
+    for isurf in (4, 5):
+        b_ref = refdirect.surface_bpdf(ref, fm, str(tmp_path), isurf, N, rmu, ga, 1.5, os_nb, os_ns, os_nb + os_ns)
+        b = solver.surface_bpdf(isurf, N, rmu, ga, 1.5, os_nb, os_ns, os_nb + os_ns)
+        assert np.mean(b.view(np.uint32) == b_ref.view(np.uint32)) > 0.999, isurf
+        assert np.abs(b - b_ref).max() <= 2e-7 * np.abs(b_ref).max()
+    s_ref = refdirect.bpdf_ajout_brdf(ref, fm, str(tmp_path), b_ref, rj_ref)
+    s_gpu = solver.bpdf_ajout_brdf(b, rj)
+    assert np.array_equal(solver.bpdf_ajout_brdf(b_ref, rj_ref).view(np.uint32), s_ref.view(np.uint32))
+    # cfg4 for real: Roujean BRDF + Breon BPDF surface, each side with its own file
+    import copy
+    wl = syn.config_hyperspectral(nwave=3, nb_gauss=24, os_nb=80)
+    for o in wl.optics:
+        o.rho = 0.0
+    wl_ref, wl_gpu = copy.deepcopy(wl), copy.deepcopy(wl)
+    for o in wl_ref.optics:
+        o.surf = s_ref
+    for o in wl_gpu.optics:
+        o.surf = s_gpu
+    ids = list(range(len(wl.terms)))
+    res, _, _ = refdirect.runner().solve_terms(wl_ref, ids, CORES)
+    tr, gr = solver.solve(wl_gpu)
+    bad = refdirect.compare_terms(tr, res, ids, wl, assert_stokes_close, "cfg4-real")
+    _tally("cfg4 with the Roujean + Breon surface file made on each side (N=25)", bad, len(ids))
+    assert not bad
