@@ -145,6 +145,7 @@ int  sosgpu_batch_group_buffer(sosgpu_batch *batch, void **dev_ptr, size_t *n_do
 typedef struct {
   long long steps; double flops; double bytes; double step_ms; long long step_launches;
   double total_ms; long long launches;
+  double aggregate_ms;      /* device ms of the CKD aggregation kernel (SOS_AGGREGATE), CUDA events */
 } sosgpu_stats;
 int  sosgpu_batch_stats(const sosgpu_batch *batch, sosgpu_stats *st);
 
@@ -219,11 +220,11 @@ int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *batch, int igli, double wi
 int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
                    int os_nm, double wind, double ind_surf, float *surf, int *il_out);
 
-/* SOS_SURFACE_BPDF (SOS_SURFACE_BPDF.F:219-392) for the Rondeaux (isurf = 4) and Breon (isurf = 5) vegetation / soil BPDF
- * models: SOS_GSF_RONDEAUX_BREON + SOS_MAT_FRESNEL + SOS_MAT_REFLEXION + SOS_MISE_FORMAT; same record layout as sosgpu_glitter.
- * (The Nadal and Maignan models, isurf 6 / 7, are not provided: SOSGPU_ERR_ARG.) */
+/* SOS_SURFACE_BPDF (SOS_SURFACE_BPDF.F:219-392) for the Rondeaux (isurf = 4), Breon (5) and Maignan (7, coefficient coef_c)
+ * vegetation / soil BPDF models: SOS_GSF_RONDEAUX_BREON or SOS_GSF_MAIGNAN + SOS_MAT_FRESNEL + SOS_MAT_REFLEXION +
+ * SOS_MISE_FORMAT; same record layout as sosgpu_glitter.  (Nadal, isurf 6, is not provided: SOSGPU_ERR_ARG.) */
 int sosgpu_surface_bpdf(sosgpu_ctx *ctx, int isurf, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
-                        int os_nm, double ind_surf, float *surf);
+                        int os_nm, double ind_surf, double coef_c, float *surf);
 
 /* SOS_ROUJEAN (SOS_ROUJEAN.F:212-416: SOS_FSF_ROUJEAN + SOS_MISE_FORMAT_RJ): Fourier series of Roujean's BRDF (k0, k1, k2) for
  * every (incidence, reflection) pair, surf [os_nb+1][9][N][N] REAL*4 (only R11 non-zero).  SOSGPU_ERR_IER when the model

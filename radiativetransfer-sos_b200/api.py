@@ -58,7 +58,8 @@ class CDirectModels(C.Structure):
 
 class CStats(C.Structure):
     _fields_ = [("steps", C.c_longlong), ("flops", C.c_double), ("bytes", C.c_double), ("step_ms", C.c_double),
-                ("step_launches", C.c_longlong), ("total_ms", C.c_double), ("launches", C.c_longlong)]
+                ("step_launches", C.c_longlong), ("total_ms", C.c_double), ("launches", C.c_longlong),
+                ("aggregate_ms", C.c_double)]
 
 
 _lib = None
@@ -445,11 +446,13 @@ class Solver:
         self._check(rc, "glitter")
         return surf, il
 
-    def surface_bpdf(self, isurf, nbmu, rmu, chr_, ind_surf, os_nb, os_ns, os_nm):
-        """SOS_SURFACE_BPDF (SOS_SURFACE_BPDF.F:219) for isurf = 4 (Rondeaux) or 5 (Breon): records [os_nb+1, 9, N, N] REAL*4."""
+    def surface_bpdf(self, isurf, nbmu, rmu, chr_, ind_surf, os_nb, os_ns, os_nm, coef_c=0.0):
+        """SOS_SURFACE_BPDF (SOS_SURFACE_BPDF.F:219) for isurf = 4 (Rondeaux), 5 (Breon) or 7 (Maignan, coef_c): records
+        [os_nb+1, 9, N, N] REAL*4."""
         surf = np.zeros((os_nb + 1, 9, nbmu, nbmu), dtype=np.float32)
         rc = self.lib.sosgpu_surface_bpdf(self.ctx, C.c_int(isurf), C.c_int(nbmu), _d(_f64(rmu)), _d(_f64(chr_)), C.c_int(os_nb),
-                                          C.c_int(os_ns), C.c_int(os_nm), C.c_double(ind_surf), surf.ctypes.data_as(c_fp))
+                                          C.c_int(os_ns), C.c_int(os_nm), C.c_double(ind_surf), C.c_double(coef_c),
+                                          surf.ctypes.data_as(c_fp))
         self._check(rc, "surface_bpdf")
         return surf
 

@@ -22,6 +22,15 @@ __device__ __forceinline__ double calcg(double cs12, double c12, double s12, dou
   return x * x * exp(-(x - 1) / sig);
 }
 
+// SOS_CALCG_MAIGNAN, SOS_SURFACE_BPDF.F:1606-1641
+__device__ __forceinline__ double calcg_maignan(double c1, double c2, double s12, double phi, double coef_c)
+{
+  const double cos_2i = c1 * c2 - s12 * cos(phi);
+  double tan2_i = (1 - cos_2i) / (1 + cos_2i);
+  if (tan2_i < 0.0) tan2_i = 0.0;
+  return coef_c * exp(-sqrt(tan2_i)) / (1. / c1 + 1. / c2);
+}
+
 // smem: U[1025] | G[nm_alloc] | K[6][2][ns+1] | scalars
 __global__ void k_glitter(GlitterParams p, float *__restrict__ surf, int *__restrict__ il_out)
 {
@@ -47,8 +56,12 @@ __global__ void k_glitter(GlitterParams p, float *__restrict__ surf, int *__rest
   double cs12 = (c1 + c2);
   cs12 = .5 * cs12 * cs12;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  // G(theta1, theta2, phi): Cox-Munk wave-slope function (SOS_CALCG) or Maignan's BPDF function (gmodel 3, SOS_CALCG_MAIGNAN)
+  auto gfun = [&](double phi) -> double {
+    return (p.gmodel == 3) ? calcg_maignan(c1, c2, s12, phi, p.coef_c) : calcg(cs12, c12, s12, sig, phi);
+  };
 
-  if (p.gmodel != 0) {
+  if (p.gmodel == 1 || p.gmodel == 2) {
     // ---------------- SOS_GSF_RONDEAUX_BREON (SOS_SURFACE_BPDF.F:463-591): G does not depend on the azimuth ----------------
     for (int i = tid; i < ng; i += nthr) G[i] = 0.0;
     __syncthreads();
@@ -61,9 +74,9 @@ __global__ void k_glitter(GlitterParams p, float *__restrict__ surf, int *__rest
   } else {
   // ---------------- SOS_GSF: support [0, PHIB] of G(phi) ----------------
   if (tid == 0) {
-    double g = calcg(cs12, c12, s12, sig, 0.0);
+    double g = gfun(0.0);
     const double gmax = g;
-    g = calcg(cs12, c12, s12, sig, pi);
+    g = gfun(pi);
     double gmin = g, phib, q;
     double x = PH_TEST * gmin;
     if (x >= gmax) {                                         // :568-573
@@ -73,7 +86,7 @@ __global__ void k_glitter(GlitterParams p, float *__restrict__ surf, int *__rest
       double phi1 = 0, phi2 = pi;
       for (;;) {
         phib = .5 * (phi1 + phi2);
-        g = calcg(cs12, c12, s12, sig, phib);
+        g = gfun(phib);
         x = PH_TEST * g;
         if (fabs(x - gmax) < (double)0.01f * gmax) break;
         if (x <= gmax) phi2 = phib; else phi1 = phib;
@@ -86,7 +99,7 @@ __global__ void k_glitter(GlitterParams p, float *__restrict__ surf, int *__rest
   }
   __syncthreads();
   const double phib = s_phib, q = s_q, gmax = s_gmax;
-  for (int i = 1 + tid; i <= PH_NU; i += nthr) U[i] = calcg(cs12, c12, s12, sig, q * i);   // :574-578 / :630-634
+  for (int i = 1 + tid; i <= PH_NU; i += nthr) U[i] = gfun(q * i);   // :574-578 / :630-634
   for (int i = tid; i < ng; i += nthr) G[i] = 0.0;
   __syncthreads();
   const double gmin = (s_gmin < 0.0) ? U[PH_NU] : s_gmin;
@@ -117,7 +130,7 @@ __global__ void k_glitter(GlitterParams p, float *__restrict__ surf, int *__rest
     for (int is = 1; is <= NM; ++is) {
       t1 = t1 + 2 * G[is];
       const double b1 = fabs(t1 - gmax) / gmax;
-      if (!(b1 > (double)0.001f)) { il = is; break; }
+      if (!(b1 > (double)0.001f) && p.gmodel != 3) { il = is; break; }   // SOS_GSF_MAIGNAN never leaves the loop: IL = OS_NM
     }
     s_il = il;
     if (il_out) il_out[pair] = il;

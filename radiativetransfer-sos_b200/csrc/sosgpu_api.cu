@@ -698,8 +698,10 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     s0 = s1;
   }
 
+  CK(cudaEventRecord(b->ev0, st));
   sos_launch_aggregate(b->d_terms, b->d_group_start, b->d_group_terms, b->ngroup, b->d_rec, b->d_nf, b->rs_dev, b->w_dev,
                        b->d_grec, b->d_gnrec, st);
+  CK(cudaEventRecord(b->ev1, st));
   ctx->launches += 1;
   CK(cudaEventRecord(b->evt1, st));
   CK(cudaStreamSynchronize(st));
@@ -707,6 +709,8 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, b->evt0, b->evt1));
   b->stats.total_ms = ms;
+  CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  b->stats.aggregate_ms = ms;
   b->stats.launches = ctx->launches;
   return SOSGPU_OK;
 }
@@ -949,10 +953,11 @@ extern "C" int sosgpu_noyaux(sosgpu_ctx *ctx, int is, int nbmu, const double *rm
   size_t o_g = ar.put(gamma, (os_nb + 1) * 8), o_z = ar.put(zeta, (os_nb + 1) * 8);
   const size_t nb_basis = (size_t)3 * (os_nb + 2) * W, nb_ker = (size_t)6 * W * W, nb_xpl = (size_t)3 * W;
   char *d = nullptr; double *dw = nullptr; OpticsDev *dop = nullptr; KsetDev *dks = nullptr;
-  CK(sos_dmalloc(ctx, &d, ar.buf.size()));
-  CK(sos_dmalloc(ctx, &dw, (nb_basis + nb_ker + nb_xpl) * 8));
-  CK(sos_dmalloc(ctx, &dop, sizeof(OpticsDev)));
-  CK(sos_dmalloc(ctx, &dks, sizeof(KsetDev)));
+  SosFreeGuard guard(ctx);                                       // releases the temporaries on every return path
+  CK(sos_dmalloc(ctx, &d, ar.buf.size())); guard.add(d);
+  CK(sos_dmalloc(ctx, &dw, (nb_basis + nb_ker + nb_xpl) * 8)); guard.add(dw);
+  CK(sos_dmalloc(ctx, &dop, sizeof(OpticsDev))); guard.add(dop);
+  CK(sos_dmalloc(ctx, &dks, sizeof(KsetDev))); guard.add(dks);
   CK(cudaMemcpy(d, ar.buf.data(), ar.buf.size(), cudaMemcpyHostToDevice));
   CK(cudaMemset(dw, 0, (nb_basis + nb_ker + nb_xpl) * 8));
   OpticsDev op{};
@@ -975,7 +980,6 @@ extern "C" int sosgpu_noyaux(sosgpu_ctx *ctx, int is, int nbmu, const double *rm
   memcpy(bp, &ker[0], WW * 8); memcpy(gr, &ker[WW], WW * 8); memcpy(gt, &ker[2 * WW], WW * 8);
   memcpy(arr, &ker[3 * WW], WW * 8); memcpy(art, &ker[4 * WW], WW * 8); memcpy(att, &ker[5 * WW], WW * 8);
   memcpy(xpl, &x3[0], W * 8); memcpy(xrl, &x3[W], W * 8); memcpy(xtl, &x3[2 * W], W * 8);
-  sos_dfree(ctx, d); sos_dfree(ctx, dw); sos_dfree(ctx, dop); sos_dfree(ctx, dks);
   return SOSGPU_OK;
 }
 
@@ -1003,6 +1007,8 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
   sosgpu_batch *b = nullptr;
   int rc = upload_impl(ctx, &o, 1, &t, 1, 1, true, &b);
   if (rc != SOSGPU_OK) return rc;
+  struct BatchGuard { sosgpu_ctx *c; sosgpu_batch *b; ~BatchGuard() { sosgpu_batch_free(c, b); } } bguard{ctx, b};
+  SosFreeGuard guard(ctx);
   b->optics_dev[0].tab = rmu2[N];       // exact mu_s of the caller
   // rmu[N] in the arena was set from tetas; overwrite with the exact value
   CK(cudaMemcpy((void *)(b->optics_dev[0].rmu + N), &rmu2[N], 8, cudaMemcpyHostToDevice));
@@ -1017,7 +1023,7 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
   ks.optics = 0; ks.is = is; ks.dual = (is <= 2) ? 1 : 0; ks.beta0 = (is == 0) ? 1.0 : 0.0;
   const size_t kbytes = rup(3 * (os_nb + 2) * W * 8) + rup(6 * W * W * 8) + rup(3 * W * 8) + 2 * rup((size_t)KP * KP * 8) + 5 * rup(KP * 8) + rup(16 * KP * 8);
   char *kp = nullptr;
-  CK(sos_dmalloc(ctx, &kp, kbytes));
+  CK(sos_dmalloc(ctx, &kp, kbytes)); guard.add(kp);
   CK(cudaMemset(kp, 0, kbytes));
   char *p = kp;
   ks.basis = (double *)p; p += rup(3 * (os_nb + 2) * W * 8);
@@ -1032,7 +1038,7 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
   ks.urow = (double *)p; p += rup(KP * 8);
   ks.vpack = (double *)p; p += rup(16 * KP * 8);
   KsetDev *dks = nullptr;
-  CK(sos_dmalloc(ctx, &dks, sizeof(KsetDev)));
+  CK(sos_dmalloc(ctx, &dks, sizeof(KsetDev))); guard.add(dks);
   CK(cudaMemcpy(dks, &ks, sizeof(ks), cudaMemcpyHostToDevice));
   // fields: x[1] = input (order n=1 parity), x[0] = output, plus J dump
   const size_t fsz = std::max(SOS_XSIZE(KP, L), (size_t)KP * LP);   // field (chunk-major) or J dump ([row][LP])
@@ -1046,14 +1052,14 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
         for (int lv = 0; lv < L; ++lv) xin[SOS_XIDX(KP, r, lv)] = src[s][(size_t)(kk + N) * L + lv];
       }
   double *dx = nullptr;
-  CK(sos_dmalloc(ctx, &dx, 3 * fsz * 8));
+  CK(sos_dmalloc(ctx, &dx, 3 * fsz * 8)); guard.add(dx);
   CK(cudaMemset(dx, 0, 3 * fsz * 8));
   CK(cudaMemcpy(dx + fsz, xin.data(), fsz * 8, cudaMemcpyHostToDevice));
   ItemDev it{};
   it.term = 0; it.is = is; it.kset = 0; it.n = 1; it.active = 1;
   it.x[0] = dx; it.x[1] = dx + fsz;
   ItemDev *dit = nullptr;
-  CK(sos_dmalloc(ctx, &dit, sizeof(ItemDev)));
+  CK(sos_dmalloc(ctx, &dit, sizeof(ItemDev))); guard.add(dit);
   CK(cudaMemcpy(dit, &it, sizeof(it), cudaMemcpyHostToDevice));
   sos_launch_basis(dks, b->d_optics, 1, ctx->stream);
   sos_launch_kernels(dks, b->d_optics, 1, W, ctx->stream);
@@ -1077,7 +1083,5 @@ extern "C" int sosgpu_order_step(sosgpu_ctx *ctx, int is, int nbmu, const double
           if (dstj[s]) dstj[s][(size_t)(kk + N) * L + lv] = jo[(size_t)r * LP + lv];
         }
       }
-  sos_dfree(ctx, kp); sos_dfree(ctx, dks); sos_dfree(ctx, dx); sos_dfree(ctx, dit);
-  sosgpu_batch_free(ctx, b);
   return SOSGPU_OK;
 }

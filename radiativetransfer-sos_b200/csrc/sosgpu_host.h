@@ -36,6 +36,14 @@ struct sosgpu_ctx {
   cudaMemPool_t pool = nullptr;      // stream-ordered pool (release threshold = never) behind sos_dmalloc / sos_dfree
 };
 
+// frees a list of pool allocations when a routine leaves early (CK returns) or normally
+struct SosFreeGuard {
+  sosgpu_ctx *ctx; void *p[8]; int n = 0;
+  explicit SosFreeGuard(sosgpu_ctx *c) : ctx(c) {}
+  void add(void *q) { if (n < 8) p[n++] = q; }
+  ~SosFreeGuard();
+};
+
 template <class T> static inline cudaError_t sos_dmalloc(sosgpu_ctx *ctx, T **p, size_t bytes)
 {
   return cudaMallocFromPoolAsync((void **)p, bytes ? bytes : 8, ctx->pool, ctx->stream);
@@ -46,6 +54,7 @@ static inline void sos_dfree(sosgpu_ctx *ctx, void *p)
   if (ctx) cudaFreeAsync(p, ctx->stream);
   else cudaFree(p);
 }
+inline SosFreeGuard::~SosFreeGuard() { for (int i = 0; i < n; ++i) sos_dfree(ctx, p[i]); }
 
 struct HostOptics {
   int N, W, HB, KP, os_nb, n0, imat_surf, ifresnel, ipolar, igmax, n_surf_rec;

@@ -42,11 +42,12 @@ static int trphi_core(sosgpu_ctx *ctx, const double *rec, int nrec, int N, const
   double *d_rec = nullptr, *d_rmu = nullptr, *d_phi = nullptr, *d_out = nullptr;
   TrphiGroup *d_g = nullptr;
   const size_t nout = (size_t)2 * 7 * nphi * N;
-  CK(cudaMalloc(&d_rec, (size_t)nrec * 3 * W * 8));
-  CK(cudaMalloc(&d_rmu, W * 8));
-  CK(cudaMalloc(&d_phi, nphi * 8));
-  CK(cudaMalloc(&d_out, nout * 8));
-  CK(cudaMalloc(&d_g, sizeof(TrphiGroup)));
+  SosFreeGuard guard(ctx);                                       // pool allocations, released on every return path
+  CK(sos_dmalloc(ctx, &d_rec, (size_t)nrec * 3 * W * 8)); guard.add(d_rec);
+  CK(sos_dmalloc(ctx, &d_rmu, W * 8)); guard.add(d_rmu);
+  CK(sos_dmalloc(ctx, &d_phi, nphi * 8)); guard.add(d_phi);
+  CK(sos_dmalloc(ctx, &d_out, nout * 8)); guard.add(d_out);
+  CK(sos_dmalloc(ctx, &d_g, sizeof(TrphiGroup))); guard.add(d_g);
   CK(cudaMemcpyAsync(d_rec, rec, (size_t)nrec * 3 * W * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_rmu, rmu, W * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_phi, phis.data(), nphi * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -59,7 +60,6 @@ static int trphi_core(sosgpu_ctx *ctx, const double *rec, int nrec, int N, const
   CK(cudaMemcpyAsync(out.data(), d_out, nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
-  cudaFree(d_rec); cudaFree(d_rmu); cudaFree(d_phi); cudaFree(d_out); cudaFree(d_g);
   return SOSGPU_OK;
 }
 
@@ -144,7 +144,7 @@ extern "C" int sosgpu_mat_fresnel(sosgpu_ctx *ctx, int nbmu, const double *rmu, 
 // SOS_GLITTER (SOS_GLITTER.F:229-371): surface-file records of a rough sea, one fused kernel (glitter_kernel.cu)
 // gmodel 0: Cox-Munk glitter (wind); 1 / 2: Rondeaux / Breon BPDF (SOS_SURFACE_BPDF.F:219-392 with ISURF = 4 / 5)
 static int reflection_matrices(sosgpu_ctx *ctx, int gmodel, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
-                               int os_nm, double wind, double ind_surf, float *surf, int *il_out)
+                               int os_nm, double wind, double ind_surf, float *surf, int *il_out, double coef_c = 0.0)
 {
   if (!ctx) return SOSGPU_ERR_NO_DEVICE;
   if (!rmu || !chr || !surf || nbmu < 1 || nbmu > SOSGPU_NBMU_MAX || os_nb > SOSGPU_NB_MAX || os_ns < 2 || os_ns > 136 ||
@@ -165,7 +165,7 @@ static int reflection_matrices(sosgpu_ctx *ctx, int gmodel, int nbmu, const doub
   const int rcf = mat_fresnel_device(ctx, N, ind_surf, os_ns, d_in, coef);
   if (rcf != SOSGPU_OK) return rcf;
   GlitterParams p{};
-  p.nbmu = N; p.os_nb = os_nb; p.os_ns = os_ns; p.os_nm = os_nm; p.gmodel = gmodel;
+  p.nbmu = N; p.os_nb = os_nb; p.os_ns = os_ns; p.os_nm = os_nm; p.gmodel = gmodel; p.coef_c = coef_c;
   p.sig = (double)0.003f + (double)0.00512f * wind;            // SIG = .003 + .00512*WIND (SOS_GLITTER.F:300)
   p.coef = gmodel == 0 ? 1.0 / p.sig : 1.0;                    // (1./SIG) (:315); SOS_MAT_REFLEXION(1.D+00, ...) for the BPDF models
   p.pi = std::acos(-1.0);
@@ -189,10 +189,13 @@ extern "C" int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, cons
 }
 
 extern "C" int sosgpu_surface_bpdf(sosgpu_ctx *ctx, int isurf, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
-                                   int os_nm, double ind_surf, float *surf)
+                                   int os_nm, double ind_surf, double coef_c, float *surf)
 {
-  if (ctx && isurf != 4 && isurf != 5) { ctx->err = "sosgpu_surface_bpdf: only the Rondeaux (4) and Breon (5) models are provided"; return SOSGPU_ERR_ARG; }
-  return reflection_matrices(ctx, isurf == 4 ? 1 : 2, nbmu, rmu, chr, os_nb, os_ns, os_nm, 0.0, ind_surf, surf, nullptr);
+  if (ctx && isurf != 4 && isurf != 5 && isurf != 7) {
+    ctx->err = "sosgpu_surface_bpdf: the Rondeaux (4), Breon (5) and Maignan (7) models are provided, Nadal (6) is not";
+    return SOSGPU_ERR_ARG;
+  }
+  return reflection_matrices(ctx, isurf == 4 ? 1 : (isurf == 5 ? 2 : 3), nbmu, rmu, chr, os_nb, os_ns, os_nm, 0.0, ind_surf, surf, nullptr, coef_c);
 }
 
 // SOS_ROUJEAN (SOS_ROUJEAN.F:212): Fourier series of Roujean's BRDF in the surface-file record layout

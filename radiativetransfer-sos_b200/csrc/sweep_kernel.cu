@@ -87,15 +87,16 @@ __device__ __forceinline__ int acc_slot(int row, int cpair) { return row * (SW_A
 // (the zero padding at the end of a direction block is skipped).
 template <int NFR, int LR, int OWN, int KS>
 __device__ __forceinline__ void slab_mma(double (&acc)[2][8][2], double (&tacc)[2], const double *__restrict__ a,
-                                         const double *__restrict__ v, const double *__restrict__ b, int wr, int gq, int tq)
+                                         const double *__restrict__ v, const double *__restrict__ b, const double *__restrict__ bt,
+                                         bool do_t, int gq, int tq)
 {
   const int swz = 4 * (gq & 3);
 #pragma unroll
   for (int ks4 = 0; ks4 < KS; ++ks4) {
     const int kc = (ks4 * 4 + tq) ^ swz;
-    if (OWN) {
+    if (OWN && NFR > 0) {
       const double a0 = a[kc], a1 = a[8 * SOS_KB + kc];
-      double bv[NFR];
+      double bv[NFR > 0 ? NFR : 1];
 #pragma unroll
       for (int ni = 0; ni < NFR; ++ni) bv[ni] = b[ks4 * 4 * SOS_SB + ni * 8];
 #pragma unroll
@@ -104,7 +105,7 @@ __device__ __forceinline__ void slab_mma(double (&acc)[2][8][2], double (&tacc)[
         dmma8x8x4(acc[1][ni][0], acc[1][ni][1], a1, bv[ni]);
       }
     }
-    if (LR && wr < NFR) dmma8x8x4(tacc[0], tacc[1], v[kc], b[ks4 * 4 * SOS_SB + wr * 8]);   // T = V X, column block wr
+    if (LR && do_t) dmma8x8x4(tacc[0], tacc[1], v[kc], bt[ks4 * 4 * SOS_SB]);   // T = V X, this warp's column block
   }
 }
 
@@ -121,25 +122,27 @@ __device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned pari
 template <int NFR, int LR, int OWN>
 __device__ __forceinline__ void chunk_mma(double (&acc)[2][8][2], double (&tacc)[2], const unsigned char *sStage,
                                           unsigned long long *full, unsigned long long *empty, unsigned &q, int n_slab, int HB,
-                                          int N3, int wr, int lane, int gq, int tq)
+                                          int N3, int rg, int col0, int tcol, int lane, int gq, int tq)
 {
+  const bool do_t = tcol >= 0;                                   // this warp owns column block tcol / 8 of T = V X
   bool ready = mbar_test(full + q % SW_STG, (q / SW_STG) & 1);
   int kq = 0;                                                  // first k-row of the slab within its direction block
   for (int slab = 0; slab < n_slab; ++slab, ++q) {
     const int st = q % SW_STG;
     if (!ready) mbar_wait(full + st, (q / SW_STG) & 1);
     const unsigned char *sp = sStage + st * SW_STAGE;
-    const double *a = reinterpret_cast<const double *>(sp) + (wr * 16 + gq) * SOS_KB;
+    const double *a = reinterpret_cast<const double *>(sp) + (rg * 16 + gq) * SOS_KB;
     const double *v = reinterpret_cast<const double *>(sp + SW_A_BYTES) + gq * SOS_KB;
-    const double *b = reinterpret_cast<const double *>(sp + SW_A_BYTES + SW_V_BYTES) + tq * SOS_SB + gq;
+    const double *b0 = reinterpret_cast<const double *>(sp + SW_A_BYTES + SW_V_BYTES) + tq * SOS_SB + gq;
+    const double *b = b0 + col0, *bt = b0 + (do_t ? tcol : 0);
     ready = mbar_test(full + (q + 1) % SW_STG, ((q + 1) / SW_STG) & 1);   // result is consumed after this slab's DMMAs
-    if (kq + SOS_KB <= N3) slab_mma<NFR, LR, OWN, 4>(acc, tacc, a, v, b, wr, gq, tq);
+    if (kq + SOS_KB <= N3) slab_mma<NFR, LR, OWN, 4>(acc, tacc, a, v, b, bt, do_t, gq, tq);
     else {                                                     // tail of a direction block: k-steps of pure padding skipped
       const int ks_lim = max(0, (N3 - kq + 3) >> 2);
-      if (ks_lim == 3) slab_mma<NFR, LR, OWN, 3>(acc, tacc, a, v, b, wr, gq, tq);
-      else if (ks_lim == 2) slab_mma<NFR, LR, OWN, 2>(acc, tacc, a, v, b, wr, gq, tq);
-      else if (ks_lim == 1) slab_mma<NFR, LR, OWN, 1>(acc, tacc, a, v, b, wr, gq, tq);
-      else if (ks_lim >= 4) slab_mma<NFR, LR, OWN, 4>(acc, tacc, a, v, b, wr, gq, tq);
+      if (ks_lim == 3) slab_mma<NFR, LR, OWN, 3>(acc, tacc, a, v, b, bt, do_t, gq, tq);
+      else if (ks_lim == 2) slab_mma<NFR, LR, OWN, 2>(acc, tacc, a, v, b, bt, do_t, gq, tq);
+      else if (ks_lim == 1) slab_mma<NFR, LR, OWN, 1>(acc, tacc, a, v, b, bt, do_t, gq, tq);
+      else if (ks_lim >= 4) slab_mma<NFR, LR, OWN, 4>(acc, tacc, a, v, b, bt, do_t, gq, tq);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + st);
@@ -149,20 +152,16 @@ __device__ __forceinline__ void chunk_mma(double (&acc)[2][8][2], double (&tacc)
 }
 
 template <int LR, int OWN>
-__device__ __forceinline__ void chunk_dispatch(int nfr, double (&acc)[2][8][2], double (&tacc)[2], const unsigned char *sStage,
+__device__ __forceinline__ void chunk_dispatch(int live, double (&acc)[2][8][2], double (&tacc)[2], const unsigned char *sStage,
                                                unsigned long long *full, unsigned long long *empty, unsigned &q, int n_slab, int HB,
-                                               int N3, int wr, int lane, int gq, int tq)
+                                               int N3, int rg, int col0, int tcol, int lane, int gq, int tq)
 {
-  switch (nfr) {
-    case 8: chunk_mma<8, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
-    case 7: chunk_mma<7, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
-    case 6: chunk_mma<6, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
-    case 5: chunk_mma<5, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
-    case 4: chunk_mma<4, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
-    case 3: chunk_mma<3, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
-    case 2: chunk_mma<2, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
-    default: chunk_mma<1, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, wr, lane, gq, tq); break;
+#define SW_CASE(n) case n: chunk_mma<n, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, rg, col0, tcol, lane, gq, tq); break;
+  switch (live) {                                              // live 8-level column blocks of this warp in this chunk
+    SW_CASE(8) SW_CASE(7) SW_CASE(6) SW_CASE(5) SW_CASE(4) SW_CASE(3) SW_CASE(2) SW_CASE(1)
+    default: chunk_mma<0, LR, OWN>(acc, tacc, sStage, full, empty, q, n_slab, HB, N3, rg, col0, tcol, lane, gq, tq); break;
   }
+#undef SW_CASE
 }
 
 struct Unit {                                                  // decoded work unit (uniform per CTA), 64 bytes
@@ -198,7 +197,10 @@ __device__ __forceinline__ Unit decode_unit(int w, const ItemDev *items, const T
 
 }  // namespace
 
-__global__ void __launch_bounds__(SW_THREADS, 1)   // 13 warps are allocated as 16: 128 registers per thread
+// MW = number of DMMA warps: 8 (16 rows x 64 levels each) or 16 (16 rows x 32 levels each: warp w owns row group w & 7 and
+// column half w >> 3 of the 128 x 64 tile; twice the warps per scheduler to cover each other's stalls, 80 registers)
+template <int MW>
+__global__ void __launch_bounds__((MW + SW_EPI_WARPS + 1) * 32, 1)   // warps are allocated in fours: 13 -> 16 (128 regs), 21 -> 24 (80 regs)
 k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, const OpticsDev *__restrict__ optics,
         const KsetDev *__restrict__ ksets, const int *__restrict__ list, const int *__restrict__ count_ptr, int count_fixed,
         int tiles_per_dir, unsigned *__restrict__ work_counter, double *__restrict__ jdump, int dbg)
@@ -219,16 +221,16 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
 
   const int tid = threadIdx.x, lane = tid & 31, wr = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < SW_STG; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, SW_MMA_WARPS); }
-    mbar_init(acc_full, SW_MMA_WARPS); mbar_init(acc_empty, SW_EPI_WARPS);
+    for (int s = 0; s < SW_STG; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, MW); }
+    mbar_init(acc_full, MW); mbar_init(acc_empty, SW_EPI_WARPS);
     mbar_init(tab_full, 1); mbar_init(tab_empty, SW_EPI_WARPS);
-    for (int s = 0; s < 2; ++s) { mbar_init(work_full + s, 1); mbar_init(work_empty + s, SW_MMA_WARPS + SW_EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(work_full + s, 1); mbar_init(work_empty + s, MW + SW_EPI_WARPS); }
     fence_proxy_async();
   }
   __syncthreads();
   const int nwork = (count_ptr ? *count_ptr : count_fixed) * 2 * tiles_per_dir;
 
-  if (wr == SW_MMA_WARPS + SW_EPI_WARPS) {
+  if (wr == MW + SW_EPI_WARPS) {
     // =============================== producer warp ===============================
     if (lane != 0) return;
     unsigned q = 0, tabn = 0, wn = 0;
@@ -277,9 +279,11 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
     return;
   }
 
-  if (wr < SW_MMA_WARPS) {
+  if (wr < MW) {
     // =============================== MMA warps ===============================
+    constexpr int NFW = 64 / MW;                                // 8-level column blocks per warp
     const int gq = lane >> 2, tq = lane & 3;
+    const int rg = wr & 7, chh = wr >> 3;                       // row group, column half
     unsigned q = 0, accn = 0, wn = 0;
     double acc[2][8][2];
     double tacc[2];
@@ -292,23 +296,26 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
       ++wn;
       if (u.w < 0) break;
       if (!u.valid) continue;
-      const bool own = wr < u.ng;
+      const bool own = rg < u.ng;
       const bool up = (u.dir == 0);
       for (int chunk = 0; chunk < u.n_chunk; ++chunk) {
         const int ci = up ? (u.n_chunk - 1 - chunk) : chunk;
         const int c0 = ci * SOS_CH;
         const int nfr = (min(SOS_CH, u.L - c0) + 7) >> 3;
+        const int live = min(NFW, max(0, nfr - chh * NFW));      // live column blocks of this warp
+        const int col0 = chh * NFW * 8;
+        const int tcol = (u.lr && chh == 0 && rg < nfr) ? rg * 8 : -1;   // T = V X: column block rg, by the warps of half 0
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
           for (int ni = 0; ni < 8; ++ni) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
         tacc[0] = tacc[1] = 0.0;
         if (u.lr) {
-          if (own) chunk_dispatch<1, 1>(nfr, acc, tacc, sStage, full, empty, q, u.n_slab, u.HB, 3 * u.N, wr, lane, gq, tq);
-          else chunk_dispatch<1, 0>(nfr, acc, tacc, sStage, full, empty, q, u.n_slab, u.HB, 3 * u.N, wr, lane, gq, tq);
+          if (own) chunk_dispatch<1, 1>(live, acc, tacc, sStage, full, empty, q, u.n_slab, u.HB, 3 * u.N, rg, col0, tcol, lane, gq, tq);
+          else chunk_dispatch<1, 0>(live, acc, tacc, sStage, full, empty, q, u.n_slab, u.HB, 3 * u.N, rg, col0, tcol, lane, gq, tq);
         } else {
-          if (own) chunk_dispatch<0, 1>(nfr, acc, tacc, sStage, full, empty, q, u.n_slab, u.HB, 3 * u.N, wr, lane, gq, tq);
-          else chunk_dispatch<0, 0>(nfr, acc, tacc, sStage, full, empty, q, u.n_slab, u.HB, 3 * u.N, wr, lane, gq, tq);
+          if (own) chunk_dispatch<0, 1>(live, acc, tacc, sStage, full, empty, q, u.n_slab, u.HB, 3 * u.N, rg, col0, tcol, lane, gq, tq);
+          else chunk_dispatch<0, 0>(live, acc, tacc, sStage, full, empty, q, u.n_slab, u.HB, 3 * u.N, rg, col0, tcol, lane, gq, tq);
         }
         // ---- hand the raw accumulators to the recurrence warps ----
         if (accn >= 1) mbar_wait(acc_empty, (accn - 1) & 1);
@@ -316,12 +323,12 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
           double2 *sA2 = reinterpret_cast<double2 *>(sAcc);
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) {
-            const int row = wr * 16 + mi * 8 + gq;
+            const int row = rg * 16 + mi * 8 + gq;
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni) sA2[acc_slot(row, ni * 4 + tq)] = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+            for (int ni = 0; ni < NFW; ++ni) sA2[acc_slot(row, (chh * NFW + ni) * 4 + tq)] = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
           }
         }
-        if (u.lr && gq < 4 && wr < nfr) { sT[gq * SOS_CH + wr * 8 + 2 * tq] = tacc[0]; sT[gq * SOS_CH + wr * 8 + 2 * tq + 1] = tacc[1]; }
+        if (tcol >= 0 && gq < 4) { sT[gq * SOS_CH + tcol + 2 * tq] = tacc[0]; sT[gq * SOS_CH + tcol + 2 * tq + 1] = tacc[1]; }
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_full);
         ++accn;
@@ -332,7 +339,8 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
 
   // =============================== recurrence warps: one thread per tile row ===============================
   {
-    const int e = tid - SW_MMA_WARPS * 32;                       // tile row of this thread
+    constexpr int EB = (MW == 16) ? 4 : 8;                       // levels per block of the fused pass (register budget: 80 / 128)
+    const int e = tid - MW * 32;                                 // tile row of this thread
     unsigned accn = 0, wn = 0;
     while (true) {
       const int slot = wn & 1;
@@ -429,8 +437,8 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
           if (up) {
             // ---- from the ground upwards: levels top .. c0; level i uses layer i and S(i+1) ----
             int lv = top;
-            const int full_hi = jdump ? c0 - 1 : ((top == NT) ? (NT & ~7) - 1 : top);   // levels c0 .. full_hi: whole blocks of 8 below NT
-            for (; lv > full_hi; --lv) {                         // ragged head (at most 8 levels; holds level NT)
+            const int full_hi = jdump ? c0 - 1 : ((top == NT) ? (NT & ~(EB - 1)) - 1 : top);   // levels c0 .. full_hi: whole blocks below NT
+            for (; lv > full_hi; --lv) {                         // ragged head (at most EB levels; holds level NT)
               const int col = lv - c0;
               const double rw = raw(col);
               const double s = source(rw, col);
@@ -443,22 +451,22 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
             if (!u.lr) {
               // aerosol-only orders: c = pup*acc(i) + qup*acc(i+1), 3 FP64 instructions per level
               const double *__restrict__ pp = tm.pup + (kk - 1), *__restrict__ qp = tm.qup + (kk - 1);
-              for (; lv >= c0; lv -= 8) {
-                const int cb = lv - 7 - c0;
-                double R[9], aa[8], pw[8], qw[8];
+              for (; lv >= c0; lv -= EB) {                       // whole blocks of EB levels, lv = highest level of the block
+                const int cb = lv - (EB - 1) - c0;               // first column of the block
+                double R[EB + 1], aa[EB], pw[EB], qw[EB];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < EB; ++j) {
                   const size_t l = (size_t)(c0 + cb + j) * N;
                   aa[j] = attp[l]; pw[j] = pp[l]; qw[j] = qp[l];
                 }
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
+                for (int p = 0; p < EB / 2; ++p) {
                   const double2 t = sA2[acc_slot(e, (cb >> 1) + p)];
                   R[2 * p] = t.x; R[2 * p + 1] = t.y;
                 }
-                R[8] = redge;
+                R[EB] = redge;
 #pragma unroll
-                for (int p = 3; p >= 0; --p) {
+                for (int p = EB / 2 - 1; p >= 0; --p) {          // the new field replaces the accumulators pair by pair
                   const double zo = z * aa[2 * p + 1] + (pw[2 * p + 1] * R[2 * p + 1] + qw[2 * p + 1] * R[2 * p + 2]);
                   z = zo * aa[2 * p] + (pw[2 * p] * R[2 * p] + qw[2 * p] * R[2 * p + 1]);
                   sAw2[acc_slot(e, (cb >> 1) + p)] = make_double2(z, zo);
@@ -466,23 +474,23 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
                 redge = R[0];
               }
             } else
-            for (; lv >= c0; lv -= 8) {                          // whole blocks of 8 levels, lv = highest level of the block
-              const int cb = lv - 7 - c0;                        // first column of the block (multiple of 8)
-              double S[9], aa[8], gg[8], bb[8];
+            for (; lv >= c0; lv -= EB) {
+              const int cb = lv - (EB - 1) - c0;
+              double S[EB + 1], aa[EB], gg[EB], bb[EB];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < EB; ++j) {
                 const size_t l = (size_t)(c0 + cb + j) * N;
                 aa[j] = attp[l]; gg[j] = gp[l]; bb[j] = bp[l];
               }
 #pragma unroll
-              for (int p = 0; p < 4; ++p) {
+              for (int p = 0; p < EB / 2; ++p) {
                 const double2 t = sA2[acc_slot(e, (cb >> 1) + p)];
                 S[2 * p] = source(t.x, cb + 2 * p);
                 S[2 * p + 1] = source(t.y, cb + 2 * p + 1);
               }
-              S[8] = sedge;
+              S[EB] = sedge;
 #pragma unroll
-              for (int p = 3; p >= 0; --p) {                     // the new field replaces the accumulators pair by pair
+              for (int p = EB / 2 - 1; p >= 0; --p) {
                 const double zo = z * aa[2 * p + 1] + (bb[2 * p + 1] * S[2 * p + 1] + gg[2 * p + 1] * S[2 * p + 2]);
                 z = zo * aa[2 * p] + (bb[2 * p] * S[2 * p] + gg[2 * p] * S[2 * p + 1]);
                 sAw2[acc_slot(e, (cb >> 1) + p)] = make_double2(z, zo);
@@ -492,58 +500,58 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
           } else {
             // ---- from the top downwards: levels c0 .. top; level i uses layer i-1 and S(i-1) ----
             int lv = c0;
-            const int n_full = jdump ? 0 : ((top + 1 - c0) >> 3);  // whole blocks of 8 in this chunk
+            const int n_full = jdump ? 0 : ((top + 1 - c0) / EB);  // whole blocks of EB levels in this chunk
             if (!u.lr) {
               const double *__restrict__ pp = tm.pdn + (kk - 1), *__restrict__ qp = tm.qdn + (kk - 1);
-              for (int blk = 0; blk < n_full; ++blk, lv += 8) {
+              for (int blk = 0; blk < n_full; ++blk, lv += EB) {
                 const int cb = lv - c0;
-                double R[9], aa[8], pw[8], qw[8];
+                double R[EB + 1], aa[EB], pw[EB], qw[EB];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < EB; ++j) {
                   aa[j] = attp[(size_t)max(lv + j - 1, 0) * N];   // layer above level lv+j
                   const size_t l = (size_t)(lv + j) * N;
                   pw[j] = pp[l]; qw[j] = qp[l];                   // level-indexed (row 0 is zero: X(0) = 0)
                 }
                 R[0] = redge;
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
+                for (int p = 0; p < EB / 2; ++p) {
                   const double2 t = sA2[acc_slot(e, (cb >> 1) + p)];
                   R[2 * p + 1] = t.x; R[2 * p + 2] = t.y;
                 }
                 if (lv == 0) aa[0] = 0.0;
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
+                for (int p = 0; p < EB / 2; ++p) {
                   const double ze = z * aa[2 * p] + (pw[2 * p] * R[2 * p + 1] + qw[2 * p] * R[2 * p]);
                   z = ze * aa[2 * p + 1] + (pw[2 * p + 1] * R[2 * p + 2] + qw[2 * p + 1] * R[2 * p + 1]);
                   sAw2[acc_slot(e, (cb >> 1) + p)] = make_double2(ze, z);
                 }
-                redge = R[8];
-                sedge = sXd[cb + 7] * R[8];                       // the ragged tail of the profile continues with the generic form
+                redge = R[EB];
+                sedge = sXd[cb + EB - 1] * R[EB];                 // the ragged tail of the profile continues with the generic form
               }
             } else
-            for (int blk = 0; blk < n_full; ++blk, lv += 8) {
+            for (int blk = 0; blk < n_full; ++blk, lv += EB) {
               const int cb = lv - c0;
-              double S[9], aa[8], gg[8], bb[8];
+              double S[EB + 1], aa[EB], gg[EB], bb[EB];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < EB; ++j) {
                 const size_t l = (size_t)max(lv + j - 1, 0) * N;   // layer above level lv+j (level 0 has none: fixed below)
                 aa[j] = attp[l]; gg[j] = gp[l]; bb[j] = bp[l];
               }
               S[0] = sedge;
 #pragma unroll
-              for (int p = 0; p < 4; ++p) {
+              for (int p = 0; p < EB / 2; ++p) {
                 const double2 t = sA2[acc_slot(e, (cb >> 1) + p)];
                 S[2 * p + 1] = source(t.x, cb + 2 * p);
                 S[2 * p + 2] = source(t.y, cb + 2 * p + 1);
               }
               if (lv == 0) { aa[0] = 0.0; gg[0] = 0.0; bb[0] = 0.0; }   // level 0: X = 0
 #pragma unroll
-              for (int p = 0; p < 4; ++p) {
+              for (int p = 0; p < EB / 2; ++p) {
                 const double ze = z * aa[2 * p] + (bb[2 * p] * S[2 * p + 1] + gg[2 * p] * S[2 * p]);
                 z = ze * aa[2 * p + 1] + (bb[2 * p + 1] * S[2 * p + 2] + gg[2 * p + 1] * S[2 * p + 1]);
                 sAw2[acc_slot(e, (cb >> 1) + p)] = make_double2(ze, z);
               }
-              sedge = S[8];
+              sedge = S[EB];
             }
             for (; lv <= top; ++lv) {                            // ragged tail
               const int col = lv - c0;
@@ -605,11 +613,18 @@ extern "C" int sos_launch_sweep(const ItemDev *items, const TermDev *terms, cons
   const int groups = maxHB / 16;
   const int tiles_per_dir = (groups + SW_MMA_WARPS - 1) / SW_MMA_WARPS;
   const size_t smem = sweep_smem_bytes();
-  cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static const int mw = getenv("SOS_SWEEP_MW") ? atoi(getenv("SOS_SWEEP_MW")) : 8;   // A/B switch of the DMMA warp count
   cudaMemsetAsync(work_counter, 0, sizeof(unsigned), st);
   const long long units = (long long)nitem * 2 * tiles_per_dir;
   const int grid = (int)std::min<long long>(num_sms, units);
-  k_sweep<<<grid, SW_THREADS, smem, st>>>(items, terms, optics, ksets, list, count_ptr, nitem, tiles_per_dir, work_counter, jdump,
-                                             sweep_dbg());
+  if (mw == 16) {
+    cudaFuncSetAttribute(k_sweep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_sweep<16><<<grid, (16 + SW_EPI_WARPS + 1) * 32, smem, st>>>(items, terms, optics, ksets, list, count_ptr, nitem, tiles_per_dir, work_counter,
+                                                                 jdump, sweep_dbg());
+  } else {
+    cudaFuncSetAttribute(k_sweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_sweep<8><<<grid, (8 + SW_EPI_WARPS + 1) * 32, smem, st>>>(items, terms, optics, ksets, list, count_ptr, nitem, tiles_per_dir, work_counter,
+                                                               jdump, sweep_dbg());
+  }
   return 1;
 }

@@ -78,14 +78,14 @@ def roujean(ref, fm, tmp, N, rmu, ga, os_nb, k0, k1, k2):
     return ier.value, (fm.read_surface_bin(f, N) if ier.value == 0 else None)
 
 
-def surface_bpdf(ref, fm, tmp, isurf, N, rmu, ga, ind, os_nb, os_ns, os_nm):
+def surface_bpdf(ref, fm, tmp, isurf, N, rmu, ga, ind, os_nb, os_ns, os_nm, coef_c=0.0):
     """SOS_SURFACE_BPDF (SOS_SURFACE_BPDF.F:219) through its files -> REAL*4 records."""
     r, g = _angles(rmu, ga, N)
     f = os.path.join(tmp, "BPDF.bin")
     if os.path.exists(f):
         os.remove(f)
     ier = C.c_int(99)
-    ref.sos_surface_bpdf_(_ip(N), _P(r), _P(g), _dp(ind), _ip(isurf), _dp(0.0), _dp(0.0), _dp(0.0), _ip(os_nb), _ip(os_ns), _ip(os_nm),
+    ref.sos_surface_bpdf_(_ip(N), _P(r), _P(g), _dp(ind), _ip(isurf), _dp(0.0), _dp(0.0), _dp(coef_c), _ip(os_nb), _ip(os_ns), _ip(os_nm),
                           _fs(os.path.join(tmp, "B_GSF")), _fs(os.path.join(tmp, "B_FRESNEL")), _fs(os.path.join(tmp, "B_MAT_REFLEX")),
                           _fs(f), _ip(0), C.byref(ier), _L, _L, _L, _L)
     assert ier.value == 0, "reference SOS_SURFACE_BPDF IER=%d" % ier.value

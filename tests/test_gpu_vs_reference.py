@@ -205,10 +205,12 @@ def test_land_surface_files_roujean_breon(pkg, solver, ref, tmp_path):
     print("\n[roujean N=%d] REAL*4 records bit-identical: %.4f %%; orders with a non-zero coefficient: %d (reference %d)"
           % (N, 100 * same, nz, nz_ref))
     assert same > 0.995 and np.abs(rj - rj_ref).max() <= 2e-7 * np.abs(rj_ref).max()
-    for isurf in (4, 5):
-        b_ref = refdirect.surface_bpdf(ref, fm, str(tmp_path), isurf, N, rmu, ga, 1.5, os_nb, os_ns, os_nb + os_ns)
-        b = solver.surface_bpdf(isurf, N, rmu, ga, 1.5, os_nb, os_ns, os_nb + os_ns)
-        assert np.mean(b.view(np.uint32) == b_ref.view(np.uint32)) > 0.999, isurf
+    for isurf in (7, 4, 5):                                  # Maignan (C = 6), Rondeaux, Breon (the last one is used below)
+        b_ref = refdirect.surface_bpdf(ref, fm, str(tmp_path), isurf, N, rmu, ga, 1.5, os_nb, os_ns, os_nb + os_ns, coef_c=6.0)
+        b = solver.surface_bpdf(isurf, N, rmu, ga, 1.5, os_nb, os_ns, os_nb + os_ns, coef_c=6.0)
+        same_b = np.mean(b.view(np.uint32) == b_ref.view(np.uint32))
+        print("[BPDF isurf=%d] REAL*4 records bit-identical: %.4f %%" % (isurf, 100 * same_b))
+        assert same_b > 0.999, isurf
         assert np.abs(b - b_ref).max() <= 2e-7 * np.abs(b_ref).max()
     s_ref = refdirect.bpdf_ajout_brdf(ref, fm, str(tmp_path), b_ref, rj_ref)
     s_gpu = solver.bpdf_ajout_brdf(b, rj)
