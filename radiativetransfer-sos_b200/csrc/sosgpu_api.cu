@@ -15,17 +15,30 @@
 
 static inline int roundup(int x, int m) { return (x + m - 1) / m * m; }
 
-// host-side arena that is uploaded in one copy; offsets are turned into device pointers afterwards
+// host-side arena that is uploaded in one copy; offsets are turned into device pointers afterwards.  With a pinned backing
+// store (the context's staging buffer, sized up front) the upload is one true asynchronous DMA instead of a staged copy
+// of pageable memory, and nothing is reallocated while the arena is filled.
 struct Arena {
-  std::vector<char> buf;
+  std::vector<char> own;                                        // fallback storage (small single-routine calls)
+  char *base = nullptr; size_t cap = 0, used = 0;
+  Arena() {}
+  Arena(char *pinned, size_t capacity) : base(pinned), cap(capacity) {}
   size_t put(const void *p, size_t bytes)
   {
-    size_t off = (buf.size() + 15) / 16 * 16;
-    buf.resize(off + bytes);
-    if (p) memcpy(buf.data() + off, p, bytes); else memset(buf.data() + off, 0, bytes);
+    const size_t off = (used + 15) / 16 * 16;
+    if (!base || off + bytes > cap) {                            // grow the private vector (or switch to it)
+      if (base) { own.assign(base, base + used); base = nullptr; cap = 0; }
+      own.resize(off + bytes);
+    }
+    char *dst = (base ? base : own.data()) + off;
+    if (off > used) memset((base ? base : own.data()) + used, 0, off - used);
+    if (p) memcpy(dst, p, bytes); else memset(dst, 0, bytes);
+    used = off + bytes;
     return off;
   }
   template <class T> size_t putv(const std::vector<T> &v) { return put(v.data(), v.size() * sizeof(T)); }
+  const char *data() const { return base ? base : own.data(); }
+  size_t size() const { return used; }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -81,6 +94,7 @@ extern "C" void sosgpu_destroy(sosgpu_ctx *ctx)
   sosgpu_comm_destroy(ctx);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   if (ctx->h_count) cudaFreeHost(ctx->h_count);
+  if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   for (int k = 0; k < 8; ++k) if (ctx->ev_cnt[k]) cudaEventDestroy(ctx->ev_cnt[k]);
@@ -288,7 +302,21 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
 
   const auto t_up1 = std::chrono::steady_clock::now();
   // ---- constant arena ----
-  Arena ar;
+  // size of the arena: per optics the angle / coefficient vectors (+ surface records), per term seven level arrays
+  size_t need_bytes = 4096;
+  for (int i = 0; i < noptics; ++i) {
+    const HostOptics &h = b->ho[i];
+    need_bytes += (size_t)(2 * h.W + 4 * (h.os_nb + 1) + 3 * (h.N + 1)) * 8 + 10 * 16;
+    if (h.imat_surf == 1) need_bytes += (size_t)std::min(h.n_surf_rec, h.os_nb + 1) * 9 * h.N * h.N * sizeof(float) + 16;
+  }
+  for (int i = 0; i < nterm; ++i) need_bytes += (size_t)7 * ((b->ht[i].nt + 2) * 8 + 16);
+  if (need_bytes > ctx->h_arena_cap) {                           // pinned staging buffer of the context, grown on demand
+    if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
+    ctx->h_arena = nullptr; ctx->h_arena_cap = 0;
+    if (cudaMallocHost(&ctx->h_arena, need_bytes + need_bytes / 4) == cudaSuccess) ctx->h_arena_cap = need_bytes + need_bytes / 4;
+    else cudaGetLastError();                                     // no pinned memory: the arena falls back to pageable storage
+  }
+  Arena ar(ctx->h_arena, ctx->h_arena_cap);
   b->optics_dev.resize(noptics);
   std::vector<size_t> o_off(noptics * 10);
   for (int i = 0; i < noptics; ++i) {
@@ -316,8 +344,8 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     i4_off[i] = i4_total; i4_total += (size_t)12 * b->ho[h.optics].N;
   }
   b->i4_total = i4_total;
-  CK(sos_dmalloc(ctx, &b->d_arena, ar.buf.size()));
-  CK(cudaMemcpyAsync(b->d_arena, ar.buf.data(), ar.buf.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(sos_dmalloc(ctx, &b->d_arena, ar.size()));
+  CK(cudaMemcpyAsync(b->d_arena, ar.data(), ar.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(sos_dmalloc(ctx, &b->d_att, 7 * att_total * sizeof(double)));      // a, g, 1-a-g, pup, qup, pdn, qdn tables (k_att)
   CK(cudaMemsetAsync(b->d_att, 0, 7 * att_total * sizeof(double), ctx->stream));
   CK(sos_dmalloc(ctx, &b->d_i4, i4_total * sizeof(double)));
@@ -954,11 +982,11 @@ extern "C" int sosgpu_noyaux(sosgpu_ctx *ctx, int is, int nbmu, const double *rm
   const size_t nb_basis = (size_t)3 * (os_nb + 2) * W, nb_ker = (size_t)6 * W * W, nb_xpl = (size_t)3 * W;
   char *d = nullptr; double *dw = nullptr; OpticsDev *dop = nullptr; KsetDev *dks = nullptr;
   SosFreeGuard guard(ctx);                                       // releases the temporaries on every return path
-  CK(sos_dmalloc(ctx, &d, ar.buf.size())); guard.add(d);
+  CK(sos_dmalloc(ctx, &d, ar.size())); guard.add(d);
   CK(sos_dmalloc(ctx, &dw, (nb_basis + nb_ker + nb_xpl) * 8)); guard.add(dw);
   CK(sos_dmalloc(ctx, &dop, sizeof(OpticsDev))); guard.add(dop);
   CK(sos_dmalloc(ctx, &dks, sizeof(KsetDev))); guard.add(dks);
-  CK(cudaMemcpy(d, ar.buf.data(), ar.buf.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d, ar.data(), ar.size(), cudaMemcpyHostToDevice));
   CK(cudaMemset(dw, 0, (nb_basis + nb_ker + nb_xpl) * 8));
   OpticsDev op{};
   op.nbmu = N; op.W = W; op.HB = roundup(3 * N, 16); op.KP = 2 * op.HB; op.os_nb = os_nb;

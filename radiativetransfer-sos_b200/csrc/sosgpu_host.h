@@ -30,6 +30,7 @@ struct sosgpu_ctx {
   char *cache_field = nullptr; size_t cache_field_bytes = 0;   // wave pools parked by the last freed batch
   char *cache_kpool = nullptr; size_t cache_kpool_bytes = 0;
   double *grec_cache = nullptr; size_t grec_cache_bytes = 0;   // group-sum buffer parked by the last freed batch
+  char *h_arena = nullptr; size_t h_arena_cap = 0;     // pinned staging buffer of the batch uploads
   unsigned *d_work_counter = nullptr; int num_sms = 0;   // work queue of the persistent sweep kernel
   void *nccl_comm = nullptr; int nranks = 1, rank = 0;   // sosgpu_comm_init
   double *d_gather = nullptr; size_t gather_cap = 0; std::vector<double> h_gather;   // root side of sosgpu_batch_gather_tables
