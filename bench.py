@@ -32,9 +32,12 @@ POINTS_PER_GPU = int(os.environ.get("SOS_BENCH_POINTS", "96"))
 NB_GAUSS, OS_NB = 40, 80
 METRIC = "polarized SOS spectral solves/sec"
 # DRAM traffic of one full-width launch of the hot kernel on this workload, from the ncu --set full capture under profiles/
-NCU_TRAFFIC_BYTES = 4.157373e9 + 2.000106e9
-NCU_TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one full-width launch from the committed ncu capture "
-                      "under profiles/ (not measured live)")
+NCU_TRAFFIC_BYTES = 5.900181e9 + 3.017455e9
+NCU_TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one full-width k_sweep launch (148 persistent CTAs, 4 960 "
+                      "items, 6.3 ms under ncu) from the committed round-2 capture profiles/r2_ksweep_ncu_full_summary.txt; not "
+                      "measured live.  The field itself is 16 B per element and launch (read + write); the rest are the "
+                      "per-(layer, angle) weight tables (3 x 8 B per element) and the second read of the field by the other "
+                      "direction's work unit")
 UNIT = "spectral points/s"
 
 

@@ -32,13 +32,15 @@ k_order1(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, c
   const bool fres = (op.ifresnel == 1);
   double *__restrict__ xo = it.x[1];
   const double *__restrict__ attp = tm.att + (kk - 1);
-  const double *__restrict__ chp = tm.ch, *__restrict__ cfp = tm.cf, *__restrict__ xdp = tm.xdel, *__restrict__ ydp = tm.ydel;
-  const double *__restrict__ dtp = tm.dt, *__restrict__ ivp = tm.inv;
-  // source function of level lv (SOS_OS.F:2553-2560 and :3224-3292)
+  const double *__restrict__ gp = tm.gco + (kk - 1), *__restrict__ bp = tm.bco + (kk - 1);
+  const double *__restrict__ sxd = tm.sxd, *__restrict__ syd = tm.syd, *__restrict__ cfp = tm.cf;
+  const double *__restrict__ xdp = tm.xdel, *__restrict__ ydp = tm.ydel;
+  // Source function of level lv (SOS_OS.F:2553-2560 and :3224-3292): CH*(S2*XDEL + S1*YDEL) with CH*XDEL, CH*YDEL tabulated
+  // per level (k_beam); vector FP64 is the scarce resource of this kernel (about 1/8 of the DMMA rate on B200), so the
+  // source costs 2 instructions per level and the layer update 3 (tables of k_att, as in k_sweep).
   auto source = [&](int lv) -> double {
-    const double xdv = xdp[lv], ydv = ydp[lv];
-    double v = __dmul_rn(chp[lv], __dadd_rn(__dmul_rn(c2, xdv), __dmul_rn(c1, ydv)));
-    if (fres && (up ? (lv <= NT - 1) : (lv >= 1))) v = v + cfp[lv] * (fz2 * xdv + fz1 * ydv);
+    double v = c2 * sxd[lv] + c1 * syd[lv];
+    if (fres && (up ? (lv <= NT - 1) : (lv >= 1))) v = v + cfp[lv] * (fz2 * xdp[lv] + fz1 * ydp[lv]);
     return v;
   };
   double bc = 0.0;                                               // SOS_OS.F:970-992
@@ -52,7 +54,6 @@ k_order1(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, c
       bc = (so == 0) ? bc + rv * rr : rv * rr;
     }
   }
-  const double rmuk = -mu;
   double z = 0.0, sedge = 0.0;
   double *trow = tile + tid * O1_PITCH;
   const int nblk = (NT + 16) >> 4;                               // blocks of 16 levels covering 0..NT
@@ -65,20 +66,16 @@ k_order1(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, c
         double *tg = trow + (b0 - b16);
         if (up) {
           if (b0 + 7 < NT) {                                     // whole group below the ground level
-            double S[9], cst[8], aa[8], o[8];
+            double S[9], o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) S[j] = source(b0 + j);
             S[8] = sedge;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int l = b0 + j;
-              const double a = attp[(size_t)l * N], dl = dtp[l], iv = ivp[l];
-              const double A = (S[j + 1] - S[j]) * iv;
-              cst[j] = (1.0 - a) * (A * mu + S[j]) - A * (a * dl);
-              aa[j] = a;
+            for (int j = 7; j >= 0; --j) {
+              const size_t l = (size_t)(b0 + j) * N;
+              z = z * attp[l] + (bp[l] * S[j] + gp[l] * S[j + 1]);
+              o[j] = z;
             }
-#pragma unroll
-            for (int j = 7; j >= 0; --j) { z = z * aa[j] + cst[j]; o[j] = z; }
             sedge = S[0];
 #pragma unroll
             for (int p = 0; p < 4; ++p) *reinterpret_cast<double2 *>(tg + 2 * p) = make_double2(o[2 * p], o[2 * p + 1]);
@@ -86,32 +83,24 @@ k_order1(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, c
             for (int lv = min(b0 + 7, NT); lv >= b0; --lv) {      // the group that holds level NT
               const double s = source(lv);
               if (lv == NT) z = bc;
-              else {
-                const double a = attp[(size_t)lv * N], dl = dtp[lv], iv = ivp[lv];
-                const double A = (sedge - s) * iv;
-                z = z * a + ((1.0 - a) * (A * mu + s) - A * (a * dl));
-              }
+              else z = z * attp[(size_t)lv * N] + (bp[(size_t)lv * N] * s + gp[(size_t)lv * N] * sedge);
               sedge = s;
               tg[lv - b0] = z;
             }
           }
         } else {
           if (b0 + 7 <= NT) {
-            double S[9], cst[8], aa[8], o[8];
+            double S[9], o[8];
             S[0] = sedge;
 #pragma unroll
             for (int j = 0; j < 8; ++j) S[j + 1] = source(b0 + j);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int l = max(b0 + j - 1, 0);
-              const double a = attp[(size_t)l * N], dl = dtp[l], iv = ivp[l];
-              const double A = (S[j + 1] - S[j]) * iv;
-              cst[j] = (1.0 - a) * (A * rmuk + S[j + 1]) + A * (a * dl);
-              aa[j] = a;
+              const size_t l = (size_t)max(b0 + j - 1, 0) * N;
+              z = z * attp[l] + (bp[l] * S[j + 1] + gp[l] * S[j]);
+              if (b0 + j == 0) z = 0.0;                           // level 0: X = 0
+              o[j] = z;
             }
-            if (b0 == 0) { cst[0] = 0.0; aa[0] = 0.0; }           // level 0: X = 0
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { z = z * aa[j] + cst[j]; o[j] = z; }
             sedge = S[8];
 #pragma unroll
             for (int p = 0; p < 4; ++p) *reinterpret_cast<double2 *>(tg + 2 * p) = make_double2(o[2 * p], o[2 * p + 1]);
@@ -120,9 +109,8 @@ k_order1(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, c
               const double s = source(lv);
               if (lv == 0) z = 0.0;
               else {
-                const double a = attp[(size_t)(lv - 1) * N], dl = dtp[lv - 1], iv = ivp[lv - 1];
-                const double A = (s - sedge) * iv;
-                z = z * a + ((1.0 - a) * (A * rmuk + s) + A * (a * dl));
+                const size_t l = (size_t)(lv - 1) * N;
+                z = z * attp[l] + (bp[l] * s + gp[l] * sedge);
               }
               sedge = s;
               tg[lv - b0] = z;

@@ -129,6 +129,13 @@ __global__ void k_trphi(const TrphiGroup *groups, const double *phis, int nphi, 
   const double pi = prm.pi;
   if (nout < 0) nout = N;
   if (g.nrec <= 0) return;
+  // cos(s*phi), sin(s*phi) depend on (order, azimuth) only: computed once per CTA, not once per direction
+  __shared__ double s_cos[SOSGPU_NB_MAX_DEV + 1], s_sin[SOSGPU_NB_MAX_DEV + 1];
+  for (int is = threadIdx.x; is < g.nrec && is <= SOSGPU_NB_MAX_DEV; is += blockDim.x) {
+    const double xphi = is * phi;
+    s_cos[is] = cos(xphi); s_sin[is] = sin(xphi);
+  }
+  __syncthreads();
   for (int t = threadIdx.x; t < 2 * N; t += blockDim.x) {
     const int j = (t < N) ? (t + 1) : -(t - N + 1);
     const double rmuj = g.rmu[j + N];
@@ -140,10 +147,9 @@ __global__ void k_trphi(const TrphiGroup *groups, const double *phis, int nphi, 
       xq = g.rec[j + N]; xu = g.rec[W + j + N]; xi = g.rec[2 * W + j + N];
       for (int is = 1; is < g.nrec; ++is) {
         const double *r = g.rec + (size_t)is * 3 * W;
-        const double xphi = is * phi;
-        xq = xq + 2.0 * r[j + N] * cos(xphi);
-        xu = xu + 2.0 * r[W + j + N] * sin(xphi);
-        xi = xi + 2.0 * r[2 * W + j + N] * cos(xphi);
+        xq = xq + 2.0 * r[j + N] * s_cos[is];
+        xu = xu + 2.0 * r[W + j + N] * s_sin[is];
+        xi = xi + 2.0 * r[2 * W + j + N] * s_cos[is];
       }
     }
     if (prm.igli == 1 && j > 0) {                              // :946-1001

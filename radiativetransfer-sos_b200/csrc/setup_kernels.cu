@@ -330,8 +330,11 @@ __global__ void k_beam(const TermDev *terms, const OpticsDev *optics)
   const OpticsDev &op = optics[tm.optics];
   const double coefnt = exp(2.0 * tm.h[tm.nt] / op.tab) / 4.0;
   for (int i = threadIdx.x; i <= tm.nt; i += blockDim.x) {
-    const_cast<double *>(tm.ch)[i] = exp(-tm.h[i] / (-op.tab)) / 4.0;
+    const double ch = exp(-tm.h[i] / (-op.tab)) / 4.0;
+    const_cast<double *>(tm.ch)[i] = ch;
     const_cast<double *>(tm.cf)[i] = coefnt * exp(-tm.h[i] / op.tab);
+    const_cast<double *>(tm.sxd)[i] = ch * tm.xdel[i];          // order-1 source = c2(row)*sxd + c1(row)*syd (SOS_OS.F:2553-2560)
+    const_cast<double *>(tm.syd)[i] = ch * tm.ydel[i];
   }
 }
 

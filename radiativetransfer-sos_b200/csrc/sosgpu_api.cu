@@ -333,7 +333,8 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
   }
   std::vector<size_t> t_off(nterm * 7);
   size_t att_total = 0, i4_total = 0;
-  std::vector<size_t> att_off(nterm), i4_off(nterm);
+  std::vector<size_t> att_off(nterm), i4_off(nterm), lvl_off(nterm);
+  size_t lvl_total = 0;
   for (int i = 0; i < nterm; ++i) {
     HostTerm &h = b->ht[i];
     size_t *o = &t_off[i * 7];
@@ -342,12 +343,14 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     // 16-byte aligned; rows >= nt up to the end of the last 64-level chunk (+2) stay zero: k_step2 reads them as a = 0
     att_off[i] = att_total; att_total += (((size_t)(roundup(h.nt + 1, SOS_CH) + 2) * b->ho[h.optics].N + 1) & ~(size_t)1);
     i4_off[i] = i4_total; i4_total += (size_t)12 * b->ho[h.optics].N;
+    lvl_off[i] = lvl_total; lvl_total += (size_t)((h.nt + 2 + 1) & ~1);
   }
   b->i4_total = i4_total;
   CK(sos_dmalloc(ctx, &b->d_arena, ar.size()));
   CK(cudaMemcpyAsync(b->d_arena, ar.data(), ar.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CK(sos_dmalloc(ctx, &b->d_att, 7 * att_total * sizeof(double)));      // a, g, 1-a-g, pup, qup, pdn, qdn tables (k_att)
-  CK(cudaMemsetAsync(b->d_att, 0, 7 * att_total * sizeof(double), ctx->stream));
+  // a, g, 1-a-g, pup, qup, pdn, qdn tables (k_att) + the two level tables of the order-1 source (k_beam)
+  CK(sos_dmalloc(ctx, &b->d_att, (7 * att_total + 2 * lvl_total) * sizeof(double)));
+  CK(cudaMemsetAsync(b->d_att, 0, (7 * att_total + 2 * lvl_total) * sizeof(double), ctx->stream));
   CK(sos_dmalloc(ctx, &b->d_i4, i4_total * sizeof(double)));
   for (int i = 0; i < noptics; ++i) {
     HostOptics &h = b->ho[i];
@@ -381,6 +384,7 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     d.bco = b->d_att + 2 * att_total + att_off[i];
     d.pup = b->d_att + 3 * att_total + att_off[i]; d.qup = b->d_att + 4 * att_total + att_off[i];
     d.pdn = b->d_att + 5 * att_total + att_off[i]; d.qdn = b->d_att + 6 * att_total + att_off[i];
+    d.sxd = b->d_att + 7 * att_total + lvl_off[i]; d.syd = b->d_att + 7 * att_total + lvl_total + lvl_off[i];
     d.i4 = b->d_i4 + i4_off[i];
   }
   CK(sos_dmalloc(ctx, &b->d_optics, noptics * sizeof(OpticsDev)));
@@ -690,6 +694,7 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
       CK(cudaEventRecord(e0, st));
       const int nl = sos_launch_sweep(b->d_items, b->d_terms, b->d_optics, b->d_ksets, list_cur, count_cur, ub, b->maxHB,
                                       ctx->d_work_counter, ctx->num_sms, jdump_dev, st);
+      if (nl < 0) { ctx->err = "k_sweep: cannot opt in to its shared-memory size on this device"; return SOSGPU_ERR_CUDA; }
       CK(cudaEventRecord(e1, st));
       sos_launch_test(b->d_items, b->d_terms, b->d_optics, list_cur, count_cur, ub, b->d_list[cur ^ 1], b->d_count + (cur ^ 1), st);
       ctx->launches += nl + 1;

@@ -44,6 +44,7 @@ struct TermDev {              // one per (wavelength, CKD term)
   const double *cf;                   // [nt+1] flat-sea source attenuation (SOS_OS.F:3219,3278) or null
   const double *att;                  // [nt][N] a = exp(-dt/mu_k)
   const double *gco, *bco;            // [nt][N] layer-integration weights g = (1-a)*mu/dt - a and 1 - a - g (k_att)
+  const double *sxd, *syd;            // [nt+1] CH*XDEL, CH*YDEL: the order-1 source is c2*sxd + c1*syd (k_beam)
   const double *pup, *qup, *pdn, *qdn;   // [nt+1][N] the same weights times XDEL of the two levels, per sweep direction (k_att)
   double *i4;                         // [6][2N] running Fourier sums I4,Q4,U4,I5,Q5,U5 (component order below)
 };

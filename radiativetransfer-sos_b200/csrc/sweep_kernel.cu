@@ -30,7 +30,6 @@
 #include <math.h>
 #include <algorithm>
 #include <cstdio>
-#include <cstdlib>
 
 #define SW_STG 4                       // operand pipeline stages
 #define SW_MMA_WARPS 8
@@ -197,13 +196,13 @@ __device__ __forceinline__ Unit decode_unit(int w, const ItemDev *items, const T
 
 }  // namespace
 
-// MW = number of DMMA warps: 8 (16 rows x 64 levels each) or 16 (16 rows x 32 levels each: warp w owns row group w & 7 and
-// column half w >> 3 of the 128 x 64 tile; twice the warps per scheduler to cover each other's stalls, 80 registers)
+// MW = number of DMMA warps: 8 (16 rows x 64 levels each, the shipped instantiation) or 16 (16 rows x 32 levels each: warp w
+// owns row group w & 7 and column half w >> 3 of the 128 x 64 tile; measured slower, not instantiated)
 template <int MW>
 __global__ void __launch_bounds__((MW + SW_EPI_WARPS + 1) * 32, 1)   // warps are allocated in fours: 13 -> 16 (128 regs), 21 -> 24 (80 regs)
 k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, const OpticsDev *__restrict__ optics,
         const KsetDev *__restrict__ ksets, const int *__restrict__ list, const int *__restrict__ count_ptr, int count_fixed,
-        int tiles_per_dir, unsigned *__restrict__ work_counter, double *__restrict__ jdump, int dbg)
+        int tiles_per_dir, unsigned *__restrict__ work_counter, double *__restrict__ jdump)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // ---- shared memory carve ----
@@ -319,7 +318,7 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
         }
         // ---- hand the raw accumulators to the recurrence warps ----
         if (accn >= 1) mbar_wait(acc_empty, (accn - 1) & 1);
-        if (own && !(dbg & 2)) {
+        if (own) {
           double2 *sA2 = reinterpret_cast<double2 *>(sAcc);
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) {
@@ -413,7 +412,7 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
         const int c0 = ci * SOS_CH;
         mbar_wait(tab_full, accn & 1);
         mbar_wait(acc_full, accn & 1);
-        if (rowvalid && !(dbg & 1)) {
+        if (rowvalid) {
           // Layer l of this row: a = exp(-dtau/mu), g = (1-a)*mu/dtau - a, b = 1 - a - g (tables of k_att, coalesced over the
           // rows of a warp).  With S the source function at the two levels of a layer, SOS_INTEGR_EPOPT's update
           //   z <- z*a + (1-a)*(A*mu + S_i) -/+ A*a*dtau,  A = dS/dtau   (SOS_OS.F:2288-2309, 2332-2353)
@@ -591,12 +590,6 @@ k_sweep(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, co
   }
 }
 
-static int sweep_dbg()
-{
-  static const int v = getenv("SOS_SWEEP_DBG") ? atoi(getenv("SOS_SWEEP_DBG")) : 0;   // timing experiments only (results invalid)
-  return v;
-}
-
 static size_t sweep_smem_bytes()
 {
   return (size_t)SW_STG * SW_STAGE + (size_t)128 * SW_ACC_PITCH * 8 + (4 * SOS_CH + 2 * 72 + 3 * 80) * 8 + (2 * SW_STG + 24) * 8 +
@@ -613,18 +606,19 @@ extern "C" int sos_launch_sweep(const ItemDev *items, const TermDev *terms, cons
   const int groups = maxHB / 16;
   const int tiles_per_dir = (groups + SW_MMA_WARPS - 1) / SW_MMA_WARPS;
   const size_t smem = sweep_smem_bytes();
-  static const int mw = getenv("SOS_SWEEP_MW") ? atoi(getenv("SOS_SWEEP_MW")) : 8;   // A/B switch of the DMMA warp count
   cudaMemsetAsync(work_counter, 0, sizeof(unsigned), st);
   const long long units = (long long)nitem * 2 * tiles_per_dir;
   const int grid = (int)std::min<long long>(num_sms, units);
-  if (mw == 16) {
-    cudaFuncSetAttribute(k_sweep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_sweep<16><<<grid, (16 + SW_EPI_WARPS + 1) * 32, smem, st>>>(items, terms, optics, ksets, list, count_ptr, nitem, tiles_per_dir, work_counter,
-                                                                 jdump, sweep_dbg());
-  } else {
-    cudaFuncSetAttribute(k_sweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_sweep<8><<<grid, (8 + SW_EPI_WARPS + 1) * 32, smem, st>>>(items, terms, optics, ksets, list, count_ptr, nitem, tiles_per_dir, work_counter,
-                                                               jdump, sweep_dbg());
+  // 8 DMMA warps.  (A 16-warp instantiation, 16 rows x 32 levels per warp, was measured at 20.5 TFLOP/s against 28.0: the A
+  // fragments are then loaded by twice as many warps and the register budget drops to 80.)
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {                  // the opt-in to > 48 KB dynamic shared memory is per device
+    if (cudaFuncSetAttribute(k_sweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    attr_set[dev] = true;
   }
+  k_sweep<8><<<grid, (8 + SW_EPI_WARPS + 1) * 32, smem, st>>>(items, terms, optics, ksets, list, count_ptr, nitem, tiles_per_dir, work_counter,
+                                                             jdump);
   return 1;
 }

@@ -18,7 +18,7 @@ N = (rmu.size - 1) // 2
 for rep in range(3):
     t0 = time.perf_counter()
     surf, il = s.glitter(N, rmu, ga, 2.0, 1.34, 80, 80, 160)
-    print("glitter N=%d OS_NB=80 OS_NS=80 OS_NM=160: call %.2f ms (H2D, host SOS_MAT_FRESNEL, kernel, D2H of %.1f MB), "
+    print("glitter N=%d OS_NB=80 OS_NS=80 OS_NM=160: call %.2f ms (H2D, k_mat_fresnel + E15.8 round trip, kernel, D2H of %.1f MB), "
           "k_glitter %.3f ms, mean IL %.1f" % (N, (time.perf_counter() - t0) * 1e3, surf.nbytes / 1e6, s.last_kernel_ms, il.mean()))
 if "--cpu" in sys.argv:
     from oracle import oracle as orc
