@@ -66,14 +66,18 @@ k_order1(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, c
         double *tg = trow + (b0 - b16);
         if (up) {
           if (b0 + 7 < NT) {                                     // whole group below the ground level
-            double S[9], o[8];
+            double S[9], o[8], aa[8], bb[8], gg[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {                         // all table loads of the group in flight before any use
+              const size_t l = (size_t)(b0 + j) * N;
+              aa[j] = attp[l]; bb[j] = bp[l]; gg[j] = gp[l];
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) S[j] = source(b0 + j);
             S[8] = sedge;
 #pragma unroll
             for (int j = 7; j >= 0; --j) {
-              const size_t l = (size_t)(b0 + j) * N;
-              z = z * attp[l] + (bp[l] * S[j] + gp[l] * S[j + 1]);
+              z = z * aa[j] + (bb[j] * S[j] + gg[j] * S[j + 1]);
               o[j] = z;
             }
             sedge = S[0];
@@ -90,14 +94,18 @@ k_order1(const ItemDev *__restrict__ items, const TermDev *__restrict__ terms, c
           }
         } else {
           if (b0 + 7 <= NT) {
-            double S[9], o[8];
+            double S[9], o[8], aa[8], bb[8], gg[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const size_t l = (size_t)max(b0 + j - 1, 0) * N;
+              aa[j] = attp[l]; bb[j] = bp[l]; gg[j] = gp[l];
+            }
             S[0] = sedge;
 #pragma unroll
             for (int j = 0; j < 8; ++j) S[j + 1] = source(b0 + j);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const size_t l = (size_t)max(b0 + j - 1, 0) * N;
-              z = z * attp[l] + (bp[l] * S[j + 1] + gp[l] * S[j]);
+              z = z * aa[j] + (bb[j] * S[j + 1] + gg[j] * S[j]);
               if (b0 + j == 0) z = 0.0;                           // level 0: X = 0
               o[j] = z;
             }

@@ -653,17 +653,21 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
       CK(cudaStreamSynchronize(st));                             // iota / items are stack-lifetime host buffers
     }
 
+    cudaEvent_t ph[5] = {};
+    if (ctx->trace) { for (auto &e : ph) cudaEventCreate(&e); cudaEventRecord(ph[0], st); }
     // ---- kernel matrices of the wave ----
     sos_launch_basis(b->d_ksets, b->d_optics, (int)nk, st);
     sos_launch_kernels(b->d_ksets, b->d_optics, (int)nk, b->maxW, st);
     sos_launch_pack(b->d_ksets, b->d_optics, (int)nk, b->maxKP, st);
     ctx->launches += 3;
+    if (ctx->trace) cudaEventRecord(ph[1], st);
     // ---- order 1 ----
     ctx->launches += sos_launch_order1(b->d_items, b->d_terms, b->d_optics, b->d_ksets, (int)nitem, b->maxKP, st);
     sos_launch_init(b->d_items, b->d_terms, b->d_optics, (int)nitem, st);
     ctx->launches += 1;
     CK(cudaGetLastError());
 
+    if (ctx->trace) cudaEventRecord(ph[2], st);
     // ---- scattering orders ----
     // The loop never waits for the GPU: the sweep kernel and k_test read the number of still-active items from device
     // memory; the host only follows it with a lag of SOS_LAG orders (pinned counters + events) to shrink k_test's grid
@@ -712,6 +716,7 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
       if (ctx->trace) fprintf(stderr, "wave s0=%d ws=%d ig=%d step_ms=%.3f\n", s0, ws, order_ev[k], ms);
     }
 
+    if (ctx->trace) cudaEventRecord(ph[3], st);
     // ---- per-order bookkeeping and Fourier stop, in order ----
     sos_launch_fourier(b->d_items, b->d_terms, b->d_optics, nterm, b->d_item_of, s0, s1, b->rs_dev, b->w_dev, b->d_rec,
                        b->d_nf, b->d_nsc, b->d_rsn, b->d_emoins, b->d_eplus, b->d_done, st);
@@ -720,6 +725,14 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     CK(cudaMemcpyAsync(items.data(), b->d_items, nitem * sizeof(ItemDev), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    if (ctx->trace) {
+      cudaEventRecord(ph[4], st); cudaEventSynchronize(ph[4]);
+      float m[4];
+      for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&m[k], ph[k], ph[k + 1]);
+      fprintf(stderr, "wave s0=%d ws=%d items=%zu ksets=%zu: setup kernels %.3f ms, order 1 + init %.3f ms, orders >= 2 %.3f ms, fourier + readback %.3f ms\n",
+              s0, ws, nitem, nk, m[0], m[1], m[2], m[3]);
+      for (auto &e : ph) cudaEventDestroy(e);
+    }
     for (size_t i = 0; i < nitem; ++i) {
       const HostTerm &ht = b->ht[items[i].term];
       const HostOptics &ho = b->ho[ht.optics];
