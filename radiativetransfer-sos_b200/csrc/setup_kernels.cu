@@ -320,6 +320,13 @@ __global__ void k_att(const TermDev *terms, const OpticsDev *optics)
   const_cast<double *>(tm.qup)[up_i] = g * xd_hi;
   const_cast<double *>(tm.pdn)[dn_i] = b * xd_hi;
   const_cast<double *>(tm.qdn)[dn_i] = g * xd_lo;
+  // First scattering order (k_order1): the source c2(row)*sx + c1(row)*sy of the two levels folded with b and g (k_beam ran before).
+  const double sx_lo = tm.sxd[layer], sx_hi = tm.sxd[layer + 1], sy_lo = tm.syd[layer], sy_hi = tm.syd[layer + 1];
+  const_cast<double *>(tm.o1u2)[up_i] = b * sx_lo + g * sx_hi;
+  const_cast<double *>(tm.o1u1)[up_i] = b * sy_lo + g * sy_hi;
+  const_cast<double *>(tm.adn)[dn_i] = a;
+  const_cast<double *>(tm.o1d2)[dn_i] = b * sx_hi + g * sx_lo;
+  const_cast<double *>(tm.o1d1)[dn_i] = b * sy_hi + g * sy_lo;
 }
 
 // Per-level attenuation of the direct solar beam: CH(i) = exp(-H(i)/mu_s)/4 (SOS_OS.F:837-839) and, for a flat sea, the beam
@@ -601,8 +608,8 @@ void sos_launch_att(const TermDev *terms, const OpticsDev *optics, int nterm, in
 {
   if (nterm <= 0) return;
   dim3 grid((max_elems + 127) / 128, nterm);
+  k_beam<<<nterm, 128, 0, st>>>(terms, optics);                 // k_att reads its sxd / syd
   k_att<<<grid, 128, 0, st>>>(terms, optics);
-  k_beam<<<nterm, 128, 0, st>>>(terms, optics);
 }
 void sos_launch_init(ItemDev *items, const TermDev *terms, const OpticsDev *optics, int nitem, cudaStream_t st)
 {

@@ -285,6 +285,7 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     if (rc != SOSGPU_OK) { ctx->err = "invalid optics entry"; return rc; }
     b->maxHB = std::max(b->maxHB, b->ho[i].HB); b->maxW = std::max(b->maxW, b->ho[i].W);
     b->maxKP = std::max(b->maxKP, b->ho[i].KP); b->maxNB = std::max(b->maxNB, b->ho[i].os_nb);
+    if (b->ho[i].ifresnel == 1) b->any_fresnel = 1;
   }
   int max_att = 0;
   for (int i = 0; i < nterm; ++i) {
@@ -348,9 +349,9 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
   b->i4_total = i4_total;
   CK(sos_dmalloc(ctx, &b->d_arena, ar.size()));
   CK(cudaMemcpyAsync(b->d_arena, ar.data(), ar.size(), cudaMemcpyHostToDevice, ctx->stream));
-  // a, g, 1-a-g, pup, qup, pdn, qdn tables (k_att) + the two level tables of the order-1 source (k_beam)
-  CK(sos_dmalloc(ctx, &b->d_att, (7 * att_total + 2 * lvl_total) * sizeof(double)));
-  CK(cudaMemsetAsync(b->d_att, 0, (7 * att_total + 2 * lvl_total) * sizeof(double), ctx->stream));
+  // a, g, 1-a-g, pup, qup, pdn, qdn and the five first-order tables (k_att) + the two level tables of the order-1 source (k_beam)
+  CK(sos_dmalloc(ctx, &b->d_att, (12 * att_total + 2 * lvl_total) * sizeof(double)));
+  CK(cudaMemsetAsync(b->d_att, 0, (12 * att_total + 2 * lvl_total) * sizeof(double), ctx->stream));
   CK(sos_dmalloc(ctx, &b->d_i4, i4_total * sizeof(double)));
   for (int i = 0; i < noptics; ++i) {
     HostOptics &h = b->ho[i];
@@ -384,7 +385,10 @@ static int upload_impl(sosgpu_ctx *ctx, const sosgpu_optics *optics, int noptics
     d.bco = b->d_att + 2 * att_total + att_off[i];
     d.pup = b->d_att + 3 * att_total + att_off[i]; d.qup = b->d_att + 4 * att_total + att_off[i];
     d.pdn = b->d_att + 5 * att_total + att_off[i]; d.qdn = b->d_att + 6 * att_total + att_off[i];
-    d.sxd = b->d_att + 7 * att_total + lvl_off[i]; d.syd = b->d_att + 7 * att_total + lvl_total + lvl_off[i];
+    d.o1u1 = b->d_att + 7 * att_total + att_off[i]; d.o1u2 = b->d_att + 8 * att_total + att_off[i];
+    d.adn = b->d_att + 9 * att_total + att_off[i];
+    d.o1d1 = b->d_att + 10 * att_total + att_off[i]; d.o1d2 = b->d_att + 11 * att_total + att_off[i];
+    d.sxd = b->d_att + 12 * att_total + lvl_off[i]; d.syd = b->d_att + 12 * att_total + lvl_total + lvl_off[i];
     d.i4 = b->d_i4 + i4_off[i];
   }
   CK(sos_dmalloc(ctx, &b->d_optics, noptics * sizeof(OpticsDev)));
@@ -662,7 +666,12 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
     ctx->launches += 3;
     if (ctx->trace) cudaEventRecord(ph[1], st);
     // ---- order 1 ----
-    ctx->launches += sos_launch_order1(b->d_items, b->d_terms, b->d_optics, b->d_ksets, (int)nitem, b->maxKP, st);
+    {
+      const int nl = sos_launch_order1(b->d_items, b->d_terms, b->d_optics, b->d_ksets, (int)nitem, b->maxKP, (b->maxW - 1) / 2,
+                                       b->any_fresnel, st);
+      if (nl < 0) { ctx->err = "order-1 kernel launch failed"; return SOSGPU_ERR_CUDA; }
+      ctx->launches += nl;
+    }
     sos_launch_init(b->d_items, b->d_terms, b->d_optics, (int)nitem, st);
     ctx->launches += 1;
     CK(cudaGetLastError());

@@ -75,7 +75,7 @@ struct sosgpu_batch {
   std::vector<HostOptics> ho;
   std::vector<HostTerm> ht;
   int nterm = 0, noptics = 0, ngroup = 0;
-  int rs_dev = 0, w_dev = 0, maxHB = 0, maxW = 0, maxKP = 0, maxNB = 0, smax = 0;
+  int rs_dev = 0, w_dev = 0, maxHB = 0, maxW = 0, maxKP = 0, maxNB = 0, smax = 0, any_fresnel = 0;
   char *d_arena = nullptr;
   OpticsDev *d_optics = nullptr;
   TermDev *d_terms = nullptr;

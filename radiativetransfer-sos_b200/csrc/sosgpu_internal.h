@@ -46,6 +46,10 @@ struct TermDev {              // one per (wavelength, CKD term)
   const double *gco, *bco;            // [nt][N] layer-integration weights g = (1-a)*mu/dt - a and 1 - a - g (k_att)
   const double *sxd, *syd;            // [nt+1] CH*XDEL, CH*YDEL: the order-1 source is c2*sxd + c1*syd (k_beam)
   const double *pup, *qup, *pdn, *qdn;   // [nt+1][N] the same weights times XDEL of the two levels, per sweep direction (k_att)
+  // First-order tables, indexed by the level they update (k_att): with sx = CH*XDEL, sy = CH*YDEL of the two levels of a layer,
+  //   upward   X(i) = X(i+1)*att[i] + c2*o1u2[i] + c1*o1u1[i],   o1u2 = b*sx(i) + g*sx(i+1),  o1u1 likewise with sy
+  //   downward X(i) = X(i-1)*adn[i] + c2*o1d2[i] + c1*o1d1[i],   adn[i] = att[i-1], o1d2 = b*sx(i) + g*sx(i-1)
+  const double *o1u1, *o1u2, *adn, *o1d1, *o1d2;
   double *i4;                         // [6][2N] running Fourier sums I4,Q4,U4,I5,Q5,U5 (component order below)
 };
 
@@ -94,9 +98,10 @@ void sos_launch_fourier(ItemDev *items, TermDev *terms, const OpticsDev *optics,
 void sos_launch_aggregate(const TermDev *terms, const int *group_start, const int *group_terms, int ngroup,
                           const double *rec, const int *n_fourier, int rec_stride_dev, int wdev,
                           double *grec, int *gnrec, cudaStream_t st);
-// first scattering order of every item of a wave (analytic source, boundary values, layer integration)
+// first scattering order of every item of a wave (analytic source, boundary values, layer integration); any_fresnel selects
+// the general kernel that also integrates the flat-sea source.  Returns the launches made, -1 on a CUDA error.
 int  sos_launch_order1(const ItemDev *items, const TermDev *terms, const OpticsDev *optics, const KsetDev *ksets,
-                       int nitem, int maxKP, cudaStream_t st);
+                       int nitem, int maxKP, int maxN, int any_fresnel, cudaStream_t st);
 // one scattering order n >= 2 (sweep_kernel.cu): persistent warp-specialised kernel; the item count is read from
 // count_ptr on the device when non-null (nitem is then an upper bound)
 int  sos_launch_sweep(const ItemDev *items, const TermDev *terms, const OpticsDev *optics, const KsetDev *ksets,

@@ -27,6 +27,7 @@
 // The main loop of chunk c+1 runs while the recurrence warps work on chunk c; the tensor pipe only waits for the
 // accumulator hand-off.  Work units are fetched dynamically (atomic counter), so ragged profiles (2..10 chunks) balance.
 #include "sosgpu_internal.h"
+#include "sosgpu_async.cuh"
 #include <math.h>
 #include <algorithm>
 #include <cstdio>
@@ -43,34 +44,6 @@
 
 namespace {
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-  const unsigned addr = smem_u32(bar);
-  unsigned ok;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, double b)
 {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -108,13 +81,6 @@ __device__ __forceinline__ void slab_mma(double (&acc)[2][8][2], double (&tacc)[
   }
 }
 
-__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity)
-{
-  unsigned ok;
-  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
 
 // The k-slabs of one level chunk for one warp.  The readiness of the NEXT stage is probed while the DMMAs of the current
 // slab are in flight, so the blocking wait at the top of a slab is normally skipped.
