@@ -247,6 +247,55 @@ int sosgpu_write_updown(const char *fic_up, const char *fic_down, int nbmu, int 
                         const double *phi_fin, const double *theta_fin, const double *up, const double *down, int nphi_cap,
                         int fix_sca_index);
 
+/* ---- the per-term profile chain that precedes every term-solve (SOS_PROC.F:3459-3537) ------------
+ * For each (wavelength, CKD term): SOS_ABSPROFILE (SOS_ABSPROFILE.F:184-425, with COEFF_ABS_CKD SOS_SUB_TRS.F:171-393)
+ * gives the gas optical thickness at the 50 levels of the gas atmosphere, SOS_PROFILE (SOS_PROFIL.F:224-1156, SOS_DISC :1210)
+ * cuts the atmosphere into NT layers of about equal optical thickness, and the PROFIL_TMP text file (format 2X,I5,F10.5,
+ * 3(E15.8)) carries ZPROF, H, PCAER, PCMOL to SOS (SOS.F:511-516).  Here the chain runs as device kernels over all terms of a
+ * band at once and its outputs are the arrays sosgpu_term points to.  Tables in the reference's Fortran storage (column-major,
+ * the compile-time extents of inc/SOS.h:246-282), as READ_CKD_COEFF and SOS_PREPA_ABSPROFILE fill them. */
+typedef struct {
+  int nb_temp, nb_pres, nb_conc_h2o;
+  const double *tab_temp;        /* TAB_TEMP(9)                    */
+  const double *tab_pres;        /* TAB_PRES(31)                   */
+  const double *tab_conc_h2o;    /* TAB_CONC_H2O(12)               */
+  const int    *nexp;            /* NEXP(8,50)                     */
+  const double *kdis_ki;         /* KDIS_KI(9,31,5,8,50)           */
+  const double *kdis_ki_h2o;     /* KDIS_KI_H2O(9,31,12,5,50)      */
+} sosgpu_ckd;
+typedef struct {
+  const double *userprofil;      /* USERPROFIL(50,13): altitude, P (mbar), T (K), H2O ... (SOS_ABSPROFILE.F:91-104) */
+  const double *altabs;          /* ALTABS(50), descending         */
+  const double *ro;              /* RO(8,50) particles/cm2 per gas and layer */
+} sosgpu_gas_profile;
+typedef struct {
+  int lamb1;                     /* spectral interval of the CKD tables, 1-based (unused when absprofil = 7) */
+  int ik[8];                     /* IK1..IK8: exponential index per gas (H2O CO2 O3 N2O CO CH4 O2 NO2) */
+  int absprofil;                 /* 7: no gaseous absorption       */
+  int iprofil;                   /* 1: exponential profiles, 2: aerosols between zmin and zmax */
+  double tr, hr, ta, ha, zmin, zmax;
+} sosgpu_profile_term;
+/* per-term error codes returned in ier[]: 0, the reference's error label (900..923 COEFF_ABS_CKD, 940 / 1010 / 1020
+ * SOS_PROFILE), or 9600 when a profile would need more than SOSGPU_NT_MAX levels (the reference writes out of bounds there) */
+/* SOS_ABSPROFILE for nterm terms: tauabs [nterm][50] */
+int sosgpu_absprofile(sosgpu_ctx *ctx, const sosgpu_ckd *ckd, const sosgpu_gas_profile *atm, const sosgpu_profile_term *terms,
+                      int nterm, double *tauabs, int *ier);
+/* SOS_PROFILE for nterm terms from given absorption profiles tauabs [nterm][50]; outputs nt [nterm] and zprof, h, pcaer,
+ * pcmol [nterm][SOSGPU_NT_MAX+1].  text_hop = 1 returns the values SOS reads back from PROFIL_TMP (5 decimals / 8 significant
+ * digits), 0 the unrounded ones */
+int sosgpu_profile(sosgpu_ctx *ctx, const double *altabs, const double *tauabs, const sosgpu_profile_term *terms, int nterm,
+                   int text_hop, int *nt, double *zprof, double *h, double *pcaer, double *pcmol, int *ier);
+/* both stages without the host hop in between; tauabs may be NULL */
+int sosgpu_profile_chain(sosgpu_ctx *ctx, const sosgpu_ckd *ckd, const sosgpu_gas_profile *atm, const sosgpu_profile_term *terms,
+                         int nterm, int text_hop, double *tauabs, int *nt, double *zprof, double *h, double *pcaer, double *pcmol,
+                         int *ier);
+/* READ_CKD_COEFF (SOS_SUB_TRS.F:481-905): host-side reader of $SOS_ABS_ROOT/fic/COEFF_CKD/<step>cmm1/coef_<GAS>_<max>_<min>_
+ * <step>cmm1 for gas nabs (1..8) and wavenumber nu; jabs = 0 fills the "gas not selected" defaults.  sos_abs_root NULL reads the
+ * environment variable as the reference does.  kdis_ai is KDIS_AI(5,8,50).  Returns 0 or -1 (the reference's IER). */
+int sosgpu_read_ckd_coeff(const char *sos_abs_root, int nabs, int jabs, double nu, double nustep, int *nexp, double *kdis_ai,
+                          double *kdis_ki, double *kdis_ki_h2o, double *numax, double *numin, double *tab_pres, int *nb_pres,
+                          double *tab_temp, int *nb_temp, double *tab_conc_h2o, int *nb_conc_h2o);
+
 /* ---- gfortran-ABI drop-in symbols (F77 by-reference, fixed SOS.h strides, hidden string lengths) */
 /* SOS_OS.F:303-308 */
 void sos_os_(const int *nbmu, double *rmu, const double *ga, const int *os_nb, const int *nt,
@@ -304,6 +353,22 @@ void sos_trphi_option_(const int *nbmu, const double *rmu, const double *ga, con
                        double *pol_rate_up, double *l_pol_up,
                        double *sca_down, double *i_down, double *q_down, double *u_down, double *pol_ang_down,
                        double *pol_rate_down, double *l_pol_down, int *ier, size_t len_fichos);
+
+/* SOS_SUB_TRS.F:481-485 (INTEGER*2 arguments are short) */
+void read_ckd_coeff_(const short *nabs, const short *jabs, const double *nu, const double *nustep, int *nexp, double *kdis_ai,
+                     double *kdis_ki, double *kdis_ki_h2o, double *numax, double *numin, double *tab_pres, int *nb_pres,
+                     double *tab_temp, int *nb_temp, double *tab_conc_h2o, int *nb_conc_h2o, int *ier);
+/* SOS_ABSPROFILE.F:184-190 */
+void sos_absprofile_(const short *absprofil, const double *nu, const int *lamb1, const short *iabs, const double *userprofil,
+                     const double *altabs, const double *ro, const int *nexp, const double *kdis_ki, const double *kdis_ki_h2o,
+                     const int *ik1, const int *ik2, const int *ik3, const int *ik4, const int *ik5, const int *ik6,
+                     const int *ik7, const int *ik8, const double *tab_pres, const int *nb_pres, const double *tab_temp,
+                     const int *nb_temp, const double *tab_conc_h2o, const int *nb_conc_h2o, double *tauabstot,
+                     const int *trace, const int *idlog, int *ier);
+/* SOS_PROFIL.F:224-226: writes FICPROFIL (format 20), returns NT */
+void sos_profile_(const short *iprofil, const double *tr, const double *hr, const double *ta, const double *ha,
+                  const double *zmin, const double *zmax, const short *absprofil, const double *altabs, const double *tabs,
+                  const int *trace, const int *idlog, const char *ficprofil, int *nt, int *ier, size_t len_ficprofil);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,10 @@ OUT = os.path.join(HERE, "_ref")
 # hot path + the input generator's Gauss angles + the "next" rows N1 / N2 of section 8(f), whose
 # reference routines are then available to future parity tests (and make SOS_TRPHI's Roujean / BPDF branches callable)
 FILES = ["SOS_OS.F", "SOS.F", "SOS_AGGREGATE.F", "SOS_TRPHI.F", "SOS_GLITTER.F", "SOS_SURFACE.F", "SOS_ANGLES.F",
-         "SOS_ROUJEAN.F", "SOS_SURFACE_BPDF.F", "SOS_PROFIL.F", "SOS_ABSPROFILE.F"]
+         "SOS_ROUJEAN.F", "SOS_SURFACE_BPDF.F", "SOS_PROFIL.F", "SOS_ABSPROFILE.F",
+         # N1: COEFF_ABS_CKD and the linear / spline interpolators it calls (the other routines of these two files do not
+         # translate -- DATA tables, list-directed string I/O -- and are not on the path)
+         "SOS_SUB_TRS.F", "SOS_AEROSOLS.F"]
 
 
 def build(force=False, verbose=True):
@@ -39,11 +42,13 @@ def build(force=False, verbose=True):
     known = set()
     for p in srcs:
         known |= t.subroutine_names(p)
+    skipped = set()
     for p in srcs:                                              # first pass: which routines translate at all
         _, _, rep = t.translate_file(p, defines, known=known)
-        known -= {name for name, st in rep if st != "ok"}        # calls of skipped routines become run-time aborts
+        skipped |= {name for name, st in rep if st != "ok"}      # calls of skipped routines become run-time aborts
+    known -= skipped
     for p in srcs:
-        c, pr, rep = t.translate_file(p, defines, known=known)
+        c, pr, rep = t.translate_file(p, defines, known=known, skipped=skipped)
         protos += pr
         bodies.append(c)
         report += [(os.path.basename(p),) + r for r in rep]

@@ -882,7 +882,10 @@ def translate_unit(name, args, stmts, defines, known_subs):
             continue
         if v["dims"]:
             size = " * ".join("((%s) - (%s) + 1)" % (u.cstr(hi, "i"), u.cstr(lo, "i")) for lo, hi in v["dims"])
-            decl.append("  static %s %s[%s];" % (CT[v["type"]], u.cname(n), size))
+            if "(*" in size:                                   # automatic array sized by a dummy argument: stack, zeroed
+                decl.append("  %s %s[%s]; memset(%s, 0, sizeof %s);" % (CT[v["type"]], u.cname(n), size, u.cname(n), u.cname(n)))
+            else:
+                decl.append("  static %s %s[%s];" % (CT[v["type"]], u.cname(n), size))
         else:
             decl.append("  %s %s = 0;" % (CT[v["type"]], u.cname(n)))
     # drop labels that no GOTO targets (avoids unused-label noise)
@@ -965,7 +968,7 @@ def subroutine_names(path):
     return names
 
 
-def translate_file(path, defines, wanted=None, known=None):
+def translate_file(path, defines, wanted=None, known=None, skipped=None):
     """Returns (c_source, prototypes, report) for the SUBROUTINEs of one file."""
     defines = dict(defines)
     stmts = list(logical_lines(path, defines))
@@ -982,7 +985,7 @@ def translate_file(path, defines, wanted=None, known=None):
     src, protos, report = [], [], []
     ok = set()
     # two passes so that a routine may CALL one defined later in the file
-    known = set(names) | set(known or ())
+    known = (set(names) | set(known or ())) - set(skipped or ())   # calls of `skipped` routines become run-time aborts
     for name, args, body in units:
         if wanted and name not in wanted:
             continue

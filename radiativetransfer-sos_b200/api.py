@@ -56,6 +56,23 @@ class CDirectModels(C.Structure):
                 ("beta_nadal", C.c_double), ("imaignan", C.c_int), ("coef_c_maignan", C.c_double)]
 
 
+class CCkd(C.Structure):
+    _fields_ = [("nb_temp", C.c_int), ("nb_pres", C.c_int), ("nb_conc_h2o", C.c_int), ("tab_temp", c_dp), ("tab_pres", c_dp),
+                ("tab_conc_h2o", c_dp), ("nexp", c_ip), ("kdis_ki", c_dp), ("kdis_ki_h2o", c_dp)]
+
+
+class CGasProfile(C.Structure):
+    _fields_ = [("userprofil", c_dp), ("altabs", c_dp), ("ro", c_dp)]
+
+
+class CProfileTerm(C.Structure):
+    _fields_ = [("lamb1", C.c_int), ("ik", C.c_int * 8), ("absprofil", C.c_int), ("iprofil", C.c_int), ("tr", C.c_double),
+                ("hr", C.c_double), ("ta", C.c_double), ("ha", C.c_double), ("zmin", C.c_double), ("zmax", C.c_double)]
+
+
+NT_MAX = 600
+
+
 class CStats(C.Structure):
     _fields_ = [("steps", C.c_longlong), ("flops", C.c_double), ("bytes", C.c_double), ("step_ms", C.c_double),
                 ("step_launches", C.c_longlong), ("total_ms", C.c_double), ("launches", C.c_longlong),
@@ -482,6 +499,72 @@ class Solver:
                                          C.c_int(os_ns), _d(out[0]), _d(out[1]), _d(out[2]), _d(out[3]))
         self._check(rc, "mat_fresnel")
         return out
+
+    # ---- the per-term profile chain ----
+    @staticmethod
+    def _profile_terms(terms):
+        arr = (CProfileTerm * len(terms))()
+        for a, t in zip(arr, terms):
+            a.lamb1, a.absprofil, a.iprofil = int(t["lamb1"]), int(t["absprofil"]), int(t["iprofil"])
+            for k in range(8):
+                a.ik[k] = int(t["ik"][k])
+            a.tr, a.hr, a.ta, a.ha, a.zmin, a.zmax = (float(t[k]) for k in ("tr", "hr", "ta", "ha", "zmin", "zmax"))
+        return arr
+
+    @staticmethod
+    def _ckd(tables):
+        """tables: dict of Fortran-ordered arrays as READ_CKD_COEFF fills them (keys as tests/profile_cases.ckd_tables)."""
+        keep = [np.asfortranarray(tables[k], dtype=np.float64) for k in ("tab_temp", "tab_pres", "tab_conc", "ki", "kh")]
+        nexp = np.asfortranarray(tables["nexp"], dtype=np.int32)
+        c = CCkd(int(tables["nb_temp"]), int(tables["nb_pres"]), int(tables["nb_conc"]), _d(keep[0]), _d(keep[1]), _d(keep[2]),
+                 nexp.ctypes.data_as(c_ip), _d(keep[3]), _d(keep[4]))
+        return c, keep + [nexp]
+
+    def absprofile(self, tables, userprofil, ro, terms):
+        """SOS_ABSPROFILE (SOS_ABSPROFILE.F:184) for every term: (tauabs [nterm, 50], ier [nterm])."""
+        c, keep = self._ckd(tables)
+        user, ro = np.asfortranarray(userprofil, dtype=np.float64), np.asfortranarray(ro, dtype=np.float64)
+        g = CGasProfile(_d(user), None, _d(ro))
+        arr = self._profile_terms(terms)
+        tau, ier = np.zeros((len(terms), 50)), np.zeros(len(terms), dtype=np.int32)
+        self.lib.sosgpu_absprofile.argtypes = [C.c_void_p, C.POINTER(CCkd), C.POINTER(CGasProfile), C.POINTER(CProfileTerm), C.c_int,
+                                               c_dp, c_ip]
+        rc = self.lib.sosgpu_absprofile(self.ctx, C.byref(c), C.byref(g), arr, len(terms), _d(tau), ier.ctypes.data_as(c_ip))
+        self._check(rc, "absprofile")
+        return tau, ier
+
+    def _profile_out(self, n):
+        return (np.zeros(n, dtype=np.int32), *(np.zeros((n, NT_MAX + 1)) for _ in range(4)), np.zeros(n, dtype=np.int32))
+
+    def profile(self, altabs, tauabs, terms, text_hop=True):
+        """SOS_PROFILE (SOS_PROFIL.F:224) for every term from given absorption profiles [nterm, 50]:
+        (nt, zprof, h, pcaer, pcmol [nterm, 601], ier).  text_hop: the values SOS reads back from PROFIL_TMP."""
+        n = len(terms)
+        nt, z, h, pa, pm, ier = self._profile_out(n)
+        tau = _f64(tauabs).reshape(n, 50)
+        self.lib.sosgpu_profile.argtypes = [C.c_void_p, c_dp, c_dp, C.POINTER(CProfileTerm), C.c_int, C.c_int, c_ip, c_dp, c_dp, c_dp,
+                                            c_dp, c_ip]
+        rc = self.lib.sosgpu_profile(self.ctx, _d(_f64(altabs)), _d(tau), self._profile_terms(terms), n, int(bool(text_hop)),
+                                     nt.ctypes.data_as(c_ip), _d(z), _d(h), _d(pa), _d(pm), ier.ctypes.data_as(c_ip))
+        self._check(rc, "profile")
+        return nt, z, h, pa, pm, ier
+
+    def profile_chain(self, tables, userprofil, altabs, ro, terms, text_hop=True, want_tauabs=False):
+        """SOS_ABSPROFILE -> SOS_PROFILE -> PROFIL_TMP hop for every term of a band, on the device without a host hop in between
+        (SOS_PROC.F:3494-3537).  Returns (nt, zprof, h, pcaer, pcmol, ier[, tauabs])."""
+        n = len(terms)
+        c, keep = self._ckd(tables)
+        user, ro, alt = np.asfortranarray(userprofil, dtype=np.float64), np.asfortranarray(ro, dtype=np.float64), _f64(altabs)
+        g = CGasProfile(_d(user), _d(alt), _d(ro))
+        nt, z, h, pa, pm, ier = self._profile_out(n)
+        tau = np.zeros((n, 50)) if want_tauabs else None
+        self.lib.sosgpu_profile_chain.argtypes = [C.c_void_p, C.POINTER(CCkd), C.POINTER(CGasProfile), C.POINTER(CProfileTerm), C.c_int,
+                                                  C.c_int, c_dp, c_ip, c_dp, c_dp, c_dp, c_dp, c_ip]
+        rc = self.lib.sosgpu_profile_chain(self.ctx, C.byref(c), C.byref(g), self._profile_terms(terms), n, int(bool(text_hop)),
+                                           _d(tau) if want_tauabs else None, nt.ctypes.data_as(c_ip), _d(z), _d(h), _d(pa), _d(pm),
+                                           ier.ctypes.data_as(c_ip))
+        self._check(rc, "profile_chain")
+        return (nt, z, h, pa, pm, ier) + ((tau,) if want_tauabs else ())
 
     def batch_trphi(self, batch, igli, wind, ind_surf, ifresnel, itrphi, phios, pas_phi, ipolar, download=True):
         """SOS_TRPHI_OPTION for every wavelength of a resident batch (after run); tables [ngroup, 7, nphi, Nmax]."""

@@ -164,3 +164,45 @@ def compare_terms(tr, res, ids, wl, assert_close, what):
         for k in ("ttot_tronc", "ttot_vrai", "tauout"):
             assert getattr(tr, k)[n] == r[k], (what, i, k)
     return bad
+
+
+# ---- the per-term profile chain ------------------------------------------------------------------------
+_IP = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def absprofile(ref, tables, user, altabs, ro, term):
+    """SOS_ABSPROFILE (SOS_ABSPROFILE.F:184) -> (IER, TAUABSTOT[50]).  INTEGER*2 arguments are int in the translated library."""
+    tau = np.zeros(50)
+    ier = C.c_int(99)
+    iabs = np.ones(8, dtype=np.int32)
+    ik = [_ip(v) for v in term["ik"]]
+    ref.sos_absprofile_(_ip(term["absprofil"]), _dp(13000.0), _ip(term["lamb1"]), _IP(iabs), _P(user), _P(altabs), _P(ro),
+                        _IP(tables["nexp"]), _P(tables["ki"]), _P(tables["kh"]), *ik, _P(tables["tab_pres"]), _ip(tables["nb_pres"]),
+                        _P(tables["tab_temp"]), _ip(tables["nb_temp"]), _P(tables["tab_conc"]), _ip(tables["nb_conc"]), _P(tau),
+                        _ip(0), _ip(0), C.byref(ier))
+    return ier.value, tau
+
+
+def read_profile_file(path):
+    """PROFIL_TMP as SOS reads it (SOS.F:511-516, format 2X,I5,F10.5,3(E15.8)) -> zprof, h, pcaer, pcmol."""
+    z, h, pa, pm = [], [], [], []
+    with open(path) as f:
+        for line in f:
+            if not line.strip():
+                continue
+            z.append(float(line[7:17])); h.append(float(line[17:32])); pa.append(float(line[32:47])); pm.append(float(line[47:62]))
+    return np.array(z), np.array(h), np.array(pa), np.array(pm)
+
+
+def profile(ref, tmp, altabs, tabs, term):
+    """SOS_PROFILE (SOS_PROFIL.F:224) through its file -> (IER, NT, text, zprof, h, pcaer, pcmol)."""
+    f = os.path.join(tmp, "PROFIL_REF.txt")
+    if os.path.exists(f):
+        os.remove(f)
+    nt, ier = C.c_int(0), C.c_int(99)
+    ref.sos_profile_(_ip(term["iprofil"]), _dp(term["tr"]), _dp(term["hr"]), _dp(term["ta"]), _dp(term["ha"]), _dp(term["zmin"]),
+                     _dp(term["zmax"]), _ip(term["absprofil"]), _P(altabs), _P(tabs), _ip(0), _ip(0), _fs(f), C.byref(nt), C.byref(ier), _L)
+    if ier.value != 0:
+        return ier.value, 0, b"", None, None, None, None
+    text = open(f, "rb").read()
+    return (0, nt.value, text) + read_profile_file(f)

@@ -232,3 +232,125 @@ def test_land_surface_files_roujean_breon(pkg, solver, ref, tmp_path):
     bad = refdirect.compare_terms(tr, res, ids, wl, assert_stokes_close, "cfg4-real")
     _tally("cfg4 with the Roujean + Breon surface file made on each side (N=25)", bad, len(ids))
     assert not bad
+
+
+# ---- the per-term profile chain ------------------------------------------------------------------------
+def _chain_reference(ref, tmp, t, user, altabs, ro, terms):
+    out = []
+    for term in terms:
+        ier, tau = refdirect.absprofile(ref, t, user, altabs, ro, term)
+        assert ier == 0
+        out.append((tau,) + refdirect.profile(ref, tmp, altabs, tau, term))
+    return out
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_profile_chain_vs_reference(solver, ref, seed, tmp_path):
+    """SOS_ABSPROFILE -> SOS_PROFILE -> PROFIL_TMP for 150 (wavelength, CKD term) entries in one device call, against the
+    reference's routines called term by term: every NT identical, the absorption profile within 1e-13 (device exp / log are
+    not glibc's), and the values SOS reads back from the text file identical except where a 1-ulp difference crosses a
+    rounding boundary of the 8-digit decimal (counted, and bounded)."""
+    import profile_cases as pc
+    user, altabs, ro = pc.gas_atmosphere(seed)
+    t = pc.ckd_tables(seed)
+    terms = pc.make_terms(t, 150, seed)
+    want = _chain_reference(ref, str(tmp_path), t, user, altabs, ro, terms)
+    nt, z, h, pa, pm, ier, tau = solver.profile_chain(t, user, altabs, ro, terms, text_hop=True, want_tauabs=True)
+    nvals = ndiff = nbad_nt = 0
+    branches = {"nogas": 0, "weak": 0, "strong": 0}
+    for i, (tau_r, ier_r, nt_r, _, z_r, h_r, pa_r, pm_r) in enumerate(want):
+        assert (ier[i] != 0) == (ier_r != 0), (i, ier[i], ier_r)
+        if ier_r != 0:
+            continue
+        np.testing.assert_allclose(tau[i], tau_r, rtol=1e-13, atol=1e-300, err_msg="TAUABSTOT term %d" % i)
+        branches["nogas" if tau_r[-1] == 0 else "strong" if tau_r[-1] > 1.5 else "weak"] += 1
+        if nt[i] != nt_r:
+            nbad_nt += 1
+            continue
+        for a, b in ((z[i], z_r), (h[i], h_r), (pa[i], pa_r), (pm[i], pm_r)):
+            a = a[:nt_r + 1]
+            nvals += a.size
+            ndiff += int((a != b).sum())
+            np.testing.assert_allclose(a, b, rtol=2e-7, atol=1e-5, err_msg="profile term %d" % i)
+        assert not h[i, nt_r + 1:].any()
+    print("\n[profile chain seed %d] NT mismatches %d / %d terms; text values differing %d / %d; branches %s"
+          % (seed, nbad_nt, len(terms), ndiff, nvals, branches))
+    assert nbad_nt == 0
+    assert ndiff <= max(2, nvals // 100000)
+    assert min(branches.values()) >= 2
+
+
+def test_profile_stages_and_errors(solver, ref, tmp_path):
+    """The two stages separately (sosgpu_absprofile, sosgpu_profile incl. IPROFIL = 2 and the unrounded output), the error
+    codes per term, and the solver fed from the chain's arrays."""
+    import profile_cases as pc
+    user, altabs, ro = pc.gas_atmosphere(2)
+    t = pc.ckd_tables(2)
+    terms = pc.make_terms(t, 24, 2)
+    tau, ier = solver.absprofile(t, user, ro, terms)
+    assert not ier.any()
+    for i, term in enumerate(terms):
+        _, tau_r = refdirect.absprofile(ref, t, user, altabs, ro, term)
+        np.testing.assert_allclose(tau[i], tau_r, rtol=1e-13, atol=1e-300)
+    # stage 2 from the reference's absorption profiles: the text-hop values equal the reference's file
+    taus = np.array([refdirect.absprofile(ref, t, user, altabs, ro, term)[1] for term in terms])
+    nt, z, h, pa, pm, ier = solver.profile(altabs, taus, terms, text_hop=True)
+    nt0, z0, h0, pa0, pm0, _ = solver.profile(altabs, taus, terms, text_hop=False)
+    assert not ier.any() and np.array_equal(nt, nt0)
+    for i, term in enumerate(terms):
+        ier_r, nt_r, _, z_r, h_r, pa_r, pm_r = refdirect.profile(ref, str(tmp_path), altabs, taus[i], term)
+        assert ier_r == 0 and nt[i] == nt_r
+        np.testing.assert_allclose(h[i, :nt_r + 1], h_r, rtol=2e-7)
+        assert np.mean(h[i, :nt_r + 1] == h_r) > 0.99
+        np.testing.assert_allclose(h0[i, :nt_r + 1], h_r, rtol=1e-7, atol=1e-12)      # unrounded values sit within the text precision
+        assert (np.diff(h0[i, :nt_r + 1]) > 0).all() and (np.diff(z0[i, :nt_r + 1]) < 0).all()
+    # IPROFIL = 2 and the error exits (bad altitudes 1010, too little aerosol 1020, IPROFIL 940)
+    t2 = [dict(terms[0], iprofil=2, absprofil=7, tr=0.2, ta=0.3, zmin=1.0, zmax=4.0),
+          dict(terms[0], iprofil=2, absprofil=7, tr=0.2, ta=0.3, zmin=4.0, zmax=1.0),
+          dict(terms[0], iprofil=2, absprofil=7, tr=0.2, ta=1e-9, zmin=0.0, zmax=3.0),
+          dict(terms[0], iprofil=3),
+          dict(terms[0], iprofil=1, absprofil=2, tr=0.345, ta=1.17, ha=2.25)]     # > 600 levels: the reference never returns
+    tau2 = np.zeros((5, 50))
+    tau2[4] = np.linspace(0.0, 1.31, 50)
+    nt, z, h, pa, pm, ier = solver.profile(altabs, tau2, t2, text_hop=True)
+    assert list(ier) == [0, 1010, 1020, 940, 9600] and not nt[1:].any()
+    import ctypes as C
+    import shutil
+    fresh = str(tmp_path / "libsosref_fresh.so")                   # IPROFIL = 2 reads Hmol(0) before setting it: fresh image
+    shutil.copy(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libsosref.so"), fresh)
+    ier_r, nt_r, _, z_r, h_r, pa_r, pm_r = refdirect.profile(C.CDLL(fresh), str(tmp_path), altabs, np.zeros(50), t2[0])
+    assert ier_r == 0 and nt[0] == nt_r
+    np.testing.assert_allclose(h[0, :nt_r + 1], h_r, rtol=2e-7)
+    np.testing.assert_allclose(pa[0, :nt_r + 1], pa_r, rtol=2e-7, atol=1e-12)
+
+
+def test_profile_chain_feeds_the_solver(pkg, solver, ref, tmp_path):
+    """End of the N1 row: profiles made by the device chain go into the device solve, profiles made by the reference chain go
+    into the reference solve; same Fourier-order counts and Stokes within 1e-9 on every term."""
+    import profile_cases as pc
+    syn = pkg.synth
+    user, altabs, ro = pc.gas_atmosphere(4)
+    t = pc.ckd_tables(4)
+    terms = [dict(x, absprofil=2, ta=0.15, ha=2.0, tr=0.05, hr=8.0) for x in pc.make_terms(t, 12, 4)]
+    nt, z, h, pa, pm, ier = solver.profile_chain(t, user, altabs, ro, terms, text_hop=True)
+    assert not ier.any()
+    wl_ref, wl_gpu = syn.Workload("chain-ref"), syn.Workload("chain-gpu")
+    for w in (wl_ref, wl_gpu):
+        w.optics.append(syn.make_optics(nb_gauss=24, tetas=35.0, os_nb=40, surface="lambert", rho=0.1))
+    for i, term in enumerate(terms):
+        ier_r, tau_r = refdirect.absprofile(ref, t, user, altabs, ro, term)
+        _, nt_r, _, z_r, h_r, pa_r, pm_r = refdirect.profile(ref, str(tmp_path), altabs, tau_r, term)
+        assert nt[i] == nt_r
+        n = int(nt[i]) + 1
+        wl_ref.terms.append(syn.Term(0, 1.0 / len(terms), z_r, h_r, pa_r, pm_r))
+        wl_gpu.terms.append(syn.Term(0, 1.0 / len(terms), z[i, :n].copy(), h[i, :n].copy(), pa[i, :n].copy(), pm[i, :n].copy()))
+    ids = list(range(len(terms)))
+    res, _, _ = refdirect.runner().solve_terms(wl_ref, ids, CORES)
+    b = solver.upload(wl_gpu)
+    try:
+        tr, gr = solver.run(b)
+        bad = refdirect.compare_terms(tr, res, ids, wl_ref, assert_stokes_close, "profile chain -> solve")
+        _tally("profile chain -> solve (12 terms, N=25)", bad, len(ids))
+        assert not bad
+    finally:
+        b.free()
