@@ -52,8 +52,8 @@ const char *sosgpu_last_error(const sosgpu_ctx *ctx);
 int  sosgpu_device_count(void);
 /* number of kernels this library has launched since create (bench.py's gpu_launches) */
 long long sosgpu_launch_count(const sosgpu_ctx *ctx);
-/* device time (CUDA events on the library's stream) of the kernel launched by the last sosgpu_glitter or
- * sosgpu_batch_trphi call, ms */
+/* device time (CUDA events on the library's stream) of the kernel(s) launched by the last sosgpu_glitter,
+ * sosgpu_batch_trphi or sosgpu_absprofile / sosgpu_profile / sosgpu_profile_chain call, ms */
 double sosgpu_last_kernel_ms(const sosgpu_ctx *ctx);
 /* wave sizing knobs: device memory budget for field buffers (bytes, 0 = default) and the
  * maximum number of Fourier orders solved concurrently per term (0 = automatic) */

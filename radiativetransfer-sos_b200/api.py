@@ -502,7 +502,10 @@ class Solver:
 
     # ---- the per-term profile chain ----
     @staticmethod
-    def _profile_terms(terms):
+    def profile_terms(terms):
+        """list of dicts (lamb1, ik[8], absprofil, iprofil, tr, hr, ta, ha, zmin, zmax) -> C array; a C array passes through."""
+        if isinstance(terms, C.Array):
+            return terms
         arr = (CProfileTerm * len(terms))()
         for a, t in zip(arr, terms):
             a.lamb1, a.absprofil, a.iprofil = int(t["lamb1"]), int(t["absprofil"]), int(t["iprofil"])
@@ -525,7 +528,7 @@ class Solver:
         c, keep = self._ckd(tables)
         user, ro = np.asfortranarray(userprofil, dtype=np.float64), np.asfortranarray(ro, dtype=np.float64)
         g = CGasProfile(_d(user), None, _d(ro))
-        arr = self._profile_terms(terms)
+        arr = self.profile_terms(terms)
         tau, ier = np.zeros((len(terms), 50)), np.zeros(len(terms), dtype=np.int32)
         self.lib.sosgpu_absprofile.argtypes = [C.c_void_p, C.POINTER(CCkd), C.POINTER(CGasProfile), C.POINTER(CProfileTerm), C.c_int,
                                                c_dp, c_ip]
@@ -544,7 +547,7 @@ class Solver:
         tau = _f64(tauabs).reshape(n, 50)
         self.lib.sosgpu_profile.argtypes = [C.c_void_p, c_dp, c_dp, C.POINTER(CProfileTerm), C.c_int, C.c_int, c_ip, c_dp, c_dp, c_dp,
                                             c_dp, c_ip]
-        rc = self.lib.sosgpu_profile(self.ctx, _d(_f64(altabs)), _d(tau), self._profile_terms(terms), n, int(bool(text_hop)),
+        rc = self.lib.sosgpu_profile(self.ctx, _d(_f64(altabs)), _d(tau), self.profile_terms(terms), n, int(bool(text_hop)),
                                      nt.ctypes.data_as(c_ip), _d(z), _d(h), _d(pa), _d(pm), ier.ctypes.data_as(c_ip))
         self._check(rc, "profile")
         return nt, z, h, pa, pm, ier
@@ -560,7 +563,7 @@ class Solver:
         tau = np.zeros((n, 50)) if want_tauabs else None
         self.lib.sosgpu_profile_chain.argtypes = [C.c_void_p, C.POINTER(CCkd), C.POINTER(CGasProfile), C.POINTER(CProfileTerm), C.c_int,
                                                   C.c_int, c_dp, c_ip, c_dp, c_dp, c_dp, c_dp, c_ip]
-        rc = self.lib.sosgpu_profile_chain(self.ctx, C.byref(c), C.byref(g), self._profile_terms(terms), n, int(bool(text_hop)),
+        rc = self.lib.sosgpu_profile_chain(self.ctx, C.byref(c), C.byref(g), self.profile_terms(terms), n, int(bool(text_hop)),
                                            _d(tau) if want_tauabs else None, nt.ctypes.data_as(c_ip), _d(z), _d(h), _d(pa), _d(pm),
                                            ier.ctypes.data_as(c_ip))
         self._check(rc, "profile_chain")

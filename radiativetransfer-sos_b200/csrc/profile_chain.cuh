@@ -17,8 +17,10 @@
 
 #ifdef __CUDACC__
 #define PC_HD __host__ __device__ inline
+#define PC_HDM __host__ __device__
 #else
 #define PC_HD static inline
+#define PC_HDM
 #endif
 
 // dimensions of SOS.h:246-282
@@ -182,39 +184,124 @@ PC_HD void pc_absprofile_scan(const double *tau_layer, double *tauabs)
   }
 }
 
-// Gas optical thickness at altitude z by linear interpolation in the 50-level table (the three variants of SOS_PROFIL.F).
+// Index j (2..50, 1-based) of the first gas level at or below altitude z: the linear search `J=2; DO WHILE(Z.LT.ALTABS(J))` of
+// SOS_PROFIL.F as a binary search.  ALTABS is strictly descending (the host checks it), so the first j with z >= ALTABS(j) is
+// where the predicate flips; z below ALTABS(50) (never: altitudes are >= 0 = ALTABS(50)) stops at 50 instead of running off.
 PC_HD int pc_abs_bracket(const double *altabs, double z)
 {
-  int j = 2;
-  while (z < altabs[j - 1]) ++j;
-  return j;
+  if (!(z < altabs[1])) return 2;
+  int lo = 2, hi = PC_NLEV;                                       // z < altabs(lo) holds; answer in (lo, hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (z < altabs[mid - 1]) lo = mid; else hi = mid;
+  }
+  return hi;
+}
+
+struct PcColumn {              // what the optical depth at an altitude depends on
+  double ta, ha, tr, hr;
+  const double *tabs, *altabs;
+  double tg_zlim;              // SOS_DISC: gas is interpolated only when TG_ZLIM > 0
+};
+
+// total optical depth at altitude z as SOS_DISC forms it (SOS_PROFIL.F:1285-1306)
+PC_HD double pc_disc_tau(const PcColumn &c, double zmoy)
+{
+  double tg;
+  if (c.tg_zlim > 0.0) {
+    const int j = pc_abs_bracket(c.altabs, zmoy);
+    double zz;
+    if (zmoy > c.altabs[0]) zz = 0.0;
+    else zz = (zmoy - c.altabs[j - 2]) / (c.altabs[j - 1] - c.altabs[j - 2]);
+    tg = (1 - zz) * c.tabs[j - 2] + zz * c.tabs[j - 1];
+  } else tg = 0.0;
+  return c.ta * exp(-zmoy / c.ha) + c.tr * exp(-zmoy / c.hr) + tg;
+}
+// ... and as the search of the first level forms it: without gas (SOS_PROFIL.F:428) / with gas (:661-678)
+PC_HD double pc_first_tau_ng(const PcColumn &c, double z) { return c.tr * exp(-z / c.hr) + c.ta * exp(-z / c.ha); }
+PC_HD double pc_first_tau_gas(const PcColumn &c, double z)
+{
+  const int j = pc_abs_bracket(c.altabs, z);
+  double vg;
+  if (z <= c.altabs[0]) {
+    const double zz = (z - c.altabs[j - 2]) / (c.altabs[j - 1] - c.altabs[j - 2]);
+    vg = (1 - zz) * c.tabs[j - 2] + zz * c.tabs[j - 1];
+  } else vg = 0.0;
+  const double vr = c.tr * exp(-z / c.hr), va = c.ta * exp(-z / c.ha);
+  return vr + va + vg;
+}
+
+#define PC_DISC_TOL ((double).000001f)
+// One step of SOS_DISC's bisection at the candidate zmoy: bit 0 = stop here (:1311-1312), bit 1 = continue with ZMIN = ZMOY
+// (else ZMAX = ZMOY, :1316-1320).
+PC_HD int pc_disc_step(const PcColumn &c, double ti, double zmoy)
+{
+  const double tzmoy = pc_disc_tau(c, zmoy);
+  const double xd = fabs(ti - tzmoy);
+  int r = 0;
+  if (xd < PC_DISC_TOL) r |= 1;
+  if (zmoy == 0.0) r |= 1;
+  if ((ti - tzmoy) < 0.0) r |= 2;
+  return r;
 }
 
 // SOS_DISC (SOS_PROFIL.F:1210-1332): altitude whose total optical depth is tim1 + dt, by bisection between zlim and zmax_init.
-PC_HD double pc_disc(double dt, double ta, double ha, double tr, double hr, const double *tabs, const double *altabs, double tim1,
-                     double zmax_init, double tg_zlim, double zlim)
+PC_HD double pc_disc(double dt, const PcColumn &c, double tim1, double zmax_init, double zlim)
 {
   const double ti = tim1 + dt;
   double zmax = zmax_init, zmin = zlim, zmoy;
-  const double tol = (double).000001f;
   for (;;) {
     zmoy = (zmax + zmin) / 2.0;
-    double tg;
-    if (tg_zlim > 0.0) {
-      const int j = pc_abs_bracket(altabs, zmoy);
-      double zz;
-      if (zmoy > altabs[0]) zz = 0.0;
-      else zz = (zmoy - altabs[j - 2]) / (altabs[j - 1] - altabs[j - 2]);
-      tg = (1 - zz) * tabs[j - 2] + zz * tabs[j - 1];
-    } else tg = 0.0;
-    const double tzmoy = ta * exp(-zmoy / ha) + tr * exp(-zmoy / hr) + tg;
-    const double xd = fabs(ti - tzmoy);
-    if (xd < tol) break;
-    if (zmoy == 0.0) break;
-    if ((ti - tzmoy) < 0.0) zmin = zmoy; else zmax = zmoy;
+    const int r = pc_disc_step(c, ti, zmoy);
+    if (r & 1) break;
+    if (r & 2) zmin = zmoy; else zmax = zmoy;
   }
   return zmoy;
 }
+
+// The same bisection, five levels at a time: the 31 candidates of a depth-5 subtree are independent once the interval at its
+// root is known, so 31 lanes evaluate them at once and the path the serial loop would have taken is read off their results.
+// Node n (heap order, 1 = root, children 2n / 2n+1) sits at the end of the path spelled by the bits of n below its leading
+// one, most significant first: bit 1 = "ZMIN = ZMOY" at that ancestor.  The midpoints are formed with the reference's own
+// expression at every ancestor, so a node's candidate is the very double the serial loop would test there.
+PC_HD void pc_tree_interval(int n, int depth, double zmin, double zmax, double *lo, double *hi)
+{
+  double l = zmin, h = zmax;
+  for (int b = depth - 1; b >= 0; --b) {
+    const double mid = (h + l) / 2.0;
+    if ((n >> b) & 1) l = mid; else h = mid;
+  }
+  *lo = l; *hi = h;
+}
+PC_HD int pc_tree_depth(int n) { int d = 0; while ((n >> (d + 1)) != 0) ++d; return d; }
+// stop / direction masks (bit n = node n) -> node where the serial loop stops (returns 1) or the depth-5 virtual node (32..63)
+// whose interval is the next root (returns 0)
+PC_HD int pc_tree_walk(unsigned stop, unsigned dir, int *node)
+{
+  int m = 1;
+  for (int lvl = 0; lvl < 5; ++lvl) {
+    if ((stop >> m) & 1u) { *node = m; return 1; }
+    m = 2 * m + (int)((dir >> m) & 1u);
+  }
+  *node = m;
+  return 0;
+}
+
+// Search strategies of pc_profile.  PcSerial is the reference's control flow statement by statement; the kernels use a
+// warp-wide strategy built on pc_tree_* (sosgpu_profile.cu) and tests/profile_host.cpp holds a host emulation of that one.
+struct PcSerial {
+  PC_HDM double disc(double dt, const PcColumn &c, double tim1, double zmax_init, double zlim) const { return pc_disc(dt, c, tim1, zmax_init, zlim); }
+  // first level: Z steps down by CTE_DELTA_Z until the optical depth reaches t_first (SOS_PROFIL.F:424-429, 657-679)
+  PC_HDM void first(bool gas, const PcColumn &c, double t_first, double *z, double *dtau) const
+  {
+    double d = 0.0, zz = *z;
+    while (d < t_first) {
+      zz = zz - PC_DELTA_Z;
+      d = gas ? pc_first_tau_gas(c, zz) : pc_first_tau_ng(c, zz);
+    }
+    *z = zz; *dtau = d;
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // The text hop.  A value written with Ew.8 and read back is the double nearest to its 8-significant-digit decimal, the
@@ -289,9 +376,10 @@ PC_HD double pc_round_f5(double x)                                 // WRITE F10.
 // scratch: PC_LEVELS doubles (the altitudes of the profile without gas, kept for the profile with gas).
 // Returns 0, or the reference's error label (940, 1010, 1020), or 9600 when the level count would leave the reference's arrays
 // (CTE_OS_NT = 600: the reference writes out of bounds there; this implementation refuses).
-PC_HD int pc_profile(int iprofil, double tr, double hr, double ta, double ha, double zmin_in, double zmax_in, int absprofil,
-                     const double *altabs, const double *tabs, double *zng, double *zprof, double *h, double *pcaer, double *pcmol,
-                     int *nt_out)
+template <class Search>
+PC_HD int pc_profile(const Search &srch, int iprofil, double tr, double hr, double ta, double ha, double zmin_in, double zmax_in,
+                     int absprofil, const double *altabs, const double *tabs, double *zng, double *zprof, double *h, double *pcaer,
+                     double *pcmol, int *nt_out)
 {
   if (iprofil != 1 && iprofil != 2) return 940;
   int nt = 0;
@@ -329,18 +417,16 @@ PC_HD int pc_profile(int iprofil, double tr, double hr, double ta, double ha, do
       }
     } else {
       zng[0] = PC_TOA_ALT; hng[0] = 0.0;
+      const PcColumn cng = {ta, ha, tr, hr, tabs, altabs, 0.0};
       double dtau = 0.0, z = PC_TOA_ALT;
-      while (dtau < t_first_ng) {
-        z = z - PC_DELTA_Z;
-        dtau = tr * exp(-z / hr) + ta * exp(-z / ha);
-      }
+      srch.first(false, cng, t_first_ng, &z, &dtau);
       zng[1] = z;
       double vr = tr * exp(-z / hr), va = ta * exp(-z / ha);
       double hmol_prev = vr, haer_prev = va;
       hng[1] = dtau; pm[1] = vr / dtau; pa[1] = va / dtau;
       pm[0] = pm[1]; pa[0] = pa[1];
       for (int i = 2; i <= nt_ng - 1; ++i) {
-        z = pc_disc(t_layer_ng, ta, ha, tr, hr, tabs, altabs, hng[i - 1], zng[1], 0.0, 0.0);
+        z = srch.disc(t_layer_ng, cng, hng[i - 1], zng[1], 0.0);
         zng[i] = z;
         vr = tr * exp(-z / hr); va = ta * exp(-z / ha);
         const double hm = vr, hae = va;
@@ -400,27 +486,18 @@ PC_HD int pc_profile(int iprofil, double tr, double hr, double ta, double ha, do
       double hmol_pp = 0.0, haer_pp = 0.0, habs_pp = 0.0;          // ... of level NT-2 (needed if the last level is dropped)
       h[0] = 0.0;
       const double ttot_zlim = ta * exp(-zlim / ha) + tr * exp(-zlim / hr) + tg_zlim;
+      const PcColumn cg = {ta, ha, tr, hr, tabs, altabs, tg_zlim};
       while ((ttot_zlim - h[nt - 1]) > t_layer) {
         const int i = nt;
         if (i >= PC_OS_NT) return 9600;
         if (i == 1) {
           double dtau = 0.0;
-          while (dtau < t_first) {
-            z = z - PC_DELTA_Z;
-            const int j = pc_abs_bracket(altabs, z);
-            double vg;
-            if (z <= altabs[0]) {
-              const double zz = (z - altabs[j - 2]) / (altabs[j - 1] - altabs[j - 2]);
-              vg = (1 - zz) * tabs[j - 2] + zz * tabs[j - 1];
-            } else vg = 0.0;
-            const double vr = tr * exp(-z / hr), va = ta * exp(-z / ha);
-            dtau = vr + va + vg;
-          }
+          srch.first(true, cg, t_first, &z, &dtau);
           zprof[1] = z;
           h[1] = dtau;
           ing = 1;
         } else {
-          z = pc_disc(t_layer, ta, ha, tr, hr, tabs, altabs, h[i - 1], zprof[1], tg_zlim, zlim);
+          z = srch.disc(t_layer, cg, h[i - 1], zprof[1], zlim);
         }
         if (z <= zing) {
           z = zing;

@@ -53,23 +53,83 @@ k_absprofile(PcCkd ckd, const double *__restrict__ userprofil, const double *__r
   }
 }
 
-// SOS_PROFILE: one thread per term (the levels of a profile are found one after the other, each by a bisection that starts from
-// the optical depth of the level above).  Arrays [nterm][PC_LEVELS].
-__global__ void __launch_bounds__(32)
+// The search strategy of the kernels: one warp per term.  SOS_DISC's bisection advances five levels per round (31 lanes
+// evaluate the candidates of a depth-5 subtree, pc_tree_walk reads the serial path off their results) and the first-level scan
+// 32 steps of CTE_DELTA_Z per round.  Every candidate is the double the serial loop would have tested (tests/profile_host.cpp
+// runs this strategy lane by lane on the host against the reference), so NT and the levels do not depend on the strategy; what
+// changes is the length of the dependent chain of FP64 exp / divide evaluations per profile: about 8000 -> 1200.
+struct PcWarp {
+  __host__ __device__ double disc(double dt, const PcColumn &c, double tim1, double zmax_init, double zlim) const
+  {
+#ifdef __CUDA_ARCH__
+    const int lane = threadIdx.x & 31;
+    const int node = lane ? lane : 1;                              // lane 0 repeats the root; bit 0 of the masks is never read
+    const int depth = 31 - __clz(node);
+    const double ti = tim1 + dt;
+    double zmax = zmax_init, zmin = zlim;
+    for (;;) {
+      double lo, hi;
+      pc_tree_interval(node, depth, zmin, zmax, &lo, &hi);
+      const double cand = (hi + lo) / 2.0;
+      const int r = pc_disc_step(c, ti, cand);
+      const unsigned stop = __ballot_sync(0xffffffffu, r & 1), dir = __ballot_sync(0xffffffffu, r & 2);
+      int n;
+      if (pc_tree_walk(stop, dir, &n)) return __shfl_sync(0xffffffffu, cand, n);
+      pc_tree_interval(n, 5, zmin, zmax, &zmin, &zmax);
+    }
+#else
+    (void)dt; (void)c; (void)tim1; (void)zmax_init; (void)zlim;
+    return 0.0;                                                    // never instantiated for the host
+#endif
+  }
+  __host__ __device__ void first(bool gas, const PcColumn &c, double t_first, double *z, double *dtau) const
+  {
+#ifdef __CUDA_ARCH__
+    if (!(0.0 < t_first)) return;
+    const int lane = threadIdx.x & 31;
+    double z0 = *z;
+    for (;;) {
+      double zz = z0;
+      for (int k = 0; k <= lane; ++k) zz = zz - PC_DELTA_Z;        // the reference's repeated subtraction, so the same doubles
+      const double d = gas ? pc_first_tau_gas(c, zz) : pc_first_tau_ng(c, zz);
+      const unsigned hit = __ballot_sync(0xffffffffu, !(d < t_first));
+      if (hit) {
+        const int l = __ffs(hit) - 1;
+        *z = __shfl_sync(0xffffffffu, zz, l);
+        *dtau = __shfl_sync(0xffffffffu, d, l);
+        return;
+      }
+      z0 = __shfl_sync(0xffffffffu, zz, 31);
+    }
+#else
+    (void)gas; (void)c; (void)t_first; (void)z; (void)dtau;
+#endif
+  }
+};
+
+// SOS_PROFILE: one warp per term, four terms per block; the 50-level gas tables of the block's terms sit in shared memory.
+// All lanes of a warp run the same (uniform) bookkeeping and store the same values.  Arrays [nterm][PC_LEVELS].
+#define PROF_WARPS 4
+__global__ void __launch_bounds__(PROF_WARPS * 32)
 k_profile(const ProfTermDev *__restrict__ terms, int nterm, const double *__restrict__ altabs, const double *__restrict__ tauabs,
           double *__restrict__ scratch, double *__restrict__ zprof, double *__restrict__ h, double *__restrict__ pcaer,
           double *__restrict__ pcmol, int *__restrict__ nt, int *__restrict__ ier)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double s_alt[PC_NLEV], s_tabs[PROF_WARPS][PC_NLEV];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * PROF_WARPS + w;
+  for (int k = threadIdx.x; k < PC_NLEV; k += blockDim.x) s_alt[k] = altabs[k];
+  if (i < nterm) for (int k = lane; k < PC_NLEV; k += 32) s_tabs[w][k] = tauabs[(size_t)i * PC_NLEV + k];
+  __syncthreads();
   if (i >= nterm) return;
-  if (ier[i] != 0) { nt[i] = 0; return; }
+  if (ier[i] != 0) { if (lane == 0) nt[i] = 0; return; }
   const ProfTermDev &t = terms[i];
   const size_t o = (size_t)i * PC_LEVELS;
   int n = 0;
-  const int rc = pc_profile(t.iprofil, t.tr, t.hr, t.ta, t.ha, t.zmin, t.zmax, t.absprofil, altabs, tauabs + (size_t)i * PC_NLEV,
-                            scratch + o, zprof + o, h + o, pcaer + o, pcmol + o, &n);
-  ier[i] = rc;
-  nt[i] = (rc == 0) ? n : 0;
+  const int rc = pc_profile(PcWarp(), t.iprofil, t.tr, t.hr, t.ta, t.ha, t.zmin, t.zmax, t.absprofil, s_alt, s_tabs[w], scratch + o,
+                            zprof + o, h + o, pcaer + o, pcmol + o, &n);
+  __syncwarp();
+  if (lane == 0) { ier[i] = rc; nt[i] = (rc == 0) ? n : 0; }
 }
 
 // The PROFIL_TMP text hop (format 20 written by SOS_PROFILE, read by SOS.F:511-516), elementwise over (term, level <= NT).
@@ -130,11 +190,16 @@ int run_chain(sosgpu_ctx *ctx, const sosgpu_ckd *ckd, const sosgpu_gas_profile *
   CK(sos_dmalloc(ctx, &d_tau, sizeof(double) * nterm * PC_NLEV)); guard.add(d_tau);
   CK(cudaMemcpyAsync(d_terms, ht.data(), sizeof(ProfTermDev) * nterm, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(d_ier, 0, sizeof(int) * nterm * 2, st));
+  bool timed = false;                                              // ev_a .. ev_b bracket the kernels of this call
   std::vector<double> packed;                                      // lives until the stream has consumed it
   std::vector<int> nexp_packed;
   double *d_atm = nullptr;                                         // [altabs 50 | userprofil 650 | ro 400]
   CK(sos_dmalloc(ctx, &d_atm, sizeof(double) * (PC_NLEV + PC_NLEV * PC_NCOL + PC_NBABS * PC_NLEV))); guard.add(d_atm);
-  if (altabs_host) CK(cudaMemcpyAsync(d_atm, altabs_host, sizeof(double) * PC_NLEV, cudaMemcpyHostToDevice, st));
+  if (altabs_host) {
+    for (int k = 1; k < PC_NLEV; ++k)                              // the level search is a bisection of this table
+      if (!(altabs_host[k] < altabs_host[k - 1])) { ctx->err = "profile chain: ALTABS must be strictly descending"; return SOSGPU_ERR_ARG; }
+    CK(cudaMemcpyAsync(d_atm, altabs_host, sizeof(double) * PC_NLEV, cudaMemcpyHostToDevice, st));
+  }
   if (ckd) {
     if (!atm || !atm->userprofil || !atm->ro || !ckd->tab_temp || !ckd->tab_pres || !ckd->tab_conc_h2o || !ckd->nexp || !ckd->kdis_ki ||
         !ckd->kdis_ki_h2o) { ctx->err = "profile chain: null table"; return SOSGPU_ERR_ARG; }
@@ -165,6 +230,8 @@ int run_chain(sosgpu_ctx *ctx, const sosgpu_ckd *ckd, const sosgpu_gas_profile *
     c.nb_temp = ckd->nb_temp; c.nb_pres = ckd->nb_pres; c.nb_conc = ckd->nb_conc_h2o;
     c.tab_temp = d_packed; c.tab_pres = d_packed + PC_NTMAX; c.tab_conc = d_packed + PC_NTMAX + PC_NPMAX;
     c.nexp = d_nexp; c.ki = d_packed + head; c.ki_h2o = d_packed + head + nl * KI_SLICE;
+    if (ctx->ev_a) cudaEventRecord(ctx->ev_a, st);
+    timed = true;
     k_absprofile<<<nterm, 64, 0, st>>>(c, d_atm + PC_NLEV, d_atm + PC_NLEV + PC_NLEV * PC_NCOL, d_terms, d_tau, d_ier);
     CK(cudaGetLastError());
     ctx->launches += 1;
@@ -179,7 +246,9 @@ int run_chain(sosgpu_ctx *ctx, const sosgpu_ckd *ckd, const sosgpu_gas_profile *
     if (!altabs_host || !nt || !zprof || !h || !pcaer || !pcmol) { ctx->err = "profile chain: null output"; return SOSGPU_ERR_ARG; }
     CK(sos_dmalloc(ctx, &d_prof, sizeof(double) * per * 5)); guard.add(d_prof);
     CK(cudaMemsetAsync(d_prof, 0, sizeof(double) * per * 5, st));
-    k_profile<<<(nterm + 31) / 32, 32, 0, st>>>(d_terms, nterm, d_atm, d_tau, d_prof, d_prof + per, d_prof + 2 * per, d_prof + 3 * per,
+    if (!timed && ctx->ev_a) cudaEventRecord(ctx->ev_a, st);
+    timed = true;
+    k_profile<<<(nterm + PROF_WARPS - 1) / PROF_WARPS, PROF_WARPS * 32, 0, st>>>(d_terms, nterm, d_atm, d_tau, d_prof, d_prof + per, d_prof + 2 * per, d_prof + 3 * per,
                                                 d_prof + 4 * per, d_nt, d_ier);
     CK(cudaGetLastError());
     ctx->launches += 1;
@@ -189,14 +258,17 @@ int run_chain(sosgpu_ctx *ctx, const sosgpu_ckd *ckd, const sosgpu_gas_profile *
       CK(cudaGetLastError());
       ctx->launches += 1;
     }
+    if (ctx->ev_b) cudaEventRecord(ctx->ev_b, st);
     CK(cudaMemcpyAsync(zprof, d_prof + per, sizeof(double) * per, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h, d_prof + 2 * per, sizeof(double) * per, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(pcaer, d_prof + 3 * per, sizeof(double) * per, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(pcmol, d_prof + 4 * per, sizeof(double) * per, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(nt, d_nt, sizeof(int) * nterm, cudaMemcpyDeviceToHost, st));
   }
+  if (!do_profile && timed && ctx->ev_b) cudaEventRecord(ctx->ev_b, st);
   CK(cudaMemcpyAsync(ier, d_ier, sizeof(int) * nterm, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (timed && ctx->ev_a && ctx->ev_b) cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);
   return SOSGPU_OK;
 }
 

@@ -50,11 +50,11 @@ def host_absprofile(host, t, user, ro, term):
     return rc, tau
 
 
-def host_profile(host, altabs, tabs, term, text_hop):
+def host_profile(host, altabs, tabs, term, text_hop, wide=0):
     z, h, pa, pm = (np.zeros(pc.NT_MAX + 1) for _ in range(4))
     nt = C.c_int(0)
     rc = host.pch_profile(term["iprofil"], C.c_double(term["tr"]), C.c_double(term["hr"]), C.c_double(term["ta"]), C.c_double(term["ha"]),
-                          C.c_double(term["zmin"]), C.c_double(term["zmax"]), term["absprofil"], _P(altabs), _P(tabs), text_hop,
+                          C.c_double(term["zmin"]), C.c_double(term["zmax"]), term["absprofil"], _P(altabs), _P(tabs), text_hop, wide,
                           C.byref(nt), _P(z), _P(h), _P(pa), _P(pm))
     return rc, nt.value, z, h, pa, pm
 
@@ -95,17 +95,19 @@ def test_absprofile_host_vs_reference(host, ref, seed):
     assert nstrong >= 5                                                    # the saturated branch of SOS_PROFILE gets inputs
 
 
+@pytest.mark.parametrize("wide", [0, 1])
 @pytest.mark.parametrize("seed", [0, 1, 2])
-def test_profile_host_vs_reference(host, ref, seed, tmp_path):
+def test_profile_host_vs_reference(host, ref, seed, wide, tmp_path):
     """SOS_PROFILE: same NT, and the PROFIL_TMP values SOS reads back are identical (the device functions with the text hop
-    against the reference's file)."""
+    against the reference's file).  wide = 1: the kernels' search strategy (31 bisection candidates / 32 first-level steps at
+    a time), emulated lane by lane, must take exactly the path of the reference's serial loops."""
     user, altabs, ro = pc.gas_atmosphere(seed)
     t = pc.ckd_tables(seed)
     cases = {"nogas": 0, "weak": 0, "strong": 0}
     for term in pc.make_terms(t, 150 if seed < 2 else 60, seed):
         _, tabs = refdirect.absprofile(ref, t, user, altabs, ro, term)
         ier, nt, text, z, h, pa, pm = refdirect.profile(ref, str(tmp_path), altabs, tabs, term)
-        rc, nt2, z2, h2, pa2, pm2 = host_profile(host, altabs, tabs, term, 1)
+        rc, nt2, z2, h2, pa2, pm2 = host_profile(host, altabs, tabs, term, 1, wide)
         assert (rc != 0) == (ier != 0), (term, rc, ier)
         if ier != 0:
             continue
