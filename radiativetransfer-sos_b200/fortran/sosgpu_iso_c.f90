@@ -35,6 +35,22 @@ module sosgpu_iso_c
     type(c_ptr)       :: zprof, h, pcaer, pcmol
   end type
 
+  type, bind(c) :: sosgpu_ckd               ! tables of READ_CKD_COEFF, Fortran storage (inc/SOS.h extents)
+    integer(c_int)    :: nb_temp, nb_pres, nb_conc_h2o
+    type(c_ptr)       :: tab_temp, tab_pres, tab_conc_h2o, nexp, kdis_ki, kdis_ki_h2o
+  end type
+
+  type, bind(c) :: sosgpu_gas_profile       ! ABS_USERPROFIL(50,13), ALTABS(50), RO(8,50)
+    type(c_ptr)       :: userprofil, altabs, ro
+  end type
+
+  type, bind(c) :: sosgpu_profile_term      ! one (wavelength, CKD term) of the profile chain
+    integer(c_int)    :: lamb1
+    integer(c_int)    :: ik(8)
+    integer(c_int)    :: absprofil, iprofil
+    real(c_double)    :: tr, hr, ta, ha, zmin, zmax
+  end type
+
   type, bind(c) :: sosgpu_term_out
     type(c_ptr) :: rec, n_fourier, n_scatter, stop_reason, emoins, eplus, ttot_tronc, ttot_vrai, tauout, ier
   end type
@@ -125,6 +141,19 @@ module sosgpu_iso_c
       type(c_ptr), value :: ctx, batch, up, down
       integer(c_int), value :: root, nphi, nmax
       integer(c_int), intent(in) :: groups_of_rank(*)
+    end function
+    ! SOS_ABSPROFILE -> SOS_PROFILE -> PROFIL_TMP round trip for nterm terms (SOS_PROC.F:3494-3537)
+    integer(c_int) function sosgpu_profile_chain(ctx, ckd, atm, terms, nterm, text_hop, tauabs, nt, zprof, h, pcaer, pcmol, ier) &
+        bind(c, name="sosgpu_profile_chain")
+      import :: c_ptr, c_int, c_double, sosgpu_ckd, sosgpu_gas_profile, sosgpu_profile_term
+      type(c_ptr), value :: ctx
+      type(sosgpu_ckd), intent(in) :: ckd
+      type(sosgpu_gas_profile), intent(in) :: atm
+      type(sosgpu_profile_term), intent(in) :: terms(*)
+      integer(c_int), value :: nterm, text_hop
+      type(c_ptr), value :: tauabs                     ! [50, nterm] or c_null_ptr
+      integer(c_int), intent(out) :: nt(*), ier(*)
+      real(c_double), intent(out) :: zprof(0:600,*), h(0:600,*), pcaer(0:600,*), pcmol(0:600,*)
     end function
     subroutine sosgpu_batch_free(ctx, batch) bind(c, name="sosgpu_batch_free")
       import :: c_ptr
