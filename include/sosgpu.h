@@ -247,6 +247,16 @@ int sosgpu_write_updown(const char *fic_up, const char *fic_down, int nbmu, int 
                         const double *phi_fin, const double *theta_fin, const double *up, const double *down, int nphi_cap,
                         int fix_sca_index);
 
+/* The optional transmission and flux files SOS_PROC writes after the synthesis (SOS_PROC.F:3779-3874, FORMAT :4944-4951); host-only.
+ * rmu / tdifmug: RMU(1:N), TDIFMUG(1:N).  zalt: ABS_USERPROFIL(1:50,1); tauabs: TAUABS(1:50) of the last term, as there.
+ * sosgpu_write_flux also returns TDIR_VRAI, FLUX_DIFF_DOWN, FLUX_DOWN (SOS_PROC outputs) and writes nothing for 'NO_OUTPUT'.
+ * The list-directed records follow gfortran's documented layout (unpinned: no Fortran compiler in the build environment). */
+int sosgpu_write_trans(const char *fictrans, double tetas, double ttot_tronc, double ttot_vrai, double tdifmus, int nbmu,
+                       const double *rmu, const double *tdifmug);
+int sosgpu_write_flux(const char *ficflux, double tetas, double ttot_tronc, double ttot_vrai, double emoins, double eplus,
+                      double tr, double hr, double ta, double ha, const double *zalt, const double *tauabs,
+                      double *tdir_vrai, double *flux_diff_down, double *flux_down);
+
 /* ---- the per-term profile chain that precedes every term-solve (SOS_PROC.F:3459-3537) ------------
  * For each (wavelength, CKD term): SOS_ABSPROFILE (SOS_ABSPROFILE.F:184-425, with COEFF_ABS_CKD SOS_SUB_TRS.F:171-393)
  * gives the gas optical thickness at the 50 levels of the gas atmosphere, SOS_PROFILE (SOS_PROFIL.F:224-1156, SOS_DISC :1210)

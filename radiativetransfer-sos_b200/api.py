@@ -145,6 +145,29 @@ def write_updown(fic_up, fic_down, nbmu, itrphi, phios, pas_phi, zout, phi_fin, 
         raise RuntimeError("sosgpu_write_updown failed (rc=%d)" % rc)
 
 
+def write_trans(fictrans, tetas, ttot_tronc, ttot_vrai, tdifmus, rmu_pos, tdifmug):
+    """The -SOS.Trans file of SOS_PROC.F:3779-3818 (rmu_pos = RMU(1:N), tdifmug = TDIFMUG(1:N)).  Host-only."""
+    lib = load_library()
+    rmu_pos, tdifmug = _f64(rmu_pos), _f64(tdifmug)
+    lib.sosgpu_write_trans.argtypes = [C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, c_dp, c_dp]
+    rc = lib.sosgpu_write_trans(str(fictrans).encode(), tetas, ttot_tronc, ttot_vrai, tdifmus, rmu_pos.size, _d(rmu_pos), _d(tdifmug))
+    if rc != SOSGPU_OK:
+        raise RuntimeError("sosgpu_write_trans failed (rc=%d)" % rc)
+
+
+def write_flux(ficflux, tetas, ttot_tronc, ttot_vrai, emoins, eplus, tr, hr, ta, ha, zalt, tauabs):
+    """The -SOS.Flux file of SOS_PROC.F:3820-3874; returns (TDIR_VRAI, FLUX_DIFF_DOWN, FLUX_DOWN).  Host-only."""
+    lib = load_library()
+    zalt, tauabs = _f64(zalt), _f64(tauabs)
+    out = [C.c_double(0) for _ in range(3)]
+    lib.sosgpu_write_flux.argtypes = [C.c_char_p] + [C.c_double] * 9 + [c_dp, c_dp] + [c_dp] * 3
+    rc = lib.sosgpu_write_flux(str(ficflux).encode(), tetas, ttot_tronc, ttot_vrai, emoins, eplus, tr, hr, ta, ha, _d(zalt), _d(tauabs),
+                               *[C.byref(o) for o in out])
+    if rc != SOSGPU_OK:
+        raise RuntimeError("sosgpu_write_flux failed (rc=%d)" % rc)
+    return tuple(o.value for o in out)
+
+
 class TermResults:
     """Per-term outputs of SOS / SOS_OS: Fourier records (file order Q,U,I), counts, fluxes, optical depths."""
     pass

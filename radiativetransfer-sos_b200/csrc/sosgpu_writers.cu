@@ -177,3 +177,95 @@ extern "C" int sosgpu_write_updown(const char *fic_up, const char *fic_down, int
   fclose(fu); fclose(fd);
   return ok ? SOSGPU_OK : SOSGPU_ERR_IER;
 }
+
+// ------------------------------------------------------------------------------------------------
+// The two optional ASCII files SOS_PROC writes after the synthesis (SOS_PROC.F:3779-3874): transmissions (-SOS.Trans) and
+// fluxes (-SOS.Flux).  The formatted records follow FORMAT 1005 / 1006 / 1010 / 2010 / 2016-2018 / 2020 (:4944-4951).  The
+// list-directed records (WRITE(u,*)) are laid out as gfortran lays them out -- one leading blank, character items as they are,
+// a REAL*8 item as a separator blank + G25.17E3 (F form between 0.1 and 1e17: right-justified in 20 columns + 5 blanks, else
+// 1PE25.17E3) -- from the documented rules, not from a run: there is no Fortran compiler here to pin those few lines against.
+namespace {
+std::string list_real8(double x)
+{
+  char b[80];
+  const double ax = std::fabs(x);
+  if (x == 0.0) return std::string("   0.0000000000000000     ");
+  if (ax >= 0.1 && ax < 1e17) {                                    // F editing: 17 significant digits
+    snprintf(b, sizeof b, "%.16e", ax);
+    const int k = atoi(strchr(b, 'e') + 1) + 1;                     // 10^(k-1) <= ax < 10^k after rounding to 17 digits
+    snprintf(b, sizeof b, "%s%.*f", x < 0 ? "-" : "", 17 - k, ax);
+    std::string f(b);
+    if (f.size() < 20) f = std::string(20 - f.size(), ' ') + f;
+    return " " + f + "     ";
+  }
+  snprintf(b, sizeof b, "%.16E", ax);                              // d.ddddddddddddddddE+ee -> three exponent digits
+  char *e = strchr(b, 'E');
+  const int ex = atoi(e + 1);
+  *e = 0;
+  char out[96];
+  snprintf(out, sizeof out, "%s%sE%c%03d", x < 0 ? "-" : "", b, ex < 0 ? '-' : '+', abs(ex));
+  std::string f(out);
+  if (f.size() < 25) f = std::string(25 - f.size(), ' ') + f;
+  return " " + f;
+}
+}  // namespace
+
+extern "C" int sosgpu_write_trans(const char *fictrans, double tetas, double ttot_tronc, double ttot_vrai, double tdifmus, int nbmu,
+                                  const double *rmu, const double *tdifmug)
+{
+  if (!fictrans || !rmu || !tdifmug || nbmu < 1) return SOSGPU_ERR_ARG;
+  FILE *f = fopen(fictrans, "w");
+  if (!f) return SOSGPU_ERR_IER;
+  const double pi = std::acos(-1.0);
+  double tdir_tronc = std::exp(-ttot_tronc / std::cos(pi * tetas / 180.0));
+  double tdir_vrai = std::exp(-ttot_vrai / std::cos(pi * tetas / 180.0));
+  fprintf(f, "Solar Zenith Angle : %s\n", ff(tetas, 7, 3).c_str());
+  fprintf(f, "Direct transmission TOA -> surface : %s\n", ff(tdir_vrai, 8, 4).c_str());
+  fprintf(f, "  \n");
+  fprintf(f, " Diffuse transmittance : TOA -> surface\n");
+  fprintf(f, "    thetas = %s   td(thetas) = %s\n", ff(tetas, 6, 3).c_str(), ff(tdifmus + tdir_tronc - tdir_vrai, 7, 4).c_str());
+  fprintf(f, "  \n");
+  fprintf(f, " Diffuse transmittance : surface -> TOA\n");
+  for (int j = 1; j <= nbmu; ++j) {                                // rmu[j-1] = RMU(J), tdifmug[j-1] = TDIFMUG(J)
+    tdir_tronc = std::exp(-ttot_tronc / rmu[j - 1]);
+    tdir_vrai = std::exp(-ttot_vrai / rmu[j - 1]);
+    fprintf(f, "    thetav = %s   td(thetav) = %s\n", ff(std::acos(rmu[j - 1]) * 180.0 / pi, 6, 3).c_str(),
+            ff(tdifmug[j - 1] + tdir_tronc - tdir_vrai, 7, 4).c_str());
+  }
+  return fclose(f) == 0 ? SOSGPU_OK : SOSGPU_ERR_IER;
+}
+
+extern "C" int sosgpu_write_flux(const char *ficflux, double tetas, double ttot_tronc, double ttot_vrai, double emoins, double eplus,
+                                 double tr, double hr, double ta, double ha, const double *zalt, const double *tauabs,
+                                 double *tdir_vrai_out, double *flux_diff_down_out, double *flux_down_out)
+{
+  const double pi = std::acos(-1.0);
+  const double tdir_tronc = std::exp(-ttot_tronc / std::cos(pi * tetas / 180.0));
+  const double tdir_vrai = std::exp(-ttot_vrai / std::cos(pi * tetas / 180.0));
+  const double flux_diff_down = emoins + tdir_tronc - tdir_vrai, flux_down = emoins + tdir_tronc;
+  if (tdir_vrai_out) *tdir_vrai_out = tdir_vrai;                   // SOS_PROC returns them whether or not the file is written
+  if (flux_diff_down_out) *flux_diff_down_out = flux_diff_down;
+  if (flux_down_out) *flux_down_out = flux_down;
+  if (!ficflux || strcmp(ficflux, "NO_OUTPUT") == 0) return SOSGPU_OK;
+  if (!zalt || !tauabs) return SOSGPU_ERR_ARG;
+  FILE *f = fopen(ficflux, "w");
+  if (!f) return SOSGPU_ERR_IER;
+  fprintf(f, "Solar Zenith Angle : %s\n", ff(tetas, 7, 3).c_str());
+  fprintf(f, "  \n");
+  fprintf(f, " Downward fluxes at BOA (normalized by TOA solar flux)\n");
+  fprintf(f, "   - Downward direct flux at BOA : %s\n", ff(tdir_vrai, 9, 5).c_str());
+  fprintf(f, "   - Downward diffuse flux at BOA: %s\n", ff(flux_diff_down, 9, 5).c_str());
+  fprintf(f, "   ==> Downward total flux at BOA: %s\n", ff(flux_down, 9, 5).c_str());
+  fprintf(f, "  \n");
+  fprintf(f, " Upward diffuse flux at TOA (normalized by TOA solar flux):%s\n", list_real8(eplus).c_str());
+  fprintf(f, "\n\n");
+  fprintf(f, " According to the following profile\n");
+  fprintf(f, " Z(km)    MOT     AOT     GOT     TOTAL\n");
+  for (int i = 50; i >= 1; --i) {                                  // zalt[i-1] = ABS_USERPROFIL(I,1); tauabs[50-i] = TAUABS(51-I)
+    const double z = zalt[i - 1];
+    const double tr_z = tr * std::exp(-z / hr), ta_z = ta * std::exp(-z / ha), tg_z = tauabs[50 - i];
+    fprintf(f, "%s  %s %s %s %s\n", ff(z, 7, 2).c_str(), ff(tr_z, 7, 4).c_str(), ff(ta_z, 7, 4).c_str(), ff(tg_z, 7, 4).c_str(),
+            ff(tr_z + ta_z + tg_z, 7, 4).c_str());
+  }
+  return fclose(f) == 0 ? SOSGPU_OK : SOSGPU_ERR_IER;
+}

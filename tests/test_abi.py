@@ -56,7 +56,8 @@ def test_ctypes_structs_match_header(tmp_path):
     import subprocess
     api = importlib.import_module("radiativetransfer-sos_b200.api")
     pairs = {"sosgpu_optics": api.COptics, "sosgpu_term": api.CTerm, "sosgpu_term_out": api.CTermOut,
-             "sosgpu_group_out": api.CGroupOut, "sosgpu_stats": api.CStats}
+             "sosgpu_group_out": api.CGroupOut, "sosgpu_stats": api.CStats, "sosgpu_direct_models": api.CDirectModels,
+             "sosgpu_ckd": api.CCkd, "sosgpu_gas_profile": api.CGasProfile, "sosgpu_profile_term": api.CProfileTerm}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sosgpu.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
@@ -109,3 +110,14 @@ def test_gfortran_shims_refuse_without_gpu(tmp_path):
                 ip(0), ip(0), dp(1.34), P(h), P(zero), P(zero + 1), P(zero), dp(0.0279), P(co), P(co), P(co), P(co),
                 dp(-1.0), ip(10), ip(2), ip(1), ip(0), ip(6), C.byref(em), C.byref(ep), C.byref(ier), L500, L500)
     assert ier.value == -1 and not os.path.exists(str(tmp_path / "OS.bin"))
+    # the profile chain: SOS_PROFILE / SOS_ABSPROFILE shims (INTEGER*2 arguments are short)
+    sp = lambda v: C.byref(C.c_short(v))
+    altabs, tabs = np.linspace(120.0, 0.0, 50), np.zeros(50)
+    nt, ier = C.c_int(0), C.c_int(0)
+    prof = str(tmp_path / "PROFIL.txt")
+    lib.sos_profile_(sp(1), dp(0.1), dp(8.0), dp(0.2), dp(2.0), dp(0.0), dp(0.0), sp(7), P(altabs), P(tabs), ip(0), ip(0),
+                     fstr(prof), C.byref(nt), C.byref(ier), L500)
+    assert ier.value == -1 and not os.path.exists(prof)
+    assert lib.sosgpu_profile_chain(None, None, None, None, 1, 1, None, None, None, None, None, None, None) == api.SOSGPU_ERR_NO_DEVICE
+    assert lib.sosgpu_absprofile(None, None, None, None, 1, None, None) == api.SOSGPU_ERR_NO_DEVICE
+    assert lib.sosgpu_profile(None, None, None, None, 1, 1, None, None, None, None, None, None) == api.SOSGPU_ERR_NO_DEVICE

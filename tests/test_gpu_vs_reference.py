@@ -354,3 +354,40 @@ def test_profile_chain_feeds_the_solver(pkg, solver, ref, tmp_path):
         assert not bad
     finally:
         b.free()
+
+
+def test_profile_shims_write_the_reference_file(pkg, ref, tmp_path):
+    """The gfortran-ABI symbols sos_absprofile_ / sos_profile_ of libsosgpu.so (INTEGER*2 arguments, hidden string length,
+    PROFIL_TMP written with format 20): the file is the reference's file byte for byte."""
+    import ctypes as C
+    import profile_cases as pc
+    import importlib
+    lib = importlib.import_module("radiativetransfer-sos_b200.api").load_library()
+    user, altabs, ro = pc.gas_atmosphere(5)
+    t = pc.ckd_tables(5)
+    ip, dp, sp = (lambda v: C.byref(C.c_int(v))), (lambda v: C.byref(C.c_double(v))), (lambda v: C.byref(C.c_short(v)))
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    nsame = 0
+    terms = pc.make_terms(t, 16, 5)
+    for term in terms:
+        ier_r, tau_r = refdirect.absprofile(ref, t, user, altabs, ro, term)
+        tau, ier = np.zeros(50), C.c_int(99)
+        iabs = np.ones(8, dtype=np.int16)
+        lib.sos_absprofile_(sp(term["absprofil"]), dp(13000.0), ip(term["lamb1"]), iabs.ctypes.data_as(C.POINTER(C.c_short)), P(user),
+                            P(altabs), P(ro), t["nexp"].ctypes.data_as(C.POINTER(C.c_int)), P(t["ki"]), P(t["kh"]),
+                            *[ip(v) for v in term["ik"]], P(t["tab_pres"]), ip(t["nb_pres"]), P(t["tab_temp"]), ip(t["nb_temp"]),
+                            P(t["tab_conc"]), ip(t["nb_conc"]), P(tau), ip(0), ip(0), C.byref(ier))
+        assert ier.value == 0 and ier_r == 0
+        np.testing.assert_allclose(tau, tau_r, rtol=1e-13, atol=1e-300)
+        _, nt_r, text_r, *_ = refdirect.profile(ref, str(tmp_path), altabs, tau_r, term)
+        f = str(tmp_path / "PROFIL_GPU.txt")
+        nt, ier = C.c_int(0), C.c_int(99)
+        lib.sos_profile_(sp(term["iprofil"]), dp(term["tr"]), dp(term["hr"]), dp(term["ta"]), dp(term["ha"]), dp(term["zmin"]),
+                         dp(term["zmax"]), sp(term["absprofil"]), P(altabs), P(tau_r), ip(0), ip(0),
+                         C.create_string_buffer(f.encode().ljust(500), 500), C.byref(nt), C.byref(ier), C.c_size_t(500))
+        assert ier.value == 0 and nt.value == nt_r
+        text = open(f, "rb").read()
+        assert len(text) == len(text_r)
+        nsame += text == text_r
+    print("\n[PROFIL_TMP] files byte-identical to the reference's: %d / %d" % (nsame, len(terms)))
+    assert nsame >= len(terms) - 1

@@ -73,3 +73,52 @@ def test_updown_view2_bytes(pkg, tmp_path, tag, zout, pas):
     api.write_updown(fu, fd, N, 2, 0.0, pas, zout, phi, theta, up, down, fix_sca_index=True)
     line = open(fu).read().splitlines()[-1]
     assert line.split()[2] == fm.fortran_f(up[0, nphi - 1, N - 1], 7, 2).strip()
+
+
+def _F(x, w, d):
+    s = "%*.*f" % (w, d, x)
+    return s if len(s) <= w else "*" * w
+
+
+def test_trans_and_flux_files(tmp_path):
+    """-SOS.Trans / -SOS.Flux (SOS_PROC.F:3779-3874): the formatted records against an independent rendering of FORMAT
+    1005 / 1006 / 1010 / 2010 / 2016-2018 / 2020 (:4944-4951); the list-directed records against gfortran's layout rules
+    for a few known values (documented behaviour: `print *, 0.1d0` gives `  0.10000000000000001     `)."""
+    api = importlib.import_module("radiativetransfer-sos_b200.api")
+    rng = np.random.default_rng(3)
+    N = 24
+    rmu = np.sort(rng.uniform(0.02, 1.0, N))
+    tdg = rng.uniform(0.0, 0.3, N)
+    tetas, tt, tv, tds = 32.5, 0.4123, 0.4671, 0.0934
+    ft = str(tmp_path / "SOS_Trans.txt")
+    api.write_trans(ft, tetas, tt, tv, tds, rmu, tdg)
+    pi = np.arccos(-1.0)
+    mus = np.cos(pi * tetas / 180.0)
+    want = ["Solar Zenith Angle : " + _F(tetas, 7, 3), "Direct transmission TOA -> surface : " + _F(np.exp(-tv / mus), 8, 4), "  ",
+            " Diffuse transmittance : TOA -> surface",
+            "    thetas = " + _F(tetas, 6, 3) + "   td(thetas) = " + _F(tds + np.exp(-tt / mus) - np.exp(-tv / mus), 7, 4), "  ",
+            " Diffuse transmittance : surface -> TOA"]
+    for j in range(N):
+        want.append("    thetav = " + _F(np.degrees(np.arccos(rmu[j])), 6, 3) + "   td(thetav) = "
+                    + _F(tdg[j] + np.exp(-tt / rmu[j]) - np.exp(-tv / rmu[j]), 7, 4))
+    assert open(ft).read().split("\n") == want + [""]
+    z = np.concatenate([np.arange(0, 25.0), np.arange(25.0, 50.0, 2.5), np.arange(50.0, 121.0, 5.0)])
+    tau = np.linspace(0.0, 0.83, 50)
+    ff = str(tmp_path / "SOS_Flux.txt")
+    for eplus, shown in ((0.1, "  0.10000000000000001     "), (1.5, "   1.5000000000000000     "), (0.0876, "   8.7599999999999997E-002"),
+                         (0.25, "  0.25000000000000000     ")):
+        tdv, fdd, fd = api.write_flux(ff, tetas, tt, tv, 0.2, eplus, 0.05, 8.0, 0.2, 2.0, z, tau)
+        assert (tdv, fdd, fd) == (np.exp(-tv / mus), 0.2 + np.exp(-tt / mus) - np.exp(-tv / mus), 0.2 + np.exp(-tt / mus))
+        got = open(ff).read().split("\n")
+        assert got[:7] == ["Solar Zenith Angle : " + _F(tetas, 7, 3), "  ", " Downward fluxes at BOA (normalized by TOA solar flux)",
+                           "   - Downward direct flux at BOA : " + _F(tdv, 9, 5), "   - Downward diffuse flux at BOA: " + _F(fdd, 9, 5),
+                           "   ==> Downward total flux at BOA: " + _F(fd, 9, 5), "  "]
+        assert got[7] == " Upward diffuse flux at TOA (normalized by TOA solar flux):" + shown
+        assert got[8:12] == ["", "", " According to the following profile", " Z(km)    MOT     AOT     GOT     TOTAL"]
+        for n, i in enumerate(range(50, 0, -1)):
+            a, b, c = 0.05 * np.exp(-z[i - 1] / 8.0), 0.2 * np.exp(-z[i - 1] / 2.0), tau[50 - i]
+            assert got[12 + n] == _F(z[i - 1], 7, 2) + "  " + " ".join(_F(v, 7, 4) for v in (a, b, c, a + b + c))
+        assert got[62:] == [""]
+    # 'NO_OUTPUT' writes nothing and still returns the three scalars SOS_PROC hands back
+    assert api.write_flux("NO_OUTPUT", tetas, tt, tv, 0.2, 0.1, 0.05, 8.0, 0.2, 2.0, z, tau)[0] == np.exp(-tv / mus)
+    assert not os.path.exists("NO_OUTPUT")
