@@ -316,7 +316,7 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = solver.launches
-    st_acc = {"flops": 0.0, "step_ms": 0.0, "step_launches": 0, "steps": 0, "bytes": 0.0, "total_ms": 0.0}
+    st_acc = {"flops": 0.0, "step_ms": 0.0, "step_launches": 0, "steps": 0, "bytes": 0.0, "total_ms": 0.0, "useful_flops": 0.0}
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -420,8 +420,10 @@ def main():
                          "traffic_source": NCU_TRAFFIC_SOURCE,
                          "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 "
                                         "entry)",
-                         "algorithmic": "2*(6N)^2*(NT+1) FLOP per (term, Fourier order, scattering order>=2), only orders "
-                                        "the reference computes too (orders past a Fourier stop are not counted)",
+                         "algorithmic": "2*(6N)^2*(NT+1) FLOP per (term, Fourier order, scattering order>=2) launched; a wave "
+                                        "solves 8 Fourier orders at once, useful_frac is the share spent on orders the terms keep "
+                                        "(s < n_fourier), the rest is computed past the Fourier stop and discarded",
+                         "useful_frac": st_acc["useful_flops"] / st_acc["flops"] if st_acc["flops"] else None,
                          "kernel_ms_per_step": st_acc["step_ms"] / args.steps,
                          "kernel_launches_per_step": st_acc["step_launches"] / args.steps,
                          "kernel_share_of_step": st_acc["step_ms"] / max(st_acc["total_ms"], 1e-9),

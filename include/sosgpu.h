@@ -146,6 +146,8 @@ typedef struct {
   long long steps; double flops; double bytes; double step_ms; long long step_launches;
   double total_ms; long long launches;
   double aggregate_ms;      /* device ms of the CKD aggregation kernel (SOS_AGGREGATE), CUDA events */
+  double useful_flops;      /* the part of `flops` spent on Fourier orders the term ends up keeping (s < n_fourier): a wave
+                               solves several orders at once, those past the Fourier stop are computed and discarded */
 } sosgpu_stats;
 int  sosgpu_batch_stats(const sosgpu_batch *batch, sosgpu_stats *st);
 

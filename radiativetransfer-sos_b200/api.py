@@ -76,7 +76,7 @@ NT_MAX = 600
 class CStats(C.Structure):
     _fields_ = [("steps", C.c_longlong), ("flops", C.c_double), ("bytes", C.c_double), ("step_ms", C.c_double),
                 ("step_launches", C.c_longlong), ("total_ms", C.c_double), ("launches", C.c_longlong),
-                ("aggregate_ms", C.c_double)]
+                ("aggregate_ms", C.c_double), ("useful_flops", C.c_double)]
 
 
 _lib = None

@@ -484,6 +484,8 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
   const int nterm = b->nterm;
   const size_t per = (size_t)b->rs_dev * 3 * b->w_dev;
   b->stats = sosgpu_stats{};
+  struct ItemFlops { int term, is; double flops; };
+  std::vector<ItemFlops> item_flops;                             // for stats.useful_flops, once the Fourier counts are final
   b->reduced = false;
   CK(cudaEventRecord(b->evt0, st));
   CK(cudaMemsetAsync(b->d_rec, 0, (size_t)nterm * per * sizeof(double), st));
@@ -747,8 +749,10 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
       const HostOptics &ho = b->ho[ht.optics];
       const long long steps = std::max(0, items[i].n - 1);
       b->stats.steps += steps;
-      b->stats.flops += (double)steps * 2.0 * (6.0 * ho.N) * (6.0 * ho.N) * (ht.nt + 1);
+      const double fl = (double)steps * 2.0 * (6.0 * ho.N) * (6.0 * ho.N) * (ht.nt + 1);
+      b->stats.flops += fl;
       b->stats.bytes += (double)steps * 96.0 * ho.N * (ht.nt + 1);
+      if (steps > 0) item_flops.push_back({items[i].term, items[i].is, fl});
     }
     s0 = s1;
   }
@@ -767,6 +771,11 @@ static int run_impl(sosgpu_ctx *ctx, sosgpu_batch *b, double *jdump_dev, int for
   CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
   b->stats.aggregate_ms = ms;
   b->stats.launches = ctx->launches;
+  {                                                              // work on Fourier orders the terms kept
+    std::vector<int> nf(nterm);
+    CK(cudaMemcpy(nf.data(), b->d_nf, nterm * sizeof(int), cudaMemcpyDeviceToHost));
+    for (const ItemFlops &f : item_flops) if (f.is < nf[f.term]) b->stats.useful_flops += f.flops;
+  }
   return SOSGPU_OK;
 }
 
