@@ -68,9 +68,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None):
+        """Samples taken at or after t_begin (the start of the timed region).  nvidia-smi needs a few hundred ms to deliver
+        its first line, so the sampler is started during the warm-up steps (same kernels, same load); when the timed region is
+        too short to hold a sample of its own, the samples of the last warm-up steps stand in and `window` says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -80,7 +83,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if t_begin is None or t >= t_begin]
+        window = "timed region"
+        if not inside:
+            inside, window = [r for _, r in self.rows[-8:]], "last warm-up steps (timed region shorter than one nvidia-smi sample)"
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -89,7 +96,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_baseline(wl, budget_s=20.0, max_threads=None):
@@ -309,11 +316,13 @@ def main():
         solver.run(batch, want_terms=False, want_groups=False, part_only=args.shard == "terms" and world > 1)
         finish(batch, False)
 
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local)
+    for w in range(args.warmup):
+        if rank == 0 and w == max(0, args.warmup - 2):     # running before the timed region starts (see ClockSampler.stop)
+            sampler.start()
         step_resident()
     sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and sampler.proc is None:
         sampler.start()
     l0 = solver.launches
     st_acc = {"flops": 0.0, "step_ms": 0.0, "step_launches": 0, "steps": 0, "bytes": 0.0, "total_ms": 0.0, "useful_flops": 0.0}
@@ -334,7 +343,7 @@ def main():
     dev_ms, wall_ms = float(dev_ms[0]), float(dev_ms[1])
     # the barrier-to-barrier wall clock bounds the device time from above; report the conservative one
     step_ms = max(dev_ms, wall_ms) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t0) if rank == 0 else None
 
     # ---- e2e: host buffers in, host buffers out, every step ----
     e2e_steps = max(1, min(args.steps, 3))

@@ -130,7 +130,8 @@ __global__ void k_glitter(GlitterParams p, float *__restrict__ surf, int *__rest
     for (int is = 1; is <= NM; ++is) {
       t1 = t1 + 2 * G[is];
       const double b1 = fabs(t1 - gmax) / gmax;
-      if (!(b1 > (double)0.001f) && p.gmodel != 3) { il = is; break; }   // SOS_GSF_MAIGNAN never leaves the loop: IL = OS_NM
+      if (!(b1 > (double)0.001f)) { il = is; break; }           // same cut in SOS_GSF (:664-679) and SOS_GSF_MAIGNAN (SOS_SURFACE_BPDF.F:1497-1502);
+                                                                // Maignan's cusped G rarely converges to 1e-3 below OS_NM, but some pairs do
     }
     s_il = il;
     if (il_out) il_out[pair] = il;

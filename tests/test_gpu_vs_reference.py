@@ -210,8 +210,8 @@ def test_land_surface_files_roujean_breon(pkg, solver, ref, tmp_path):
         b = solver.surface_bpdf(isurf, N, rmu, ga, 1.5, os_nb, os_ns, os_nb + os_ns, coef_c=6.0)
         same_b = np.mean(b.view(np.uint32) == b_ref.view(np.uint32))
         print("[BPDF isurf=%d] REAL*4 records bit-identical: %.4f %%" % (isurf, 100 * same_b))
-        # Maignan keeps all OS_NM+1 orders of its G series (no cut), down to rounding noise: more 1-ulp(float) rounding ties
-        assert same_b > (0.98 if isurf == 7 else 0.999), isurf
+        # Maignan's cusped G keeps (nearly) all OS_NM+1 orders of its series, down to rounding noise: more 1-ulp(float) ties
+        assert same_b > (0.995 if isurf == 7 else 0.999), isurf
         assert np.abs(b - b_ref).max() <= 2e-7 * np.abs(b_ref).max()
     s_ref = refdirect.bpdf_ajout_brdf(ref, fm, str(tmp_path), b_ref, rj_ref)
     s_gpu = solver.bpdf_ajout_brdf(b, rj)
