@@ -208,10 +208,13 @@ def test_land_surface_files_roujean_breon(pkg, solver, ref, tmp_path):
     for isurf in (7, 4, 5):                                  # Maignan (C = 6), Rondeaux, Breon (the last one is used below)
         b_ref = refdirect.surface_bpdf(ref, fm, str(tmp_path), isurf, N, rmu, ga, 1.5, os_nb, os_ns, os_nb + os_ns, coef_c=6.0)
         b = solver.surface_bpdf(isurf, N, rmu, ga, 1.5, os_nb, os_ns, os_nb + os_ns, coef_c=6.0)
-        same_b = np.mean(b.view(np.uint32) == b_ref.view(np.uint32))
-        print("[BPDF isurf=%d] REAL*4 records bit-identical: %.4f %%" % (isurf, 100 * same_b))
-        # Maignan's cusped G keeps (nearly) all OS_NM+1 orders of its series, down to rounding noise: more 1-ulp(float) ties
-        assert same_b > (0.995 if isurf == 7 else 0.999), isurf
+        eq = b.view(np.uint32) == b_ref.view(np.uint32)
+        sig = np.abs(b_ref) > 1e-6 * np.abs(b_ref).max()
+        print("[BPDF isurf=%d] REAL*4 records bit-identical: %.4f %% of all entries, %.4f %% of those above 1e-6 of the largest; "
+              "max |diff| / max %.1e" % (isurf, 100 * eq.mean(), 100 * eq[sig].mean(), np.abs(b - b_ref).max() / np.abs(b_ref).max()))
+        # Maignan's cusped G keeps (nearly) all OS_NM+1 orders of its series; the high output orders are cancellation noise of
+        # about 1e-15 (against 0.03), where the last bits are arbitrary on either side: 1 % of the entries, none above 1e-6 of max
+        assert eq[sig].mean() > 0.999 and eq.mean() > (0.98 if isurf == 7 else 0.999), isurf
         assert np.abs(b - b_ref).max() <= 2e-7 * np.abs(b_ref).max()
     s_ref = refdirect.bpdf_ajout_brdf(ref, fm, str(tmp_path), b_ref, rj_ref)
     s_gpu = solver.bpdf_ajout_brdf(b, rj)
