@@ -1,0 +1,151 @@
+"""Multi-wavelength front end over the C ABI: what SOS_PROC does for ONE wavelength (SOS_PROC.F:3340-3874) --
+CKD term list and weights, per-term gas and scattering profiles, one term-solve per CKD term, CKD aggregation, azimuth
+synthesis, result files -- done for a LIST of wavelengths with every stage batched on the device:
+
+    CKD terms + AIK      enumerate_ckd_terms          the eight nested loops of SOS_PROC.F:3459-3487, host (a few integers)
+    profiles             Solver.profile_chain         SOS_ABSPROFILE -> SOS_PROFILE -> PROFIL_TMP hop, all terms at once
+    term-solves + sum    Solver.upload / run          SOS + SOS_OS + SOS_AGGREGATE, all terms of all wavelengths at once
+    synthesis            Solver.batch_trphi           SOS_TRPHI_OPTION, all wavelengths at once
+    transmissions        Solver.transmissions         the -SOS.Trans solves of SOS.F:605-637 (optional)
+    files                write_updown / write_trans / write_flux / formats.write_result_bin, one directory per wavelength
+
+Keyword parsing (SOS_ABS_MAIN.F) and the aerosol / Mie preparation (SOS_PREPA_OS) stay with the caller: a wavelength arrives as
+the optics SOS_PREPA_OS would hand to SOS plus the scalars of the profile.  No CPU fallback: Solver() raises without a GPU."""
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import api, formats
+from .synth import Optics, Term, Workload
+
+NBABS = 8
+
+
+@dataclass
+class Wavelength:
+    """One spectral point of the band."""
+    optics: Optics                  # outputs of SOS_PREPA_OS for this wavelength + the per-run scalars of the SOS call
+    lamb1: int                      # index of its spectral interval in the CKD tables (1-based, SOS_PREPA_ABSPROFILE)
+    tr: float                       # Rayleigh optical thickness
+    ta: float                       # aerosol optical thickness
+    hr: float = 8.0
+    ha: float = 2.0
+    absprofil: int = 2              # 7: no gaseous absorption
+    iprofil: int = 1
+    zmin: float = 0.0
+    zmax: float = 0.0
+    name: str = ""
+
+
+@dataclass
+class BandResult:
+    nterm: List[int] = field(default_factory=list)         # CKD terms per wavelength
+    nt: Optional[np.ndarray] = None                        # levels per term
+    groups: object = None                                  # api.GroupResults (CKD-summed Fourier coefficients, fluxes, taus)
+    nphi: int = 0
+    up: Optional[np.ndarray] = None                        # [nwave, 7, nphi, N]
+    down: Optional[np.ndarray] = None
+    tdifmus: Optional[np.ndarray] = None                   # [nwave]
+    tdifmug: Optional[np.ndarray] = None                   # [nwave, N]
+    dirs: List[str] = field(default_factory=list)
+
+
+def enumerate_ckd_terms(nexp, kdis_ai, lamb1):
+    """The CKD terms of one spectral interval in the reference's loop order (IK1 outermost .. IK8 innermost,
+    SOS_PROC.F:3459-3466) with their weights AIK = prod_k KDIS_AI(IKk, k, LAMB1) / sum (:3481-3489).
+    nexp: NEXP(8, 50); kdis_ai: KDIS_AI(5, 8, 50), Fortran order.  Raises where the reference stops (|sum - 1| >= 1e-6)."""
+    n = [int(nexp[k, lamb1 - 1]) for k in range(NBABS)]
+    iks, aik = [], []
+    idx = [1] * NBABS
+    total = int(np.prod(n))
+    for _ in range(total):
+        a = kdis_ai[idx[0] - 1, 0, lamb1 - 1]
+        for k in range(1, NBABS):                            # left to right as the Fortran product
+            a = a * kdis_ai[idx[k] - 1, k, lamb1 - 1]
+        iks.append(tuple(idx))
+        aik.append(float(a))
+        for k in range(NBABS - 1, -1, -1):                   # IK8 fastest
+            idx[k] += 1
+            if idx[k] <= n[k]:
+                break
+            idx[k] = 1
+    s = 0.0
+    for a in aik:
+        s = s + a
+    if abs(s - 1.0) >= 1e-6:                                 # SOS_PROC.F:3410
+        raise ValueError("CKD weights of interval %d sum to %.9f" % (lamb1, s))
+    return iks, [a / s for a in aik]
+
+
+def run_band(solver, tables, kdis_ai, userprofil, altabs, ro, waves, itrphi=1, phios=0.0, pas_phi=30, outdir=None,
+             trans=False, flux=False):
+    """Runs the band.  tables: CKD tables as READ_CKD_COEFF fills them (dict, Fortran-ordered: nb_temp, nb_pres, nb_conc,
+    tab_temp, tab_pres, tab_conc, nexp, ki, kh); kdis_ai: KDIS_AI(5,8,50); userprofil / altabs / ro: the gas atmosphere of
+    SOS_PREPA_ABSPROFILE.  With outdir, wavelength w gets outdir/<name or index>/SOS_Up.txt, SOS_Down.txt, SOS_Result.bin and,
+    on request, SOS_Trans.txt / SOS_Flux.txt."""
+    res = BandResult()
+    pterms, aiks, owner = [], [], []
+    for w, wv in enumerate(waves):
+        if wv.absprofil == 7:
+            iks, aik = [(1,) * NBABS], [1.0]
+        else:
+            iks, aik = enumerate_ckd_terms(tables["nexp"], kdis_ai, wv.lamb1)
+        res.nterm.append(len(iks))
+        for ik, a in zip(iks, aik):
+            pterms.append(dict(lamb1=wv.lamb1, ik=ik, absprofil=wv.absprofil, iprofil=wv.iprofil, tr=wv.tr, hr=wv.hr, ta=wv.ta,
+                               ha=wv.ha, zmin=wv.zmin, zmax=wv.zmax))
+            aiks.append(a)
+            owner.append(w)
+    # ---- per-term profiles (device) ----
+    nt, z, h, pa, pm, ier, tau = solver.profile_chain(tables, userprofil, altabs, ro, pterms, text_hop=True, want_tauabs=True)
+    if ier.any():
+        bad = int(np.flatnonzero(ier)[0])
+        raise RuntimeError("profile chain: term %d of wavelength %d failed with code %d" % (bad, owner[bad], int(ier[bad])))
+    res.nt = nt
+    # ---- term-solves, CKD sums, synthesis (device) ----
+    wl = Workload("band")
+    wl.optics = [wv.optics for wv in waves]
+    for i, w in enumerate(owner):
+        n = int(nt[i]) + 1
+        wl.terms.append(Term(w, aiks[i], z[i, :n].copy(), h[i, :n].copy(), pa[i, :n].copy(), pm[i, :n].copy()))
+    batch = solver.upload(wl, groups=owner, ngroup=len(waves))
+    try:
+        _, gr = solver.run(batch, want_terms=False, want_groups=True)
+        res.groups = gr
+        o0 = waves[0].optics
+        res.nphi, res.up, res.down = solver.batch_trphi(batch, o0.igli, o0.wind, o0.ind_surf, o0.ifresnel, itrphi, phios, pas_phi,
+                                                        o0.ipolar)
+    finally:
+        batch.free()
+    if trans:
+        tds, tdg = solver.transmissions(wl)
+        nw, nmax = len(waves), max(wv.optics.nbmu for wv in waves)
+        res.tdifmus, res.tdifmug = np.zeros(nw), np.zeros((nw, nmax))
+        for i, w in enumerate(owner):                         # SOS_AGGREGATE.F:415-436: AIK-weighted sums, term order
+            res.tdifmus[w] += aiks[i] * tds[i]
+            res.tdifmug[w, :waves[w].optics.nbmu] += aiks[i] * tdg[i, :waves[w].optics.nbmu]
+    # ---- files ----
+    if outdir is not None:
+        first = np.cumsum([0] + res.nterm)
+        for w, wv in enumerate(waves):
+            o = wv.optics
+            d = os.path.join(outdir, wv.name or "wave_%04d" % w)
+            os.makedirs(d, exist_ok=True)
+            res.dirs.append(d)
+            N = o.nbmu
+            nrec = int(gr.n_rec[w])
+            formats.write_result_bin(os.path.join(d, "SOS_Result.bin"), gr.rec[w, :nrec, :, :2 * N + 1])
+            theta = np.degrees(np.arccos(np.asarray(o.rmu)[N + 1:2 * N + 1]))
+            phi = np.array([phios, phios + 180.0]) if itrphi == 1 else np.arange(0.0, 360.0 + 0.5 * pas_phi, pas_phi)
+            api.write_updown(os.path.join(d, "SOS_Up.txt"), os.path.join(d, "SOS_Down.txt"), N, itrphi, phios, pas_phi, o.zout,
+                             phi[:res.nphi], theta, res.up[w, :, :res.nphi, :N], res.down[w, :, :res.nphi, :N])
+            if trans:
+                api.write_trans(os.path.join(d, "SOS_Trans.txt"), o.tetas, gr.ttot_tronc[w], gr.ttot_vrai[w], res.tdifmus[w],
+                                np.asarray(o.rmu)[N + 1:2 * N + 1], res.tdifmug[w, :N])
+            if flux:
+                last = first[w + 1] - 1                       # TAUABS of the last CKD term, as SOS_PROC leaves it (:3860)
+                api.write_flux(os.path.join(d, "SOS_Flux.txt"), o.tetas, gr.ttot_tronc[w], gr.ttot_vrai[w], gr.emoins[w], gr.eplus[w],
+                               wv.tr, wv.hr, wv.ta, wv.ha, np.asarray(userprofil)[:, 0], tau[last])
+    return res

@@ -394,3 +394,91 @@ def test_profile_shims_write_the_reference_file(pkg, ref, tmp_path):
         nsame += text == text_r
     print("\n[PROFIL_TMP] files byte-identical to the reference's: %d / %d" % (nsame, len(terms)))
     assert nsame >= len(terms) - 1
+
+
+def _parse_updown(path):
+    rows = []
+    for line in open(path):
+        if line.startswith("#") or not line.strip():
+            continue
+        rows.append([float(x) for x in line.split()])
+    return np.array(rows)
+
+
+def test_band_front_end_files(pkg, solver, ref, tmp_path):
+    """the multi-wavelength front end (band.run_band: CKD term list -> device profile chain -> device solves
+    and CKD sums -> device synthesis -> SOS_Up/Down.txt, SOS_Result.bin, Trans / Flux files per wavelength) against the
+    reference's flow run stage by stage for every wavelength: SOS_ABSPROFILE, SOS_PROFILE, SOS + SOS_OS, SOS_AGGREGATE,
+    SOS_TRPHI_OPTION.  CKD weights against a direct rendering of the nested loops."""
+    import importlib
+    import itertools
+    import profile_cases as pc
+    band = importlib.import_module("radiativetransfer-sos_b200.band")
+    api = importlib.import_module("radiativetransfer-sos_b200.api")
+    syn, fm = pkg.synth, pkg.formats
+    user, altabs, ro = pc.gas_atmosphere(6)
+    t = pc.ckd_tables(6)
+    counts = [int(np.prod(t["nexp"][:, l])) for l in range(pc.NWVL)]
+    lambs = [l + 1 for l in np.argsort(counts) if 2 <= counts[l] <= 12][:2] + [int(np.argmin(counts)) + 1]
+    waves = []
+    for n, l in enumerate(lambs):
+        o = syn.make_optics(nb_gauss=12, tetas=30.0 + 5 * n, os_nb=24, surface="lambert", rho=0.05 + 0.1 * n)
+        waves.append(band.Wavelength(optics=o, lamb1=l, tr=0.08 - 0.02 * n, ta=0.1 + 0.05 * n, name="w%d" % n))
+    waves[-1].absprofil = 7                                         # one wavelength without gaseous absorption
+    # CKD weights: the eight nested loops, IK8 innermost
+    iks, aik = band.enumerate_ckd_terms(t["nexp"], t["ai"], lambs[0])
+    ne = [int(t["nexp"][k, lambs[0] - 1]) for k in range(8)]
+    want = list(itertools.product(*[range(1, n + 1) for n in ne]))
+    assert iks == want
+    raw = np.array([np.prod([t["ai"][ik[k] - 1, k, lambs[0] - 1] for k in range(8)]) for ik in want])
+    np.testing.assert_allclose(aik, raw / raw.sum(), rtol=1e-14)
+    out = str(tmp_path / "band")
+    res = band.run_band(solver, t, t["ai"], user, altabs, ro, waves, itrphi=2, phios=0.0, pas_phi=60, outdir=out, trans=True, flux=True)
+    assert res.nterm == [len(iks), int(np.prod(t["nexp"][:, lambs[1] - 1])), 1]
+    rr = refdirect.runner()
+    nbad = nlines = nsame = 0
+    for w, wv in enumerate(waves):
+        o, N = wv.optics, wv.optics.nbmu
+        if wv.absprofil == 7:
+            ik_w, aik_w = [(1,) * 8], [1.0]
+        else:
+            ik_w, aik_w = band.enumerate_ckd_terms(t["nexp"], t["ai"], wv.lamb1)
+        wl_ref = syn.Workload("ref")
+        wl_ref.optics.append(o)
+        for ik, a in zip(ik_w, aik_w):
+            term = dict(lamb1=wv.lamb1, ik=ik, absprofil=wv.absprofil, iprofil=1, tr=wv.tr, hr=wv.hr, ta=wv.ta, ha=wv.ha, zmin=0.0, zmax=0.0)
+            _, tau_r = refdirect.absprofile(ref, t, user, altabs, ro, term)
+            ier_r, nt_r, _, z_r, h_r, pa_r, pm_r = refdirect.profile(ref, str(tmp_path), altabs, tau_r, term)
+            assert ier_r == 0
+            wl_ref.terms.append(syn.Term(0, a, z_r, h_r, pa_r, pm_r))
+        ids = list(range(len(ik_w)))
+        r, _, _ = rr.solve_terms(wl_ref, ids, CORES)
+        agg_rec, agg_sc = rr.aggregate_point(ref, fm, str(tmp_path), N, [(aik_w[i], r[i]) for i in ids])
+        nr = int(res.groups.n_rec[w])
+        if agg_rec[nr:].any() or nr > agg_rec.shape[0]:
+            nbad += 1
+            continue
+        got = fm.read_result_bin(os.path.join(res.dirs[w], "SOS_Result.bin"), N)
+        assert_stokes_close(got, agg_rec[:nr], "SOS_Result.bin of wavelength %d" % w)
+        for k in ("emoins", "eplus", "ttot_tronc", "ttot_vrai", "tauout"):
+            assert_stokes_close(getattr(res.groups, k)[w], agg_sc[k], k)
+        n0, pf, th, up0, dn0 = refdirect.trphi_option(ref, fm, str(tmp_path), agg_rec[:nr], N, o.rmu, o.ga, agg_sc["ttot_tronc"],
+                                                      agg_sc["tauout"], o.igli, o.n0, o.wind, o.ind_surf, o.ifresnel, 2, 0.0, 60)
+        assert n0 == res.nphi == 7
+        fu, fd = str(tmp_path / "REF_Up.txt"), str(tmp_path / "REF_Down.txt")
+        api.write_updown(fu, fd, N, 2, 0.0, 60, o.zout, pf, th, up0, dn0)
+        for mine, theirs in ((os.path.join(res.dirs[w], "SOS_Up.txt"), fu), (os.path.join(res.dirs[w], "SOS_Down.txt"), fd)):
+            a, b = open(mine).read().split("\n"), open(theirs).read().split("\n")
+            assert len(a) == len(b)
+            nlines += len(a)
+            nsame += sum(x == y for x, y in zip(a, b))
+            pa_, pb_ = _parse_updown(mine), _parse_updown(theirs)
+            assert pa_.shape == pb_.shape and pa_.shape[0] == 7 * N
+            np.testing.assert_allclose(pa_[:, :3], pb_[:, :3], atol=0.011)            # angles, printed with 2 decimals
+            np.testing.assert_allclose(pa_[:, 3:6], pb_[:, 3:6], rtol=3e-6, atol=1e-12)   # I, Q, U printed with 6 digits
+        # flux file: the three scalars SOS_PROC derives, and the files exist
+        for f in ("SOS_Trans.txt", "SOS_Flux.txt"):
+            assert os.path.getsize(os.path.join(res.dirs[w], f)) > 200
+    print("\n[band front end] count mismatches %d / %d wavelengths; SOS_Up/Down lines identical to the reference-side rendering: %d / %d"
+          % (nbad, len(waves), nsame, nlines))
+    assert nbad == 0 and nsame >= nlines - 4
