@@ -20,7 +20,9 @@ FILES = ["SOS_OS.F", "SOS.F", "SOS_AGGREGATE.F", "SOS_TRPHI.F", "SOS_GLITTER.F",
          "SOS_ROUJEAN.F", "SOS_SURFACE_BPDF.F", "SOS_PROFIL.F", "SOS_ABSPROFILE.F",
          # N1: COEFF_ABS_CKD and the linear / spline interpolators it calls (the other routines of these two files do not
          # translate -- DATA tables, list-directed string I/O -- and are not on the path)
-         "SOS_SUB_TRS.F", "SOS_AEROSOLS.F"]
+         "SOS_SUB_TRS.F", "SOS_AEROSOLS.F",
+         # N3: Mie theory (SOS_MIE, SOS_FPHASE_MIE); SOS_GRANU and SOS_DECOMPO_LEGENDRE come from SOS_AEROSOLS.F above
+         "SOS_MIE.F"]
 
 
 def build(force=False, verbose=True):
