@@ -308,6 +308,58 @@ int sosgpu_read_ckd_coeff(const char *sos_abs_root, int nabs, int jabs, double n
                           double *kdis_ki, double *kdis_ki_h2o, double *numax, double *numin, double *tab_pres, int *nb_pres,
                           double *tab_temp, int *nb_temp, double *tab_conc_h2o, int *nb_conc_h2o);
 
+/* ---- aerosol optics per wavelength ----------------------------------------------------------------
+ * What SOS_AEROSOLS does on the host before a wavelength is solved: Mie theory on a grid of size parameters (SOS_MIE,
+ * SOS_FPHASE_MIE, SOS_MIE.F:205-690, 801-944; cached in MIE files keyed by refractive index and size-parameter range), the
+ * integral over a size distribution (SOS_GRANU, SOS_AEROSOLS.F:4392-4767), the mixture of modes (SOS_AEROSOLS.F:1455-1490,
+ * 2085-2110) and the Legendre expansion with the optional truncation of the forward peak (SOS_DECOMPO_LEGENDRE,
+ * SOS_AEROSOLS.F:3924-4260), whose ALPHA, BETA11, GAMMA12, ZETA (0:os_nb) and truncated albedo are the solver's inputs.
+ * Angle vectors V(-nbmu:nbmu) as everywhere: double v[2*nbmu+1], element j at v[j+nbmu]; nang = 2*nbmu+1.
+ * A Mie table has one record per size parameter: rec[k][3] = ALPHA, QEXT, QSCA (REAL*4), g[k] (REAL*8) and the phase
+ * functions imie / qmie / umie [k][nang] (REAL*4) -- the contents of the reference's MIE file. */
+#define SOSGPU_MIE_NBMU_MAX 100     /* CTE_MIE_NBMU_MAX (inc/SOS.h:457) */
+#define SOSGPU_MIE_DIM      10000   /* CTE_MIE_DIM (inc/SOS.h:96): alphaf + alphaf + 20 must not exceed it */
+typedef struct {
+  double rn, in;             /* refractive index of the particles; in <= 0 */
+  double alpha0, alphaf;     /* size-parameter range of the Mie table (SOS_MIE's ALPHAO, ALPHAF) */
+  int igranu;                /* 1: log-normal, v1 = modal radius (microns), v2 = sigma; 2: Junge, v1 = r0, v2 = slope, v3 = rmax */
+  double v1, v2, v3;
+  double wa;                 /* wavelength (microns) */
+} sosgpu_aer_component;
+typedef struct {
+  int ncomp;                 /* 0: component comp[0] as it is (mono-modal); 1..4: mixture of comp[0..ncomp-1] */
+  int comp[4];               /* indices into the component list */
+  double weight[4];          /* number fractions: N(I)/NTOT (WMO) or the normalised CVI(I) (bimodal); 0 skips the component */
+  int itronc;                /* 1: truncate the forward peak (cancelled when the coefficient stays below 0.1) */
+} sosgpu_aer_model;
+/* number of records SOS_MIE writes for [alpha0, alphaf] (variable step, SOS_MIE.F:406-411), or -1 (its error 997) */
+int sosgpu_mie_count(double alpha0, double alphaf);
+/* SOS_MIE for one table; outputs are host arrays of capacity nrec_cap records, *nrec the number written */
+int sosgpu_mie(sosgpu_ctx *ctx, int nbmu, const double *rmu, double rn, double in, double alpha0, double alphaf, int nrec_cap,
+               float *rec, double *g, float *imie, float *qmie, float *umie, int *nrec);
+/* SOS_GRANU on a Mie table in host arrays (alphaf: the table's header value).  kmat[3] = KMAT1, KMAT2 (cross sections,
+ * square microns), SOMME_NR; *ier = -1 when the table ends before the size distribution does (the reference's read error) */
+int sosgpu_granu(sosgpu_ctx *ctx, int nbmu, int nrec, const float *rec, const float *imie, const float *qmie, const float *umie,
+                 double alphaf, int igranu, double v1, double v2, double v3, double wa, double *kmat, double *p11, double *p12,
+                 double *p33, int *ier);
+/* SOS_DECOMPO_LEGENDRE: p11 in / out (truncated on exit), ttt out (P11 before truncation), *itronc in / out; the coefficient
+ * arrays (0:os_nb) are overwritten (the reference accumulates into arrays its caller has zeroed) */
+int sosgpu_decompo_legendre(sosgpu_ctx *ctx, int *itronc, int nbmu, const double *xmu, const double *xhr, int os_nb, double *p11,
+                            double *ttt, const double *p12, const double *p22, const double *p33, double *coef_tronca, double *z1,
+                            double *alp, double *beta11, double *beta22, double *gamma12, double *delta33, double *zeta, int *ier);
+/* The whole chain on the device for ncomp components (one per mode and wavelength) and nmodel models (one per wavelength):
+ * one Mie table per distinct (rn, in, alpha0, alphaf), never copied to the host.  Host outputs (NULL = not wanted):
+ *   comp_k [ncomp][3] KMAT1, KMAT2, SOMME_NR; comp_phase [ncomp][3][nang] P11, P12, P33; comp_ier [ncomp];
+ *   scal [nmodel][8] KMAT1, KMAT2, PIZ, PIZTR (albedo after truncation), COEF_TRONCA, asymmetry factor, Z1, ITRONC on exit;
+ *   coef [nmodel][6][os_nb+1] ALPHA, BETA11, GAMMA12, ZETA, BETA22, DELTA33; phase [nmodel][4][nang] P11 (truncated), P12,
+ *   P33, TTT; model_ier [nmodel] */
+int sosgpu_aerosols(sosgpu_ctx *ctx, int nbmu, const double *xmu, const double *xhr, int ncomp, const sosgpu_aer_component *comp,
+                    int nmodel, const sosgpu_aer_model *models, int os_nb, double *comp_k, double *comp_phase, int *comp_ier,
+                    double *scal, double *coef, double *phase, int *model_ier);
+/* the aerosol result file SOS_AEROSOLS writes and SOS_PREPA_OS reads (SOS_AEROSOLS.F:2810-2832, formats 39-50); host only */
+int sosgpu_write_aerosols(const char *path, int os_nb, double kmat1, double kmat2, double asym, double coef_tronca, double piztr,
+                          const double *alp, const double *beta11, const double *gamma12, const double *zeta);
+
 /* ---- gfortran-ABI drop-in symbols (F77 by-reference, fixed SOS.h strides, hidden string lengths) */
 /* SOS_OS.F:303-308 */
 void sos_os_(const int *nbmu, double *rmu, const double *ga, const int *os_nb, const int *nt,
@@ -381,6 +433,19 @@ void sos_absprofile_(const short *absprofil, const double *nu, const int *lamb1,
 void sos_profile_(const short *iprofil, const double *tr, const double *hr, const double *ta, const double *ha,
                   const double *zmin, const double *zmax, const short *absprofil, const double *altabs, const double *tabs,
                   const int *trace, const int *idlog, const char *ficprofil, int *nt, int *ier, size_t len_ficprofil);
+
+/* SOS_MIE.F:205-206: writes the unformatted MIE file (hidden lengths of FICMIE, FICLOG last); angle vectors (-100:100) */
+void sos_mie_(const int *mie_nbmu, const double *rmu, const double *chr, const double *rn, const double *in, const double *alphao,
+              const double *alphaf, const char *ficmie, const char *ficlog, int *ier, size_t len_ficmie, size_t len_ficlog);
+/* SOS_AEROSOLS.F:4392-4394: reads the MIE file */
+void sos_granu_(const char *ficmie, const int *igranu, const double *v1, const double *v2, const double *v3, const double *wa,
+                const int *mie_nbmu, const double *xmu, const int *trace, double *kmat1, double *kmat2, double *somme_nr,
+                double *p11, double *p12, double *p33, int *ier, size_t len_ficmie);
+/* SOS_AEROSOLS.F:3924-3928: coefficient arrays (0:200) */
+void sos_decompo_legendre_(int *itronc, const int *trace, const int *mie_nbmu, const double *xmu, const double *xhr, const int *os_nb,
+                           double *p11, double *ttt, const double *p12, const double *p22, const double *p33, double *coef_tronca,
+                           double *z1, double *alp, double *beta11, double *beta22, double *gamma12, double *delta33, double *zeta,
+                           int *ier);
 
 #ifdef __cplusplus
 }

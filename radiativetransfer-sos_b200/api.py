@@ -70,6 +70,15 @@ class CProfileTerm(C.Structure):
                 ("hr", C.c_double), ("ta", C.c_double), ("ha", C.c_double), ("zmin", C.c_double), ("zmax", C.c_double)]
 
 
+class CAerComponent(C.Structure):
+    _fields_ = [("rn", C.c_double), ("in_", C.c_double), ("alpha0", C.c_double), ("alphaf", C.c_double), ("igranu", C.c_int),
+                ("v1", C.c_double), ("v2", C.c_double), ("v3", C.c_double), ("wa", C.c_double)]
+
+
+class CAerModel(C.Structure):
+    _fields_ = [("ncomp", C.c_int), ("comp", C.c_int * 4), ("weight", C.c_double * 4), ("itronc", C.c_int)]
+
+
 NT_MAX = 600
 
 
@@ -166,6 +175,17 @@ def write_flux(ficflux, tetas, ttot_tronc, ttot_vrai, emoins, eplus, tr, hr, ta,
     if rc != SOSGPU_OK:
         raise RuntimeError("sosgpu_write_flux failed (rc=%d)" % rc)
     return tuple(o.value for o in out)
+
+
+def write_aerosols(path, os_nb, kmat1, kmat2, asym, coef_tronca, piztr, alp, beta11, gamma12, zeta):
+    """The aerosol result file of SOS_AEROSOLS (SOS_AEROSOLS.F:2810-2832), read by SOS_PREPA_OS.  Host-side formatting inside
+    the library; needs no GPU."""
+    lib = load_library()
+    lib.sosgpu_write_aerosols.argtypes = [C.c_char_p, C.c_int] + [C.c_double] * 5 + [c_dp] * 4
+    rc = lib.sosgpu_write_aerosols(os.fsencode(path), os_nb, kmat1, kmat2, asym, coef_tronca, piztr, _d(_f64(alp)), _d(_f64(beta11)),
+                                   _d(_f64(gamma12)), _d(_f64(zeta)))
+    if rc != SOSGPU_OK:
+        raise RuntimeError("write_aerosols failed (%d)" % rc)
 
 
 class TermResults:
@@ -591,6 +611,89 @@ class Solver:
                                            ier.ctypes.data_as(c_ip))
         self._check(rc, "profile_chain")
         return (nt, z, h, pa, pm, ier) + ((tau,) if want_tauabs else ())
+
+    # ---- aerosol optics per wavelength ----
+    def mie_count(self, alpha0, alphaf):
+        self.lib.sosgpu_mie_count.argtypes = [C.c_double, C.c_double]
+        return int(self.lib.sosgpu_mie_count(alpha0, alphaf))
+
+    def mie(self, nbmu, rmu, rn, in_, alpha0, alphaf):
+        """SOS_MIE (SOS_MIE.F:205) without its file: dict rec [nrec, 3] (ALPHA, QEXT, QSCA, REAL*4), g [nrec], imie / qmie / umie
+        [nrec, 2 nbmu + 1] (REAL*4), alphaf."""
+        n = self.mie_count(alpha0, alphaf)
+        if n < 1:
+            raise RuntimeError("mie: size-parameter range outside CTE_MIE_DIM (SOS_MIE error 997)")
+        nang = 2 * nbmu + 1
+        rec, g = np.zeros((n, 3), dtype=np.float32), np.zeros(n)
+        im, qm, um = (np.zeros((n, nang), dtype=np.float32) for _ in range(3))
+        nrec = C.c_int(0)
+        f = lambda a: a.ctypes.data_as(c_fp)
+        self.lib.sosgpu_mie.argtypes = [C.c_void_p, C.c_int, c_dp] + [C.c_double] * 4 + [C.c_int, c_fp, c_dp, c_fp, c_fp, c_fp, c_ip]
+        rc = self.lib.sosgpu_mie(self.ctx, nbmu, _d(_f64(rmu)), rn, in_, alpha0, alphaf, n, f(rec), _d(g), f(im), f(qm), f(um), C.byref(nrec))
+        self._check(rc, "mie")
+        assert nrec.value == n
+        return dict(rec=rec, g=g, imie=im, qmie=qm, umie=um, alphaf=float(alphaf))
+
+    def granu(self, nbmu, table, igranu, v1, v2, v3, wa):
+        """SOS_GRANU (SOS_AEROSOLS.F:4392) on a Mie table (dict as mie() returns): (ier, kmat1, kmat2, somme_nr, p11, p12, p33)."""
+        nang = 2 * nbmu + 1
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        rec, im, qm, um = f(table["rec"]), f(table["imie"]), f(table["qmie"]), f(table["umie"])
+        k, ier = np.zeros(3), C.c_int(-1)
+        p11, p12, p33 = np.zeros(nang), np.zeros(nang), np.zeros(nang)
+        p = lambda a: a.ctypes.data_as(c_fp)
+        self.lib.sosgpu_granu.argtypes = [C.c_void_p, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, C.c_double, C.c_int] + [C.c_double] * 4 + \
+                                         [c_dp, c_dp, c_dp, c_dp, c_ip]
+        rc = self.lib.sosgpu_granu(self.ctx, nbmu, rec.shape[0], p(rec), p(im), p(qm), p(um), table["alphaf"], igranu, v1, v2, v3, wa,
+                                   _d(k), _d(p11), _d(p12), _d(p33), C.byref(ier))
+        self._check(rc, "granu")
+        return ier.value, k[0], k[1], k[2], p11, p12, p33
+
+    def decompo_legendre(self, itronc, nbmu, xmu, xhr, os_nb, p11, p12, p22, p33):
+        """SOS_DECOMPO_LEGENDRE (SOS_AEROSOLS.F:3924): dict with alp, beta11, beta22, gamma12, delta33, zeta (0:os_nb), the
+        (possibly truncated) p11, ttt, coef_tronca, z1, itronc on exit, ier."""
+        nang = 2 * nbmu + 1
+        q11, ttt = _f64(p11).copy(), np.zeros(nang)
+        co = {k: np.zeros(os_nb + 1) for k in ("alp", "beta11", "beta22", "gamma12", "delta33", "zeta")}
+        it, ct, z1, ier = C.c_int(itronc), C.c_double(0), C.c_double(0), C.c_int(-1)
+        self.lib.sosgpu_decompo_legendre.argtypes = [C.c_void_p, c_ip, C.c_int, c_dp, c_dp, C.c_int] + [c_dp] * 5 + [c_dp, c_dp] + \
+                                                    [c_dp] * 6 + [c_ip]
+        rc = self.lib.sosgpu_decompo_legendre(self.ctx, C.byref(it), nbmu, _d(_f64(xmu)), _d(_f64(xhr)), os_nb, _d(q11), _d(ttt),
+                                              _d(_f64(p12)), _d(_f64(p22)), _d(_f64(p33)), C.byref(ct), C.byref(z1), _d(co["alp"]),
+                                              _d(co["beta11"]), _d(co["beta22"]), _d(co["gamma12"]), _d(co["delta33"]), _d(co["zeta"]),
+                                              C.byref(ier))
+        self._check(rc, "decompo_legendre")
+        co.update(p11=q11, ttt=ttt, coef_tronca=ct.value, z1=z1.value, itronc=it.value, ier=ier.value)
+        return co
+
+    def aerosols(self, nbmu, xmu, xhr, components, models, os_nb, want_phase=True):
+        """The whole chain on the device (SOS_AEROSOLS.F:1158-1304, 1706-2123 without their MIE files): components = list of
+        (rn, in, alpha0, alphaf, igranu, v1, v2, v3, wa), models = list of (ncomp, comp indices, weights, itronc).  Returns dict:
+        comp_k [nc, 3], comp_phase [nc, 3, nang], comp_ier, scal [nm, 8] (KMAT1, KMAT2, PIZ, PIZTR, COEF_TRONCA, asymmetry
+        factor, Z1, ITRONC on exit), coef [nm, 6, os_nb+1] (ALPHA, BETA11, GAMMA12, ZETA, BETA22, DELTA33), phase [nm, 4, nang],
+        model_ier."""
+        nc, nm, nang = len(components), len(models), 2 * nbmu + 1
+        ca = (CAerComponent * nc)()
+        for a, c in zip(ca, components):
+            a.rn, a.in_, a.alpha0, a.alphaf, a.igranu, a.v1, a.v2, a.v3, a.wa = c
+        ma = (CAerModel * max(nm, 1))()
+        for a, m in zip(ma, models):
+            a.ncomp, a.itronc = int(m[0]), int(m[3])
+            for i, ci in enumerate(m[1]):
+                a.comp[i] = int(ci)
+            for i, w in enumerate(m[2]):
+                a.weight[i] = float(w)
+        out = dict(comp_k=np.zeros((nc, 3)), comp_phase=np.zeros((nc, 3, nang)) if want_phase else None,
+                   comp_ier=np.zeros(nc, dtype=np.int32), scal=np.zeros((nm, 8)), coef=np.zeros((nm, 6, os_nb + 1)),
+                   phase=np.zeros((nm, 4, nang)) if want_phase else None, model_ier=np.zeros(nm, dtype=np.int32))
+        self.lib.sosgpu_aerosols.argtypes = [C.c_void_p, C.c_int, c_dp, c_dp, C.c_int, C.POINTER(CAerComponent), C.c_int,
+                                             C.POINTER(CAerModel), C.c_int, c_dp, c_dp, c_ip, c_dp, c_dp, c_dp, c_ip]
+        rc = self.lib.sosgpu_aerosols(self.ctx, nbmu, _d(_f64(xmu)), _d(_f64(xhr)), nc, ca, nm, ma, os_nb, _d(out["comp_k"]),
+                                      _d(out["comp_phase"]) if want_phase else None, out["comp_ier"].ctypes.data_as(c_ip),
+                                      _d(out["scal"]), _d(out["coef"]), _d(out["phase"]) if want_phase else None,
+                                      out["model_ier"].ctypes.data_as(c_ip))
+        self._check(rc, "aerosols")
+        return out
 
     def batch_trphi(self, batch, igli, wind, ind_surf, ifresnel, itrphi, phios, pas_phi, ipolar, download=True):
         """SOS_TRPHI_OPTION for every wavelength of a resident batch (after run); tables [ngroup, 7, nphi, Nmax]."""

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     src = open(os.path.join(ROOT, "include", "sosgpu.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"\b(sosgpu_[a-z_0-9]+|sos_os_|sos_aggregate_|sos_|sos_glitter_|sos_trphi_|sos_trphi_option_)\s*\(", src)
+    names = re.findall(r"\b(sosgpu_[a-z_0-9]+|sos_[a-z_0-9]*_|sos_|read_ckd_coeff_)\s*\(", src)
     return sorted(set(names))
 
 
@@ -22,6 +22,9 @@ def test_header_symbols_exported():
     lib = api.load_library()
     syms = _declared_symbols()
     assert len(syms) >= 15
+    for s in ("sos_", "sos_os_", "sos_aggregate_", "sos_glitter_", "sos_trphi_", "sos_trphi_option_", "sos_absprofile_", "sos_profile_",
+              "read_ckd_coeff_", "sos_mie_", "sos_granu_", "sos_decompo_legendre_", "sosgpu_aerosols", "sosgpu_mie"):
+        assert s in syms, s
     for s in syms:
         assert hasattr(lib, s), "libsosgpu.so does not export %s declared in include/sosgpu.h" % s
 
@@ -57,12 +60,13 @@ def test_ctypes_structs_match_header(tmp_path):
     api = importlib.import_module("radiativetransfer-sos_b200.api")
     pairs = {"sosgpu_optics": api.COptics, "sosgpu_term": api.CTerm, "sosgpu_term_out": api.CTermOut,
              "sosgpu_group_out": api.CGroupOut, "sosgpu_stats": api.CStats, "sosgpu_direct_models": api.CDirectModels,
-             "sosgpu_ckd": api.CCkd, "sosgpu_gas_profile": api.CGasProfile, "sosgpu_profile_term": api.CProfileTerm}
+             "sosgpu_ckd": api.CCkd, "sosgpu_gas_profile": api.CGasProfile, "sosgpu_profile_term": api.CProfileTerm,
+             "sosgpu_aer_component": api.CAerComponent, "sosgpu_aer_model": api.CAerModel}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sosgpu.h"', 'int main(void) {']
     for cname, cls in pairs.items():
         lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
         for fname, _ in cls._fields_:
-            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname.rstrip("_")))
     lines += ['  return 0;', '}']
     src = tmp_path / "layout.c"
     src.write_text("\n".join(lines))
@@ -121,3 +125,22 @@ def test_gfortran_shims_refuse_without_gpu(tmp_path):
     assert lib.sosgpu_profile_chain(None, None, None, None, 1, 1, None, None, None, None, None, None, None) == api.SOSGPU_ERR_NO_DEVICE
     assert lib.sosgpu_absprofile(None, None, None, None, 1, None, None) == api.SOSGPU_ERR_NO_DEVICE
     assert lib.sosgpu_profile(None, None, None, None, 1, 1, None, None, None, None, None, None) == api.SOSGPU_ERR_NO_DEVICE
+    # aerosol optics: SOS_MIE / SOS_GRANU / SOS_DECOMPO_LEGENDRE shims and the batched entries
+    mu, w = np.zeros(201), np.zeros(201)
+    mu[101:105], w[101:105] = [0.3, 0.5, 0.85, 0.97], 0.25
+    mu[96:100], w[96:100] = -mu[101:105][::-1], 0.25
+    ier = C.c_int(0)
+    fmie = str(tmp_path / "MIE.bin")
+    lib.sos_mie_(ip(4), P(mu), P(w), dp(1.4), dp(-0.01), dp(0.0001), dp(5.0), fstr(fmie), fstr("NO_LOG_FILE"), C.byref(ier), L500, L500)
+    assert ier.value == -1 and not os.path.exists(fmie)
+    ier = C.c_int(0)
+    it = C.c_int(1)
+    ph = np.ones(201)
+    lib.sos_decompo_legendre_(C.byref(it), ip(0), ip(4), P(mu), P(w), ip(8), P(ph), P(ph.copy()), P(ph), P(ph), P(ph), dp(0.0), dp(0.0),
+                              P(co), P(co), P(co), P(co), P(co), P(co), C.byref(ier))
+    assert ier.value == -1
+    assert lib.sosgpu_aerosols(None, 4, None, None, 1, None, 0, None, 8, None, None, None, None, None, None, None) == api.SOSGPU_ERR_NO_DEVICE
+    lib.sosgpu_mie.argtypes = [C.c_void_p, C.c_int, C.c_void_p] + [C.c_double] * 4 + [C.c_int] + [C.c_void_p] * 6
+    assert lib.sosgpu_mie(None, 4, None, 1.4, -0.01, 0.0001, 5.0, 0, None, None, None, None, None, None) == api.SOSGPU_ERR_NO_DEVICE
+    lib.sosgpu_mie_count.argtypes = [C.c_double, C.c_double]
+    assert lib.sosgpu_mie_count(0.0001, 200.0) == 4000 and lib.sosgpu_mie_count(0.0001, 5000.0) == -1     # host-side grid arithmetic only
