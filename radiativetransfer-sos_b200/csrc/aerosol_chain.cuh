@@ -31,18 +31,20 @@
 #define AC_MU2_TRONCA ((double)0.94f)   // CTE_AER_MU2_TRONCA (SOS.h:167)
 #define AC_SEUIL_TRONCA ((double)0.1f)  // CTE_PH_SEUIL_TRONCA (SOS.h:172)
 
-// Work arrays of one size parameter, Fortran index i at [i + 1] (CNA, SNA, RGNA, IGNA start at -1).
+// Work arrays of one size parameter: seven arrays of `stride` doubles, Fortran index i at [i + 1] (CNA, SNA, RGNA, IGNA start at
+// -1).  The a_n / b_n of order i overwrite the G_n / D_n(m alpha) entries of the same order (each thread reads its seven inputs
+// before it writes), the terms of the three sums over n go where C_n, S_n and D_n(alpha) were.
 struct AcMieWork {
   double *cna, *sna, *rgna, *igna, *rdna, *rdnb, *idnb, *ra, *ia, *rb, *ib, *tq1, *tq2, *tg;
 };
-#define AC_WORK_ARRAYS 14
+#define AC_WORK_ARRAYS 7
 AC_HD AcMieWork ac_work(double *base, size_t stride)
 {
   AcMieWork w;
   w.cna = base; w.sna = base + stride; w.rgna = base + 2 * stride; w.igna = base + 3 * stride; w.rdna = base + 4 * stride;
-  w.rdnb = base + 5 * stride; w.idnb = base + 6 * stride; w.ra = base + 7 * stride; w.ia = base + 8 * stride;
-  w.rb = base + 9 * stride; w.ib = base + 10 * stride; w.tq1 = base + 11 * stride; w.tq2 = base + 12 * stride;
-  w.tg = base + 13 * stride;
+  w.rdnb = base + 5 * stride; w.idnb = base + 6 * stride;
+  w.ra = w.rgna + 1; w.ia = w.igna + 1; w.rb = w.rdnb + 1; w.ib = w.idnb + 1;      // RA(i) in the slot of RGNA(i) ...
+  w.tq1 = w.cna; w.tq2 = w.sna; w.tg = w.rdna;
   return w;
 }
 

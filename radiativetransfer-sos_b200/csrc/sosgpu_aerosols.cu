@@ -114,6 +114,8 @@ struct DevTables {
   double *g = nullptr;
 };
 
+// ev_a is recorded right before the kernel: the stream is idle while the host allocates, so an earlier record would time the
+// growth of the memory pool as well
 int launch_mie(sosgpu_ctx *ctx, int nbmu, const double *d_rmu, const std::vector<HostTable> &tabs, const std::vector<double> &alpha,
                const DevTables &dt, SosFreeGuard &guard)
 {
@@ -144,6 +146,7 @@ int launch_mie(sosgpu_ctx *ctx, int nbmu, const double *d_rmu, const std::vector
   CK(cudaMemcpyAsync(d + o_it, items.data(), sizeof(MieItem) * items.size(), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d + o_al, alpha.data(), sizeof(double) * total, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(d + o_cnt, 0, sizeof(unsigned), st));
+  if (ctx->ev_a) cudaEventRecord(ctx->ev_a, st);
   k_mie<<<grid, MIE_THREADS, 0, st>>>((const MieTableDev *)(d + o_tab), (const MieItem *)(d + o_it), (int)total, (const double *)(d + o_al), nbmu,
                                       d_rmu, (double *)(d + o_work), stride, (unsigned *)(d + o_cnt), dt.rec, dt.g, dt.imie, dt.qmie, dt.umie);
   CK(cudaGetLastError());
@@ -219,7 +222,6 @@ extern "C" int sosgpu_mie(sosgpu_ctx *ctx, int nbmu, const double *rmu, double r
   CK(sos_dmalloc(ctx, &d_rmu, sizeof(double) * nang)); guard.add(d_rmu);
   CK(cudaMemcpyAsync(d_rmu, rmu, sizeof(double) * nang, cudaMemcpyHostToDevice, st));
   std::vector<HostTable> tabs{HostTable{rn, in, alpha0, alphaf, 0, (int)total}};
-  if (ctx->ev_a) cudaEventRecord(ctx->ev_a, st);
   rc = launch_mie(ctx, nbmu, d_rmu, tabs, alpha, dt, guard);
   if (rc != SOSGPU_OK) return rc;
   if (ctx->ev_b) cudaEventRecord(ctx->ev_b, st);
@@ -239,7 +241,7 @@ namespace {
 int run_granu_models(sosgpu_ctx *ctx, int nbmu, const double *xmu, const double *xhr, const DevTables &dt, const std::vector<GranuCompDev> &comps,
                      const double *host_comp_in /* [ncomp][3 + 4 nang]: k, p11, p12, p33, p22 given instead of k_granu, or null */,
                      bool with_p22, const std::vector<AcModel> &models, int os_nb, double *comp_k, double *comp_phase, int *comp_ier, double *scal,
-                     double *coef, double *phase, int *model_ier, SosFreeGuard &guard)
+                     double *coef, double *phase, int *model_ier, SosFreeGuard &guard, bool start_timer = true)
 {
   cudaStream_t st = ctx->stream;
   const size_t nang = 2 * (size_t)nbmu + 1, nc = comps.size(), nm = models.size();
@@ -275,8 +277,10 @@ int run_granu_models(sosgpu_ctx *ctx, int nbmu, const double *xmu, const double 
     CK(cudaMemcpyAsync(d_ck, stage.data(), sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_p11, stage.data() + 3 * nc, sizeof(double) * 4 * nc * nang, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_cier, 0, sizeof(int) * nc, st));
+    if (start_timer && ctx->ev_a) cudaEventRecord(ctx->ev_a, st);
   } else {
     CK(cudaMemcpyAsync(d + o_comp, comps.data(), sizeof(GranuCompDev) * nc, cudaMemcpyHostToDevice, st));
+    if (start_timer && ctx->ev_a) cudaEventRecord(ctx->ev_a, st);
     k_granu<<<(unsigned)nc, 128, 0, st>>>((const GranuCompDev *)(d + o_comp), (int)nang, dt.rec, dt.imie, dt.qmie, dt.umie, (double *)(d + o_scr),
                                           sstride, d_ck, d_p11, d_p12, d_p33, d_cier);
     CK(cudaGetLastError());
@@ -351,7 +355,6 @@ extern "C" int sosgpu_granu(sosgpu_ctx *ctx, int nbmu, int nrec, const float *re
   CK(cudaMemcpyAsync(dt.umie, umie, sizeof(float) * total * nang, cudaMemcpyHostToDevice, st));
   std::vector<GranuCompDev> comps{GranuCompDev{0, nrec, igranu, alphaf, v1, v2, v3, wa}};
   std::vector<double> zero(nang, 0.0), ph(3 * nang);
-  if (ctx->ev_a) cudaEventRecord(ctx->ev_a, st);
   rc = run_granu_models(ctx, nbmu, zero.data(), nullptr, dt, comps, nullptr, false, {}, 2, kmat, ph.data(), ier, nullptr, nullptr, nullptr, nullptr, guard);
   if (rc != SOSGPU_OK) return rc;
   memcpy(p11, &ph[0], sizeof(double) * nang); memcpy(p12, &ph[nang], sizeof(double) * nang); memcpy(p33, &ph[2 * nang], sizeof(double) * nang);
@@ -381,7 +384,6 @@ extern "C" int sosgpu_decompo_legendre(sosgpu_ctx *ctx, int *itronc, int nbmu, c
   std::vector<GranuCompDev> comps(1);
   std::vector<double> scal(8), coef(6 * (size_t)(os_nb + 1)), ph(4 * nang);
   SosFreeGuard guard(ctx);
-  if (ctx->ev_a) cudaEventRecord(ctx->ev_a, ctx->stream);
   const int rc = run_granu_models(ctx, nbmu, xmu, xhr, DevTables{}, comps, in.data(), true, models, os_nb, nullptr, nullptr, nullptr, scal.data(),
                                   coef.data(), ph.data(), ier, guard);
   if (rc != SOSGPU_OK) return rc;
@@ -443,10 +445,10 @@ extern "C" int sosgpu_aerosols(sosgpu_ctx *ctx, int nbmu, const double *xmu, con
   double *d_rmu = nullptr;
   CK(sos_dmalloc(ctx, &d_rmu, sizeof(double) * nang)); guard.add(d_rmu);
   CK(cudaMemcpyAsync(d_rmu, xmu, sizeof(double) * nang, cudaMemcpyHostToDevice, st));
-  if (ctx->ev_a) cudaEventRecord(ctx->ev_a, st);
   rc = launch_mie(ctx, nbmu, d_rmu, tabs, alpha, dt, guard);
   if (rc != SOSGPU_OK) return rc;
-  return run_granu_models(ctx, nbmu, xmu, xhr, dt, comps, nullptr, false, mods, os_nb, comp_k, comp_phase, comp_ier, scal, coef, phase, model_ier, guard);
+  return run_granu_models(ctx, nbmu, xmu, xhr, dt, comps, nullptr, false, mods, os_nb, comp_k, comp_phase, comp_ier, scal, coef, phase, model_ier, guard,
+                          false);
 }
 
 // ---- the aerosol result file (SOS_AEROSOLS.F:2810-2832, formats 39-50) --------------------------

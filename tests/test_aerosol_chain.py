@@ -255,7 +255,7 @@ def test_gpu_mie_vs_reference(solver, ref, tmp_path, case):
     _, r = ac.ref_mie(ref, str(tmp_path), nbmu, xmu, xhr, rn, in_, a0, af)
     t_ref = time.time() - t0
     g = solver.mie(nbmu, xmu, rn, in_, a0, af)
-    ms = solver.last_kernel_ms()
+    ms = solver.last_kernel_ms
     assert g["rec"].shape == r["rec"].shape
     assert np.array_equal(g["rec"][:, 0], r["rec"][:, 0])                  # the size-parameter grid itself is exact
     frac, worst = _check_mie_tables(g, r)
@@ -366,7 +366,7 @@ def test_gpu_aerosols_chain_vs_reference(solver, ref, tmp_path):
     print("[GPU aerosol chain] %d models / %d components / %d Mie tables: truncation decisions identical, coefficients within 2e-7 "
           "of beta11's scale (REAL*4 Mie records), result-file lines identical %d / %d; device time of the chain %.1f ms (call %.0f "
           "ms), reference flow %.1f s on one host core" % (len(models), len(comps), ntab, same_lines, total_lines,
-                                                           solver.last_kernel_ms(), 1e3 * t_gpu, t_ref))
+                                                           solver.last_kernel_ms, 1e3 * t_gpu, t_ref))
 
 
 @pytest.mark.gpu
@@ -416,4 +416,4 @@ def test_gpu_aerosols_sweep_timing(solver):
     assert ((o["scal"][:, 2] > 0.8) & (o["scal"][:, 2] < 1.0)).all()          # single-scattering albedo
     nrec = sum(solver.mie_count(c[2], c[3]) for c in comps)
     print("[GPU aerosol sweep] 64 wavelengths x 2 modes = 128 Mie tables (%d records x 81 angles), expansions to order 80: device "
-          "time %.1f ms, call %.0f ms" % (nrec, solver.last_kernel_ms(), 1e3 * dt))
+          "time %.1f ms, call %.0f ms" % (nrec, solver.last_kernel_ms, 1e3 * dt))
