@@ -117,3 +117,32 @@ def alphaf_for(rmax, wa):
 COARSE = (1.45, -0.004, 1, 0.40, 0.60, -999.0)
 FINE = (1.42, -0.008, 1, 0.08, 0.45, -999.0)
 JUNGE = (1.40, -0.002, 2, 0.05, 4.0, 3.0)
+
+
+def write_wmo_file(path, seed=3):
+    """A data file in the layout SOS_INIT_PARAMWMO reads (formats 333 / 444 / 555, SOS_AEROSOLS.F:3545-3547): modal radii,
+    log10 sigmas, particle volumes, then wavelength + four complex indices per line.  Values generated here (not the reference's
+    table), so the GPU box can build it."""
+    rng = np.random.default_rng(seed)
+    rm = [0.45, 0.006, 0.28, 0.012]
+    s10 = [0.46, 0.47, 0.40, 0.30]
+    vol = [95.0, 1.1e-4, 5.2, 6.0e-5]
+    with open(path, "w") as f:
+        f.write("".join(" %9.5f" % x for x in rm) + "\n")
+        f.write("".join(" %9.5f" % x for x in s10) + "\n")
+        f.write(" %9.5f %12.5E %9.5f %12.5E\n" % tuple(vol))
+        for wa in (0.3, 0.4, 0.55, 0.7, 0.9, 1.1, 1.6, 2.2, 3.0):
+            row = [wa]
+            for i in range(4):
+                row += [1.35 + 0.1 * i + 0.02 * rng.random(), -abs(rng.normal()) * 10.0 ** (-1 - (i % 3))]
+            f.write("".join(" %9.5f" % x for x in row) + "\n")
+    return path
+
+
+def ref_wmo_params(ref, path, wa):
+    """SOS_INIT_PARAMWMO (SOS_AEROSOLS.F:3334) of the reference library."""
+    v1, v2, mr, mi = (np.zeros(5) for _ in range(4))
+    vol = np.zeros(4)
+    ier = C.c_int(99)
+    ref.sos_init_paramwmo_(_fs(path), _dp(wa), _P(v1), _P(v2), _P(mr), _P(mi), _P(vol), C.byref(ier), _L)
+    return ier.value, v1[:4].copy(), v2[:4].copy(), mr[:4].copy(), mi[:4].copy(), vol.copy()

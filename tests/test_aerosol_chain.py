@@ -417,3 +417,84 @@ def test_gpu_aerosols_sweep_timing(solver):
     nrec = sum(solver.mie_count(c[2], c[3]) for c in comps)
     print("[GPU aerosol sweep] 64 wavelengths x 2 modes = 128 Mie tables (%d records x 81 angles), expansions to order 80: device "
           "time %.1f ms, call %.0f ms" % (nrec, solver.last_kernel_ms, 1e3 * dt))
+
+
+# ------------------------------------------------------------------------------------------------ host front end (aerosols.py)
+def _aer():
+    import importlib
+    return importlib.import_module("radiativetransfer-sos_b200.aerosols")
+
+
+def test_wmo_params_vs_reference(ref, tmp_path):
+    """aerosols.wmo_params against SOS_INIT_PARAMWMO of the reference library: a generated file in the reference's fixed-column
+    layout at several wavelengths, and the reference's own WMO table where the reference tree is present."""
+    aer = _aer()
+    files = [ac.write_wmo_file(str(tmp_path / "Data_WMO_test"))]
+    real = "/root/reference/fic/Data_WMO_cor_2015_12_16"
+    if os.path.exists(real):
+        files.append(real)
+    if not hasattr(ref, "sos_init_paramwmo_"):
+        pytest.skip("SOS_INIT_PARAMWMO not in the reference library")
+    for path in files:
+        for wa in (0.4, 0.443, 0.55, 0.865, 0.91, 1.6, 2.13):
+            e, v1, v2, mr, mi, vol = ac.ref_wmo_params(ref, path, wa)
+            g1, g2, gr, gi, gv = aer.wmo_params(path, wa)
+            assert e == 0
+            assert np.array_equal(v1, g1) and np.array_equal(v2, g2) and np.array_equal(vol, gv), (path, wa)
+            assert np.array_equal(mr, gr) and np.array_equal(mi, gi), (path, wa, mr, gr, mi, gi)
+
+
+def test_aerosol_plan_host_logic(tmp_path):
+    """The component / model lists aerosols.plan builds: Mie table ranges (ALPHAF), index rounding, mixture weights."""
+    aer = _aer()
+    # mono-modal: the table is sized for CTE_WAMIN whatever the wavelength (SOS_AEROSOLS.F:1183)
+    p = aer.plan(aer.MonoModal(1.4449, -0.0040049, 1, 0.40, 0.60), [0.55, 0.865])
+    assert len(p.components) == 2 and p.models == [(0, [0], [1.0], 1), (0, [1], [1.0], 1)]
+    assert p.components[0][:2] == (1.445, -0.004) and p.components[0][3] == p.components[1][3] == 200.0
+    assert aer.round_index(1.4445, -0.004005) == (1.445, -0.00401)            # DNINT: halves away from zero
+    # bimodal: one table per mode and wavelength, ALPHAF from the wavelength; CVI normalised
+    b = aer.BimodalLnd(1.45, -0.004, 0.40, 0.60, 1.42, -0.008, 0.08, 0.45, cv_coarse=0.3, cv_fine=0.9)
+    p = aer.plan(b, [0.443, 2.13], itronc=0)
+    assert [c[3] for c in p.components] == [200.0, 100.0, 100.0, 100.0]
+    assert p.models[1] == (2, [2, 3], [0.3 / 1.2, 0.9 / 1.2], 0)
+    for c, (rm, sg) in zip(p.components[:2], ((0.40, 0.60), (0.08, 0.45))):
+        assert c[3] == ac.alphaf_for(ac.lnd_rmax(rm, sg), 0.443)
+    # WMO maritime: water-soluble + oceanic, weights N(I) / NTOT with N = C / V
+    f = ac.write_wmo_file(str(tmp_path / "wmo"))
+    p = aer.plan(aer.Wmo(f, 2), [0.91])
+    v1, v2, mr, mi, vol = aer.wmo_params(f, 0.91)
+    n = [0.05 / vol[1], 0.95 / vol[2]]
+    assert p.models == [(2, [0, 1], [n[0] / (0.0 / vol[0] + n[0] + n[1] + 0.0 / vol[3]), n[1] / (n[0] + n[1])], 1)]
+    assert [c[3] for c in p.components] == [50.0, 800.0] and p.components[1][:2] == (mr[2], mi[2])
+    with pytest.raises(ValueError):
+        aer.plan(aer.MonoModal(1.4, 0.01, 1, 0.4, 0.6), [0.55])               # positive imaginary part
+
+
+@pytest.mark.gpu
+def test_gpu_aerosols_front_end_wmo_demo(solver, ref, tmp_path):
+    """aerosols.run for the demo's aerosol description (-AER.Model 1 -AER.WMO.Model 2 -AER.Waref 0.550 -AER.AOTref 0.3 at
+    0.910 microns, exe/runSOS-ABS_demo.ksh) on a generated WMO table, against the reference's flow: SOS_INIT_PARAMWMO ->
+    SOS_MIE files -> SOS_GRANU -> mixture -> SOS_DECOMPO_LEGENDRE, and TA = KMAT1(WA) / KMAT1(WAREF) * AOT_REF."""
+    aer = _aer()
+    nbmu, xmu, xhr = ac.mie_angles(24, (0.0,))
+    os_nb, wa, waref, aot = 48, 0.910, 0.550, 0.3
+    f = ac.write_wmo_file(str(tmp_path / "wmo"))
+    got = aer.run(solver, nbmu, xmu, xhr, os_nb, aer.Wmo(f, 2), [wa], waref=waref, aot_ref=aot, itronc=1)[0]
+    k1 = {}
+    for w in (wa, waref):
+        e, v1, v2, mr, mi, vol = ac.ref_wmo_params(ref, f, w)
+        comps = [(mr[i], mi[i], 0.0001, (4000.0, 50.0, 800.0, 10.0)[i], 1, v1[i], v2[i], -999.0, w) for i in (1, 2)]
+        n = np.array([0.0 / vol[0], 0.05 / vol[1], 0.95 / vol[2], 0.0 / vol[3]])
+        ntot = 0.0
+        for x in n:
+            ntot = ntot + x
+        kc, pc, refs, _ = _reference_chain(ref, str(tmp_path), nbmu, xmu, xhr, comps, [(2, [0, 1], [n[1] / ntot, n[2] / ntot], 1)], os_nb)
+        k1[w] = refs[0]
+    d = k1[wa]
+    assert got.itronc == d["itronc"] and np.isclose(got.kmat1, d["kmat1"], rtol=2e-7) and abs(got.coef_tronca - d["coef_tronca"]) < 2e-7
+    assert np.isclose(got.ta, d["kmat1"] / k1[waref]["kmat1"] * aot, rtol=4e-7)
+    scale = np.abs(d["beta11"]).max()
+    for a, n in ((got.alpha, "alp"), (got.beta, "beta11"), (got.gamma, "gamma12"), (got.zeta, "zeta")):
+        assert np.abs(a - d[n]).max() <= 2e-7 * scale, n
+    print("[GPU aerosols front end] WMO maritime at 0.910 um: TA = %.6f (reference flow %.6f), truncation coefficient %.6f (%.6f)"
+          % (got.ta, d["kmat1"] / k1[waref]["kmat1"] * aot, got.coef_tronca, d["coef_tronca"]))
