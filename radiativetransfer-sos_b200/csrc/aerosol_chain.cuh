@@ -36,14 +36,18 @@
 // before it writes), the terms of the three sums over n go where C_n, S_n and D_n(alpha) were.
 struct AcMieWork {
   double *cna, *sna, *rgna, *igna, *rdna, *rdnb, *idnb, *ra, *ia, *rb, *ib, *tq1, *tq2, *tg;
+  size_t es;               // distance between consecutive elements of an array: 1, or 32 when the arrays of the 32 size parameters
+                           // of a warp are interleaved (element i of lane l at [i * 32 + l]: coalesced)
 };
 #define AC_WORK_ARRAYS 7
-AC_HD AcMieWork ac_work(double *base, size_t stride)
+AC_HD AcMieWork ac_work(double *base, size_t stride, size_t es = 1)
 {
   AcMieWork w;
-  w.cna = base; w.sna = base + stride; w.rgna = base + 2 * stride; w.igna = base + 3 * stride; w.rdna = base + 4 * stride;
-  w.rdnb = base + 5 * stride; w.idnb = base + 6 * stride;
-  w.ra = w.rgna + 1; w.ia = w.igna + 1; w.rb = w.rdnb + 1; w.ib = w.idnb + 1;      // RA(i) in the slot of RGNA(i) ...
+  const size_t a = stride * es;
+  w.es = es;
+  w.cna = base; w.sna = base + a; w.rgna = base + 2 * a; w.igna = base + 3 * a; w.rdna = base + 4 * a;
+  w.rdnb = base + 5 * a; w.idnb = base + 6 * a;
+  w.ra = w.rgna + es; w.ia = w.igna + es; w.rb = w.rdnb + es; w.ib = w.idnb + es;      // RA(i) in the slot of RGNA(i) ...
   w.tq1 = w.cna; w.tq2 = w.sna; w.tg = w.rdna;
   return w;
 }
@@ -69,11 +73,11 @@ AC_HD void ac_mie_orders(double alpha, int *n1, int *n2)
 AC_HD void ac_mie_chain_c(double alpha, const AcMieWork &w, int *n1, int *n2)
 {
   double cm2 = -sin(alpha), cm1 = cos(alpha);
-  w.cna[0] = cm2; w.cna[1] = cm1;
+  w.cna[(size_t)(0) * w.es] = cm2; w.cna[(size_t)(1) * w.es] = cm1;
   const int n2_0 = *n2;
   for (int i = 1; i <= n2_0; ++i) {
     const double c = (2 * i - 1.0) * cm1 / alpha - cm2;
-    w.cna[i + 1] = c;
+    w.cna[(size_t)(i + 1) * w.es] = c;
     cm2 = cm1; cm1 = c;
     if (c < 1.e+304) continue;
     *n2 = i; *n1 = i + 15;                              // C_n diverges: cut here (SOS_MIE.F:463-467)
@@ -83,13 +87,13 @@ AC_HD void ac_mie_chain_c(double alpha, const AcMieWork &w, int *n1, int *n2)
 AC_HD void ac_mie_chain_g(double alpha, const AcMieWork &w, int n2)
 {
   double x = 0.0, y = -1.0;
-  w.rgna[0] = 0.0; w.rgna[1] = 0.0; w.igna[0] = 0.0; w.igna[1] = -1.0;
+  w.rgna[(size_t)(0) * w.es] = 0.0; w.rgna[(size_t)(1) * w.es] = 0.0; w.igna[(size_t)(0) * w.es] = 0.0; w.igna[(size_t)(1) * w.es] = -1.0;
   for (int i = 1; i <= n2; ++i) {
     const double z = i / alpha;
     const double ww = ((z - x) * (z - x) + (y * y));
     const double xr = (z - x) / ww - z;
     const double yi = y / ww;
-    w.rgna[i + 1] = xr; w.igna[i + 1] = yi;
+    w.rgna[(size_t)(i + 1) * w.es] = xr; w.igna[(size_t)(i + 1) * w.es] = yi;
     x = xr; y = yi;
   }
 }
@@ -101,38 +105,38 @@ AC_HD void ac_mie_chain_db(double alpha, double rn, double in, const AcMieWork &
   const double x1 = rbeta * rbeta + ibeta * ibeta;
   const double x2 = rbeta / x1, x3 = ibeta / x1;
   double x = 0.0, y = 0.0;
-  w.rdnb[n1 + 1] = 0.0; w.idnb[n1 + 1] = 0.0;
+  w.rdnb[(size_t)(n1 + 1) * w.es] = 0.0; w.idnb[(size_t)(n1 + 1) * w.es] = 0.0;
   for (int i = n1 - 1; i >= 0; --i) {
     const double z = x + (i + 1.0) * x2;
     const double ww = y - (i + 1.0) * x3;
     const double x4 = z * z + ww * ww;
     x = (i + 1.0) * x2 - z / x4;
     y = -((i + 1.0) * x3) + ww / x4;
-    w.rdnb[i + 1] = x; w.idnb[i + 1] = y;
+    w.rdnb[(size_t)(i + 1) * w.es] = x; w.idnb[(size_t)(i + 1) * w.es] = y;
   }
 }
 AC_HD void ac_mie_chain_da(double alpha, const AcMieWork &w, int n1)
 {
   double x = 0.0;
-  w.rdna[n1 + 1] = 0.0;
+  w.rdna[(size_t)(n1 + 1) * w.es] = 0.0;
   for (int i = n1 - 1; i >= 0; --i) {
     const double z = (i + 1.0) / alpha;
     x = z - 1.0 / (x + z);
-    w.rdna[i + 1] = x;
+    w.rdna[(size_t)(i + 1) * w.es] = x;
   }
 }
 AC_HD void ac_mie_chain_s(double alpha, const AcMieWork &w, int n1, int n2)
 {
   double sp1 = 0.0, s0 = 1.0;                           // SNA(I+1), SNA(I)
-  w.sna[n1 + 1] = 0.0; w.sna[n1] = 1.0;
+  w.sna[(size_t)(n1 + 1) * w.es] = 0.0; w.sna[(size_t)(n1) * w.es] = 1.0;
   for (int i = n1 - 1; i >= 0; --i) {
     const double sm1 = (2.0 * i + 1.0) * s0 / alpha - sp1;
-    w.sna[i] = sm1;                                     // SNA(I-1)
+    w.sna[(size_t)(i) * w.es] = sm1;                                     // SNA(I-1)
     if (sm1 > 1.e+304) {                                // renormalise what has been computed (SOS_MIE.F:509-515)
       const int test = i - 1;
       const double xx = sm1;
-      for (int j = test; j <= n2; ++j) w.sna[j + 1] = w.sna[j + 1] / xx;
-      sp1 = w.sna[i + 1]; s0 = w.sna[i];
+      for (int j = test; j <= n2; ++j) w.sna[(size_t)(j + 1) * w.es] = w.sna[(size_t)(j + 1) * w.es] / xx;
+      sp1 = w.sna[(size_t)(i + 1) * w.es]; s0 = w.sna[(size_t)(i) * w.es];
     } else {
       sp1 = s0; s0 = sm1;
     }
@@ -140,13 +144,13 @@ AC_HD void ac_mie_chain_s(double alpha, const AcMieWork &w, int n1, int n2)
 }
 
 // SOS_MIE.F:527-531: S_n normalised so that S_0 = sin(alpha); q = SNA(0) / DSIN(ALPHA)
-AC_HD double ac_mie_snorm(double alpha, const AcMieWork &w) { return w.sna[1] / sin(alpha); }
+AC_HD double ac_mie_snorm(double alpha, const AcMieWork &w) { return w.sna[(size_t)(1) * w.es] / sin(alpha); }
 
 // ---- SOS_MIE.F:541-590: a_n, b_n of order i (1 <= i <= n2) ----
 AC_HD void ac_mie_ab(int i, double rn, double in, const AcMieWork &w)
 {
-  const double x1 = w.sna[i + 1], x2 = w.cna[i + 1], x3 = w.rdnb[i + 1], x4 = w.idnb[i + 1], x5 = w.rdna[i + 1];
-  const double x6 = w.rgna[i + 1], x7 = w.igna[i + 1];
+  const double x1 = w.sna[(size_t)(i + 1) * w.es], x2 = w.cna[(size_t)(i + 1) * w.es], x3 = w.rdnb[(size_t)(i + 1) * w.es], x4 = w.idnb[(size_t)(i + 1) * w.es], x5 = w.rdna[(size_t)(i + 1) * w.es];
+  const double x6 = w.rgna[(size_t)(i + 1) * w.es], x7 = w.igna[(size_t)(i + 1) * w.es];
   double y1 = x3 - rn * x5;
   double y2 = x4 - in * x5;
   double y3 = x3 - rn * x6 + in * x7;
@@ -172,23 +176,23 @@ AC_HD void ac_mie_ab(int i, double rn, double in, const AcMieWork &w)
     y3 = x1 * (x1 * z7 + x2 * z8) / z5 / z9;
     y4 = x1 * (x1 * z8 - x2 * z7) / z5 / z9;
   }
-  w.ra[i] = y2 * q;
-  w.ib[i] = y3 * q;
+  w.ra[(size_t)(i) * w.es] = y2 * q;
+  w.ib[(size_t)(i) * w.es] = y3 * q;
   q = -q;
-  w.rb[i] = y4 * q;
-  w.ia[i] = y1 * q;
+  w.rb[(size_t)(i) * w.es] = y4 * q;
+  w.ia[(size_t)(i) * w.es] = y1 * q;
 }
 
 // ---- SOS_MIE.F:606-630: the terms of the three sums over n (each independent of the running sums) ----
 AC_HD void ac_mie_qterms(int n, const AcMieWork &w)
 {
-  const double x = w.ra[n], y = w.ia[n], z = w.rb[n], t = w.ib[n];
-  const double xx = w.ra[n + 1], yy = w.ia[n + 1], zz = w.rb[n + 1], tt = w.ib[n + 1];
+  const double x = w.ra[(size_t)(n) * w.es], y = w.ia[(size_t)(n) * w.es], z = w.rb[(size_t)(n) * w.es], t = w.ib[(size_t)(n) * w.es];
+  const double xx = w.ra[(size_t)(n + 1) * w.es], yy = w.ia[(size_t)(n + 1) * w.es], zz = w.rb[(size_t)(n + 1) * w.es], tt = w.ib[(size_t)(n + 1) * w.es];
   const double a2 = (n + 1.0);
   const int j = (n & 1) ? -1 : 1;
-  w.tq1[n] = n * a2 * j * (y - t);
-  w.tq2[n] = (n * n) * a2 * a2 / (n + a2) * (x * x + y * y + z * z + t * t);
-  w.tg[n] = a2 * n / (a2 + n) * (n * (a2 + (double)1.f) * (a2 + (double)1.f) / (double)(2.f * n + 3.f) *
+  w.tq1[(size_t)(n) * w.es] = n * a2 * j * (y - t);
+  w.tq2[(size_t)(n) * w.es] = (n * n) * a2 * a2 / (n + a2) * (x * x + y * y + z * z + t * t);
+  w.tg[(size_t)(n) * w.es] = a2 * n / (a2 + n) * (n * (a2 + (double)1.f) * (a2 + (double)1.f) / (double)(2.f * n + 3.f) *
                                  (y * yy + x * xx + t * tt + z * zz) + y * t + x * z);
 }
 // which = 0: QEXT, 1: QSCA, 2: G (before the final scalings)
@@ -196,8 +200,8 @@ AC_HD double ac_mie_qsum(int which, int n2, const AcMieWork &w)
 {
   const double *t = which == 0 ? w.tq1 : which == 1 ? w.tq2 : w.tg;
   double s = 0.0;
-  if (which == 2) for (int n = 1; n <= n2; ++n) s = s - t[n];
-  else for (int n = 1; n <= n2; ++n) s = s + t[n];
+  if (which == 2) for (int n = 1; n <= n2; ++n) s = s - t[(size_t)n * w.es];
+  else for (int n = 1; n <= n2; ++n) s = s + t[(size_t)n * w.es];
   return s;
 }
 AC_HD void ac_mie_qfinal(double alpha, double *qext, double *qsca, double *g)
@@ -358,7 +362,12 @@ AC_HD void ac_min_int(int *p, int v)
 
 struct AcCoef {
   const double *ra, *ia, *rb, *ib;
-  AC_HDM void operator()(int n, double *ar, double *ai, double *br, double *bi) const { *ar = ra[n]; *ai = ia[n]; *br = rb[n]; *bi = ib[n]; }
+  size_t es;
+  AC_HDM void operator()(int n, double *ar, double *ai, double *br, double *bi) const
+  {
+    const size_t o = (size_t)n * es;
+    *ar = ra[o]; *ai = ia[o]; *br = rb[o]; *bi = ib[o];
+  }
 };
 
 // One record of the Mie table (SOS_MIE.F:399-646 for one ALPHA).  sh_n[2], sh_q[4]: CTA-shared.  Outputs: rec[0..2] = ALPHA, QEXT,
@@ -379,12 +388,12 @@ template <class Sync> AC_HD void ac_mie_record(int tid, int nthr, Sync sync, dou
   if (tid == ac_role(2, nthr)) { ac_mie_chain_s(alpha, w, n1, n2); sh_q[3] = ac_mie_snorm(alpha, w); }
   sync();
   const double q = sh_q[3];
-  for (int i = tid; i <= n2; i += nthr) w.sna[i + 1] = w.sna[i + 1] / q;
+  for (int i = tid; i <= n2; i += nthr) w.sna[(size_t)(i + 1) * w.es] = w.sna[(size_t)(i + 1) * w.es] / q;
   sync();
   for (int i = 1 + tid; i <= n2; i += nthr) ac_mie_ab(i, rn, in, w);
   if (tid == 0) {
-    w.ra[0] = 0.0; w.ia[0] = 0.0; w.rb[0] = 0.0; w.ib[0] = 0.0;
-    w.ra[n2 + 1] = 0.0; w.ia[n2 + 1] = 0.0; w.rb[n2 + 1] = 0.0; w.ib[n2 + 1] = 0.0;
+    w.ra[(size_t)(0) * w.es] = 0.0; w.ia[(size_t)(0) * w.es] = 0.0; w.rb[(size_t)(0) * w.es] = 0.0; w.ib[(size_t)(0) * w.es] = 0.0;
+    w.ra[(size_t)(n2 + 1) * w.es] = 0.0; w.ia[(size_t)(n2 + 1) * w.es] = 0.0; w.rb[(size_t)(n2 + 1) * w.es] = 0.0; w.ib[(size_t)(n2 + 1) * w.es] = 0.0;
   }
   sync();
   for (int n = 1 + tid; n <= n2; n += nthr) ac_mie_qterms(n, w);
@@ -399,7 +408,7 @@ template <class Sync> AC_HD void ac_mie_record(int tid, int nthr, Sync sync, dou
     rec[0] = (float)alpha; rec[1] = (float)qe; rec[2] = (float)qs; *g = gg;
   }
   sync();
-  AcCoef cf{w.ra, w.ia, w.rb, w.ib};
+  AcCoef cf{w.ra, w.ia, w.rb, w.ib, w.es};
   const double kma2 = sh_q[1];
   for (int j = tid; j <= 2 * nbmu; j += nthr) ac_mie_phase(rmu[j], alpha, kma2, n2, cf, &imie[j], &qmie[j], &umie[j]);
   sync();
@@ -584,4 +593,114 @@ template <class Sync> AC_HD void ac_model(int tid, int nthr, Sync sync, int nbmu
     scal[5] = ac_asym(ct, s.beta11[1] / z1); scal[6] = z1; scal[7] = (double)s.itronc;
     *ier = 0;
   }
+}
+
+// =====================================================================================================================
+// Mie tables with one size parameter per LANE (what the kernels run; ac_mie_record above is the same arithmetic with one size
+// parameter per CTA and serves the CPU tests as the plain serial routine).  ncu on the CTA-per-size-parameter kernel showed 56 %
+// of its FP64 instructions issued with one active lane (the five serial recurrences), each costing the FP64 pipe as much as a
+// full warp.  Here the 32 lanes of a warp run the same recurrence for 32 size parameters of similar magnitude (the work list is
+// sorted), their work arrays interleaved element by element (coalesced), and the phase functions are a second stage with one
+// (angle, 32 size parameters) task per warp.
+//   stage 1 (ac_coef_phase, phases 0..6 separated by CTA barriers; warp roles wr = 0..nw-1, nw >= 3):
+//     0: C_n (decides N1, N2) | G_n         1: D_n(m alpha) | D_n(alpha) | S_n + its normalisation factor
+//     2: S_n normalised                     3: a_n, b_n (orders strided over the warps)
+//     4: terms of the sums over n           5: QEXT | QSCA | G sums               6: final scalings, record header
+//   stage 2 (ac_mie_phase): Imie, Qmie, Umie of one angle, coefficients read from the stage-1 arrays
+// =====================================================================================================================
+struct AcLaneState { int n1, n2; double snorm, sum[3]; };
+#define AC_COEF_PHASES 7
+
+AC_HD void ac_coef_phase(int p, int wr, int nw, double alpha, double rn, double in, const AcMieWork &w, AcLaneState &st, float *rec, double *g,
+                         int *out_n2, double *out_qsca)
+{
+  switch (p) {
+  case 0: {
+    int n1, n2;
+    ac_mie_orders(alpha, &n1, &n2);
+    if (wr == 0) { ac_mie_chain_c(alpha, w, &n1, &n2); st.n1 = n1; st.n2 = n2; }
+    else if (wr == 1) ac_mie_chain_g(alpha, w, n2);
+    break;
+  }
+  case 1:
+    if (wr == 0) ac_mie_chain_db(alpha, rn, in, w, st.n1);
+    else if (wr == 1) ac_mie_chain_da(alpha, w, st.n1);
+    else if (wr == 2) { ac_mie_chain_s(alpha, w, st.n1, st.n2); st.snorm = ac_mie_snorm(alpha, w); }
+    break;
+  case 2:
+    for (int i = wr; i <= st.n2; i += nw) w.sna[(size_t)(i + 1) * w.es] = w.sna[(size_t)(i + 1) * w.es] / st.snorm;
+    break;
+  case 3:
+    for (int i = 1 + wr; i <= st.n2; i += nw) ac_mie_ab(i, rn, in, w);
+    if (wr == 0) {
+      const size_t e = (size_t)(st.n2 + 1) * w.es;
+      w.ra[0] = 0.0; w.ia[0] = 0.0; w.rb[0] = 0.0; w.ib[0] = 0.0;
+      w.ra[e] = 0.0; w.ia[e] = 0.0; w.rb[e] = 0.0; w.ib[e] = 0.0;
+    }
+    break;
+  case 4:
+    for (int n = 1 + wr; n <= st.n2; n += nw) ac_mie_qterms(n, w);
+    break;
+  case 5:
+    if (wr < 3) st.sum[wr] = ac_mie_qsum(wr, st.n2, w);
+    break;
+  default:
+    if (wr == 0) {
+      double qe = st.sum[0], qs = st.sum[1], gg = st.sum[2];
+      ac_mie_qfinal(alpha, &qe, &qs, &gg);
+      rec[0] = (float)alpha; rec[1] = (float)qe; rec[2] = (float)qs; *g = gg;
+      *out_n2 = st.n2; *out_qsca = qs;
+    }
+    break;
+  }
+}
+
+// ---- host only ----
+#include <algorithm>
+#include <vector>
+// Work list of the two stages: the records of all tables sorted by decreasing size parameter (work grows with it), cut into
+// groups of 32 (one warp), padded with table = -1; per group the length of its work arrays (the largest N1 + 4 of its lanes) and
+// its offset in the arena; groups packed into chunks that fit an arena of `budget` doubles (a chunk is one launch of each stage).
+struct AcMiePlan {
+  std::vector<int> item_table, item_rec;         // [ngroup * 32]
+  std::vector<long long> group_off;              // doubles, relative to the arena start of the group's chunk
+  std::vector<int> group_stride;
+  std::vector<int> chunk_first;                  // first group of every chunk, then ngroup
+  size_t arena = 0;                              // doubles
+};
+static inline AcMiePlan ac_mie_plan(const std::vector<long long> &rec0, const std::vector<int> &nrec, const std::vector<double> &alpha,
+                                    size_t budget)
+{
+  AcMiePlan p;
+  std::vector<std::pair<int, int>> items;
+  for (size_t t = 0; t < rec0.size(); ++t)
+    for (int r = 0; r < nrec[t]; ++r) items.push_back({(int)t, r});
+  std::stable_sort(items.begin(), items.end(), [&](const std::pair<int, int> &a, const std::pair<int, int> &b) {
+    return alpha[(size_t)rec0[a.first] + a.second] > alpha[(size_t)rec0[b.first] + b.second];
+  });
+  const size_t ngroup = (items.size() + 31) / 32;
+  p.item_table.assign(ngroup * 32, -1);
+  p.item_rec.assign(ngroup * 32, 0);
+  p.group_off.resize(ngroup);
+  p.group_stride.resize(ngroup);
+  size_t used = 0;
+  p.chunk_first.push_back(0);
+  for (size_t g = 0; g < ngroup; ++g) {
+    int n1max = 0;
+    for (size_t l = 0; l < 32 && g * 32 + l < items.size(); ++l) {
+      const size_t it = g * 32 + l;
+      p.item_table[it] = items[it].first; p.item_rec[it] = items[it].second;
+      const double a = alpha[(size_t)rec0[items[it].first] + items[it].second];
+      n1max = std::max(n1max, (int)trunc(a + a + 20));
+    }
+    const int stride = n1max + 4;
+    const size_t need = (size_t)AC_WORK_ARRAYS * stride * 32;
+    if (used > 0 && used + need > budget) { p.chunk_first.push_back((int)g); used = 0; }
+    p.group_off[g] = (long long)used;
+    p.group_stride[g] = stride;
+    used += need;
+    p.arena = std::max(p.arena, used);
+  }
+  p.chunk_first.push_back((int)ngroup);
+  return p;
 }

@@ -2,8 +2,10 @@
 // their integration over size distributions (SOS_GRANU), the mixture of modes (SOS_AEROSOLS) and the Legendre expansion with
 // the optional truncation (SOS_DECOMPO_LEGENDRE) -- what the reference runs serially on the host, through MIE files, for every
 // wavelength of a sweep and whose output are the alpha, beta, gamma, zeta coefficients the solver consumes.
-//   k_mie              persistent CTAs over (table, size parameter) work items, heaviest first; the five serial recurrences of a
-//                      size parameter on five warps, a_n / b_n one order per thread, the phase functions one angle per thread
+//   k_mie_coef         one CTA per group of 32 size parameters (work list sorted by size parameter, all tables together): the lanes
+//                      of a warp run the same serial recurrence for 32 size parameters, five recurrences on three warps, a_n / b_n
+//                      and the sums over n strided over the warps; work arrays interleaved lane by lane (coalesced)
+//   k_mie_phase        one warp per (group, scattering angle): the amplitude sums over n of 32 size parameters
 //   k_granu            one CTA per component: weights of all records in parallel, sums over records one angle per thread
 //   k_legendre_tables  P_k(mu_j), P^2_k(mu_j) once per angle set
 //   k_model            one CTA per aerosol model: mixture, truncation, expansion one order per thread
@@ -27,31 +29,53 @@ struct AcCtaSync { __device__ void operator()() const { __syncthreads(); } };
 
 struct MieTableDev { double rn, in; long long rec0; int nrec, pad; };
 struct MieItem { int table, rec; };
+struct MieGroupDev { long long off; int stride, pad; };
 struct GranuCompDev { long long rec0; int nrec, igranu; double alphaf, v1, v2, v3, wa; };
 
-constexpr int MIE_THREADS = 128, MIE_CTAS_PER_SM = 8;
+constexpr int COEF_WARPS = 4;
 
-__global__ void __launch_bounds__(MIE_THREADS, MIE_CTAS_PER_SM)
-k_mie(const MieTableDev *__restrict__ tables, const MieItem *__restrict__ items, int nitems, const double *__restrict__ alpha, int nbmu,
-      const double *__restrict__ rmu, double *__restrict__ work, size_t stride, unsigned *__restrict__ counter, float *__restrict__ rec,
-      double *__restrict__ g, float *__restrict__ imie, float *__restrict__ qmie, float *__restrict__ umie)
+// stage 1: blockIdx.x = group of the chunk that starts at group0
+__global__ void __launch_bounds__(COEF_WARPS * 32, 4)
+k_mie_coef(const MieTableDev *__restrict__ tables, const MieItem *__restrict__ items, const MieGroupDev *__restrict__ groups, int group0,
+           const double *__restrict__ alpha, double *__restrict__ arena, float *__restrict__ rec, double *__restrict__ g,
+           int *__restrict__ it_n2, double *__restrict__ it_qsca)
 {
-  __shared__ int sh_n[2];
-  __shared__ double sh_q[4];
-  __shared__ int sh_item;
-  const AcMieWork w = ac_work(work + (size_t)blockIdx.x * AC_WORK_ARRAYS * stride, stride);
-  const size_t nang = 2 * (size_t)nbmu + 1;
-  for (;;) {
-    if (threadIdx.x == 0) sh_item = (int)atomicAdd(counter, 1u);
+  __shared__ AcLaneState st[32];
+  const int grp = group0 + (int)blockIdx.x, lane = (int)threadIdx.x & 31, wr = (int)threadIdx.x >> 5;
+  const size_t it = (size_t)grp * 32 + lane;
+  const MieItem wi = items[it];
+  const bool valid = wi.table >= 0;
+  const MieGroupDev gd = groups[grp];
+  const AcMieWork w = ac_work(arena + gd.off + lane, (size_t)gd.stride, 32);
+  MieTableDev t{};
+  size_t r = 0;
+  double a = 1.0;
+  if (valid) { t = tables[wi.table]; r = (size_t)t.rec0 + wi.rec; a = alpha[r]; }
+  for (int ph = 0; ph < AC_COEF_PHASES; ++ph) {
+    if (valid) ac_coef_phase(ph, wr, COEF_WARPS, a, t.rn, t.in, w, st[lane], rec + 3 * r, g + r, it_n2 + it, it_qsca + it);
     __syncthreads();
-    const int it = sh_item;
-    if (it >= nitems) break;
-    const MieItem wi = items[it];
-    const MieTableDev t = tables[wi.table];
-    const size_t r = (size_t)t.rec0 + wi.rec;
-    ac_mie_record((int)threadIdx.x, MIE_THREADS, AcCtaSync(), alpha[r], t.rn, t.in, nbmu, rmu, w, sh_n, sh_q, rec + 3 * r, g + r,
-                  imie + r * nang, qmie + r * nang, umie + r * nang);
   }
+}
+
+// stage 2: one warp per (group, angle) of the chunk; tasks of the heaviest groups first
+__global__ void __launch_bounds__(128)
+k_mie_phase(const MieTableDev *__restrict__ tables, const MieItem *__restrict__ items, const MieGroupDev *__restrict__ groups, int group0,
+            int ngroups, int nang, const double *__restrict__ rmu, const double *__restrict__ alpha, const double *__restrict__ arena,
+            const int *__restrict__ it_n2, const double *__restrict__ it_qsca, float *__restrict__ imie, float *__restrict__ qmie,
+            float *__restrict__ umie)
+{
+  const long long task = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (task >= (long long)ngroups * nang) return;
+  const int grp = group0 + (int)(task / nang), j = (int)(task % nang), lane = (int)threadIdx.x & 31;
+  const size_t it = (size_t)grp * 32 + lane;
+  const MieItem wi = items[it];
+  if (wi.table < 0) return;
+  const MieGroupDev gd = groups[grp];
+  const AcMieWork w = ac_work(const_cast<double *>(arena) + gd.off + lane, (size_t)gd.stride, 32);
+  const size_t r = (size_t)tables[wi.table].rec0 + wi.rec;
+  const AcCoef cf{w.ra, w.ia, w.rb, w.ib, w.es};
+  const size_t o = r * (size_t)nang + j;
+  ac_mie_phase(rmu[j], alpha[r], it_qsca[it], it_n2[it], cf, imie + o, qmie + o, umie + o);
 }
 
 __global__ void __launch_bounds__(128)
@@ -114,43 +138,55 @@ struct DevTables {
   double *g = nullptr;
 };
 
-// ev_a is recorded right before the kernel: the stream is idle while the host allocates, so an earlier record would time the
-// growth of the memory pool as well
+// ev_a is recorded right before the first kernel: the stream is idle while the host allocates, so an earlier record would time
+// the growth of the memory pool as well
+constexpr size_t MIE_ARENA_DOUBLES = (size_t)1 << 28;      // 2 GB of work arrays per chunk of the work list
+
 int launch_mie(sosgpu_ctx *ctx, int nbmu, const double *d_rmu, const std::vector<HostTable> &tabs, const std::vector<double> &alpha,
                const DevTables &dt, SosFreeGuard &guard)
 {
   cudaStream_t st = ctx->stream;
   const size_t total = alpha.size();
+  const int nang = 2 * nbmu + 1;
   std::vector<MieTableDev> td(tabs.size());
-  std::vector<MieItem> items;
-  items.reserve(total);
-  double amax = 0.0;
+  std::vector<long long> rec0(tabs.size());
+  std::vector<int> nrec(tabs.size());
   for (size_t t = 0; t < tabs.size(); ++t) {
     td[t] = MieTableDev{tabs[t].rn, tabs[t].in, (long long)tabs[t].rec0, tabs[t].nrec, 0};
-    for (int r = 0; r < tabs[t].nrec; ++r) items.push_back(MieItem{(int)t, r});
-    amax = std::max(amax, tabs[t].alphaf);
+    rec0[t] = (long long)tabs[t].rec0; nrec[t] = tabs[t].nrec;
   }
-  std::stable_sort(items.begin(), items.end(), [&](const MieItem &a, const MieItem &b) {
-    return alpha[tabs[a.table].rec0 + a.rec] > alpha[tabs[b.table].rec0 + b.rec];      // the work of a record grows with alpha
-  });
-  const size_t stride = (size_t)trunc(amax + amax + 20) + 8;
-  const int sms = ctx->num_sms > 0 ? ctx->num_sms : 148;
-  const int grid = (int)std::min<size_t>(total, (size_t)sms * MIE_CTAS_PER_SM);
+  const AcMiePlan plan = ac_mie_plan(rec0, nrec, alpha, MIE_ARENA_DOUBLES);
+  const size_t nitem = plan.item_table.size(), ngroup = plan.group_off.size();
+  std::vector<MieItem> items(nitem);
+  for (size_t i = 0; i < nitem; ++i) items[i] = MieItem{plan.item_table[i], plan.item_rec[i]};
+  std::vector<MieGroupDev> gd(ngroup);
+  for (size_t g = 0; g < ngroup; ++g) gd[g] = MieGroupDev{plan.group_off[g], plan.group_stride[g], 0};
   Arena a;
-  const size_t o_tab = a.take(sizeof(MieTableDev) * td.size()), o_it = a.take(sizeof(MieItem) * items.size());
-  const size_t o_al = a.take(sizeof(double) * total), o_cnt = a.take(sizeof(unsigned));
-  const size_t o_work = a.take(sizeof(double) * AC_WORK_ARRAYS * stride * grid);
+  const size_t o_tab = a.take(sizeof(MieTableDev) * td.size()), o_it = a.take(sizeof(MieItem) * nitem), o_gd = a.take(sizeof(MieGroupDev) * ngroup);
+  const size_t o_al = a.take(sizeof(double) * total), o_n2 = a.take(sizeof(int) * nitem), o_q = a.take(sizeof(double) * nitem);
+  const size_t o_work = a.take(sizeof(double) * plan.arena);
   char *d = nullptr;
   CK(sos_dmalloc(ctx, &d, a.bytes)); guard.add(d);
   CK(cudaMemcpyAsync(d + o_tab, td.data(), sizeof(MieTableDev) * td.size(), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d + o_it, items.data(), sizeof(MieItem) * items.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_it, items.data(), sizeof(MieItem) * nitem, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_gd, gd.data(), sizeof(MieGroupDev) * ngroup, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d + o_al, alpha.data(), sizeof(double) * total, cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(d + o_cnt, 0, sizeof(unsigned), st));
   if (ctx->ev_a) cudaEventRecord(ctx->ev_a, st);
-  k_mie<<<grid, MIE_THREADS, 0, st>>>((const MieTableDev *)(d + o_tab), (const MieItem *)(d + o_it), (int)total, (const double *)(d + o_al), nbmu,
-                                      d_rmu, (double *)(d + o_work), stride, (unsigned *)(d + o_cnt), dt.rec, dt.g, dt.imie, dt.qmie, dt.umie);
-  CK(cudaGetLastError());
-  ctx->launches += 1;
+  for (size_t c = 0; c + 1 < plan.chunk_first.size(); ++c) {          // the arena is reused chunk after chunk, in stream order
+    const int g0 = plan.chunk_first[c], ng = plan.chunk_first[c + 1] - g0;
+    if (ng <= 0) continue;
+    k_mie_coef<<<ng, COEF_WARPS * 32, 0, st>>>((const MieTableDev *)(d + o_tab), (const MieItem *)(d + o_it), (const MieGroupDev *)(d + o_gd), g0,
+                                               (const double *)(d + o_al), (double *)(d + o_work), dt.rec, dt.g, (int *)(d + o_n2),
+                                               (double *)(d + o_q));
+    CK(cudaGetLastError());
+    const long long tasks = (long long)ng * nang;
+    k_mie_phase<<<(unsigned)((tasks + 3) / 4), 128, 0, st>>>((const MieTableDev *)(d + o_tab), (const MieItem *)(d + o_it),
+                                                             (const MieGroupDev *)(d + o_gd), g0, ng, nang, d_rmu, (const double *)(d + o_al),
+                                                             (const double *)(d + o_work), (const int *)(d + o_n2),
+                                                             (const double *)(d + o_q), dt.imie, dt.qmie, dt.umie);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+  }
   CK(cudaStreamSynchronize(st));             // the host vectors above are consumed
   return SOSGPU_OK;
 }

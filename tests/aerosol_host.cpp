@@ -33,6 +33,56 @@ int ach_mie(int nbmu, const double *rmu, double rn, double in, double alpha0, do
   }
   return nrec;
 }
+// The two-stage layout of the kernels (one size parameter per lane, interleaved work arrays, chunks that fit an arena budget),
+// lane by lane on the host with the same plan, phase functions and offsets as sosgpu_aerosols.cu: tables t = 0..ntab-1 with
+// (rn, in, alpha0, alphaf), records concatenated in table order.
+int ach_mie_lanes(int nbmu, const double *rmu, int ntab, const double *tab, long long budget_doubles, int cap, float *rec, double *g, float *imie,
+                  float *qmie, float *umie)
+{
+  const size_t nang = 2 * (size_t)nbmu + 1;
+  std::vector<long long> rec0; std::vector<int> nrec; std::vector<double> alpha;
+  for (int t = 0; t < ntab; ++t) {
+    const double a0 = tab[4 * t + 2], af = tab[4 * t + 3];
+    const int n = ach_mie_count(a0, af);
+    if (n < 0) return -1;
+    rec0.push_back((long long)alpha.size()); nrec.push_back(n);
+    double a = a0;
+    for (int k = 0; k < n; ++k) { alpha.push_back(a); a = a + ac_mie_step(a); }
+  }
+  if ((int)alpha.size() > cap) return -1;
+  const AcMiePlan p = ac_mie_plan(rec0, nrec, alpha, (size_t)budget_doubles);
+  std::vector<double> arena(p.arena, 0.0);
+  const size_t nitem = p.item_table.size();
+  std::vector<int> it_n2(nitem, 0); std::vector<double> it_q(nitem, 0.0);
+  const int nw = 4;
+  for (size_t c = 0; c + 1 < p.chunk_first.size(); ++c) {
+    for (int grp = p.chunk_first[c]; grp < p.chunk_first[c + 1]; ++grp) {          // stage 1: one CTA per group
+      AcLaneState st[32];
+      for (int ph = 0; ph < AC_COEF_PHASES; ++ph)
+        for (int wr = 0; wr < nw; ++wr)
+          for (int lane = 0; lane < 32; ++lane) {
+            const size_t it = (size_t)grp * 32 + lane;
+            const int t = p.item_table[it];
+            if (t < 0) continue;
+            const size_t r = (size_t)rec0[t] + p.item_rec[it];
+            const AcMieWork w = ac_work(arena.data() + p.group_off[grp] + lane, (size_t)p.group_stride[grp], 32);
+            ac_coef_phase(ph, wr, nw, alpha[r], tab[4 * t], tab[4 * t + 1], w, st[lane], rec + 3 * r, g + r, &it_n2[it], &it_q[it]);
+          }
+    }
+    for (int grp = p.chunk_first[c]; grp < p.chunk_first[c + 1]; ++grp)            // stage 2: one warp per (group, angle)
+      for (size_t j = 0; j < nang; ++j)
+        for (int lane = 0; lane < 32; ++lane) {
+          const size_t it = (size_t)grp * 32 + lane;
+          const int t = p.item_table[it];
+          if (t < 0) continue;
+          const size_t r = (size_t)rec0[t] + p.item_rec[it];
+          const AcMieWork w = ac_work(arena.data() + p.group_off[grp] + lane, (size_t)p.group_stride[grp], 32);
+          const AcCoef cf{w.ra, w.ia, w.rb, w.ib, w.es};
+          ac_mie_phase(rmu[j], alpha[r], it_q[it], it_n2[it], cf, &imie[r * nang + j], &qmie[r * nang + j], &umie[r * nang + j]);
+        }
+  }
+  return (int)alpha.size();
+}
 int ach_granu(int nrec, const float *rec, const float *imie, const float *qmie, const float *umie, int nang, double alphaf, int igranu,
               double v1, double v2, double v3, double wa, double *out, double *p11, double *p12, double *p33)
 {

@@ -113,6 +113,28 @@ def test_host_mie_bit_identical(host, ref, tmp_path, case):
     print("[Mie m=%g%+gi alphaf=%g] %d records x %d angles identical to SOS_MIE" % (rn, in_, af, r["g"].size, 2 * nbmu + 1))
 
 
+def test_host_mie_lane_layout_bit_identical(host, ref, tmp_path):
+    """The layout the kernels run -- work list of all tables sorted by size parameter, 32 size parameters per warp with interleaved
+    work arrays, a_n / b_n in place, chunks that fit an arena budget -- stepped lane by lane on the host with the kernels' own plan
+    and phase functions: still 0 differing values against SOS_MIE, with one chunk and with many."""
+    nbmu, xmu, xhr = ac.mie_angles(6, (0.0,))
+    nang = 2 * nbmu + 1
+    refs = [ac.ref_mie(ref, str(tmp_path), nbmu, xmu, xhr, *t, name="L%d.bin" % i)[1] for i, t in enumerate(TABLES)]
+    n = sum(r["g"].size for r in refs)
+    tab = np.array(TABLES).ravel().copy()
+    for budget in (1 << 40, 3_000_000):
+        rec, g = np.zeros((n, 3), np.float32), np.zeros(n)
+        im, qm, um = (np.zeros((n, nang), np.float32) for _ in range(3))
+        k = host.ach_mie_lanes(nbmu, _P(xmu), len(TABLES), _P(tab), C.c_longlong(budget), n, _F(rec), _P(g), _F(im), _F(qm), _F(um))
+        assert k == n
+        o = 0
+        for r in refs:
+            m = r["g"].size
+            for a, b in ((rec, "rec"), (g, "g"), (im, "imie"), (qm, "qmie"), (um, "umie")):
+                assert np.array_equal(a[o:o + m], r[b]), (budget, b)
+            o += m
+
+
 def test_host_mie_count_is_grid(host):
     assert host.ach_mie_count(0.0001, 200.0) == 4000
     assert host.ach_mie_count(0.0001, 4990.0) == 3900 + 4890
