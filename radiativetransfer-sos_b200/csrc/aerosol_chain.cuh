@@ -673,11 +673,32 @@ static inline AcMiePlan ac_mie_plan(const std::vector<long long> &rec0, const st
 {
   AcMiePlan p;
   std::vector<std::pair<int, int>> items;
-  for (size_t t = 0; t < rec0.size(); ++t)
-    for (int r = 0; r < nrec[t]; ++r) items.push_back({(int)t, r});
-  std::stable_sort(items.begin(), items.end(), [&](const std::pair<int, int> &a, const std::pair<int, int> &b) {
-    return alpha[(size_t)rec0[a.first] + a.second] > alpha[(size_t)rec0[b.first] + b.second];
-  });
+  items.reserve(alpha.size());
+  bool same_grid = true;                          // tables that start at the same size parameter share one grid: record r of every
+  int longest = 0;                                // table has the same alpha, and the sorted list is "r descending, table ascending"
+  for (size_t t = 0; t < rec0.size(); ++t) {
+    same_grid = same_grid && nrec[t] > 0 && alpha[(size_t)rec0[t]] == alpha[(size_t)rec0[0]];
+    longest = std::max(longest, nrec[t]);
+  }
+  if (same_grid) {
+    std::vector<int> by_len(rec0.size());
+    for (size_t t = 0; t < rec0.size(); ++t) by_len[t] = (int)t;
+    std::stable_sort(by_len.begin(), by_len.end(), [&](int a, int b) { return nrec[a] > nrec[b]; });
+    std::vector<int> live;                        // tables with nrec > r, in table order
+    size_t next = 0;
+    for (int r = longest - 1; r >= 0; --r) {
+      bool grew = false;
+      while (next < by_len.size() && nrec[by_len[next]] > r) { live.push_back(by_len[next++]); grew = true; }
+      if (grew) std::sort(live.begin(), live.end());
+      for (int t : live) items.push_back({t, r});
+    }
+  } else {
+    for (size_t t = 0; t < rec0.size(); ++t)
+      for (int r = 0; r < nrec[t]; ++r) items.push_back({(int)t, r});
+    std::stable_sort(items.begin(), items.end(), [&](const std::pair<int, int> &a, const std::pair<int, int> &b) {
+      return alpha[(size_t)rec0[a.first] + a.second] > alpha[(size_t)rec0[b.first] + b.second];
+    });
+  }
   const size_t ngroup = (items.size() + 31) / 32;
   p.item_table.assign(ngroup * 32, -1);
   p.item_rec.assign(ngroup * 32, 0);
@@ -686,14 +707,12 @@ static inline AcMiePlan ac_mie_plan(const std::vector<long long> &rec0, const st
   size_t used = 0;
   p.chunk_first.push_back(0);
   for (size_t g = 0; g < ngroup; ++g) {
-    int n1max = 0;
     for (size_t l = 0; l < 32 && g * 32 + l < items.size(); ++l) {
       const size_t it = g * 32 + l;
       p.item_table[it] = items[it].first; p.item_rec[it] = items[it].second;
-      const double a = alpha[(size_t)rec0[items[it].first] + items[it].second];
-      n1max = std::max(n1max, (int)trunc(a + a + 20));
     }
-    const int stride = n1max + 4;
+    const double a = alpha[(size_t)rec0[items[g * 32].first] + items[g * 32].second];      // the list is sorted: lane 0 is the largest
+    const int stride = (int)trunc(a + a + 20) + 4;
     const size_t need = (size_t)AC_WORK_ARRAYS * stride * 32;
     if (used > 0 && used + need > budget) { p.chunk_first.push_back((int)g); used = 0; }
     p.group_off[g] = (long long)used;

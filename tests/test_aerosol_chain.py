@@ -119,6 +119,11 @@ def test_host_mie_lane_layout_bit_identical(host, ref, tmp_path):
     and phase functions: still 0 differing values against SOS_MIE, with one chunk and with many."""
     nbmu, xmu, xhr = ac.mie_angles(6, (0.0,))
     nang = 2 * nbmu + 1
+    for tables in (TABLES, TABLES[:2] + [(1.5, -0.01, 0.5, 30.0)]):          # one shared grid (linear-time plan) / grids that differ (sort)
+        _lane_layout_case(host, ref, tmp_path, nbmu, xmu, xhr, nang, tables)
+
+
+def _lane_layout_case(host, ref, tmp_path, nbmu, xmu, xhr, nang, TABLES):
     refs = [ac.ref_mie(ref, str(tmp_path), nbmu, xmu, xhr, *t, name="L%d.bin" % i)[1] for i, t in enumerate(TABLES)]
     n = sum(r["g"].size for r in refs)
     tab = np.array(TABLES).ravel().copy()
