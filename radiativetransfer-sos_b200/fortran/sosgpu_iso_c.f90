@@ -51,6 +51,18 @@ module sosgpu_iso_c
     real(c_double)    :: tr, hr, ta, ha, zmin, zmax
   end type
 
+  type, bind(c) :: sosgpu_aer_component     ! one aerosol mode at one wavelength (SOS_MIE / SOS_GRANU arguments)
+    real(c_double)    :: rn, in               ! refractive index, in <= 0
+    real(c_double)    :: alpha0, alphaf       ! size-parameter range of its Mie table
+    integer(c_int)    :: igranu               ! 1 log-normal (v1 modal radius, v2 sigma), 2 Junge (v1 r0, v2 slope, v3 rmax)
+    real(c_double)    :: v1, v2, v3, wa
+  end type
+  type, bind(c) :: sosgpu_aer_model         ! one wavelength: mixture of components + truncation option
+    integer(c_int)    :: ncomp                ! 0: comp(1) as it is; 1..4: mixture
+    integer(c_int)    :: comp(4)              ! 0-based indices into the component list
+    real(c_double)    :: weight(4)            ! number fractions (N(I)/NTOT, normalised CVI)
+    integer(c_int)    :: itronc
+  end type
   type, bind(c) :: sosgpu_term_out
     type(c_ptr) :: rec, n_fourier, n_scatter, stop_reason, emoins, eplus, ttot_tronc, ttot_vrai, tauout, ier
   end type
@@ -160,6 +172,26 @@ module sosgpu_iso_c
       type(c_ptr), value :: ctx, batch
     end subroutine
     ! ---- SOS_Up.txt / SOS_Down.txt (SOS_ABS_MAIN.F:2250-2519), byte-compatible ---------------------------------------
+    ! aerosol optics of a wavelength list (SOS_MIE -> SOS_GRANU -> mixture -> SOS_DECOMPO_LEGENDRE); outputs may be c_null_ptr
+    integer(c_int) function sosgpu_aerosols(ctx, nbmu, xmu, xhr, ncomp, comp, nmodel, models, os_nb, comp_k, comp_phase, &
+        comp_ier, scal, coef, phase, model_ier) bind(c, name="sosgpu_aerosols")
+      import :: c_ptr, c_int, sosgpu_aer_component, sosgpu_aer_model
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nbmu, ncomp, nmodel, os_nb
+      type(c_ptr), value :: xmu, xhr                   ! XMU(-nbmu:nbmu), XHR(-nbmu:nbmu)
+      type(sosgpu_aer_component), intent(in) :: comp(*)
+      type(sosgpu_aer_model), intent(in) :: models(*)
+      type(c_ptr), value :: comp_k, comp_phase, comp_ier   ! [3,ncomp], [nang,3,ncomp], [ncomp]
+      type(c_ptr), value :: scal, coef, phase, model_ier   ! [8,nmodel], [0:os_nb,6,nmodel], [nang,4,nmodel], [nmodel]
+    end function
+    integer(c_int) function sosgpu_write_aerosols(path, os_nb, kmat1, kmat2, asym, coef_tronca, piztr, alp, beta11, gamma12, zeta) &
+        bind(c, name="sosgpu_write_aerosols")
+      import :: c_char, c_int, c_double
+      character(kind=c_char), intent(in) :: path(*)    ! NUL-terminated
+      integer(c_int), value :: os_nb
+      real(c_double), value :: kmat1, kmat2, asym, coef_tronca, piztr
+      real(c_double), intent(in) :: alp(0:*), beta11(0:*), gamma12(0:*), zeta(0:*)
+    end function
     integer(c_int) function sosgpu_write_updown(fic_up, fic_down, nbmu, itrphi, phios, pas_phi, zout, phi_fin, theta_fin, &
                                                 up, down, nphi_cap, fix_sca_index) bind(c, name="sosgpu_write_updown")
       import :: c_int, c_double, c_char
