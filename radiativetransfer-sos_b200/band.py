@@ -99,7 +99,14 @@ def run_band(solver, tables, kdis_ai, userprofil, altabs, ro, waves, itrphi=1, p
             aiks.append(a)
             owner.append(w)
     # ---- per-term profiles (device) ----
-    nt, z, h, pa, pm, ier, tau = solver.profile_chain(tables, userprofil, altabs, ro, pterms, text_hop=True, want_tauabs=True)
+    if tables is None:                                        # -AP.AbsProfile.Type 7 for every wavelength: no gas tables needed
+        if any(wv.absprofil != 7 for wv in waves):
+            raise ValueError("run_band without CKD tables: every wavelength must have absprofil = 7 (no gaseous absorption)")
+        altabs = np.linspace(120.0, 0.0, 50) if altabs is None else altabs
+        tau = np.zeros((len(pterms), 50))
+        nt, z, h, pa, pm, ier = solver.profile(altabs, tau, pterms, text_hop=True)
+    else:
+        nt, z, h, pa, pm, ier, tau = solver.profile_chain(tables, userprofil, altabs, ro, pterms, text_hop=True, want_tauabs=True)
     if ier.any():
         bad = int(np.flatnonzero(ier)[0])
         raise RuntimeError("profile chain: term %d of wavelength %d failed with code %d" % (bad, owner[bad], int(ier[bad])))
@@ -145,6 +152,8 @@ def run_band(solver, tables, kdis_ai, userprofil, altabs, ro, waves, itrphi=1, p
                 api.write_trans(os.path.join(d, "SOS_Trans.txt"), o.tetas, gr.ttot_tronc[w], gr.ttot_vrai[w], res.tdifmus[w],
                                 np.asarray(o.rmu)[N + 1:2 * N + 1], res.tdifmug[w, :N])
             if flux:
+                if userprofil is None:
+                    raise ValueError("the Flux file needs the gas atmosphere's altitudes (userprofil)")
                 last = first[w + 1] - 1                       # TAUABS of the last CKD term, as SOS_PROC leaves it (:3860)
                 api.write_flux(os.path.join(d, "SOS_Flux.txt"), o.tetas, gr.ttot_tronc[w], gr.ttot_vrai[w], gr.emoins[w], gr.eplus[w],
                                wv.tr, wv.hr, wv.ta, wv.ha, np.asarray(userprofil)[:, 0], tau[last])

@@ -1,0 +1,182 @@
+"""Keyword-driven front end: what SOS_ABS_MAIN + SOS_PROC do for ONE wavelength from the command-line keywords
+(SOS_ABS_MAIN.F:213-912, SOS_PROC.F:1218-3874), for a LIST of wavelengths with every stage on the device:
+
+    angles        SOS_ANGLES            synth.sos_angles (radiance angles + solar angle), mie_angles (phase-function angles)   host
+    aerosols      SOS_AEROSOLS          aerosols.run: all wavelengths in one device call
+    surface       SOS_SURFACE           Solver.glitter / roujean / surface_bpdf / bpdf_ajout_brdf                              device
+    profiles      SOS_PROFIL (+ gas)    band.run_band -> Solver.profile / profile_chain                                        device
+    solves        SOS, SOS_OS, SOS_AGGREGATE, SOS_TRPHI_OPTION   band.run_band                                                 device
+    files         SOS_Up / SOS_Down / SOS_Result.bin / Trans / Flux, aerosol result file                                       host
+
+Supported keyword values: -SURF.Type 0 1 2 3 4 5 (6: the Nadal series generator is not built); -AER.Model 0 1 3 (2 4 5: not built);
+-AP.AbsProfile.Type 7 (no gaseous absorption), or any type with the gas atmosphere and CKD tables handed in by the caller (`gas=`:
+the standard-atmosphere tables of the reference are data of the reference, not part of this package); user angle files are not
+read.  Unsupported values raise NotImplementedError naming the keyword; nothing is silently replaced.  No CPU fallback."""
+import os
+
+import numpy as np
+
+from . import aerosols, api, band, keywords, synth
+from .formats import round_e
+
+DEFAULT_NBMU_LUM, DEFAULT_NBMU_MIE = 24, 40                      # inc/SOS.h:508-514
+DEFAULT_OS_NB, DEFAULT_OS_NS, DEFAULT_OS_NM = 80, 48, 128        # inc/SOS.h:521-535
+HT_STD_PSURF = 1013.0                                            # CTE_HT_STD_PSURF (inc/SOS.h:192)
+
+
+def expansion_orders(nb_gauss_mie, nb_gauss_lum):
+    """OS_NB, OS_NS, OS_NM from the numbers of Gauss angles as given on the command line (None = keyword absent)
+    (SOS_ANGLES.F:303-329)."""
+    os_nb = DEFAULT_OS_NB if nb_gauss_mie is None else 2 * nb_gauss_mie
+    if nb_gauss_lum is None:
+        os_ns, os_nm = DEFAULT_OS_NS, DEFAULT_OS_NM
+    else:
+        os_ns = 2 * nb_gauss_lum
+        os_nm = os_nb + os_ns
+    if os_nm < os_nb + os_ns:
+        raise ValueError("OS_NM < OS_NB + OS_NS (SOS_ANGLES error 947)")
+    return os_nb, os_ns, os_nm
+
+
+def mie_angles(nb_gauss):
+    """Angles of the phase-function calculations (SOS_ANGLES_GAUSS_USER with USAGE = 'MIE', SOS_ANGLES.F:713-860): the Gauss angles
+    in ascending mu, through the D21.14 fields of the angles file SOS_AEROSOLS reads back (format 300, :639)."""
+    mu, w = synth.sos_gauss(nb_gauss + 1)
+    mu, w = round_e(np.sort(mu[:nb_gauss]), 14), round_e(np.asarray(w[:nb_gauss])[np.argsort(mu[:nb_gauss])], 14)
+    n = nb_gauss
+    xmu, xhr = np.zeros(2 * n + 1), np.zeros(2 * n + 1)
+    xmu[n + 1:], xhr[n + 1:] = mu, w
+    xmu[:n], xhr[:n] = -mu[::-1], w[::-1]
+    return n, xmu, xhr
+
+
+def rayleigh_thickness(psurf, wa):
+    """CNES formulation (Perbos, 1982) of the molecular optical thickness (SOS_PROC.F:3331-3334)."""
+    return (psurf / HT_STD_PSURF) * 1.e-4 * (float(np.float32(84.35)) / wa ** 4 - float(np.float32(1.225)) / wa ** 5
+                                             + float(np.float32(1.4)) / wa ** 6)
+
+
+def aerosol_model(kw):
+    """-AER.* keywords -> a model of aerosols.py."""
+    m = kw.get("-AER.Model")
+    if m == 0:
+        sd = kw.get("-AER.MMD.SDtype")
+        if sd == 1:
+            return aerosols.MonoModal(kw["-AER.MMD.MRwa"], kw["-AER.MMD.MIwa"], 1, kw["-AER.MMD.LNDradius"], kw["-AER.MMD.LNDvar"])
+        if sd == 2:
+            return aerosols.MonoModal(kw["-AER.MMD.MRwa"], kw["-AER.MMD.MIwa"], 2, kw["-AER.MMD.JD.rmin"], kw["-AER.MMD.JD.slope"],
+                                      kw.get("-AER.MMD.JD.rmax", 50.0))             # CTE_DEFAULT_AER_JUNGE_RMAX
+        raise ValueError("-AER.MMD.SDtype must be 1 or 2")
+    if m == 1:
+        root = os.environ.get("SOS_ABS_ROOT", "")
+        data = os.path.join(root, "fic", "Data_WMO_cor_2015_12_16")                  # CTE_AER_DATAWMO
+        return aerosols.Wmo(data, kw["-AER.WMO.Model"],
+                            [kw.get(k, 0.0) for k in ("-AER.WMO.DL", "-AER.WMO.WS", "-AER.WMO.OC", "-AER.WMO.SO")])
+    if m == 3:
+        b = aerosols.BimodalLnd(kw["-AER.BMD.CM.MRwa"], kw["-AER.BMD.CM.MIwa"], kw["-AER.BMD.CM.SDradius"], kw["-AER.BMD.CM.SDvar"],
+                                kw["-AER.BMD.FM.MRwa"], kw["-AER.BMD.FM.MIwa"], kw["-AER.BMD.FM.SDradius"], kw["-AER.BMD.FM.SDvar"])
+        if kw.get("-AER.BMD.VCdef") == 1:
+            b.cv_coarse, b.cv_fine = kw["-AER.BMD.CoarseVC"], kw["-AER.BMD.FineVC"]
+        elif kw.get("-AER.BMD.VCdef") == 2:
+            b.rtauct = kw["-AER.BMD.RAOT"]
+            ref = (kw["-AER.BMD.CM.MRwaref"], kw["-AER.BMD.CM.MIwaref"], kw["-AER.BMD.FM.MRwaref"], kw["-AER.BMD.FM.MIwaref"])
+            waref = kw["-AER.Waref"]
+            sim = (b.coarse_rn, b.coarse_in, b.fine_rn, b.fine_in)
+            b.coarse_rn, b.coarse_in, b.fine_rn, b.fine_in = (
+                (lambda wa, r=r, s=s: r if wa == waref else s) for r, s in zip(ref, sim))
+        else:
+            raise ValueError("-AER.BMD.VCdef must be 1 or 2")
+        return b
+    raise NotImplementedError("-AER.Model %r: only 0 (mono-modal), 1 (WMO) and 3 (bimodal log-normal) are built" % (m,))
+
+
+def surface(solver, kw, nbmu, rmu, ga, os_nb, os_ns, os_nm):
+    """-SURF.* keywords -> (fields of synth.Optics, direct-term models of SOS_TRPHI).  The surface records are computed on the
+    device for this angle set (the reference caches them in -SURF.Dir; a cache is the caller's business)."""
+    t = kw["-SURF.Type"]
+    o, direct = dict(rho=kw["-SURF.Alb"]), {}
+    if t == 0:
+        return o, direct
+    if t == 2:
+        o.update(ifresnel=1, ind_surf=kw["-SURF.Ind"])
+        return o, direct
+    if t == 1:
+        surf, _ = solver.glitter(nbmu, rmu, ga, kw["-SURF.Glitter.Wind"], kw["-SURF.Ind"], os_nb, os_ns, os_nm)
+        o.update(imat_surf=1, igli=1, surf=surf, ind_surf=kw["-SURF.Ind"], wind=kw["-SURF.Glitter.Wind"])
+        return o, direct
+    if t in (3, 4, 5):
+        k = (kw["-SURF.Roujean.K0"], kw["-SURF.Roujean.K1"], kw["-SURF.Roujean.K2"])
+        surf = solver.roujean(nbmu, rmu, os_nb, *k)
+        direct["roujean"] = k
+        if t in (4, 5):
+            bpdf = solver.surface_bpdf(t, nbmu, rmu, ga, kw["-SURF.Ind"], os_nb, os_ns, os_nm)
+            surf = solver.bpdf_ajout_brdf(bpdf, surf)
+            direct["irondeaux" if t == 4 else "ibreon"] = 1
+            o["ind_surf"] = kw["-SURF.Ind"]
+        o.update(imat_surf=1, surf=surf)
+        return o, direct
+    raise NotImplementedError("-SURF.Type %r: the Nadal series generator (6) is not built" % (t,))
+
+
+def run_keywords(solver, argv, wavelengths=None, gas=None):
+    """Runs the simulation the keywords describe, for `wavelengths` (microns; default: the one of -SOS_Main.Wa).  gas: None with
+    -AP.AbsProfile.Type 7, else dict(tables=, kdis_ai=, userprofil=, altabs=, ro=, lamb1=[per wavelength]) as band.run_band
+    takes them.  Results go to <-SOS_Main.ResRoot>/SOS/<wavelength>/ under the names of -SOS.ResFileUp / -SOS.ResFileDown /
+    -SOS.ResBin (+ -SOS.Trans / -SOS.Flux), the aerosol result files to <ResRoot>/AER.  Returns (band.BandResult, [AerosolOptics])."""
+    kw = keywords.parse(argv)
+    for k in ("-ANG.Rad.UserAngFile", "-ANG.Aer.UserAngFile", "-AER.UserFile", "-SURF.File", "-SOS.ResFileUp.UserAng", "-SOS.ResFileDown.UserAng"):
+        if k in kw:
+            raise NotImplementedError("%s: user angle / user data files are not read by this front end" % k)
+    wl = [float(w) for w in (wavelengths if wavelengths is not None else [kw["-SOS_Main.Wa"]])]
+    nb_lum, nb_mie = kw.get("-ANG.Rad.NbGauss"), kw.get("-ANG.Aer.NbGauss")
+    os_nb, os_ns, os_nm = expansion_orders(nb_mie, nb_lum)
+    rmu, ga, n0, _ = synth.sos_angles(nb_lum or DEFAULT_NBMU_LUM, kw["-ANG.Thetas"])
+    nbmu = (rmu.size - 1) // 2
+    mie_n, xmu, xhr = mie_angles(nb_mie or DEFAULT_NBMU_MIE)
+    absprofil = kw["-AP.AbsProfile.Type"]
+    if absprofil != 7 and gas is None:
+        raise NotImplementedError("-AP.AbsProfile.Type %d needs the gas atmosphere and the CKD tables (gas=...): the standard "
+                                  "atmospheres of the reference are not part of this package" % absprofil)
+    # ---- aerosols: all wavelengths in one device call ----
+    aot_ref = kw.get("-AER.AOTref", 0.0)
+    if aot_ref > 0.0:
+        aer = aerosols.run(solver, mie_n, xmu, xhr, os_nb, aerosol_model(kw), wl, waref=kw["-AER.Waref"], aot_ref=aot_ref,
+                           itronc=kw["-AER.Tronca"])
+    else:                                                         # no aerosols: PIZ = 0, coefficients 0 (SOS_AEROSOLS.F:1136-1139)
+        z = np.zeros(os_nb + 1)
+        aer = [aerosols.AerosolOptics(w, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0, z, z, z, z, 0.0) for w in wl]
+    # ---- surface: once (the keywords carry one refractive index for all wavelengths) ----
+    sf, direct = surface(solver, kw, nbmu, rmu, ga, os_nb, os_ns, os_nm)
+    solver.set_direct_models(**direct)
+    itype = kw["-AP.AerProfile.Type"]
+    waves = []
+    for k, (w, a) in enumerate(zip(wl, aer)):
+        f = aerosols.through_result_file(a)
+        o = synth.Optics(nbmu=nbmu, rmu=rmu.copy(), ga=ga, n0=n0, tetas=kw["-ANG.Thetas"], os_nb=os_nb, alpha=f["alpha"], beta=f["beta"],
+                         gamma=f["gamma"], zeta=f["zeta"], a_trunc=f["a_trunc"], piztr=f["piztr"], igmax=kw["-SOS.IGmax"],
+                         ipolar=kw["-SOS.Ipolar"], zout=kw["-SOS.OutputAlt"], **sf)
+        tr = kw["-AP.MOT"] if "-AP.MOT" in kw else rayleigh_thickness(kw.get("-AP.Psurf", HT_STD_PSURF), w)
+        waves.append(band.Wavelength(optics=o, lamb1=(gas["lamb1"][k] if gas else 1), tr=tr, ta=a.ta, hr=kw.get("-AP.HR", 8.0),
+                                     ha=kw.get("-AP.AerHS.HA", 2.0), absprofil=absprofil, iprofil=itype,
+                                     zmin=kw.get("-AP.AerLayer.Zmin", 0.0), zmax=kw.get("-AP.AerLayer.Zmax", 0.0), name="%.6f" % w))
+    root = kw["-SOS_Main.ResRoot"]
+    g = gas or {}
+    res = band.run_band(solver, g.get("tables"), g.get("kdis_ai"), g.get("userprofil"), g.get("altabs"), g.get("ro"), waves,
+                        itrphi=kw["-SOS.View"], phios=kw.get("-SOS.View.Phi", 0.0), pas_phi=kw.get("-SOS.View.Dphi", 30),
+                        outdir=os.path.join(root, "SOS"), trans="-SOS.Trans" in kw, flux="-SOS.Flux" in kw and gas is not None)
+    # ---- the reference's file names ----
+    names = {"SOS_Up.txt": kw["-SOS.ResFileUp"], "SOS_Down.txt": kw["-SOS.ResFileDown"], "SOS_Result.bin": kw["-SOS.ResBin"],
+             "SOS_Trans.txt": kw.get("-SOS.Trans"), "SOS_Flux.txt": kw.get("-SOS.Flux")}
+    for d in res.dirs:
+        for src, dst in names.items():
+            p = os.path.join(d, src)
+            if dst and dst != src and os.path.exists(p):
+                os.replace(p, os.path.join(d, dst))
+    if aot_ref > 0.0:
+        os.makedirs(os.path.join(root, "AER"), exist_ok=True)
+        base = kw.get("-AER.ResFile", "Aerosols.txt")
+        for w, a in zip(wl, aer):
+            name = base if len(wl) == 1 else "%s_%.6f" % (base, w)
+            api.write_aerosols(os.path.join(root, "AER", name), os_nb, a.kmat1, a.kmat2, a.asym, a.coef_tronca, a.piztr, a.alpha, a.beta,
+                               a.gamma, a.zeta)
+    return res, aer

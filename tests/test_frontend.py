@@ -1,0 +1,184 @@
+"""Keyword-driven front end: the keyword set of SOS_ABS_MAIN and what frontend.py derives from it on the host
+(CPU tests), and the whole run from keywords to SOS_Up / SOS_Down on the device against the reference's flow stage by stage
+(GPU test: SOS_INIT_PARAMWMO -> SOS_MIE -> SOS_GRANU -> mixture -> SOS_DECOMPO_LEGENDRE -> aerosol result file -> SOS_GLITTER ->
+SOS_PROFILE -> SOS + SOS_OS -> SOS_AGGREGATE -> SOS_TRPHI_OPTION of oracle/_ref/libsosref.so)."""
+import ctypes as C
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import aerosol_cases as ac
+import refdirect
+
+DEMO = ("-SOS_Main.Wa 0.910 -SOS_Main.ResRoot {root} -SOS_Main.Log SOS_Main_Demo.Log -ANG.Rad.NbGauss {nrad} -ANG.Aer.NbGauss {naer} "
+        "-ANG.Thetas 35. -SOS.View 1 -SOS.View.Phi 0. -SOS.ResFileUp SOS_Up_Demo.txt -SOS.ResFileDown SOS_Down_Demo.txt -AP.Log Profile_Demo.Log "
+        "-AP.Psurf 1013 -AP.AerProfile.Type 1 -AP.HR 8.0 -AP.AerHS.HA 2.0 -AP.AbsProfile.Type {abs} -AP.SpectralResol 10. -SOS.AbsModeCKD 1 "
+        "-AER.DirMie {root}/MIE -AER.Model 1 -AER.WMO.Model 2 -AER.Waref 0.550 -AER.AOTref 0.3 -AER.ResFile Aerosols_Demo.txt "
+        "-AER.Log Aerosols_Demo.Log -SURF.Dir {root}/SURF -SURF.Type 1 -SURF.Alb 0.00 -SURF.Ind 1.34 -SURF.Glitter.Wind 2.0")
+
+
+def _mods():
+    m = lambda n: importlib.import_module("radiativetransfer-sos_b200." + n)
+    return m("keywords"), m("frontend"), m("aerosols")
+
+
+def test_keyword_set_is_the_references():
+    """Every keyword SOS_ABS_MAIN documents (SOS_ABS_MAIN.F:213-912) is known with the documented value type; the demo script's
+    command line parses; unknown keywords and missing required ones are refused."""
+    kw, fe, _ = _mods()
+    src = "/root/reference/src/SOS_ABS_MAIN.F"
+    if os.path.exists(src):
+        lines = open(src, encoding="latin-1").read().split("\n")[212:915]
+        cur, seen = None, {}
+        for ln in lines:
+            m = re.match(r"^C\s+Keyword\s*:\s*(-[\w.]+)", ln)
+            if m:
+                cur = m.group(1)
+            elif cur and "Value format" in ln and cur not in seen:
+                seen[cur] = "f" if "Float" in ln else "i" if "Integer" in ln else "s"
+        assert len(seen) >= 90
+        for k, t in seen.items():
+            assert k in kw.KEYWORDS, k
+            if k != "-AER.WMO.WS":                                  # documented as a string by a copy-paste slip, read as a float
+                assert kw.KEYWORDS[k] == t, (k, t)
+        demo = open("/root/reference/exe/runSOS-ABS_demo.ksh", encoding="latin-1").read()
+        for k in re.findall(r"(-[A-Z_a-z]+\.[\w.]+)\s", demo[demo.index("SOS_ABS_MAIN.exe"):]):
+            assert k in kw.KEYWORDS, k
+    d = kw.parse(DEMO.format(root="/tmp/x", nrad=40, naer=40, abs=1).split())
+    assert d["-SOS_Main.Wa"] == 0.910 and d["-ANG.Rad.NbGauss"] == 40 and d["-SURF.Type"] == 1 and d["-SOS.IGmax"] == 100
+    assert d["-SOS.ResBin"] == "SOS_Result.bin" and d["-SOS.Ipolar"] == 1 and d["-SOS.OutputAlt"] == -1.0
+    assert kw.parse(["-AP.MOT", "1.D-2"], require=False)["-AP.MOT"] == 0.01
+    with pytest.raises(ValueError):
+        kw.parse(["-SOS.Wavelength", "0.5"], require=False)
+    with pytest.raises(ValueError):
+        kw.parse(["-SOS_Main.Wa", "0.5"])
+    with pytest.raises(ValueError):
+        kw.parse(["-SOS.IGmax", "many"], require=False)
+
+
+def test_frontend_host_logic():
+    kw, fe, aer = _mods()
+    assert fe.expansion_orders(None, None) == (80, 48, 128)           # SOS_ANGLES.F:303-329
+    assert fe.expansion_orders(40, 40) == (80, 80, 160) and fe.expansion_orders(20, None) == (40, 48, 128)
+    n, xmu, xhr = fe.mie_angles(20)
+    assert n == 20 and xmu[20] == 0.0 and (np.diff(xmu) > 0).all() and abs(xhr[21:].sum() - 1.0) < 1e-13
+    syn = importlib.import_module("radiativetransfer-sos_b200.synth")
+    mu, w = syn.sos_gauss(21)                                       # equal to the reference's SOS_GAUSS (test_oracle_vs_reference.py)
+    assert np.array_equal(xmu[21:], [float("%.13E" % v) for v in np.sort(mu)])
+    tr = fe.rayleigh_thickness(1013.0, 0.910)
+    assert abs(tr - 1e-4 * (84.35 / 0.91 ** 4 - 1.225 / 0.91 ** 5 + 1.4 / 0.91 ** 6)) < 1e-9 and 0.012 < tr < 0.0125
+    d = kw.parse(DEMO.format(root="/tmp/x", nrad=12, naer=20, abs=7).split())
+    os.environ["SOS_ABS_ROOT"] = "/somewhere"
+    m = fe.aerosol_model(d)
+    assert isinstance(m, aer.Wmo) and m.imodele == 2 and m.datafile == "/somewhere/fic/Data_WMO_cor_2015_12_16"
+    d.update({"-AER.Model": 3, "-AER.BMD.VCdef": 2, "-AER.BMD.RAOT": 0.4, "-AER.BMD.CM.MRwa": 1.45, "-AER.BMD.CM.MIwa": -0.004,
+              "-AER.BMD.CM.MRwaref": 1.46, "-AER.BMD.CM.MIwaref": -0.005, "-AER.BMD.CM.SDradius": 0.4, "-AER.BMD.CM.SDvar": 0.6,
+              "-AER.BMD.FM.MRwa": 1.42, "-AER.BMD.FM.MIwa": -0.008, "-AER.BMD.FM.MRwaref": 1.43, "-AER.BMD.FM.MIwaref": -0.009,
+              "-AER.BMD.FM.SDradius": 0.08, "-AER.BMD.FM.SDvar": 0.45})
+    b = fe.aerosol_model(d)
+    assert b.rtauct == 0.4 and b.coarse_rn(0.55) == 1.46 and b.coarse_rn(0.91) == 1.45 and b.fine_in(0.55) == -0.009
+    d["-AER.Model"] = 2
+    with pytest.raises(NotImplementedError):
+        fe.aerosol_model(d)
+    with pytest.raises(NotImplementedError):                         # gas absorption without the caller's tables
+        fe.run_keywords(None, DEMO.format(root="/tmp/x", nrad=12, naer=20, abs=1).split())
+
+
+def _parse_updown(path):
+    rows = []
+    for ln in open(path):
+        p = ln.split()
+        try:
+            rows.append([float(x) for x in p])
+        except ValueError:
+            continue
+    n = max(len(r) for r in rows)
+    return np.array([r for r in rows if len(r) == n])
+
+
+@pytest.mark.gpu
+def test_gpu_run_from_keywords_demo(pkg, solver, tmp_path):
+    """The demo's command line (exe/runSOS-ABS_demo.ksh: WMO maritime aerosols scaled from 0.550 microns, rough-sea surface, solar
+    plane) with 12 / 20 Gauss angles and without gaseous absorption, from keywords to SOS_Up_Demo.txt / SOS_Down_Demo.txt on the
+    device -- against the reference's routines run one after the other on the host."""
+    kwm, fe, aer = _mods()
+    api = importlib.import_module("radiativetransfer-sos_b200.api")
+    import test_aerosol_chain as tac
+    ref = refdirect.lib()
+    assert ref is not None and hasattr(ref, "sos_mie_")
+    syn, fm = pkg.synth, pkg.formats
+    root = str(tmp_path / "res")
+    os.makedirs(os.path.join(str(tmp_path), "abs_root", "fic"))
+    os.environ["SOS_ABS_ROOT"] = os.path.join(str(tmp_path), "abs_root")
+    wmo = ac.write_wmo_file(os.path.join(os.environ["SOS_ABS_ROOT"], "fic", "Data_WMO_cor_2015_12_16"))
+    argv = DEMO.format(root=root, nrad=12, naer=20, abs=7).split()
+    res, aopt = fe.run_keywords(solver, argv)
+    d = res.dirs[0]
+    assert sorted(os.listdir(d)) == ["SOS_Down_Demo.txt", "SOS_Result.bin", "SOS_Up_Demo.txt"]
+    assert os.path.exists(os.path.join(root, "AER", "Aerosols_Demo.txt"))
+    # ---- the reference's flow ----
+    wa, waref, aot, os_nb, os_ns, os_nm = 0.910, 0.550, 0.3, 40, 24, 64
+    assert fe.expansion_orders(20, 12) == (os_nb, os_ns, os_nm)
+    nbm, xmu, xhr = fe.mie_angles(20)
+    k1 = {}
+    for w in (wa, waref):
+        e, v1, v2, mr, mi, vol = ac.ref_wmo_params(ref, wmo, w)
+        comps = [(mr[i], mi[i], 0.0001, (4000.0, 50.0, 800.0, 10.0)[i], 1, v1[i], v2[i], -999.0, w) for i in (1, 2)]
+        n = np.array([0.0 / vol[0], 0.05 / vol[1], 0.95 / vol[2], 0.0 / vol[3]])
+        ntot = 0.0
+        for x in n:
+            ntot = ntot + x
+        k1[w] = tac._reference_chain(ref, str(tmp_path), nbm, xmu, xhr, comps, [(2, [0, 1], [n[1] / ntot, n[2] / ntot], 1)], os_nb)[2][0]
+    dd = k1[wa]
+    ta = dd["kmat1"] / k1[waref]["kmat1"] * aot
+    piz = dd["kmat2"] / dd["kmat1"]
+    ct = dd["coef_tronca"]
+    fa = str(tmp_path / "Aer_ref.txt")
+    api.write_aerosols(fa, os_nb, dd["kmat1"], dd["kmat2"], ct / 2.0 + (1.0 - ct / 2.0) * dd["beta11"][1] / 3.0, ct,
+                       piz * (1.0 - ct / 2.0) / (1.0 - piz * ct / 2.0), dd["alp"], dd["beta11"], dd["gamma12"], dd["zeta"])
+    la, lb = open(os.path.join(root, "AER", "Aerosols_Demo.txt")).read().split("\n"), open(fa).read().split("\n")
+    same_aer = sum(x == y for x, y in zip(la, lb))
+    assert la[:8] == lb[:8] and same_aer >= len(lb) - 2
+    r8 = lambda v: np.array([float("%.7E" % x) for x in v])
+    rmu, ga, n0, _ = syn.sos_angles(12, 35.0)
+    N = (rmu.size - 1) // 2
+    surf_ref = refdirect.glitter(ref, fm, str(tmp_path), N, rmu, ga, 2.0, 1.34, os_nb, os_ns, os_nm)
+    o = syn.Optics(nbmu=N, rmu=rmu.copy(), ga=ga, n0=n0, tetas=35.0, os_nb=os_nb, alpha=r8(dd["alp"]), beta=r8(dd["beta11"]),
+                   gamma=r8(dd["gamma12"]), zeta=r8(dd["zeta"]), a_trunc=float("%.5f" % ct),
+                   piztr=float("%.5f" % (piz * (1.0 - ct / 2.0) / (1.0 - piz * ct / 2.0))), rho=0.0, imat_surf=1, igli=1, surf=surf_ref,
+                   ind_surf=1.34, wind=2.0, igmax=100, ipolar=1, zout=-1.0)
+    tr = fe.rayleigh_thickness(1013.0, wa)
+    term = dict(lamb1=1, ik=(1,) * 8, absprofil=7, iprofil=1, tr=tr, hr=8.0, ta=ta, ha=2.0, zmin=0.0, zmax=0.0)
+    ier_r, nt_r, _, z_r, h_r, pa_r, pm_r = refdirect.profile(ref, str(tmp_path), np.linspace(120.0, 0.0, 50), np.zeros(50), term)
+    assert ier_r == 0 and nt_r == int(res.nt[0])
+    wl_ref = syn.Workload("ref")
+    wl_ref.optics.append(o)
+    wl_ref.terms.append(syn.Term(0, 1.0, z_r, h_r, pa_r, pm_r))
+    rr = refdirect.runner()
+    r, _, _ = rr.solve_terms(wl_ref, [0], 1)
+    agg_rec, agg_sc = rr.aggregate_point(ref, fm, str(tmp_path), N, [(1.0, r[0])])
+    nr = int(res.groups.n_rec[0])
+    assert not agg_rec[nr:].any(), "number of Fourier orders differs"
+    got = fm.read_result_bin(os.path.join(d, "SOS_Result.bin"), N)
+    scale = np.abs(agg_rec[:nr]).max()
+    err = np.abs(got - agg_rec[:nr]).max() / scale
+    assert err < 5e-6, err                                        # aerosol optical thickness through REAL*4 Mie records (2e-7 on TA)
+    nphi, pf, th, up0, dn0 = refdirect.trphi_option(ref, fm, str(tmp_path), agg_rec[:nr], N, o.rmu, o.ga, agg_sc["ttot_tronc"],
+                                                    agg_sc["tauout"], 1, o.n0, 2.0, 1.34, 0, 1, 0.0, 30)
+    fu, fd = str(tmp_path / "REF_Up.txt"), str(tmp_path / "REF_Down.txt")
+    api.write_updown(fu, fd, N, 1, 0.0, 30, -1.0, pf, th, up0, dn0)
+    nlines = nsame = 0
+    for mine, theirs in ((os.path.join(d, "SOS_Up_Demo.txt"), fu), (os.path.join(d, "SOS_Down_Demo.txt"), fd)):
+        a, b = open(mine).read().split("\n"), open(theirs).read().split("\n")
+        assert len(a) == len(b)
+        nlines += len(a)
+        nsame += sum(x == y for x, y in zip(a, b))
+        pa_, pb_ = _parse_updown(mine), _parse_updown(theirs)
+        assert pa_.shape == pb_.shape
+        np.testing.assert_allclose(pa_[:, 3:6], pb_[:, 3:6], rtol=2e-5, atol=1e-9)
+    print("\n[keywords -> files] demo command line (12 / 20 Gauss angles, no gas): NT %d = reference's, Fourier orders %d = reference's, "
+          "SOS_Result.bin within %.1e of scale, aerosol file lines identical %d / %d, SOS_Up/Down lines identical %d / %d; TA = %.6f"
+          % (nt_r, nr, err, same_aer, len(lb), nsame, nlines, ta))
