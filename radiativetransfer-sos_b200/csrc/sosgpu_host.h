@@ -37,6 +37,9 @@ struct sosgpu_ctx {
   cudaMemPool_t pool = nullptr;      // stream-ordered pool (release threshold = never) behind sos_dmalloc / sos_dfree
 };
 
+// the process-wide context of the gfortran-ABI symbols, created on first use (sosgpu_shims.cu); nullptr without a usable device
+sosgpu_ctx *sos_shim_ctx();
+
 // frees a list of pool allocations when a routine leaves early (CK returns) or normally
 struct SosFreeGuard {
   sosgpu_ctx *ctx; void *p[8]; int n = 0;

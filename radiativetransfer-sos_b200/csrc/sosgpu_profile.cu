@@ -278,17 +278,7 @@ std::string fstr_(const char *s, size_t len)
   return std::string(s, len);
 }
 
-sosgpu_ctx *profile_shim_ctx()
-{
-  static sosgpu_ctx *ctx = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    const char *e = getenv("SOSGPU_DEVICE");
-    if (sosgpu_create(&ctx, e ? atoi(e) : 0) != SOSGPU_OK) ctx = nullptr;
-  }
-  return ctx;
-}
+sosgpu_ctx *profile_shim_ctx() { return sos_shim_ctx(); }
 
 }  // namespace
 

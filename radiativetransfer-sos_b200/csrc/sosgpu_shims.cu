@@ -250,17 +250,20 @@ extern "C" int sosgpu_bpdf_ajout_brdf(sosgpu_ctx *ctx, const float *surf1, const
 
 // ---------------------------------------------------------------------------------------------
 // gfortran-ABI drop-ins.  One process-wide context, created on first use.
+// (device: SOSGPU_DEVICE, default 0); shared by the shims of sosgpu_profile.cu and sosgpu_aerosols.cu.
 static sosgpu_ctx *g_ctx = nullptr;
-static sosgpu_ctx *shim_ctx()
+sosgpu_ctx *sos_shim_ctx()
 {
   if (!g_ctx) {
-    if (sosgpu_create(&g_ctx, 0) != SOSGPU_OK) {
+    const char *e = getenv("SOSGPU_DEVICE");
+    if (sosgpu_create(&g_ctx, e ? atoi(e) : 0) != SOSGPU_OK) {
       fprintf(stderr, "  libsosgpu: no usable CUDA device -- the SOS hot path has no CPU fallback\n");
       g_ctx = nullptr;
     }
   }
   return g_ctx;
 }
+static sosgpu_ctx *shim_ctx() { return sos_shim_ctx(); }
 
 static std::string fstr(const char *s, size_t n)
 {

@@ -140,6 +140,23 @@ def _lane_layout_case(host, ref, tmp_path, nbmu, xmu, xhr, nang, TABLES):
             o += m
 
 
+def test_host_mie_largest_table_bit_identical(host, ref, tmp_path):
+    """The largest table inc/SOS.h allows (2 alphaf + 20 <= CTE_MIE_DIM = 10000): 8 790 size parameters up to 4990, series of up to
+    9 985 orders, through the lane layout of the kernels -- 0 differing values against SOS_MIE."""
+    nbmu, xmu, xhr = ac.mie_angles(2)
+    nang = 2 * nbmu + 1
+    case = (1.53, -0.008, 0.0001, 4990.0)
+    r = ac.ref_mie(ref, str(tmp_path), nbmu, xmu, xhr, *case)[1]
+    n = r["g"].size
+    assert n == 8790
+    rec, g = np.zeros((n, 3), np.float32), np.zeros(n)
+    im, qm, um = (np.zeros((n, nang), np.float32) for _ in range(3))
+    tab = np.array(case)
+    assert host.ach_mie_lanes(nbmu, _P(xmu), 1, _P(tab), C.c_longlong(1 << 40), n, _F(rec), _P(g), _F(im), _F(qm), _F(um)) == n
+    for a, b in ((rec, "rec"), (g, "g"), (im, "imie"), (qm, "qmie"), (um, "umie")):
+        assert np.array_equal(a, r[b]), b
+
+
 def test_host_mie_count_is_grid(host):
     assert host.ach_mie_count(0.0001, 200.0) == 4000
     assert host.ach_mie_count(0.0001, 4990.0) == 3900 + 4890
