@@ -123,7 +123,11 @@ def run_keywords(solver, argv, wavelengths=None, gas=None):
     -AP.AbsProfile.Type 7, else dict(tables=, kdis_ai=, userprofil=, altabs=, ro=, lamb1=[per wavelength]) as band.run_band
     takes them.  Results go to <-SOS_Main.ResRoot>/SOS/<wavelength>/ under the names of -SOS.ResFileUp / -SOS.ResFileDown /
     -SOS.ResBin (+ -SOS.Trans / -SOS.Flux), the aerosol result files to <ResRoot>/AER.  Returns (band.BandResult, [AerosolOptics])."""
-    kw = keywords.parse(argv)
+    return run(solver, keywords.parse(argv), wavelengths, gas)
+
+
+def run(solver, kw, wavelengths=None, gas=None):
+    """run_keywords on an already parsed keyword dict (keywords.parse, or sos.sos_proc's arguments)."""
     for k in ("-ANG.Rad.UserAngFile", "-ANG.Aer.UserAngFile", "-AER.UserFile", "-SURF.File", "-SOS.ResFileUp.UserAng", "-SOS.ResFileDown.UserAng"):
         if k in kw:
             raise NotImplementedError("%s: user angle / user data files are not read by this front end" % k)

@@ -1,4 +1,5 @@
-"""The command-line keywords of SOS_ABS_MAIN (SOS_ABS_MAIN.F:213-912): names, value types, the defaults of inc/SOS.h, and a parser
+"""The command-line keywords of SOS_ABS_MAIN -- the 98 names its argument loop compares with (SOS_ABS_MAIN.F:1499-2200; documented at
+:213-912, where -AER.SF.RH appears as "-AER.SF.HR") -- with their value types, the defaults of inc/SOS.h, and a parser
 that accepts exactly the reference's `-KEYWORD value` pairs.  The keyword set is the drop-in surface; which combinations the
 device front end can run is decided in frontend.py, not here."""
 
@@ -15,7 +16,7 @@ KEYWORDS = {
     "-AER.MMD.MRwa": F, "-AER.MMD.MIwa": F, "-AER.MMD.MRwaref": F, "-AER.MMD.MIwaref": F, "-AER.MMD.SDtype": I,
     "-AER.MMD.LNDradius": F, "-AER.MMD.LNDvar": F, "-AER.MMD.JD.slope": F, "-AER.MMD.JD.rmin": F, "-AER.MMD.JD.rmax": F,
     "-AER.WMO.Model": I, "-AER.WMO.DL": F, "-AER.WMO.WS": F, "-AER.WMO.OC": F, "-AER.WMO.SO": F,
-    "-AER.SF.Model": I, "-AER.SF.HR": F,
+    "-AER.SF.Model": I, "-AER.SF.RH": F,
     "-AER.BMD.VCdef": I, "-AER.BMD.CoarseVC": F, "-AER.BMD.FineVC": F, "-AER.BMD.RAOT": F,
     "-AER.BMD.CM.MRwa": F, "-AER.BMD.CM.MIwa": F, "-AER.BMD.CM.MRwaref": F, "-AER.BMD.CM.MIwaref": F, "-AER.BMD.CM.SDradius": F,
     "-AER.BMD.CM.SDvar": F, "-AER.BMD.FM.MRwa": F, "-AER.BMD.FM.MIwa": F, "-AER.BMD.FM.MRwaref": F, "-AER.BMD.FM.MIwaref": F,

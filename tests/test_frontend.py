@@ -40,10 +40,13 @@ def test_keyword_set_is_the_references():
             elif cur and "Value format" in ln and cur not in seen:
                 seen[cur] = "f" if "Float" in ln else "i" if "Integer" in ln else "s"
         assert len(seen) >= 90
+        seen["-AER.SF.RH"] = seen.pop("-AER.SF.HR")                 # the documentation block misspells the keyword the code parses
         for k, t in seen.items():
             assert k in kw.KEYWORDS, k
             if k != "-AER.WMO.WS":                                  # documented as a string by a copy-paste slip, read as a float
                 assert kw.KEYWORDS[k] == t, (k, t)
+        parsed = set(re.findall(r'KEYWORD\.EQ\."(-[\w.]+)"', open(src, encoding="latin-1").read()))
+        assert parsed == set(kw.KEYWORDS), (parsed ^ set(kw.KEYWORDS))   # exactly the names the argument loop compares with
         demo = open("/root/reference/exe/runSOS-ABS_demo.ksh", encoding="latin-1").read()
         for k in re.findall(r"(-[A-Z_a-z]+\.[\w.]+)\s", demo[demo.index("SOS_ABS_MAIN.exe"):]):
             assert k in kw.KEYWORDS, k
@@ -182,3 +185,53 @@ def test_gpu_run_from_keywords_demo(pkg, solver, tmp_path):
     print("\n[keywords -> files] demo command line (12 / 20 Gauss angles, no gas): NT %d = reference's, Fourier orders %d = reference's, "
           "SOS_Result.bin within %.1e of scale, aerosol file lines identical %d / %d, SOS_Up/Down lines identical %d / %d; TA = %.6f"
           % (nt_r, nr, err, same_aer, len(lb), nsame, nlines, ta))
+
+
+def test_sos_proc_arguments():
+    """sos.sos_proc takes the arguments of the f2py wrapper binding/run_sos.py calls (names, order, "not defined" values)."""
+    sos = importlib.import_module("radiativetransfer-sos_b200.sos")
+    names = [a for a, _ in sos.ARGS]
+    src = "/root/reference/src/SOS_PROC.F"
+    if os.path.exists(src):
+        txt = open(src, encoding="latin-1").read()
+        ins = re.findall(r"^Cf2py intent\(in\)\s+(.*)$", txt, re.M)
+        want = [w.strip().lower() for ln in ins for w in ln.split(",") if w.strip()]
+        want = [sos._ALIASES.get(w, w) for w in want]
+        assert want == names, [(a, b) for a, b in zip(want, names) if a != b]
+        call = open("/root/reference/binding/run_sos.py", encoding="latin-1").read()
+        used = re.findall(r"\b(\w+)=[A-Za-z_]+[,)]", call[call.index("sos.sos_proc("):call.index("print(i_up.shape)")])
+        for u in used:
+            assert sos._ALIASES.get(u, u) in names, u
+    kw = sos.to_keywords(resroot="/tmp/r", wa_simu=0.44, tetas=40.0, nbmu_gauss_lum=24, nbmu_gauss_mie=-999, ficangles_user_lum="NO_USER_ANGLES",
+                         ficanglog="Angles.Log", waref_aot=0.55, aot_ref=0.3, itronc_aer=1, imod_aer=1, imodele_wmo=1, c_wmo_dl=-999.0,
+                         tr=0.23, hr=8, ha=2, iprofil=1, absprofil=7, isurf=1, surf_ind=1.33, wind=2.0, rho=0.0, igmax=30, itrphi=1, phios=35,
+                         pas_phi=-999, zout=-999.0, ier=0, trace=True)
+    assert kw["-SOS_Main.Wa"] == 0.44 and kw["-ANG.Rad.NbGauss"] == 24 and "-ANG.Aer.NbGauss" not in kw and "-ANG.Rad.UserAngFile" not in kw
+    assert "-ANG.Log" not in kw and "-AER.WMO.DL" not in kw and kw["-SOS.IGmax"] == 30 and kw["-SOS.OutputAlt"] == -1.0 and kw["-AP.HR"] == 8.0
+    with pytest.raises(TypeError):
+        sos.to_keywords(wavelength=0.5)
+    with pytest.raises(ValueError):
+        sos.to_keywords(resroot="/tmp/r", wa_simu=0.44)             # required arguments not defined
+
+
+@pytest.mark.gpu
+def test_gpu_sos_proc_entry(solver, tmp_path):
+    """The f2py-shaped entry end to end: same numbers as frontend.run_keywords for the same description, in the wrapper's shapes."""
+    sos = importlib.import_module("radiativetransfer-sos_b200.sos")
+    _, fe, _ = _mods()
+    os.makedirs(os.path.join(str(tmp_path), "abs_root", "fic"))
+    os.environ["SOS_ABS_ROOT"] = os.path.join(str(tmp_path), "abs_root")
+    ac.write_wmo_file(os.path.join(os.environ["SOS_ABS_ROOT"], "fic", "Data_WMO_cor_2015_12_16"))
+    out = sos.sos_proc(solver=solver, resroot=str(tmp_path / "a"), wa_simu=0.910, tetas=35.0, nbmu_gauss_lum=12, nbmu_gauss_mie=20, waref_aot=0.55,
+                       aot_ref=0.3, itronc_aer=1, imod_aer=1, imodele_wmo=2, hr=8.0, ha=2.0, iprofil=1, psurf=1013.0, absprofil=7, isurf=1,
+                       surf_ind=1.34, wind=2.0, rho=0.0, itrphi=2, pas_phi=60, igmax=-999, zout=-999.0, ier=0, trace=False)
+    assert len(out) == 23
+    n, ind, phi, vza, tabs, (tdir, fdd, fd, eplus, ct) = out[0], out[1], out[2], out[3], out[4:18], out[18:]
+    res, aer = fe.run_keywords(solver, DEMO.format(root=str(tmp_path / "b"), nrad=12, naer=20, abs=7).replace("-SOS.View 1 -SOS.View.Phi 0.",
+                                                                                                                "-SOS.View 2 -SOS.View.Dphi 60").split())
+    assert n == res.up.shape[3] == 13 and ind.shape == (161,) and phi.shape == (361,) and vza.shape == (81,) and tabs[0].shape == (361, 81)
+    assert list(phi[:7]) == [0.0, 60.0, 120.0, 180.0, 240.0, 300.0, 360.0] and res.nphi == 7
+    for t in range(7):
+        assert np.array_equal(tabs[t][:7, :n], res.up[0, t, :7, :n]) and np.array_equal(tabs[7 + t][:7, :n], res.down[0, t, :7, :n])
+        assert not tabs[t][7:].any() and not tabs[t][:, n:].any()
+    assert ct == aer[0].coef_tronca and eplus == float(res.groups.eplus[0]) and 0.0 < tdir < 1.0 and abs(fd - (fdd + tdir)) < 1e-12
