@@ -394,10 +394,8 @@ extern "C" int sosgpu_decompo_legendre(sosgpu_ctx *ctx, int *itronc, int nbmu, c
                                        double *alp, double *beta11, double *beta22, double *gamma12, double *delta33, double *zeta, int *ier)
 {
   if (!ctx) return SOSGPU_ERR_NO_DEVICE;
-  if (!angles_ok(ctx, nbmu, xmu, "sosgpu_decompo_legendre") || !xhr || !itronc || !p11 || !p12 || !p22 || !p33 || !ier) {
-    if (ctx->err.empty()) ctx->err = "sosgpu_decompo_legendre: null argument";
-    return SOSGPU_ERR_ARG;
-  }
+  if (!angles_ok(ctx, nbmu, xmu, "sosgpu_decompo_legendre")) return SOSGPU_ERR_ARG;
+  if (!xhr || !itronc || !p11 || !p12 || !p22 || !p33 || !ier) { ctx->err = "sosgpu_decompo_legendre: null argument"; return SOSGPU_ERR_ARG; }
   sosgpu_aer_model mod{};
   mod.ncomp = 0; mod.comp[0] = 0; mod.weight[0] = 1.0; mod.itronc = *itronc;
   std::vector<AcModel> models;
@@ -433,10 +431,8 @@ extern "C" int sosgpu_aerosols(sosgpu_ctx *ctx, int nbmu, const double *xmu, con
                                double *scal, double *coef, double *phase, int *model_ier)
 {
   if (!ctx) return SOSGPU_ERR_NO_DEVICE;
-  if (!angles_ok(ctx, nbmu, xmu, "sosgpu_aerosols") || !xhr || ncomp < 1 || !comp) {
-    if (ctx->err.empty()) ctx->err = "sosgpu_aerosols: bad arguments";
-    return SOSGPU_ERR_ARG;
-  }
+  if (!angles_ok(ctx, nbmu, xmu, "sosgpu_aerosols")) return SOSGPU_ERR_ARG;
+  if (!xhr || ncomp < 1 || !comp) { ctx->err = "sosgpu_aerosols: null weights or no component"; return SOSGPU_ERR_ARG; }
   std::vector<AcModel> mods;
   if (!models_ok(ctx, models, nmodel, ncomp, os_nb, &mods)) return SOSGPU_ERR_ARG;
   std::vector<HostTable> tabs;
