@@ -584,8 +584,19 @@ def translate_unit(name, args, stmts, defines, known_subs):
             kv = dict((c.split("=", 1)[0].strip().upper(), c.split("=", 1)[1].strip()) for c in ctl if "=" in c)
             formatted = len(pos) > 1 or "FMT" in kv
             unit_txt = kv.get("UNIT", pos[0] if pos else "0").strip()
+            # internal file: WRITE(CHARVAR,'(Iw)') integer-expression  (SOS_NOM_FICMIE builds the MIE file name this way)
+            mi = re.match(r"^'\(\s*I(\d+)\s*\)'$", (pos[1] if len(pos) > 1 else "").strip(), re.I)
+            if kind == "WRITE" and mi and unit_txt.upper() in u.vars and u.vars[unit_txt.upper()]["type"] == "c":
+                dst = u.cexpr(unit_txt)
+                val = u.cexpr(rest[j + 1:].strip())
+                if val[1] != "i":
+                    raise Unsupported("internal WRITE of a non-integer")
+                return "{ char b_[64]; snprintf(b_, sizeof b_, \"%%*d\", %d, (int)(%s)); f77_assign(%s, b_, strlen(b_)); }" % (int(mi.group(1)), val[0], dst[0])
             fmt_lab = kv.get("FMT", pos[1] if len(pos) > 1 else None)
             text_file = formatted and unit_txt in u.text_units and fmt_lab is not None and fmt_lab.strip() in u.formats
+            if formatted and not text_file and not re.match(r"^\d+$", unit_txt) and not re.match(r"^\w+$", unit_txt) and u.text_units \
+                    and fmt_lab is not None and fmt_lab.strip() in u.formats:
+                text_file = True                                   # computed unit, e.g. READ((I+10),555): one of the units opened here
             if formatted and not text_file:
                 if kind == "READ":
                     raise Unsupported("formatted READ on a unit that is not opened here")
@@ -844,7 +855,7 @@ def translate_unit(name, args, stmts, defines, known_subs):
                 continue
             if lab:
                 emit("L%s: ;" % lab)
-            if up.startswith("IF"):
+            if re.match(r"^IF\s*\(", up):                           # not IFIN = ... (a variable whose name starts with IF)
                 # logical IF: find the matching parenthesis
                 i = txt.index("(")
                 depth, j = 0, i

@@ -5,11 +5,13 @@ for a LIST of wavelengths, with the work itself done on the device by Solver.aer
 
     mono-modal (IMOD = 0)        SOS_AEROSOLS.F:1158-1304   log-normal or Junge size distribution
     WMO models (IMOD = 1)        SOS_AEROSOLS.F:1309-1510   dust-like / water-soluble / oceanic / soot, SOS_INIT_PARAMWMO :3334-3556
+    Shettle & Fenn (IMOD = 2)    SOS_AEROSOLS.F:1514-1702   rural / urban / oceanic components at a relative humidity, SOS_INIT_PARAMSF
+                                                            :3557-3843
     bimodal log-normal (IMOD=3)  SOS_AEROSOLS.F:1706-2123   volume concentrations given, or the coarse share of the optical
                                                             thickness at the reference wavelength (MODE_PARAM_BILND = 1 / 2)
     optical thickness at WA      SOS_PROC.F:2941-3063       TA = KMAT1(WA) / KMAT1(WAREF) * AOT_REF
 
-Shettle & Fenn (IMOD = 2), external phase functions (4) and user mixtures (5) are not built.  Keyword parsing stays with the
+External phase functions (4) and user mixtures (5) are not built.  Keyword parsing stays with the
 caller.  No CPU fallback: the numbers come from Solver.aerosols, which needs the GPU."""
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
@@ -21,7 +23,15 @@ COEF_NRMAX = float(np.float32(0.0001))             # CTE_COEF_NRMAX (SOS.h:134),
 WAMIN = float(np.float32(0.364))                   # CTE_WAMIN (SOS.h:70)
 NOT_DEFINED = -999.0                               # CTE_NOT_DEFINED_VALUE_DBLE (SOS.h:78)
 ALPHAMAX_WMO = (4000.0, 50.0, 800.0, 10.0)         # CTE_ALPHAMAX_WMO_DL / WS / OC / SO (SOS.h:122-125)
-WMO_VOLUMES = {1: (0.70, 0.29, 0.0, 0.01), 2: (0.0, 0.05, 0.95, 0.0), 3: (0.17, 0.61, 0.0, 0.22)}   # SOS_AEROSOLS.F:1340-1353
+ALPHAMAX_SF = {0: 70.0, 2: 90.0}                   # CTE_ALPHAMAX_SF_SR / SU (SOS.h:126-127): small rural, small urban
+_f32 = lambda *v: tuple(float(np.float32(x)) for x in v)
+# volume proportions of DL, WS, OC, SO (SOS_AEROSOLS.F:1340-1353) and number densities of the five Shettle & Fenn components
+# (:1536-1551): REAL*4 literals assigned to DOUBLE PRECISION variables -- 0.70 is (double)0.70f there
+WMO_VOLUMES = {1: _f32(0.70, 0.29, 0.0, 0.01), 2: _f32(0.0, 0.05, 0.95, 0.0), 3: _f32(0.17, 0.61, 0.0, 0.22)}
+SF_DENSITIES = {1: _f32(1.0, 0.0, 0.0, 0.0, 0.0), 2: _f32(0.0, 0.0, 0.999875, 0.000125, 0.0), 3: _f32(0.99, 0.0, 0.0, 0.0, 0.01),
+                4: _f32(0.995, 0.0, 0.0, 0.0, 0.005)}
+SF_FILES = ("Data_SF_cor_2015_12_16", "IRefrac_SR_cor_2015_12_16", "IRefrac_LR", "IRefrac_SU_cor_2015_12_16", "IRefrac_LU_cor_2015_12_16",
+            "IRefrac_OM_cor_2015_12_16")          # CTE_AER_DATASF, CTE_AER_SR_SF .. CTE_AER_OM_SF (SOS.h:149-160)
 _PI = float(np.arccos(-1.0))
 
 
@@ -55,13 +65,7 @@ def wmo_params(path, wa):
     log-normal sigmas (the file's log10 values times ln 10), volumes of one particle, and the refractive indices interpolated to
     `wa` and rounded to the MIE file-name precision; four components DL, WS, OC, SO.  Indices stay 0 when `wa` is outside the
     table, as in the reference."""
-    def cols(line, widths):
-        out, pos = [], 0
-        for skip, w in widths:
-            pos += skip
-            out.append(float(line[pos:pos + w].strip() or 0.0))
-            pos += w
-        return out
+    cols = _cols
     with open(path) as f:
         lines = f.read().split("\n")
     f9 = [(1, 9)] * 4
@@ -78,6 +82,68 @@ def wmo_params(path, wa):
                 mr[i], mi[i] = round_index(r, im)
             break
     return v1, v2, mr, mi, vol
+
+
+def _cols(line, widths):
+    out, pos = [], 0
+    for skip, w in widths:
+        pos += skip
+        out.append(float(line[pos:pos + w].strip() or 0.0))
+        pos += w
+    return out
+
+
+def sf_params(dirfic, wa, rh):
+    """SOS_INIT_PARAMSF (SOS_AEROSOLS.F:3557-3843): the Shettle & Fenn data files (formats 222 / 333 / 555) -> modal radii at the
+    relative humidity `rh` (percent), log-normal sigmas, refractive indices interpolated in wavelength and humidity and rounded to
+    the MIE file-name precision; five components small rural, large rural, small urban, large urban, oceanic."""
+    import os
+    with open(os.path.join(dirfic, SF_FILES[0])) as f:
+        lines = [ln for ln in f.read().split("\n") if ln.strip()]
+    v2 = [x * np.log(10.0) for x in _cols(lines[0], [(1, 9)] * 5)]
+    rows = [_cols(ln, [(1, 5)] + [(1, 9)] * 5) for ln in lines[1:]]
+    rh1, rm1, cpt = rows[0][0], rows[0][1:], 1
+    v1, rh2 = None, None
+    if rh1 == rh:
+        v1 = list(rm1)
+    else:
+        for row in rows[1:]:
+            rh2, rm2 = row[0], row[1:]
+            cpt += 1
+            if rh1 < rh <= rh2:
+                v1 = [interpol(a, b, rh1, rh2, rh) for a, b in zip(rm1, rm2)]
+                break
+            rh1, rm1 = rh2, rm2
+    if v1 is None:
+        raise ValueError("relative humidity %g outside the Shettle & Fenn table" % rh)
+    mr, mi = [0.0] * 5, [0.0] * 5
+    for i in range(5):
+        with open(os.path.join(dirfic, SF_FILES[1 + i])) as f:
+            tab = [_cols(ln, [(1, 9)] * 17) for ln in f.read().split("\n") if ln.strip()]
+        for a, b in zip(tab[:-1], tab[1:]):
+            if a[0] <= wa <= b[0]:
+                col = lambda row, h, im: row[1 + 2 * (h - 1) + im]          # MR(h) / MI(h), h = 1..8 humidities
+                if cpt == 1:
+                    r = interpol(col(a, 1, 0), col(b, 1, 0), a[0], b[0], wa)
+                    m = interpol(col(a, 1, 1), col(b, 1, 1), a[0], b[0], wa)
+                else:
+                    r = interpol(interpol(col(a, cpt - 1, 0), col(b, cpt - 1, 0), a[0], b[0], wa),
+                                 interpol(col(a, cpt, 0), col(b, cpt, 0), a[0], b[0], wa), rh1, rh2, rh)
+                    m = interpol(interpol(col(a, cpt - 1, 1), col(b, cpt - 1, 1), a[0], b[0], wa),
+                                 interpol(col(a, cpt, 1), col(b, cpt, 1), a[0], b[0], wa), rh1, rh2, rh)
+                mr[i], mi[i] = r, m
+                break
+        mr[i], mi[i] = round_index(mr[i], mi[i])
+    return v1, v2, mr, mi
+
+
+@dataclass
+class ShettleFenn:
+    """-AER.Model 2: imodele 1 tropospheric, 2 urban, 3 maritime, 4 coastal; rh = relative humidity in percent; dirfic = the
+    directory of the Shettle & Fenn data files ($SOS_ABS_ROOT/fic)."""
+    dirfic: str
+    imodele: int
+    rh: float
 
 
 @dataclass
@@ -187,6 +253,20 @@ def plan(model, wavelengths, itronc=1, bilnd_weights=None):
                 wts.append(n[i] / ntot)
                 p.components.append((mr[i], mi[i], ALPHA0, ALPHAMAX_WMO[i], 1, v1[i], v2[i], NOT_DEFINED, wa))
             p.models.append((len(idx), idx, wts, itronc))
+        elif isinstance(model, ShettleFenn):
+            v1, v2, mr, mi = sf_params(model.dirfic, wa, model.rh)
+            ni = SF_DENSITIES[model.imodele]
+            idx, wts = [], []
+            for i in range(5):
+                if ni[i] == 0.0:
+                    continue
+                af = ALPHAMAX_SF[i] if i in ALPHAMAX_SF else alphaf_of(lnd_rmax(v1[i], v2[i]), wa)       # :1582-1591
+                if ALPHA0 > af or af >= 1e5:
+                    raise ValueError("size-parameter range of the Mie table out of bounds (SOS_AEROSOLS error 1009)")
+                idx.append(len(p.components))
+                wts.append(ni[i])                                      # number densities as they are (:1657-1664): they sum to 1
+                p.components.append((mr[i], mi[i], ALPHA0, af, 1, v1[i], v2[i], NOT_DEFINED, wa))
+            p.models.append((len(idx), idx, wts, itronc))
         elif isinstance(model, BimodalLnd):
             if in_pos(model, wa):
                 raise ValueError("imaginary parts of refractive indexes have to be negative")
@@ -255,3 +335,59 @@ def through_result_file(a: AerosolOptics):
     r8 = lambda v: np.array([float("%.7E" % x) for x in v])
     return dict(alpha=r8(a.alpha), beta=r8(a.beta), gamma=r8(a.gamma), zeta=r8(a.zeta), a_trunc=float("%.5f" % a.coef_tronca),
                 piztr=float("%.5f" % a.piztr))
+
+
+# ---- the MIE file cache of -AER.DirMie: names and format are the reference's, so either side can reuse the other's files ----
+def mie_file_name(nbmu_gauss, rn, in_, alpha0, alphaf):
+    """SOS_NOM_FICMIE (SOS_AEROSOLS.F:3128-3254) without a user angle file: MIEr.rrr-i.iiiii-a.aaaa-AAAAA.AA-MUnn, the digits
+    being INT(RN*1000), INT(-IN*100000), INT(ALPHAO*10000), INT(ALPHAF*100) zero-padded (truncation, as the reference)."""
+    crn, cin = "%04d" % int(rn * 1000), "%06d" % int(-in_ * 100000)
+    ca0, caf = "%05d" % int(alpha0 * 10000), "%07d" % int(alphaf * 100)
+    return "MIE%s.%s-%s.%s-%s.%s-%s.%s-MU%d" % (crn[0], crn[1:], cin[0], cin[1:], ca0[0], ca0[1:], caf[:5], caf[5:], nbmu_gauss)
+
+
+def write_mie_file(path, table, rn, in_, nbmu):
+    """A Mie table (dict of Solver.mie) as the unformatted sequential file SOS_MIE writes (SOS_MIE.F:395, 919-922): header record RN,
+    IN, ALPHAF (REAL*8), MIE_NBMU (INTEGER*4); per size parameter ALPHA, QEXT, QSCA (REAL*4), G (REAL*8), IMIE, QMIE, UMIE
+    (-nbmu:nbmu) (REAL*4); 4-byte record markers of gfortran."""
+    import struct
+    nang = 2 * nbmu + 1
+    n = table["g"].size
+    rec = np.dtype([("l0", "<i4"), ("rec", "<f4", 3), ("g", "<f8"), ("i", "<f4", nang), ("q", "<f4", nang), ("u", "<f4", nang), ("l1", "<i4")])
+    a = np.zeros(n, dtype=rec)
+    a["l0"] = a["l1"] = 12 + 8 + 12 * nang
+    a["rec"], a["g"], a["i"], a["q"], a["u"] = table["rec"], table["g"], table["imie"], table["qmie"], table["umie"]
+    with open(path, "wb") as f:
+        f.write(struct.pack("<i", 28) + struct.pack("<dddi", rn, in_, table["alphaf"], nbmu) + struct.pack("<i", 28))
+        f.write(a.tobytes())
+
+
+def read_mie_file(path, nbmu):
+    """The inverse of write_mie_file (what SOS_GRANU reads, SOS_AEROSOLS.F:4505-4532): dict for Solver.granu."""
+    import struct
+    raw = open(path, "rb").read()
+    nang = 2 * nbmu + 1
+    l0, = struct.unpack_from("<i", raw, 0)
+    rn, in_, alphaf, nb = struct.unpack_from("<dddi", raw, 4)
+    if l0 != 28 or nb != nbmu:
+        raise ValueError("MIE file %s: header does not match %d angles" % (path, nbmu))
+    rec = np.dtype([("l0", "<i4"), ("rec", "<f4", 3), ("g", "<f8"), ("i", "<f4", nang), ("q", "<f4", nang), ("u", "<f4", nang), ("l1", "<i4")])
+    a = np.frombuffer(raw, dtype=rec, offset=36)
+    return dict(rn=rn, in_=in_, alphaf=alphaf, rec=np.ascontiguousarray(a["rec"]), g=np.ascontiguousarray(a["g"]),
+                imie=np.ascontiguousarray(a["i"]), qmie=np.ascontiguousarray(a["q"]), umie=np.ascontiguousarray(a["u"]))
+
+
+def export_mie_cache(solver, dir_mie, nbmu_gauss, nbmu, xmu, components):
+    """Computes the Mie table of every distinct (rn, in, alpha0, alphaf) of `components` on the device and stores it in dir_mie under
+    the reference's file name, unless the file exists (SOS_AEROSOLS.F:1208-1237): the reference then finds its MIE files already
+    calculated.  Returns the file names."""
+    import os
+    os.makedirs(dir_mie, exist_ok=True)
+    names = []
+    for key in dict.fromkeys((c[0], c[1], c[2], c[3]) for c in components):
+        name = mie_file_name(nbmu_gauss, *key)
+        names.append(name)
+        path = os.path.join(dir_mie, name)
+        if not os.path.exists(path):
+            write_mie_file(path, solver.mie(nbmu, xmu, *key), key[0], key[1], nbmu)
+    return names

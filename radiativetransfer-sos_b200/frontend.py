@@ -8,7 +8,7 @@
     solves        SOS, SOS_OS, SOS_AGGREGATE, SOS_TRPHI_OPTION   band.run_band                                                 device
     files         SOS_Up / SOS_Down / SOS_Result.bin / Trans / Flux, aerosol result file                                       host
 
-Supported keyword values: -SURF.Type 0 1 2 3 4 5 (6: the Nadal series generator is not built); -AER.Model 0 1 3 (2 4 5: not built);
+Supported keyword values: -SURF.Type 0 1 2 3 4 5 (6: the Nadal series generator is not built); -AER.Model 0 1 2 3 (4 5: not built);
 -AP.AbsProfile.Type 7 (no gaseous absorption), or any type with the gas atmosphere and CKD tables handed in by the caller (`gas=`:
 the standard-atmosphere tables of the reference are data of the reference, not part of this package); user angle files are not
 read.  Unsupported values raise NotImplementedError naming the keyword; nothing is silently replaced.  No CPU fallback."""
@@ -72,6 +72,8 @@ def aerosol_model(kw):
         data = os.path.join(root, "fic", "Data_WMO_cor_2015_12_16")                  # CTE_AER_DATAWMO
         return aerosols.Wmo(data, kw["-AER.WMO.Model"],
                             [kw.get(k, 0.0) for k in ("-AER.WMO.DL", "-AER.WMO.WS", "-AER.WMO.OC", "-AER.WMO.SO")])
+    if m == 2:
+        return aerosols.ShettleFenn(os.path.join(os.environ.get("SOS_ABS_ROOT", ""), "fic"), kw["-AER.SF.Model"], kw["-AER.SF.RH"])
     if m == 3:
         b = aerosols.BimodalLnd(kw["-AER.BMD.CM.MRwa"], kw["-AER.BMD.CM.MIwa"], kw["-AER.BMD.CM.SDradius"], kw["-AER.BMD.CM.SDvar"],
                                 kw["-AER.BMD.FM.MRwa"], kw["-AER.BMD.FM.MIwa"], kw["-AER.BMD.FM.SDradius"], kw["-AER.BMD.FM.SDvar"])
@@ -87,7 +89,7 @@ def aerosol_model(kw):
         else:
             raise ValueError("-AER.BMD.VCdef must be 1 or 2")
         return b
-    raise NotImplementedError("-AER.Model %r: only 0 (mono-modal), 1 (WMO) and 3 (bimodal log-normal) are built" % (m,))
+    raise NotImplementedError("-AER.Model %r: 0 (mono-modal), 1 (WMO), 2 (Shettle & Fenn) and 3 (bimodal log-normal) are built" % (m,))
 
 
 def surface(solver, kw, nbmu, rmu, ga, os_nb, os_ns, os_nm):

@@ -146,3 +146,36 @@ def ref_wmo_params(ref, path, wa):
     ier = C.c_int(99)
     ref.sos_init_paramwmo_(_fs(path), _dp(wa), _P(v1), _P(v2), _P(mr), _P(mi), _P(vol), C.byref(ier), _L)
     return ier.value, v1[:4].copy(), v2[:4].copy(), mr[:4].copy(), mi[:4].copy(), vol.copy()
+
+
+def write_sf_files(dirfic, seed=5):
+    """Data files in the layout SOS_INIT_PARAMSF reads (formats 222 / 333 / 555, SOS_AEROSOLS.F:3838-3840) under the reference's
+    file names: log10 sigmas, modal radii per relative humidity, and per component a table wavelength x 8 humidities of complex
+    indices.  Values generated here."""
+    rng = np.random.default_rng(seed)
+    names = ("Data_SF_cor_2015_12_16", "IRefrac_SR_cor_2015_12_16", "IRefrac_LR", "IRefrac_SU_cor_2015_12_16", "IRefrac_LU_cor_2015_12_16",
+             "IRefrac_OM_cor_2015_12_16")
+    os.makedirs(dirfic, exist_ok=True)
+    rhs = (0.0, 50.0, 70.0, 80.0, 90.0, 95.0, 98.0, 99.0)
+    with open(os.path.join(dirfic, names[0]), "w") as f:
+        f.write("".join(" %9.5f" % x for x in (0.35, 0.40, 0.35, 0.40, 0.40)) + "\n")
+        base = np.array([0.027, 0.43, 0.025, 0.40, 0.16])
+        for k, rh in enumerate(rhs):
+            f.write(" %05.2f" % rh + "".join(" %9.5f" % x for x in base * (1.0 + 0.12 * k * k / 7.0)) + "\n")
+    for i in range(5):
+        with open(os.path.join(dirfic, names[1 + i]), "w") as f:
+            for wa in (0.2, 0.3, 0.4, 0.55, 0.7, 0.9, 1.1, 1.6, 2.2, 3.0):
+                row = [wa]
+                for h in range(8):
+                    row += [1.53 - 0.02 * h - 0.01 * i + 0.005 * rng.random(), -abs(rng.normal()) * 10.0 ** (-2 - (i % 2)) / (1 + h)]
+                f.write("".join(" %9.5f" % x for x in row) + "\n")
+    return dirfic
+
+
+def ref_sf_params(ref, dirfic, wa, rh):
+    """SOS_INIT_PARAMSF (SOS_AEROSOLS.F:3557) of the reference library."""
+    v1, v2, mr, mi = (np.zeros(5) for _ in range(4))
+    ier = C.c_int(99)
+    ref.sos_init_paramsf_(C.create_string_buffer(dirfic.encode().ljust(350), 350), _dp(wa), _dp(rh), _P(v1), _P(v2), _P(mr), _P(mi),
+                          C.byref(ier), C.c_size_t(350))
+    return ier.value, v1, v2, mr, mi

@@ -488,6 +488,31 @@ def test_wmo_params_vs_reference(ref, tmp_path):
             assert np.array_equal(mr, gr) and np.array_equal(mi, gi), (path, wa, mr, gr, mi, gi)
 
 
+def test_sf_params_vs_reference(ref, tmp_path):
+    """aerosols.sf_params against SOS_INIT_PARAMSF of the reference library: generated data files in the reference's layout, and
+    the reference's own Shettle & Fenn tables where the reference tree is present; humidities on and between the table's rows."""
+    aer = _aer()
+    if not hasattr(ref, "sos_init_paramsf_"):
+        pytest.skip("SOS_INIT_PARAMSF not in the reference library")
+    dirs = [ac.write_sf_files(str(tmp_path / "fic"))]
+    if os.path.exists("/root/reference/fic/Data_SF_cor_2015_12_16"):
+        dirs.append("/root/reference/fic")
+    for d in dirs:
+        for wa in (0.4, 0.55, 0.865, 1.6, 2.13):
+            for rh in (0.0, 30.0, 50.0, 70.0, 75.5, 90.0, 99.0):
+                e, v1, v2, mr, mi = ac.ref_sf_params(ref, d, wa, rh)
+                g1, g2, gr, gi = aer.sf_params(d, wa, rh)
+                assert e == 0
+                assert np.array_equal(v1, g1) and np.array_equal(v2, g2) and np.array_equal(mr, gr) and np.array_equal(mi, gi), (d, wa, rh)
+    # the maritime model: small rural + oceanic, number densities 0.99 / 0.01 as REAL*4 literals, ALPHAF 70 resp. from the radius
+    p = aer.plan(aer.ShettleFenn(dirs[0], 3, 70.0), [0.55])
+    v1, v2, mr, mi = aer.sf_params(dirs[0], 0.55, 70.0)
+    assert p.models == [(2, [0, 1], [float(np.float32(0.99)), float(np.float32(0.01))], 1)]
+    assert p.components[0] == (mr[0], mi[0], 0.0001, 70.0, 1, v1[0], v2[0], -999.0, 0.55)
+    assert p.components[1][3] == ac.alphaf_for(ac.lnd_rmax(v1[4], v2[4]), 0.55) and p.components[1][:2] == (mr[4], mi[4])
+    assert [c[3] for c in aer.plan(aer.ShettleFenn(dirs[0], 2, 0.0), [0.865]).components][0] == 90.0      # urban: small urban first
+
+
 def test_aerosol_plan_host_logic(tmp_path):
     """The component / model lists aerosols.plan builds: Mie table ranges (ALPHAF), index rounding, mixture weights."""
     aer = _aer()
@@ -507,7 +532,7 @@ def test_aerosol_plan_host_logic(tmp_path):
     f = ac.write_wmo_file(str(tmp_path / "wmo"))
     p = aer.plan(aer.Wmo(f, 2), [0.91])
     v1, v2, mr, mi, vol = aer.wmo_params(f, 0.91)
-    n = [0.05 / vol[1], 0.95 / vol[2]]
+    n = [float(np.float32(0.05)) / vol[1], float(np.float32(0.95)) / vol[2]]    # C(2) = 0.05, C(3) = 0.95 are REAL*4 literals (:1345-1346)
     assert p.models == [(2, [0, 1], [n[0] / (0.0 / vol[0] + n[0] + n[1] + 0.0 / vol[3]), n[1] / (n[0] + n[1])], 1)]
     assert [c[3] for c in p.components] == [50.0, 800.0] and p.components[1][:2] == (mr[2], mi[2])
     with pytest.raises(ValueError):
@@ -528,7 +553,7 @@ def test_gpu_aerosols_front_end_wmo_demo(solver, ref, tmp_path):
     for w in (wa, waref):
         e, v1, v2, mr, mi, vol = ac.ref_wmo_params(ref, f, w)
         comps = [(mr[i], mi[i], 0.0001, (4000.0, 50.0, 800.0, 10.0)[i], 1, v1[i], v2[i], -999.0, w) for i in (1, 2)]
-        n = np.array([0.0 / vol[0], 0.05 / vol[1], 0.95 / vol[2], 0.0 / vol[3]])
+        n = np.array([0.0 / vol[0], np.float64(np.float32(0.05)) / vol[1], np.float64(np.float32(0.95)) / vol[2], 0.0 / vol[3]])   # C(2) = 0.05, C(3) = 0.95: REAL*4 literals
         ntot = 0.0
         for x in n:
             ntot = ntot + x
@@ -542,3 +567,27 @@ def test_gpu_aerosols_front_end_wmo_demo(solver, ref, tmp_path):
         assert np.abs(a - d[n]).max() <= 2e-7 * scale, n
     print("[GPU aerosols front end] WMO maritime at 0.910 um: TA = %.6f (reference flow %.6f), truncation coefficient %.6f (%.6f)"
           % (got.ta, d["kmat1"] / k1[waref]["kmat1"] * aot, got.coef_tronca, d["coef_tronca"]))
+
+
+def test_mie_file_cache_interchange(host, ref, tmp_path):
+    """MIE file names against SOS_NOM_FICMIE of the reference library; a table written by aerosols.write_mie_file is byte for byte the
+    file SOS_MIE writes, and SOS_GRANU of the reference reads it."""
+    aer = _aer()
+    if hasattr(ref, "sos_nom_ficmie_"):
+        for nb, rn, in_, a0, af in ((40, 1.45, -0.004, 0.0001, 200.0), (24, 1.333, 0.0, 0.0001, 100.0), (8, 1.75, -0.44, 0.0001, 4900.0),
+                                    (83, 1.501, -0.00563, 0.0001, 70.0), (40, 1.386, -0.00001, 0.0001, 12300.0)):
+            out = C.create_string_buffer(b" " * 150, 150)
+            ref.sos_nom_ficmie_(ac._ip(nb), ac._fs("NO_USER_ANGLES"), ac._dp(rn), ac._dp(in_), ac._dp(a0), ac._dp(af), out, ac._L, C.c_size_t(150))
+            assert out.raw.decode().strip() == aer.mie_file_name(nb, rn, in_, a0, af), (nb, rn, in_, af)
+    nbmu, xmu, xhr = ac.mie_angles(8, (0.0,))
+    rn, in_, a0, af = 1.45, -0.004, 0.0001, 60.0
+    f_ref, r = ac.ref_mie(ref, str(tmp_path), nbmu, xmu, xhr, rn, in_, a0, af, "REF.bin")
+    t = host_mie(host, nbmu, xmu, rn, in_, a0, af)
+    f_mine = str(tmp_path / aer.mie_file_name(8, rn, in_, a0, af))
+    aer.write_mie_file(f_mine, t, rn, in_, nbmu)
+    assert open(f_mine, "rb").read() == open(f_ref, "rb").read()
+    back = aer.read_mie_file(f_mine, nbmu)
+    assert back["alphaf"] == af and np.array_equal(back["imie"], r["imie"]) and np.array_equal(back["g"], r["g"])
+    a = ac.ref_granu(ref, f_mine, 1, 0.3, 0.5, 0.0, 0.55, nbmu, xmu)
+    b = ac.ref_granu(ref, f_ref, 1, 0.3, 0.5, 0.0, 0.55, nbmu, xmu)
+    assert a[0] == 0 and a[1:4] == b[1:4] and np.array_equal(a[4], b[4])

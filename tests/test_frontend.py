@@ -83,7 +83,10 @@ def test_frontend_host_logic():
               "-AER.BMD.FM.SDradius": 0.08, "-AER.BMD.FM.SDvar": 0.45})
     b = fe.aerosol_model(d)
     assert b.rtauct == 0.4 and b.coarse_rn(0.55) == 1.46 and b.coarse_rn(0.91) == 1.45 and b.fine_in(0.55) == -0.009
-    d["-AER.Model"] = 2
+    d.update({"-AER.Model": 2, "-AER.SF.Model": 3, "-AER.SF.RH": 70.0})
+    sf = fe.aerosol_model(d)
+    assert isinstance(sf, aer.ShettleFenn) and sf.imodele == 3 and sf.rh == 70.0 and sf.dirfic == "/somewhere/fic"
+    d["-AER.Model"] = 4
     with pytest.raises(NotImplementedError):
         fe.aerosol_model(d)
     with pytest.raises(NotImplementedError):                         # gas absorption without the caller's tables
@@ -130,7 +133,7 @@ def test_gpu_run_from_keywords_demo(pkg, solver, tmp_path):
     for w in (wa, waref):
         e, v1, v2, mr, mi, vol = ac.ref_wmo_params(ref, wmo, w)
         comps = [(mr[i], mi[i], 0.0001, (4000.0, 50.0, 800.0, 10.0)[i], 1, v1[i], v2[i], -999.0, w) for i in (1, 2)]
-        n = np.array([0.0 / vol[0], 0.05 / vol[1], 0.95 / vol[2], 0.0 / vol[3]])
+        n = np.array([0.0 / vol[0], np.float64(np.float32(0.05)) / vol[1], np.float64(np.float32(0.95)) / vol[2], 0.0 / vol[3]])   # REAL*4 literals
         ntot = 0.0
         for x in n:
             ntot = ntot + x
