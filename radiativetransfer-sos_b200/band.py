@@ -50,6 +50,7 @@ class BandResult:
     tdifmus: Optional[np.ndarray] = None                   # [nwave]
     tdifmug: Optional[np.ndarray] = None                   # [nwave, N]
     dirs: List[str] = field(default_factory=list)
+    ind_angout: Optional[np.ndarray] = None                # user-angle flags of the radiance angles (set by frontend.run)
 
 
 def enumerate_ckd_terms(nexp, kdis_ai, lamb1):

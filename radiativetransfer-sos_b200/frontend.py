@@ -10,8 +10,8 @@
 
 Supported keyword values: -SURF.Type 0 1 2 3 4 5 (6: the Nadal series generator is not built); -AER.Model 0 1 2 3 (4 5: not built);
 -AP.AbsProfile.Type 7 (no gaseous absorption), or any type with the gas atmosphere and CKD tables handed in by the caller (`gas=`:
-the standard-atmosphere tables of the reference are data of the reference, not part of this package); user angle files are not
-read.  Unsupported values raise NotImplementedError naming the keyword; nothing is silently replaced.  No CPU fallback."""
+the standard-atmosphere tables of the reference are data of the reference, not part of this package); user angle files
+(-ANG.Rad.UserAngFile, -ANG.Aer.UserAngFile) with their output files (-SOS.ResFileUp.UserAng, -SOS.ResFileDown.UserAng).  Unsupported values raise NotImplementedError naming the keyword; nothing is silently replaced.  No CPU fallback."""
 import os
 
 import numpy as np
@@ -38,12 +38,33 @@ def expansion_orders(nb_gauss_mie, nb_gauss_lum):
     return os_nb, os_ns, os_nm
 
 
-def mie_angles(nb_gauss):
+def read_user_angles(path):
+    """A user angle file (-ANG.Rad.UserAngFile / -ANG.Aer.UserAngFile): one zenith angle in degrees per line, 0 <= angle <= 90
+    (SOS_ANGLES.F:776-786, list-directed READ of one value per record)."""
+    out = []
+    with open(path) as f:
+        for ln in f:
+            if not ln.strip():
+                continue
+            v = float(ln.replace(",", " ").split()[0].replace("D", "E").replace("d", "e"))
+            if v < 0.0 or v > 90.0:
+                raise ValueError("user angle %g outside [0, 90] degrees (SOS_ANGLES error 972)" % v)
+            out.append(v)
+    return out
+
+
+def mie_angles(nb_gauss, user_deg=()):
     """Angles of the phase-function calculations (SOS_ANGLES_GAUSS_USER with USAGE = 'MIE', SOS_ANGLES.F:713-860): the Gauss angles
-    in ascending mu, through the D21.14 fields of the angles file SOS_AEROSOLS reads back (format 300, :639)."""
+    and the user angles (weight 0) in ascending mu, through the D21.14 fields of the angles file SOS_AEROSOLS reads back (format
+    300, :639)."""
     mu, w = synth.sos_gauss(nb_gauss + 1)
-    mu, w = round_e(np.sort(mu[:nb_gauss]), 14), round_e(np.asarray(w[:nb_gauss])[np.argsort(mu[:nb_gauss])], 14)
-    n = nb_gauss
+    mu = list(mu[:nb_gauss]) + [float(np.cos(a * (np.arccos(-1.0) / 180.0))) for a in user_deg]
+    w = list(w[:nb_gauss]) + [0.0] * len(user_deg)
+    if len(mu) > 100:
+        raise ValueError("more than CTE_MIE_NBMU_MAX = 100 angles (SOS_ANGLES error 980)")
+    order = np.argsort(mu, kind="stable")
+    mu, w = round_e(np.asarray(mu)[order], 14), round_e(np.asarray(w)[order], 14)
+    n = len(mu)
     xmu, xhr = np.zeros(2 * n + 1), np.zeros(2 * n + 1)
     xmu[n + 1:], xhr[n + 1:] = mu, w
     xmu[:n], xhr[:n] = -mu[::-1], w[::-1]
@@ -120,6 +141,27 @@ def surface(solver, kw, nbmu, rmu, ga, os_nb, os_ns, os_nm):
     raise NotImplementedError("-SURF.Type %r: the Nadal series generator (6) is not built" % (t,))
 
 
+def user_angle_file(src, dst, itrphi, nbmu, flags):
+    """-SOS.ResFileUp.UserAng / -SOS.ResFileDown.UserAng: the header of the full file and the records of the user angles only
+    (IND_ANGOUT = 1), in the order SOS_ABS_MAIN writes them (SOS_ABS_MAIN.F:2303-2420 for -SOS.View 1: angle index N-1 .. 0 of the
+    half plane phi + 180, then 0 .. N-1; :2449-2504 for -SOS.View 2: 0 .. N-1 for every azimuth)."""
+    head, rows = [], []
+    for ln in open(src).read().split("\n"):
+        if ln == "":
+            continue
+        (head if ln.lstrip().startswith("#") else rows).append(ln)
+    if itrphi == 1:
+        if len(rows) != 2 * nbmu:
+            raise ValueError("%s: %d records, expected %d" % (src, len(rows), 2 * nbmu))
+        jj = list(range(nbmu - 1, -1, -1)) + list(range(nbmu))
+    else:
+        if len(rows) % nbmu:
+            raise ValueError("%s: %d records are not a multiple of %d angles" % (src, len(rows), nbmu))
+        jj = list(range(nbmu)) * (len(rows) // nbmu)
+    with open(dst, "w") as f:
+        f.write("\n".join(head + [r for r, j in zip(rows, jj) if flags[j] == 1]) + "\n")
+
+
 def run_keywords(solver, argv, wavelengths=None, gas=None):
     """Runs the simulation the keywords describe, for `wavelengths` (microns; default: the one of -SOS_Main.Wa).  gas: None with
     -AP.AbsProfile.Type 7, else dict(tables=, kdis_ai=, userprofil=, altabs=, ro=, lamb1=[per wavelength]) as band.run_band
@@ -130,15 +172,22 @@ def run_keywords(solver, argv, wavelengths=None, gas=None):
 
 def run(solver, kw, wavelengths=None, gas=None):
     """run_keywords on an already parsed keyword dict (keywords.parse, or sos.sos_proc's arguments)."""
-    for k in ("-ANG.Rad.UserAngFile", "-ANG.Aer.UserAngFile", "-AER.UserFile", "-SURF.File", "-SOS.ResFileUp.UserAng", "-SOS.ResFileDown.UserAng"):
+    for k in ("-AER.UserFile", "-SURF.File"):
         if k in kw:
-            raise NotImplementedError("%s: user angle / user data files are not read by this front end" % k)
+            raise NotImplementedError("%s: user aerosol / surface data files are not read by this front end" % k)
     wl = [float(w) for w in (wavelengths if wavelengths is not None else [kw["-SOS_Main.Wa"]])]
     nb_lum, nb_mie = kw.get("-ANG.Rad.NbGauss"), kw.get("-ANG.Aer.NbGauss")
     os_nb, os_ns, os_nm = expansion_orders(nb_mie, nb_lum)
-    rmu, ga, n0, _ = synth.sos_angles(nb_lum or DEFAULT_NBMU_LUM, kw["-ANG.Thetas"])
+    user_lum = read_user_angles(kw["-ANG.Rad.UserAngFile"]) if "-ANG.Rad.UserAngFile" in kw else []
+    user_mie = read_user_angles(kw["-ANG.Aer.UserAngFile"]) if "-ANG.Aer.UserAngFile" in kw else []
+    rmu, ga, n0, flags = synth.sos_angles(nb_lum or DEFAULT_NBMU_LUM, kw["-ANG.Thetas"], user_lum)
     nbmu = (rmu.size - 1) // 2
-    mie_n, xmu, xhr = mie_angles(nb_mie or DEFAULT_NBMU_MIE)
+    if nbmu > 80:
+        raise ValueError("more than CTE_OS_NBMU_MAX = 80 radiance angles (SOS_ANGLES error 981)")
+    for k in ("-SOS.ResFileUp.UserAng", "-SOS.ResFileDown.UserAng"):
+        if k in kw and not user_lum:
+            raise ValueError("%s requires -ANG.Rad.UserAngFile" % k)             # SOS_ABS_MAIN.F:100-103
+    mie_n, xmu, xhr = mie_angles(nb_mie or DEFAULT_NBMU_MIE, user_mie)
     absprofil = kw["-AP.AbsProfile.Type"]
     if absprofil != 7 and gas is None:
         raise NotImplementedError("-AP.AbsProfile.Type %d needs the gas atmosphere and the CKD tables (gas=...): the standard "
@@ -173,7 +222,11 @@ def run(solver, kw, wavelengths=None, gas=None):
     # ---- the reference's file names ----
     names = {"SOS_Up.txt": kw["-SOS.ResFileUp"], "SOS_Down.txt": kw["-SOS.ResFileDown"], "SOS_Result.bin": kw["-SOS.ResBin"],
              "SOS_Trans.txt": kw.get("-SOS.Trans"), "SOS_Flux.txt": kw.get("-SOS.Flux")}
+    res.ind_angout = np.asarray(flags, dtype=np.int32)          # IND_ANGOUT(1:N): 1 for the user angles
     for d in res.dirs:
+        for key, full in (("-SOS.ResFileUp.UserAng", "SOS_Up.txt"), ("-SOS.ResFileDown.UserAng", "SOS_Down.txt")):
+            if key in kw:
+                user_angle_file(os.path.join(d, full), os.path.join(d, kw[key]), kw["-SOS.View"], nbmu, flags)
         for src, dst in names.items():
             p = os.path.join(d, src)
             if dst and dst != src and os.path.exists(p):

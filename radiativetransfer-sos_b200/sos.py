@@ -98,9 +98,11 @@ def sos_proc(*args, solver=None, gas=None, **kwargs):
         if own:
             s.close()
     nb_lum = kw.get("-ANG.Rad.NbGauss") or frontend.DEFAULT_NBMU_LUM
-    rmu, ga, n0, user = synth.sos_angles(nb_lum, kw["-ANG.Thetas"])
+    user = frontend.read_user_angles(kw["-ANG.Rad.UserAngFile"]) if "-ANG.Rad.UserAngFile" in kw else []
+    rmu, ga, n0, flags = synth.sos_angles(nb_lum, kw["-ANG.Thetas"], user)
     n = (rmu.size - 1) // 2
-    ind = np.zeros(2 * NBMU_MAX + 1, dtype=np.int32)      # IND_ANGOUT(-80:80): 1 where the angle is a user angle (none here)
+    ind = np.zeros(NBMU_MAX + 1, dtype=np.int32)          # IND_ANGOUT_FIN(0:80): 1 where the angle is a user angle
+    ind[:n] = flags
     phi, vza = np.zeros(361), np.zeros(NBMU_MAX + 1)
     tabs = [np.zeros((361, NBMU_MAX + 1)) for _ in range(14)]
     itrphi = kw["-SOS.View"]

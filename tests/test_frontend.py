@@ -238,3 +238,71 @@ def test_gpu_sos_proc_entry(solver, tmp_path):
         assert np.array_equal(tabs[t][:7, :n], res.up[0, t, :7, :n]) and np.array_equal(tabs[7 + t][:7, :n], res.down[0, t, :7, :n])
         assert not tabs[t][7:].any() and not tabs[t][:, n:].any()
     assert ct == aer[0].coef_tronca and eplus == float(res.groups.eplus[0]) and 0.0 < tdir < 1.0 and abs(fd - (fdd + tdir)) < 1e-12
+
+
+def test_user_angle_files(tmp_path):
+    """-ANG.Rad.UserAngFile / -ANG.Aer.UserAngFile and the UserAng output files, host side: the file reader, the merged angle sets and
+    the selection of the records of the user angles in the order SOS_ABS_MAIN writes them (both view modes)."""
+    kw, fe, aer = _mods()
+    api = importlib.import_module("radiativetransfer-sos_b200.api")
+    syn = importlib.import_module("radiativetransfer-sos_b200.synth")
+    f = tmp_path / "ang.txt"
+    f.write_text("5.\n 20.5\n\n60.D0\n")
+    assert fe.read_user_angles(str(f)) == [5.0, 20.5, 60.0]
+    (tmp_path / "bad.txt").write_text("95.\n")
+    with pytest.raises(ValueError):
+        fe.read_user_angles(str(tmp_path / "bad.txt"))
+    n, xmu, xhr = fe.mie_angles(10, [5.0, 20.5, 60.0])
+    assert n == 13 and (np.diff(xmu) > 0).all() and (xhr[n + 1:] == 0).sum() == 3 and abs(xhr[n + 1:].sum() - 1.0) < 1e-13
+    assert np.isin([float("%.13E" % np.cos(np.radians(a))) for a in (5.0, 20.5, 60.0)], xmu).all()
+    rmu, ga, n0, flags = syn.sos_angles(6, 35.0, [5.0, 20.5, 60.0])
+    N = (rmu.size - 1) // 2
+    assert N == 10 and flags.sum() == 3 and flags[n0 - 1] == 0
+    theta = np.degrees(np.arccos(rmu[N + 1:]))
+    for itrphi, nphi, phis in ((1, 2, np.array([0.0, 180.0])), (2, 4, np.arange(0.0, 361.0, 120.0))):
+        up = np.arange(7 * nphi * N, dtype=float).reshape(7, nphi, N) * 1e-3 + 0.1
+        fu, fd = str(tmp_path / ("u%d.txt" % itrphi)), str(tmp_path / ("d%d.txt" % itrphi))
+        api.write_updown(fu, fd, N, itrphi, 0.0, 120, -1.0, phis, theta, up, up + 1.0)
+        out = str(tmp_path / ("user%d.txt" % itrphi))
+        fe.user_angle_file(fu, out, itrphi, N, flags)
+        full = [ln for ln in open(fu).read().split("\n") if ln]
+        got = [ln for ln in open(out).read().split("\n") if ln]
+        head = [ln for ln in full if ln.lstrip().startswith("#")]
+        rows = [ln for ln in got if not ln.lstrip().startswith("#")]
+        assert got[:len(head)] == head and len(rows) == (2 if itrphi == 1 else nphi) * 3
+        col = 0 if itrphi == 1 else 1
+        ang = sorted({round(abs(float(r.split()[col])), 2) for r in rows})
+        assert ang == [5.0, 20.5, 60.0]
+        assert all(r in full for r in rows)
+    with pytest.raises(ValueError):                                  # UserAng output without a user angle file
+        fe.run(None, kw.parse((DEMO.format(root="/tmp/x", nrad=12, naer=20, abs=7) + " -SOS.ResFileUp.UserAng U.txt").split()))
+
+
+@pytest.mark.gpu
+def test_gpu_user_angles_do_not_change_the_field(solver, tmp_path):
+    """User angles have quadrature weight 0: a run with user angle files gives, at the Gauss angles, the radiances of the run without
+    them (1e-9), and the UserAng files hold exactly the user-angle records of the full files."""
+    _, fe, _ = _mods()
+    os.makedirs(os.path.join(str(tmp_path), "abs_root", "fic"))
+    os.environ["SOS_ABS_ROOT"] = os.path.join(str(tmp_path), "abs_root")
+    ac.write_wmo_file(os.path.join(os.environ["SOS_ABS_ROOT"], "fic", "Data_WMO_cor_2015_12_16"))
+    ua = tmp_path / "user.txt"
+    ua.write_text("10.\n40.\n")
+    base = DEMO.format(root=str(tmp_path / "a"), nrad=12, naer=20, abs=7)
+    res0, _ = fe.run_keywords(solver, base.split())
+    # (radiance angles only: a user angle among the phase-function angles may become the anchor of the truncation line,
+    # SOS_AEROSOLS.F:4036-4052, and then changes the aerosol coefficients -- in the reference too)
+    extra = " -ANG.Rad.UserAngFile %s -SOS.ResFileUp.UserAng Up_user.txt -SOS.ResFileDown.UserAng Down_user.txt" % ua
+    res1, _ = fe.run_keywords(solver, (base.replace(str(tmp_path / "a"), str(tmp_path / "b")) + extra).split())
+    keep = np.flatnonzero(res1.ind_angout == 0)
+    assert res1.ind_angout.sum() == 2 and keep.size == res0.up.shape[3] == 13 and res1.up.shape[3] == 15
+    for a, b in ((res0.up, res1.up), (res0.down, res1.down)):
+        for t in (1, 2, 3):                                          # I, Q, U
+            x, y = a[0, t, :2, :13], b[0, t, :2][:, keep]
+            assert np.abs(x - y).max() <= 1e-9 * np.abs(a[0, 1]).max() + 1e-12, t
+    d = res1.dirs[0]
+    for full, user in (("SOS_Up_Demo.txt", "Up_user.txt"), ("SOS_Down_Demo.txt", "Down_user.txt")):
+        lf = open(os.path.join(d, full)).read().split("\n")
+        rows = [ln for ln in open(os.path.join(d, user)).read().split("\n") if ln and not ln.lstrip().startswith("#")]
+        assert len(rows) == 4 and all(r in lf for r in rows)
+        assert sorted({round(abs(float(r.split()[0])), 2) for r in rows}) == [10.0, 40.0]
