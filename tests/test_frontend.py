@@ -232,7 +232,7 @@ def test_gpu_sos_proc_entry(solver, tmp_path):
     n, ind, phi, vza, tabs, (tdir, fdd, fd, eplus, ct) = out[0], out[1], out[2], out[3], out[4:18], out[18:]
     res, aer = fe.run_keywords(solver, DEMO.format(root=str(tmp_path / "b"), nrad=12, naer=20, abs=7).replace("-SOS.View 1 -SOS.View.Phi 0.",
                                                                                                                 "-SOS.View 2 -SOS.View.Dphi 60").split())
-    assert n == res.up.shape[3] == 13 and ind.shape == (161,) and phi.shape == (361,) and vza.shape == (81,) and tabs[0].shape == (361, 81)
+    assert n == res.up.shape[3] == 13 and ind.shape == (81,) and not ind.any() and phi.shape == (361,) and vza.shape == (81,) and tabs[0].shape == (361, 81)
     assert list(phi[:7]) == [0.0, 60.0, 120.0, 180.0, 240.0, 300.0, 360.0] and res.nphi == 7
     for t in range(7):
         assert np.array_equal(tabs[t][:7, :n], res.up[0, t, :7, :n]) and np.array_equal(tabs[7 + t][:7, :n], res.down[0, t, :7, :n])
