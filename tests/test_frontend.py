@@ -306,3 +306,119 @@ def test_gpu_user_angles_do_not_change_the_field(solver, tmp_path):
         rows = [ln for ln in open(os.path.join(d, user)).read().split("\n") if ln and not ln.lstrip().startswith("#")]
         assert len(rows) == 4 and all(r in lf for r in rows)
         assert sorted({round(abs(float(r.split()[0])), 2) for r in rows}) == [10.0, 40.0]
+
+
+class _StubSolver:
+    """Stands in for api.Solver in the CPU test of the host-side flow below: same method names, argument lists and array shapes,
+    values that depend only on the inputs (radiances are functions of the cosine of the angle, so zero-weight angles cannot change
+    the values at the others).  TEST INFRASTRUCTURE; nothing here computes radiative transfer."""
+    def __init__(self):
+        self.calls = []
+
+    def aerosols(self, nbmu, xmu, xhr, components, models, os_nb, want_phase=True):
+        self.calls.append(("aerosols", len(components), len(models)))
+        nc, nm = len(components), len(models)
+        ck = np.array([[2.0 / c[8] + 0.1 * c[0], 1.8 / c[8], 1.0] for c in components]).reshape(nc, 3)
+        scal, coef = np.zeros((nm, 8)), np.zeros((nm, 6, os_nb + 1))
+        for m, (ncomp, idx, w, itronc) in enumerate(models):
+            k1 = ck[idx[0], 0] if ncomp == 0 else sum(wi * ck[i, 0] for wi, i in zip(w, idx))
+            scal[m] = [k1, 0.9 * k1, 0.9, 0.88, 0.3 * itronc, 0.7, 1.0, itronc]
+            coef[m, 1] = 0.8 ** np.arange(os_nb + 1) * (2 * np.arange(os_nb + 1) + 1)
+        return dict(comp_k=ck, comp_phase=None, comp_ier=np.zeros(nc, np.int32), scal=scal, coef=coef, phase=None, model_ier=np.zeros(nm, np.int32))
+
+    def glitter(self, nbmu, rmu, ga, wind, ind, os_nb, os_ns, os_nm):
+        self.calls.append(("glitter", nbmu, os_nb, os_ns, os_nm))
+        return np.zeros((os_nb + 1, 9, nbmu, nbmu), np.float32), np.zeros(nbmu * (nbmu + 1) // 2, np.int32)
+
+    def roujean(self, nbmu, rmu, os_nb, k0, k1, k2):
+        return np.zeros((os_nb + 1, 9, nbmu, nbmu), np.float32)
+
+    def surface_bpdf(self, isurf, nbmu, rmu, ga, ind, os_nb, os_ns, os_nm, coef_c=0.0):
+        return np.zeros((os_nb + 1, 9, nbmu, nbmu), np.float32)
+
+    def bpdf_ajout_brdf(self, a, b):
+        return a + b
+
+    def set_direct_models(self, **kw):
+        self.calls.append(("direct", sorted(kw)))
+
+    def profile(self, altabs, tau, terms, text_hop=True):
+        n = len(terms)
+        nt = np.full(n, 12, np.int32)
+        z = np.tile(np.linspace(120.0, 0.0, 601), (n, 1))
+        h = np.tile(np.linspace(0.0, 0.3, 601), (n, 1))
+        return nt, z, h, np.full((n, 601), 0.5), np.full((n, 601), 0.5), np.zeros(n, np.int32)
+
+    def upload(self, wl, groups=None, ngroup=None):
+        outer = self
+
+        class B:
+            def __init__(s):
+                s.ngroup, s.wl = ngroup, wl
+                s.wmax = max(2 * o.nbmu + 1 for o in wl.optics)
+
+            def free(s):
+                outer.calls.append(("free",))
+        return B()
+
+    def run(self, batch, want_terms=True, want_groups=True):
+        g, w = batch.ngroup, batch.wmax
+
+        class G:
+            n_rec = np.full(g, 3, np.int32)
+            rec = np.ones((g, 5, 3, w)) * 0.01
+            ttot_tronc, ttot_vrai, tauout = np.full(g, 0.2), np.full(g, 0.25), np.zeros(g)
+            emoins, eplus = np.full(g, 0.15), np.full(g, 0.05)
+        return None, G
+
+    def batch_trphi(self, batch, igli, wind, ind, ifresnel, itrphi, phios, pas_phi, ipolar, download=True):
+        nphi = 2 if itrphi == 1 else 360 // pas_phi + 1
+        nmax = (batch.wmax - 1) // 2
+        up = np.zeros((batch.ngroup, 7, nphi, nmax))
+        for g, o in enumerate(batch.wl.optics):
+            mu = np.asarray(o.rmu)[o.nbmu + 1:]
+            for t in range(7):
+                for ip in range(nphi):
+                    up[g, t, ip, :o.nbmu] = (t + 1) * 0.01 * mu + 0.001 * ip
+        return nphi, up, up + 1.0
+
+
+def test_host_flow_with_stub_solver(tmp_path):
+    """frontend.run_keywords, the user-angle outputs and sos.sos_proc end to end on the host with a stand-in for the device (shapes,
+    file names, argument plumbing, optical-thickness scaling); the numbers come from the stub, the GPU tests check the real ones."""
+    kwm, fe, aer = _mods()
+    sos = importlib.import_module("radiativetransfer-sos_b200.sos")
+    os.makedirs(os.path.join(str(tmp_path), "abs_root", "fic"))
+    os.environ["SOS_ABS_ROOT"] = os.path.join(str(tmp_path), "abs_root")
+    ac.write_wmo_file(os.path.join(os.environ["SOS_ABS_ROOT"], "fic", "Data_WMO_cor_2015_12_16"))
+    ac.write_sf_files(os.path.join(os.environ["SOS_ABS_ROOT"], "fic"))
+    s = _StubSolver()
+    base = DEMO.format(root=str(tmp_path / "a"), nrad=12, naer=20, abs=7)
+    res, aopt = fe.run_keywords(s, base.split(), wavelengths=[0.865, 0.910])
+    assert len(res.dirs) == 2 and res.nphi == 2 and res.up.shape == (2, 7, 2, 13)
+    for d in res.dirs:
+        assert sorted(os.listdir(d)) == ["SOS_Down_Demo.txt", "SOS_Result.bin", "SOS_Up_Demo.txt"]
+    assert sorted(os.listdir(str(tmp_path / "a" / "AER"))) == ["Aerosols_Demo.txt_0.865000", "Aerosols_Demo.txt_0.910000"]
+    assert ("glitter", 13, 40, 24, 64) in s.calls and ("aerosols", 6, 3) in s.calls        # 2 wavelengths + the reference one, 2 components each
+    assert abs(aopt[0].ta / aopt[1].ta - aopt[0].kmat1 / aopt[1].kmat1) < 1e-14 and 0.0 < aopt[1].ta < 0.3      # TA = K(WA) / K(WAREF) * AOT_REF
+    # user angles + UserAng files, view 2, Shettle & Fenn aerosols, Roujean + Breon surface, transmissions
+    ua = tmp_path / "user.txt"
+    ua.write_text("10.\n40.\n")
+    argv = (base.replace(str(tmp_path / "a"), str(tmp_path / "b")).replace("-SOS.View 1 -SOS.View.Phi 0.", "-SOS.View 2 -SOS.View.Dphi 90")
+            .replace("-AER.Model 1 -AER.WMO.Model 2", "-AER.Model 2 -AER.SF.Model 3 -AER.SF.RH 70.")
+            .replace("-SURF.Type 1", "-SURF.Type 5 -SURF.Roujean.K0 0.1 -SURF.Roujean.K1 0.05 -SURF.Roujean.K2 0.3")
+            + " -ANG.Rad.UserAngFile %s -ANG.Aer.UserAngFile %s -SOS.ResFileUp.UserAng U.txt -SOS.ResFileDown.UserAng D.txt" % (ua, ua))
+    res2, _ = fe.run_keywords(s, argv.split())
+    assert res2.ind_angout.sum() == 2 and res2.up.shape == (1, 7, 5, 15) and ("direct", ["ibreon", "roujean"]) in s.calls
+    rows = [ln for ln in open(os.path.join(res2.dirs[0], "U.txt")).read().split("\n") if ln and not ln.lstrip().startswith("#")]
+    assert len(rows) == 5 * 2
+    keep = np.flatnonzero(res2.ind_angout == 0)
+    res1, _ = fe.run_keywords(s, base.replace(str(tmp_path / "a"), str(tmp_path / "c")).replace("-SOS.View 1 -SOS.View.Phi 0.", "-SOS.View 2 -SOS.View.Dphi 90").split())
+    assert np.allclose(res1.up[0, 1, :5, :13], res2.up[0, 1, :5][:, keep], rtol=0, atol=1e-15)
+    # the f2py-shaped entry
+    out = sos.sos_proc(solver=s, resroot=str(tmp_path / "d"), wa_simu=0.910, tetas=35.0, nbmu_gauss_lum=12, nbmu_gauss_mie=20, waref_aot=0.55,
+                       aot_ref=0.3, itronc_aer=1, imod_aer=1, imodele_wmo=2, hr=8.0, ha=2.0, iprofil=1, psurf=1013.0, absprofil=7, isurf=1,
+                       surf_ind=1.34, wind=2.0, rho=0.0, itrphi=2, pas_phi=60, igmax=-999, zout=-999.0, ficangles_user_lum=str(ua), ier=0, trace=False)
+    assert len(out) == 23 and out[0] == 15 and out[1].shape == (81,) and out[1].sum() == 2 and out[2].shape == (361,) and out[4].shape == (361, 81)
+    assert list(out[2][:7]) == [0.0, 60.0, 120.0, 180.0, 240.0, 300.0, 360.0] and not out[4][7:].any() and out[4][:7, :15].all()
+    assert 0.0 < out[18] < 1.0 and abs(out[20] - (out[19] + out[18])) < 1e-12 and out[21] == 0.05 and out[22] == 0.3
