@@ -11,8 +11,8 @@ for a LIST of wavelengths, with the work itself done on the device by Solver.aer
                                                             thickness at the reference wavelength (MODE_PARAM_BILND = 1 / 2)
     optical thickness at WA      SOS_PROC.F:2941-3063       TA = KMAT1(WA) / KMAT1(WAREF) * AOT_REF
 
-External phase functions (4) and user mixtures (5) are not built.  Keyword parsing stays with the
-caller.  No CPU fallback: the numbers come from Solver.aerosols, which needs the GPU."""
+External phase functions (4) and user mixtures (5) are not built.  Keywords: frontend.aerosol_model maps -AER.* to these models.
+No CPU fallback: the numbers come from Solver.aerosols, which needs the GPU."""
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 

@@ -9,7 +9,7 @@ synthesis, result files -- done for a LIST of wavelengths with every stage batch
     transmissions        Solver.transmissions         the -SOS.Trans solves of SOS.F:605-637 (optional)
     files                write_updown / write_trans / write_flux / formats.write_result_bin, one directory per wavelength
 
-Keyword parsing (SOS_ABS_MAIN.F) and the aerosol / Mie preparation (SOS_PREPA_OS) stay with the caller: a wavelength arrives as
+Keywords and the aerosol / surface preparation are frontend.py's (which calls this module): here a wavelength arrives as
 the optics SOS_PREPA_OS would hand to SOS plus the scalars of the profile.  No CPU fallback: Solver() raises without a GPU."""
 import os
 from dataclasses import dataclass, field
