@@ -422,3 +422,18 @@ def test_host_flow_with_stub_solver(tmp_path):
     assert len(out) == 23 and out[0] == 15 and out[1].shape == (81,) and out[1].sum() == 2 and out[2].shape == (361,) and out[4].shape == (361, 81)
     assert list(out[2][:7]) == [0.0, 60.0, 120.0, 180.0, 240.0, 300.0, 360.0] and not out[4][7:].any() and out[4][:7, :15].all()
     assert 0.0 < out[18] < 1.0 and abs(out[20] - (out[19] + out[18])) < 1e-12 and out[21] == 0.05 and out[22] == 0.3
+
+
+def test_command_line_entry(capsys):
+    """python -m radiativetransfer-sos_b200 <keywords>: exit status 1 with a message for a bad command line, and -- on a machine
+    without a GPU -- for a good one (no CPU fallback)."""
+    import ctypes
+    main = importlib.import_module("radiativetransfer-sos_b200.__main__").main
+    assert main(["-SOS_Main.Wa", "0.5"]) == 1 and "missing required keyword" in capsys.readouterr().err
+    assert main(["-SOS.Wavelength", "0.5"]) == 1 and "unknown keyword" in capsys.readouterr().err
+    api = importlib.import_module("radiativetransfer-sos_b200.api")
+    lib = api.load_library()
+    lib.sosgpu_device_count.restype = ctypes.c_int
+    if lib.sosgpu_device_count() == 0:
+        argv = "-SOS_Main.Wa 0.91 -SOS_Main.ResRoot /tmp/x -ANG.Thetas 35. -SOS.View 1 -SURF.Type 0 -SURF.Alb 0.1 -AP.AerProfile.Type 1 -AP.AbsProfile.Type 7"
+        assert main(argv.split()) == 1 and "no CPU fallback" in capsys.readouterr().err
