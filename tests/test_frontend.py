@@ -281,7 +281,9 @@ def test_user_angle_files(tmp_path):
 @pytest.mark.gpu
 def test_gpu_user_angles_do_not_change_the_field(solver, tmp_path):
     """User angles have quadrature weight 0: a run with user angle files gives, at the Gauss angles, the radiances of the run without
-    them (1e-9), and the UserAng files hold exactly the user-angle records of the full files."""
+    them -- to the level of the stop tests (1e-5, inc/SOS.h:389-400), not to rounding, because the stop tests of SOS_OS take their
+    maxima over ALL angles, user angles included, so the two runs may stop at different scattering / Fourier orders -- and the
+    UserAng files hold exactly the user-angle records of the full files."""
     _, fe, _ = _mods()
     os.makedirs(os.path.join(str(tmp_path), "abs_root", "fic"))
     os.environ["SOS_ABS_ROOT"] = os.path.join(str(tmp_path), "abs_root")
@@ -299,7 +301,7 @@ def test_gpu_user_angles_do_not_change_the_field(solver, tmp_path):
     for a, b in ((res0.up, res1.up), (res0.down, res1.down)):
         for t in (1, 2, 3):                                          # I, Q, U
             x, y = a[0, t, :2, :13], b[0, t, :2][:, keep]
-            assert np.abs(x - y).max() <= 1e-9 * np.abs(a[0, 1]).max() + 1e-12, t
+            assert np.abs(x - y).max() <= 1e-4 * np.abs(a[0, 1]).max(), t
     d = res1.dirs[0]
     for full, user in (("SOS_Up_Demo.txt", "Up_user.txt"), ("SOS_Down_Demo.txt", "Down_user.txt")):
         lf = open(os.path.join(d, full)).read().split("\n")
