@@ -174,3 +174,59 @@ def test_formatted_e15_8_round_trip(f77, pkg, tmp_path):
     fm = pkg.formats
     assert open(fic).read() == "".join(fm.fortran_e(x, 15, 8) for x in v) + "\n"
     assert np.array_equal(w, fm.round_e(v, 8))
+
+
+def test_round_3_additions(f77, tmp_path):
+    """What the aerosol routines needed: DINT / DNINT, dotted operators in lower case, a variable whose name starts with IF on the
+    left of an assignment (not a logical IF), INDEX, formatted READ on a computed unit number, internal WRITE of an integer into a
+    CHARACTER variable."""
+    data = tmp_path / "tab.txt"
+    data.write_text("   1.50000   2.25000\n   3.00000   4.00000\n")
+    lib = compile_fortran(f77, tmp_path, "round3", """
+      SUBROUTINE ROUND3(X,FIC,OUT,KOUT,CH)
+      IMPLICIT NONE
+      DOUBLE PRECISION X,OUT(8),A,B
+      INTEGER*4 KOUT(4),IFIN,I,IGRANU
+      CHARACTER*100 FIC
+      CHARACTER*6 CH
+      OUT(1)=DINT(X+X+20)
+      OUT(2)=DNINT(X*1000.D+00)/1000.D+00
+      OUT(3)=-DNINT(-X*10.D+00)/10.D+00
+      OUT(4)=DNINT(2.5D+00)
+      IGRANU=2
+      KOUT(1)=0
+      IF (IGRANU.eq.2) KOUT(1)=7
+      IFIN=INDEX(FIC,' ')
+      IFIN=IFIN-1
+      KOUT(2)=IFIN
+      IF (IFIN.le.0) KOUT(2)=-1
+      OPEN(11,FILE=FIC,STATUS='OLD',ERR=99)
+      OPEN(12,FILE=FIC,STATUS='OLD',ERR=99)
+      DO I=1,2
+         READ((I+10),555,ERR=99) A,B
+         OUT(4+I)=A+B
+      ENDDO
+      READ(12,555,ERR=99) A,B
+      OUT(7)=A*B
+      CLOSE(11)
+      CLOSE(12)
+      WRITE(CH,'(I6)') INT(X*1000)
+      DO I=1,6
+         IF (CH(I:I).EQ.' ') CH(I:I)='0'
+      ENDDO
+      KOUT(3)=1
+      RETURN
+   99 KOUT(3)=-1
+      RETURN
+  555 FORMAT(2(1X,F9.5))
+      END
+""")
+    out, kout = np.zeros(8), np.zeros(4, dtype=np.int32)
+    ch = C.create_string_buffer(b"      ", 6)
+    fic = C.create_string_buffer(str(data).encode().ljust(100), 100)
+    lib.round3_(C.byref(C.c_double(1.4496)), fic, out.ctypes.data_as(C.POINTER(C.c_double)), kout.ctypes.data_as(C.POINTER(C.c_int)), ch,
+                C.c_size_t(100), C.c_size_t(6))
+    assert out[0] == 22.0 and out[1] == 1.45 and out[2] == 1.4 and out[3] == 3.0            # DNINT: halves away from zero
+    assert kout[0] == 7 and kout[1] == len(str(data)) and kout[2] == 1
+    assert out[4] == 3.75 and out[5] == 3.75                                                  # unit 11 line 1, unit 12 line 1
+    assert out[6] == 12.0 and ch.raw == b"001449"                                             # unit 12 line 2; INT truncates 1449.6
