@@ -15,13 +15,15 @@ What is implemented is what those routines use, with Fortran's own semantics whe
     zeroed .bss);
   * expression typing by Fortran's rules: REAL*4 literals and all-REAL*4 sub-expressions are evaluated in single
     precision, mixed operands are promoted operand by operand, integer division truncates, x**n with an integer n is
-    libgcc's __powidf2 / __powisf2 multiplication chain, x**y otherwise pow / powf; generic and specific intrinsics;
+    libgcc's __powidf2 / __powisf2 multiplication chain, x**y otherwise pow / powf; generic and specific intrinsics (DINT
+    truncates, DNINT rounds halves away from zero); dotted operators in either case;
   * DO loops with the iteration count fixed at entry (labelled, shared terminal labels, ENDDO), DO WHILE, block and
     logical IF, GOTO, CONTINUE, CALL (temporaries for expression arguments), RETURN;
   * I/O as gfortran does it: unformatted sequential records with 4-byte markers (implied DO lists, whole arrays, ERR=,
-    END=, IOSTAT=), formatted records on files opened in the routine (nX, Iw, Fw.d, Ew.d, Dw.d, repeat groups, format
-    reversion), OPEN (STATUS OLD / NEW / UNKNOWN), CLOSE (STATUS='DELETE'), REWIND, INQUIRE(FILE=, EXIST=);
-    trace / message WRITEs (list-directed or to units not opened in the routine) are dropped;
+    END=, IOSTAT=), formatted records on files opened in the routine, also through a computed unit number (nX, Iw, Fw.d,
+    Ew.d, Dw.d, repeat groups, format reversion), internal WRITE of an integer with '(Iw)' into a CHARACTER variable, OPEN (STATUS OLD / NEW / UNKNOWN), CLOSE (STATUS='DELETE'), REWIND, INQUIRE(FILE=, EXIST=);
+    trace / message WRITEs (list-directed or to units not opened in the routine) are dropped, formatted WRITEs of character
+    items (trace tables) abort if they are ever reached;
   * CHARACTER: comparison with blank padding, assignment, substrings, //, INDEX, CALL SYSTEM.
 Calls of routines that are not among the translated files abort at run time (they are outside the hot path).
 Anything else raises Unsupported and the routine is skipped (reported in oracle/_ref/translation_report.txt).
