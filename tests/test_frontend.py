@@ -310,6 +310,48 @@ def test_gpu_user_angles_do_not_change_the_field(solver, tmp_path):
         assert sorted({round(abs(float(r.split()[0])), 2) for r in rows}) == [10.0, 40.0]
 
 
+def test_user_angles_do_not_change_the_reference_field(tmp_path):
+    """The property the GPU test above relies on, on the reference itself (oracle/_ref/libsosref.so, CPU): SOS_GLITTER ->
+    SOS_PROFILE -> SOS + SOS_OS -> SOS_AGGREGATE -> SOS_TRPHI_OPTION with and without two user angles (weight 0) give the same
+    radiances at the Gauss angles and at the solar angle, with the same number of Fourier orders."""
+    _, fe, _ = _mods()
+    pkg = importlib.import_module("radiativetransfer-sos_b200")
+    syn, fm = pkg.synth, pkg.formats
+    ref = refdirect.lib()
+    if ref is None or not hasattr(ref, "sos_glitter_"):
+        pytest.skip("oracle/_ref/libsosref.so not built")
+    tmp = str(tmp_path)
+    os_nb, os_ns, os_nm = fe.expansion_orders(20, 12)
+    k = np.arange(os_nb + 1)
+    beta = (2 * k + 1) * 0.75 ** k                                   # Henyey-Greenstein-like expansion, mildly polarizing
+    gamma, alpha, zeta = np.where(k >= 2, -0.05 * beta, 0.0), np.where(k >= 2, 0.6 * beta, 0.0), np.where(k >= 2, 0.55 * beta, 0.0)
+    term = dict(lamb1=1, ik=(1,) * 8, absprofil=7, iprofil=1, tr=fe.rayleigh_thickness(1013.0, 0.910), hr=8.0, ta=0.25, ha=2.0, zmin=0.0, zmax=0.0)
+    ier, nt, _, z, h, pa, pm = refdirect.profile(ref, tmp, np.linspace(120.0, 0.0, 50), np.zeros(50), term)
+    assert ier == 0
+    rr = refdirect.runner()
+    out = {}
+    for name, user in (("plain", []), ("user", [10.0, 40.0])):
+        rmu, ga, n0, flags = syn.sos_angles(12, 35.0, user)
+        N = (rmu.size - 1) // 2
+        surf = refdirect.glitter(ref, fm, tmp, N, rmu, ga, 2.0, 1.34, os_nb, os_ns, os_nm)
+        o = syn.Optics(nbmu=N, rmu=rmu.copy(), ga=ga, n0=n0, tetas=35.0, os_nb=os_nb, alpha=alpha, beta=beta, gamma=gamma, zeta=zeta,
+                       a_trunc=0.4, piztr=0.95, rho=0.0, imat_surf=1, igli=1, surf=surf, ind_surf=1.34, wind=2.0, igmax=100, ipolar=1, zout=-1.0)
+        wl = syn.Workload("ref")
+        wl.optics.append(o)
+        wl.terms.append(syn.Term(0, 1.0, z, h, pa, pm))
+        r, _, _ = rr.solve_terms(wl, [0], 1)
+        rec, sc = rr.aggregate_point(ref, fm, tmp, N, [(1.0, r[0])])
+        nr = int(np.flatnonzero(np.abs(rec).reshape(rec.shape[0], -1).max(axis=1))[-1]) + 1
+        _, _, _, up, down = refdirect.trphi_option(ref, fm, tmp, rec[:nr], N, o.rmu, o.ga, sc["ttot_tronc"], sc["tauout"], 1, o.n0, 2.0, 1.34,
+                                                   0, 1, 0.0, 30)
+        out[name] = (N, nr, flags, up, down)
+    keep = np.flatnonzero(out["user"][2] == 0)
+    assert out["plain"][0] == 13 and out["user"][0] == 15 and keep.size == 13 and out["plain"][1] == out["user"][1]
+    for a, b in ((out["plain"][3], out["user"][3]), (out["plain"][4], out["user"][4])):
+        for t in (1, 2, 3):
+            assert np.abs(a[t, :2, :13] - b[t, :2][:, keep]).max() <= 1e-9 * np.abs(a[1]).max(), t
+
+
 class _StubSolver:
     """Stands in for api.Solver in the CPU test of the host-side flow below: same method names, argument lists and array shapes,
     values that depend only on the inputs (radiances are functions of the cosine of the angle, so zero-weight angles cannot change
