@@ -224,9 +224,19 @@ int sosgpu_glitter(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *c
 
 /* SOS_SURFACE_BPDF (SOS_SURFACE_BPDF.F:219-392) for the Rondeaux (isurf = 4), Breon (5) and Maignan (7, coefficient coef_c)
  * vegetation / soil BPDF models: SOS_GSF_RONDEAUX_BREON or SOS_GSF_MAIGNAN + SOS_MAT_FRESNEL + SOS_MAT_REFLEXION +
- * SOS_MISE_FORMAT; same record layout as sosgpu_glitter.  (Nadal, isurf 6, is not provided: SOSGPU_ERR_ARG.) */
+ * SOS_MISE_FORMAT; same record layout as sosgpu_glitter.  (Nadal, isurf 6: sosgpu_surface_nadal; here SOSGPU_ERR_ARG.) */
 int sosgpu_surface_bpdf(sosgpu_ctx *ctx, int isurf, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
                         int os_nm, double ind_surf, double coef_c, float *surf);
+
+/* SOS_SURFACE_BPDF with ISURF = 6 (SOS_SURFACE_BPDF.F:219-392): Nadal's BPDF model (alpha, beta; > 0) = SOS_F21SF_NADAL +
+ * SOS_CALC_F21_NADAL_SUR_FRESNEL (:686-1223: Fourier series of F21 of Nadal / F21 of Fresnel up to os_nb, cut by its recombination
+ * test) + SOS_MAT_FRESNEL + SOS_MAT_REFLEXION + SOS_MISE_FORMAT; same record layout as sosgpu_glitter.
+ * pairing 0: the reference's file.  SOS_F21SF_NADAL writes a series for each of the N*N (theta1, theta2) pairs and
+ * SOS_MAT_REFLEXION reads the series file sequentially for its N(N+1)/2 pairs (I, J <= I) (SOS_SURFACE.F:1832-1842), so that
+ * pair number p gets the series of (p / N + 1, p mod N + 1).  pairing 1: every pair gets its own series (not what the reference
+ * computes).  il_out (may be NULL): [N(N+1)/2] series lengths IL (-1: the recombination got worse at order 0). */
+int sosgpu_surface_nadal(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns, int os_nm,
+                         double ind_surf, double alpha, double beta, int pairing, float *surf, int *il_out);
 
 /* SOS_ROUJEAN (SOS_ROUJEAN.F:212-416: SOS_FSF_ROUJEAN + SOS_MISE_FORMAT_RJ): Fourier series of Roujean's BRDF (k0, k1, k2) for
  * every (incidence, reflection) pair, surf [os_nb+1][9][N][N] REAL*4 (only R11 non-zero).  SOSGPU_ERR_IER when the model

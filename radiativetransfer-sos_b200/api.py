@@ -516,6 +516,20 @@ class Solver:
         self._check(rc, "surface_bpdf")
         return surf
 
+    def surface_nadal(self, nbmu, rmu, chr_, ind_surf, alpha, beta, os_nb, os_ns, os_nm, pairing="reference"):
+        """SOS_SURFACE_BPDF with ISURF = 6 (SOS_SURFACE_BPDF.F:219, series generator SOS_F21SF_NADAL :686): Nadal's BPDF (alpha,
+        beta) -> (records [os_nb+1, 9, N, N] REAL*4, series lengths [N(N+1)/2]).  pairing "reference": the file the reference
+        writes (its SOS_MAT_REFLEXION gives pair number p the series of (p / N + 1, p mod N + 1)); "own": each pair its own series."""
+        if pairing not in ("reference", "own"):
+            raise ValueError("pairing: 'reference' or 'own'")
+        surf = np.zeros((os_nb + 1, 9, nbmu, nbmu), dtype=np.float32)
+        il = np.zeros(nbmu * (nbmu + 1) // 2, dtype=np.int32)
+        rc = self.lib.sosgpu_surface_nadal(self.ctx, C.c_int(nbmu), _d(_f64(rmu)), _d(_f64(chr_)), C.c_int(os_nb), C.c_int(os_ns),
+                                           C.c_int(os_nm), C.c_double(ind_surf), C.c_double(alpha), C.c_double(beta),
+                                           C.c_int(0 if pairing == "reference" else 1), surf.ctypes.data_as(c_fp), il.ctypes.data_as(c_ip))
+        self._check(rc, "surface_nadal")
+        return surf, il
+
     def roujean(self, nbmu, rmu, os_nb, k0, k1, k2):
         """SOS_ROUJEAN (SOS_ROUJEAN.F:212): Fourier series of Roujean's BRDF, records [os_nb+1, 9, N, N] REAL*4."""
         surf = np.zeros((os_nb + 1, 9, nbmu, nbmu), dtype=np.float32)

@@ -8,6 +8,7 @@
 // Compute-type kernel (FP64 CUDA cores + SFU): ~1025 exp and up to (OS_NM+1)*1023 cos per pair.
 #include "sosgpu_internal.h"
 #include "post_kernels.h"
+#include "nadal_series.cuh"
 #include <math.h>
 
 #define PH_NU 1024      // CTE_PH_NU   SOS.h:319
@@ -31,7 +32,14 @@ __device__ __forceinline__ double calcg_maignan(double c1, double c2, double s12
   return coef_c * exp(-sqrt(tan2_i)) / (1. / c1 + 1. / c2);
 }
 
-// smem: U[1025] | G[nm_alloc] | K[6][2][ns+1] | scalars
+// B1(s) = max over the azimuths of a non-negative deviation: non-negative doubles order like their bit patterns, and NaN (0/0) has
+// a larger pattern than any finite value, which makes the comparisons B1 > threshold / B1 < B1_PREC false, as in the reference
+__device__ __forceinline__ void atomic_max_nonneg(double *addr, double v)
+{
+  atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// smem: U[1025] | G[nm_alloc] | K[6][2][ns+1] | B1[nb+1] (gmodel 4 only) | scalars
 __global__ void k_glitter(GlitterParams p, float *__restrict__ surf, int *__restrict__ il_out)
 {
   extern __shared__ double sh[];
@@ -69,6 +77,37 @@ __global__ void k_glitter(GlitterParams p, float *__restrict__ surf, int *__rest
       G[0] = (p.gmodel == 1) ? 1. / (1. / c1 + 1. / c2) : 1.;    // Rondeaux : Breon
       s_il = 0;
       if (il_out) il_out[pair] = 0;
+    }
+    __syncthreads();
+  } else if (p.gmodel == 4) {
+    // ---------------- SOS_F21SF_NADAL (SOS_SURFACE_BPDF.F:686-1069): series of F(phi) up to OS_NB with a recombination test ----------------
+    // The reference writes one series per (I1, I2) for all N*N pairs and SOS_MAT_REFLEXION reads the file sequentially for the
+    // N(N+1)/2 pairs (I, J <= I) (SOS_SURFACE.F:1832-1842): pair number `pair` gets the series of (pair / N + 1, pair mod N + 1).
+    // nadal_pairing 0 reproduces that file; 1 takes the series of the pair (I, J) itself.
+    const int a1 = p.nadal_pairing ? I : pair / N + 1, a2 = p.nadal_pairing ? J : pair % N + 1;
+    const double n1 = p.rmu[a1 + N], n2 = p.rmu[a2 + N];
+    const double q = pi / NAD_PH_NU;
+    double *B1 = K + 12 * (NS + 1);
+    for (int i = tid; i <= NAD_PH_NU; i += nthr) U[i] = nadal_f(p.ind, p.alpha_nadal, p.beta_nadal, n1, n2, q * i);   // :773-782
+    for (int i = tid; i < ng; i += nthr) G[i] = 0.0;
+    for (int s = tid; s <= NB; s += nthr) B1[s] = 0.0;
+    __syncthreads();
+    for (int s = tid; s <= NB; s += nthr) G[s] = nadal_coef(U, s, q, pi);                                             // :856-861
+    __syncthreads();
+    for (int i = tid; i <= NAD_PH_NU; i += nthr) {           // :868-883, one azimuth per thread walking the orders upwards
+      const double phi = i * q, f = U[i];
+      double t1 = G[0];
+      atomic_max_nonneg(&B1[0], fabs((t1 - f) / f));
+      for (int s = 1; s <= NB; ++s) {
+        t1 = nadal_recomb_step(t1, G[s], s, phi);
+        atomic_max_nonneg(&B1[s], fabs((t1 - f) / f));
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int il = nadal_cut(B1, NB);                      // :888-900
+      s_il = il;
+      if (il_out) il_out[pair] = il;
     }
     __syncthreads();
   } else {
@@ -271,7 +310,7 @@ __global__ void k_glitter(GlitterParams p, float *__restrict__ surf, int *__rest
 extern "C" void sos_launch_glitter(GlitterParams p, float *surf, int *il_out, cudaStream_t st)
 {
   const int npair = p.nbmu * (p.nbmu + 1) / 2;
-  const size_t smem = (size_t)(PH_NU + 1 + p.os_nm + p.os_ns + p.os_nb + 2 + 12 * (p.os_ns + 1)) * sizeof(double);
+  const size_t smem = (size_t)(PH_NU + 1 + p.os_nm + p.os_ns + p.os_nb + 2 + 12 * (p.os_ns + 1) + (p.gmodel == 4 ? p.os_nb + 1 : 0)) * sizeof(double);
   k_glitter<<<npair, 256, smem, st>>>(p, surf, il_out);
 }
 

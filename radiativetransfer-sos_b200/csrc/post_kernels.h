@@ -21,8 +21,10 @@ struct TrphiParams {
 struct GlitterParams {       // SOS_GLITTER (SOS_GLITTER.F:229): one surface file
   int nbmu, os_nb, os_ns, os_nm;
   int gmodel;                // G function: 0 Cox-Munk (SOS_GSF), 1 Rondeaux, 2 Breon (SOS_GSF_RONDEAUX_BREON, azimuth independent),
-                             // 3 Maignan (SOS_GSF_MAIGNAN)
+                             // 3 Maignan (SOS_GSF_MAIGNAN), 4 Nadal (SOS_F21SF_NADAL)
   double coef_c;             // Maignan's coefficient C
+  double ind, alpha_nadal, beta_nadal;   // gmodel 4: Nadal's BPDF over F21 of Fresnel (SOS_F21SF_NADAL)
+  int nadal_pairing;         // 0: the series the reference's SOS_MAT_REFLEXION reads for each pair (glitter_kernel.cu); 1: the pair's own
   double sig, coef, pi;      // sigma^2 = .003 + .00512*W (REAL*4 literals), COEF = 1/sigma^2
   const double *rmu;         // [2N+1] device
   const double *alpha, *beta, *gamma, *zeta;   // [os_ns+1] Fresnel expansion (after the E15.8 channel), device

@@ -144,7 +144,8 @@ extern "C" int sosgpu_mat_fresnel(sosgpu_ctx *ctx, int nbmu, const double *rmu, 
 // SOS_GLITTER (SOS_GLITTER.F:229-371): surface-file records of a rough sea, one fused kernel (glitter_kernel.cu)
 // gmodel 0: Cox-Munk glitter (wind); 1 / 2: Rondeaux / Breon BPDF (SOS_SURFACE_BPDF.F:219-392 with ISURF = 4 / 5)
 static int reflection_matrices(sosgpu_ctx *ctx, int gmodel, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns,
-                               int os_nm, double wind, double ind_surf, float *surf, int *il_out, double coef_c = 0.0)
+                               int os_nm, double wind, double ind_surf, float *surf, int *il_out, double coef_c = 0.0,
+                               double alpha_nadal = 0.0, double beta_nadal = 0.0, int nadal_pairing = 0)
 {
   if (!ctx) return SOSGPU_ERR_NO_DEVICE;
   if (!rmu || !chr || !surf || nbmu < 1 || nbmu > SOSGPU_NBMU_MAX || os_nb > SOSGPU_NB_MAX || os_ns < 2 || os_ns > 136 ||
@@ -166,6 +167,7 @@ static int reflection_matrices(sosgpu_ctx *ctx, int gmodel, int nbmu, const doub
   if (rcf != SOSGPU_OK) return rcf;
   GlitterParams p{};
   p.nbmu = N; p.os_nb = os_nb; p.os_ns = os_ns; p.os_nm = os_nm; p.gmodel = gmodel; p.coef_c = coef_c;
+  p.ind = ind_surf; p.alpha_nadal = alpha_nadal; p.beta_nadal = beta_nadal; p.nadal_pairing = nadal_pairing;
   p.sig = (double)0.003f + (double)0.00512f * wind;            // SIG = .003 + .00512*WIND (SOS_GLITTER.F:300)
   p.coef = gmodel == 0 ? 1.0 / p.sig : 1.0;                    // (1./SIG) (:315); SOS_MAT_REFLEXION(1.D+00, ...) for the BPDF models
   p.pi = std::acos(-1.0);
@@ -192,10 +194,24 @@ extern "C" int sosgpu_surface_bpdf(sosgpu_ctx *ctx, int isurf, int nbmu, const d
                                    int os_nm, double ind_surf, double coef_c, float *surf)
 {
   if (ctx && isurf != 4 && isurf != 5 && isurf != 7) {
-    ctx->err = "sosgpu_surface_bpdf: the Rondeaux (4), Breon (5) and Maignan (7) models are provided, Nadal (6) is not";
+    ctx->err = "sosgpu_surface_bpdf: the Rondeaux (4), Breon (5) and Maignan (7) models; Nadal (6) has its own entry, sosgpu_surface_nadal";
     return SOSGPU_ERR_ARG;
   }
   return reflection_matrices(ctx, isurf == 4 ? 1 : (isurf == 5 ? 2 : 3), nbmu, rmu, chr, os_nb, os_ns, os_nm, 0.0, ind_surf, surf, nullptr, coef_c);
+}
+
+// SOS_SURFACE_BPDF with ISURF = 6 (SOS_SURFACE_BPDF.F:219-392): Nadal's BPDF, series generator SOS_F21SF_NADAL (:686-1069).
+// pairing 0: the surface file of the reference (its SOS_MAT_REFLEXION pairs the series by position in the file, see
+// glitter_kernel.cu); 1: every pair (I, J) gets its own series.  il_out (may be NULL): series length per pair [N(N+1)/2].
+extern "C" int sosgpu_surface_nadal(sosgpu_ctx *ctx, int nbmu, const double *rmu, const double *chr, int os_nb, int os_ns, int os_nm,
+                                    double ind_surf, double alpha, double beta, int pairing, float *surf, int *il_out)
+{
+  if (ctx && (!(alpha > 0.0) || !(beta > 0.0) || os_nb < 0 || (pairing != 0 && pairing != 1))) {
+    // alpha = 0 or beta = 0 make F = 0 and the reference's recombination test 0/0
+    ctx->err = "sosgpu_surface_nadal: alpha and beta must be positive, pairing 0 or 1";
+    return SOSGPU_ERR_ARG;
+  }
+  return reflection_matrices(ctx, 4, nbmu, rmu, chr, os_nb, os_ns, os_nm, 0.0, ind_surf, surf, il_out, 0.0, alpha, beta, pairing);
 }
 
 // SOS_ROUJEAN (SOS_ROUJEAN.F:212): Fourier series of Roujean's BRDF in the surface-file record layout

@@ -8,7 +8,8 @@
     solves        SOS, SOS_OS, SOS_AGGREGATE, SOS_TRPHI_OPTION   band.run_band                                                 device
     files         SOS_Up / SOS_Down / SOS_Result.bin / Trans / Flux, aerosol result file                                       host
 
-Supported keyword values: -SURF.Type 0 1 2 3 4 5 (6: the Nadal series generator is not built); -AER.Model 0 1 2 3 (4 5: not built);
+Supported keyword values: -SURF.Type 0 1 2 3 4 5 7 (6, Nadal: refused as SOS_PROC.F:2210-2226 refuses it; its surface file is
+Solver.surface_nadal); -AER.Model 0 1 2 3 (4 5: not built);
 -AP.AbsProfile.Type 7 (no gaseous absorption), or any type with the gas atmosphere and CKD tables handed in by the caller (`gas=`:
 the standard-atmosphere tables of the reference are data of the reference, not part of this package); user angle files
 (-ANG.Rad.UserAngFile, -ANG.Aer.UserAngFile) with their output files (-SOS.ResFileUp.UserAng, -SOS.ResFileDown.UserAng).  Unsupported values raise NotImplementedError naming the keyword; nothing is silently replaced.  No CPU fallback."""
@@ -127,18 +128,27 @@ def surface(solver, kw, nbmu, rmu, ga, os_nb, os_ns, os_nm):
         surf, _ = solver.glitter(nbmu, rmu, ga, kw["-SURF.Glitter.Wind"], kw["-SURF.Ind"], os_nb, os_ns, os_nm)
         o.update(imat_surf=1, igli=1, surf=surf, ind_surf=kw["-SURF.Ind"], wind=kw["-SURF.Glitter.Wind"])
         return o, direct
-    if t in (3, 4, 5):
+    if t == 6:
+        # SOS_PROC.F:2210-2226 prints this and stops before its parameter checks; the surface file of SOS_SURFACE_BPDF with ISURF = 6
+        # is available below the front end (Solver.surface_nadal, the direct term through set_direct_models(nadal=...))
+        raise ValueError("The Nadal's BPDF model is not supported ==> Select another surface model (-SURF.Type 6, as SOS_PROC)")
+    if t in (3, 4, 5, 7):
         k = (kw["-SURF.Roujean.K0"], kw["-SURF.Roujean.K1"], kw["-SURF.Roujean.K2"])
         surf = solver.roujean(nbmu, rmu, os_nb, *k)
         direct["roujean"] = k
-        if t in (4, 5):
-            bpdf = solver.surface_bpdf(t, nbmu, rmu, ga, kw["-SURF.Ind"], os_nb, os_ns, os_nm)
+        if t in (4, 5, 7):
+            if t == 7 and "-SURF.Maignan.C" not in kw:
+                raise ValueError("-SURF.Type 7 requires -SURF.Maignan.C (SOS_PROC.F:2238-2240)")
+            bpdf = solver.surface_bpdf(t, nbmu, rmu, ga, kw["-SURF.Ind"], os_nb, os_ns, os_nm, coef_c=kw.get("-SURF.Maignan.C", 0.0))
             surf = solver.bpdf_ajout_brdf(bpdf, surf)
-            direct["irondeaux" if t == 4 else "ibreon"] = 1
+            if t == 7:
+                direct["maignan"] = kw["-SURF.Maignan.C"]
+            else:
+                direct["irondeaux" if t == 4 else "ibreon"] = 1
             o["ind_surf"] = kw["-SURF.Ind"]
         o.update(imat_surf=1, surf=surf)
         return o, direct
-    raise NotImplementedError("-SURF.Type %r: the Nadal series generator (6) is not built" % (t,))
+    raise ValueError("-SURF.Type %r: 0 .. 7 (SOS_PROC.F:2177)" % (t,))
 
 
 def user_angle_file(src, dst, itrphi, nbmu, flags):

@@ -16,7 +16,7 @@ def pytest_configure(config):
 # GPU run order: the hot path first (kernels, solves, the configs of BASELINE.json against the reference library), then the chains
 # either side of it, then the keyword / sos_proc front ends.  With -x a failure at the edge does not hide the parity of the core.
 _GPU_ORDER = ("test_gpu_parity.py", "test_gpu_vs_reference.py", "test_profile_chain.py", "test_aerosol_chain.py", "test_writers.py",
-              "test_frontend.py")
+              "test_frontend.py", "test_surface_nadal.py")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -459,6 +459,15 @@ def test_host_flow_with_stub_solver(tmp_path):
     keep = np.flatnonzero(res2.ind_angout == 0)
     res1, _ = fe.run_keywords(s, base.replace(str(tmp_path / "a"), str(tmp_path / "c")).replace("-SOS.View 1 -SOS.View.Phi 0.", "-SOS.View 2 -SOS.View.Dphi 90").split())
     assert np.allclose(res1.up[0, 1, :5, :13], res2.up[0, 1, :5][:, keep], rtol=0, atol=1e-15)
+    # Maignan's BPDF + Roujean (-SURF.Type 7); Nadal (6) is refused, as SOS_PROC refuses it (SOS_PROC.F:2210-2226)
+    argv7 = (base.replace(str(tmp_path / "a"), str(tmp_path / "e"))
+             .replace("-SURF.Type 1", "-SURF.Type 7 -SURF.Roujean.K0 0.1 -SURF.Roujean.K1 0.05 -SURF.Roujean.K2 0.3 -SURF.Maignan.C 6.0"))
+    res7, _ = fe.run_keywords(s, argv7.split())
+    assert res7.up.shape == (1, 7, 2, 13) and ("direct", ["maignan", "roujean"]) in s.calls
+    with pytest.raises(ValueError, match="-SURF.Maignan.C"):
+        fe.run_keywords(s, argv7.replace(" -SURF.Maignan.C 6.0", "").split())
+    with pytest.raises(ValueError, match="Nadal"):
+        fe.run_keywords(s, argv7.replace("-SURF.Type 7", "-SURF.Type 6 -SURF.Nadal.Alpha 0.0159 -SURF.Nadal.Beta 44.8").split())
     # the f2py-shaped entry
     out = sos.sos_proc(solver=s, resroot=str(tmp_path / "d"), wa_simu=0.910, tetas=35.0, nbmu_gauss_lum=12, nbmu_gauss_mie=20, waref_aot=0.55,
                        aot_ref=0.3, itronc_aer=1, imod_aer=1, imodele_wmo=2, hr=8.0, ha=2.0, iprofil=1, psurf=1013.0, absprofil=7, isurf=1,
