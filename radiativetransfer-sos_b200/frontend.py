@@ -12,7 +12,8 @@ Supported keyword values: -SURF.Type 0 1 2 3 4 5 7 (6, Nadal: refused as SOS_PRO
 Solver.surface_nadal); -AER.Model 0 1 2 3 (4 5: not built);
 -AP.AbsProfile.Type 7 (no gaseous absorption), or any type with the gas atmosphere and CKD tables handed in by the caller (`gas=`:
 the standard-atmosphere tables of the reference are data of the reference, not part of this package); user angle files
-(-ANG.Rad.UserAngFile, -ANG.Aer.UserAngFile) with their output files (-SOS.ResFileUp.UserAng, -SOS.ResFileDown.UserAng).  Unsupported values raise NotImplementedError naming the keyword; nothing is silently replaced.  No CPU fallback."""
+(-ANG.Rad.UserAngFile, -ANG.Aer.UserAngFile) with their output files (-SOS.ResFileUp.UserAng, -SOS.ResFileDown.UserAng); a user
+aerosol file (-AER.UserFile) and a user surface matrix file (-SURF.File) in the layouts of the reference's own files.  Unsupported values raise NotImplementedError naming the keyword; nothing is silently replaced.  No CPU fallback."""
 import os
 
 import numpy as np
@@ -124,8 +125,13 @@ def surface(solver, kw, nbmu, rmu, ga, os_nb, os_ns, os_nm):
     if t == 2:
         o.update(ifresnel=1, ind_surf=kw["-SURF.Ind"])
         return o, direct
+    user = None
+    if "-SURF.File" in kw:
+        # a surface file of the user replaces the computation of SOS_SURFACE (SOS_PROC.F:3186-3189); the surface type still selects
+        # the direct terms of SOS_TRPHI (SOS_PREPA_OS.F:486-497)
+        user = read_surface_file(kw["-SURF.File"], nbmu, os_nb)
     if t == 1:
-        surf, _ = solver.glitter(nbmu, rmu, ga, kw["-SURF.Glitter.Wind"], kw["-SURF.Ind"], os_nb, os_ns, os_nm)
+        surf = user if user is not None else solver.glitter(nbmu, rmu, ga, kw["-SURF.Glitter.Wind"], kw["-SURF.Ind"], os_nb, os_ns, os_nm)[0]
         o.update(imat_surf=1, igli=1, surf=surf, ind_surf=kw["-SURF.Ind"], wind=kw["-SURF.Glitter.Wind"])
         return o, direct
     if t == 6:
@@ -134,13 +140,14 @@ def surface(solver, kw, nbmu, rmu, ga, os_nb, os_ns, os_nm):
         raise ValueError("The Nadal's BPDF model is not supported ==> Select another surface model (-SURF.Type 6, as SOS_PROC)")
     if t in (3, 4, 5, 7):
         k = (kw["-SURF.Roujean.K0"], kw["-SURF.Roujean.K1"], kw["-SURF.Roujean.K2"])
-        surf = solver.roujean(nbmu, rmu, os_nb, *k)
+        surf = user if user is not None else solver.roujean(nbmu, rmu, os_nb, *k)
         direct["roujean"] = k
         if t in (4, 5, 7):
             if t == 7 and "-SURF.Maignan.C" not in kw:
                 raise ValueError("-SURF.Type 7 requires -SURF.Maignan.C (SOS_PROC.F:2238-2240)")
-            bpdf = solver.surface_bpdf(t, nbmu, rmu, ga, kw["-SURF.Ind"], os_nb, os_ns, os_nm, coef_c=kw.get("-SURF.Maignan.C", 0.0))
-            surf = solver.bpdf_ajout_brdf(bpdf, surf)
+            if user is None:
+                bpdf = solver.surface_bpdf(t, nbmu, rmu, ga, kw["-SURF.Ind"], os_nb, os_ns, os_nm, coef_c=kw.get("-SURF.Maignan.C", 0.0))
+                surf = solver.bpdf_ajout_brdf(bpdf, surf)
             if t == 7:
                 direct["maignan"] = kw["-SURF.Maignan.C"]
             else:
@@ -149,6 +156,40 @@ def surface(solver, kw, nbmu, rmu, ga, os_nb, os_ns, os_nm):
         o.update(imat_surf=1, surf=surf)
         return o, direct
     raise ValueError("-SURF.Type %r: 0 .. 7 (SOS_PROC.F:2177)" % (t,))
+
+
+def read_surface_file(path, nbmu, os_nb):
+    """-SURF.File: a surface matrix file in the layout SOS_OS reads (SOS_OS.F:916-925: one unformatted record per Fourier order
+    0..OS_NB with nine N x N REAL*4 matrices).  The file must have been made for the angle set of the run."""
+    import struct
+    from .formats import _read_records
+    if not os.path.exists(path):
+        raise ValueError("-SURF.File %s does not exist (SOS_PREPA_OS error 1020)" % path)
+    recs = _read_records(path)
+    want = 9 * nbmu * nbmu * 4
+    if len(recs) < os_nb + 1 or any(len(r) != want for r in recs[:os_nb + 1]):
+        raise ValueError("-SURF.File %s: %d records of %s bytes, expected %d records of %d bytes (%d angles, OS_NB = %d)"
+                         % (path, len(recs), sorted({len(r) for r in recs}), os_nb + 1, want, nbmu, os_nb))
+    return np.array([np.frombuffer(r, dtype="<f4").reshape(9, nbmu, nbmu) for r in recs[:os_nb + 1]])
+
+
+def read_user_aerosols(path, wa, os_nb, aot):
+    """-AER.UserFile: an aerosol file in the layout of SOS_AEROSOLS' result file, read the way SOS_PREPA_OS.F:669-693 reads it
+    (truncation coefficient and truncated albedo after the ':' of lines 4 and 5, OS_NB + 1 list-directed rows of alpha, beta,
+    gamma, zeta from line 9).  The optical thickness is -AER.AOTref itself (SOS_PROC.F:1867-1876: the simulation wavelength must
+    be the reference one)."""
+    with open(path) as f:
+        lines = f.read().splitlines()
+    num = lambda t: float(t.replace("D", "E").replace("d", "e"))
+    try:
+        a, piztr = num(lines[3].split(":", 1)[1].split()[0]), num(lines[4].split(":", 1)[1].split()[0])
+        rows = np.array([[num(x) for x in ln.replace(",", " ").split()[:4]] for ln in lines[8:8 + os_nb + 1]])
+    except (IndexError, ValueError):
+        raise ValueError("-AER.UserFile %s: not in the layout of the aerosol result file (SOS_PREPA_OS error 923)" % path)
+    if rows.shape != (os_nb + 1, 4):
+        raise ValueError("-AER.UserFile %s: %d coefficient rows, expected OS_NB + 1 = %d" % (path, rows.shape[0], os_nb + 1))
+    piz = piztr / (1 + 0.5 * a * (piztr - 1))                     # SOS_PREPA_OS.F:700
+    return aerosols.AerosolOptics(wa, 0.0, 0.0, piz, piztr, a, 0.0, 1 if a != 0.0 else 0, rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], aot)
 
 
 def user_angle_file(src, dst, itrphi, nbmu, flags):
@@ -182,9 +223,6 @@ def run_keywords(solver, argv, wavelengths=None, gas=None):
 
 def run(solver, kw, wavelengths=None, gas=None):
     """run_keywords on an already parsed keyword dict (keywords.parse, or sos.sos_proc's arguments)."""
-    for k in ("-AER.UserFile", "-SURF.File"):
-        if k in kw:
-            raise NotImplementedError("%s: user aerosol / surface data files are not read by this front end" % k)
     wl = [float(w) for w in (wavelengths if wavelengths is not None else [kw["-SOS_Main.Wa"]])]
     nb_lum, nb_mie = kw.get("-ANG.Rad.NbGauss"), kw.get("-ANG.Aer.NbGauss")
     os_nb, os_ns, os_nm = expansion_orders(nb_mie, nb_lum)
@@ -204,7 +242,14 @@ def run(solver, kw, wavelengths=None, gas=None):
                                   "atmospheres of the reference are not part of this package" % absprofil)
     # ---- aerosols: all wavelengths in one device call ----
     aot_ref = kw.get("-AER.AOTref", 0.0)
-    if aot_ref > 0.0:
+    user_aer = aot_ref > 0.0 and "-AER.UserFile" in kw
+    if user_aer:                                                  # no aerosol processing (SOS_PROC.F:1867-1876, 2929-2933)
+        if wl != [float(kw["-AER.Waref"])]:
+            raise ValueError("-AER.UserFile: the simulation wavelength must be the reference wavelength -AER.Waref (SOS_PROC error 2350)")
+        if "-AER.ResFile" in kw:
+            raise ValueError("-AER.UserFile and -AER.ResFile exclude each other (SOS_PROC error 2351)")
+        aer = [read_user_aerosols(kw["-AER.UserFile"], wl[0], os_nb, aot_ref)]
+    elif aot_ref > 0.0:
         aer = aerosols.run(solver, mie_n, xmu, xhr, os_nb, aerosol_model(kw), wl, waref=kw["-AER.Waref"], aot_ref=aot_ref,
                            itronc=kw["-AER.Tronca"])
     else:                                                         # no aerosols: PIZ = 0, coefficients 0 (SOS_AEROSOLS.F:1136-1139)
@@ -216,7 +261,9 @@ def run(solver, kw, wavelengths=None, gas=None):
     itype = kw["-AP.AerProfile.Type"]
     waves = []
     for k, (w, a) in enumerate(zip(wl, aer)):
-        f = aerosols.through_result_file(a)
+        # a user file is read as it is (list-directed READ of SOS_PREPA_OS); computed coefficients go through the result file's formats
+        f = (dict(alpha=a.alpha, beta=a.beta, gamma=a.gamma, zeta=a.zeta, a_trunc=a.coef_tronca, piztr=a.piztr) if user_aer
+             else aerosols.through_result_file(a))
         o = synth.Optics(nbmu=nbmu, rmu=rmu.copy(), ga=ga, n0=n0, tetas=kw["-ANG.Thetas"], os_nb=os_nb, alpha=f["alpha"], beta=f["beta"],
                          gamma=f["gamma"], zeta=f["zeta"], a_trunc=f["a_trunc"], piztr=f["piztr"], igmax=kw["-SOS.IGmax"],
                          ipolar=kw["-SOS.Ipolar"], zout=kw["-SOS.OutputAlt"], **sf)
@@ -241,7 +288,7 @@ def run(solver, kw, wavelengths=None, gas=None):
             p = os.path.join(d, src)
             if dst and dst != src and os.path.exists(p):
                 os.replace(p, os.path.join(d, dst))
-    if aot_ref > 0.0:
+    if aot_ref > 0.0 and not user_aer:
         os.makedirs(os.path.join(root, "AER"), exist_ok=True)
         base = kw.get("-AER.ResFile", "Aerosols.txt")
         for w, a in zip(wl, aer):

@@ -468,6 +468,27 @@ def test_host_flow_with_stub_solver(tmp_path):
         fe.run_keywords(s, argv7.replace(" -SURF.Maignan.C 6.0", "").split())
     with pytest.raises(ValueError, match="Nadal"):
         fe.run_keywords(s, argv7.replace("-SURF.Type 7", "-SURF.Type 6 -SURF.Nadal.Alpha 0.0159 -SURF.Nadal.Beta 44.8").split())
+    # user files: the aerosol result file of the first run as -AER.UserFile (simulation at the reference wavelength), a surface matrix
+    # file as -SURF.File -- no aerosol / surface computation is asked from the device
+    fm = importlib.import_module("radiativetransfer-sos_b200.formats")
+    fsurf = str(tmp_path / "surf.bin")
+    fm.write_surface_bin(fsurf, np.full((41, 9, 13, 13), 0.25, np.float32))
+    faer = os.path.join(str(tmp_path / "a"), "AER", "Aerosols_Demo.txt_0.910000")
+    n_before = len(s.calls)
+    argv_u = (base.replace(str(tmp_path / "a"), str(tmp_path / "f")).replace("-AER.Waref 0.550", "-AER.Waref 0.910")
+              .replace(" -AER.ResFile Aerosols_Demo.txt", "") + " -AER.UserFile %s -SURF.File %s" % (faer, fsurf))
+    res_u, aer_u = fe.run_keywords(s, argv_u.split())
+    new_calls = [c[0] for c in s.calls[n_before:]]
+    assert "aerosols" not in new_calls and "glitter" not in new_calls and res_u.up.shape == (1, 7, 2, 13)
+    assert aer_u[0].ta == 0.3 and aer_u[0].coef_tronca == float("%.5f" % aopt[1].coef_tronca) and not os.path.exists(str(tmp_path / "f" / "AER"))
+    assert np.array_equal(aer_u[0].beta, np.array([float("%.7E" % x) for x in aopt[1].beta]))
+    with pytest.raises(ValueError, match="2350"):
+        fe.run_keywords(s, argv_u.replace("-AER.Waref 0.910", "-AER.Waref 0.550").split())
+    with pytest.raises(ValueError, match="2351"):
+        fe.run_keywords(s, (argv_u + " -AER.ResFile A.txt").split())
+    fm.write_surface_bin(fsurf, np.zeros((41, 9, 12, 12), np.float32))
+    with pytest.raises(ValueError, match="expected 41 records"):
+        fe.run_keywords(s, argv_u.split())
     # the f2py-shaped entry
     out = sos.sos_proc(solver=s, resroot=str(tmp_path / "d"), wa_simu=0.910, tetas=35.0, nbmu_gauss_lum=12, nbmu_gauss_mie=20, waref_aot=0.55,
                        aot_ref=0.3, itronc_aer=1, imod_aer=1, imodele_wmo=2, hr=8.0, ha=2.0, iprofil=1, psurf=1013.0, absprofil=7, isurf=1,
