@@ -152,7 +152,7 @@ def cpu_baseline_reference(wl, points_per_core=3):
                       "occupancy-based (cores x points / sum of busy seconds) %.3f points/s; reference Fortran translated "
                       "to C by oracle/f77_to_c.py, gcc -O2 (no Fortran compiler available)"
                       % (r["points"], r["terms"], r["wall"], r["workers"], wall_rate, occ_rate),
-            "term_solves_per_s": r["terms"] / r["wall"], "occupancy_value": occ_rate}
+            "term_solves_per_s": r["terms"] / r["wall"], "occupancy_value": occ_rate, "wall_s": r["wall"]}
 
 
 def run_reference(args, rank, world):
@@ -160,19 +160,27 @@ def run_reference(args, rank, world):
         return
     wl = make_workload(POINTS_PER_GPU)
     vals = []
-    for s in range(args.warmup + args.steps):
+    total = args.warmup + args.steps
+    ppc = 3                                          # spectral points per host core in one step's sample
+    for s in range(total):
+        t0 = time.perf_counter()
         try:
-            r = cpu_baseline_reference(wl)
+            r = cpu_baseline_reference(wl, points_per_core=ppc)
         except Exception as e:                       # no oracle/_ref on this box: time the (bit-identical) port instead
             print("reference library unavailable (%r): timing the oracle port" % (e,), file=sys.stderr)
             r = cpu_baseline(wl, budget_s=8.0)
+        if s == 0:                                   # keep the whole run within ~10 minutes on a slow box: smaller samples
+            dt = time.perf_counter() - t0
+            ppc = int(min(3, max(1, 3 * 600.0 / max(dt * total, 1e-9))))
         if s >= args.warmup:
             vals.append(r)
     v = float(np.mean([x["value"] for x in vals]))
+    walls = [x["wall_s"] for x in vals if "wall_s" in x]
     r = vals[-1]
     r["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": (1e3 * float(np.mean(walls)) if walls else None), "higher_is_better": True,
+            "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "O2 A-band-like CKD band (BASELINE configs[2]), bounded sample per step",
                        "nb_gauss": NB_GAUSS, "os_nb": OS_NB},
