@@ -11,10 +11,17 @@ for a LIST of wavelengths, with the work itself done on the device by Solver.aer
                                                             thickness at the reference wavelength (MODE_PARAM_BILND = 1 / 2)
     optical thickness at WA      SOS_PROC.F:2941-3063       TA = KMAT1(WA) / KMAT1(WAREF) * AOT_REF
 
-External phase functions (4) and user mixtures (5) are not built.  Keywords: frontend.aerosol_model maps -AER.* to these models.
+    external phase functions (4) SOS_AEROSOLS.F:2143-2279   -AER.ExtData: spline interpolation to the phase-function angles (host,
+                                                            <= 200 nodes), SOS_DECOMPO_LEGENDRE on the device
+    user mixture (IMOD = 5)      SOS_AEROSOLS.F:2283-2760   -AER.DefMixture: log-normal / Junge modes with their shares of the
+                                                            optical thickness at the reference wavelength (up to 4 modes)
+
+Keywords: frontend.aerosol_model maps -AER.* to these models.
 No CPU fallback: the numbers come from Solver.aerosols, which needs the GPU."""
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
+
+import math
 
 import numpy as np
 
@@ -209,6 +216,163 @@ class Plan:
     wavelengths: List[float] = field(default_factory=list)
 
 
+@dataclass
+class UserMixture:
+    """-AER.Model 5 (-AER.DefMixture, SOS_AEROSOLS.F:2283-2760): up to four log-normal / Junge modes, each with its refractive
+    index at the simulation wavelength and at the reference wavelength and its share of the optical thickness at the reference
+    wavelength.  modes: list of (igranu, v1, v2, v3, rn_wa, in_wa, rn_waref, in_waref, aot_rate); igranu 1: v1 modal radius,
+    v2 sigma; igranu 2: v1 minimal radius, v2 slope, v3 maximal radius (the arguments of SOS_GRANU)."""
+    modes: List[tuple]
+    waref: float
+
+
+GAP_TOLER_SUM_RATES = float(np.float32(0.000001))   # CTE_GAP_TOLER_SUM_RATES (SOS.h:184)
+MAX_MODES_DEVICE = 4                                # components per model of sosgpu_aer_model (the reference allows 20, SOS.h:178)
+
+
+def read_mixture_file(path, waref):
+    """The mixture definition file of -AER.DefMixture as SOS_AEROSOLS reads it (SOS_AEROSOLS.F:2297-2385): every value after the
+    ':' of its line -- number of modes; per mode: LND | JUNGE, (modal radius, standard deviation) or (slope, minimal radius,
+    maximal radius), real and imaginary index at the simulation wavelength, then at the reference wavelength, share of the optical
+    thickness at the reference wavelength.  The shares must sum to 1 within CTE_GAP_TOLER_SUM_RATES and are then normalised."""
+    with open(path) as f:
+        vals = [ln.split(":", 1)[1].split()[0] for ln in f.read().splitlines() if ":" in ln]
+    num = lambda t: float(t.replace("D", "E").replace("d", "e"))
+    it = iter(vals)
+    try:
+        n = int(num(next(it)))
+        modes = []
+        for _ in range(n):
+            kind = next(it).strip("'\"")
+            if kind == "LND":
+                v1, v2, v3, ig = num(next(it)), num(next(it)), 0.0, 1
+            elif kind == "JUNGE":
+                v2, v1, v3, ig = num(next(it)), num(next(it)), num(next(it)), 2
+            else:
+                raise ValueError("%s: size distribution %r is neither LND nor JUNGE (SOS_AEROSOLS error 962)" % (path, kind))
+            rn_wa, in_wa, rn_ref, in_ref, rate = (num(next(it)) for _ in range(5))
+            modes.append((ig, v1, v2, v3, rn_wa, in_wa, rn_ref, in_ref, rate))
+    except StopIteration:
+        raise ValueError("%s: the mixture file ends before its %d modes are described (SOS_AEROSOLS error 961)" % (path, n))
+    tot = 0.0
+    for m in modes:
+        tot = tot + m[8]
+    if abs(tot - 1.0) > GAP_TOLER_SUM_RATES:
+        raise ValueError("%s: the shares of the optical thickness sum to %r, not 1 (SOS_AEROSOLS error 963)" % (path, tot))
+    return UserMixture(modes, float(waref))
+
+
+def _mixture_component(mode, wa, waref):
+    """Component of one mode of a UserMixture at wavelength wa: indices of the reference wavelength when wa == waref, the table
+    sized for CTE_WAMIN (SOS_AEROSOLS.F:2626-2650); no rounding of the indices (unlike the other models)."""
+    ig, v1, v2, v3, rn_wa, in_wa, rn_ref, in_ref, _ = mode
+    rn, in_ = (rn_ref, in_ref) if wa == waref else (rn_wa, in_wa)
+    af = alphaf_of(lnd_rmax(v1, v2) if ig == 1 else v3, WAMIN)
+    if ALPHA0 > af or af >= 1e5:
+        raise ValueError("size-parameter range of the Mie table out of bounds (SOS_AEROSOLS error 1009)")
+    return (rn, in_, ALPHA0, af, ig, v1, v2, v3, wa)
+
+
+# ---- -AER.Model 4: phase functions from an external file (SOS_AEROSOLS.F:2143-2279) ----
+MAXNB_ANG_EXT = 200                                  # CTE_MAXNB_ANG_EXT (SOS.h:101)
+_BIG = float(np.float32(0.99e30))                    # .99E30 (REAL*4 literal) of SOS_SPLINE
+
+
+def spline(x, y, dy1, dyn):
+    """SOS_SPLINE (SOS_AEROSOLS.F:4952-5002): second derivatives of the cubic spline through (x, y), x ascending, with the first
+    derivatives dy1, dyn at the ends; the reference's statements in their order (host work on <= 200 nodes)."""
+    n = len(x)
+    d2, u = [0.0] * n, [0.0] * n
+    if dy1 > _BIG:
+        d2[0], u[0] = 0.0, 0.0
+    else:
+        d2[0] = -0.5
+        u[0] = (3. / (x[1] - x[0])) * ((y[1] - y[0]) / (x[1] - x[0]) - dy1)
+    for k in range(1, n - 1):
+        sig = (x[k] - x[k - 1]) / (x[k + 1] - x[k - 1])
+        p = sig * d2[k - 1] + 2.
+        d2[k] = (sig - 1.) / p
+        u[k] = (6. * ((y[k + 1] - y[k]) / (x[k + 1] - x[k]) - (y[k] - y[k - 1]) / (x[k] - x[k - 1])) / (x[k + 1] - x[k - 1]) - sig * u[k - 1]) / p
+    if dyn > _BIG:
+        qn, un = 0.0, 0.0
+    else:
+        qn = 0.5
+        un = (3. / (x[n - 1] - x[n - 2])) * (dyn - (y[n - 1] - y[n - 2]) / (x[n - 1] - x[n - 2]))
+    d2[n - 1] = (un - qn * u[n - 2]) / (qn * d2[n - 2] + 1.)
+    for k in range(n - 2, -1, -1):
+        d2[k] = d2[k] * d2[k + 1] + u[k]
+    return d2
+
+
+def splint(x, y, d2, xval):
+    """SOS_SPLINT (SOS_AEROSOLS.F:5042-5105): the spline at xval (bisection for the interval, then the cubic)."""
+    klo, khi = 1, len(x)
+    while khi - klo > 1:
+        k = (khi + klo) // 2
+        if x[k - 1] > xval:
+            khi = k
+        else:
+            klo = k
+    h = x[khi - 1] - x[klo - 1]
+    if h == 0.0:
+        raise ValueError("SPLINT interpolation: two nodes share an abscissa (bad X table input)")
+    a = (x[khi - 1] - xval) / h
+    b = (xval - x[klo - 1]) / h
+    return a * y[klo - 1] + b * y[khi - 1] + ((a * (a * a) - a) * d2[klo - 1] + (b * (b * b) - b) * d2[khi - 1]) * (h * h) / 6.
+
+
+def interpo_splint(xin, yin, xout):
+    """SOS_INTERPO_SPLINT (SOS_AEROSOLS.F:4822-4925): nodes sorted by ascending abscissa, end slopes from the end intervals."""
+    order = sorted(range(len(xin)), key=lambda i: xin[i])
+    x, y = [float(xin[i]) for i in order], [float(yin[i]) for i in order]
+    if any(b == a for a, b in zip(x, x[1:])):                     # the reference divides by zero, then SOS_SPLINT returns IER = -1
+        raise ValueError("spline interpolation: two nodes share an abscissa (SOS_SPLINT: bad X table input)")
+    dy1 = (y[1] - y[0]) / (x[1] - x[0])
+    dyn = (y[-1] - y[-2]) / (x[-1] - x[-2])
+    d2 = spline(x, y, dy1, dyn)
+    return np.array([splint(x, y, d2, float(v)) for v in xout])
+
+
+def read_external_data(path):
+    """The file of -AER.ExtData as SOS_AEROSOLS reads it (:2148-2172): extinction and scattering cross sections and the number of
+    angles after the ':' of the first three lines, one header line, then rows ANGLE, F11, -F12/F11, F22/F11, F33/F11.
+    Returns (kmat1, kmat2, mu[n], f11[n], f12[n], f22[n], f33[n])."""
+    num = lambda t: float(t.replace("D", "E").replace("d", "e"))
+    with open(path) as f:
+        lines = f.read().splitlines()
+    try:
+        kmat1, kmat2 = (num(lines[i].split(":", 1)[1].split()[0]) for i in (0, 1))
+        n = int(num(lines[2].split(":", 1)[1].split()[0]))
+        if n > MAXNB_ANG_EXT:
+            raise ValueError("%s: %d angles, more than CTE_MAXNB_ANG_EXT = %d (SOS_AEROSOLS error 950)" % (path, n, MAXNB_ANG_EXT))
+        rows = np.array([[num(v) for v in ln.replace(",", " ").split()[:5]] for ln in lines[4:4 + n]])
+    except (IndexError, ValueError) as e:
+        if "CTE_MAXNB_ANG_EXT" in str(e):
+            raise
+        raise ValueError("%s: not in the layout of the external phase-function file (SOS_AEROSOLS error 941)" % path)
+    if rows.shape != (n, 5):
+        raise ValueError("%s: the file ends before its %d angles (SOS_AEROSOLS error 942)" % (path, n))
+    ang, f11 = rows[:, 0], rows[:, 1]
+    mu = np.array([math.cos(a * _PI / 180.0) for a in ang])          # libm's cos, as the reference's DCOS
+    return kmat1, kmat2, mu, f11, -rows[:, 2] * f11, rows[:, 3] * f11, rows[:, 4] * f11
+
+
+def external_data(solver, path, nbmu, xmu, xhr, os_nb, itronc, wa, aot):
+    """-AER.Model 4: external phase functions -> spline interpolation to the phase-function angles (host, <= 200 nodes) ->
+    SOS_DECOMPO_LEGENDRE on the device -> AerosolOptics (the common tail of SOS_AEROSOLS, :2775-2781).  The optical thickness is
+    aot itself: SOS_PROC requires the simulation wavelength to be the reference one (error 2331)."""
+    kmat1, kmat2, mu, f11, f12, f22, f33 = read_external_data(path)
+    p11, p12, p22, p33 = (interpo_splint(mu, f, xmu) for f in (f11, f12, f22, f33))
+    d = solver.decompo_legendre(itronc, nbmu, xmu, xhr, os_nb, p11, p12, p22, p33)
+    if d["ier"] != 0:
+        raise RuntimeError("SOS_DECOMPO_LEGENDRE failed on the external phase functions (IER = %d)" % d["ier"])
+    ct = d["coef_tronca"]
+    piz = kmat2 / kmat1
+    piztr = piz * (1. - ct / 2.) / (1. - piz * ct / 2.)
+    asym = ct / 2. + (1. - ct / 2.) * d["beta11"][1] / 3.
+    return AerosolOptics(float(wa), kmat1, kmat2, piz, piztr, ct, asym, int(d["itronc"]), d["alp"], d["beta11"], d["gamma12"], d["zeta"], float(aot))
+
+
 def _at(x, wa):
     return float(x(wa)) if callable(x) else float(x)
 
@@ -281,6 +445,15 @@ def plan(model, wavelengths, itronc=1, bilnd_weights=None):
                     raise ValueError("BimodalLnd with rtauct: pass bilnd_weights=reference_weights(...)")
                 w = list(bilnd_weights)
             p.models.append((2, [n0, n0 + 1], w, itronc))
+        elif isinstance(model, UserMixture):
+            if len(model.modes) > MAX_MODES_DEVICE:
+                raise NotImplementedError("a mixture of %d modes: the device mixes at most %d (the reference 20)"
+                                          % (len(model.modes), MAX_MODES_DEVICE))
+            if bilnd_weights is None:
+                raise ValueError("UserMixture: pass bilnd_weights=reference_weights(...)")
+            for m in model.modes:
+                p.components.append(_mixture_component(m, wa, model.waref))
+            p.models.append((len(model.modes), list(range(n0, n0 + len(model.modes))), list(bilnd_weights), itronc))
         else:
             raise TypeError("unsupported aerosol model %r" % (model,))
     return p
@@ -293,6 +466,24 @@ def in_pos(model, wa):
 def reference_weights(solver, nbmu, xmu, xhr, model, waref, aot_ref):
     """MODE_PARAM_BILND = 2 (SOS_AEROSOLS.F:1806-2058): the extinction cross sections of the two modes at the reference
     wavelength give CVI(coarse) = rtauct * AOT_REF / KMAT1c, CVI(fine) = (1 - rtauct) * AOT_REF / KMAT1f, then normalised."""
+    if isinstance(model, UserMixture):
+        # SOS_AEROSOLS.F:2383, 2452-2465, 2486-2594: AOT of each mode = AOT_REF * share (shares normalised when their sum is not
+        # exactly 1), COEF_ALPHA = AOT / KMAT1 of the mode at the reference wavelength, then normalised
+        comps = [_mixture_component(m, waref, waref) for m in model.modes]
+        o = solver.aerosols(nbmu, xmu, xhr, comps, [], 2, want_phase=False)
+        if o["comp_ier"].any():
+            raise RuntimeError("SOS_GRANU failed at the reference wavelength")
+        aot = [aot_ref * m[8] for m in model.modes]
+        tot = 0.0
+        for m in model.modes:
+            tot = tot + m[8]
+        if tot != 1.0:
+            aot = [a / tot for a in aot]
+        ca = [a / o["comp_k"][i, 0] for i, a in enumerate(aot)]
+        som = 0.0
+        for c in ca:
+            som = som + c
+        return [c / som for c in ca]
     comps = [_lnd_component(_at(model.coarse_rn, waref), _at(model.coarse_in, waref), model.coarse_rmodal, model.coarse_sigma, waref, waref),
              _lnd_component(_at(model.fine_rn, waref), _at(model.fine_in, waref), model.fine_rmodal, model.fine_sigma, waref, waref)]
     o = solver.aerosols(nbmu, xmu, xhr, comps, [], 2, want_phase=False)
@@ -309,9 +500,9 @@ def run(solver, nbmu, xmu, xhr, os_nb, model, wavelengths, waref=None, aot_ref=N
     wl = [float(w) for w in wavelengths]
     with_ref = waref is not None and aot_ref is not None and aot_ref != 0.0
     weights = None
-    if isinstance(model, BimodalLnd) and model.rtauct is not None:
+    if (isinstance(model, BimodalLnd) and model.rtauct is not None) or isinstance(model, UserMixture):
         if not with_ref:
-            raise ValueError("BimodalLnd with rtauct needs waref and aot_ref")
+            raise ValueError("a mixture defined by shares of the optical thickness needs waref and aot_ref")
         weights = reference_weights(solver, nbmu, xmu, xhr, model, float(waref), float(aot_ref))
     allw = wl + ([float(waref)] if with_ref and float(waref) not in wl else [])
     p = plan(model, allw, itronc, weights)

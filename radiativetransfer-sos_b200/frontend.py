@@ -9,7 +9,7 @@
     files         SOS_Up / SOS_Down / SOS_Result.bin / Trans / Flux, aerosol result file                                       host
 
 Supported keyword values: -SURF.Type 0 1 2 3 4 5 7 (6, Nadal: refused as SOS_PROC.F:2210-2226 refuses it; its surface file is
-Solver.surface_nadal); -AER.Model 0 1 2 3 (4 5: not built);
+Solver.surface_nadal); -AER.Model 0 1 2 3 4 5 (5: up to four modes);
 -AP.AbsProfile.Type 7 (no gaseous absorption), or any type with the gas atmosphere and CKD tables handed in by the caller (`gas=`:
 the standard-atmosphere tables of the reference are data of the reference, not part of this package); user angle files
 (-ANG.Rad.UserAngFile, -ANG.Aer.UserAngFile) with their output files (-SOS.ResFileUp.UserAng, -SOS.ResFileDown.UserAng); a user
@@ -112,7 +112,12 @@ def aerosol_model(kw):
         else:
             raise ValueError("-AER.BMD.VCdef must be 1 or 2")
         return b
-    raise NotImplementedError("-AER.Model %r: 0 (mono-modal), 1 (WMO), 2 (Shettle & Fenn) and 3 (bimodal log-normal) are built" % (m,))
+    if m == 5:
+        if "-AER.DefMixture" not in kw:
+            raise ValueError("-AER.Model 5 requires -AER.DefMixture (SOS_PROC error 2340)")
+        return aerosols.read_mixture_file(kw["-AER.DefMixture"], kw["-AER.Waref"])
+    raise ValueError("-AER.Model %r: 0 (mono-modal), 1 (WMO), 2 (Shettle & Fenn), 3 (bimodal log-normal), 4 (external phase functions, "
+                     "handled by run), 5 (user mixture)" % (m,))
 
 
 def surface(solver, kw, nbmu, rmu, ga, os_nb, os_ns, os_nm):
@@ -249,6 +254,12 @@ def run(solver, kw, wavelengths=None, gas=None):
         if "-AER.ResFile" in kw:
             raise ValueError("-AER.UserFile and -AER.ResFile exclude each other (SOS_PROC error 2351)")
         aer = [read_user_aerosols(kw["-AER.UserFile"], wl[0], os_nb, aot_ref)]
+    elif aot_ref > 0.0 and kw.get("-AER.Model") == 4:             # external phase functions (SOS_PROC.F:1837-1847)
+        if "-AER.ExtData" not in kw:
+            raise ValueError("-AER.Model 4 requires -AER.ExtData (SOS_PROC error 2330)")
+        if wl != [float(kw["-AER.Waref"])]:
+            raise ValueError("-AER.Model 4: the simulation wavelength must be the reference wavelength -AER.Waref (SOS_PROC error 2331)")
+        aer = [aerosols.external_data(solver, kw["-AER.ExtData"], mie_n, xmu, xhr, os_nb, kw["-AER.Tronca"], wl[0], aot_ref)]
     elif aot_ref > 0.0:
         aer = aerosols.run(solver, mie_n, xmu, xhr, os_nb, aerosol_model(kw), wl, waref=kw["-AER.Waref"], aot_ref=aot_ref,
                            itronc=kw["-AER.Tronca"])

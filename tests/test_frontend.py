@@ -86,8 +86,8 @@ def test_frontend_host_logic():
     d.update({"-AER.Model": 2, "-AER.SF.Model": 3, "-AER.SF.RH": 70.0})
     sf = fe.aerosol_model(d)
     assert isinstance(sf, aer.ShettleFenn) and sf.imodele == 3 and sf.rh == 70.0 and sf.dirfic == "/somewhere/fic"
-    d["-AER.Model"] = 4
-    with pytest.raises(NotImplementedError):
+    d["-AER.Model"] = 6
+    with pytest.raises(ValueError):
         fe.aerosol_model(d)
     with pytest.raises(NotImplementedError):                         # gas absorption without the caller's tables
         fe.run_keywords(None, DEMO.format(root="/tmp/x", nrad=12, naer=20, abs=1).split())
@@ -370,6 +370,12 @@ class _StubSolver:
             coef[m, 1] = 0.8 ** np.arange(os_nb + 1) * (2 * np.arange(os_nb + 1) + 1)
         return dict(comp_k=ck, comp_phase=None, comp_ier=np.zeros(nc, np.int32), scal=scal, coef=coef, phase=None, model_ier=np.zeros(nm, np.int32))
 
+    def decompo_legendre(self, itronc, nbmu, xmu, xhr, os_nb, p11, p12, p22, p33):
+        self.calls.append(("decompo", nbmu, os_nb, len(p11)))
+        z, k = np.zeros(os_nb + 1), np.arange(os_nb + 1)
+        b = 0.8 ** k * (2 * k + 1)
+        return dict(alp=z, beta11=b, beta22=b, gamma12=z, delta33=z, zeta=z, p11=p11, ttt=p11, coef_tronca=0.3, z1=1.0, itronc=itronc, ier=0)
+
     def glitter(self, nbmu, rmu, ga, wind, ind, os_nb, os_ns, os_nm):
         self.calls.append(("glitter", nbmu, os_nb, os_ns, os_nm))
         return np.zeros((os_nb + 1, 9, nbmu, nbmu), np.float32), np.zeros(nbmu * (nbmu + 1) // 2, np.int32)
@@ -489,6 +495,25 @@ def test_host_flow_with_stub_solver(tmp_path):
     fm.write_surface_bin(fsurf, np.zeros((41, 9, 12, 12), np.float32))
     with pytest.raises(ValueError, match="expected 41 records"):
         fe.run_keywords(s, argv_u.split())
+    # -AER.Model 4 (external phase functions, at the reference wavelength only) and 5 (user mixture)
+    import test_aerosol_models as tam
+    fext, fmix = str(tmp_path / "ext.txt"), tmp_path / "mix.txt"
+    tam._write_ext(fext)
+    fmix.write_text(tam.MIX)
+    argv4 = (base.replace(str(tmp_path / "a"), str(tmp_path / "g")).replace("-AER.Waref 0.550", "-AER.Waref 0.910")
+             .replace("-AER.Model 1 -AER.WMO.Model 2", "-AER.Model 4 -AER.ExtData " + fext))
+    res4, aer4 = fe.run_keywords(s, argv4.split())
+    assert ("decompo", 20, 40, 41) in s.calls and aer4[0].ta == 0.3 and aer4[0].kmat1 == 2.5 and aer4[0].coef_tronca == 0.3
+    assert os.path.exists(str(tmp_path / "g" / "AER" / "Aerosols_Demo.txt")) and res4.up.shape == (1, 7, 2, 13)
+    with pytest.raises(ValueError, match="2331"):
+        fe.run_keywords(s, argv4.replace("-AER.Waref 0.910", "-AER.Waref 0.550").split())
+    with pytest.raises(ValueError, match="2330"):
+        fe.run_keywords(s, argv4.replace(" -AER.ExtData " + fext, "").split())
+    argv5 = (base.replace(str(tmp_path / "a"), str(tmp_path / "h")).replace("-AER.Model 1 -AER.WMO.Model 2", "-AER.Model 5 -AER.DefMixture %s" % fmix))
+    res5, aer5 = fe.run_keywords(s, argv5.split())
+    assert ("aerosols", 4, 2) in s.calls and 0.0 < aer5[0].ta and res5.up.shape == (1, 7, 2, 13)
+    with pytest.raises(ValueError, match="2340"):
+        fe.run_keywords(s, argv5.replace(" -AER.DefMixture %s" % fmix, "").split())
     # the f2py-shaped entry
     out = sos.sos_proc(solver=s, resroot=str(tmp_path / "d"), wa_simu=0.910, tetas=35.0, nbmu_gauss_lum=12, nbmu_gauss_mie=20, waref_aot=0.55,
                        aot_ref=0.3, itronc_aer=1, imod_aer=1, imodele_wmo=2, hr=8.0, ha=2.0, iprofil=1, psurf=1013.0, absprofil=7, isurf=1,
