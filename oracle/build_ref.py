@@ -22,7 +22,9 @@ FILES = ["SOS_OS.F", "SOS.F", "SOS_AGGREGATE.F", "SOS_TRPHI.F", "SOS_GLITTER.F",
          # translate -- DATA tables, list-directed string I/O -- and are not on the path)
          "SOS_SUB_TRS.F", "SOS_AEROSOLS.F",
          # N3: Mie theory (SOS_MIE, SOS_FPHASE_MIE); SOS_GRANU and SOS_DECOMPO_LEGENDRE come from SOS_AEROSOLS.F above
-         "SOS_MIE.F"]
+         "SOS_MIE.F",
+         # N1 rest: the gas atmosphere of a run (standard atmospheres are DATA tables of SOS_SUB_TRS.F)
+         "SOS_PREPA_ABSPROFILE.F"]
 
 
 def build(force=False, verbose=True):

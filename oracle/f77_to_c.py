@@ -17,6 +17,8 @@ What is implemented is what those routines use, with Fortran's own semantics whe
     precision, mixed operands are promoted operand by operand, integer division truncates, x**n with an integer n is
     libgcc's __powidf2 / __powisf2 multiplication chain, x**y otherwise pow / powf; generic and specific intrinsics (DINT
     truncates, DNINT rounds halves away from zero); dotted operators in either case;
+  * DATA statements for whole one-dimensional arrays, implied DO lists from 1 and scalars (repeat counts n*c), rewritten as
+    assignments executed at every call (tables of constants that the routine never modifies);
   * DO loops with the iteration count fixed at entry (labelled, shared terminal labels, ENDDO), DO WHILE, block and
     logical IF, GOTO, CONTINUE, CALL (temporaries for expression arguments), RETURN;
   * I/O as gfortran does it: unformatted sequential records with 4-byte markers (implied DO lists, whole arrays, ERR=,
@@ -483,6 +485,42 @@ class Unit:
             self.vars[name] = {"type": t, "dims": dims, "clen": clen}
 
 
+def expand_data(exe):
+    """DATA statements of the two forms the reference uses -- `DATA A/ c1, c2, ... /` (a scalar, or a whole one-dimensional array
+    with lower bound 1) and `DATA (A(I), I = 1, N)/ c1, ... /` -- rewritten as assignments A(k) = c_k at the place of the statement
+    (repeat counts n*c expanded).  The assignments are executed at every call instead of once at load time, which is the same thing
+    for variables the routine never modifies afterwards (the case of every DATA statement of the reference: tables of constants);
+    the constants keep their own type (a REAL*4 constant stored in a DOUBLE PRECISION element is converted, as DATA does)."""
+    out = []
+    for lab, txt, no in exe:
+        m = re.match(r"^DATA\s+(.*)$", txt, re.I | re.S)
+        if not m or re.match(r"^DATA\w*\s*(\(.*\))?\s*=", txt, re.I):
+            out.append((lab, txt, no))
+            continue
+        body = m.group(1).strip()
+        m1 = re.match(r"^\(\s*(\w+)\s*\(\s*(\w+)\s*\)\s*,\s*(\w+)\s*=\s*1\s*,\s*[^)]*\)\s*/(.*)/\s*$", body, re.S)
+        m2 = re.match(r"^(\w+)\s*/(.*)/\s*$", body, re.S)
+        if m1 and m1.group(2).upper() == m1.group(3).upper():
+            var, vals = m1.group(1), m1.group(4)
+        elif m2:
+            var, vals = m2.group(1), m2.group(2)
+        else:
+            raise Unsupported("DATA form: %s" % txt[:60])
+        consts = []
+        for c in split_top(vals):
+            c = c.strip()
+            r = re.match(r"^(\d+)\s*\*\s*(.*)$", c)
+            consts += [r.group(2)] * int(r.group(1)) if r else [c]
+        if lab:
+            out.append((lab, "CONTINUE", no))
+        if len(consts) == 1 and m2 and not m1:
+            out.append(("", "%s = %s" % (var, consts[0]), no))               # a scalar (a one-element array is not used by the reference)
+        else:
+            for k, c in enumerate(consts):
+                out.append(("", "%s(%d) = %s" % (var, k + 1, c), no))
+    return out
+
+
 def translate_unit(name, args, stmts, defines, known_subs):
     u = Unit(name, args, defines)
     out = []
@@ -520,6 +558,7 @@ def translate_unit(name, args, stmts, defines, known_subs):
             pending_dims.append(m2.group(1))
             continue
         exe.append((lab, txt, no))
+    exe = expand_data(exe)
     for lab, txt, no in exe:
         m = re.match(r"^FORMAT\s*(\(.*\))\s*$", txt, re.I | re.S)
         if m and lab:

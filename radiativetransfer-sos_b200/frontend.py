@@ -10,15 +10,16 @@
 
 Supported keyword values: -SURF.Type 0 1 2 3 4 5 7 (6, Nadal: refused as SOS_PROC.F:2210-2226 refuses it; its surface file is
 Solver.surface_nadal); -AER.Model 0 1 2 3 4 5 (5: up to four modes);
--AP.AbsProfile.Type 7 (no gaseous absorption), or any type with the gas atmosphere and CKD tables handed in by the caller (`gas=`:
-the standard-atmosphere tables of the reference are data of the reference, not part of this package); user angle files
+-AP.AbsProfile.Type 7 (no gaseous absorption), 0 (user profile file) and 1 .. 6 (predefined atmospheres: absprofile.py reads their
+tables from the user's installation of the reference, $SOS_ABS_ROOT/src/SOS_SUB_TRS.F, and the CKD coefficients from
+$SOS_ABS_ROOT/fic/COEFF_CKD), or the gas atmosphere and CKD tables handed in by the caller (`gas=`); user angle files
 (-ANG.Rad.UserAngFile, -ANG.Aer.UserAngFile) with their output files (-SOS.ResFileUp.UserAng, -SOS.ResFileDown.UserAng); a user
 aerosol file (-AER.UserFile) and a user surface matrix file (-SURF.File) in the layouts of the reference's own files.  Unsupported values raise NotImplementedError naming the keyword; nothing is silently replaced.  No CPU fallback."""
 import os
 
 import numpy as np
 
-from . import aerosols, api, band, keywords, synth
+from . import absprofile, aerosols, api, band, keywords, synth
 from .formats import round_e
 
 DEFAULT_NBMU_LUM, DEFAULT_NBMU_MIE = 24, 40                      # inc/SOS.h:508-514
@@ -242,9 +243,17 @@ def run(solver, kw, wavelengths=None, gas=None):
             raise ValueError("%s requires -ANG.Rad.UserAngFile" % k)             # SOS_ABS_MAIN.F:100-103
     mie_n, xmu, xhr = mie_angles(nb_mie or DEFAULT_NBMU_MIE, user_mie)
     absprofil = kw["-AP.AbsProfile.Type"]
+    if absprofil != 7 and kw["-AP.AerProfile.Type"] == 2:
+        raise ValueError("an aerosol layer profile (-AP.AerProfile.Type 2) goes with -AP.AbsProfile.Type 7 only (SOS_PROC error 2513)")
     if absprofil != 7 and gas is None:
-        raise NotImplementedError("-AP.AbsProfile.Type %d needs the gas atmosphere and the CKD tables (gas=...): the standard "
-                                  "atmospheres of the reference are not part of this package" % absprofil)
+        # SOS_PREPA_ABSPROFILE: the user's profile file (type 0) or a predefined atmosphere (1 .. 6, tables read from the user's
+        # installation of the reference), the CKD coefficient files of $SOS_ABS_ROOT/fic/COEFF_CKD
+        if "-AP.SpectralResol" not in kw:
+            raise ValueError("-AP.AbsProfile.Type %d requires -AP.SpectralResol" % absprofil)
+        nd = absprofile.NOT_DEFINED
+        gas = absprofile.prepare(getattr(solver, "lib", None) or api.load_library(), wl, kw["-AP.SpectralResol"], absprofil,
+                                 kw.get("-AP.AbsProfile.UserFile"), kw.get("-AP.Psurf", nd), kw.get("-AP.H2O", nd), kw.get("-AP.O3", nd),
+                                 kw.get("-AP.CO2", nd), kw.get("-AP.CH4", nd))
     # ---- aerosols: all wavelengths in one device call ----
     aot_ref = kw.get("-AER.AOTref", 0.0)
     user_aer = aot_ref > 0.0 and "-AER.UserFile" in kw

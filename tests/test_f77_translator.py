@@ -230,3 +230,39 @@ def test_round_3_additions(f77, tmp_path):
     assert kout[0] == 7 and kout[1] == len(str(data)) and kout[2] == 1
     assert out[4] == 3.75 and out[5] == 3.75                                                  # unit 11 line 1, unit 12 line 1
     assert out[6] == 12.0 and ch.raw == b"001449"                                             # unit 12 line 2; INT truncates 1449.6
+
+
+def test_data_statements(f77, tmp_path):
+    """DATA in the forms the reference uses (whole array, implied DO from 1, repeat counts, a scalar): REAL*4 constants stored in
+    DOUBLE PRECISION elements keep their single-precision value, as DATA converts them."""
+    lib = compile_fortran(f77, tmp_path, "datast", """
+      SUBROUTINE DATAST(OUT,KOUT)
+      PARAMETER(N=4)
+      DOUBLE PRECISION OUT(12), A(N), B(3), S
+      REAL R(2)
+      INTEGER*4 KOUT(3), K(3)
+      DATA A/
+     C 1.013E+03, 0.1,
+     C 2*2.5D0/
+      DATA (B(I),I=1,3)/3.410E+22,18.,1.0E-06/
+      DATA S/0.3/
+      DATA R/0.7,1.5/
+      DATA K/3*7/
+      DO I=1,N
+         OUT(I)=A(I)
+      ENDDO
+      DO I=1,3
+         OUT(4+I)=B(I)
+         KOUT(I)=K(I)
+      ENDDO
+      OUT(8)=S
+      OUT(9)=R(1)
+      OUT(10)=R(2)
+      RETURN
+      END
+""")
+    out, kout = np.zeros(12), np.zeros(3, dtype=np.int32)
+    lib.datast_(out.ctypes.data_as(C.POINTER(C.c_double)), kout.ctypes.data_as(C.POINTER(C.c_int)))
+    f = lambda x: float(np.float32(x))
+    assert list(out[:10]) == [f(1.013e3), f(0.1), 2.5, 2.5, f(3.410e22), 18.0, f(1.0e-6), f(0.3), f(0.7), 1.5]
+    assert list(kout) == [7, 7, 7]

@@ -89,7 +89,8 @@ def test_frontend_host_logic():
     d["-AER.Model"] = 6
     with pytest.raises(ValueError):
         fe.aerosol_model(d)
-    with pytest.raises(NotImplementedError):                         # gas absorption without the caller's tables
+    os.environ["SOS_ABS_ROOT"] = "/nonexistent"                      # a predefined atmosphere without the reference's installation
+    with pytest.raises(ValueError, match="SOS_SUB_TRS.F"):
         fe.run_keywords(None, DEMO.format(root="/tmp/x", nrad=12, naer=20, abs=1).split())
 
 
@@ -399,6 +400,10 @@ class _StubSolver:
         h = np.tile(np.linspace(0.0, 0.3, 601), (n, 1))
         return nt, z, h, np.full((n, 601), 0.5), np.full((n, 601), 0.5), np.zeros(n, np.int32)
 
+    def profile_chain(self, tables, userprofil, altabs, ro, terms, text_hop=True, want_tauabs=False):
+        self.calls.append(("profile_chain", len(terms), int(tables["nb_pres"]), float(np.asarray(ro)[6, :49].sum())))
+        return self.profile(altabs, None, terms) + (np.zeros((len(terms), 50)),)
+
     def upload(self, wl, groups=None, ngroup=None):
         outer = self
 
@@ -514,6 +519,23 @@ def test_host_flow_with_stub_solver(tmp_path):
     assert ("aerosols", 4, 2) in s.calls and 0.0 < aer5[0].ta and res5.up.shape == (1, 7, 2, 13)
     with pytest.raises(ValueError, match="2340"):
         fe.run_keywords(s, argv5.replace(" -AER.DefMixture %s" % fmix, "").split())
+    # gaseous absorption from the keywords: a user profile file, CKD coefficient files under $SOS_ABS_ROOT
+    import profile_cases as pc
+    import test_absprofile as tab
+    band = importlib.import_module("radiativetransfer-sos_b200.band")
+    t = pc.ckd_tables(4)
+    pc.write_ckd_files(os.environ["SOS_ABS_ROOT"], t)
+    fprof = str(tmp_path / "gas_profile.txt")
+    tab._write_profile(fprof, tab._user())
+    wa = 1e4 / 13255.0
+    argv_g = (base.replace(str(tmp_path / "a"), str(tmp_path / "i")).replace("-SOS_Main.Wa 0.910", "-SOS_Main.Wa %.12f" % wa)
+              .replace("-AP.AbsProfile.Type 7", "-AP.AbsProfile.Type 0 -AP.AbsProfile.UserFile %s -AP.H2O 2.0" % fprof))
+    res_g, _ = fe.run_keywords(s, argv_g.split())
+    nterm = len(band.enumerate_ckd_terms(t["nexp"], t["ai"], 25)[0])
+    pcall = [c for c in s.calls if c[0] == "profile_chain"][-1]
+    assert res_g.nterm == [nterm] and pcall[1] == nterm and pcall[2] == pc.NPMAX and 4.0e24 < pcall[3] < 5.0e24     # O2 column, molecules / cm2
+    with pytest.raises(ValueError, match="2513"):
+        fe.run_keywords(s, argv_g.replace("-AP.AerProfile.Type 1", "-AP.AerProfile.Type 2 -AP.AerLayer.Zmin 1. -AP.AerLayer.Zmax 3.").split())
     # the f2py-shaped entry
     out = sos.sos_proc(solver=s, resroot=str(tmp_path / "d"), wa_simu=0.910, tetas=35.0, nbmu_gauss_lum=12, nbmu_gauss_mie=20, waref_aot=0.55,
                        aot_ref=0.3, itronc_aer=1, imod_aer=1, imodele_wmo=2, hr=8.0, ha=2.0, iprofil=1, psurf=1013.0, absprofil=7, isurf=1,
