@@ -199,21 +199,21 @@ def read_ckd(lib, nu, nustep, sos_abs_root=None):
 
 def prepare(lib, wavelengths, nustep, absprofil, ficabsprofil=None, psurf=NOT_DEFINED, h2o=NOT_DEFINED, o3=NOT_DEFINED, co2=NOT_DEFINED,
             ch4=NOT_DEFINED, sos_abs_root=None):
-    """SOS_PREPA_ABSPROFILE for a list of wavelengths (microns) that share their CKD coefficient files (50 spectral intervals per
-    file): the `gas=` dict of frontend.run -- tables, kdis_ai, userprofil, altabs, ro, lamb1 = 1 + INT((NUMAX - NU) / NUSTEP) per
-    wavelength (:565)."""
+    """SOS_PREPA_ABSPROFILE for a list of wavelengths (microns): the `gas=` dict of frontend.run -- userprofil, altabs, ro of the
+    run, and per wavelength the CKD tables of its coefficient file (50 spectral intervals per file; wavelengths of the same file
+    share one set, read once), kdis_ai and lamb1 = 1 + INT((NUMAX - NU) / NUSTEP) (:565)."""
     user, altabs, ro = atmosphere(absprofil, ficabsprofil, psurf, h2o, o3, co2, ch4, sos_abs_root)
-    tables, rng, lamb1 = None, None, []
+    files, tables, lamb1 = [], [], []                         # files: (numax, numin, tables) already read
     for wa in wavelengths:
         nu = _f(1.0E+4) / float(wa)
         if nu > CKD_NUMAX or nu < CKD_NUMIN:
             raise ValueError("the wavelength %g is not included in the spectral range of the CKD data, %g .. %g cm-1 (error 905)"
                              % (wa, CKD_NUMIN, CKD_NUMAX))
-        if rng is None or not (rng[1] < nu <= rng[0]):
-            if tables is not None:
-                raise NotImplementedError("wavelengths in different CKD coefficient files (%g cm-1 outside ]%g, %g]): run them in groups"
-                                          % (nu, rng[1], rng[0]))
-            tables, numax, numin = read_ckd(lib, nu, nustep, sos_abs_root)
-            rng = (numax, numin)
-        lamb1.append(1 + int((rng[0] - nu) / nustep))
-    return dict(tables=tables, kdis_ai=tables["ai"], userprofil=user, altabs=altabs, ro=ro, lamb1=lamb1)
+        hit = next((f for f in files if f[1] <= nu < f[0]), None)       # the file READ_CKD_COEFF picks: NUMIN <= NU < NUMAX
+        if hit is None:
+            t, numax, numin = read_ckd(lib, nu, nustep, sos_abs_root)
+            hit = (numax, numin, t)
+            files.append(hit)
+        tables.append(hit[2])
+        lamb1.append(1 + int((hit[0] - nu) / nustep))
+    return dict(tables=tables, kdis_ai=[t["ai"] for t in tables], userprofil=user, altabs=altabs, ro=ro, lamb1=lamb1)

@@ -83,16 +83,22 @@ def enumerate_ckd_terms(nexp, kdis_ai, lamb1):
 def run_band(solver, tables, kdis_ai, userprofil, altabs, ro, waves, itrphi=1, phios=0.0, pas_phi=30, outdir=None,
              trans=False, flux=False):
     """Runs the band.  tables: CKD tables as READ_CKD_COEFF fills them (dict, Fortran-ordered: nb_temp, nb_pres, nb_conc,
-    tab_temp, tab_pres, tab_conc, nexp, ki, kh); kdis_ai: KDIS_AI(5,8,50); userprofil / altabs / ro: the gas atmosphere of
+    tab_temp, tab_pres, tab_conc, nexp, ki, kh) -- or a list of such dicts, one per wavelength (the same object for wavelengths of the
+    same coefficient file); kdis_ai: KDIS_AI(5,8,50) (or the list of them); userprofil / altabs / ro: the gas atmosphere of
     SOS_PREPA_ABSPROFILE.  With outdir, wavelength w gets outdir/<name or index>/SOS_Up.txt, SOS_Down.txt, SOS_Result.bin and,
     on request, SOS_Trans.txt / SOS_Flux.txt."""
     res = BandResult()
     pterms, aiks, owner = [], [], []
+    # tables / kdis_ai: one set for the band, or a list with one entry per wavelength (a band that spans several CKD coefficient
+    # files: READ_CKD_COEFF fills the tables with the 50 spectral intervals of one file)
+    per_wave = isinstance(tables, (list, tuple))
+    tab_of = (lambda w: tables[w]) if per_wave else (lambda w: tables)
+    ai_of = (lambda w: kdis_ai[w]) if per_wave else (lambda w: kdis_ai)
     for w, wv in enumerate(waves):
         if wv.absprofil == 7:
             iks, aik = [(1,) * NBABS], [1.0]
         else:
-            iks, aik = enumerate_ckd_terms(tables["nexp"], kdis_ai, wv.lamb1)
+            iks, aik = enumerate_ckd_terms(tab_of(w)["nexp"], ai_of(w), wv.lamb1)
         res.nterm.append(len(iks))
         for ik, a in zip(iks, aik):
             pterms.append(dict(lamb1=wv.lamb1, ik=ik, absprofil=wv.absprofil, iprofil=wv.iprofil, tr=wv.tr, hr=wv.hr, ta=wv.ta,
@@ -106,8 +112,20 @@ def run_band(solver, tables, kdis_ai, userprofil, altabs, ro, waves, itrphi=1, p
         altabs = np.linspace(120.0, 0.0, 50) if altabs is None else altabs
         tau = np.zeros((len(pterms), 50))
         nt, z, h, pa, pm, ier = solver.profile(altabs, tau, pterms, text_hop=True)
-    else:
+    elif not per_wave:
         nt, z, h, pa, pm, ier, tau = solver.profile_chain(tables, userprofil, altabs, ro, pterms, text_hop=True, want_tauabs=True)
+    else:                                                     # one device call per run of wavelengths that share their tables
+        parts, i0 = [], 0
+        while i0 < len(pterms):
+            t0 = tab_of(owner[i0])
+            i1 = i0
+            while i1 < len(pterms) and tab_of(owner[i1]) is t0:
+                i1 += 1
+            if t0 is None:
+                raise ValueError("wavelength %d has gaseous absorption but no CKD tables" % owner[i0])
+            parts.append(solver.profile_chain(t0, userprofil, altabs, ro, pterms[i0:i1], text_hop=True, want_tauabs=True))
+            i0 = i1
+        nt, z, h, pa, pm, ier, tau = (np.concatenate([p[k] for p in parts]) for k in range(7))
     if ier.any():
         bad = int(np.flatnonzero(ier)[0])
         raise RuntimeError("profile chain: term %d of wavelength %d failed with code %d" % (bad, owner[bad], int(ier[bad])))

@@ -121,14 +121,21 @@ def test_prepare_reads_ckd_tables(tmp_path):
     pc.write_ckd_files(root, t)
     f = str(tmp_path / "profile.txt")
     _write_profile(f, _user())
-    wl = [1e4 / 13255.0, 1e4 / 13004.0, 1e4 / 13500.0]
+    wl = [1e4 / 13255.0, 1e4 / 13004.0, 1e4 / 13495.0]
     g = ab.prepare(lib, wl, 10.0, 0, f, sos_abs_root=root)
     assert g["lamb1"] == [25, 50, 1]                              # 1 + INT((NUMAX - NU) / NUSTEP), NUMAX = 13500
+    assert g["tables"][0] is g["tables"][1] is g["tables"][2]     # one coefficient file, read once
     for k in ("nexp", "ai", "ki", "kh", "tab_temp", "tab_pres", "tab_conc"):
-        assert np.array_equal(g["tables"][k], t[k]), k
-    assert g["kdis_ai"] is g["tables"]["ai"] and g["userprofil"].shape == (50, 13) and g["ro"].shape == (8, 50)
-    with pytest.raises(NotImplementedError):
-        ab.prepare(lib, [1e4 / 13255.0, 1e4 / 12800.0], 10.0, 0, f, sos_abs_root=root)
+        assert np.array_equal(g["tables"][0][k], t[k]), k
+    assert g["kdis_ai"][0] is g["tables"][0]["ai"] and g["userprofil"].shape == (50, 13) and g["ro"].shape == (8, 50)
+    # a list that spans two coefficient files: each wavelength gets the tables of its own file
+    t2 = pc.ckd_tables(5)
+    pc.write_ckd_files(root, t2, numax=13000)
+    g2 = ab.prepare(lib, [1e4 / 13255.0, 1e4 / 12800.0, 1e4 / 13100.0], 10.0, 0, f, sos_abs_root=root)
+    assert g2["lamb1"] == [25, 21, 41] and g2["tables"][0] is g2["tables"][2] and g2["tables"][1] is not g2["tables"][0]
+    assert np.array_equal(g2["tables"][1]["ki"], t2["ki"]) and np.array_equal(g2["tables"][0]["ki"], t["ki"])
+    with pytest.raises(ValueError, match="READ_CKD_COEFF"):       # no file for 13500 .. 14000 cm-1
+        ab.prepare(lib, [1e4 / 13500.0], 10.0, 0, f, sos_abs_root=root)
     with pytest.raises(ValueError, match="905"):
         ab.prepare(lib, [5.0], 10.0, 0, f, sos_abs_root=root)
     with pytest.raises(ValueError, match="READ_CKD_COEFF"):

@@ -534,6 +534,14 @@ def test_host_flow_with_stub_solver(tmp_path):
     nterm = len(band.enumerate_ckd_terms(t["nexp"], t["ai"], 25)[0])
     pcall = [c for c in s.calls if c[0] == "profile_chain"][-1]
     assert res_g.nterm == [nterm] and pcall[1] == nterm and pcall[2] == pc.NPMAX and 4.0e24 < pcall[3] < 5.0e24     # O2 column, molecules / cm2
+    # two wavelengths in two coefficient files: one profile-chain call per file, the terms of each wavelength from its own tables
+    t2 = pc.ckd_tables(5)
+    pc.write_ckd_files(os.environ["SOS_ABS_ROOT"], t2, numax=13000)
+    n_before = len(s.calls)
+    res_g2, _ = fe.run_keywords(s, argv_g.replace(str(tmp_path / "i"), str(tmp_path / "j")).split(), wavelengths=[wa, 1e4 / 12800.0])
+    nterm2 = len(band.enumerate_ckd_terms(t2["nexp"], t2["ai"], 21)[0])
+    pcalls = [c for c in s.calls[n_before:] if c[0] == "profile_chain"]
+    assert res_g2.nterm == [nterm, nterm2] and [c[1] for c in pcalls] == [nterm, nterm2] and len(res_g2.dirs) == 2
     with pytest.raises(ValueError, match="2513"):
         fe.run_keywords(s, argv_g.replace("-AP.AerProfile.Type 1", "-AP.AerProfile.Type 2 -AP.AerLayer.Zmin 1. -AP.AerLayer.Zmax 3.").split())
     # the f2py-shaped entry
