@@ -17,6 +17,9 @@ What is implemented is what those routines use, with Fortran's own semantics whe
     precision, mixed operands are promoted operand by operand, integer division truncates, x**n with an integer n is
     libgcc's __powidf2 / __powisf2 multiplication chain, x**y otherwise pow / powf; generic and specific intrinsics (DINT
     truncates, DNINT rounds halves away from zero); dotted operators in either case;
+  * list-directed READ of numbers from text files opened in the routine (a new record per statement, further records as the list
+    needs them, ERR= / END=), `A` / `Aw` output of CHARACTER items, Hollerith and quoted literals in FORMATs, character
+    constants as actual arguments, blanks inside dotted operators (". AND.");
   * DATA statements for whole one-dimensional arrays, implied DO lists from 1 and scalars (repeat counts n*c), rewritten as
     assignments executed at every call (tables of constants that the routine never modifies);
   * DO loops with the iteration count fixed at entry (labelled, shared terminal labels, ENDDO), DO WHILE, block and
@@ -101,7 +104,7 @@ def logical_lines(path, defines):
 
 TOKEN_RE = re.compile(r"""\s*(?:
     (?P<str>'(?:[^']|'')*'|"[^"]*") |
-    (?P<dotop>\.(?i:EQ|NE|LT|LE|GT|GE|AND|OR|NOT|TRUE|FALSE|EQV|NEQV)\.) |
+    (?P<dotop>\.\s*(?i:EQ|NE|LT|LE|GT|GE|AND|OR|NOT|TRUE|FALSE|EQV|NEQV)\s*\.) |
     (?P<num>(?:\d+\.?\d*|\.\d+)(?:[EDed][+-]?\d+)?) |
     (?P<id>[A-Za-z_][A-Za-z_0-9]*) |
     (?P<op>\*\*|//|[-+*/(),=:])
@@ -122,7 +125,7 @@ def tokenize(text, defines, depth=0):
                 v = "'" + v[1:-1].replace("'", "''") + "'"
             toks.append(("str", v))
         elif m.group("dotop"):
-            toks.append(("op", m.group("dotop").upper()))
+            toks.append(("op", re.sub(r"\s+", "", m.group("dotop")).upper()))       # blanks are not significant in fixed form: ". AND."
         elif m.group("num"):
             s = m.group("num").upper()
             # "1.EQ." style: a trailing '.' followed by a dotted operator belongs to the operator
@@ -638,7 +641,9 @@ def translate_unit(name, args, stmts, defines, known_subs):
             if formatted and not text_file and not re.match(r"^\d+$", unit_txt) and not re.match(r"^\w+$", unit_txt) and u.text_units \
                     and fmt_lab is not None and fmt_lab.strip() in u.formats:
                 text_file = True                                   # computed unit, e.g. READ((I+10),555): one of the units opened here
-            if formatted and not text_file:
+            # list-directed READ of numbers from a text file opened here: READ(u,*[,ERR=][,END=]) items
+            list_mode = kind == "READ" and fmt_lab is not None and fmt_lab.strip() == "*" and unit_txt in u.text_units
+            if formatted and not text_file and not list_mode:
                 if kind == "READ":
                     raise Unsupported("formatted READ on a unit that is not opened here")
                 return "; /* trace / message WRITE dropped */"
@@ -669,7 +674,7 @@ def translate_unit(name, args, stmts, defines, known_subs):
                     elif re.match(r"^\w+$", it) and it.upper() in u.vars and u.vars[it.upper()]["dims"]:
                         v = u.vars[it.upper()]                         # whole array, storage order
                         n = " * ".join("((%s) - (%s) + 1)" % (u.cstr(hi, "i"), u.cstr(lo, "i")) for lo, hi in v["dims"])
-                        if text_file:
+                        if text_file or list_mode:
                             raise Unsupported("whole-array formatted I/O")
                         if kind == "READ":
                             code.append("if (!f77_ritem(%s, %s, (size_t)(%s) * sizeof(%s))) { %s }" % (unit, u.cname(it.upper()), n, CT[v["type"]], fail))
@@ -677,9 +682,14 @@ def translate_unit(name, args, stmts, defines, known_subs):
                             code.append("f77_witem(%s, %s, (size_t)(%s) * sizeof(%s));" % (unit, u.cname(it.upper()), n, CT[v["type"]]))
                     else:
                         e = u.cexpr(it)
+                        if e[1] == "c" and text_file and kind == "WRITE":
+                            code.append("f77_fwrite_a(%s, %s);" % (unit, e[0]))
+                            continue
                         if e[1] == "c":
                             raise Unsupported("character I/O item")
-                        if text_file:
+                        if list_mode:
+                            code.append("{ double t_; if (!f77_lread(%s, &t_)) { %s } %s = (%s)t_; }" % (unit, fail, e[0], CT[e[1]]))
+                        elif text_file:
                             if kind == "READ":
                                 code.append("{ double t_; if (!f77_fread(%s, &t_)) { %s } %s = (%s)t_; }" % (unit, fail, e[0], CT[e[1]]))
                             else:
@@ -696,6 +706,9 @@ def translate_unit(name, args, stmts, defines, known_subs):
                 if kind == "WRITE" and text_file and "character I/O item" in str(ex):
                     return "abort(); /* formatted WRITE of character items (trace output): not translated, must not be reached */"
                 raise
+            if list_mode:                                          # a new record per statement; more records as the list needs them
+                at_end = ("goto L%s;" % endl) if endl else fail
+                return "{ int s_ = f77_lbegin(%s); if (s_ < 0) { %s } if (!s_) { %s } %s }" % (unit, at_end, fail, " ".join(body))
             if text_file:
                 fmt = u.formats[fmt_lab.strip()].replace("\\", "\\\\").replace('"', '\\"')
                 if kind == "READ":
@@ -767,6 +780,11 @@ def translate_unit(name, args, stmts, defines, known_subs):
                     cargs.append("&" + e[0])
                 else:
                     e = u.cexpr(a)
+                    if e[1] == "c" and e[0].startswith('"'):            # a character constant: pointer + hidden length
+                        lit, ln = e[0].rsplit(", ", 1)
+                        cargs.append("(char *)" + lit)
+                        hidden.append("(size_t)" + ln)
+                        continue
                     if e[1] == "c":
                         raise Unsupported("character actual argument")
                     tmp = new_tmp()
@@ -969,6 +987,13 @@ static int f77_exists(const char *s, size_t ls) { char p[1024]; while (ls > 0 &&
 static void f77_system(const char *s, size_t ls) { char p[4200]; while (ls > 0 && s[ls - 1] == ' ') --ls; if (ls >= sizeof p) return; memcpy(p, s, ls); p[ls] = 0; if (system(p)) {} }
 static void f77_assign(char *d, size_t ld, const char *s, size_t ls) { for (size_t i = 0; i < ld; ++i) d[i] = i < ls ? s[i] : ' '; }
 static int f77_cmp(const char *a, size_t la, const char *b, size_t lb) { size_t n = la > lb ? la : lb; for (size_t i = 0; i < n; ++i) { char ca = i < la ? a[i] : ' ', cb = i < lb ? b[i] : ' '; if (ca != cb) return ca < cb ? -1 : 1; } return 0; }
+/* list-directed READ of numbers from a text unit: a new record per statement, further records when the list needs them */
+static char f77_lline[100][4096]; static size_t f77_lpos[100];
+static int f77_lbegin(int u) { if (u < 0 || u >= 100 || !f77_fp[u]) return 0; if (!fgets(f77_lline[u], 4096, f77_fp[u])) return -1; f77_lpos[u] = 0; return 1; }
+static int f77_lsep(char c) { return c == ' ' || c == '\t' || c == ',' || c == '\n' || c == '\r'; }
+static int f77_lread(int u, double *v) { for (;;) { char *p = f77_lline[u] + f77_lpos[u]; while (*p && f77_lsep(*p)) ++p;
+  if (*p) { char b[128], *e; size_t n = 0; while (*p && !f77_lsep(*p) && n < 127) { char c = *p++; b[n++] = (c == 'D' || c == 'd') ? 'e' : c; } b[n] = 0; *v = strtod(b, &e); f77_lpos[u] = (size_t)(p - f77_lline[u]); return *e == 0 && n > 0; }
+  if (!fgets(f77_lline[u], 4096, f77_fp[u])) return 0; f77_lpos[u] = 0; } }
 static char f77_path[100][1024];
 static int f77_open(int u, const char *name, size_t len, int status) { char *path = f77_path[u]; while (len > 0 && name[len - 1] == ' ') --len; if (len >= 1024) return 0; memcpy(path, name, len); path[len] = 0;
   if (f77_fp[u]) fclose(f77_fp[u]);
@@ -977,12 +1002,15 @@ static int f77_open(int u, const char *name, size_t len, int status) { char *pat
   return f77_fp[u] != 0; }
 static void f77_close(int u, int del) { if (u >= 0 && u < 100 && f77_fp[u]) { long p = ftell(f77_fp[u]); fflush(f77_fp[u]); if (p >= 0 && f77_wr[u]) { if (ftruncate(fileno(f77_fp[u]), p)) {} } fclose(f77_fp[u]); f77_fp[u] = 0; if (del) remove(f77_path[u]); } }
 static void f77_rewind(int u) { if (f77_fp[u]) { fflush(f77_fp[u]); fseek(f77_fp[u], 0, SEEK_SET); } }
-/* formatted records: the edit descriptors the reference uses on files (nX, Iw, Fw.d, Ew.d, Dw.d, groups with repeat counts) */
-static struct { char kind; int w, d; } f77_ed[100][256]; static int f77_ned[100], f77_ied[100]; static char f77_line[100][4096]; static size_t f77_col[100]; static int f77_rd[100];
+/* formatted records: the edit descriptors the reference uses on files (nX, Iw, Fw.d, Ew.d, Dw.d, A / Aw on output, Hollerith and quoted
+   literals, groups with repeat counts) */
+static struct { char kind; int w, d; const char *lit; } f77_ed[100][256]; static int f77_ned[100], f77_ied[100]; static char f77_line[100][4096]; static size_t f77_col[100]; static int f77_rd[100];
 static const char *f77_fparse(int u, const char *p, int depth) { /* p points after '(' ; returns pointer after matching ')' */
   while (*p && *p != ')') { int rep = 0, has = 0; while (*p == ' ' || *p == ',') ++p; if (*p == ')') break; while (*p >= '0' && *p <= '9') { rep = rep * 10 + (*p - '0'); ++p; has = 1; } if (!has) rep = 1;
     if (*p == '(') { const char *q = p + 1, *e = q; for (int r = 0; r < rep; ++r) e = f77_fparse(u, q, depth + 1); p = e; continue; }
+    if (*p == '\'') { const char *q = p + 1; while (*q && *q != '\'') ++q; if (f77_ned[u] < 256) { f77_ed[u][f77_ned[u]].kind = 'H'; f77_ed[u][f77_ned[u]].w = (int)(q - p - 1); f77_ed[u][f77_ned[u]].lit = p + 1; f77_ned[u]++; } p = *q ? q + 1 : q; continue; }
     char k = *p; if (k >= 'a' && k <= 'z') k -= 32; ++p;
+    if (k == 'H') { /* Hollerith constant nHtext */ int n = 0; while (n < rep && p[n]) ++n; if (f77_ned[u] < 256) { f77_ed[u][f77_ned[u]].kind = 'H'; f77_ed[u][f77_ned[u]].w = n; f77_ed[u][f77_ned[u]].lit = p; f77_ned[u]++; } p += n; continue; }
     if (k == 'X') { if (f77_ned[u] < 256) { f77_ed[u][f77_ned[u]].kind = 'X'; f77_ed[u][f77_ned[u]].w = rep; f77_ned[u]++; } continue; }
     int w = 0, d = 0; while (*p >= '0' && *p <= '9') { w = w * 10 + (*p - '0'); ++p; } if (*p == '.') { ++p; while (*p >= '0' && *p <= '9') { d = d * 10 + (*p - '0'); ++p; } }
     for (int r = 0; r < rep && f77_ned[u] < 256; ++r) { f77_ed[u][f77_ned[u]].kind = k; f77_ed[u][f77_ned[u]].w = w; f77_ed[u][f77_ned[u]].d = d; f77_ned[u]++; } }
@@ -991,14 +1019,21 @@ static int f77_fbegin(int u, const char *fmt, int rd) { if (!f77_fp[u]) return 0
   if (rd) { if (!fgets(f77_line[u], sizeof f77_line[u], f77_fp[u])) return 0; size_t n = strlen(f77_line[u]); while (n && (f77_line[u][n - 1] == '\n' || f77_line[u][n - 1] == '\r')) f77_line[u][--n] = 0; } else f77_line[u][0] = 0;
   return 1; }
 static int f77_fnext(int u) { for (;;) { if (f77_ied[u] >= f77_ned[u]) { /* format reversion: new record */ if (f77_rd[u]) { if (!fgets(f77_line[u], sizeof f77_line[u], f77_fp[u])) return -1; } else { fprintf(f77_fp[u], "%s\n", f77_line[u]); f77_wr[u] = 1; f77_line[u][0] = 0; } f77_col[u] = 0; f77_ied[u] = 0; }
-    int i = f77_ied[u]++; if (f77_ed[u][i].kind == 'X') { if (f77_rd[u]) f77_col[u] += f77_ed[u][i].w; else { for (int k = 0; k < f77_ed[u][i].w; ++k) strcat(f77_line[u], " "); } continue; } return i; } }
+    int i = f77_ied[u]++; if (f77_ed[u][i].kind == 'X') { if (f77_rd[u]) f77_col[u] += f77_ed[u][i].w; else { for (int k = 0; k < f77_ed[u][i].w; ++k) strcat(f77_line[u], " "); } continue; }
+    if (f77_ed[u][i].kind == 'H') { if (f77_rd[u]) f77_col[u] += f77_ed[u][i].w; else strncat(f77_line[u], f77_ed[u][i].lit, (size_t)f77_ed[u][i].w); continue; } return i; } }
 static void f77_fmt_e(char *out, double x, int w, int d, char ec) { char m[64], s[96]; if (x == 0.0) { snprintf(s, sizeof s, "0.%0*d%c+00", d, 0, ec); } else { snprintf(m, sizeof m, "%.*e", d - 1, fabs(x)); char *e = strchr(m, 'e'); int ex = atoi(e + 1) + 1; *e = 0; char dig[64]; int nd = 0; for (char *c = m; *c; ++c) if (*c != '.') dig[nd++] = *c; dig[nd] = 0;
     snprintf(s, sizeof s, "%s0.%s%c%c%02d", x < 0 ? "-" : "", dig, ec, ex >= 0 ? '+' : '-', abs(ex)); }
   size_t n = strlen(s); if ((int)n > w) { if (s[0] == '0') memmove(s, s + 1, n); else if (s[0] == '-' && s[1] == '0') memmove(s + 1, s + 2, n - 1); n = strlen(s); }
   if ((int)n > w) { memset(out, '*', w); out[w] = 0; } else snprintf(out, 96, "%*s", w, s); }
 static void f77_fwrite(int u, double v, int is_int) { int i = f77_fnext(u); if (i < 0) return; char f[96]; char k = f77_ed[u][i].kind; int w = f77_ed[u][i].w, d = f77_ed[u][i].d;
   if (k == 'I') snprintf(f, sizeof f, "%*d", w, (int)v); else if (k == 'F') snprintf(f, sizeof f, "%*.*f", w, d, v); else f77_fmt_e(f, v, w, d, k == 'D' ? 'D' : 'E'); (void)is_int; strcat(f77_line[u], f); }
-static int f77_fend(int u) { if (!f77_fp[u]) return 0; fprintf(f77_fp[u], "%s\n", f77_line[u]); f77_wr[u] = 1; return 1; }
+/* character item under an A / Aw descriptor: w absent = the length of the item; longer fields are padded on the left, shorter ones keep the first w characters */
+static void f77_fwrite_a(int u, const char *s, size_t ls) { int i = f77_fnext(u); if (i < 0) return; size_t w = f77_ed[u][i].w > 0 ? (size_t)f77_ed[u][i].w : ls, n = strlen(f77_line[u]);
+  if (n + w + 1 >= sizeof f77_line[u]) return; for (size_t k = ls; k < w; ++k) f77_line[u][n++] = ' '; for (size_t k = 0; k < (ls < w ? ls : w); ++k) f77_line[u][n++] = s[k]; f77_line[u][n] = 0; }
+static int f77_fend(int u) { if (!f77_fp[u]) return 0;
+  { /* literals that follow the last item, up to the next data descriptor */ int last = -1; for (int i = f77_ied[u]; i < f77_ned[u] && (f77_ed[u][i].kind == 'X' || f77_ed[u][i].kind == 'H'); ++i) if (f77_ed[u][i].kind == 'H') last = i;
+    for (int i = f77_ied[u]; i <= last; ++i) { if (f77_ed[u][i].kind == 'X') { for (int k = 0; k < f77_ed[u][i].w; ++k) strcat(f77_line[u], " "); } else strncat(f77_line[u], f77_ed[u][i].lit, (size_t)f77_ed[u][i].w); } }
+  fprintf(f77_fp[u], "%s\n", f77_line[u]); f77_wr[u] = 1; return 1; }
 static int f77_fread(int u, double *v) { int i = f77_fnext(u); if (i < 0) return 0; int w = f77_ed[u][i].w, d = f77_ed[u][i].d; char f[128]; size_t n = strlen(f77_line[u]); int k = 0, dot = 0, expo = 0;
   for (int c = 0; c < w && k < 120; ++c) { char ch = (f77_col[u] + c < n) ? f77_line[u][f77_col[u] + c] : ' '; if (ch == ' ') continue; if (ch == 'D' || ch == 'd') ch = 'E'; if (ch == '.') dot = 1; if (ch == 'E' || ch == 'e') expo = 1; f[k++] = ch; } f[k] = 0; f77_col[u] += w;
   if (k == 0) { *v = 0.0; return 1; } char *end; *v = strtod(f, &end); if (end == f) return 0; if (!dot && !expo && f77_ed[u][i].kind != 'I') *v *= pow(10.0, -d); return 1; }

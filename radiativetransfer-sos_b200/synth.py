@@ -72,7 +72,7 @@ def sos_angles(nb_gauss, tetas, user_angles_deg=()):
     mu = [mu[i] for i in order]
     w = [w[i] for i in order]
     flag = [1 if x == 0.0 else 0 for x in w]
-    xmus = float(np.cos(tetas * np.arccos(-1.0) / 180.0))
+    xmus = float(np.cos(tetas * (np.arccos(-1.0) / 180.0)))       # XMUS = DCOS(TETAS*CONVDEGRAD), CONVDEGRAD = PI/180 (SOS_ANGLES.F:296, 402)
     imus = -1
     for j, m in enumerate(mu):
         if abs(xmus - m) < CTE_SEUIL_ECART_MUS:

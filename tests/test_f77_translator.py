@@ -266,3 +266,57 @@ def test_data_statements(f77, tmp_path):
     f = lambda x: float(np.float32(x))
     assert list(out[:10]) == [f(1.013e3), f(0.1), 2.5, 2.5, f(3.410e22), 18.0, f(1.0e-6), f(0.3), f(0.7), 1.5]
     assert list(kout) == [7, 7, 7]
+
+
+def test_list_directed_read_and_a_format(f77, tmp_path):
+    """List-directed numeric READ from a text file (values across records, D exponents, END=), a character constant as an actual
+    argument, A and Hollerith fields on output, a dotted operator written with blanks."""
+    lib = compile_fortran(f77, tmp_path, "listio", """
+      SUBROUTINE LISTIO(FIN,FOUT,N,S)
+      IMPLICIT NONE
+      CHARACTER*100 FIN,FOUT
+      INTEGER*4 N,K
+      DOUBLE PRECISION S,V,W
+      N=0
+      S=0.D+00
+      OPEN(1,FILE=FIN,STATUS='OLD',ERR=90)
+   20 READ(1,*,ERR=90,END=30) V
+      IF ( (V.GT.-1.D0).
+     &      AND.(V.LT.1.D6) ) N=N+1
+      S=S+V
+      GOTO 20
+   30 CLOSE(1)
+      OPEN(1,FILE=FIN,STATUS='OLD',ERR=90)
+      READ(1,*,ERR=90) K,V,W
+      CLOSE(1)
+      OPEN(2,FILE=FOUT,ERR=90)
+      WRITE(2,100,ERR=90) N
+      WRITE(2,120,ERR=90) FIN
+      WRITE(2,130,ERR=90) K,W
+      WRITE(2,140,ERR=90)
+      CLOSE(2)
+      CALL TAG("MIE",S)
+      RETURN
+   90 N=-1
+      RETURN
+  100 FORMAT(17hNB_TOTAL_ANGLES :,I4)
+  120 FORMAT(6hFILE :,A)
+  130 FORMAT(I3,1X,'W =',D12.5)
+  140 FORMAT(12hINDEX  VALUE)
+      END
+      SUBROUTINE TAG(NAME,S)
+      CHARACTER*3 NAME
+      DOUBLE PRECISION S
+      IF (NAME.EQ.'MIE') S=S+1000.D+00
+      RETURN
+      END
+""")
+    fin, fout = tmp_path / "in.txt", tmp_path / "out.txt"
+    fin.write_text("3\n 2.5, 1.D+01\n\n4.25\n")
+    n, s = C.c_int(0), C.c_double(0)
+    pad = lambda p: C.create_string_buffer(str(p).encode().ljust(100), 100)
+    lib.listio_(pad(fin), pad(fout), C.byref(n), C.byref(s), C.c_size_t(100), C.c_size_t(100))
+    assert n.value == 3 and s.value == 3 + 2.5 + 4.25 + 1000.0         # one value per READ statement: the rest of a record is skipped
+    out = fout.read_text().split("\n")
+    assert out[0] == "NB_TOTAL_ANGLES :   3" and out[1].rstrip() == "FILE :" + str(fin) and len(out[1]) == 6 + 100
+    assert out[2] == "  3 W = 0.10000D+02" and out[3] == "INDEX  VALUE"
