@@ -408,6 +408,7 @@ class Unit:
         self.body = []                 # C lines
         self.labels_used = set()
         self.stubs = set()
+        self.params = set()                         # names defined by PARAMETER statements
         self.formats = {}
         self.implicit_none = False
         self.implicit = {ch: ("i" if ch in "IJKLMN" else "r") for ch in "ABCDEFGHIJKLMNOPQRSTUVWXYZ"}
@@ -555,6 +556,7 @@ def translate_unit(name, args, stmts, defines, known_subs):
                 k, v = item.split("=", 1)
                 u.defines = dict(u.defines)
                 u.defines[k.strip().upper()] = "(" + v.strip() + ")"
+                u.params.add(k.strip().upper())
             continue
         m2 = re.match(r"^DIMENSION\s+(.*)$", txt, re.I | re.S)
         if m2:
@@ -629,13 +631,28 @@ def translate_unit(name, args, stmts, defines, known_subs):
             formatted = len(pos) > 1 or "FMT" in kv
             unit_txt = kv.get("UNIT", pos[0] if pos else "0").strip()
             # internal file: WRITE(CHARVAR,'(Iw)') integer-expression  (SOS_NOM_FICMIE builds the MIE file name this way)
-            mi = re.match(r"^'\(\s*I(\d+)\s*\)'$", (pos[1] if len(pos) > 1 else "").strip(), re.I)
-            if kind == "WRITE" and mi and unit_txt.upper() in u.vars and u.vars[unit_txt.upper()]["type"] == "c":
-                dst = u.cexpr(unit_txt)
+            mi = re.match(r"^'\(\s*([IA])(\d+)\s*\)'$", (pos[1] if len(pos) > 1 else "").strip(), re.I)
+            unit_name = re.match(r"^\s*(\w+)", unit_txt)
+            if kind == "WRITE" and mi and unit_name and unit_name.group(1).upper() in u.vars and u.vars[unit_name.group(1).upper()]["type"] == "c":
+                dst = u.cexpr(unit_txt)                              # a CHARACTER variable or a substring of one
                 val = u.cexpr(rest[j + 1:].strip())
+                if mi.group(1).upper() == "A":
+                    if val[1] != "c":
+                        raise Unsupported("internal WRITE: A field with a non-character item")
+                    return "{ static char a_[4096]; size_t n_ = f77_cat(a_, 0, %s); if (n_ > %d) n_ = %d; f77_assign(%s, a_, n_); }" % (
+                        val[0], int(mi.group(2)), int(mi.group(2)), dst[0])
                 if val[1] != "i":
                     raise Unsupported("internal WRITE of a non-integer")
-                return "{ char b_[64]; snprintf(b_, sizeof b_, \"%%*d\", %d, (int)(%s)); f77_assign(%s, b_, strlen(b_)); }" % (int(mi.group(1)), val[0], dst[0])
+                return "{ char b_[64]; snprintf(b_, sizeof b_, \"%%*d\", %d, (int)(%s)); f77_assign(%s, b_, strlen(b_)); }" % (int(mi.group(2)), val[0], dst[0])
+            # READ(u,'(a)') CHARVAR: one record of a text file into a CHARACTER variable
+            if kind == "READ" and len(pos) > 1 and re.match(r"^'\(\s*A\s*\)'$", pos[1].strip(), re.I) and unit_txt in u.text_units:
+                dst = u.cexpr(rest[j + 1:].strip())
+                if dst[1] != "c":
+                    raise Unsupported("READ '(a)' into a non-character item")
+                err = kv.get("ERR")
+                if err:
+                    u.labels_used.add(err)
+                return "if (!f77_readline(%s, %s)) { %s }" % (u.cstr(unit_txt, "i"), dst[0], "goto L%s;" % err if err else "abort();")
             fmt_lab = kv.get("FMT", pos[1] if len(pos) > 1 else None)
             text_file = formatted and unit_txt in u.text_units and fmt_lab is not None and fmt_lab.strip() in u.formats
             if formatted and not text_file and not re.match(r"^\d+$", unit_txt) and not re.match(r"^\w+$", unit_txt) and u.text_units \
@@ -730,15 +747,37 @@ def translate_unit(name, args, stmts, defines, known_subs):
                 else:
                     kv["UNIT"] = c.strip()
             text = "UNFORMATTED" not in kv.get("FORM", "").upper()
-            f = u.cexpr(kv["FILE"])
-            if f[1] != "c":
-                raise Unsupported("OPEN FILE= expression")
             err = kv.get("ERR")
             if err:
                 u.labels_used.add(err)
             st = kv.get("STATUS", "'UNKNOWN'").upper().strip("'")
-            return "if (!f77_open(%s, %s, %d)) { %s }" % (u.cstr(kv["UNIT"], "i"), f[0], {"OLD": 1, "NEW": 2}.get(st, 0) + (4 if text else 0),
-                                                        "goto L%s;" % err if err else "abort();")
+            flags = {"OLD": 1, "NEW": 2}.get(st, 0) + (4 if text else 0)
+            fail = "goto L%s;" % err if err else "abort();"
+            ftoks = tokenize(kv["FILE"], u.defines)
+            if any(k == "op" and v == "//" for k, v in ftoks):        # FILE = a // b // ...: concatenated into a buffer first
+                parts, cur, depth = [], [], 0
+                for k, v in ftoks:
+                    if k == "op" and v == "(":
+                        depth += 1
+                    if k == "op" and v == ")":
+                        depth -= 1
+                    if k == "op" and v == "//" and depth == 0:
+                        parts.append(cur)
+                        cur = []
+                    else:
+                        cur.append((k, v))
+                parts.append(cur)
+                code = "{ static char cat_[4096]; size_t n_ = 0; "
+                for pt in parts:
+                    e = u.cexpr(pt)
+                    if e[1] != "c":
+                        raise Unsupported("concatenation of a non-character operand")
+                    code += "n_ = f77_cat(cat_, n_, %s); " % e[0]
+                return code + "if (!f77_open(%s, cat_, n_, %d)) { %s } }" % (u.cstr(kv["UNIT"], "i"), flags, fail)
+            f = u.cexpr(kv["FILE"])
+            if f[1] != "c":
+                raise Unsupported("OPEN FILE= expression")
+            return "if (!f77_open(%s, %s, %d)) { %s }" % (u.cstr(kv["UNIT"], "i"), f[0], flags, fail)
         m = re.match(r"^CLOSE\s*\((.*)\)\s*$", txt, re.I | re.S)
         if m:
             parts = split_top(m.group(1))
@@ -760,6 +799,13 @@ def translate_unit(name, args, stmts, defines, known_subs):
         m = re.match(r"^CALL\s+SYSTEM\s*\((.*)\)\s*$", txt, re.I | re.S)
         if m:
             return "f77_system(%s);" % u.cexpr(m.group(1))[0]
+        m = re.match(r"^CALL\s+GETENV\s*\((.*)\)\s*$", txt, re.I | re.S)
+        if m:
+            a = split_top(m.group(1))
+            name, var = u.cexpr(a[0]), u.cexpr(a[1])
+            if name[1] != "c" or var[1] != "c" or not name[0].startswith('"'):
+                raise Unsupported("GETENV form")
+            return "{ const char *e_ = getenv(%s); f77_assign(%s, e_ ? e_ : \"\", e_ ? strlen(e_) : 0); }" % (name[0].rsplit(", ", 1)[0], var[0])
         m = re.match(r"^CALL\s+(\w+)\s*\((.*)\)\s*$", txt, re.I | re.S)
         if m:
             callee = m.group(1).upper()
@@ -773,7 +819,8 @@ def translate_unit(name, args, stmts, defines, known_subs):
                 if re.match(r"^\w+$", aup) and aup in u.vars and u.vars[aup]["type"] == "c":
                     cargs.append(u.cname(aup))
                     hidden.append(("len_" + u.cname(aup)) if aup in u.args else "(size_t)(%s)" % u.cstr(u.vars[aup]["clen"], "i"))
-                elif re.match(r"^\w+$", aup) and aup in u.vars:
+                elif re.match(r"^\w+$", aup) and aup in u.vars and aup not in u.params:
+                    # (a PARAMETER constant that also has a type declaration is an expression: it goes through a temporary)
                     cargs.append(u.cname(aup) if (aup in u.args or u.vars[aup]["dims"]) else "&" + u.cname(aup))
                 elif re.match(r"^\w+\s*\(.*\)$", aup) and aup.split("(")[0].strip() in u.vars and u.vars[aup.split("(")[0].strip()]["dims"]:
                     e = u.cexpr(a)
@@ -994,6 +1041,7 @@ static int f77_lsep(char c) { return c == ' ' || c == '\t' || c == ',' || c == '
 static int f77_lread(int u, double *v) { for (;;) { char *p = f77_lline[u] + f77_lpos[u]; while (*p && f77_lsep(*p)) ++p;
   if (*p) { char b[128], *e; size_t n = 0; while (*p && !f77_lsep(*p) && n < 127) { char c = *p++; b[n++] = (c == 'D' || c == 'd') ? 'e' : c; } b[n] = 0; *v = strtod(b, &e); f77_lpos[u] = (size_t)(p - f77_lline[u]); return *e == 0 && n > 0; }
   if (!fgets(f77_lline[u], 4096, f77_fp[u])) return 0; f77_lpos[u] = 0; } }
+static int f77_readline(int u, char *dst, size_t ld) { char b[4096]; if (u < 0 || u >= 100 || !f77_fp[u] || !fgets(b, sizeof b, f77_fp[u])) return 0; size_t n = strlen(b); while (n && (b[n - 1] == '\n' || b[n - 1] == '\r')) --n; f77_assign(dst, ld, b, n); return 1; }
 static char f77_path[100][1024];
 static int f77_open(int u, const char *name, size_t len, int status) { char *path = f77_path[u]; while (len > 0 && name[len - 1] == ' ') --len; if (len >= 1024) return 0; memcpy(path, name, len); path[len] = 0;
   if (f77_fp[u]) fclose(f77_fp[u]);

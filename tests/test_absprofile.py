@@ -2,10 +2,11 @@
 
 DATATM (SOS_SUB_TRS.F:908-1003) against the routine itself in oracle/_ref/libsosref.so -- BIT-IDENTICAL -- for a user profile and,
 where the reference tree is present, for the six predefined atmospheres, whose tables absprofile.py reads from the DATA statements
-of the reference's source file at run time (the translated routines TROPICA .. USTAD62 are the check of that reader).  The rest of
-SOS_PREPA_ABSPROFILE (:473-541: about 25 arithmetic statements; the routine itself does not translate) is checked by what it has
-to achieve -- column amounts and surface concentrations equal to the requested ones, layer amounts against an independent
-vectorised evaluation -- and says so: PARITY UNPINNED for those statements.  CKD tables through the host reader of libsosgpu.so."""
+of the reference's source file at run time (the translated routines TROPICA .. USTAD62 are the check of that reader).  absprofile.prepare as a whole
+against SOS_PREPA_ABSPROFILE itself -- USERPROFIL, ALTABS, RO, CKD tables, LAMB1 BIT-IDENTICAL, with and without the scalings, for
+a user profile and for predefined atmospheres on the reference's own data files; the host CKD reader of libsosgpu.so against
+READ_CKD_COEFF itself on generated files and on the reference's own coefficient files; and the scalings once more by what they
+have to achieve (column amounts and surface concentrations equal to the requested ones)."""
 import ctypes as C
 import importlib
 import os
@@ -140,3 +141,121 @@ def test_prepare_reads_ckd_tables(tmp_path):
         ab.prepare(lib, [5.0], 10.0, 0, f, sos_abs_root=root)
     with pytest.raises(ValueError, match="READ_CKD_COEFF"):
         ab.prepare(lib, [1e4 / 13255.0], 1.0, 0, f, sos_abs_root=root)
+
+
+def _ref_read_ckd(ref, root, k, jabs, nu, nustep):
+    os.environ["SOS_ABS_ROOT"] = root
+    nexp = np.zeros((pc.NBABS, pc.NWVL), dtype=np.int32, order="F")
+    ai = np.zeros((pc.NAI, pc.NBABS, pc.NWVL), order="F")
+    ki = np.zeros((pc.NTMAX, pc.NPMAX, pc.NAI, pc.NBABS, pc.NWVL), order="F")
+    kh = np.zeros((pc.NTMAX, pc.NPMAX, pc.NCMAX, pc.NAI, pc.NWVL), order="F")
+    tp, tt, tc = np.zeros(pc.NPMAX), np.zeros(pc.NTMAX), np.zeros(pc.NCMAX)
+    numax, numin, nbp, nbt, nbc, ier = C.c_double(0), C.c_double(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(99)
+    I = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    ref.read_ckd_coeff_(C.byref(C.c_int(k)), C.byref(C.c_int(jabs)), C.byref(C.c_double(nu)), C.byref(C.c_double(nustep)), I(nexp), _P(ai), _P(ki),
+                        _P(kh), C.byref(numax), C.byref(numin), _P(tp), C.byref(nbp), _P(tt), C.byref(nbt), _P(tc), C.byref(nbc), C.byref(ier))
+    return ier.value, dict(nexp=nexp, ai=ai, ki=ki, kh=kh, tab_pres=tp, tab_temp=tt, tab_conc=tc, nb=(nbp.value, nbt.value, nbc.value),
+                           rng=(numax.value, numin.value))
+
+
+def _mine_read_ckd(lib, root, k, jabs, nu, nustep):
+    nexp = np.zeros((pc.NBABS, pc.NWVL), dtype=np.int32, order="F")
+    ai = np.zeros((pc.NAI, pc.NBABS, pc.NWVL), order="F")
+    ki = np.zeros((pc.NTMAX, pc.NPMAX, pc.NAI, pc.NBABS, pc.NWVL), order="F")
+    kh = np.zeros((pc.NTMAX, pc.NPMAX, pc.NCMAX, pc.NAI, pc.NWVL), order="F")
+    tp, tt, tc = np.zeros(pc.NPMAX), np.zeros(pc.NTMAX), np.zeros(pc.NCMAX)
+    numax, numin, nbp, nbt, nbc = C.c_double(0), C.c_double(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    lib.sosgpu_read_ckd_coeff.restype = C.c_int
+    rc = lib.sosgpu_read_ckd_coeff(root.encode(), C.c_int(k), C.c_int(jabs), C.c_double(nu), C.c_double(nustep), nexp.ctypes.data_as(C.POINTER(C.c_int)),
+                                   _P(ai), _P(ki), _P(kh), C.byref(numax), C.byref(numin), _P(tp), C.byref(nbp), _P(tt), C.byref(nbt), _P(tc),
+                                   C.byref(nbc))
+    return rc, dict(nexp=nexp, ai=ai, ki=ki, kh=kh, tab_pres=tp, tab_temp=tt, tab_conc=tc, nb=(nbp.value, nbt.value, nbc.value),
+                    rng=(numax.value, numin.value))
+
+
+def test_ckd_reader_vs_the_references_reader(tmp_path):
+    """sosgpu_read_ckd_coeff (host code of libsosgpu.so) against READ_CKD_COEFF itself (SOS_SUB_TRS.F:481-905, in libsosref.so): every
+    array identical -- on generated files for the eight gases (H2O with its concentration dimension) and, where the reference tree is
+    present, on the reference's own coefficient files (O2 A band, CO2, CH4, O3 ... at 10, 5 and 1 cm-1)."""
+    ref = refdirect.lib()
+    if ref is None or not hasattr(ref, "read_ckd_coeff_"):
+        pytest.skip("oracle/_ref/libsosref.so (with READ_CKD_COEFF) not available")
+    api = importlib.import_module("radiativetransfer-sos_b200.api")
+    lib = api.load_library()
+    root = str(tmp_path)
+    pc.write_ckd_files(root, pc.ckd_tables(4))
+    cases = [(root, k, 1, 13255.0, 10.0) for k in range(1, 9)] + [(root, 7, 0, 13255.0, 10.0), (root, 1, 0, 13255.0, 10.0)]
+    if os.path.isdir(os.path.join(REFROOT, "fic", "COEFF_CKD")):
+        for step, nus in ((10, (13100.0, 4800.0, 20950.0)), (5, (13102.5,)), (1, (13120.0,))):
+            d = os.path.join(REFROOT, "fic", "COEFF_CKD", "%dcmm1" % step)
+            for k, g in enumerate(pc.GAS):
+                for nu in nus:
+                    lo = (int(27500 - nu) // (50 * step) + 1) * 50 * step
+                    if os.path.exists(os.path.join(d, "coef_%s_%d_%d_%dcmm1" % (g, 27500 - lo + 50 * step, 27500 - lo, step))):
+                        cases.append((REFROOT, k + 1, 1, nu, float(step)))
+    nreal = 0
+    for rt, k, jabs, nu, step in cases:
+        ier, a = _ref_read_ckd(ref, rt, k, jabs, nu, step)
+        rc, b = _mine_read_ckd(lib, rt, k, jabs, nu, step)
+        assert ier == rc == 0, (rt, k, nu, step, ier, rc)
+        nreal += rt == REFROOT
+        for key in ("nexp", "ai", "ki", "kh", "tab_pres", "tab_temp", "tab_conc"):
+            if key in ("tab_conc",) and k != 1:
+                continue
+            assert np.array_equal(a[key], b[key]), (rt, k, nu, step, key)
+        if jabs:
+            assert a["rng"] == b["rng"] and a["nb"][:2] == b["nb"][:2], (rt, k, nu)
+    print("\n[CKD reader] %d cases identical to READ_CKD_COEFF, %d of them on the reference's own coefficient files" % (len(cases), nreal))
+    for bad in ((root, 7, 1, 13255.0, 2.0), (root, 7, 1, 5000.0, 10.0)):       # unsupported resolution, missing file: IER = -1 on both sides
+        assert _ref_read_ckd(ref, *bad)[0] == -1 and _mine_read_ckd(lib, *bad)[0] == -1
+
+
+def test_prepare_vs_sos_prepa_absprofile(tmp_path):
+    """absprofile.prepare against SOS_PREPA_ABSPROFILE itself (SOS_PREPA_ABSPROFILE.F:248-752, in libsosref.so; it calls DATATM and
+    READ_CKD_COEFF of the same library): USERPROFIL, ALTABS, RO, the CKD tables, LAMB1 -- BIT-IDENTICAL -- for a user profile with
+    and without the scalings of -AP.Psurf / H2O / O3 / CO2 / CH4 and, where the reference tree is present, for the predefined
+    atmospheres with the reference's own SO2-NO2 and coefficient files."""
+    ref = refdirect.lib()
+    if ref is None or not hasattr(ref, "sos_prepa_absprofile_"):
+        pytest.skip("oracle/_ref/libsosref.so (with SOS_PREPA_ABSPROFILE) not available")
+    ab = _ab()
+    api = importlib.import_module("radiativetransfer-sos_b200.api")
+    lib = api.load_library()
+    root = str(tmp_path)
+    pc.write_ckd_files(root, pc.ckd_tables(4))
+    f = str(tmp_path / "profile.txt")
+    _write_profile(f, _user())
+    I = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+
+    def reference(rt, wa, step, absprofil, fic, psurf, h2o, o3, co2, ch4):
+        os.environ["SOS_ABS_ROOT"] = rt
+        nexp = np.zeros((pc.NBABS, pc.NWVL), dtype=np.int32, order="F")
+        ai = np.zeros((pc.NAI, pc.NBABS, pc.NWVL), order="F")
+        ki = np.zeros((pc.NTMAX, pc.NPMAX, pc.NAI, pc.NBABS, pc.NWVL), order="F")
+        kh = np.zeros((pc.NTMAX, pc.NPMAX, pc.NCMAX, pc.NAI, pc.NWVL), order="F")
+        tp, tt, tc = np.zeros(pc.NPMAX), np.zeros(pc.NTMAX), np.zeros(pc.NCMAX)
+        user, altabs, ro = np.zeros((50, 13), order="F"), np.zeros(50), np.zeros((8, 50), order="F")
+        iabs = np.zeros(8, dtype=np.int32)
+        nu, lamb1, nbp, nbt, nbc, ier = C.c_double(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(99)
+        d = lambda v: C.byref(C.c_double(v))
+        ref.sos_prepa_absprofile_(d(wa), d(step), d(psurf), d(h2o), d(o3), d(co2), d(ch4), C.byref(C.c_int(absprofil)), refdirect._fs(fic or "NONE"),
+                                  C.byref(C.c_int(0)), C.byref(C.c_int(0)), C.byref(nu), C.byref(lamb1), I(iabs), _P(user), _P(altabs), _P(ro),
+                                  I(nexp), _P(ai), _P(ki), _P(kh), _P(tp), C.byref(nbp), _P(tt), C.byref(nbt), _P(tc), C.byref(nbc), C.byref(ier),
+                                  refdirect._L)
+        return ier.value, dict(user=user, altabs=altabs, ro=ro, lamb1=lamb1.value, nexp=nexp, ai=ai, ki=ki, kh=kh, tab_pres=tp, tab_temp=tt, tab_conc=tc)
+
+    nd = -999.0
+    cases = [(root, 1e4 / 13255.0, 10.0, 0, f, nd, nd, nd, nd, nd), (root, 1e4 / 13004.0, 10.0, 0, f, 1000.0, 2.5, 300.0, 420.0, 1.9),
+             (root, 1e4 / 13495.0, 10.0, 0, f, nd, 0.8, nd, nd, 1.7)]
+    if os.path.isdir(os.path.join(REFROOT, "fic", "COEFF_CKD")) and all(
+            os.path.exists(os.path.join(REFROOT, "fic", "COEFF_CKD", "10cmm1", "coef_%s_13500_13000_10cmm1" % g)) for g in pc.GAS):
+        cases += [(REFROOT, 0.7625, 10.0, 6, None, nd, nd, nd, nd, nd), (REFROOT, 0.7625, 10.0, 1, None, 1005.0, 4.1, 250.0, nd, nd),
+                  (REFROOT, 0.765, 10.0, 3, None, nd, nd, nd, 400.0, nd)]
+    for rt, wa, step, absprofil, fic, psurf, h2o, o3, co2, ch4 in cases:
+        ier, r = reference(rt, wa, step, absprofil, fic, psurf, h2o, o3, co2, ch4)
+        assert ier == 0, (rt, wa, absprofil)
+        g = ab.prepare(lib, [wa], step, absprofil, fic, psurf, h2o, o3, co2, ch4, sos_abs_root=rt)
+        assert g["lamb1"] == [r["lamb1"]]
+        assert _same(g["userprofil"], r["user"]) and _same(g["altabs"], r["altabs"]) and _same(g["ro"], r["ro"]), (rt, wa, absprofil)
+        for key in ("nexp", "ai", "ki", "kh", "tab_pres", "tab_temp", "tab_conc"):
+            assert np.array_equal(g["tables"][0][key], r[key]), key
