@@ -17,9 +17,12 @@ What is implemented is what those routines use, with Fortran's own semantics whe
     precision, mixed operands are promoted operand by operand, integer division truncates, x**n with an integer n is
     libgcc's __powidf2 / __powisf2 multiplication chain, x**y otherwise pow / powf; generic and specific intrinsics (DINT
     truncates, DNINT rounds halves away from zero); dotted operators in either case;
-  * list-directed READ of numbers from text files opened in the routine (a new record per statement, further records as the list
-    needs them, ERR= / END=), `A` / `Aw` output of CHARACTER items, Hollerith and quoted literals in FORMATs, character
-    constants as actual arguments, blanks inside dotted operators (". AND.");
+  * list-directed READ of numbers and character tokens from text files opened in the routine (a new record per statement, further
+    records as the list needs them, ERR= / END=) and from CHARACTER variables / substrings (internal files), READ(u,'(a)') of a
+    whole record, `A` / `Aw` output of CHARACTER items, Hollerith and quoted literals in FORMATs, internal WRITE with (Iw) / (Aw)
+    into variables and substrings, OPEN with a concatenated file name, GETENV, one-dimensional CHARACTER arrays, character
+    constants and PARAMETER constants as actual arguments, blanks inside dotted operators (". AND."); the error messages the
+    reference writes on unit 6 are printed to stderr when F77_TO_C_MESSAGES is set (debugging aid);
   * DATA statements for whole one-dimensional arrays, implied DO lists from 1 and scalars (repeat counts n*c), rewritten as
     assignments executed at every call (tables of constants that the routine never modifies);
   * DO loops with the iteration count fixed at entry (labelled, shared terminal labels, ENDDO), DO WHILE, block and
@@ -307,6 +310,13 @@ class Parser:
             lit = v[1:-1].replace("''", "'")
             return ('"%s", %d' % (lit.replace("\\", "\\\\").replace('"', '\\"'), len(lit)), "c")
         if k == "id":
+            if self.at("(") and v in self.u.vars and self.u.vars[v]["type"] == "c" and len(self.u.vars[v]["dims"]) == 1:
+                self.take("(")                                      # element of a one-dimensional CHARACTER array
+                ix = self.expr()
+                self.take(")")
+                lo = self.u.cstr(self.u.vars[v]["dims"][0][0], "i")
+                ln = self.u.cstr(self.u.vars[v]["clen"], "i")
+                return ("%s + (size_t)((%s) - (%s)) * (size_t)(%s), (size_t)(%s)" % (self.u.cname(v), ix[0], lo, ln, ln), "c")
             if self.at("(") and v in self.u.vars and self.u.vars[v]["type"] == "c" and not self.u.vars[v]["dims"]:
                 self.take("(")
                 lo = self.expr()
@@ -658,13 +668,22 @@ def translate_unit(name, args, stmts, defines, known_subs):
             if formatted and not text_file and not re.match(r"^\d+$", unit_txt) and not re.match(r"^\w+$", unit_txt) and u.text_units \
                     and fmt_lab is not None and fmt_lab.strip() in u.formats:
                 text_file = True                                   # computed unit, e.g. READ((I+10),555): one of the units opened here
-            # list-directed READ of numbers from a text file opened here: READ(u,*[,ERR=][,END=]) items
+            # list-directed READ from a text file opened here, READ(u,*[,ERR=][,END=]) items, or from a CHARACTER variable / substring
             list_mode = kind == "READ" and fmt_lab is not None and fmt_lab.strip() == "*" and unit_txt in u.text_units
+            internal = None
+            if kind == "READ" and fmt_lab is not None and fmt_lab.strip() == "*" and not list_mode and unit_name \
+                    and unit_name.group(1).upper() in u.vars and u.vars[unit_name.group(1).upper()]["type"] == "c":
+                internal = u.cexpr(unit_txt)
+                list_mode = True
             if formatted and not text_file and not list_mode:
                 if kind == "READ":
                     raise Unsupported("formatted READ on a unit that is not opened here")
+                lit = re.match(r"^\s*('(?:[^']|'')*'|\"[^\"]*\")", items)
+                if unit_txt == "6" and lit:                        # error messages of the reference: shown on request (debugging aid)
+                    txt_ = lit.group(1)[1:-1].replace("\\", "\\\\").replace('"', '\\"')
+                    return "if (getenv(\"F77_TO_C_MESSAGES\")) fprintf(stderr, \"%%s\\n\", \"%s\");" % txt_
                 return "; /* trace / message WRITE dropped */"
-            unit = u.cstr(unit_txt, "i")
+            unit = "100" if internal else u.cstr(unit_txt, "i")
             err = kv.get("ERR")
             fail = "goto L%s;" % err if err else "abort();"
             if err:
@@ -699,6 +718,9 @@ def translate_unit(name, args, stmts, defines, known_subs):
                             code.append("f77_witem(%s, %s, (size_t)(%s) * sizeof(%s));" % (unit, u.cname(it.upper()), n, CT[v["type"]]))
                     else:
                         e = u.cexpr(it)
+                        if e[1] == "c" and list_mode:
+                            code.append("if (!f77_lread_c(%s, %s)) { %s }" % (unit, e[0], fail))
+                            continue
                         if e[1] == "c" and text_file and kind == "WRITE":
                             code.append("f77_fwrite_a(%s, %s);" % (unit, e[0]))
                             continue
@@ -725,6 +747,8 @@ def translate_unit(name, args, stmts, defines, known_subs):
                 raise
             if list_mode:                                          # a new record per statement; more records as the list needs them
                 at_end = ("goto L%s;" % endl) if endl else fail
+                if internal:
+                    return "{ f77_ibegin(%s); %s }" % (internal[0], " ".join(body))
                 return "{ int s_ = f77_lbegin(%s); if (s_ < 0) { %s } if (!s_) { %s } %s }" % (unit, at_end, fail, " ".join(body))
             if text_file:
                 fmt = u.formats[fmt_lab.strip()].replace("\\", "\\\\").replace('"', '\\"')
@@ -998,8 +1022,12 @@ def translate_unit(name, args, stmts, defines, known_subs):
         if n in args:
             continue
         if v["type"] == "c":
+            if len(v["dims"]) > 1:
+                raise Unsupported("CHARACTER array %s of more than one dimension" % n)
             if v["dims"]:
-                raise Unsupported("CHARACTER array %s" % n)
+                lo, hi = v["dims"][0]
+                decl.append("  static char %s[((%s) - (%s) + 1) * (%s)];" % (u.cname(n), u.cstr(hi, "i"), u.cstr(lo, "i"), u.cstr(v["clen"], "i")))
+                continue
             decl.append("  static char %s[%s];" % (u.cname(n), u.cstr(v["clen"], "i")))
             continue
         if v["dims"]:
@@ -1034,13 +1062,18 @@ static int f77_exists(const char *s, size_t ls) { char p[1024]; while (ls > 0 &&
 static void f77_system(const char *s, size_t ls) { char p[4200]; while (ls > 0 && s[ls - 1] == ' ') --ls; if (ls >= sizeof p) return; memcpy(p, s, ls); p[ls] = 0; if (system(p)) {} }
 static void f77_assign(char *d, size_t ld, const char *s, size_t ls) { for (size_t i = 0; i < ld; ++i) d[i] = i < ls ? s[i] : ' '; }
 static int f77_cmp(const char *a, size_t la, const char *b, size_t lb) { size_t n = la > lb ? la : lb; for (size_t i = 0; i < n; ++i) { char ca = i < la ? a[i] : ' ', cb = i < lb ? b[i] : ' '; if (ca != cb) return ca < cb ? -1 : 1; } return 0; }
-/* list-directed READ of numbers from a text unit: a new record per statement, further records when the list needs them */
-static char f77_lline[100][4096]; static size_t f77_lpos[100];
+/* list-directed READ from a text unit (or from a character string: pseudo-unit 100): a new record per statement, further records
+   when the list needs them; items are numbers or unquoted / quoted character tokens */
+static char f77_lline[101][4096]; static size_t f77_lpos[101];
 static int f77_lbegin(int u) { if (u < 0 || u >= 100 || !f77_fp[u]) return 0; if (!fgets(f77_lline[u], 4096, f77_fp[u])) return -1; f77_lpos[u] = 0; return 1; }
+static int f77_ibegin(const char *s, size_t ls) { if (ls > 4095) ls = 4095; memcpy(f77_lline[100], s, ls); f77_lline[100][ls] = 0; f77_lpos[100] = 0; return 1; }
 static int f77_lsep(char c) { return c == ' ' || c == '\t' || c == ',' || c == '\n' || c == '\r'; }
-static int f77_lread(int u, double *v) { for (;;) { char *p = f77_lline[u] + f77_lpos[u]; while (*p && f77_lsep(*p)) ++p;
-  if (*p) { char b[128], *e; size_t n = 0; while (*p && !f77_lsep(*p) && n < 127) { char c = *p++; b[n++] = (c == 'D' || c == 'd') ? 'e' : c; } b[n] = 0; *v = strtod(b, &e); f77_lpos[u] = (size_t)(p - f77_lline[u]); return *e == 0 && n > 0; }
-  if (!fgets(f77_lline[u], 4096, f77_fp[u])) return 0; f77_lpos[u] = 0; } }
+static int f77_ltoken(int u, char *b, size_t cap) { for (;;) { char *p = f77_lline[u] + f77_lpos[u]; while (*p && f77_lsep(*p)) ++p;
+  if (*p) { size_t n = 0; if (*p == '\'' || *p == '"') { char q = *p++; while (*p && *p != q && n + 1 < cap) b[n++] = *p++; if (*p == q) ++p; } else { while (*p && !f77_lsep(*p) && n + 1 < cap) b[n++] = *p++; }
+    b[n] = 0; f77_lpos[u] = (size_t)(p - f77_lline[u]); return 1; }
+  if (u == 100 || !f77_fp[u] || !fgets(f77_lline[u], 4096, f77_fp[u])) return 0; f77_lpos[u] = 0; } }
+static int f77_lread(int u, double *v) { char b[128], *e; if (!f77_ltoken(u, b, sizeof b) || !b[0]) return 0; for (char *c = b; *c; ++c) if (*c == 'D' || *c == 'd') *c = 'e'; *v = strtod(b, &e); return *e == 0; }
+static int f77_lread_c(int u, char *dst, size_t ld) { char b[4096]; if (!f77_ltoken(u, b, sizeof b)) return 0; size_t n = strlen(b); for (size_t i = 0; i < ld; ++i) dst[i] = i < n ? b[i] : ' '; return 1; }
 static int f77_readline(int u, char *dst, size_t ld) { char b[4096]; if (u < 0 || u >= 100 || !f77_fp[u] || !fgets(b, sizeof b, f77_fp[u])) return 0; size_t n = strlen(b); while (n && (b[n - 1] == '\n' || b[n - 1] == '\r')) --n; f77_assign(dst, ld, b, n); return 1; }
 static char f77_path[100][1024];
 static int f77_open(int u, const char *name, size_t len, int status) { char *path = f77_path[u]; while (len > 0 && name[len - 1] == ' ') --len; if (len >= 1024) return 0; memcpy(path, name, len); path[len] = 0;

@@ -80,15 +80,28 @@ def rayleigh_thickness(psurf, wa):
                                              + float(np.float32(1.4)) / wa ** 6)
 
 
-def aerosol_model(kw):
-    """-AER.* keywords -> a model of aerosols.py."""
+def aerosol_model(kw, wavelengths=None):
+    """-AER.* keywords -> a model of aerosols.py (wavelengths: those of the run, where the reference's rules depend on them)."""
     m = kw.get("-AER.Model")
+    waref = kw.get("-AER.Waref")
+    only_ref = wavelengths is not None and waref is not None and [float(w) for w in wavelengths] == [float(waref)]
     if m == 0:
+        # the refractive index at the reference wavelength (-AER.MMD.MRwaref / MIwaref) is what SOS_PROC hands to SOS_AEROSOLS in its
+        # call at that wavelength; required when the simulation wavelength differs (SOS_PROC.F:1702-1711, error 2314)
+        rn, in_ = kw["-AER.MMD.MRwa"], kw["-AER.MMD.MIwa"]
+        if not only_ref:
+            if "-AER.MMD.MRwaref" not in kw or "-AER.MMD.MIwaref" not in kw:
+                if wavelengths is not None:
+                    raise ValueError("-AER.Model 0 with a simulation wavelength other than -AER.Waref requires -AER.MMD.MRwaref and "
+                                     "-AER.MMD.MIwaref (SOS_PROC error 2314)")
+            else:
+                rn = (lambda wa, r=kw["-AER.MMD.MRwaref"], s_=rn: r if wa == waref else s_)
+                in_ = (lambda wa, r=kw["-AER.MMD.MIwaref"], s_=in_: r if wa == waref else s_)
         sd = kw.get("-AER.MMD.SDtype")
         if sd == 1:
-            return aerosols.MonoModal(kw["-AER.MMD.MRwa"], kw["-AER.MMD.MIwa"], 1, kw["-AER.MMD.LNDradius"], kw["-AER.MMD.LNDvar"])
+            return aerosols.MonoModal(rn, in_, 1, kw["-AER.MMD.LNDradius"], kw["-AER.MMD.LNDvar"])
         if sd == 2:
-            return aerosols.MonoModal(kw["-AER.MMD.MRwa"], kw["-AER.MMD.MIwa"], 2, kw["-AER.MMD.JD.rmin"], kw["-AER.MMD.JD.slope"],
+            return aerosols.MonoModal(rn, in_, 2, kw["-AER.MMD.JD.rmin"], kw["-AER.MMD.JD.slope"],
                                       kw.get("-AER.MMD.JD.rmax", 50.0))             # CTE_DEFAULT_AER_JUNGE_RMAX
         raise ValueError("-AER.MMD.SDtype must be 1 or 2")
     if m == 1:
@@ -105,13 +118,20 @@ def aerosol_model(kw):
             b.cv_coarse, b.cv_fine = kw["-AER.BMD.CoarseVC"], kw["-AER.BMD.FineVC"]
         elif kw.get("-AER.BMD.VCdef") == 2:
             b.rtauct = kw["-AER.BMD.RAOT"]
-            ref = (kw["-AER.BMD.CM.MRwaref"], kw["-AER.BMD.CM.MIwaref"], kw["-AER.BMD.FM.MRwaref"], kw["-AER.BMD.FM.MIwaref"])
-            waref = kw["-AER.Waref"]
+        else:
+            raise ValueError("-AER.BMD.VCdef must be 1 or 2")
+        # SOS_PROC's call of SOS_AEROSOLS at the reference wavelength passes the indices of that wavelength (-AER.BMD.*.M?waref) as
+        # the mode indices, whatever the definition of the mixture (SOS_PROC.F:2896-2907); when the simulation wavelength is the
+        # reference one, the indices of the simulation wavelength are used for both (:1815-1822)
+        keys = ("-AER.BMD.CM.MRwaref", "-AER.BMD.CM.MIwaref", "-AER.BMD.FM.MRwaref", "-AER.BMD.FM.MIwaref")
+        if all(k in kw for k in keys) and not only_ref:
+            ref = tuple(kw[k] for k in keys)
             sim = (b.coarse_rn, b.coarse_in, b.fine_rn, b.fine_in)
             b.coarse_rn, b.coarse_in, b.fine_rn, b.fine_in = (
                 (lambda wa, r=r, s=s: r if wa == waref else s) for r, s in zip(ref, sim))
-        else:
-            raise ValueError("-AER.BMD.VCdef must be 1 or 2")
+        elif b.rtauct is not None and not only_ref:
+            raise ValueError("-AER.BMD.VCdef 2 requires the indices at the reference wavelength, -AER.BMD.CM/FM.MRwaref / MIwaref "
+                             "(SOS_PROC error 2329)")
         return b
     if m == 5:
         if "-AER.DefMixture" not in kw:
@@ -270,7 +290,7 @@ def run(solver, kw, wavelengths=None, gas=None):
             raise ValueError("-AER.Model 4: the simulation wavelength must be the reference wavelength -AER.Waref (SOS_PROC error 2331)")
         aer = [aerosols.external_data(solver, kw["-AER.ExtData"], mie_n, xmu, xhr, os_nb, kw["-AER.Tronca"], wl[0], aot_ref)]
     elif aot_ref > 0.0:
-        aer = aerosols.run(solver, mie_n, xmu, xhr, os_nb, aerosol_model(kw), wl, waref=kw["-AER.Waref"], aot_ref=aot_ref,
+        aer = aerosols.run(solver, mie_n, xmu, xhr, os_nb, aerosol_model(kw, wl), wl, waref=kw["-AER.Waref"], aot_ref=aot_ref,
                            itronc=kw["-AER.Tronca"])
     else:                                                         # no aerosols: PIZ = 0, coefficients 0 (SOS_AEROSOLS.F:1136-1139)
         z = np.zeros(os_nb + 1)

@@ -83,6 +83,21 @@ def test_frontend_host_logic():
               "-AER.BMD.FM.SDradius": 0.08, "-AER.BMD.FM.SDvar": 0.45})
     b = fe.aerosol_model(d)
     assert b.rtauct == 0.4 and b.coarse_rn(0.55) == 1.46 and b.coarse_rn(0.91) == 1.45 and b.fine_in(0.55) == -0.009
+    # the indices of the reference wavelength: used at that wavelength whatever the definition of the mixture (SOS_PROC.F:2896-2907),
+    # ignored when the simulation wavelength IS the reference one (:1815-1822), required otherwise for VCdef 2 (error 2329)
+    b1 = fe.aerosol_model(dict(d, **{"-AER.BMD.VCdef": 1, "-AER.BMD.CoarseVC": 0.3, "-AER.BMD.FineVC": 0.7}), [0.91])
+    assert b1.rtauct is None and b1.cv_coarse == 0.3 and b1.coarse_rn(0.55) == 1.46 and b1.coarse_rn(0.91) == 1.45
+    b2 = fe.aerosol_model(d, [0.55])
+    assert b2.coarse_rn == 1.45 and b2.fine_in == -0.008
+    with pytest.raises(ValueError, match="2329"):
+        fe.aerosol_model({k: v for k, v in d.items() if k != "-AER.BMD.FM.MIwaref"}, [0.91])
+    mono = {"-AER.Model": 0, "-AER.Waref": 0.55, "-AER.MMD.MRwa": 1.45, "-AER.MMD.MIwa": -0.004, "-AER.MMD.SDtype": 1, "-AER.MMD.LNDradius": 0.1,
+            "-AER.MMD.LNDvar": 0.46}
+    assert fe.aerosol_model(mono, [0.55]).rn == 1.45                  # simulation at the reference wavelength: one index
+    with pytest.raises(ValueError, match="2314"):
+        fe.aerosol_model(mono, [0.91])
+    mm = fe.aerosol_model(dict(mono, **{"-AER.MMD.MRwaref": 1.47, "-AER.MMD.MIwaref": -0.006}), [0.91])
+    assert mm.rn(0.55) == 1.47 and mm.rn(0.91) == 1.45 and mm.in_(0.55) == -0.006 and mm.in_(0.91) == -0.004
     d.update({"-AER.Model": 2, "-AER.SF.Model": 3, "-AER.SF.RH": 70.0})
     sf = fe.aerosol_model(d)
     assert isinstance(sf, aer.ShettleFenn) and sf.imodele == 3 and sf.rh == 70.0 and sf.dirfic == "/somewhere/fic"
