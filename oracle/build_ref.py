@@ -24,7 +24,10 @@ FILES = ["SOS_OS.F", "SOS.F", "SOS_AGGREGATE.F", "SOS_TRPHI.F", "SOS_GLITTER.F",
          # N3: Mie theory (SOS_MIE, SOS_FPHASE_MIE); SOS_GRANU and SOS_DECOMPO_LEGENDRE come from SOS_AEROSOLS.F above
          "SOS_MIE.F",
          # N1 rest: the gas atmosphere of a run (standard atmospheres are DATA tables of SOS_SUB_TRS.F)
-         "SOS_PREPA_ABSPROFILE.F"]
+         "SOS_PREPA_ABSPROFILE.F",
+         # the whole run: the entry binding/run_sos.py calls (SOS_PROC) with SOS_PREPA_OS and the surface file names, so that the keyword
+         # front end can be compared with the reference's own driver from its arguments to its result files
+         "SOS_PROC.F", "SOS_PREPA_OS.F", "SOS_NOM_FIC_SURFACE.F"]
 
 
 def build(force=False, verbose=True):

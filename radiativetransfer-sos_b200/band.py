@@ -80,13 +80,29 @@ def enumerate_ckd_terms(nexp, kdis_ai, lamb1):
     return iks, [a / s for a in aik]
 
 
+def estimated_absorption(aik, tau):
+    """-SOS.AbsModeCKD 2: the absorption profile of ONE solve from the CKD terms of an interval (SOS_PROC.F:3613-3662):
+    TRSCKD(I) = sum over the terms, in loop order, of AIK exp(-TAUABS(I)); TAUABS(I) = -log TRSCKD(I), negative values set to 0.
+    aik [nterm], tau [nterm, 50] -> [50]."""
+    trs = np.zeros(tau.shape[1])
+    for a, t in zip(aik, tau):
+        trs = trs + a * np.exp(-t)
+    est = -np.log(trs)
+    est[est < 0.0] = 0.0
+    return est
+
+
 def run_band(solver, tables, kdis_ai, userprofil, altabs, ro, waves, itrphi=1, phios=0.0, pas_phi=30, outdir=None,
-             trans=False, flux=False):
+             trans=False, flux=False, ckd_mode=1):
     """Runs the band.  tables: CKD tables as READ_CKD_COEFF fills them (dict, Fortran-ordered: nb_temp, nb_pres, nb_conc,
     tab_temp, tab_pres, tab_conc, nexp, ki, kh) -- or a list of such dicts, one per wavelength (the same object for wavelengths of the
     same coefficient file); kdis_ai: KDIS_AI(5,8,50) (or the list of them); userprofil / altabs / ro: the gas atmosphere of
     SOS_PREPA_ABSPROFILE.  With outdir, wavelength w gets outdir/<name or index>/SOS_Up.txt, SOS_Down.txt, SOS_Result.bin and,
-    on request, SOS_Trans.txt / SOS_Flux.txt."""
+    on request, SOS_Trans.txt / SOS_Flux.txt.  ckd_mode: -SOS.AbsModeCKD, 1 = one solve per CKD term and the AIK-weighted sum
+    (SOS_PROC.F:3454-3600), 2 = one solve per wavelength on the absorption profile estimated from its CKD terms (:3609-3716);
+    a wavelength without gaseous absorption is one solve in either mode (:2366)."""
+    if ckd_mode not in (1, 2):
+        raise ValueError("-SOS.AbsModeCKD must be 1 or 2 (SOS_PROC error 2515)")
     res = BandResult()
     pterms, aiks, owner = [], [], []
     # tables / kdis_ai: one set for the band, or a list with one entry per wavelength (a band that spans several CKD coefficient
@@ -129,6 +145,18 @@ def run_band(solver, tables, kdis_ai, userprofil, altabs, ro, waves, itrphi=1, p
     if ier.any():
         bad = int(np.flatnonzero(ier)[0])
         raise RuntimeError("profile chain: term %d of wavelength %d failed with code %d" % (bad, owner[bad], int(ier[bad])))
+    if ckd_mode == 2 and tables is not None:
+        # one solve per wavelength: the per-term absorption profiles (device) -> estimated profile (host, 50 levels per wavelength)
+        # -> SOS_PROFILE for one term per wavelength (device).  The per-term profiles of the chain above are not used.
+        first = np.cumsum([0] + res.nterm)
+        tau = np.array([estimated_absorption(aiks[first[w]:first[w + 1]], tau[first[w]:first[w + 1]]) if wv.absprofil != 7
+                        else tau[first[w]] for w, wv in enumerate(waves)])
+        pterms = [pterms[first[w]] for w in range(len(waves))]
+        aiks, owner, res.nterm = [1.0] * len(waves), list(range(len(waves))), [1] * len(waves)
+        nt, z, h, pa, pm, ier = solver.profile(altabs, tau, pterms, text_hop=True)
+        if ier.any():
+            bad = int(np.flatnonzero(ier)[0])
+            raise RuntimeError("profile of wavelength %d (estimated absorption) failed with code %d" % (bad, int(ier[bad])))
     res.nt = nt
     # ---- term-solves, CKD sums, synthesis (device) ----
     wl = Workload("band")

@@ -265,6 +265,8 @@ def run(solver, kw, wavelengths=None, gas=None):
     absprofil = kw["-AP.AbsProfile.Type"]
     if absprofil != 7 and kw["-AP.AerProfile.Type"] == 2:
         raise ValueError("an aerosol layer profile (-AP.AerProfile.Type 2) goes with -AP.AbsProfile.Type 7 only (SOS_PROC error 2513)")
+    if absprofil != 7 and kw.get("-SOS.AbsModeCKD") not in (1, 2):
+        raise ValueError("-AP.AbsProfile.Type %d requires -SOS.AbsModeCKD 1 or 2 (SOS_PROC error 2515)" % absprofil)
     if absprofil != 7 and gas is None:
         # SOS_PREPA_ABSPROFILE: the user's profile file (type 0) or a predefined atmosphere (1 .. 6, tables read from the user's
         # installation of the reference), the CKD coefficient files of $SOS_ABS_ROOT/fic/COEFF_CKD
@@ -315,7 +317,8 @@ def run(solver, kw, wavelengths=None, gas=None):
     g = gas or {}
     res = band.run_band(solver, g.get("tables"), g.get("kdis_ai"), g.get("userprofil"), g.get("altabs"), g.get("ro"), waves,
                         itrphi=kw["-SOS.View"], phios=kw.get("-SOS.View.Phi", 0.0), pas_phi=kw.get("-SOS.View.Dphi", 30),
-                        outdir=os.path.join(root, "SOS"), trans="-SOS.Trans" in kw, flux="-SOS.Flux" in kw and gas is not None)
+                        outdir=os.path.join(root, "SOS"), trans="-SOS.Trans" in kw, flux="-SOS.Flux" in kw and gas is not None,
+                        ckd_mode=(kw.get("-SOS.AbsModeCKD", 1) if absprofil != 7 else 1))
     # ---- the reference's file names ----
     names = {"SOS_Up.txt": kw["-SOS.ResFileUp"], "SOS_Down.txt": kw["-SOS.ResFileDown"], "SOS_Result.bin": kw["-SOS.ResBin"],
              "SOS_Trans.txt": kw.get("-SOS.Trans"), "SOS_Flux.txt": kw.get("-SOS.Flux")}

@@ -206,3 +206,51 @@ def profile(ref, tmp, altabs, tabs, term):
         return ier.value, 0, b"", None, None, None, None
     text = open(f, "rb").read()
     return (0, nt.value, text) + read_profile_file(f)
+
+
+# ---- the whole run: SOS_PROC (SOS_PROC.F:415-481), the entry binding/run_sos.py calls through f2py ----
+_SOS_PROC_DEFAULTS = dict(
+    resroot="UNDEFINED_REPERTORY", ficmain_log="NO_LOG_FILE", ficangles_user_lum="NO_USER_ANGLES", ficangles_res_lum="SOS_UsedAngles.txt",
+    ficangles_user_mie="NO_USER_ANGLES", ficangles_res_mie="Aer_UsedAngles.txt", ficanglog="NO_LOG_FILE", itronc_aer=1, ficgranu_log="NO_LOG_FILE",
+    ficmie_log="NO_LOG_FILE", dir_mie="UNDEFINED_REPERTORY", ficgranu="Aerosols.txt", jd_rmax_mmd_aer=50.0,
+    ficextdata_aer="NO_USER_AEROSOLS_PHAZE_FCT", ficmixture_aer="NO_USER_AEROSOLS_MIXTURE", ficuser_aer="NO_USER_AEROSOLS",
+    ficprofil_log="NO_LOG_FILE", psurf=1013.0, ficabsprofil="NO_USER_ABS_PROFILE_FILE", dir_surf="UNDEFINED_REPERTORY", ficsurf_log="NO_LOG_FILE",
+    ficsurf="DEFAULT", ficsos_log="NO_LOG_FILE", ficsos_res_bin="SOS_Result.bin", fictrans="NO_OUTPUT", ficflux="NO_OUTPUT", zout=-1.0, igmax=100,
+    ipolar=1, ier=0, trace=0)                                    # the initial values of SOS_ABS_MAIN.F:1280-1470
+
+
+def sos_proc(ref, **given):
+    """SOS_PROC of the reference library with the arguments of the f2py wrapper by name (radiativetransfer-sos_b200/sos.py: ARGS);
+    arguments not given keep the values SOS_ABS_MAIN initialises them with ("not defined" = -999).  Returns (IER, the 23 outputs in
+    the wrapper's order: tables as [361, 81] = X_FIN(0:360, 0:80) transposed to (azimuth, angle))."""
+    import importlib
+    sos = importlib.import_module("radiativetransfer-sos_b200.sos")
+    kwm = importlib.import_module("radiativetransfer-sos_b200.keywords")
+    args, lens, keep = [], [], []
+    ier = C.c_int(0)
+    for name, key in sos.ARGS:
+        v = given.get(name, _SOS_PROC_DEFAULTS.get(name))
+        t = kwm.KEYWORDS[key] if key else "i"
+        if name == "ier":
+            args.append(C.byref(ier))
+        elif t == "s":
+            b = _fs(str(v) if v is not None else "UNDEFINED")
+            keep.append(b)
+            args.append(b)
+            lens.append(_L)
+        elif t == "i":
+            c = C.c_int(int(v) if v is not None else -999)
+            keep.append(c)
+            args.append(C.byref(c))
+        else:
+            c = C.c_double(float(v) if v is not None else -999.0)
+            keep.append(c)
+            args.append(C.byref(c))
+    nb = C.c_int(0)
+    ind = np.zeros(MX + 1, dtype=np.int32)
+    phi, theta = np.zeros(361), np.zeros(MX + 1)
+    tabs = [np.zeros((MX + 1, 361)) for _ in range(14)]          # Fortran X_FIN(0:360, 0:80): azimuth fastest
+    sc = [C.c_double(0) for _ in range(5)]
+    ref.sos_proc_(*args, C.byref(nb), ind.ctypes.data_as(C.POINTER(C.c_int)), _P(phi), _P(theta), *[_P(t) for t in tabs],
+                  *[C.byref(s) for s in sc], *lens)
+    return ier.value, (nb.value, ind, phi, theta, *[t.T.copy() for t in tabs], *[s.value for s in sc])
