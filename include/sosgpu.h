@@ -168,6 +168,12 @@ int sosgpu_batch_reduce_groups(sosgpu_ctx *ctx, sosgpu_batch *batch, int root);
 int sosgpu_batch_groups(sosgpu_ctx *ctx, sosgpu_batch *batch, int rec_stride, int wmax, sosgpu_group_out *group_out);
 /* optics entry (index into the uploaded optics array) of every group: needed on a rank that owns no term of a group */
 int sosgpu_batch_set_group_optics(sosgpu_batch *batch, const int *optics_of_group);
+/* direct[ngroup]: non-zero for a group that is ONE solve whose result the reference does not pass through SOS_AGGREGATE --
+ * a wavelength without gaseous absorption or -SOS.AbsModeCKD 2 (SOS_PROC.F:2366, 3609-3716: SOS writes FICSOS_RES_BIN itself and
+ * SOS_TRPHI_OPTION gets SOS's own TTOT_TRONC / TAUOUT).  Such a group's optical thicknesses are then the term's own instead of
+ * -log(1 * exp(-tau)) (SOS_AGGREGATE.F:467-488), which differs in the last bit.  Ignored for groups of several terms and after
+ * sosgpu_batch_reduce_groups (a reduced band sum is an aggregate). */
+int sosgpu_batch_set_group_direct(sosgpu_batch *batch, const int *direct);
 /* Wavelength-sharded layout (every rank owns whole wavelengths; no reduce): collects the tables of the last
  * sosgpu_batch_trphi call of every rank on `root`, in rank order, with one grouped ncclSend/ncclRecv.
  * groups_of_rank[nranks]; up/down (root; may be NULL): [sum of groups][7][nphi][nmax]. */

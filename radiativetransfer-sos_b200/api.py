@@ -126,6 +126,7 @@ def load_library():
         lib.sosgpu_batch_reduce_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         lib.sosgpu_batch_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(CGroupOut)]
         lib.sosgpu_batch_set_group_optics.argtypes = [C.c_void_p, c_ip]
+        lib.sosgpu_batch_set_group_direct.argtypes = [C.c_void_p, c_ip]
         lib.sosgpu_batch_gather_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_ip, C.c_int, C.c_int, c_dp, c_dp]
         _lib = lib
     return _lib
@@ -403,6 +404,14 @@ class Solver:
     def set_group_optics(self, batch, optics_of_group):
         a = np.ascontiguousarray(optics_of_group, dtype=np.int32)
         self._check(self.lib.sosgpu_batch_set_group_optics(batch.handle, a.ctypes.data_as(c_ip)), "set_group_optics")
+
+    def set_group_direct(self, batch, direct):
+        """Groups that are one solve the reference does not pass through SOS_AGGREGATE (no gas, -SOS.AbsModeCKD 2): their optical
+        thicknesses are the term's own (include/sosgpu.h: sosgpu_batch_set_group_direct)."""
+        a = np.ascontiguousarray(direct, dtype=np.int32)
+        if a.size != batch.ngroup:
+            raise ValueError("set_group_direct: one flag per group")
+        self._check(self.lib.sosgpu_batch_set_group_direct(batch.handle, a.ctypes.data_as(c_ip)), "set_group_direct")
 
     def reduce_groups(self, batch, root=0):
         """Term-sharded layout: ONE in-place ncclReduce of the partial CKD sums + group metadata to `root`."""

@@ -166,6 +166,10 @@ def run_band(solver, tables, kdis_ai, userprofil, altabs, ro, waves, itrphi=1, p
         wl.terms.append(Term(w, aiks[i], z[i, :n].copy(), h[i, :n].copy(), pa[i, :n].copy(), pm[i, :n].copy()))
     batch = solver.upload(wl, groups=owner, ngroup=len(waves))
     try:
+        # one solve that SOS_PROC does not aggregate (no gas: SOS_PROC.F:2366; mode 2: :3700-3708): SOS's own optical thicknesses
+        direct = [int(n == 1 and (wv.absprofil == 7 or ckd_mode == 2)) for n, wv in zip(res.nterm, waves)]
+        if any(direct):
+            solver.set_group_direct(batch, direct)
         _, gr = solver.run(batch, want_terms=False, want_groups=True)
         res.groups = gr
         o0 = waves[0].optics

@@ -854,7 +854,9 @@ static int download(sosgpu_ctx *ctx, sosgpu_batch *b, int rec_stride, int wmax, 
         const double aik = b->ht[i].aik;
         emg = emg + aik * em[i];
         epg = epg + aik * ep[i];
-        if (part_only) {
+        if (!part_only && b->is_direct(g)) {                     // one solve, no SOS_AGGREGATE: the values of SOS itself
+          tt = b->ht[i].ttot_tronc; tv = b->ht[i].ttot_vrai; to_ = b->ht[i].tauout;
+        } else if (part_only) {
           tt += aik * std::exp(-b->ht[i].ttot_tronc); tv += aik * std::exp(-b->ht[i].ttot_vrai);
           to_ += aik * std::exp(-b->ht[i].tauout);
         } else {
@@ -912,6 +914,13 @@ extern "C" int sosgpu_group_finalize(double *ttot_tronc, double *ttot_vrai, doub
   return SOSGPU_OK;
 }
 
+extern "C" int sosgpu_batch_set_group_direct(sosgpu_batch *b, const int *direct)
+{
+  if (!b || !direct) return SOSGPU_ERR_ARG;
+  b->group_direct.assign(direct, direct + b->ngroup);
+  return SOSGPU_OK;
+}
+
 extern "C" int sosgpu_batch_group_buffer(sosgpu_batch *b, void **dev_ptr, size_t *n_doubles)
 {
   if (!b || !dev_ptr || !n_doubles) return SOSGPU_ERR_ARG;
@@ -953,6 +962,7 @@ extern "C" int sosgpu_batch_trphi(sosgpu_ctx *ctx, sosgpu_batch *b, int igli, do
     double tt = 0.0, to_ = 0.0;
     const int opt = b->group_optics[g];
     if (b->reduced) { tt = b->g_tt[g]; to_ = b->g_to[g]; }       // band-wide values after sosgpu_batch_reduce_groups
+    else if (b->is_direct(g)) { const HostTerm &ht = b->ht[b->group_terms[b->group_start[g]]]; tt = ht.ttot_tronc; to_ = ht.tauout; }
     else
       for (int x = b->group_start[g]; x < b->group_start[g + 1]; ++x) {   // SOS_AGGREGATE.F:467-488, term order
         const HostTerm &ht = b->ht[b->group_terms[x]];

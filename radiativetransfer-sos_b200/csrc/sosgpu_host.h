@@ -109,6 +109,9 @@ struct sosgpu_batch {
   // multi-GPU (sosgpu_comm.cu): optics entry of every group (default: first local term's), and the band-wide group
   // metadata after sosgpu_batch_reduce_groups (sums of a*exp(-tau), fluxes, longest series)
   std::vector<int> group_optics;
+  // groups SOS_PROC solves once and does not pass through SOS_AGGREGATE (sosgpu_batch_set_group_direct)
+  std::vector<char> group_direct;
+  bool is_direct(int g) const { return (size_t)g < group_direct.size() && group_direct[g] && group_start[g + 1] - group_start[g] == 1; }
   bool reduced = false;
   std::vector<double> g_em, g_ep, g_tt, g_tv, g_to;
   std::vector<int> g_nrec;

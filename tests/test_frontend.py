@@ -431,6 +431,9 @@ class _StubSolver:
                 outer.calls.append(("free",))
         return B()
 
+    def set_group_direct(self, batch, direct):
+        self.calls.append(("direct_groups", list(direct)))
+
     def run(self, batch, want_terms=True, want_groups=True):
         g, w = batch.ngroup, batch.wmax
 
