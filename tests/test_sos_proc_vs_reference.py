@@ -234,8 +234,10 @@ def test_gpu_sos_proc_against_the_reference_driver(solver, tmp_path, case):
     np.testing.assert_allclose(got[3], want[3], rtol=1e-13, atol=0, err_msg="THETA_FIN")
     a = fm.read_result_bin(os.path.join(tmp, "gpu", "SOS", "%.6f" % {**ARGS, **more}["wa_simu"], "SOS_Result.bin"), n)
     b = fm.read_result_bin(os.path.join(root, "SOS", "SOS_Result.bin"), n)
-    nb = b.shape[0] - (0 if b[-1].any() else 1)                   # SOS_AGGREGATE ends its file with a record of zeros
-    assert a.shape[0] in (nb, b.shape[0]) and not a[nb:].any(), "number of Fourier orders: %d, reference %d" % (a.shape[0], nb)
+    # every SOS_AGGREGATE call after the first ends its file with one more record of zeros (both inputs at their end, :372-393):
+    # the driver's file of K aggregated terms carries K - 1 of them after the longest series; the front end's file ends there
+    nb = int(np.flatnonzero(b.reshape(b.shape[0], -1).any(axis=1))[-1]) + 1
+    assert a.shape[0] >= nb and not a[nb:].any(), "number of Fourier orders: %d, reference %d" % (a.shape[0], nb)
     err = float(np.abs(a[:nb] - b[:nb]).max() / np.abs(b).max())
     assert err < 5e-6, err                                        # the aerosol thickness goes through REAL*4 Mie records (2e-7)
     worst = 0.0
@@ -319,3 +321,68 @@ def test_run_band_ckd_mode_2_host_flow(pkg, tmp_path):
     assert abs(got - tau2[0][-1]) < 5e-5
     with pytest.raises(ValueError, match="2515"):
         band.run_band(s2, t, t["ai"], user, altabs, ro, waves, ckd_mode=3)
+
+
+from test_aerosol_chain import host  # noqa: E402,F401  (fixture: the aerosol device functions compiled for the host)
+
+_LAND = dict(isurf=5, rho=0.0, k0_roujean=0.25, k1_roujean=0.04, k2_roujean=0.3, surf_ind=1.5)
+_FRONT_END_CASES = {
+    "ocean_wmo_view2": {},
+    "ocean_view1_phi30_unpolarized": dict(itrphi=1, phios=30.0, ipolar=0, igmax=6),
+    "land_roujean_breon_lnd": dict(_LAND, imod_aer=0, rn_wa=1.45, in_wa=-0.005, rn_waref=1.45, in_waref=-0.005, igranu=1,
+                                   lnd_radius_mmd_aer=0.12, lnd_lnvar_mmd_aer=0.5, wa_simu=0.670),
+    "lambert_flat_sea_no_aerosols": dict(isurf=2, rho=0.03, aot_ref=0.0, zout=3.0),
+    "gas_mode1_lambert": dict(isurf=0, rho=0.2, gas=1),
+    "gas_mode2_lambert": dict(isurf=0, rho=0.2, gas=2),
+}
+
+
+@pytest.mark.parametrize("name", list(_FRONT_END_CASES))
+def test_front_end_host_logic_is_the_drivers(pkg, host, tmp_path, name):
+    """sos.sos_proc -> frontend.run -> band.run_band with every device stage replaced by the reference's own routine
+    (tests/reference_flow_solver.py) against SOS_PROC itself on the same arguments: the 23 outputs BIT FOR BIT, the aerosol file line
+    by line, SOS_Result.bin record by record.  What is compared is the host side of the product: keyword mapping, reference-wavelength
+    scaling of the optical thickness, the result-file hop of the coefficients, Rayleigh thickness, CKD term lists / weights / modes,
+    aggregated and direct groups, direct-term models, output layout."""
+    import profile_cases as pc
+    import test_absprofile as tab
+    from reference_flow_solver import ReferenceFlowSolver
+    sos = importlib.import_module("radiativetransfer-sos_b200.sos")
+    fm = importlib.import_module("radiativetransfer-sos_b200.formats")
+    ref = refdirect.lib()
+    if ref is None or not hasattr(ref, "sos_proc_"):
+        pytest.skip("oracle/_ref without SOS_PROC")
+    tmp = str(tmp_path)
+    _installation(tmp)
+    more = dict(_FRONT_END_CASES[name])
+    gas = more.pop("gas", None)
+    if gas:
+        pc.write_ckd_files(os.environ["SOS_ABS_ROOT"], pc.ckd_tables(4))
+        fprof = os.path.join(tmp, "profile.txt")
+        tab._write_profile(fprof, tab._user())
+        more.update(wa_simu=1e4 / 13255.0, absprofil=0, ficabsprofil=fprof, nustep=10.0, imode_ckd_calcul=gas)
+    args = {**ARGS, **more}
+    root, want = _driver(ref, tmp, **more)
+    _, ga, _, _ = pkg.synth.sos_angles(args["nbmu_gauss_lum"], args["tetas"])
+    s = ReferenceFlowSolver(host, ref, tmp_path, ga)
+    got = sos.sos_proc(solver=s, resroot=os.path.join(tmp, "mine"), trace=False, **args)
+    assert len(got) == len(want) == 23
+    names = ("NBMU", "IND_ANGOUT", "PHI", "THETA") + tuple("%s_%s" % (t, d) for d in ("UP", "DOWN") for t in
+                                                           ("SCA", "I", "Q", "U", "POL_ANG", "POL_RATE", "L_POL")) + ("TDIR", "FDD", "FD", "EPLUS", "COEF_TRONCA")
+    for k, (g, w) in enumerate(zip(got, want)):
+        if names[k] == "THETA":                                   # acos of the Gauss cosines: numpy's against the reference's DACOS
+            np.testing.assert_allclose(g, w, rtol=1e-14, atol=0)
+        elif names[k] in ("TDIR", "FDD", "FD"):                   # exp / division of identical inputs by the product's own writer
+            assert abs(g - w) <= 2e-16 * max(1.0, abs(w)), (names[k], g, w)
+        else:
+            assert np.array_equal(np.asarray(g), np.asarray(w)), (name, names[k], np.abs(np.asarray(g) - np.asarray(w)).max())
+    a = fm.read_result_bin(os.path.join(tmp, "mine", "SOS", "%.6f" % args["wa_simu"], "SOS_Result.bin"), want[0])
+    b = fm.read_result_bin(os.path.join(root, "SOS", "SOS_Result.bin"), want[0])
+    nb = int(np.flatnonzero(b.reshape(b.shape[0], -1).any(axis=1))[-1]) + 1
+    assert a.shape[0] == nb and np.array_equal(a, b[:nb])
+    if args["aot_ref"] > 0.0:
+        la = open(os.path.join(root, "SOS", "Aerosols.txt")).read().split("\n")
+        lb = open(os.path.join(tmp, "mine", "AER", "Aerosols.txt")).read().split("\n")
+        assert la == lb, [(x, y) for x, y in zip(la, lb) if x != y][:3]
+    print("\n[front end = driver] %s: 23 outputs bit for bit, SOS_Result.bin %d records (+ %d of zeros in the driver's file), E+ %.8f"
+          % (name, nb, b.shape[0] - nb, want[21]))
