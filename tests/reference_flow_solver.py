@@ -40,13 +40,27 @@ class ReferenceFlowSolver(HostSolver):
         self.direct = dict(roujean=roujean, bpdf=dict(irondeaux=irondeaux, ibreon=ibreon, imaignan=int(maignan is not None),
                                                       coef=0.0 if maignan is None else maignan))
 
+    def _fresh_library(self):
+        import ctypes
+        import os
+        import shutil
+        self.ncopy = getattr(self, "ncopy", 0) + 1
+        dst = os.path.join(self.tmp, "libsosref_copy%d.so" % self.ncopy)
+        shutil.copy(refdirect.runner().LIB, dst)
+        return ctypes.CDLL(dst)
+
     # ---- profiles (SOS_ABSPROFILE, SOS_PROFILE and the PROFIL_TMP hop) ----
     def profile(self, altabs, tau, terms, text_hop=True):
         n = len(terms)
         nt, ier = np.zeros(n, np.int32), np.zeros(n, np.int32)
         z, h, pa, pm = (np.zeros((n, 601)) for _ in range(4))
         for i, t in enumerate(terms):
-            e, k, _, zz, hh, aa, mm = refdirect.profile(self.ref, self.tmp, np.asarray(altabs), np.asarray(tau)[i], t)
+            # the layer branch of SOS_PROFILE starts its Rayleigh sums from Hmol(0) without setting it (SOS_PROFIL.F:873, set at
+            # :926 only): a second call in one process starts from the previous call's top-of-atmosphere value (3e-7 TR) instead of
+            # the zeroed storage the driver's single call -- and the product, csrc/profile_chain.cuh -- start from.  A fresh copy of
+            # the library has fresh storage.
+            lib = self._fresh_library() if t["iprofil"] == 2 else self.ref
+            e, k, _, zz, hh, aa, mm = refdirect.profile(lib, self.tmp, np.asarray(altabs), np.asarray(tau)[i], t)
             ier[i] = e
             if e == 0:
                 nt[i] = k

@@ -25,6 +25,7 @@ def _installation(tmp):
     """A stand-in for the user's installation of the reference ($SOS_ABS_ROOT/fic with the WMO data file)."""
     os.makedirs(os.path.join(tmp, "abs_root", "fic"), exist_ok=True)
     os.environ["SOS_ABS_ROOT"] = os.path.join(tmp, "abs_root")
+    ac.write_sf_files(os.path.join(os.environ["SOS_ABS_ROOT"], "fic"))
     return ac.write_wmo_file(os.path.join(os.environ["SOS_ABS_ROOT"], "fic", "Data_WMO_cor_2015_12_16"))
 
 
@@ -332,6 +333,19 @@ _FRONT_END_CASES = {
     "land_roujean_breon_lnd": dict(_LAND, imod_aer=0, rn_wa=1.45, in_wa=-0.005, rn_waref=1.45, in_waref=-0.005, igranu=1,
                                    lnd_radius_mmd_aer=0.12, lnd_lnvar_mmd_aer=0.5, wa_simu=0.670),
     "lambert_flat_sea_no_aerosols": dict(isurf=2, rho=0.03, aot_ref=0.0, zout=3.0),
+    "roujean_only_junge_no_truncation": dict(isurf=3, rho=0.0, k0_roujean=0.3, k1_roujean=0.05, k2_roujean=0.4, imod_aer=0, rn_wa=1.40, in_wa=-0.002,
+                                             rn_waref=1.42, in_waref=-0.001, igranu=2, jd_slope_mmd_aer=4.0, jd_rmin_mmd_aer=0.05,
+                                             jd_rmax_mmd_aer=10.0, itronc_aer=0, tetas=50.0),
+    "rondeaux_shettle_fenn": dict(_LAND, isurf=4, imod_aer=2, imodele_sf=2, rh=70.0, wa_simu=0.865, psurf=950.0, hr=7.5, ha=1.5),
+    "maignan_bimodal_volumes": dict(_LAND, isurf=7, coef_c_maignan=6.5, imod_aer=3, mode_param_bilnd=1, user_cv_coarse=0.02, user_cv_fine=0.01,
+                                    bmd_cm_mrwa=1.50, bmd_cm_miwa=-0.003, bmd_cm_mrwaref=1.50, bmd_cm_miwaref=-0.003, bmd_cm_rmodal=0.8,
+                                    bmd_cm_var=0.6, bmd_fm_mrwa=1.43, bmd_fm_miwa=-0.005, bmd_fm_mrwaref=1.44, bmd_fm_miwaref=-0.005,
+                                    bmd_fm_rmodal=0.08, bmd_fm_var=0.45),
+    "bimodal_share_aerosol_layer_given_rayleigh": dict(imod_aer=3, mode_param_bilnd=2, rtauct_waref=0.4, bmd_cm_mrwa=1.50, bmd_cm_miwa=-0.003,
+                                                       bmd_cm_mrwaref=1.50, bmd_cm_miwaref=-0.003, bmd_cm_rmodal=0.8, bmd_cm_var=0.6,
+                                                       bmd_fm_mrwa=1.43, bmd_fm_miwa=-0.005, bmd_fm_mrwaref=1.44, bmd_fm_miwaref=-0.005,
+                                                       bmd_fm_rmodal=0.08, bmd_fm_var=0.45, iprofil=2, zmin=1.0, zmax=3.0, tr=0.05),
+    "wmo_user_volumes": dict(imodele_wmo=4, c_wmo_dl=0.2, c_wmo_ws=0.3, c_wmo_oc=0.4, c_wmo_so=0.1, isurf=0, rho=0.1),
     "gas_mode1_lambert": dict(isurf=0, rho=0.2, gas=1),
     "gas_mode2_lambert": dict(isurf=0, rho=0.2, gas=2),
 }
