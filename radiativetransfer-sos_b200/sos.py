@@ -117,4 +117,7 @@ def sos_proc(*args, solver=None, gas=None, **kwargs):
     g = res.groups
     tdir, fdd, fd = api.write_flux("NO_OUTPUT", kw["-ANG.Thetas"], float(g.ttot_tronc[0]), float(g.ttot_vrai[0]), float(g.emoins[0]),
                                    float(g.eplus[0]), 0.0, 8.0, 0.0, 2.0, np.zeros(50), np.zeros(50))
-    return (n, ind, phi, vza, *tabs, tdir, fdd, fd, float(g.eplus[0]), float(aer[0].coef_tronca))
+    # COEF_TRONCA is an output of the SOS_AEROSOLS calls (SOS_PROC.F:2912, 3047): with a user aerosol file there is none and the
+    # wrapper hands back its initial 0, not the coefficient read from the file
+    ct = 0.0 if "-AER.UserFile" in kw else float(aer[0].coef_tronca)
+    return (n, ind, phi, vza, *tabs, tdir, fdd, fd, float(g.eplus[0]), ct)

@@ -346,6 +346,8 @@ _FRONT_END_CASES = {
                                                        bmd_fm_mrwa=1.43, bmd_fm_miwa=-0.005, bmd_fm_mrwaref=1.44, bmd_fm_miwaref=-0.005,
                                                        bmd_fm_rmodal=0.08, bmd_fm_var=0.45, iprofil=2, zmin=1.0, zmax=3.0, tr=0.05),
     "wmo_user_volumes": dict(imodele_wmo=4, c_wmo_dl=0.2, c_wmo_ws=0.3, c_wmo_oc=0.4, c_wmo_so=0.1, isurf=0, rho=0.1),
+    "user_angle_files": dict(user_angles=[5.0, 20.5, 60.0], user_mie_angles=[10.0, 75.0]),
+    "aerosol_and_surface_files_of_the_user": dict(from_files=True, wa_simu=0.55),
     "gas_mode1_lambert": dict(isurf=0, rho=0.2, gas=1),
     "gas_mode2_lambert": dict(isurf=0, rho=0.2, gas=2),
 }
@@ -370,14 +372,34 @@ def test_front_end_host_logic_is_the_drivers(pkg, host, tmp_path, name):
     _installation(tmp)
     more = dict(_FRONT_END_CASES[name])
     gas = more.pop("gas", None)
+    user = more.pop("user_angles", [])
+    for key, arg, fname in (("user_angles", "ficangles_user_lum", "rad_angles.txt"), ("user_mie_angles", "ficangles_user_mie", "mie_angles.txt")):
+        angles = user if key == "user_angles" else more.pop(key, [])
+        if angles:
+            with open(os.path.join(tmp, fname), "w") as f:
+                f.write("".join("%.2f\n" % a for a in angles))
+            more[arg] = os.path.join(tmp, fname)
     if gas:
         pc.write_ckd_files(os.environ["SOS_ABS_ROOT"], pc.ckd_tables(4))
         fprof = os.path.join(tmp, "profile.txt")
         tab._write_profile(fprof, tab._user())
         more.update(wa_simu=1e4 / 13255.0, absprofil=0, ficabsprofil=fprof, nustep=10.0, imode_ckd_calcul=gas)
-    args = {**ARGS, **more}
-    root, want = _driver(ref, tmp, **more)
-    _, ga, _, _ = pkg.synth.sos_angles(args["nbmu_gauss_lum"], args["tetas"])
+    if more.pop("from_files", False):
+        # -AER.UserFile and -SURF.File: the aerosol file and the surface file a first run of the driver leaves behind, given back
+        # to both sides as the user's files (SOS_PROC.F:1867-1876, 3186-3189)
+        first, _ = _driver(ref, tmp, **more)
+        import glob
+        import shutil
+        (fsurf,) = glob.glob(os.path.join(first, "SURF", "GLITTER", "*")) or glob.glob(os.path.join(first, "SURF", "*", "*"))
+        shutil.copy(os.path.join(first, "SOS", "Aerosols.txt"), os.path.join(tmp, "user_aerosols.txt"))
+        shutil.copy(fsurf, os.path.join(tmp, "user_surface.bin"))
+        shutil.rmtree(first)
+        more.update(ficuser_aer=os.path.join(tmp, "user_aerosols.txt"), ficsurf=os.path.join(tmp, "user_surface.bin"), ficgranu=None)
+        for k in ("imod_aer", "imodele_wmo"):
+            more[k] = None
+    args = {k: v for k, v in {**ARGS, **more}.items() if v is not None}
+    root, want = _driver(ref, tmp, **{k: v for k, v in more.items() if v is not None or k in ARGS})
+    _, ga, _, _ = pkg.synth.sos_angles(args["nbmu_gauss_lum"], args["tetas"], user)
     s = ReferenceFlowSolver(host, ref, tmp_path, ga)
     got = sos.sos_proc(solver=s, resroot=os.path.join(tmp, "mine"), trace=False, **args)
     assert len(got) == len(want) == 23
@@ -394,7 +416,9 @@ def test_front_end_host_logic_is_the_drivers(pkg, host, tmp_path, name):
     b = fm.read_result_bin(os.path.join(root, "SOS", "SOS_Result.bin"), want[0])
     nb = int(np.flatnonzero(b.reshape(b.shape[0], -1).any(axis=1))[-1]) + 1
     assert a.shape[0] == nb and np.array_equal(a, b[:nb])
-    if args["aot_ref"] > 0.0:
+    if "ficuser_aer" in args:                                     # no aerosol computation, no aerosol file on either side
+        assert not os.path.exists(os.path.join(root, "SOS", "Aerosols.txt")) and not os.path.isdir(os.path.join(tmp, "mine", "AER"))
+    elif args["aot_ref"] > 0.0:
         la = open(os.path.join(root, "SOS", "Aerosols.txt")).read().split("\n")
         lb = open(os.path.join(tmp, "mine", "AER", "Aerosols.txt")).read().split("\n")
         assert la == lb, [(x, y) for x, y in zip(la, lb) if x != y][:3]
