@@ -113,7 +113,7 @@ def _one_after_the_other(ref, pkg, tmp, wmo, wa, gas=None, mode=2):
         assert ier_r == 0
         wl.terms.append(syn.Term(0, a, z_r, h_r, pa_r, pm_r))
     rr = refdirect.runner()
-    r, _, _ = rr.solve_terms(wl, list(range(len(terms))), 1)
+    r, _, _ = rr.solve_terms(wl, list(range(len(terms))), min(8, os.cpu_count() or 1))
     if len(terms) == 1 and (gas is None or mode == 2):            # one solve, no SOS_AGGREGATE (SOS_PROC.F:3700-3708)
         rec, sc = r[0]["rec"], {k: r[0][k] for k in ("ttot_tronc", "ttot_vrai", "tauout", "emoins", "eplus")}
     else:
@@ -345,7 +345,7 @@ _FRONT_END_CASES = {
                                                        bmd_cm_mrwaref=1.50, bmd_cm_miwaref=-0.003, bmd_cm_rmodal=0.8, bmd_cm_var=0.6,
                                                        bmd_fm_mrwa=1.43, bmd_fm_miwa=-0.005, bmd_fm_mrwaref=1.44, bmd_fm_miwaref=-0.005,
                                                        bmd_fm_rmodal=0.08, bmd_fm_var=0.45, iprofil=2, zmin=1.0, zmax=3.0, tr=0.05),
-    "wmo_user_volumes": dict(imodele_wmo=4, c_wmo_dl=0.2, c_wmo_ws=0.3, c_wmo_oc=0.4, c_wmo_so=0.1, isurf=0, rho=0.1),
+    "wmo_user_volumes": dict(imodele_wmo=4, c_wmo_dl=0.0, c_wmo_ws=0.5, c_wmo_oc=0.4, c_wmo_so=0.1, isurf=0, rho=0.1),
     "user_angle_files": dict(user_angles=[5.0, 20.5, 60.0], user_mie_angles=[10.0, 75.0]),
     "aerosol_and_surface_files_of_the_user": dict(from_files=True, wa_simu=0.55),
     "gas_mode1_lambert": dict(isurf=0, rho=0.2, gas=1),
