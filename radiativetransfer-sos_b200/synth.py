@@ -156,15 +156,14 @@ def profile(tau_ray, h_ray, tau_aer, h_aer, tau_gas=0.0, h_gas=2.0, z_toa=120.0)
     nt = h.size - 1
     z = np.zeros(nt + 1)
     z[0] = z_toa
-    for i in range(1, nt):
-        lo, hi = 0.0, z_toa                      # t_of_z decreasing in z
+    if nt > 1:                                   # all levels bisect at once (t_of_z decreasing in z); same arithmetic per level
+        lo, hi = np.zeros(nt - 1), np.full(nt - 1, z_toa)
         for _ in range(80):
             mid = 0.5 * (lo + hi)
-            if t_of_z(mid) > h[i]:
-                lo = mid
-            else:
-                hi = mid
-        z[i] = 0.5 * (lo + hi)
+            above = t_of_z(mid) > h[1:nt]
+            lo = np.where(above, mid, lo)
+            hi = np.where(above, hi, mid)
+        z[1:nt] = 0.5 * (lo + hi)
     z[nt] = 0.0
     tr = tau_ray * np.exp(-z / h_ray)
     ta = tau_aer * np.exp(-z / h_aer)
